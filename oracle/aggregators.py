@@ -1,0 +1,120 @@
+"""TEST INFRASTRUCTURE ONLY -- NumPy restatement of the reference aggregators.
+
+The reference evaluates these with TensorFlow-1.x ops that are not in /root/reference
+(tf.sparse_tensor_dense_matmul, tf.gather, tf.scatter_update, tf.concat); TensorFlow is not
+installed here, and the reference holds no test or golden vector at this boundary, so this part
+of the oracle is **parity unpinned**: it follows the reference's formulas line by line
+(citations below) but cannot be checked against reference outputs.
+
+Each function takes the feed-dict pieces exactly as ``PyScheduler.batch`` produces them
+(COO triples ``(idx[ne,2], val[ne], shape)``, int32 fields, float32 scales) and a ``dtype``:
+``np.float64`` gives the high-precision reference value the 1e-4-relative parity bound is
+measured against; ``np.float32`` mirrors the TF CPU kernel's fp32 storage-order accumulation
+(via oracle/sgcn_oracle.c) and is what the CPU baseline times.
+"""
+import numpy as np
+
+from . import native
+
+
+def _coo_matmul(adj, x, dtype):
+    """dot(adj, x, sparse=True), gcn/layers.py:31-37."""
+    idx, val, shape = adj
+    idx = np.asarray(idx).reshape(-1, 2)
+    if dtype == np.float32:
+        return native.spmm_coo(idx, val, shape, x)
+    y = np.zeros((int(shape[0]), x.shape[1]), dtype=np.float64)
+    np.add.at(y, idx[:, 0], np.asarray(val, np.float64)[:, None] * x.astype(np.float64)[idx[:, 1]])
+    return y
+
+
+def _coo_matmul_t(adj, dy, dtype):
+    """gradient of dot(adj, x) w.r.t. x (TF autodiff, gcn/models.py:187): adj^T dy."""
+    idx, val, shape = adj
+    idx = np.asarray(idx).reshape(-1, 2)
+    if dtype == np.float32:
+        return native.spmm_coo_t(idx, val, shape, dy)
+    dx = np.zeros((int(shape[1]), dy.shape[1]), dtype=np.float64)
+    np.add.at(dx, idx[:, 1], np.asarray(val, np.float64)[:, None] * dy.astype(np.float64)[idx[:, 0]])
+    return dx
+
+
+def plain_forward(adj, inputs, graphsage, dtype=np.float64):
+    """PlainAggregator._call, non-tuple branch, gcn/layers.py:249-257."""
+    n_out = int(adj[2][0])
+    a_self = inputs[:n_out].astype(dtype)
+    a_nb = _coo_matmul(adj, inputs, dtype)
+    return np.concatenate((a_self, a_nb), axis=1) if graphsage else a_nb
+
+
+def plain_backward(adj, d_out, n_in, graphsage, dtype=np.float64):
+    """d(inputs) for plain_forward: adj^T d(a_neighbour) (+ d(a_self) on the first n_out rows)."""
+    n_out = int(adj[2][0])
+    d_out = d_out.astype(dtype)
+    if graphsage:
+        dim = d_out.shape[1] // 2
+        d_self, d_nb = d_out[:, :dim], d_out[:, dim:]
+    else:
+        d_self, d_nb = None, d_out
+    dx = _coo_matmul_t((adj[0], adj[1], (n_out, n_in)), d_nb, dtype)
+    if d_self is not None:
+        dx[:n_out] += d_self
+    return dx
+
+
+def cv_forward(adj, fadj, ifield, ffield, history, inputs, graphsage, dtype=np.float64):
+    """VRAggregator._call, CV branch, gcn/layers.py:350-362.
+
+    a_neighbour = adj@inputs - adj@history[ifield] + fadj@history[ffield]; new_history=[inputs].
+    """
+    n_out = int(adj[2][0])
+    a_self = inputs[:n_out].astype(dtype)
+    cur = _coo_matmul(adj, inputs, dtype)
+    old = _coo_matmul(adj, history[ifield], dtype)
+    mean = _coo_matmul(fadj, history[ffield], dtype)
+    a_nb = cur - old + mean
+    out = np.concatenate((a_self, a_nb), axis=1) if graphsage else a_nb
+    return out, [inputs]
+
+
+def cvd_forward(adj, fadj, ifield, ffield, history, scale, h, mu, graphsage, dtype=np.float64):
+    """VRAggregator._call, CVD branch, gcn/layers.py:298-319.
+
+    mu_nb = adj@(mu - history[ifield]) + fadj@history[ffield]
+    h_nb  = (adj@(h - mu)) * scale[:,None] + mu_nb ; new_history=[mu]
+    """
+    n_out = int(adj[2][0])
+    h_self, mu_self = h[:n_out].astype(dtype), mu[:n_out].astype(dtype)
+    mu_small = history[ifield].astype(dtype)
+    mu_large = history[ffield].astype(dtype)
+    z = h.astype(dtype) - mu.astype(dtype)
+    delta_mu = mu.astype(dtype) - mu_small
+    mu_mean = _coo_matmul(fadj, mu_large, dtype)
+    mu_nb = _coo_matmul(adj, delta_mu, dtype) + mu_mean
+    h_nb = _coo_matmul(adj, z, dtype) * np.asarray(scale, dtype)[:, None] + mu_nb
+    if graphsage:
+        return (np.concatenate((h_self, h_nb), axis=1), np.concatenate((mu_self, mu_nb), axis=1)), [mu]
+    return (h_nb, mu_nb), [mu]
+
+
+def cvd_backward_h(adj, scale, d_h_out, n_in, graphsage, dtype=np.float64):
+    """d(h) for cvd_forward.  mu is stop_gradient-ed where it is produced (gcn/layers.py:412) and
+    history is non-trainable, so h is the only differentiable input: d(h) = adj^T (d(h_nb)*scale)
+    (+ d(h_self) on the first n_out rows)."""
+    n_out = int(adj[2][0])
+    d = d_h_out.astype(dtype)
+    if graphsage:
+        dim = d.shape[1] // 2
+        d_self, d_nb = d[:, :dim], d[:, dim:]
+    else:
+        d_self, d_nb = None, d
+    dx = _coo_matmul_t((adj[0], adj[1], (n_out, n_in)), d_nb * np.asarray(scale, dtype)[:, None], dtype)
+    if d_self is not None:
+        dx[:n_out] += d_self
+    return dx
+
+
+def history_update(history, ifield, new_rows):
+    """tf.scatter_update(history, fields[l], new_history), gcn/models.py:160-166 (in place)."""
+    history[np.asarray(ifield)] = new_rows
+    return history
