@@ -1,0 +1,214 @@
+/* sgcn_b200.h -- C ABI of libsgcn_b200.so: the B200 (sm_100a) implementation of the
+ * variance-reduced GCN training hot path of thu-ml/stochastic_gcn.
+ *
+ * This is the drop-in boundary.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference checkout, e.g. gcn/scheduler.h:6-28).  Signatures use plain
+ * pointers and sizes only (no torch / CUDA types): `stream` arguments are a cudaStream_t passed
+ * as void* (NULL = the legacy default stream).  Unless a parameter is marked HOST, every pointer
+ * is a DEVICE pointer into the HBM of the sampler's / caller's current device.
+ *
+ * All functions return 0 on success and a negative SGCN_E* code on failure; the message for the
+ * last failure on the calling thread is available from sgcn_last_error().
+ * There is NO CPU fallback anywhere in this library.
+ */
+#ifndef SGCN_B200_H
+#define SGCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGCN_OK 0
+#define SGCN_EINVAL (-1)   /* bad argument */
+#define SGCN_ECUDA (-2)    /* CUDA runtime error (message has the CUDA string) */
+#define SGCN_ESTATE (-3)   /* call out of order (e.g. expand before start_batch) */
+#define SGCN_EDATA (-4)    /* data-dependent failure reported by a kernel (duplicate batch ids,
+                              capacity overflow, NaN edge weight = the reference's
+                              runtime_error("nan"), empty neighbour pool = "Prob is empty") */
+
+int sgcn_abi_version(void);
+const char* sgcn_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t sgcn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Neighbour sampler.  Replaces `class Scheduler` (gcn/scheduler.h:6-28, gcn/scheduler.cpp:11-189)
+ * and `struct Mult` (gcn/mult.h:8-27) as bound by gcn/_scheduler.pyx:10-19.
+ *
+ * The sampler owns a private, mutable copy of the CSR adjacency in HBM (the reference deep-copies
+ * it too, scheduler.cpp:14-16): the uniform branch permutes row entries in place and that
+ * permutation, like the mt19937 state, persists across batches.  All outputs of expand() stay in
+ * HBM; nothing is copied to the host unless a *_copy_* accessor is called.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sgcn_sampler sgcn_sampler;
+
+/* Scheduler::Scheduler(adj_w, adj_i, adj_p, num_data, num_edges, L, cv, is)  scheduler.cpp:11-35.
+ * adj_w/adj_i/adj_p are HOST arrays (adj_p needs num_data entries; entry num_data is taken to be
+ * num_edges as the reference does).  `device` is the CUDA ordinal that will hold the state.
+ * `L` is the number of expand() levels kept alive per batch (results of the k-th expand after
+ * start_batch are addressed as level k). */
+int sgcn_sampler_create(sgcn_sampler** out, const float* adj_w, const int32_t* adj_i,
+                        const int32_t* adj_p, int32_t num_data, int32_t num_edges, int32_t L,
+                        int32_t cv, int32_t is, int32_t device);
+/* same, with adj_w/adj_i/adj_p already in the HBM of `device` (copied device-to-device: the sampler
+ * still owns a private mutable copy) */
+int sgcn_sampler_create_device(sgcn_sampler** out, const float* adj_w, const int32_t* adj_i,
+                               const int32_t* adj_p, int32_t num_data, int32_t num_edges,
+                               int32_t L, int32_t cv, int32_t is, int32_t device);
+void sgcn_sampler_destroy(sgcn_sampler* s);
+
+/* Scheduler::seed  scheduler.cpp:37-39 (std::mt19937::seed) */
+int sgcn_sampler_seed(sgcn_sampler* s, int32_t seed);
+
+/* Pre-size every per-batch buffer for batches of up to max_batch ids expanded with degrees[0..L)
+ * (degrees[k] = degree of the k-th expand call).  Optional: expand() grows buffers on demand, but
+ * growing cannot happen inside CUDA-graph capture.  materialize_full != 0 also sizes the
+ * reference-format full-neighbour outputs (ffield / fedg_*). */
+int sgcn_sampler_reserve(sgcn_sampler* s, int32_t max_batch, const int32_t* degrees /*HOST*/,
+                         int32_t n_degrees, int32_t materialize_full);
+
+/* Scheduler::start_batch  scheduler.cpp:41-44.  ids must be distinct node ids. */
+int sgcn_sampler_start_batch(sgcn_sampler* s, int32_t n, const int32_t* ids /*HOST*/);
+int sgcn_sampler_start_batch_device(sgcn_sampler* s, int32_t n, const int32_t* ids /*DEVICE*/);
+
+/* Scheduler::expand(degree)  scheduler.cpp:46-189 (uniform / CV branch 125-180, importance branch
+ * 63-123).  Asynchronous on the sampler's stream.  materialize_full selects whether the
+ * reference-format full-neighbour COO (fedg_s/fedg_t/fedg_w + ffield) is written (cv only); the
+ * fused aggregate kernels below do not need it -- they read the rows in place. */
+int sgcn_sampler_expand(sgcn_sampler* s, int32_t degree, int32_t materialize_full);
+
+/* sizes of level `level` (-1 = most recent expand): blocks until the level is complete.
+ * out[0]=n_out |field before|, out[1]=n_in |field after|, out[2]=nnz_s sampled edges,
+ * out[3]=nnz_f full-neighbour edges (cv), out[4]=n_ff |ffield| (cv, materialized), out[5]=status */
+int sgcn_sampler_sizes(sgcn_sampler* s, int32_t level, int32_t out[6] /*HOST*/);
+
+/* Device views of the reference's public vectors (scheduler.h:17-27) for one level.  *ptr is a
+ * device pointer owned by the sampler, valid until the next start_batch; *len is the capacity
+ * bound -- the exact length is in sgcn_sampler_sizes / the device meta block. */
+enum {
+    SGCN_VEC_FIELD = 0,    /* int32  field after expand (old field is its prefix)   [n_in]  */
+    SGCN_VEC_FFIELD = 1,   /* int32  ffield                                          [n_ff]  */
+    SGCN_VEC_EDG_S = 2,    /* int32  sampled edge row (index into old field)          [nnz_s] */
+    SGCN_VEC_EDG_T = 3,    /* int32  sampled edge col (index into new field)          [nnz_s] */
+    SGCN_VEC_FEDG_S = 4,   /* int32                                                   [nnz_f] */
+    SGCN_VEC_FEDG_T = 5,   /* int32                                                   [nnz_f] */
+    SGCN_VEC_ADJ_I = 6,    /* int32  the sampler's (permuted) CSR column ids          [E]     */
+    SGCN_VEC_ADJ_P = 7,    /* int32  CSR row pointers                                 [N+1]   */
+    SGCN_VEC_ROWPTR_S = 10,/* int32  CSR row pointers of the sampled adjacency        [n_out+1] */
+    SGCN_VEC_ROWPTR_F = 11,/* int32  CSR row pointers of the full-neighbour adjacency [n_out+1] */
+    SGCN_VEC_TGT = 12,     /* int32  sampled edge col as GLOBAL node id               [nnz_s] */
+    SGCN_VEC_META = 13,    /* int32  device copy of the 6 sizes of sgcn_sampler_sizes [6]     */
+    SGCN_VEC_SCALES = 100, /* float  scales                                           [n_out] */
+    SGCN_VEC_EDG_W = 101,  /* float                                                   [nnz_s] */
+    SGCN_VEC_MEDG_W = 102, /* float                                                   [nnz_s] */
+    SGCN_VEC_FEDG_W = 103, /* float                                                   [nnz_f] */
+    SGCN_VEC_ADJ_W = 104,  /* float  the sampler's (permuted) CSR values              [E]     */
+    SGCN_VEC_IMPORTANCE = 105 /* float importance                                     [N]     */
+};
+int sgcn_sampler_vec(sgcn_sampler* s, int32_t level, int32_t which, void** ptr /*HOST out*/,
+                     int64_t* len /*HOST out*/);
+/* copy the first `count` elements (4 bytes each) of a vector to HOST memory (synchronises) */
+int sgcn_sampler_copy_vec(sgcn_sampler* s, int32_t level, int32_t which, void* dst /*HOST*/,
+                          int64_t count);
+/* the stream expand() runs on (cudaStream_t as void*); set to share the caller's stream */
+int sgcn_sampler_set_stream(sgcn_sampler* s, void* stream);
+/* std::mt19937 state (624 words) + cursor, for checkpointing (absent in the reference) */
+int sgcn_sampler_get_rng(sgcn_sampler* s, uint32_t state[624] /*HOST*/, int32_t* pos /*HOST*/);
+int sgcn_sampler_set_rng(sgcn_sampler* s, const uint32_t state[624] /*HOST*/, int32_t pos);
+
+/* ------------------------------------------------------------------------------------------
+ * Row slicers.  Replace c_indptr / c_slice / c_dense_slice (gcn/history.h:6-9,
+ * gcn/history.cpp:50-88) as bound by gcn/_history.pyx:25-62.
+ * n_dev: optional device pointer to the row count (data-dependent sizes without a host
+ * round-trip); when NULL the host value n is used, otherwise n is the launch bound.
+ * ------------------------------------------------------------------------------------------ */
+/* c_dense_slice: dst[i, 0:C] = src[idx[i], 0:C];  ld_* are row strides in elements */
+int sgcn_gather_rows(const float* src, int64_t ld_src, const int32_t* idx, int32_t n,
+                     const int32_t* n_dev, int32_t C, float* dst, int64_t ld_dst, void* stream);
+/* c_indptr: o_p[i] = sum_{j<i} (a_p[r[j]+1]-a_p[r[j]]), o_p[n] = nnz */
+int sgcn_csr_slice_indptr(const int32_t* a_p, const int32_t* r, int32_t n, int32_t* o_p,
+                          void* stream);
+/* c_slice: values + (local row, column) index pairs, rows in the order of r */
+int sgcn_csr_slice(const float* a_d, const int32_t* a_i, const int32_t* a_p, const int32_t* r,
+                   int32_t n, const int32_t* o_p, float* o_d, int32_t* o_i2, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Aggregation.  Replaces the TensorFlow ops the reference's aggregators call:
+ * tf.sparse_tensor_dense_matmul (gcn/layers.py:31-37), tf.gather (layers.py:304-305,354-355),
+ * tf.concat of the self rows (layers.py:254-257,318-319,361-362), the implicit SpMM gradient
+ * (gcn/models.py:187) and tf.scatter_update (gcn/models.py:160-166).
+ *
+ * Sparse operands are row-sorted (CSR): rowptr[n_out+1], cols[nnz], vals[nnz] -- exactly what
+ * the sampler emits (edg_s ascending).  Dense operands are row-major fp32 with explicit row
+ * strides (ld, in elements) so that outputs can be written straight into one half of a
+ * concatenated [self | neighbour] buffer.
+ * ------------------------------------------------------------------------------------------ */
+
+/* y[r, :] (+)= sum_e vals[e] * x[map ? map[cols[e]] : cols[e], :]   for e in row r.
+ * accumulate=0 overwrites y, 1 adds into it.   PlainAggregator: layers.py:249-257. */
+int sgcn_spmm_csr(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                  const int32_t* map, int32_t n_out, const int32_t* n_out_dev, const float* x,
+                  int64_t ld_x, int32_t D, float* y, int64_t ld_y, int32_t accumulate,
+                  void* stream);
+
+/* General (unsorted) COO product with atomics: y[rows[e], :] += vals[e] * x[cols[e], :].
+ * idx2 is the reference's interleaved int32[nnz,2] index array (_scheduler.pyx:80-84). */
+int sgcn_spmm_coo(const int32_t* idx2, const float* vals, int32_t nnz, const float* x,
+                  int64_t ld_x, int32_t D, float* y, int64_t ld_y, int32_t transpose,
+                  void* stream);
+
+/* dx[cols[e], :] += vals[e] * (rscale ? rscale[r] : 1) * dy[r, :]  (SpMM backward, scatter-add).
+ * dx must be initialised by the caller (zeros, or the self-row gradient). */
+int sgcn_spmm_csr_bwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                      const float* rscale, int32_t n_out, const int32_t* n_out_dev,
+                      const float* dy, int64_t ld_dy, int32_t D, float* dx, int64_t ld_dx,
+                      void* stream);
+
+/* Full-neighbour history mean, edge-balanced:  for each output row r with node s = nodes[r]:
+ *   y0[r,:] += sum_{q in [adj_p[s], adj_p[s+1])} adj_w[q] * hist[adj_i[q], :]   (and y1 if given)
+ * = dot(fadj, gather(history, ffield)) of layers.py:305,309,354,357 without materialising
+ * ffield / fadj / the gathered rows.  rowptr_f[n_out+1] is the exclusive scan of the row
+ * lengths (SGCN_VEC_ROWPTR_F). */
+int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
+                           const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
+                           const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
+                           float* y0, int64_t ld_y0, float* y1, int64_t ld_y1, void* stream);
+
+/* VRAggregator CV branch, sampled part (layers.py:350-362):
+ *   y[r,:] = sum_e vals[e] * (x[cols[e],:] - hist[tgt[e],:])
+ *   self != NULL:  self[r,:] = x[r,:]   (the concat's left half, graphsage normalisation)
+ * The full-neighbour term is added by sgcn_full_history_mean. */
+int sgcn_cv_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                        const int32_t* tgt, int32_t n_out, const int32_t* n_out_dev,
+                        const float* x, int64_t ld_x, const float* hist, int64_t ld_h, int32_t D,
+                        float* y, int64_t ld_y, float* self, int64_t ld_self, void* stream);
+
+/* VRAggregator CVD branch, sampled part (layers.py:298-319):
+ *   ymu[r,:] = sum_e vals[e] * (mu[cols[e],:] - hist[tgt[e],:])
+ *   yh[r,:]  = (sum_e vals[e] * (h[cols[e],:] - mu[cols[e],:])) * scale[r] + ymu[r,:]
+ *   self_h / self_mu (optional): copies of the first n_out rows of h / mu. */
+int sgcn_cvd_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                         const int32_t* tgt, const float* scale, int32_t n_out,
+                         const int32_t* n_out_dev, const float* h, int64_t ld_hh,
+                         const float* mu, int64_t ld_mu, const float* hist, int64_t ld_h,
+                         int32_t D, float* yh, int64_t ld_yh, float* ymu, int64_t ld_ymu,
+                         float* self_h, int64_t ld_sh, float* self_mu, int64_t ld_sm,
+                         void* stream);
+
+/* tf.scatter_update(history, fields[l], new_history)  models.py:160-166:
+ *   hist[idx[i], :] = rows[i, :]   (idx distinct) */
+int sgcn_history_update(float* hist, int64_t ld_h, const int32_t* idx, int32_t n,
+                        const int32_t* n_dev, const float* rows, int64_t ld_rows, int32_t D,
+                        void* stream);
+
+/* dst[i, :] = src[i, :] for i < n (strided 2-D copy; self-row gradient / concat halves) and
+ * dst[i, :] = 0 for n <= i < n_total */
+int sgcn_copy_rows_pad(const float* src, int64_t ld_src, int32_t n, const int32_t* n_dev,
+                       int32_t n_total, int32_t D, float* dst, int64_t ld_dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGCN_B200_H */

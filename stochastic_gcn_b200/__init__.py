@@ -1,0 +1,18 @@
+"""stochastic_gcn_b200 -- B200-native (sm_100a) hot path of thu-ml/stochastic_gcn.
+
+Neighbour sampler, sampled / full-neighbour aggregation (SpMM forward + backward) and the
+control-variate history gather / write-back as hand-written CUDA kernels behind a C ABI
+(include/sgcn_b200.h, stochastic_gcn_b200/libsgcn_b200.so), with Python mirrors of the reference's
+operator surfaces:
+
+  scheduler.PyScheduler              <- gcn/_scheduler.pyx   (ext module `scheduler`)
+  history.slice / dense_slice        <- gcn/_history.pyx     (ext module `history`)
+  layers.PlainAggregator/VRAggregator <- gcn/layers.py:214-362
+
+There is no CPU implementation in this package: every entry point raises if the CUDA library is
+missing or a kernel launch fails.
+"""
+from . import _lib  # noqa: F401
+
+__all__ = ["_lib", "ops", "sampler", "scheduler", "history", "layers", "graphs", "step", "sharding"]
+__version__ = "0.1.0"

@@ -1,0 +1,112 @@
+"""ctypes binding of libsgcn_b200.so (the C ABI declared in include/sgcn_b200.h).
+
+There is no CPU fallback: if the library is missing and cannot be built, or a call fails, this
+module raises.  PyTorch is used by callers only for device memory / streams; the library itself
+takes raw device pointers.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsgcn_b200.so")
+
+SGCN_OK, SGCN_EINVAL, SGCN_ECUDA, SGCN_ESTATE, SGCN_EDATA = 0, -1, -2, -3, -4
+
+# vector ids of sgcn_sampler_vec (include/sgcn_b200.h)
+VEC_FIELD, VEC_FFIELD, VEC_EDG_S, VEC_EDG_T, VEC_FEDG_S, VEC_FEDG_T = 0, 1, 2, 3, 4, 5
+VEC_ADJ_I, VEC_ADJ_P, VEC_ROWPTR_S, VEC_ROWPTR_F, VEC_TGT, VEC_META = 6, 7, 10, 11, 12, 13
+VEC_SCALES, VEC_EDG_W, VEC_MEDG_W, VEC_FEDG_W, VEC_ADJ_W, VEC_IMPORTANCE = 100, 101, 102, 103, 104, 105
+FLOAT_VECS = {VEC_SCALES, VEC_EDG_W, VEC_MEDG_W, VEC_FEDG_W, VEC_ADJ_W, VEC_IMPORTANCE}
+
+
+class SgcnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libsgcn_b200: %s (code %d)" % (msg, code))
+        self.code = code
+
+
+_vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
+
+# name -> (restype, argtypes); every symbol include/sgcn_b200.h declares
+SIGNATURES = {
+    "sgcn_abi_version": (_i32, []),
+    "sgcn_last_error": (C.c_char_p, []),
+    "sgcn_launch_count": (_i64, []),
+    "sgcn_sampler_create": (_i32, [C.POINTER(_vp), _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "sgcn_sampler_create_device": (_i32, [C.POINTER(_vp), _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "sgcn_sampler_destroy": (None, [_vp]),
+    "sgcn_sampler_seed": (_i32, [_vp, _i32]),
+    "sgcn_sampler_reserve": (_i32, [_vp, _i32, _vp, _i32, _i32]),
+    "sgcn_sampler_start_batch": (_i32, [_vp, _i32, _vp]),
+    "sgcn_sampler_start_batch_device": (_i32, [_vp, _i32, _vp]),
+    "sgcn_sampler_expand": (_i32, [_vp, _i32, _i32]),
+    "sgcn_sampler_sizes": (_i32, [_vp, _i32, _vp]),
+    "sgcn_sampler_vec": (_i32, [_vp, _i32, _i32, C.POINTER(_vp), C.POINTER(_i64)]),
+    "sgcn_sampler_copy_vec": (_i32, [_vp, _i32, _i32, _vp, _i64]),
+    "sgcn_sampler_set_stream": (_i32, [_vp, _vp]),
+    "sgcn_sampler_get_rng": (_i32, [_vp, _vp, C.POINTER(_i32)]),
+    "sgcn_sampler_set_rng": (_i32, [_vp, _vp, _i32]),
+    "sgcn_gather_rows": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _vp, _i64, _vp]),
+    "sgcn_csr_slice_indptr": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "sgcn_csr_slice": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "sgcn_spmm_csr": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp]),
+    "sgcn_spmm_coo": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _vp]),
+    "sgcn_spmm_csr_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "sgcn_full_history_mean": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,
+                                      _vp, _i64, _vp]),
+    "sgcn_cv_sampled_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i32, _vp,
+                                   _i64, _vp, _i64, _vp]),
+    "sgcn_cvd_sampled_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _vp,
+                                    _i64, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "sgcn_history_update": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _i32, _vp]),
+    "sgcn_copy_rows_pad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc is available).  Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build
+        build.build_library()
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().sgcn_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    if rc != SGCN_OK:
+        raise SgcnError(rc, last_error())
+
+
+def launch_count():
+    return int(load().sgcn_launch_count())
+
+
+def ptr(t):
+    """Raw address of a torch tensor / numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+def stream_ptr(stream=None):
+    """cudaStream_t of a torch stream (default: torch's current stream) as void*."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)

@@ -1,0 +1,500 @@
+// Aggregation kernels: sampled-adjacency SpMM forward (plain / CV / CVD), the edge-balanced
+// full-neighbour history mean, and the SpMM backward scatter-add.
+//
+// Mapping.  A dense row of D floats is covered by a GROUP of LPR lanes (8, 16 or 32), each lane
+// holding VPL 16-byte vectors, so one group load is one fully coalesced D*4-byte burst
+// (D=128 -> one warp, one 512 B row).  Sampled rows are short (<= degree), so the sampled kernels
+// are group-per-output-row.  The full-neighbour term is power-law skewed (mean 492, max ~22k
+// at Reddit shape), so it is EDGE-balanced: the concatenated neighbour list of the whole output
+// field is cut into fixed chunks, one warp per chunk, partial row sums are reduced in registers
+// and flushed with one 128-bit RED per lane at row / chunk boundaries.
+//
+// All kernels are HBM-bound (0.5 flop/B): no tensor cores here by design.
+#include "common.cuh"
+
+namespace sgcn {
+
+// ---- vector abstraction (float4 fast path, float fallback for odd widths / alignments) -------
+template <typename V> struct VT;
+template <> struct VT<float4> {
+    static constexpr int W = 4;
+    static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ float4 ld(const float* p) { return __ldg((const float4*)p); }
+    static __device__ __forceinline__ float4 ld_stream(const float* p) { return ldg_stream4(p); }
+    static __device__ __forceinline__ void st(float* p, float4 v) { *(float4*)p = v; }
+    static __device__ __forceinline__ void red(float* p, float4 v) { red_add4(p, v); }
+    static __device__ __forceinline__ void fma(float4& a, float w, float4 v) { fma4(a, w, v); }
+    static __device__ __forceinline__ float4 sub(float4 a, float4 b) {
+        return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    }
+    static __device__ __forceinline__ float4 add(float4 a, float4 b) {
+        return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+    static __device__ __forceinline__ float4 mul(float4 a, float s) {
+        return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
+    }
+    static __device__ __forceinline__ bool nonzero(float4 a) {
+        return a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f;
+    }
+};
+template <> struct VT<float> {
+    static constexpr int W = 1;
+    static __device__ __forceinline__ float zero() { return 0.f; }
+    static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ float ld_stream(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+    static __device__ __forceinline__ void red(float* p, float v) { atomicAdd(p, v); }
+    static __device__ __forceinline__ void fma(float& a, float w, float v) { a = fmaf(w, v, a); }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float mul(float a, float s) { return a * s; }
+    static __device__ __forceinline__ bool nonzero(float a) { return a != 0.f; }
+};
+
+constexpr int kAggThreads = 256;
+
+enum { MODE_PLAIN = 0, MODE_CV = 1, MODE_CVD = 2 };
+
+struct SampledArgs {
+    const int32_t* rowptr; const int32_t* cols; const float* vals;
+    const int32_t* map;      // PLAIN: optional row map of x;  CV/CVD: tgt (global ids into hist)
+    const float* scale;      // CVD
+    int n_out; const int32_t* n_out_dev;
+    const float* x; int64_t ld_x;      // PLAIN/CV: x ; CVD: h
+    const float* mu; int64_t ld_mu;    // CVD
+    const float* hist; int64_t ld_h;   // CV/CVD
+    int D;                             // width of this column tile, in floats
+    float* y; int64_t ld_y;            // PLAIN/CV: y ; CVD: yh
+    float* ymu; int64_t ld_ymu;        // CVD
+    float* self0; int64_t ld_s0;       // CV: copy of x[:n_out]; CVD: copy of h[:n_out]
+    float* self1; int64_t ld_s1;       // CVD: copy of mu[:n_out]
+    int accumulate;                    // PLAIN only
+};
+
+template <typename V, int LPR, int VPL, int MODE>
+__global__ void __launch_bounds__(kAggThreads)
+sampled_rows_kernel(const SampledArgs a) {
+    using T = VT<V>;
+    const int n_out = dev_count(a.n_out_dev, a.n_out);
+    const int gl = threadIdx.x % LPR;                      // lane within the group
+    const int groups = (gridDim.x * kAggThreads) / LPR;
+    int off[VPL];
+    bool ok[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        off[k] = (gl + k * LPR) * T::W;
+        ok[k] = off[k] < a.D;
+    }
+    for (int r = (blockIdx.x * kAggThreads + threadIdx.x) / LPR; r < n_out; r += groups) {
+        const int e0 = a.rowptr[r], e1 = a.rowptr[r + 1];
+        V acc[VPL], acc2[VPL];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) { acc[k] = T::zero(); acc2[k] = T::zero(); }
+#pragma unroll 2
+        for (int e = e0; e < e1; ++e) {
+            const int c = __ldg(a.cols + e);
+            const float w = __ldg(a.vals + e);
+            if (MODE == MODE_PLAIN) {
+                const int64_t src = a.map ? (int64_t)__ldg(a.map + c) : (int64_t)c;
+#pragma unroll
+                for (int k = 0; k < VPL; ++k)
+                    if (ok[k]) T::fma(acc[k], w, T::ld(a.x + src * a.ld_x + off[k]));
+            } else {
+                const int64_t t = __ldg(a.map + e);
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    if (!ok[k]) continue;
+                    const V hv = T::ld_stream(a.hist + t * a.ld_h + off[k]);
+                    if (MODE == MODE_CV) {
+                        const V xv = T::ld(a.x + (int64_t)c * a.ld_x + off[k]);
+                        T::fma(acc[k], w, T::sub(xv, hv));
+                    } else {
+                        const V hh = T::ld(a.x + (int64_t)c * a.ld_x + off[k]);
+                        const V mv = T::ld(a.mu + (int64_t)c * a.ld_mu + off[k]);
+                        T::fma(acc[k], w, T::sub(mv, hv));     // adj @ (mu - hist[ifield])
+                        T::fma(acc2[k], w, T::sub(hh, mv));    // adj @ (h - mu)
+                    }
+                }
+            }
+        }
+        const float sc = (MODE == MODE_CVD) ? a.scale[r] : 1.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            if (!ok[k]) continue;
+            if (MODE == MODE_PLAIN) {
+                float* yp = a.y + (int64_t)r * a.ld_y + off[k];
+                if (a.accumulate) acc[k] = T::add(acc[k], *(const V*)yp);
+                T::st(yp, acc[k]);
+            } else if (MODE == MODE_CV) {
+                T::st(a.y + (int64_t)r * a.ld_y + off[k], acc[k]);
+                if (a.self0) T::st(a.self0 + (int64_t)r * a.ld_s0 + off[k],
+                                   T::ld(a.x + (int64_t)r * a.ld_x + off[k]));
+            } else {
+                T::st(a.ymu + (int64_t)r * a.ld_ymu + off[k], acc[k]);
+                T::st(a.y + (int64_t)r * a.ld_y + off[k], T::add(T::mul(acc2[k], sc), acc[k]));
+                if (a.self0) T::st(a.self0 + (int64_t)r * a.ld_s0 + off[k],
+                                   T::ld(a.x + (int64_t)r * a.ld_x + off[k]));
+                if (a.self1) T::st(a.self1 + (int64_t)r * a.ld_s1 + off[k],
+                                   T::ld(a.mu + (int64_t)r * a.ld_mu + off[k]));
+            }
+        }
+    }
+}
+
+// ---- SpMM backward: dx[cols[e]] += vals[e] * rscale[r] * dy[r] --------------------------------
+struct BwdArgs {
+    const int32_t* rowptr; const int32_t* cols; const float* vals; const float* rscale;
+    int n_out; const int32_t* n_out_dev;
+    const float* dy; int64_t ld_dy; int D; float* dx; int64_t ld_dx;
+};
+
+template <typename V, int LPR, int VPL>
+__global__ void __launch_bounds__(kAggThreads)
+spmm_bwd_kernel(const BwdArgs a) {
+    using T = VT<V>;
+    const int n_out = dev_count(a.n_out_dev, a.n_out);
+    const int gl = threadIdx.x % LPR;
+    const int groups = (gridDim.x * kAggThreads) / LPR;
+    for (int r = (blockIdx.x * kAggThreads + threadIdx.x) / LPR; r < n_out; r += groups) {
+        const int e0 = a.rowptr[r], e1 = a.rowptr[r + 1];
+        if (e0 == e1) continue;
+        const float s = a.rscale ? a.rscale[r] : 1.f;
+        V g[VPL];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const int off = (gl + k * LPR) * T::W;
+            g[k] = off < a.D ? T::mul(T::ld(a.dy + (int64_t)r * a.ld_dy + off), s) : T::zero();
+        }
+        for (int e = e0; e < e1; ++e) {
+            const int64_t c = __ldg(a.cols + e);
+            const float w = __ldg(a.vals + e);
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                const int off = (gl + k * LPR) * T::W;
+                if (off < a.D) T::red(a.dx + c * a.ld_dx + off, T::mul(g[k], w));
+            }
+        }
+    }
+}
+
+// ---- unsorted COO product with atomics (reference-format adjacency triples) -------------------
+template <typename V, int LPR, int VPL>
+__global__ void __launch_bounds__(kAggThreads)
+spmm_coo_kernel(const int2* __restrict__ idx2, const float* __restrict__ vals, int nnz,
+                const float* __restrict__ x, int64_t ld_x, int D, float* __restrict__ y,
+                int64_t ld_y, int transpose) {
+    using T = VT<V>;
+    const int gl = threadIdx.x % LPR;
+    const int groups = (gridDim.x * kAggThreads) / LPR;
+    for (int e = (blockIdx.x * kAggThreads + threadIdx.x) / LPR; e < nnz; e += groups) {
+        const int2 rc = __ldg(idx2 + e);
+        const float w = __ldg(vals + e);
+        const int64_t r = transpose ? rc.y : rc.x;
+        const int64_t c = transpose ? rc.x : rc.y;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const int off = (gl + k * LPR) * T::W;
+            if (off < D) T::red(y + r * ld_y + off, T::mul(T::ld(x + c * ld_x + off), w));
+        }
+    }
+}
+
+// ---- edge-balanced full-neighbour history mean -------------------------------------------------
+// Position p of the concatenated neighbour list belongs to output row r = upper_bound(rowptr_f, p)-1
+// and is entry adj[adj_p[nodes[r]] + p - rowptr_f[r]] of the sampler's CSR.
+constexpr int kFullChunk = 64;   // edges per warp-chunk (multiple of 32)
+
+struct FullArgs {
+    const int32_t* nodes; const int32_t* rowptr_f; int n_out; const int32_t* n_out_dev;
+    const int32_t* adj_p; const int32_t* adj_i; const float* adj_w;
+    const float* hist; int64_t ld_h; int D;
+    float* y0; int64_t ld_y0; float* y1; int64_t ld_y1;
+};
+
+template <typename V, int LPR, int VPL>
+__device__ __forceinline__ void full_flush(const FullArgs& a, int row, int gl, V (&acc)[VPL]) {
+    using T = VT<V>;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int off = (gl + k * LPR) * T::W;
+        if (off < a.D && T::nonzero(acc[k])) {
+            T::red(a.y0 + (int64_t)row * a.ld_y0 + off, acc[k]);
+            if (a.y1) T::red(a.y1 + (int64_t)row * a.ld_y1 + off, acc[k]);
+        }
+        acc[k] = T::zero();
+    }
+}
+
+template <typename V, int LPR, int VPL>
+__global__ void __launch_bounds__(kAggThreads)
+full_mean_kernel(const FullArgs a) {
+    using T = VT<V>;
+    constexpr int G = 32 / LPR;           // groups per warp, each walks its own edges
+    constexpr int UN = (VPL >= 4) ? 2 : 4;   // row loads in flight per group
+    const int n_out = dev_count(a.n_out_dev, a.n_out);
+    if (n_out <= 0) return;
+    const int nnz = a.rowptr_f[n_out];
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LPR, g = lane / LPR;
+    const int warp = (blockIdx.x * kAggThreads + threadIdx.x) >> 5;
+    const int warps = (gridDim.x * kAggThreads) >> 5;
+
+    for (int p0 = warp * kFullChunk; p0 < nnz; p0 += warps * kFullChunk) {
+        const int p1 = min(p0 + kFullChunk, nnz);
+        V acc[VPL];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) acc[k] = T::zero();
+        int cur = -1;                                          // row the group is accumulating
+        for (int pb = p0; pb < p1; pb += 32) {
+            // lane-parallel metadata for 32 consecutive positions
+            const int p = pb + lane;
+            int r = -1, c = 0;
+            float w = 0.f;
+            if (p < p1) {
+                int lo = 0, hi = n_out;                        // last r with rowptr_f[r] <= p
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__ldg(a.rowptr_f + mid) <= p) lo = mid; else hi = mid;
+                }
+                r = lo;
+                const int q = __ldg(a.adj_p + __ldg(a.nodes + r)) + (p - __ldg(a.rowptr_f + r));
+                c = __ldg(a.adj_i + q);
+                w = __ldg(a.adj_w + q);
+            }
+            const int cnt = min(32, p1 - pb);
+            // group g takes positions g, g+G, g+2G, ... ; UN of them in flight
+            for (int j0 = 0; j0 < cnt; j0 += G * UN) {
+                V v[UN][VPL];
+                int rj[UN];
+                float wj[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int j = j0 + u * G + g;
+                    const int jj = min(j, 31);
+                    const int cj = __shfl_sync(0xffffffffu, c, jj);
+                    wj[u] = __shfl_sync(0xffffffffu, w, jj);
+                    rj[u] = __shfl_sync(0xffffffffu, r, jj);
+                    if (j >= cnt) rj[u] = -1;
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) {
+                        const int off = (gl + k * LPR) * T::W;
+                        v[u][k] = (rj[u] >= 0 && off < a.D)
+                                      ? T::ld_stream(a.hist + (int64_t)cj * a.ld_h + off)
+                                      : T::zero();
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    if (rj[u] < 0) continue;
+                    if (rj[u] != cur) {
+                        if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
+                        cur = rj[u];
+                    }
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) T::fma(acc[k], wj[u], v[u][k]);
+                }
+            }
+        }
+        if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
+    }
+}
+
+// ---- dispatch -----------------------------------------------------------------------------------
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+struct Shape { bool vec; int lpr, vpl, tile; };
+
+// pick the lane mapping for a row of D floats; tile = floats covered per launch
+static Shape pick_shape(int D, bool vec_ok) {
+    if (!vec_ok) return {false, 32, 8, 256};
+    const int d4 = D / 4;
+    if (d4 <= 8) return {true, 8, 1, 32};
+    if (d4 <= 16) return {true, 16, 1, 64};
+    if (d4 <= 32) return {true, 32, 1, 128};
+    if (d4 <= 64) return {true, 32, 2, 256};
+    if (d4 <= 128) return {true, 32, 4, 512};
+    return {true, 32, 8, 1024};
+}
+
+#define SGCN_DISPATCH_SHAPE(shape, CALL)                                         \
+    do {                                                                         \
+        if (!(shape).vec) { CALL(float, 32, 8); }                                \
+        else if ((shape).lpr == 8) { CALL(float4, 8, 1); }                       \
+        else if ((shape).lpr == 16) { CALL(float4, 16, 1); }                     \
+        else if ((shape).vpl == 1) { CALL(float4, 32, 1); }                      \
+        else if ((shape).vpl == 2) { CALL(float4, 32, 2); }                      \
+        else if ((shape).vpl == 4) { CALL(float4, 32, 4); }                      \
+        else { CALL(float4, 32, 8); }                                            \
+    } while (0)
+
+static int grid_for_groups(int64_t n_groups, int lpr) {
+    const int per_block = kAggThreads / lpr;
+    int64_t blocks = (n_groups + per_block - 1) / per_block;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, kNumSMs * 8));
+}
+
+template <int MODE>
+static int launch_sampled(SampledArgs a, int D, bool vec_ok, cudaStream_t st) {
+    if (a.n_out <= 0 || D <= 0) return SGCN_OK;
+    const Shape sh = pick_shape(D, vec_ok);
+    for (int c0 = 0; c0 < D; c0 += sh.tile) {
+        SampledArgs t = a;
+        t.D = std::min(sh.tile, D - c0);
+        t.x = a.x + c0;
+        if (a.mu) t.mu = a.mu + c0;
+        if (a.hist) t.hist = a.hist + c0;
+        t.y = a.y + c0;
+        if (a.ymu) t.ymu = a.ymu + c0;
+        if (a.self0) t.self0 = a.self0 + c0;
+        if (a.self1) t.self1 = a.self1 + c0;
+        const int grid = grid_for_groups(a.n_out, sh.lpr);
+#define CALL(V, L, P) sampled_rows_kernel<V, L, P, MODE><<<grid, kAggThreads, 0, st>>>(t)
+        SGCN_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+        SGCN_LAUNCHED();
+    }
+    return SGCN_OK;
+}
+
+}  // namespace sgcn
+
+using namespace sgcn;
+
+extern "C" {
+
+int sgcn_spmm_csr(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                  const int32_t* map, int32_t n_out, const int32_t* n_out_dev, const float* x,
+                  int64_t ld_x, int32_t D, float* y, int64_t ld_y, int32_t accumulate,
+                  void* stream) {
+    SGCN_REQUIRE(n_out >= 0 && D >= 0, "spmm_csr: negative size");
+    if (n_out == 0 || D == 0) return SGCN_OK;
+    SGCN_REQUIRE(rowptr && y, "spmm_csr: null pointer");
+    SGCN_REQUIRE(ld_y >= D && ld_x >= D, "spmm_csr: row stride smaller than width");
+    SampledArgs a{};
+    a.rowptr = rowptr; a.cols = cols; a.vals = vals; a.map = map;
+    a.n_out = n_out; a.n_out_dev = n_out_dev; a.x = x; a.ld_x = ld_x;
+    a.y = y; a.ld_y = ld_y; a.accumulate = accumulate;
+    const bool vec_ok = D % 4 == 0 && ld_x % 4 == 0 && ld_y % 4 == 0 && aligned16(x) && aligned16(y);
+    return launch_sampled<MODE_PLAIN>(a, D, vec_ok, (cudaStream_t)stream);
+}
+
+int sgcn_cv_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                        const int32_t* tgt, int32_t n_out, const int32_t* n_out_dev,
+                        const float* x, int64_t ld_x, const float* hist, int64_t ld_h, int32_t D,
+                        float* y, int64_t ld_y, float* self, int64_t ld_self, void* stream) {
+    SGCN_REQUIRE(n_out >= 0 && D >= 0, "cv_sampled_fwd: negative size");
+    if (n_out == 0 || D == 0) return SGCN_OK;
+    SGCN_REQUIRE(rowptr && x && hist && y, "cv_sampled_fwd: null pointer");
+    SGCN_REQUIRE(ld_x >= D && ld_h >= D && ld_y >= D && (!self || ld_self >= D),
+                 "cv_sampled_fwd: row stride smaller than width");
+    SampledArgs a{};
+    a.rowptr = rowptr; a.cols = cols; a.vals = vals; a.map = tgt;
+    a.n_out = n_out; a.n_out_dev = n_out_dev; a.x = x; a.ld_x = ld_x; a.hist = hist; a.ld_h = ld_h;
+    a.y = y; a.ld_y = ld_y; a.self0 = self; a.ld_s0 = ld_self;
+    const bool vec_ok = D % 4 == 0 && ld_x % 4 == 0 && ld_h % 4 == 0 && ld_y % 4 == 0 &&
+                        aligned16(x) && aligned16(hist) && aligned16(y) &&
+                        (!self || (ld_self % 4 == 0 && aligned16(self)));
+    return launch_sampled<MODE_CV>(a, D, vec_ok, (cudaStream_t)stream);
+}
+
+int sgcn_cvd_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                         const int32_t* tgt, const float* scale, int32_t n_out,
+                         const int32_t* n_out_dev, const float* h, int64_t ld_hh,
+                         const float* mu, int64_t ld_mu, const float* hist, int64_t ld_h,
+                         int32_t D, float* yh, int64_t ld_yh, float* ymu, int64_t ld_ymu,
+                         float* self_h, int64_t ld_sh, float* self_mu, int64_t ld_sm,
+                         void* stream) {
+    SGCN_REQUIRE(n_out >= 0 && D >= 0, "cvd_sampled_fwd: negative size");
+    if (n_out == 0 || D == 0) return SGCN_OK;
+    SGCN_REQUIRE(rowptr && scale && h && mu && hist && yh && ymu, "cvd_sampled_fwd: null pointer");
+    SGCN_REQUIRE(ld_hh >= D && ld_mu >= D && ld_h >= D && ld_yh >= D && ld_ymu >= D &&
+                     (!self_h || ld_sh >= D) && (!self_mu || ld_sm >= D),
+                 "cvd_sampled_fwd: row stride smaller than width");
+    SampledArgs a{};
+    a.rowptr = rowptr; a.cols = cols; a.vals = vals; a.map = tgt; a.scale = scale;
+    a.n_out = n_out; a.n_out_dev = n_out_dev; a.x = h; a.ld_x = ld_hh; a.mu = mu; a.ld_mu = ld_mu;
+    a.hist = hist; a.ld_h = ld_h; a.y = yh; a.ld_y = ld_yh; a.ymu = ymu; a.ld_ymu = ld_ymu;
+    a.self0 = self_h; a.ld_s0 = ld_sh; a.self1 = self_mu; a.ld_s1 = ld_sm;
+    const bool vec_ok = D % 4 == 0 && ld_hh % 4 == 0 && ld_mu % 4 == 0 && ld_h % 4 == 0 &&
+                        ld_yh % 4 == 0 && ld_ymu % 4 == 0 && aligned16(h) && aligned16(mu) &&
+                        aligned16(hist) && aligned16(yh) && aligned16(ymu) &&
+                        (!self_h || (ld_sh % 4 == 0 && aligned16(self_h))) &&
+                        (!self_mu || (ld_sm % 4 == 0 && aligned16(self_mu)));
+    return launch_sampled<MODE_CVD>(a, D, vec_ok, (cudaStream_t)stream);
+}
+
+int sgcn_spmm_csr_bwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                      const float* rscale, int32_t n_out, const int32_t* n_out_dev,
+                      const float* dy, int64_t ld_dy, int32_t D, float* dx, int64_t ld_dx,
+                      void* stream) {
+    SGCN_REQUIRE(n_out >= 0 && D >= 0, "spmm_csr_bwd: negative size");
+    if (n_out == 0 || D == 0) return SGCN_OK;
+    SGCN_REQUIRE(rowptr && dy && dx, "spmm_csr_bwd: null pointer");
+    SGCN_REQUIRE(ld_dy >= D && ld_dx >= D, "spmm_csr_bwd: row stride smaller than width");
+    const bool vec_ok = D % 4 == 0 && ld_dy % 4 == 0 && ld_dx % 4 == 0 && aligned16(dy) && aligned16(dx);
+    const Shape sh = pick_shape(D, vec_ok);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int c0 = 0; c0 < D; c0 += sh.tile) {
+        BwdArgs a{rowptr, cols, vals, rscale, n_out, n_out_dev, dy + c0, ld_dy,
+                  std::min(sh.tile, D - c0), dx + c0, ld_dx};
+        const int grid = grid_for_groups(n_out, sh.lpr);
+#define CALL(V, L, P) spmm_bwd_kernel<V, L, P><<<grid, kAggThreads, 0, st>>>(a)
+        SGCN_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+        SGCN_LAUNCHED();
+    }
+    return SGCN_OK;
+}
+
+int sgcn_spmm_coo(const int32_t* idx2, const float* vals, int32_t nnz, const float* x,
+                  int64_t ld_x, int32_t D, float* y, int64_t ld_y, int32_t transpose,
+                  void* stream) {
+    SGCN_REQUIRE(nnz >= 0 && D >= 0, "spmm_coo: negative size");
+    if (nnz == 0 || D == 0) return SGCN_OK;
+    SGCN_REQUIRE(idx2 && vals && x && y, "spmm_coo: null pointer");
+    SGCN_REQUIRE(((uintptr_t)idx2 & 7) == 0, "spmm_coo: idx2 must be 8-byte aligned");
+    SGCN_REQUIRE(ld_x >= D && ld_y >= D, "spmm_coo: row stride smaller than width");
+    const bool vec_ok = D % 4 == 0 && ld_x % 4 == 0 && ld_y % 4 == 0 && aligned16(x) && aligned16(y);
+    const Shape sh = pick_shape(D, vec_ok);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int c0 = 0; c0 < D; c0 += sh.tile) {
+        const int Dt = std::min(sh.tile, D - c0);
+        const int grid = grid_for_groups(nnz, sh.lpr);
+#define CALL(V, L, P)                                                                         \
+    spmm_coo_kernel<V, L, P><<<grid, kAggThreads, 0, st>>>((const int2*)idx2, vals, nnz, x + c0, \
+                                                           ld_x, Dt, y + c0, ld_y, transpose)
+        SGCN_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+        SGCN_LAUNCHED();
+    }
+    return SGCN_OK;
+}
+
+int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
+                           const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
+                           const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
+                           float* y0, int64_t ld_y0, float* y1, int64_t ld_y1, void* stream) {
+    SGCN_REQUIRE(n_out >= 0 && D >= 0, "full_history_mean: negative size");
+    if (n_out == 0 || D == 0) return SGCN_OK;
+    SGCN_REQUIRE(nodes && rowptr_f && adj_p && adj_i && adj_w && hist && y0,
+                 "full_history_mean: null pointer");
+    SGCN_REQUIRE(ld_h >= D && ld_y0 >= D && (!y1 || ld_y1 >= D),
+                 "full_history_mean: row stride smaller than width");
+    const bool vec_ok = D % 4 == 0 && ld_h % 4 == 0 && ld_y0 % 4 == 0 && aligned16(hist) &&
+                        aligned16(y0) && (!y1 || (ld_y1 % 4 == 0 && aligned16(y1)));
+    const Shape sh = pick_shape(D, vec_ok);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int c0 = 0; c0 < D; c0 += sh.tile) {
+        FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist + c0, ld_h,
+                   std::min(sh.tile, D - c0), y0 + c0, ld_y0, y1 ? y1 + c0 : nullptr, ld_y1};
+        const int grid = kNumSMs * 4;    // persistent, edge-strided: 4736 warps
+#define CALL(V, L, P) full_mean_kernel<V, L, P><<<grid, kAggThreads, 0, st>>>(a)
+        SGCN_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+        SGCN_LAUNCHED();
+    }
+    return SGCN_OK;
+}
+
+}  // extern "C"

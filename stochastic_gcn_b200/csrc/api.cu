@@ -1,0 +1,21 @@
+// libsgcn_b200.so -- library-wide state: error string, launch counter, ABI version.
+#include "common.cuh"
+
+namespace sgcn {
+
+static thread_local std::string t_last_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string& msg) { t_last_error = msg; }
+
+}  // namespace sgcn
+
+extern "C" {
+
+int sgcn_abi_version(void) { return 1; }
+
+const char* sgcn_last_error(void) { return sgcn::t_last_error.c_str(); }
+
+int64_t sgcn_launch_count(void) { return sgcn::g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Shared helpers for libsgcn_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <string>
+
+#include "sgcn_b200.h"
+
+namespace sgcn {
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+void set_error(const std::string& msg);
+extern std::atomic<int64_t> g_launches;
+
+inline int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s failed at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+    set_error(buf);
+    return SGCN_ECUDA;
+}
+
+#define SGCN_CUDA(call)                                                           \
+    do {                                                                          \
+        cudaError_t e__ = (call);                                                 \
+        if (e__ != cudaSuccess) return ::sgcn::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// Counts the launch and checks the launch status (cheap: no sync).
+#define SGCN_LAUNCHED()                                                           \
+    do {                                                                          \
+        ::sgcn::g_launches.fetch_add(1, std::memory_order_relaxed);               \
+        cudaError_t e__ = cudaGetLastError();                                     \
+        if (e__ != cudaSuccess) return ::sgcn::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define SGCN_REQUIRE(cond, msg)                                                   \
+    do {                                                                          \
+        if (!(cond)) { ::sgcn::set_error(std::string("invalid argument: ") + (msg)); return SGCN_EINVAL; } \
+    } while (0)
+
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- device-side helpers -------------------------------------------------------------------
+
+// 128-bit read-only global load that does not allocate in L1 (rows are read once per kernel).
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// 128-bit vector reduction (sm_90+): one RED for 4 floats.
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+}
+
+__device__ __forceinline__ int dev_count(const int32_t* n_dev, int n_host) {
+    return n_dev ? min(*n_dev, n_host) : n_host;
+}
+
+}  // namespace sgcn

@@ -1,0 +1,1079 @@
+// Device-resident neighbour sampler: the B200 replacement of `class Scheduler`
+// (gcn/scheduler.h:6-28, gcn/scheduler.cpp:11-189) and `struct Mult` (gcn/mult.h, gcn/mult.cpp).
+//
+// The reference walks the field sequentially, consuming one mt19937 output per draw, permuting
+// the stored rows in place and numbering newly met nodes by first occurrence.  Here the same
+// result is produced by data-parallel passes whose only sequential element is the order encoded
+// in prefix sums:
+//   rows     per field row: degree, sample count, scale                    (row_setup_kernel)
+//   scan     sample-count / degree prefix sums = CSR row pointers + each draw's stream offset
+//   draws    the next nnz_s engine outputs, block-parallel MT19937          (mt_draw_kernel)
+//   shuffle  per row: the <= degree Fisher-Yates swaps (rows are disjoint), edge weights,
+//            atomicMin of the edge position into slot[target]               (fisher_yates_kernel)
+//   number   first-occurrence flags -> prefix sum = index in the grown field (scan + assign)
+// Everything stays in HBM; sizes are carried in a device meta block so that no pass needs a host
+// round-trip (buffers are sized from upper bounds: |field| <= n_out (1+degree), nnz_s <= n_out
+// degree).  Only the optional reference-format full-neighbour COO (ffield / fedg_*) and the
+// importance branch synchronise, because their sizes (sum of full degrees) have no useful bound.
+#include <vector>
+
+#include "common.cuh"
+#include "mt19937.cuh"
+#include "scan.cuh"
+
+namespace sgcn {
+
+constexpr int kUnseen = 0x7fffffff;
+constexpr int kExactSizingDegree = 32;   // above this, nnz_s is read back instead of bounded
+constexpr int kMetaInts = 8;
+enum { M_NOUT = 0, M_NIN = 1, M_NNZS = 2, M_NNZF = 3, M_NFF = 4, M_STATUS = 5, M_AUX = 6 };
+enum { ST_DUPLICATE = 1, ST_RANGE = 2, ST_NAN = 4, ST_EMPTY = 8, ST_OVERFLOW = 16 };
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return SGCN_OK;
+        size_t want = std::max(bytes, cap + cap / 2);
+        want = (want + 255) & ~size_t(255);
+        if (p) SGCN_CUDA(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        SGCN_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return SGCN_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+struct Level {
+    int n_out_bound = 0, n_in_bound = 0, s_bound = 0;
+    bool done = false, full_materialized = false;
+    DevBuf field, rowptr_s, rowptr_f, edg_s, edg_t, tgt, edg_w, medg_w, scales, meta;
+    DevBuf ffield, fedg_s, fedg_t, fedg_w;
+    void release() {
+        for (DevBuf* b : {&field, &rowptr_s, &rowptr_f, &edg_s, &edg_t, &tgt, &edg_w, &medg_w,
+                          &scales, &meta, &ffield, &fedg_s, &fedg_t, &fedg_w})
+            b->release();
+    }
+};
+
+}  // namespace sgcn
+
+using namespace sgcn;
+
+struct sgcn_sampler {
+    int device = 0;
+    int N = 0, E = 0, L = 1;
+    bool cv = false, is = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // private mutable CSR + per-node state
+    float* adj_w = nullptr;
+    int32_t* adj_i = nullptr;
+    int32_t* adj_p = nullptr;
+    int32_t* slot = nullptr;     // "visited"
+    int32_t* fslot = nullptr;    // "fvisited"
+    float* importance = nullptr;
+    uint32_t* engine = nullptr;  // kMtWords
+    uint32_t* engine_is = nullptr;
+    // batch
+    DevBuf batch_ids, batch_meta;
+    int batch_n = -1;
+    int cur = 0;                 // number of expands since start_batch
+    std::vector<Level> levels;
+    // scratch
+    DevBuf take, deg, draws, rank, tile_sums, pool_mass, tree, hits;
+    int32_t* host_meta = nullptr;   // pinned
+};
+
+namespace sgcn {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- single-CTA exclusive scan with a carry over tiles -------------------------------------------
+template <typename F>
+__device__ __forceinline__ int cta_exclusive_scan(int n, F load, int* __restrict__ out) {
+    int carry = 0;
+    for (int base = 0; base < n; base += kScanTile) {
+        const int b = base + threadIdx.x * kScanItems;
+        int v[kScanItems];
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            v[k] = (b + k < n) ? load(b + k) : 0;
+            sum += v[k];
+        }
+        int total;
+        int excl = block_exclusive_scan(sum, &total) + carry;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (b + k < n) out[b + k] = excl;
+            excl += v[k];
+        }
+        carry += total;
+    }
+    return carry;
+}
+
+__global__ void fill_int_kernel(int32_t* p, int64_t n, int32_t v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+__global__ void fill_float_kernel(float* p, int64_t n, float v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+// importance[c] = 1e-6 + sum_r w_rc^2 accumulated in CSR order (scheduler.cpp:22-25).  fp32 sums
+// are order dependent, so one thread walks the matrix: constructor-time only, importance branch only.
+__global__ void importance_kernel(const float* __restrict__ adj_w, const int32_t* __restrict__ adj_i,
+                                  int E, float* __restrict__ imp) {
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int e = 0; e < E; ++e) {
+            const float w = adj_w[e];
+            imp[adj_i[e]] += __fmul_rn(w, w);
+        }
+}
+
+// ---- pass 1: per-row degree / sample count / scale; old field becomes the prefix -----------------
+__global__ void __launch_bounds__(256)
+row_setup_kernel(const int32_t* __restrict__ field_in, const int32_t* __restrict__ n_ptr, int nb,
+                 const int32_t* __restrict__ adj_p, int N, int degree, int want_deg, int want_scales,
+                 int32_t* __restrict__ take, int32_t* __restrict__ deg_out,
+                 float* __restrict__ scales, int32_t* __restrict__ field_out,
+                 int32_t* __restrict__ slot, int32_t* __restrict__ meta) {
+    const int n_out = min(*n_ptr, nb);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {   // meta was zeroed by the memset that precedes this launch
+        meta[M_NOUT] = n_out;
+        if (*n_ptr > nb) atomicOr(meta + M_STATUS, ST_OVERFLOW);
+    }
+    if (i >= n_out) return;
+    const int node = field_in[i];
+    if (node < 0 || node >= N) {
+        atomicOr(meta + M_STATUS, ST_RANGE);
+        take[i] = 0;
+        deg_out[i] = 0;
+        field_out[i] = node;
+        if (want_scales) scales[i] = 1.f;
+        return;
+    }
+    const int d = adj_p[node + 1] - adj_p[node];
+    const int t = min(d, degree);
+    take[i] = t;
+    deg_out[i] = want_deg ? d : 0;
+    if (want_scales) {
+        // scale = (float)deg / take; scales = 1.0 / sqrt(scale) in double  (scheduler.cpp:132-134)
+        float scale = (d == 0) ? 1.f : __fdiv_rn((float)d, (float)t);
+        scales[i] = (float)(1.0 / (double)__fsqrt_rn(scale));
+    }
+    field_out[i] = node;
+    slot[node] = i;
+}
+
+// ---- pass 2: row pointers of the sampled and full-neighbour adjacencies --------------------------
+__global__ void __launch_bounds__(kScanThreads)
+scan_take_deg_kernel(const int32_t* __restrict__ take, const int32_t* __restrict__ deg,
+                     int32_t* __restrict__ rowptr_s, int32_t* __restrict__ rowptr_f,
+                     int32_t* __restrict__ meta) {
+    const int n = meta[M_NOUT];
+    const int tot_s = cta_exclusive_scan(n, [&](int i) { return take[i]; }, rowptr_s);
+    const int tot_f = cta_exclusive_scan(n, [&](int i) { return deg[i]; }, rowptr_f);
+    if (threadIdx.x == 0) {
+        rowptr_s[n] = tot_s;
+        rowptr_f[n] = tot_f;
+        meta[M_NNZS] = tot_s;
+        meta[M_NNZF] = tot_f;
+    }
+}
+
+// ---- pass 4: per-row partial Fisher-Yates on the stored row + edge emission ----------------------
+__global__ void __launch_bounds__(128)
+fisher_yates_kernel(const int32_t* __restrict__ field, const int32_t* __restrict__ meta,
+                    const int32_t* __restrict__ adj_p, int32_t* __restrict__ adj_i,
+                    float* __restrict__ adj_w, const int32_t* __restrict__ rowptr_s,
+                    const uint32_t* __restrict__ draws, int s_bound, int cv,
+                    int32_t* __restrict__ edg_s, int32_t* __restrict__ tgt,
+                    float* __restrict__ edg_w, float* __restrict__ medg_w,
+                    int32_t* __restrict__ slot, int32_t* __restrict__ status) {
+    const int n_out = meta[M_NOUT];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const int e0 = rowptr_s[i];
+    const int take = rowptr_s[i + 1] - e0;
+    if (take <= 0) return;
+    if (e0 + take > s_bound) {
+        atomicOr(status, ST_OVERFLOW);
+        return;
+    }
+    const int node = field[i];
+    const int base = adj_p[node];
+    const int d = adj_p[node + 1] - base;
+    int32_t* rc = adj_i + base;
+    float* rw = adj_w + base;
+    const float scale = __fdiv_rn((float)d, (float)take);
+    for (int k = 0; k < take; ++k) {
+        // idx = min((int)(it + num_remaining * u01(generator)), adj_range-1)  (scheduler.cpp:141-143)
+        const float u = mt_canonical(draws[e0 + k]);
+        const float where = __fadd_rn((float)k, __fmul_rn((float)(d - k), u));
+        int j = (int)where;
+        if (j > d - 1) j = d - 1;
+        const int ck = rc[k], cj = rc[j];
+        const float wk = rw[k], wj = rw[j];
+        rc[k] = cj; rc[j] = ck;
+        rw[k] = wj; rw[j] = wk;
+        const int t = (j == k) ? ck : cj;
+        const float wv = (j == k) ? wk : wj;
+        const float w = __fmul_rn(wv, scale);
+        const int e = e0 + k;
+        edg_s[e] = i;
+        tgt[e] = t;
+        edg_w[e] = w;
+        if (cv) medg_w[e] = __fmul_rn(wv, w);
+        if (slot[t] >= n_out) atomicMin(slot + t, n_out + e);
+    }
+}
+
+// ---- pass 5: first-occurrence flags -> rank in the grown field ------------------------------------
+__global__ void __launch_bounds__(kScanThreads)
+scan_first_kernel(const int32_t* __restrict__ tgt, const int32_t* __restrict__ slot, int s_bound,
+                  int32_t* __restrict__ rank, int32_t* __restrict__ meta) {
+    const int n_out = meta[M_NOUT];
+    const int nnz = min(meta[M_NNZS], s_bound);
+    const int n_new = cta_exclusive_scan(
+        nnz, [&](int e) { return slot[tgt[e]] == n_out + e ? 1 : 0; }, rank);
+    if (threadIdx.x == 0) meta[M_NIN] = n_out + n_new;
+}
+
+__global__ void __launch_bounds__(256)
+assign_kernel(const int32_t* __restrict__ tgt, const int32_t* __restrict__ slot,
+              const int32_t* __restrict__ rank, const int32_t* __restrict__ meta, int s_bound,
+              int32_t* __restrict__ edg_t, int32_t* __restrict__ field) {
+    const int n_out = meta[M_NOUT];
+    const int nnz = min(meta[M_NNZS], s_bound);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const int t = tgt[e];
+    const int s = slot[t];
+    if (s < n_out) {
+        edg_t[e] = s;
+    } else {
+        const int e_first = s - n_out;
+        const int pos = n_out + rank[e_first];
+        edg_t[e] = pos;
+        if (e_first == e) field[pos] = t;
+    }
+}
+
+// visited[s] = -1 for s in field (scheduler.cpp:183-184); also detects duplicate batch ids
+__global__ void __launch_bounds__(256)
+reset_slots_kernel(const int32_t* __restrict__ field, int32_t* __restrict__ meta, int n_in_bound,
+                   int N, int32_t* __restrict__ slot) {
+    const int n_out = meta[M_NOUT];
+    const int n_in = min(meta[M_NIN], n_in_bound);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_in) return;
+    const int node = field[j];
+    if (node < 0 || node >= N) return;   // range error already flagged by row_setup_kernel
+    if (j < n_out && slot[node] != j) atomicOr(meta + M_STATUS, ST_DUPLICATE);
+    slot[node] = kUnseen;
+}
+
+// ---- reference-format full-neighbour COO (cv) / neighbour pool (importance) ----------------------
+// position p of the concatenated rows -> (row r, target t, weight); atomicMin of p into fslot[t]
+__global__ void __launch_bounds__(256)
+full_expand_kernel(const int32_t* __restrict__ field, const int32_t* __restrict__ rowptr_f, int n_out,
+                   int nnz_f, const int32_t* __restrict__ adj_p, const int32_t* __restrict__ adj_i,
+                   const float* __restrict__ adj_w, int32_t* __restrict__ fedg_s,
+                   int32_t* __restrict__ fedg_t, float* __restrict__ fedg_w,
+                   int32_t* __restrict__ fslot) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz_f) return;
+    int lo = 0, hi = n_out;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (rowptr_f[mid] <= p) lo = mid; else hi = mid;
+    }
+    const int q = adj_p[field[lo]] + (p - rowptr_f[lo]);
+    const int t = adj_i[q];
+    fedg_s[p] = lo;
+    fedg_t[p] = t;          // global id for now; renumbered by full_assign_kernel
+    fedg_w[p] = adj_w[q];
+    atomicMin(fslot + t, p);
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_full_first_kernel(const int32_t* __restrict__ fedg_t, const int32_t* __restrict__ fslot,
+                       int nnz_f, int32_t* __restrict__ rank, int32_t* __restrict__ meta,
+                       int meta_slot) {
+    const int n = cta_exclusive_scan(
+        nnz_f, [&](int p) { return fslot[fedg_t[p]] == p ? 1 : 0; }, rank);
+    if (threadIdx.x == 0) meta[meta_slot] = n;
+}
+
+__global__ void __launch_bounds__(256)
+full_assign_kernel(int32_t* __restrict__ fedg_t, const int32_t* __restrict__ fslot,
+                   const int32_t* __restrict__ rank, int nnz_f, int32_t* __restrict__ ffield) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz_f) return;
+    const int t = fedg_t[p];
+    const int p_first = fslot[t];
+    const int pos = rank[p_first];
+    fedg_t[p] = pos;
+    if (p_first == p) ffield[pos] = t;
+}
+
+__global__ void __launch_bounds__(256)
+reset_list_kernel(const int32_t* __restrict__ list, const int32_t* __restrict__ n_ptr, int n_bound,
+                  int32_t* __restrict__ table) {
+    const int n = min(*n_ptr, n_bound);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) table[list[j]] = kUnseen;
+}
+
+// ---- importance branch (scheduler.cpp:63-123 + Mult) ----------------------------------------------
+// pool = distinct neighbours in first-seen order (= ffield of the un-permuted rows); mass[j] =
+// importance[pool[j]].  The Fenwick array is what Mult::Mult builds by n left-to-right Add()s
+// (mult.cpp:7-28): bit[k] is the in-order fp32 sum of prob over (k - lowbit(k), k].
+__global__ void __launch_bounds__(256)
+pool_mass_kernel(const int32_t* __restrict__ pool, int n_pool, const float* __restrict__ imp,
+                 float* __restrict__ mass) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_pool) mass[j] = imp[pool[j]];
+}
+
+__global__ void __launch_bounds__(256)
+fenwick_build_kernel(const float* __restrict__ mass, int n_pool, int cap, float* __restrict__ tree) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;   // 1-based node
+    if (k > cap) return;
+    const int lb = k & (-k);
+    float s = 0.f;
+    const int hi = min(k, n_pool);
+    for (int i = k - lb; i < hi; ++i) s = __fadd_rn(s, mass[i]);
+    tree[k] = s;
+    if (k == 1) tree[0] = 0.f;
+}
+
+// One thread replays the draws in order (each draw removes mass, so the sequence is inherently
+// serial): sum = running in-order total, Query() = descent + clamp + Add(-p) (mult.cpp:30-51).
+// New targets are numbered by first draw (scheduler.cpp:92-99).
+__global__ void importance_draw_kernel(const int32_t* __restrict__ pool, float* __restrict__ mass,
+                                       float* __restrict__ tree, int n_pool, int cap, int n_draw,
+                                       const uint32_t* __restrict__ draws,
+                                       int32_t* __restrict__ hits, int32_t* __restrict__ slot,
+                                       int32_t* __restrict__ field, int32_t* __restrict__ meta,
+                                       float* __restrict__ mass_total_out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    // sum_importance is accumulated in pool order (scheduler.cpp:74) and Mult::sum by the Adds in
+    // the same order (mult.cpp:27): identical sequences, one running sum serves both
+    float total = 0.f;
+    for (int j = 0; j < n_pool; ++j) total = __fadd_rn(total, mass[j]);
+    *mass_total_out = total;
+    float sum = total;
+    int n_in = meta[M_NOUT];
+    for (int d = 0; d < n_draw; ++d) {
+        float u = __fmul_rn(mt_canonical(draws[d]), sum);
+        int at = 0;
+        for (int span = cap; span > 0; span >>= 1) {
+            const int nxt = at + span;
+            if (nxt <= cap) {
+                const float tv = tree[nxt];
+                if (!(tv > u)) { u = __fsub_rn(u, tv); at = nxt; }
+            }
+        }
+        int r = at;
+        if (r > n_pool - 1) r = n_pool - 1;
+        const float delta = -mass[r];
+        for (int k = r + 1; k <= cap; k += k & (-k)) tree[k] = __fadd_rn(tree[k], delta);
+        sum = __fadd_rn(sum, delta);
+        mass[r] = 0.f;
+        const int t = pool[r];
+        hits[t] += 1;
+        if (slot[t] == kUnseen) {
+            slot[t] = n_in;
+            field[n_in] = t;
+            ++n_in;
+        }
+    }
+    meta[M_NIN] = n_in;
+}
+
+// per field row: how many stored entries point at a drawn target (warp per row)
+__global__ void __launch_bounds__(256)
+importance_count_kernel(const int32_t* __restrict__ field, int n_out,
+                        const int32_t* __restrict__ adj_p, const int32_t* __restrict__ adj_i,
+                        const int32_t* __restrict__ hits, int32_t* __restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_out; i += warps) {
+        const int node = field[i];
+        const int b = adj_p[node], e = adj_p[node + 1];
+        int c = 0;
+        for (int q = b + lane; q < e; q += 32) c += hits[adj_i[q]] > 0 ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) count[i] = c;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_counts_kernel(const int32_t* __restrict__ count, int n, int32_t* __restrict__ rowptr,
+                   int32_t* __restrict__ meta) {
+    const int tot = cta_exclusive_scan(n, [&](int i) { return count[i]; }, rowptr);
+    if (threadIdx.x == 0) {
+        rowptr[n] = tot;
+        meta[M_NNZS] = tot;
+    }
+}
+
+// w = times * w * sum_importance / (importance[t] * num_samples), evaluated left to right in fp32
+// (scheduler.cpp:108-113); NaN raises the reference's runtime_error("nan") -> status
+__global__ void __launch_bounds__(256)
+importance_emit_kernel(const int32_t* __restrict__ field, int n_out,
+                       const int32_t* __restrict__ adj_p, const int32_t* __restrict__ adj_i,
+                       const float* __restrict__ adj_w, const int32_t* __restrict__ hits,
+                       const int32_t* __restrict__ slot, const float* __restrict__ imp,
+                       const float* __restrict__ mass_total, int n_draw,
+                       const int32_t* __restrict__ rowptr, int32_t* __restrict__ edg_s,
+                       int32_t* __restrict__ edg_t, int32_t* __restrict__ tgt,
+                       float* __restrict__ edg_w, int32_t* __restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const float total = *mass_total;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_out; i += warps) {
+        const int node = field[i];
+        const int b = adj_p[node], e = adj_p[node + 1];
+        int out = rowptr[i];
+        for (int q0 = b; q0 < e; q0 += 32) {
+            const int q = q0 + lane;
+            int t = -1, h = 0;
+            if (q < e) {
+                t = adj_i[q];
+                h = hits[t];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, h > 0);
+            if (h > 0) {
+                const int pos = out + __popc(m & ((1u << lane) - 1u));
+                float num = __fmul_rn((float)h, adj_w[q]);
+                num = __fmul_rn(num, total);
+                const float den = __fmul_rn(imp[t], (float)n_draw);
+                const float w = __fdiv_rn(num, den);
+                edg_s[pos] = i;
+                edg_t[pos] = slot[t];
+                tgt[pos] = t;
+                edg_w[pos] = w;
+                if (w != w) atomicOr(status, ST_NAN);
+            }
+            out += __popc(m);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+reset_hits_kernel(const int32_t* __restrict__ pool, int n_pool, int32_t* __restrict__ hits) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_pool) hits[pool[j]] = 0;
+}
+
+__global__ void set_meta_kernel(int32_t* meta, int n) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        for (int k = 0; k < kMetaInts; ++k) meta[k] = 0;
+        meta[M_NOUT] = n;
+        meta[M_NIN] = n;
+    }
+}
+
+static int fill_int(int32_t* p, int64_t n, int32_t v, cudaStream_t st) {
+    if (n <= 0) return SGCN_OK;
+    fill_int_kernel<<<(int)std::min<int64_t>((n + 255) / 256, kNumSMs * 8), 256, 0, st>>>(p, n, v);
+    SGCN_LAUNCHED();
+    return SGCN_OK;
+}
+
+static int read_meta(sgcn_sampler* s, const int32_t* meta_dev) {
+    SGCN_CUDA(cudaMemcpyAsync(s->host_meta, meta_dev, sizeof(int32_t) * kMetaInts,
+                              cudaMemcpyDeviceToHost, s->stream));
+    SGCN_CUDA(cudaStreamSynchronize(s->stream));
+    return SGCN_OK;
+}
+
+static int status_to_error(int status) {
+    if (status == 0) return SGCN_OK;
+    std::string msg = "sampler data error:";
+    if (status & ST_DUPLICATE) msg += " duplicate ids in the batch;";
+    if (status & ST_RANGE) msg += " node id out of range;";
+    if (status & ST_NAN) msg += " nan edge weight (reference: runtime_error(\"nan\"));";
+    if (status & ST_EMPTY) msg += " empty neighbour pool (reference: \"Prob is empty\");";
+    if (status & ST_OVERFLOW) msg += " buffer bound exceeded;";
+    set_error(msg);
+    return SGCN_EDATA;
+}
+
+#define SGCN_TRY(expr)                     \
+    do {                                   \
+        int rc__ = (expr);                 \
+        if (rc__ != SGCN_OK) return rc__;  \
+    } while (0)
+
+static int ensure_level(sgcn_sampler* s, Level& lv, int nb, int64_t sb, bool uniform) {
+    const int64_t n_in = std::min<int64_t>((int64_t)nb + sb, std::max(s->N, nb));
+    SGCN_TRY(lv.meta.ensure(sizeof(int32_t) * kMetaInts));
+    SGCN_TRY(lv.field.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(n_in, 1)));
+    SGCN_TRY(lv.rowptr_s.ensure(sizeof(int32_t) * ((size_t)nb + 1)));
+    SGCN_TRY(lv.rowptr_f.ensure(sizeof(int32_t) * ((size_t)nb + 1)));
+    SGCN_TRY(lv.scales.ensure(sizeof(float) * (size_t)std::max(nb, 1)));
+    const size_t se = (size_t)std::max<int64_t>(sb, 1);
+    SGCN_TRY(lv.edg_s.ensure(sizeof(int32_t) * se));
+    SGCN_TRY(lv.edg_t.ensure(sizeof(int32_t) * se));
+    SGCN_TRY(lv.tgt.ensure(sizeof(int32_t) * se));
+    SGCN_TRY(lv.edg_w.ensure(sizeof(float) * se));
+    if (s->cv && uniform) SGCN_TRY(lv.medg_w.ensure(sizeof(float) * se));
+    SGCN_TRY(s->draws.ensure(sizeof(uint32_t) * se));
+    SGCN_TRY(s->rank.ensure(sizeof(int32_t) * se));
+    SGCN_TRY(s->take.ensure(sizeof(int32_t) * (size_t)std::max(nb, 1)));
+    SGCN_TRY(s->deg.ensure(sizeof(int32_t) * (size_t)std::max(nb, 1)));
+    lv.n_out_bound = nb;
+    lv.s_bound = (int)sb;
+    lv.n_in_bound = (int)n_in;
+    return SGCN_OK;
+}
+
+static int64_t sample_bound(const sgcn_sampler* s, int nb, int degree) {
+    return std::min<int64_t>((int64_t)nb * std::max(degree, 0), s->E);
+}
+
+// cv: materialise ffield / fedg_* in the reference's format.  Synchronises (size = sum of degrees).
+static int materialize_full(sgcn_sampler* s, Level& lv, int n_out, int nnz_f) {
+    cudaStream_t st = s->stream;
+    const size_t fe = (size_t)std::max(nnz_f, 1);
+    SGCN_TRY(lv.fedg_s.ensure(sizeof(int32_t) * fe));
+    SGCN_TRY(lv.fedg_t.ensure(sizeof(int32_t) * fe));
+    SGCN_TRY(lv.fedg_w.ensure(sizeof(float) * fe));
+    SGCN_TRY(lv.ffield.ensure(sizeof(int32_t) * (size_t)std::max(std::min(nnz_f, s->N), 1)));
+    SGCN_TRY(s->rank.ensure(sizeof(int32_t) * fe));
+    int32_t* meta = lv.meta.as<int32_t>();
+    if (nnz_f > 0) {
+        full_expand_kernel<<<div_up(nnz_f, 256), 256, 0, st>>>(
+            lv.field.as<int32_t>(), lv.rowptr_f.as<int32_t>(), n_out, nnz_f, s->adj_p, s->adj_i,
+            s->adj_w, lv.fedg_s.as<int32_t>(), lv.fedg_t.as<int32_t>(), lv.fedg_w.as<float>(),
+            s->fslot);
+        SGCN_LAUNCHED();
+    }
+    scan_full_first_kernel<<<1, kScanThreads, 0, st>>>(lv.fedg_t.as<int32_t>(), s->fslot, nnz_f,
+                                                      s->rank.as<int32_t>(), meta, M_NFF);
+    SGCN_LAUNCHED();
+    if (nnz_f > 0) {
+        full_assign_kernel<<<div_up(nnz_f, 256), 256, 0, st>>>(
+            lv.fedg_t.as<int32_t>(), s->fslot, s->rank.as<int32_t>(), nnz_f, lv.ffield.as<int32_t>());
+        SGCN_LAUNCHED();
+        const int ffb = std::min(nnz_f, s->N);
+        reset_list_kernel<<<div_up(ffb, 256), 256, 0, st>>>(lv.ffield.as<int32_t>(), meta + M_NFF,
+                                                          ffb, s->fslot);
+        SGCN_LAUNCHED();
+    }
+    lv.full_materialized = true;
+    return SGCN_OK;
+}
+
+static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
+                          const int32_t* n_ptr, int nb, int degree, int materialize) {
+    cudaStream_t st = s->stream;
+    int64_t sb = sample_bound(s, nb, degree);
+    const bool exact = degree > kExactSizingDegree;
+    SGCN_TRY(ensure_level(s, lv, nb, exact ? 0 : sb, true));
+    int32_t* meta = lv.meta.as<int32_t>();
+    const int nbl = std::max(nb, 1);
+
+    SGCN_CUDA(cudaMemsetAsync(meta, 0, sizeof(int32_t) * kMetaInts, st));
+    row_setup_kernel<<<div_up(nbl, 256), 256, 0, st>>>(
+        field_in, n_ptr, nb, s->adj_p, s->N, degree, s->cv ? 1 : 0, 1, s->take.as<int32_t>(),
+        s->deg.as<int32_t>(), lv.scales.as<float>(), lv.field.as<int32_t>(), s->slot, meta);
+    SGCN_LAUNCHED();
+    scan_take_deg_kernel<<<1, kScanThreads, 0, st>>>(s->take.as<int32_t>(), s->deg.as<int32_t>(),
+                                                    lv.rowptr_s.as<int32_t>(),
+                                                    lv.rowptr_f.as<int32_t>(), meta);
+    SGCN_LAUNCHED();
+    if (exact) {
+        // large per-row degree ("Exact" runs): size the edge buffers from the true count.  The old
+        // field prefix written by row_setup_kernel must survive the re-allocation.
+        SGCN_TRY(read_meta(s, meta));
+        sb = s->host_meta[M_NNZS];
+        const int n_out = s->host_meta[M_NOUT];
+        DevBuf keep;
+        SGCN_TRY(keep.ensure(sizeof(int32_t) * (size_t)std::max(n_out, 1)));
+        SGCN_CUDA(cudaMemcpyAsync(keep.p, lv.field.p, sizeof(int32_t) * (size_t)n_out,
+                                  cudaMemcpyDeviceToDevice, st));
+        SGCN_CUDA(cudaStreamSynchronize(st));
+        int rc = ensure_level(s, lv, nb, sb, true);
+        if (rc == SGCN_OK && n_out > 0 &&
+            cudaMemcpyAsync(lv.field.p, keep.p, sizeof(int32_t) * (size_t)n_out,
+                            cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            rc = SGCN_ECUDA;
+        cudaStreamSynchronize(st);
+        keep.release();
+        SGCN_TRY(rc);
+        meta = lv.meta.as<int32_t>();
+    }
+    const int sbl = (int)std::max<int64_t>(sb, 1);
+    mt_draw_kernel<<<1, kMtThreads, 0, st>>>(s->engine, meta + M_NNZS, (int)sb,
+                                            s->draws.as<uint32_t>());
+    SGCN_LAUNCHED();
+    fisher_yates_kernel<<<div_up(nbl, 128), 128, 0, st>>>(
+        lv.field.as<int32_t>(), meta, s->adj_p, s->adj_i, s->adj_w, lv.rowptr_s.as<int32_t>(),
+        s->draws.as<uint32_t>(), (int)sb, s->cv ? 1 : 0, lv.edg_s.as<int32_t>(),
+        lv.tgt.as<int32_t>(), lv.edg_w.as<float>(), lv.medg_w.as<float>(), s->slot,
+        meta + M_STATUS);
+    SGCN_LAUNCHED();
+    scan_first_kernel<<<1, kScanThreads, 0, st>>>(lv.tgt.as<int32_t>(), s->slot, (int)sb,
+                                                 s->rank.as<int32_t>(), meta);
+    SGCN_LAUNCHED();
+    assign_kernel<<<div_up(sbl, 256), 256, 0, st>>>(lv.tgt.as<int32_t>(), s->slot,
+                                                   s->rank.as<int32_t>(), meta, (int)sb,
+                                                   lv.edg_t.as<int32_t>(), lv.field.as<int32_t>());
+    SGCN_LAUNCHED();
+    reset_slots_kernel<<<div_up(std::max(lv.n_in_bound, 1), 256), 256, 0, st>>>(
+        lv.field.as<int32_t>(), meta, lv.n_in_bound, s->N, s->slot);
+    SGCN_LAUNCHED();
+
+    lv.full_materialized = false;
+    if (s->cv && materialize) {
+        SGCN_TRY(read_meta(s, meta));
+        SGCN_TRY(materialize_full(s, lv, s->host_meta[M_NOUT], s->host_meta[M_NNZF]));
+    }
+    return SGCN_OK;
+}
+
+static int expand_importance(sgcn_sampler* s, Level& lv, const int32_t* field_in,
+                             const int32_t* n_ptr, int nb, int degree) {
+    cudaStream_t st = s->stream;
+    SGCN_TRY(ensure_level(s, lv, nb, 0, false));
+    int32_t* meta = lv.meta.as<int32_t>();
+    const int nbl = std::max(nb, 1);
+    // degrees of the field rows -> rowptr_f (take = 0: nothing is drawn per row here).  The
+    // reference leaves `scales` empty in this branch (scheduler.cpp:63-123 never pushes).
+    SGCN_CUDA(cudaMemsetAsync(meta, 0, sizeof(int32_t) * kMetaInts, st));
+    row_setup_kernel<<<div_up(nbl, 256), 256, 0, st>>>(
+        field_in, n_ptr, nb, s->adj_p, s->N, 0, 1, 0, s->take.as<int32_t>(), s->deg.as<int32_t>(),
+        lv.scales.as<float>(), lv.field.as<int32_t>(), s->slot, meta);
+    SGCN_LAUNCHED();
+    scan_take_deg_kernel<<<1, kScanThreads, 0, st>>>(s->take.as<int32_t>(), s->deg.as<int32_t>(),
+                                                    lv.rowptr_s.as<int32_t>(),
+                                                    lv.rowptr_f.as<int32_t>(), meta);
+    SGCN_LAUNCHED();
+    SGCN_TRY(read_meta(s, meta));
+    const int n_out = s->host_meta[M_NOUT];
+    const int nnz_f = s->host_meta[M_NNZF];
+    if (s->host_meta[M_STATUS]) return status_to_error(s->host_meta[M_STATUS]);
+
+    // neighbour pool in first-seen order == ffield of the rows (scheduler.cpp:66-78)
+    SGCN_TRY(materialize_full(s, lv, n_out, nnz_f));
+    lv.full_materialized = false;   // the pool is scratch, not an output of this branch
+    SGCN_TRY(read_meta(s, meta));
+    const int n_pool = s->host_meta[M_NFF];
+    if (n_pool == 0) {
+        // Mult::Mult throws "Prob is empty" (mult.cpp:17-18); the reference process would abort
+        set_meta_kernel<<<1, 32, 0, st>>>(meta, n_out);
+        SGCN_LAUNCHED();
+        reset_slots_kernel<<<div_up(nbl, 256), 256, 0, st>>>(lv.field.as<int32_t>(), meta,
+                                                            lv.n_in_bound, s->N, s->slot);
+        SGCN_LAUNCHED();
+        SGCN_CUDA(cudaStreamSynchronize(st));
+        return status_to_error(ST_EMPTY);
+    }
+    // num_samples = min(field.size()*degree, neighbors.size()) in size_t (scheduler.cpp:83)
+    const int64_t want = (int64_t)n_out * (int64_t)degree;
+    const int n_draw = (int)std::min<int64_t>(want < 0 ? 0 : want, n_pool);
+    int cap = n_pool;
+    while (cap != (cap & (-cap))) cap += cap & (-cap);
+
+    // the grown field can gain at most n_draw nodes; edges are counted exactly below
+    {
+        DevBuf keep;
+        SGCN_TRY(keep.ensure(sizeof(int32_t) * (size_t)std::max(n_out, 1)));
+        SGCN_CUDA(cudaMemcpyAsync(keep.p, lv.field.p, sizeof(int32_t) * (size_t)n_out,
+                                  cudaMemcpyDeviceToDevice, st));
+        SGCN_CUDA(cudaStreamSynchronize(st));
+        int rc = lv.field.ensure(sizeof(int32_t) * (size_t)std::max(n_out + n_draw, 1));
+        if (rc == SGCN_OK && n_out > 0 &&
+            cudaMemcpyAsync(lv.field.p, keep.p, sizeof(int32_t) * (size_t)n_out,
+                            cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            rc = SGCN_ECUDA;
+        cudaStreamSynchronize(st);
+        keep.release();
+        SGCN_TRY(rc);
+        lv.n_in_bound = n_out + n_draw;
+    }
+    SGCN_TRY(s->pool_mass.ensure(sizeof(float) * ((size_t)n_pool + 1)));
+    SGCN_TRY(s->tree.ensure(sizeof(float) * ((size_t)cap + 1)));
+    SGCN_TRY(s->draws.ensure(sizeof(uint32_t) * (size_t)std::max(n_draw, 1)));
+    float* mass = s->pool_mass.as<float>();
+    float* mass_total = mass + n_pool;
+    const int32_t* pool = lv.ffield.as<int32_t>();
+
+    pool_mass_kernel<<<div_up(n_pool, 256), 256, 0, st>>>(pool, n_pool, s->importance, mass);
+    SGCN_LAUNCHED();
+    fenwick_build_kernel<<<div_up(cap, 256), 256, 0, st>>>(mass, n_pool, cap, s->tree.as<float>());
+    SGCN_LAUNCHED();
+    // Mult owns a default-constructed std::mt19937 (seed 5489), re-created by every expand
+    // (mult.h:26, scheduler.cpp:82): the draws always restart that stream
+    {
+        uint32_t init[kMtWords];
+        mt_seed_host(5489u, init);
+        SGCN_CUDA(cudaMemcpyAsync(s->engine_is, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        SGCN_CUDA(cudaStreamSynchronize(st));   // `init` is a stack buffer
+    }
+    mt_draw_kernel<<<1, kMtThreads, 0, st>>>(s->engine_is, nullptr, n_draw, s->draws.as<uint32_t>());
+    SGCN_LAUNCHED();
+    importance_draw_kernel<<<1, 32, 0, st>>>(pool, mass, s->tree.as<float>(), n_pool, cap, n_draw,
+                                            s->draws.as<uint32_t>(), s->hits.as<int32_t>(), s->slot,
+                                            lv.field.as<int32_t>(), meta, mass_total);
+    SGCN_LAUNCHED();
+    const int row_blocks = std::min(div_up(std::max(n_out, 1), 8), kNumSMs * 8);
+    importance_count_kernel<<<row_blocks, 256, 0, st>>>(lv.field.as<int32_t>(), n_out, s->adj_p,
+                                                       s->adj_i, s->hits.as<int32_t>(),
+                                                       s->take.as<int32_t>());
+    SGCN_LAUNCHED();
+    scan_counts_kernel<<<1, kScanThreads, 0, st>>>(s->take.as<int32_t>(), n_out,
+                                                  lv.rowptr_s.as<int32_t>(), meta);
+    SGCN_LAUNCHED();
+    SGCN_TRY(read_meta(s, meta));
+    const int nnz_s = s->host_meta[M_NNZS];
+    const size_t se = (size_t)std::max(nnz_s, 1);
+    SGCN_TRY(lv.edg_s.ensure(sizeof(int32_t) * se));
+    SGCN_TRY(lv.edg_t.ensure(sizeof(int32_t) * se));
+    SGCN_TRY(lv.tgt.ensure(sizeof(int32_t) * se));
+    SGCN_TRY(lv.edg_w.ensure(sizeof(float) * se));
+    lv.s_bound = nnz_s;
+    importance_emit_kernel<<<row_blocks, 256, 0, st>>>(
+        lv.field.as<int32_t>(), n_out, s->adj_p, s->adj_i, s->adj_w, s->hits.as<int32_t>(), s->slot,
+        s->importance, mass_total, n_draw, lv.rowptr_s.as<int32_t>(), lv.edg_s.as<int32_t>(),
+        lv.edg_t.as<int32_t>(), lv.tgt.as<int32_t>(), lv.edg_w.as<float>(), meta + M_STATUS);
+    SGCN_LAUNCHED();
+    reset_hits_kernel<<<div_up(n_pool, 256), 256, 0, st>>>(pool, n_pool, s->hits.as<int32_t>());
+    SGCN_LAUNCHED();
+    reset_slots_kernel<<<div_up(std::max(lv.n_in_bound, 1), 256), 256, 0, st>>>(
+        lv.field.as<int32_t>(), meta, lv.n_in_bound, s->N, s->slot);
+    SGCN_LAUNCHED();
+    return SGCN_OK;
+}
+
+static int create_common(sgcn_sampler** out, const float* adj_w, const int32_t* adj_i,
+                         const int32_t* adj_p, int32_t num_data, int32_t num_edges, int32_t L,
+                         int32_t cv, int32_t is, int32_t device, bool src_on_device) {
+    SGCN_REQUIRE(out, "sampler_create: null out");
+    *out = nullptr;
+    SGCN_REQUIRE(num_data >= 0 && num_edges >= 0, "sampler_create: negative size");
+    SGCN_REQUIRE(num_edges == 0 || (adj_w && adj_i), "sampler_create: null adjacency");
+    SGCN_REQUIRE(num_data == 0 || adj_p, "sampler_create: null adj_p");
+    int n_dev = 0;
+    SGCN_CUDA(cudaGetDeviceCount(&n_dev));
+    SGCN_REQUIRE(device >= 0 && device < n_dev, "sampler_create: no such CUDA device");
+    DeviceGuard guard(device);
+    sgcn_sampler* s = new sgcn_sampler();
+    s->device = device;
+    s->N = num_data;
+    s->E = num_edges;
+    s->L = std::max(L, 1);
+    s->cv = cv != 0;
+    s->is = is != 0;
+    const cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    auto fail = [&](int rc) {
+        sgcn_sampler_destroy(s);
+        return rc;
+    };
+#define CK(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) return fail(cuda_fail(e__, #call, __FILE__, __LINE__)); \
+    } while (0)
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->own_stream = true;
+    const size_t ne = (size_t)std::max(num_edges, 1), nn = (size_t)std::max(num_data, 1);
+    CK(cudaMalloc(&s->adj_w, sizeof(float) * ne));
+    CK(cudaMalloc(&s->adj_i, sizeof(int32_t) * ne));
+    CK(cudaMalloc(&s->adj_p, sizeof(int32_t) * (nn + 1)));
+    CK(cudaMalloc(&s->slot, sizeof(int32_t) * nn));
+    CK(cudaMalloc(&s->fslot, sizeof(int32_t) * nn));
+    CK(cudaMalloc(&s->importance, sizeof(float) * nn));
+    CK(cudaMalloc(&s->engine, sizeof(uint32_t) * kMtWords));
+    CK(cudaMalloc(&s->engine_is, sizeof(uint32_t) * kMtWords));
+    CK(cudaMallocHost(&s->host_meta, sizeof(int32_t) * kMetaInts));
+    if (num_edges > 0) {
+        CK(cudaMemcpyAsync(s->adj_w, adj_w, sizeof(float) * (size_t)num_edges, kind, s->stream));
+        CK(cudaMemcpyAsync(s->adj_i, adj_i, sizeof(int32_t) * (size_t)num_edges, kind, s->stream));
+    }
+    // the reference takes indptr[0..num_data) and appends num_edges itself (scheduler.cpp:16,20)
+    if (num_data > 0)
+        CK(cudaMemcpyAsync(s->adj_p, adj_p, sizeof(int32_t) * (size_t)num_data, kind, s->stream));
+    const int32_t e32 = num_edges;
+    CK(cudaMemcpyAsync(s->adj_p + num_data, &e32, sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));   // e32 is a stack variable
+    int rc = fill_int(s->slot, num_data, kUnseen, s->stream);
+    if (rc == SGCN_OK) rc = fill_int(s->fslot, num_data, kUnseen, s->stream);
+    if (rc != SGCN_OK) return fail(rc);
+    if (num_data > 0) {
+        fill_float_kernel<<<std::min(div_up(num_data, 256), kNumSMs * 8), 256, 0, s->stream>>>(
+            s->importance, num_data, s->is ? (float)1e-6 : 1.0f);
+        g_launches.fetch_add(1);
+        if (s->is) {
+            importance_kernel<<<1, 32, 0, s->stream>>>(s->adj_w, s->adj_i, num_edges, s->importance);
+            g_launches.fetch_add(1);
+            rc = s->hits.ensure(sizeof(int32_t) * nn);
+            if (rc != SGCN_OK) return fail(rc);
+            CK(cudaMemsetAsync(s->hits.p, 0, sizeof(int32_t) * nn, s->stream));
+        }
+    }
+    // default-constructed std::mt19937 until seed() is called
+    uint32_t init[kMtWords];
+    mt_seed_host(5489u, init);
+    CK(cudaMemcpyAsync(s->engine, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaGetLastError());
+#undef CK
+    s->levels.resize((size_t)s->L);
+    *out = s;
+    return SGCN_OK;
+}
+
+static Level* level_at(sgcn_sampler* s, int32_t level) {
+    if (level < 0) level = s->cur - 1;
+    if (level < 0 || level >= s->cur || level >= (int)s->levels.size()) return nullptr;
+    return &s->levels[(size_t)level];
+}
+
+}  // namespace sgcn
+
+extern "C" {
+
+int sgcn_sampler_create(sgcn_sampler** out, const float* adj_w, const int32_t* adj_i,
+                        const int32_t* adj_p, int32_t num_data, int32_t num_edges, int32_t L,
+                        int32_t cv, int32_t is, int32_t device) {
+    return create_common(out, adj_w, adj_i, adj_p, num_data, num_edges, L, cv, is, device, false);
+}
+
+int sgcn_sampler_create_device(sgcn_sampler** out, const float* adj_w, const int32_t* adj_i,
+                               const int32_t* adj_p, int32_t num_data, int32_t num_edges,
+                               int32_t L, int32_t cv, int32_t is, int32_t device) {
+    return create_common(out, adj_w, adj_i, adj_p, num_data, num_edges, L, cv, is, device, true);
+}
+
+void sgcn_sampler_destroy(sgcn_sampler* s) {
+    if (!s) return;
+    DeviceGuard guard(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (Level& lv : s->levels) lv.release();
+    for (DevBuf* b : {&s->batch_ids, &s->batch_meta, &s->take, &s->deg, &s->draws, &s->rank,
+                      &s->tile_sums, &s->pool_mass, &s->tree, &s->hits})
+        b->release();
+    cudaFree(s->adj_w);
+    cudaFree(s->adj_i);
+    cudaFree(s->adj_p);
+    cudaFree(s->slot);
+    cudaFree(s->fslot);
+    cudaFree(s->importance);
+    cudaFree(s->engine);
+    cudaFree(s->engine_is);
+    if (s->host_meta) cudaFreeHost(s->host_meta);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int sgcn_sampler_seed(sgcn_sampler* s, int32_t seed) {
+    SGCN_REQUIRE(s, "sampler_seed: null sampler");
+    DeviceGuard guard(s->device);
+    uint32_t init[kMtWords];
+    mt_seed_host((uint32_t)seed, init);
+    SGCN_CUDA(cudaMemcpyAsync(s->engine, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+    SGCN_CUDA(cudaStreamSynchronize(s->stream));
+    return SGCN_OK;
+}
+
+int sgcn_sampler_set_stream(sgcn_sampler* s, void* stream) {
+    SGCN_REQUIRE(s, "sampler_set_stream: null sampler");
+    DeviceGuard guard(s->device);
+    if (s->stream) SGCN_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    s->stream = (cudaStream_t)stream;
+    s->own_stream = false;
+    return SGCN_OK;
+}
+
+int sgcn_sampler_reserve(sgcn_sampler* s, int32_t max_batch, const int32_t* degrees,
+                         int32_t n_degrees, int32_t materialize_full) {
+    SGCN_REQUIRE(s && max_batch >= 0 && n_degrees >= 0 && (n_degrees == 0 || degrees),
+                 "sampler_reserve: bad argument");
+    (void)materialize_full;   // the full COO has no useful size bound; it is grown on demand
+    DeviceGuard guard(s->device);
+    SGCN_TRY(s->batch_ids.ensure(sizeof(int32_t) * (size_t)std::max(max_batch, 1)));
+    SGCN_TRY(s->batch_meta.ensure(sizeof(int32_t) * kMetaInts));
+    if ((int)s->levels.size() < n_degrees) s->levels.resize((size_t)n_degrees);
+    int nb = max_batch;
+    for (int k = 0; k < n_degrees; ++k) {
+        Level& lv = s->levels[(size_t)k];
+        const bool exact = s->is || degrees[k] > kExactSizingDegree;
+        SGCN_TRY(ensure_level(s, lv, nb, exact ? 0 : sample_bound(s, nb, degrees[k]), !s->is));
+        if (exact) break;   // deeper bounds are unknown without running
+        nb = lv.n_in_bound;
+    }
+    return SGCN_OK;
+}
+
+static int start_batch_common(sgcn_sampler* s, int32_t n, const int32_t* ids, cudaMemcpyKind kind) {
+    SGCN_REQUIRE(s, "sampler_start_batch: null sampler");
+    SGCN_REQUIRE(n >= 0 && (n == 0 || ids), "sampler_start_batch: bad ids");
+    DeviceGuard guard(s->device);
+    SGCN_TRY(s->batch_ids.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
+    SGCN_TRY(s->batch_meta.ensure(sizeof(int32_t) * kMetaInts));
+    if (n > 0)
+        SGCN_CUDA(cudaMemcpyAsync(s->batch_ids.p, ids, sizeof(int32_t) * (size_t)n, kind, s->stream));
+    set_meta_kernel<<<1, 32, 0, s->stream>>>(s->batch_meta.as<int32_t>(), n);
+    SGCN_LAUNCHED();
+    if (kind == cudaMemcpyHostToDevice) SGCN_CUDA(cudaStreamSynchronize(s->stream));  // ids may be pageable
+    s->batch_n = n;
+    s->cur = 0;
+    for (Level& lv : s->levels) lv.done = false;
+    return SGCN_OK;
+}
+
+int sgcn_sampler_start_batch(sgcn_sampler* s, int32_t n, const int32_t* ids) {
+    return start_batch_common(s, n, ids, cudaMemcpyHostToDevice);
+}
+
+int sgcn_sampler_start_batch_device(sgcn_sampler* s, int32_t n, const int32_t* ids) {
+    return start_batch_common(s, n, ids, cudaMemcpyDeviceToDevice);
+}
+
+int sgcn_sampler_expand(sgcn_sampler* s, int32_t degree, int32_t materialize_full) {
+    SGCN_REQUIRE(s, "sampler_expand: null sampler");
+    if (s->batch_n < 0) {
+        set_error("sampler_expand called before sampler_start_batch");
+        return SGCN_ESTATE;
+    }
+    SGCN_REQUIRE(degree >= 0, "sampler_expand: negative degree");
+    DeviceGuard guard(s->device);
+    const int k = s->cur;
+    if ((int)s->levels.size() <= k) s->levels.resize((size_t)k + 1);
+    Level& lv = s->levels[(size_t)k];
+    const int32_t* field_in = k == 0 ? s->batch_ids.as<int32_t>() : s->levels[(size_t)k - 1].field.as<int32_t>();
+    const int32_t* n_ptr = k == 0 ? s->batch_meta.as<int32_t>() + M_NIN
+                                  : s->levels[(size_t)k - 1].meta.as<int32_t>() + M_NIN;
+    const int nb = k == 0 ? s->batch_n : s->levels[(size_t)k - 1].n_in_bound;
+    int rc = s->is ? expand_importance(s, lv, field_in, n_ptr, nb, degree)
+                   : expand_uniform(s, lv, field_in, n_ptr, nb, degree, materialize_full);
+    if (rc != SGCN_OK) return rc;
+    lv.done = true;
+    s->cur = k + 1;
+    return SGCN_OK;
+}
+
+int sgcn_sampler_sizes(sgcn_sampler* s, int32_t level, int32_t out[6]) {
+    SGCN_REQUIRE(s && out, "sampler_sizes: null argument");
+    DeviceGuard guard(s->device);
+    Level* lv = level_at(s, level);
+    if (!lv) {
+        set_error("sampler_sizes: no such level (expand not called yet?)");
+        return SGCN_ESTATE;
+    }
+    SGCN_TRY(read_meta(s, lv->meta.as<int32_t>()));
+    for (int k = 0; k < 6; ++k) out[k] = s->host_meta[k];
+    if (!lv->full_materialized) out[M_NFF] = 0;
+    return status_to_error(out[M_STATUS]);
+}
+
+int sgcn_sampler_vec(sgcn_sampler* s, int32_t level, int32_t which, void** ptr, int64_t* len) {
+    SGCN_REQUIRE(s && ptr && len, "sampler_vec: null argument");
+    *ptr = nullptr;
+    *len = 0;
+    switch (which) {
+        case SGCN_VEC_ADJ_I: *ptr = s->adj_i; *len = s->E; return SGCN_OK;
+        case SGCN_VEC_ADJ_P: *ptr = s->adj_p; *len = (int64_t)s->N + 1; return SGCN_OK;
+        case SGCN_VEC_ADJ_W: *ptr = s->adj_w; *len = s->E; return SGCN_OK;
+        case SGCN_VEC_IMPORTANCE: *ptr = s->importance; *len = s->N; return SGCN_OK;
+        default: break;
+    }
+    Level* lv = level_at(s, level);
+    if (!lv) {
+        set_error("sampler_vec: no such level (expand not called yet?)");
+        return SGCN_ESTATE;
+    }
+    const DevBuf* b = nullptr;
+    int64_t n = 0;
+    switch (which) {
+        case SGCN_VEC_FIELD: b = &lv->field; n = lv->n_in_bound; break;
+        case SGCN_VEC_FFIELD: b = &lv->ffield; n = (int64_t)(lv->ffield.cap / 4); break;
+        case SGCN_VEC_EDG_S: b = &lv->edg_s; n = lv->s_bound; break;
+        case SGCN_VEC_EDG_T: b = &lv->edg_t; n = lv->s_bound; break;
+        case SGCN_VEC_TGT: b = &lv->tgt; n = lv->s_bound; break;
+        case SGCN_VEC_EDG_W: b = &lv->edg_w; n = lv->s_bound; break;
+        case SGCN_VEC_MEDG_W: b = &lv->medg_w; n = lv->s_bound; break;
+        case SGCN_VEC_FEDG_S: b = &lv->fedg_s; n = (int64_t)(lv->fedg_s.cap / 4); break;
+        case SGCN_VEC_FEDG_T: b = &lv->fedg_t; n = (int64_t)(lv->fedg_t.cap / 4); break;
+        case SGCN_VEC_FEDG_W: b = &lv->fedg_w; n = (int64_t)(lv->fedg_w.cap / 4); break;
+        case SGCN_VEC_ROWPTR_S: b = &lv->rowptr_s; n = (int64_t)lv->n_out_bound + 1; break;
+        case SGCN_VEC_ROWPTR_F: b = &lv->rowptr_f; n = (int64_t)lv->n_out_bound + 1; break;
+        case SGCN_VEC_SCALES: b = &lv->scales; n = lv->n_out_bound; break;
+        case SGCN_VEC_META: b = &lv->meta; n = kMetaInts; break;
+        default:
+            set_error("sampler_vec: unknown vector id");
+            return SGCN_EINVAL;
+    }
+    *ptr = b->p;
+    *len = b->p ? n : 0;
+    return SGCN_OK;
+}
+
+int sgcn_sampler_copy_vec(sgcn_sampler* s, int32_t level, int32_t which, void* dst, int64_t count) {
+    SGCN_REQUIRE(s && (dst || count == 0) && count >= 0, "sampler_copy_vec: bad argument");
+    void* p = nullptr;
+    int64_t len = 0;
+    SGCN_TRY(sgcn_sampler_vec(s, level, which, &p, &len));
+    DeviceGuard guard(s->device);
+    if (count > 0) {
+        SGCN_REQUIRE(p && count <= len, "sampler_copy_vec: count exceeds the vector's capacity");
+        SGCN_CUDA(cudaMemcpyAsync(dst, p, (size_t)count * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    SGCN_CUDA(cudaStreamSynchronize(s->stream));
+    return SGCN_OK;
+}
+
+int sgcn_sampler_get_rng(sgcn_sampler* s, uint32_t state[624], int32_t* pos) {
+    SGCN_REQUIRE(s && state && pos, "sampler_get_rng: null argument");
+    DeviceGuard guard(s->device);
+    uint32_t tmp[kMtWords];
+    SGCN_CUDA(cudaMemcpyAsync(tmp, s->engine, sizeof(tmp), cudaMemcpyDeviceToHost, s->stream));
+    SGCN_CUDA(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < kMtN; ++i) state[i] = tmp[i];
+    *pos = (int32_t)tmp[kMtN];
+    return SGCN_OK;
+}
+
+int sgcn_sampler_set_rng(sgcn_sampler* s, const uint32_t state[624], int32_t pos) {
+    SGCN_REQUIRE(s && state && pos >= 0 && pos <= kMtN, "sampler_set_rng: bad argument");
+    DeviceGuard guard(s->device);
+    uint32_t tmp[kMtWords];
+    for (int i = 0; i < kMtN; ++i) tmp[i] = state[i];
+    tmp[kMtN] = (uint32_t)pos;
+    SGCN_CUDA(cudaMemcpyAsync(s->engine, tmp, sizeof(tmp), cudaMemcpyHostToDevice, s->stream));
+    SGCN_CUDA(cudaStreamSynchronize(s->stream));
+    return SGCN_OK;
+}
+
+}  // extern "C"

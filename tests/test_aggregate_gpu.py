@@ -1,0 +1,193 @@
+"""GPU: aggregation kernels through the C ABI vs the oracle (NumPy float64 reference value and the
+fp32 storage-order C restatement).  Tolerance: north_star's 1e-4 relative, measured against the
+magnitude of the float64 result (the CV estimator subtracts nearly equal terms, so an elementwise
+relative bound is ill-posed at the cancelling entries)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import aggregators as agg
+from oracle import native
+from tests.graphs_small import random_graph
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def close(got, want64, what):
+    got = got.detach().cpu().numpy().astype(np.float64)
+    scale = max(np.abs(want64).max(), 1e-30)
+    err = np.abs(got - want64).max() / scale
+    assert err <= RTOL, "%s: max error %.3e of scale" % (what, err)
+
+
+def sample(g, ids, degree, cv, seed=3):
+    """reference-format pieces from the CPU oracle sampler"""
+    s = native.OracleSampler(g.data, g.indices, g.indptr, cv=cv)
+    s.seed(seed)
+    s.start_batch(ids)
+    s.expand(degree)
+    z = s.snapshot()
+    n_out, n_in = len(ids), len(z["field"])
+    adj = (np.stack([z["edg_s"], z["edg_t"]], 1).astype(np.int32), z["edg_w"], (n_out, n_in))
+    fadj = None
+    if cv:
+        fadj = (np.stack([z["fedg_s"], z["fedg_t"]], 1).astype(np.int32), z["fedg_w"], (n_out, len(z["ffield"])))
+    return z, adj, fadj, s
+
+
+@pytest.mark.parametrize("d", [4, 32, 64, 100, 128, 256, 512, 1100, 30, 7])
+@pytest.mark.parametrize("graphsage", [False, True])
+def test_plain_forward_backward(d, graphsage):
+    from stochastic_gcn_b200.layers import DeviceAdj, PlainAggregator
+    g = random_graph(600, 10, d)
+    rng = np.random.RandomState(d)
+    ids = rng.choice(600, size=150, replace=False).astype(np.int32)
+    z, adj, _, _ = sample(g, ids, 3, False)
+    x = rng.randn(len(z["field"]), d).astype(np.float32)
+    want = agg.plain_forward(adj, x, graphsage)
+    xt = dev(x).requires_grad_(True)
+    layer = PlainAggregator(DeviceAdj.from_coo(adj), normalization="graphsage" if graphsage else "gcn")
+    out = layer(xt)
+    close(out, want, "plain fwd")
+    close(out, agg.plain_forward(adj, x, graphsage, dtype=np.float32).astype(np.float64), "plain fwd vs fp32 port")
+    dy = rng.randn(*want.shape).astype(np.float32)
+    out.backward(dev(dy))
+    close(xt.grad, agg.plain_backward(adj, dy, x.shape[0], graphsage), "plain bwd")
+
+
+@pytest.mark.parametrize("d", [32, 128, 256, 100, 6])
+@pytest.mark.parametrize("graphsage", [False, True])
+@pytest.mark.parametrize("in_place", [False, True])
+def test_cv_forward_backward(d, graphsage, in_place):
+    from stochastic_gcn_b200.layers import DeviceAdj, FullNeighbours, VRAggregator
+    g = random_graph(700, 25, 100 + d)
+    rng = np.random.RandomState(d)
+    ids = rng.choice(700, size=120, replace=False).astype(np.int32)
+    z, adj, fadj, s = sample(g, ids, 2, True)
+    n_in = len(z["field"])
+    hist = rng.randn(700, d).astype(np.float32)
+    x = (hist[z["field"]] + 0.1 * rng.randn(n_in, d)).astype(np.float32)   # activations close to history
+    want, new_hist = agg.cv_forward(adj, fadj, z["field"], z["ffield"], hist, x, graphsage)
+    hist_t = dev(hist)
+    ifield = dev(z["field"])
+    if in_place:   # rows read straight from the (permuted) CSR, nothing materialised
+        rowptr_f = np.concatenate([[0], np.cumsum(np.diff(g.indptr)[ids])]).astype(np.int32)
+        full = FullNeighbours.in_place(dev(ids), dev(rowptr_f), dev(s.vec("adj_p")), dev(s.vec("adj_i")),
+                                       dev(s.vec("adj_w")))
+    else:
+        full = FullNeighbours.from_coo(fadj, z["ffield"])
+    layer = VRAggregator(DeviceAdj.from_coo(adj), full, None, ifield, None, [hist_t], None, False,
+                         normalization="graphsage" if graphsage else "gcn")
+    xt = dev(x).requires_grad_(True)
+    out = layer(xt)
+    close(out, want, "cv fwd")
+    dy = rng.randn(*want.shape).astype(np.float32)
+    out.backward(dev(dy))
+    close(xt.grad, agg.plain_backward(adj, dy, n_in, graphsage), "cv bwd")
+    # write-back: history rows of the input field are overwritten by the layer input
+    layer.write_back()
+    want_hist = agg.history_update(hist.copy(), z["field"], x)
+    assert np.array_equal(hist_t.cpu().numpy(), want_hist)
+
+
+@pytest.mark.parametrize("d", [32, 128, 20])
+@pytest.mark.parametrize("graphsage", [False, True])
+def test_cvd_forward_backward(d, graphsage):
+    from stochastic_gcn_b200.layers import DeviceAdj, FullNeighbours, VRAggregator
+    g = random_graph(500, 20, 200 + d)
+    rng = np.random.RandomState(d)
+    ids = rng.choice(500, size=90, replace=False).astype(np.int32)
+    z, adj, fadj, s = sample(g, ids, 1, True)
+    n_in = len(z["field"])
+    hist = rng.randn(500, d).astype(np.float32)
+    mu = (hist[z["field"]] + 0.1 * rng.randn(n_in, d)).astype(np.float32)
+    h = (mu + 0.3 * rng.randn(n_in, d)).astype(np.float32)
+    (want_h, want_mu), _ = agg.cvd_forward(adj, fadj, z["field"], z["ffield"], hist, z["scales"], h, mu, graphsage)
+    hist_t = dev(hist)
+    layer = VRAggregator(DeviceAdj.from_coo(adj), FullNeighbours.from_coo(fadj, z["ffield"]), None,
+                         dev(z["field"]), None, [hist_t], dev(z["scales"]), True,
+                         normalization="graphsage" if graphsage else "gcn")
+    ht, mut = dev(h).requires_grad_(True), dev(mu)
+    out_h, out_mu = layer((ht, mut))
+    close(out_h, want_h, "cvd h"); close(out_mu, want_mu, "cvd mu")
+    dy = rng.randn(*want_h.shape).astype(np.float32)
+    out_h.backward(dev(dy))
+    close(ht.grad, agg.cvd_backward_h(adj, z["scales"], dy, n_in, graphsage), "cvd bwd")
+    layer.write_back()
+    assert np.array_equal(hist_t.cpu().numpy(), agg.history_update(hist.copy(), z["field"], mu))
+
+
+def test_cvd_mu_gradient_against_torch_autograd():
+    """d/d mu (unused by the reference, stop_gradient at gcn/layers.py:412) vs a dense torch fp32 model"""
+    from stochastic_gcn_b200.layers import DeviceAdj, FullNeighbours, VRAggregator
+    g = random_graph(300, 15, 9)
+    rng = np.random.RandomState(0)
+    ids = rng.choice(300, size=40, replace=False).astype(np.int32)
+    z, adj, fadj, _ = sample(g, ids, 2, True)
+    n_in, d = len(z["field"]), 32
+    hist = rng.randn(300, d).astype(np.float32)
+    h, mu = rng.randn(n_in, d).astype(np.float32), rng.randn(n_in, d).astype(np.float32)
+    A = torch.zeros(len(ids), n_in, dtype=torch.float64)
+    A.index_put_((torch.from_numpy(adj[0][:, 0]).long(), torch.from_numpy(adj[0][:, 1]).long()),
+                 torch.from_numpy(adj[1]).double(), accumulate=True)
+    hr, mr = torch.from_numpy(h).double().requires_grad_(True), torch.from_numpy(mu).double().requires_grad_(True)
+    sc = torch.from_numpy(z["scales"]).double()[:, None]
+    mu_nb = A @ (mr - torch.from_numpy(hist[z["field"]]).double())
+    h_nb = (A @ (hr - mr)) * sc + mu_nb
+    gy_h, gy_mu = torch.randn(len(ids), d, dtype=torch.float64), torch.randn(len(ids), d, dtype=torch.float64)
+    ((h_nb * gy_h).sum() + (mu_nb * gy_mu).sum()).backward()
+    layer = VRAggregator(DeviceAdj.from_coo(adj), FullNeighbours.from_coo(fadj, z["ffield"]), None,
+                         dev(z["field"]), None, [dev(hist)], dev(z["scales"]), True)
+    ht, mt = dev(h).requires_grad_(True), dev(mu).requires_grad_(True)
+    oh, om = layer((ht, mt))
+    ((oh * gy_h.float().cuda()).sum() + (om * gy_mu.float().cuda()).sum()).backward()
+    close(ht.grad, hr.grad.numpy(), "dh"); close(mt.grad, mr.grad.numpy(), "dmu")
+
+
+def test_coo_kernel_and_gather_layer():
+    from stochastic_gcn_b200 import ops
+    from stochastic_gcn_b200.layers import GatherAggregator
+    rng = np.random.RandomState(5)
+    nnz, n_r, n_c, d = 5000, 300, 400, 64
+    idx = np.stack([rng.randint(0, n_r, nnz), rng.randint(0, n_c, nnz)], 1).astype(np.int32)   # unsorted
+    val = rng.randn(nnz).astype(np.float32)
+    x = rng.randn(n_c, d).astype(np.float32)
+    want = agg._coo_matmul((idx, val, (n_r, n_c)), x, np.float64)
+    close(ops.spmm_coo(dev(idx), dev(val), dev(x), n_r), want, "coo")
+    dy = rng.randn(n_r, d).astype(np.float32)
+    want_t = agg._coo_matmul_t((idx, val, (n_r, n_c)), dy, np.float64)
+    close(ops.spmm_coo(dev(idx), dev(val), dev(dy), n_c, transpose=True), want_t, "coo^T")
+    field = dev(rng.randint(0, n_c, 77).astype(np.int32))
+    xt = dev(x).requires_grad_(True)
+    out = GatherAggregator(field)(xt)
+    assert np.array_equal(out.detach().cpu().numpy(), x[field.cpu().numpy()])
+    out.backward(torch.ones_like(out))
+    want_g = np.zeros_like(x); np.add.at(want_g, field.cpu().numpy(), 1.0)
+    close(xt.grad, want_g.astype(np.float64), "gather bwd")
+
+
+def test_full_mean_skewed_rows_and_empty_rows():
+    """edge-balanced kernel: one 40k-entry row next to empty and single-entry rows, D=128 and D=32"""
+    from stochastic_gcn_b200 import ops
+    rng = np.random.RandomState(11)
+    n = 50_000
+    deg = np.array([40_000, 0, 1, 0, 0, 700, 3, 0, 64, 65, 31, 0], dtype=np.int64)
+    indptr = np.zeros(len(deg) + 1, np.int32); indptr[1:] = np.cumsum(deg)
+    cols = np.concatenate([rng.choice(n, size=k, replace=False) for k in deg]).astype(np.int32)
+    w = rng.rand(indptr[-1]).astype(np.float32)
+    nodes = np.arange(len(deg), dtype=np.int32)
+    for d in (128, 32, 8, 36):
+        hist = rng.randn(n, d).astype(np.float32)
+        want = np.zeros((len(deg), d))
+        for r in range(len(deg)):
+            sl = slice(indptr[r], indptr[r + 1])
+            want[r] = (w[sl, None].astype(np.float64) * hist[cols[sl]].astype(np.float64)).sum(0)
+        y0 = torch.zeros((len(deg), d), device="cuda"); y1 = torch.ones((len(deg), d), device="cuda")
+        ops.full_history_mean(dev(nodes), dev(indptr), len(deg), dev(indptr), dev(cols), dev(w), dev(hist), y0, y1)
+        close(y0, want, "full mean d=%d" % d); close(y1, want + 1.0, "full mean second output")
