@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the variance-reduced GCN hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path, host cores
+
+A step = one pass of the hot path over one batch (sampler -> feature gather -> aggregate forward
+-> aggregate backward -> history write-back) on the synthetic Reddit-shaped graph of BASELINE.json
+configs[2] (233k nodes, ~115M stored edges, 602-d features -> 1204-d PP input, hidden 128, CV+PP,
+degree 2, batch 512).  Metric: aggregated edges / s = (nnz(adj) + nnz(fadj)) per step / step time
+(SURVEY.md 8d); the reference's own `amt_data` counter (sampled edges only) is reported beside it.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: graph shape, mode, degree, batch, hidden, PP feature width            BASELINE.json
+    "reddit_cv": dict(shape="reddit", mode="cv", degree=2, batch=512, hidden=128, feat=1204),       # configs[2]
+    "reddit_cvd": dict(shape="reddit", mode="cvd", degree=1, batch=512, hidden=128, feat=1204),     # configs[3]
+    "powerlaw_ns": dict(shape="powerlaw2m", mode="ns", degree=1, batch=512, hidden=128, feat=512),  # configs[4]
+    "pubmed_cvd": dict(shape="pubmed", mode="cvd", degree=1, batch=60, hidden=32, feat=500),        # configs[1]
+}
+METRIC = "aggregated edges/s (sampled + full-neighbour edges through SpMM fwd+bwd per step)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(w, seed, device, scale):
+    from stochastic_gcn_b200 import graphs
+    g = graphs.make_shape(w["shape"], seed=seed, device=device, scale=scale)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed + 1)
+    feats = torch.randn((g.n, w["feat"]), generator=gen, device=device, dtype=torch.float32)
+    return g, feats
+
+
+def make_batches(n_nodes, batch, n_steps, seed, device, lo=0, hi=None):
+    """Distinct ids per batch, drawn without replacement from [lo, hi) (an epoch-style shuffle)."""
+    hi = n_nodes if hi is None else hi
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed + 2)
+    out, pool, pos = [], None, 0
+    for _ in range(n_steps):
+        if pool is None or pos + batch > pool.numel():
+            pool = (torch.randperm(hi - lo, generator=gen, device=device) + lo).to(torch.int32)
+            pos = 0
+        out.append(pool[pos:pos + batch].contiguous())
+        pos += batch
+    return out
+
+
+def edge_counts(g, batches, degree, cv):
+    deg = g.degrees()
+    s = f = 0
+    for b in batches:
+        d = deg[b.long()]
+        s += int(torch.clamp(d, max=degree).sum())
+        f += int(d.sum()) if cv else 0
+    return s, f
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own CPU implementation of the path (compiled reference sampler + row
+# slicer where oracle/_ref exists, oracle port otherwise; the TensorFlow aggregate is restated by
+# the OpenMP C port because TensorFlow is not installed).  Only bench.py, tests/ and smoke() may
+# touch oracle/.
+# ------------------------------------------------------------------------------------------------
+class CpuPath:
+    def __init__(self, w, g_host, feats_host, seed):
+        import ctypes as C
+        from oracle import native
+        self.C, self.native, self.w = C, native, w
+        self.lib = native.oracle_lib()
+        self.threads = os.cpu_count() or 1
+        self.kind_native = "reference" if native.have_ref() else "port"
+        cls = native.RefSampler if native.have_ref() else native.OracleSampler
+        self.adj_w, self.adj_i, self.adj_p = g_host
+        self.s = cls(self.adj_w, self.adj_i, self.adj_p, cv=w["mode"] != "ns")
+        self.s.seed(seed)
+        self.slice = native.ref_dense_slice if native.have_ref() else native.oracle_dense_slice
+        self.feats = feats_host
+        self.hist = np.zeros((len(self.adj_p) - 1, w["hidden"]), dtype=np.float32)
+        self.adj_p32 = np.ascontiguousarray(self.adj_p, dtype=np.int32)      # row pointers never change
+
+    def step(self, ids):
+        nat, lib, w = self.native, self.lib, self.w
+        H = w["hidden"]
+        ip, fp = nat._ip, nat._fp
+        self.s.start_batch(ids)
+        self.s.expand(w["degree"])
+        field, edg_s, edg_t, edg_w = (self.s.vec(k) for k in ("field", "edg_s", "edg_t", "edg_w"))
+        n_out, n_in, nnz_s = len(ids), len(field), len(edg_s)
+        x0 = self.slice(self.feats, field)                                   # history.dense_slice
+        x = np.ascontiguousarray(x0[:, :H])
+        rowptr = np.searchsorted(edg_s, np.arange(n_out + 1)).astype(np.int32)
+        z = np.empty((n_out, H), dtype=np.float32)
+        if w["mode"] == "ns":
+            lib.orc_spmm_csr_omp(n_out, ip(rowptr), ip(edg_t), fp(edg_w), fp(x), H, fp(z), self.threads)
+            nnz_f = 0
+        else:
+            # fused CV forward over the sampler's own rows (same arithmetic as fadj @ H[ffield])
+            adj_p = self.adj_p32
+            ids32 = np.ascontiguousarray(ids, dtype=np.int32)
+            ci, cw = self.s._get_i, self.s._get_f
+            pi, pw = nat._i32p(), nat._f32p()
+            ci(self.s._h, nat.INT_VECS["adj_i"], self.C.byref(pi))           # zero-copy views of the
+            cw(self.s._h, nat.FLOAT_VECS["adj_w"], self.C.byref(pw))         # scheduler's permuted CSR
+            lib.orc_cv_forward_omp(n_out, ip(rowptr), ip(edg_t), fp(edg_w), fp(x), ip(field), fp(self.hist), H,
+                                   ip(ids32), ip(adj_p), pi, pw, fp(z), self.threads)
+            nnz_f = int((adj_p[ids32 + 1] - adj_p[ids32]).sum())
+        dy = np.ones((n_out, H), dtype=np.float32)
+        dx = np.zeros((n_in, H), dtype=np.float32)
+        lib.orc_spmm_coo_t(nnz_s, ip(edg_s), ip(edg_t), fp(edg_w), fp(dy), H, fp(dx), n_in)
+        if w["mode"] != "ns":
+            lib.orc_scatter_rows(n_in, H, ip(field), fp(x), fp(self.hist))   # tf.scatter_update
+        return nnz_s, nnz_f
+
+
+def cpu_leg(w, g, feats, seed, batches_host, budget_s, warmup):
+    g_host = (g.data.cpu().numpy(), g.indices.cpu().numpy(), g.indptr.cpu().numpy())
+    cpu = CpuPath(w, g_host, feats.cpu().numpy(), seed)
+    for b in batches_host[:warmup]:
+        cpu.step(b)
+    edges, steps, t0 = 0, 0, time.perf_counter()
+    for b in batches_host[warmup:]:
+        s, f = cpu.step(b)
+        edges += s + f
+        steps += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": edges / dt, "unit": "edges/s", "cores": cpu.threads, "kind": "port",
+            "ms_per_step": 1e3 * dt / max(steps, 1), "steps": steps,
+            "sample": "%d steps of the same workload (batch %d); sampler + dense_slice = %s, 1 thread as shipped "
+                      "(gcn/history.cpp:77 omp pragma commented out); TF aggregate restated in C "
+                      "(oracle/sgcn_oracle.c), OpenMP over %d threads" % (steps, w["batch"],
+                      "compiled unmodified reference (oracle/_ref)" if cpu.kind_native == "reference"
+                      else "oracle port", cpu.threads)}
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    g, feats = build_inputs(w, args.seed, dev, args.scale)
+    n = args.steps + args.warmup
+    batches = [b.cpu().numpy() for b in make_batches(g.n, w["batch"], n, args.seed, dev)]
+    g_host = (g.data.cpu().numpy(), g.indices.cpu().numpy(), g.indptr.cpu().numpy())
+    cpu = CpuPath(w, g_host, feats.cpu().numpy(), args.seed)
+    del g, feats
+    for b in batches[:args.warmup]:
+        cpu.step(b)
+    t0 = time.perf_counter()
+    s_tot = f_tot = 0
+    for b in batches[args.warmup:]:
+        s, f = cpu.step(b)
+        s_tot += s; f_tot += f
+    dt = time.perf_counter() - t0
+    val = (s_tot + f_tot) / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "edges/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, w, None),
+            "sampled_edges_per_s": s_tot / dt,
+            "cpu_baseline": {"value": val, "unit": "edges/s", "cores": cpu.threads,
+                             "kind": "reference" if cpu.kind_native == "reference" else "port",
+                             "sample": "every step of this run; sampler + dense_slice are the compiled unmodified "
+                                       "reference (1 thread, as shipped), the TensorFlow aggregate is the C port "
+                                       "with OpenMP on %d threads" % cpu.threads},
+            "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, w, extra):
+    c = {"workload": "%s: synthetic %s-shaped graph, %s+PP degree %d, batch %d/GPU, hidden %d, PP input %d-d"
+                     % (args.workload, w["shape"], w["mode"].upper(), w["degree"], w["batch"], w["hidden"], w["feat"]),
+         "scale": args.scale, "seed": args.seed,
+         "l2": "inputs larger than L2 (adjacency + features + history > 2 GB, a fresh random batch every step); "
+               "no explicit flush"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def run_ours(args, w):
+    import torch.distributed as dist
+    from stochastic_gcn_b200 import _lib
+    from stochastic_gcn_b200.step import HotPathStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    g, feats = build_inputs(w, args.seed, dev, args.scale)
+    n_total = args.steps + args.warmup
+    if world > 1:
+        from stochastic_gcn_b200.sharding import ShardedHotPathStep
+        step = ShardedHotPathStep(g, feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"],
+                                  seed=args.seed + rank, rank=rank, world=world)
+        lo, hi = step.lo, step.hi
+    else:
+        step = HotPathStep(g, feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"], seed=args.seed)
+        lo, hi = 0, g.n
+    batches = make_batches(g.n, w["batch"], n_total, args.seed + rank, dev, lo, hi)
+    step.d_out.normal_(generator=torch.Generator(device=dev).manual_seed(7))
+    s_edges, f_edges = edge_counts(g, batches[args.warmup:], w["degree"], w["mode"] != "ns")
+
+    # warm-up: the first pass is eager (sizes buffers, counts launches), then graph replays
+    step.capture(batches[0])
+    launches_per_step = step.launches_per_step
+    for b in batches[1:args.warmup]:
+        step.replay(b)
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- timed region: exactly K steps, device-resident inputs ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for b in batches[args.warmup:]:
+        step.replay(b)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    sizes_last = step.sizes()
+
+    # ---- e2e: same K steps through the host-buffer API (pinned ids in, aggregated rows out) ----
+    pinned = [b.cpu().pin_memory() for b in batches[args.warmup:]]
+    step.step_host(pinned[0])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for p in pinned:
+        out_host = step.step_host(p)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    clock_info = clocks.stop() if rank == 0 else None
+
+    # ---- dominant kernel, timed alone on its launch stream over the same K batches ----
+    kern = step.time_dominant_kernel(batches[args.warmup:]) if hasattr(step, "time_dominant_kernel") else None
+
+    t = torch.tensor([ms, ms_e2e, float(s_edges), float(f_edges)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, ms_e2e = float(tmax[0]), float(tmax[1])
+        s_edges, f_edges = float(tsum[2]), float(tsum[3])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    total_edges = s_edges + f_edges
+    value = total_edges / (ms * 1e-3)
+    alg = step.algorithmic_bytes(sizes_last)
+    line = {"metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, w, {"nodes": g.n, "stored_edges": g.nnz,
+                                                "last_step_sizes": sizes_last,
+                                                "parallelism": "row-range shards x%d" % world if world > 1 else "single GPU"}),
+            "sampled_edges_per_s": s_edges / (ms * 1e-3),
+            "step_hbm": {"algorithmic_bytes_per_step": alg["total"],
+                         "achieved_gbs": alg["total"] * world / (ms / args.steps * 1e-3) / 1e9 / world,
+                         "frac_of_peak": alg["total"] / (ms / args.steps * 1e-3) / 1e9 / peak,
+                         "stages": {k: v for k, v in alg.items() if k != "total"}},
+            "e2e": {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s",
+                    "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(pinned[0].numel() * 4),
+                    "d2h_bytes_per_step": int(out_host.numel() * 4)},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "launches_per_step": int(launches_per_step),
+            "clocks": clock_info}
+    if kern is not None:
+        line["roofline"] = {"bound": "hbm", "kernel": kern["kernel"], "achieved": kern["bytes"] / kern["sec"] / 1e9,
+                            "peak": peak, "unit": "GB/s", "frac": kern["bytes"] / kern["sec"] / 1e9 / peak,
+                            "traffic": kern.get("traffic"), "peak_source": peak_src,
+                            "us_per_launch": kern["sec"] * 1e6, "algorithmic_bytes_per_launch": kern["bytes"],
+                            "how": kern["how"]}
+    if world == 1 and not args.no_cpu:
+        host_batches = [b.cpu().numpy() for b in make_batches(g.n, w["batch"], 4000, args.seed + 99, dev)]
+        line["cpu_baseline"] = cpu_leg(w, g, feats, args.seed, host_batches, args.cpu_seconds, 3)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reddit_cv", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (tests only)")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,218 @@
+"""One pass of the hot path over one batch -- the device-resident restatement of the reference's
+per-step sequence (gcn/train.py:190,207; gcn/vrgcn.py:39-84; gcn/models.py:160-166,186-194):
+
+    sampler.expand                      scheduler.cpp:46-189      (device sampler, no host trip)
+    input = dense_slice(features, fields[0])   vrgcn.py:39-47    (row gather)
+    Z = aggregate(adj, fadj, history, X)       layers.py:223-362 (fused CV / CVD / plain forward)
+    dX = adj^T dZ (+ self rows)                 models.py:187     (SpMM backward)
+    history[fields[0]] = X                      models.py:160-166 (row scatter-store)
+
+All buffers are sized from upper bounds (|field| <= B(1+degree)) and every data-dependent length
+is read by the kernels from the sampler's device meta block, so the whole pass is a fixed launch
+sequence: it is captured once into a CUDA graph and replayed per batch.
+
+The dense layers between the gather and the aggregate (``X = relu(LN(input @ W))``) are not part
+of the hot path: the aggregator input X is taken as the first ``hidden`` columns of
+the gathered feature rows (CVD: h = columns [0,hidden), mu = columns [hidden, 2 hidden)), and the
+upstream gradient dZ is a resident synthetic tensor, so the data dependencies gather -> aggregate
+-> backward -> write-back are the real ones.
+"""
+import torch
+
+from . import _lib, ops
+from .sampler import DeviceSampler
+
+MODES = ("ns", "cv", "cvd")
+
+
+class HotPathStep:
+    def __init__(self, graph, features, hidden, batch_size, degree, mode="cv", normalization="graphsage",
+                 seed=1, history=None):
+        if mode not in MODES:
+            raise ValueError("mode must be one of %s" % (MODES,))
+        need = hidden * (2 if mode == "cvd" else 1)
+        if features.shape[1] < need:
+            raise ValueError("features need at least %d columns" % need)
+        self.dev = features.device
+        self.mode, self.hidden, self.B, self.degree = mode, int(hidden), int(batch_size), int(degree)
+        self.concat = normalization != "gcn"
+        self.features = features
+        self.n_nodes = graph.n
+        self.sampler = DeviceSampler(graph.data, graph.indices, graph.indptr, L=1, cv=mode != "ns")
+        self.sampler.seed(seed)
+        self.sampler.reserve(self.B, [self.degree])
+        self.history = history if history is not None else torch.zeros(
+            (graph.n, self.hidden), dtype=torch.float32, device=self.dev)     # vrgcn.py:23-36: zero-init
+        self.n_in_bound = min(self.B * (1 + self.degree), max(graph.n, self.B))
+        f = features.shape[1]
+        width = self.hidden * (2 if self.concat else 1)
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.dev)
+        self.ids = torch.zeros(self.B, dtype=torch.int32, device=self.dev)
+        self.x0 = z(self.n_in_bound, f)                 # gathered input rows
+        self.out = z(self.B, width)                     # aggregated h (or the only output)
+        self.out_mu = z(self.B, width) if mode == "cvd" else None
+        self.d_out = z(self.B, width)                   # upstream gradient (synthetic, resident)
+        self.dx = z(self.n_in_bound, self.hidden)
+        self.graph = None
+        self.launches_per_step = None
+        self._views = None
+        self._pinned_out = None
+        self._probe = None          # (start_event, end_event) around the dominant kernel, when timing it
+
+    # -- pieces ----------------------------------------------------------------------------------
+    def _sample(self):
+        s = self.sampler
+        s.start_batch(self.ids)
+        s.expand(self.degree, materialize_full=False)
+        if self._views is None:
+            names = ("field", "rowptr_s", "rowptr_f", "edg_t", "tgt", "edg_w", "scales", "meta")
+            v = {k: s.view(k) for k in names}
+            v["adj_p"], v["adj_i"], v["adj_w"] = s.view("adj_p"), s.view("adj_i"), s.view("adj_w")
+            v["n_out_dev"], v["n_in_dev"] = v["meta"][0:1], v["meta"][1:2]
+            self._views = v
+        return self._views
+
+    def _pass(self):
+        v = self._sample()
+        H, B = self.hidden, self.B
+        probe = self._probe
+        if probe and self.mode == "ns":
+            probe[0].record()
+        ops.gather_rows(self.features, v["field"], out=self.x0, n_dev=v["n_in_dev"])
+        if probe and self.mode == "ns":
+            probe[1].record()
+        x = self.x0[:, :H]
+        nb = self.out[:, H:] if self.concat else self.out
+        slf = self.out[:, :H] if self.concat else None
+        if self.mode == "ns":
+            ops.spmm_csr(v["rowptr_s"], v["edg_t"], v["edg_w"], x, B, out=nb, n_out_dev=v["n_out_dev"])
+            if self.concat:
+                ops.copy_rows_pad(x, B, slf, n_dev=v["n_out_dev"])
+            rscale, new_hist = None, None
+        elif self.mode == "cv":
+            ops.cv_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], B, x, self.history, nb,
+                               self_out=slf, n_out_dev=v["n_out_dev"])
+            if probe:
+                probe[0].record()
+            ops.full_history_mean(v["field"], v["rowptr_f"], B, v["adj_p"], v["adj_i"], v["adj_w"], self.history,
+                                  nb, n_out_dev=v["n_out_dev"])
+            if probe:
+                probe[1].record()
+            rscale, new_hist = None, x
+        else:
+            mu = self.x0[:, H:2 * H]
+            nb_mu = self.out_mu[:, H:] if self.concat else self.out_mu
+            ops.cvd_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], v["scales"], B, x, mu,
+                                self.history, nb, nb_mu, self_h=slf,
+                                self_mu=self.out_mu[:, :H] if self.concat else None, n_out_dev=v["n_out_dev"])
+            if probe:
+                probe[0].record()
+            ops.full_history_mean(v["field"], v["rowptr_f"], B, v["adj_p"], v["adj_i"], v["adj_w"], self.history,
+                                  nb_mu, nb, n_out_dev=v["n_out_dev"])
+            if probe:
+                probe[1].record()
+            rscale, new_hist = v["scales"], mu
+        # backward of the aggregate: dX = adj^T (dZ_nb * scale) (+ dZ_self on the first B rows)
+        d_nb = self.d_out[:, H:] if self.concat else self.d_out
+        if self.concat:
+            ops.copy_rows_pad(self.d_out[:, :H], B, self.dx, n_dev=v["n_out_dev"])
+        else:
+            ops.copy_rows_pad(None, 0, self.dx)
+        ops.spmm_csr_bwd(v["rowptr_s"], v["edg_t"], v["edg_w"], d_nb, self.dx, B, rscale=rscale,
+                         n_out_dev=v["n_out_dev"])
+        # history write-back after the forward read (models.py:186-194)
+        if new_hist is not None:
+            ops.history_update(self.history, v["field"], new_hist, n_dev=v["n_in_dev"])
+
+    # -- drivers ---------------------------------------------------------------------------------
+    def run(self, ids):
+        """Eager pass (one launch per kernel).  ids: CUDA int32 [B] of distinct node ids."""
+        self.ids.copy_(ids, non_blocking=True)
+        before = _lib.launch_count()
+        self._pass()
+        self.launches_per_step = _lib.launch_count() - before
+        return self.out
+
+    def capture(self, warmup_ids):
+        """Capture the pass into a CUDA graph (after one eager warm-up pass sized the buffers)."""
+        self.run(warmup_ids)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.dev)
+        self.sampler.use_stream(side)
+        with torch.cuda.graph(g, stream=side):
+            self._pass()
+        self.graph = g
+        self._capture_stream = side
+        return g
+
+    def replay(self, ids):
+        self.ids.copy_(ids, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+    def step_host(self, ids_pinned):
+        """End-to-end call with HOST buffers: pinned int32 ids in, aggregated rows out (pinned)."""
+        if self._pinned_out is None:
+            self._pinned_out = torch.empty(self.out.shape, dtype=torch.float32, pin_memory=True)
+        self.ids.copy_(ids_pinned, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._pass()
+        self._pinned_out.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self._pinned_out
+
+    def time_dominant_kernel(self, batches):
+        """Average device time of the dominant kernel (the edge-balanced full-neighbour history mean
+        for CV/CVD, the feature-row gather for NS), CUDA events on its launch stream, one eager pass
+        per batch, with the algorithmic bytes of exactly those launches."""
+        pairs, total_bytes = [], 0
+        for b in batches:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self._probe = ev
+            self.ids.copy_(b, non_blocking=True)
+            self._pass()
+            self._probe = None
+            pairs.append(ev)
+            z = self.sizes()
+            alg = self.algorithmic_bytes(z)
+            total_bytes += alg["gather"] if self.mode == "ns" else alg["aggregate_full"]
+        torch.cuda.synchronize(self.dev)
+        sec = sum(a.elapsed_time(b) for a, b in pairs) * 1e-3
+        n = max(len(pairs), 1)
+        return {"kernel": "move_rows_vec4_kernel<gather>" if self.mode == "ns" else "full_mean_kernel",
+                "sec": sec / n, "bytes": total_bytes / n, "launches": n,
+                "how": "CUDA events around the kernel on its launch stream, eager passes over the same %d batches "
+                       "as the timed region (the timed region itself replays a CUDA graph)" % n}
+
+    def sizes(self):
+        """(n_out, n_in, nnz_s, nnz_f) of the last pass (synchronises)."""
+        m = self._views["meta"].cpu().tolist()
+        if m[5]:
+            raise _lib.SgcnError(_lib.SGCN_EDATA, "sampler status %d" % m[5])
+        return {"n_out": m[0], "n_in": m[1], "nnz_s": m[2], "nnz_f": m[3]}
+
+    def algorithmic_bytes(self, z=None):
+        """SURVEY.md 8d per-step algorithmic HBM bytes, split per stage, for the measured sizes."""
+        z = z or self.sizes()
+        D, F = self.hidden, self.features.shape[1]
+        n_out, n_in, s, f = z["n_out"], z["n_in"], z["nnz_s"], z["nnz_f"]
+        cv = self.mode != "ns"
+        b = {}
+        b["sampler"] = 8 * n_out + 2 * 2 * 8 * s + (16 if cv else 12) * s + 4 * (n_in + 2 * n_out)
+        b["gather"] = 2 * 4 * F * n_in + 4 * n_in
+        fwd = 8 * s + 4 * (n_out + 1) + 4 * D * s + 4 * D * n_out
+        if self.concat:
+            fwd += 2 * 4 * D * n_out
+        if cv:
+            fwd += 4 * D * s + 4 * s
+        if self.mode == "cvd":
+            fwd += 4 * D * s + 4 * n_out + 4 * D * n_out * (2 if self.concat else 1)
+        b["aggregate_sampled"] = fwd
+        b["aggregate_full"] = (8 * f + 4 * (n_out + 1) + 4 * D * f) if cv else 0
+        b["backward"] = 8 * s + 4 * D * n_out * (2 if self.concat else 1) + 2 * 4 * D * s + 4 * D * n_in
+        b["writeback"] = (4 * n_in + 8 * D * n_in) if cv else 0
+        b["total"] = sum(b.values())
+        return b

@@ -1,0 +1,90 @@
+"""GPU: the whole pass (HotPathStep) -- eager and CUDA-graph replay -- against the oracle, for the
+three estimator modes, over several consecutive batches (history and sampler state carry over)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import aggregators as agg
+from oracle import native
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_step(o, mode, deg, ids, feats, hist, D, d_out, graphsage=True):
+    o.start_batch(ids)
+    o.expand(deg)
+    s = o.snapshot()
+    B, n_in = len(ids), len(s["field"])
+    x0 = feats[s["field"]]
+    adj = (np.stack([s["edg_s"], s["edg_t"]], 1).astype(np.int32), s["edg_w"], (B, n_in))
+    if mode == "ns":
+        out = agg.plain_forward(adj, x0[:, :D], graphsage)
+        dx = agg.plain_backward(adj, d_out, n_in, graphsage)
+        return out, None, dx, s
+    fadj = (np.stack([s["fedg_s"], s["fedg_t"]], 1).astype(np.int32), s["fedg_w"], (B, len(s["ffield"])))
+    if mode == "cv":
+        out, new = agg.cv_forward(adj, fadj, s["field"], s["ffield"], hist, x0[:, :D], graphsage)
+        dx = agg.plain_backward(adj, d_out, n_in, graphsage)
+        agg.history_update(hist, s["field"], new[0])
+        return out, None, dx, s
+    (oh, om), new = agg.cvd_forward(adj, fadj, s["field"], s["ffield"], hist, s["scales"], x0[:, :D],
+                                    x0[:, D:2 * D], graphsage)
+    dx = agg.cvd_backward_h(adj, s["scales"], d_out, n_in, graphsage)
+    agg.history_update(hist, s["field"], new[0])
+    return oh, om, dx, s
+
+
+def close(got, want, what):
+    err = np.abs(got.astype(np.float64) - want).max() / max(np.abs(want).max(), 1e-30)
+    assert err <= 1e-4, "%s: %.3e" % (what, err)
+
+
+@pytest.mark.parametrize("mode,deg", [("ns", 1), ("cv", 2), ("cvd", 1)])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_pass_matches_oracle_over_batches(mode, deg, use_graph):
+    from stochastic_gcn_b200 import graphs
+    from stochastic_gcn_b200.step import HotPathStep
+    g = graphs.powerlaw_graph(3000, 120_000, seed=4, device="cuda", max_degree=600)
+    D, B = 32, 48
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    feats = torch.randn((g.n, 80), generator=gen, device="cuda")
+    step = HotPathStep(g, feats, D, B, deg, mode=mode, seed=5)
+    step.history.normal_(generator=gen)
+    step.d_out.normal_(generator=gen)
+    hist = step.history.cpu().numpy().copy()
+    o = native.OracleSampler(g.data.cpu().numpy(), g.indices.cpu().numpy(), g.indptr.cpu().numpy(), cv=mode != "ns")
+    o.seed(5)
+    fh, d_out = feats.cpu().numpy(), step.d_out.cpu().numpy()
+    perm = torch.randperm(g.n, generator=gen, device="cuda").to(torch.int32)
+    batches = [perm[i * B:(i + 1) * B].contiguous() for i in range(5)]
+    for i, ids in enumerate(batches):
+        if use_graph and i == 0:
+            step.capture(ids)            # eager warm-up pass on this batch, then capture (= second pass)
+            # the capture pass does not execute; replay once so that history/sampler state advance
+            oracle_step(o, mode, deg, ids.cpu().numpy(), fh, hist, D, d_out)
+            continue
+        out = (step.replay(ids) if use_graph else step.run(ids)).cpu().numpy()
+        oh, om, dx, s = oracle_step(o, mode, deg, ids.cpu().numpy(), fh, hist, D, d_out)
+        z = step.sizes()
+        assert z["n_in"] == len(s["field"]) and z["nnz_s"] == len(s["edg_s"])
+        assert np.array_equal(step.sampler.host("field", z["n_in"]), s["field"])
+        close(out, oh, "batch %d out" % i)
+        if om is not None:
+            close(step.out_mu.cpu().numpy(), om, "batch %d out_mu" % i)
+        close(step.dx.cpu().numpy()[:z["n_in"]], dx, "batch %d dx" % i)
+        if mode != "ns":
+            assert np.array_equal(step.history.cpu().numpy(), hist), "history after batch %d" % i
+
+
+def test_host_api_round_trip():
+    from stochastic_gcn_b200 import graphs
+    from stochastic_gcn_b200.step import HotPathStep
+    g = graphs.powerlaw_graph(2000, 60_000, seed=1, device="cuda", max_degree=300)
+    feats = torch.randn((g.n, 64), device="cuda")
+    step = HotPathStep(g, feats, 32, 32, 2, mode="cv", seed=2)
+    ids = torch.arange(32, dtype=torch.int32).pin_memory()
+    out = step.step_host(ids)
+    assert out.is_pinned() and out.shape == (32, 64)
+    assert torch.equal(out, step.out.cpu())
+    b = step.algorithmic_bytes()
+    assert b["total"] == sum(v for k, v in b.items() if k != "total") and b["aggregate_full"] > 0
