@@ -177,13 +177,16 @@ int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_
                            float* y0, int64_t ld_y0, float* y1, int64_t ld_y1, void* stream);
 
 /* VRAggregator CV branch, sampled part (layers.py:350-362):
- *   y[r,:] = sum_e vals[e] * (x[cols[e],:] - hist[tgt[e],:])
+ *   y[r,:] (+)= sum_e vals[e] * (x[cols[e],:] - hist[tgt[e],:])
  *   self != NULL:  self[r,:] = x[r,:]   (the concat's left half, graphsage normalisation)
- * The full-neighbour term is added by sgcn_full_history_mean. */
+ * The full-neighbour term is added by sgcn_full_history_mean.  accumulate=0 overwrites y (run it
+ * BEFORE sgcn_full_history_mean); accumulate=1 adds with 128-bit reductions into a y the caller
+ * zeroed, so the two kernels commute and may run concurrently on different streams. */
 int sgcn_cv_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
                         const int32_t* tgt, int32_t n_out, const int32_t* n_out_dev,
                         const float* x, int64_t ld_x, const float* hist, int64_t ld_h, int32_t D,
-                        float* y, int64_t ld_y, float* self, int64_t ld_self, void* stream);
+                        float* y, int64_t ld_y, float* self, int64_t ld_self, int32_t accumulate,
+                        void* stream);
 
 /* VRAggregator CVD branch, sampled part (layers.py:298-319):
  *   ymu[r,:] = sum_e vals[e] * (mu[cols[e],:] - hist[tgt[e],:])
@@ -195,7 +198,7 @@ int sgcn_cvd_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float
                          const float* mu, int64_t ld_mu, const float* hist, int64_t ld_h,
                          int32_t D, float* yh, int64_t ld_yh, float* ymu, int64_t ld_ymu,
                          float* self_h, int64_t ld_sh, float* self_mu, int64_t ld_sm,
-                         void* stream);
+                         int32_t accumulate, void* stream);
 
 /* tf.scatter_update(history, fields[l], new_history)  models.py:160-166:
  *   hist[idx[i], :] = rows[i, :]   (idx distinct) */

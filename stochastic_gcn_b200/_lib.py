@@ -55,9 +55,9 @@ SIGNATURES = {
     "sgcn_full_history_mean": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,
                                       _vp, _i64, _vp]),
     "sgcn_cv_sampled_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i32, _vp,
-                                   _i64, _vp, _i64, _vp]),
+                                   _i64, _vp, _i64, _i32, _vp]),
     "sgcn_cvd_sampled_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _vp,
-                                    _i64, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+                                    _i64, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
     "sgcn_history_update": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _i32, _vp]),
     "sgcn_copy_rows_pad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
 }

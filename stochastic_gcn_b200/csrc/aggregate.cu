@@ -68,7 +68,8 @@ struct SampledArgs {
     float* ymu; int64_t ld_ymu;        // CVD
     float* self0; int64_t ld_s0;       // CV: copy of x[:n_out]; CVD: copy of h[:n_out]
     float* self1; int64_t ld_s1;       // CVD: copy of mu[:n_out]
-    int accumulate;                    // PLAIN only
+    int accumulate;                    // 0: overwrite y; 1: y += (PLAIN: read-modify-write by the row's
+                                       // owner; CV/CVD: 128-bit RED, commutes with full_mean_kernel)
 };
 
 template <typename V, int LPR, int VPL, int MODE>
@@ -126,12 +127,19 @@ sampled_rows_kernel(const SampledArgs a) {
                 if (a.accumulate) acc[k] = T::add(acc[k], *(const V*)yp);
                 T::st(yp, acc[k]);
             } else if (MODE == MODE_CV) {
-                T::st(a.y + (int64_t)r * a.ld_y + off[k], acc[k]);
+                if (a.accumulate) T::red(a.y + (int64_t)r * a.ld_y + off[k], acc[k]);
+                else T::st(a.y + (int64_t)r * a.ld_y + off[k], acc[k]);
                 if (a.self0) T::st(a.self0 + (int64_t)r * a.ld_s0 + off[k],
                                    T::ld(a.x + (int64_t)r * a.ld_x + off[k]));
             } else {
-                T::st(a.ymu + (int64_t)r * a.ld_ymu + off[k], acc[k]);
-                T::st(a.y + (int64_t)r * a.ld_y + off[k], T::add(T::mul(acc2[k], sc), acc[k]));
+                const V yh = T::add(T::mul(acc2[k], sc), acc[k]);
+                if (a.accumulate) {
+                    T::red(a.ymu + (int64_t)r * a.ld_ymu + off[k], acc[k]);
+                    T::red(a.y + (int64_t)r * a.ld_y + off[k], yh);
+                } else {
+                    T::st(a.ymu + (int64_t)r * a.ld_ymu + off[k], acc[k]);
+                    T::st(a.y + (int64_t)r * a.ld_y + off[k], yh);
+                }
                 if (a.self0) T::st(a.self0 + (int64_t)r * a.ld_s0 + off[k],
                                    T::ld(a.x + (int64_t)r * a.ld_x + off[k]));
                 if (a.self1) T::st(a.self1 + (int64_t)r * a.ld_s1 + off[k],
@@ -202,7 +210,15 @@ spmm_coo_kernel(const int2* __restrict__ idx2, const float* __restrict__ vals, i
 // ---- edge-balanced full-neighbour history mean -------------------------------------------------
 // Position p of the concatenated neighbour list belongs to output row r = upper_bound(rowptr_f, p)-1
 // and is entry adj[adj_p[nodes[r]] + p - rowptr_f[r]] of the sampler's CSR.
-constexpr int kFullChunk = 64;   // edges per warp-chunk (multiple of 32)
+//
+// Each warp owns one contiguous span of positions (nnz_f / #warps, rounded to 32).  Per 32
+// positions: the lanes fetch (row, column id, weight) in parallel -- row pointers come from a
+// shared-memory copy staged once per CTA, column ids / weights are one coalesced load each and
+// are prefetched one sub-chunk ahead -- then the warp walks the 32 edges with UN independent
+// 16-byte-per-lane history-row loads in flight.  A sub-chunk that lies inside one output row (the
+// common case: rows average hundreds of entries) takes a branch-free path; partial sums stay in
+// registers across the span and leave through one 128-bit RED per lane per row segment.
+constexpr int kFullStageRows = 4096;   // row pointers are staged in shared memory up to this many rows
 
 struct FullArgs {
     const int32_t* nodes; const int32_t* rowptr_f; int n_out; const int32_t* n_out_dev;
@@ -229,46 +245,97 @@ template <typename V, int LPR, int VPL>
 __global__ void __launch_bounds__(kAggThreads)
 full_mean_kernel(const FullArgs a) {
     using T = VT<V>;
-    constexpr int G = 32 / LPR;           // groups per warp, each walks its own edges
-    constexpr int UN = (VPL >= 4) ? 2 : 4;   // row loads in flight per group
+    constexpr int G = 32 / LPR;                                  // groups per warp
+    constexpr int UN = (VPL >= 4) ? 2 : ((VPL == 2) ? 4 : 8);    // row loads in flight per group
+    constexpr int US = 2;                                        // same, on the rare multi-row path
+    __shared__ int32_t s_ptr[kFullStageRows + 1];                // rowptr_f
+    __shared__ int32_t s_base[kFullStageRows];                   // adj_p[nodes[r]] - rowptr_f[r]
     const int n_out = dev_count(a.n_out_dev, a.n_out);
     if (n_out <= 0) return;
-    const int nnz = a.rowptr_f[n_out];
+    const bool staged = n_out <= kFullStageRows;
+    if (staged) {
+        for (int i = threadIdx.x; i <= n_out; i += kAggThreads) s_ptr[i] = __ldg(a.rowptr_f + i);
+        for (int i = threadIdx.x; i < n_out; i += kAggThreads)
+            s_base[i] = __ldg(a.adj_p + __ldg(a.nodes + i)) - __ldg(a.rowptr_f + i);
+        __syncthreads();
+    }
+    const int32_t* ptr = staged ? s_ptr : a.rowptr_f;
+    const int nnz = ptr[n_out];
     const int lane = threadIdx.x & 31;
     const int gl = lane % LPR, g = lane / LPR;
     const int warp = (blockIdx.x * kAggThreads + threadIdx.x) >> 5;
     const int warps = (gridDim.x * kAggThreads) >> 5;
+    const int span = max(32, (((nnz + warps - 1) / warps) + 31) & ~31);
+    const int p0 = warp * span;
+    const int p1 = min(p0 + span, nnz);
+    if (p0 >= p1) return;
 
-    for (int p0 = warp * kFullChunk; p0 < nnz; p0 += warps * kFullChunk) {
-        const int p1 = min(p0 + kFullChunk, nnz);
-        V acc[VPL];
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) acc[k] = T::zero();
-        int cur = -1;                                          // row the group is accumulating
-        for (int pb = p0; pb < p1; pb += 32) {
-            // lane-parallel metadata for 32 consecutive positions
-            const int p = pb + lane;
-            int r = -1, c = 0;
-            float w = 0.f;
-            if (p < p1) {
-                int lo = 0, hi = n_out;                        // last r with rowptr_f[r] <= p
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(a.rowptr_f + mid) <= p) lo = mid; else hi = mid;
-                }
-                r = lo;
-                const int q = __ldg(a.adj_p + __ldg(a.nodes + r)) + (p - __ldg(a.rowptr_f + r));
-                c = __ldg(a.adj_i + q);
-                w = __ldg(a.adj_w + q);
+    // lane-parallel metadata of 32 consecutive positions starting at pb
+    auto load_meta = [&](int pb, int& r, int& c, float& w) {
+        const int p = pb + lane;
+        r = -1; c = 0; w = 0.f;
+        if (p < p1) {
+            int lo = 0, hi = n_out;                               // last r with ptr[r] <= p
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (ptr[mid] <= p) lo = mid; else hi = mid;
             }
-            const int cnt = min(32, p1 - pb);
-            // group g takes positions g, g+G, g+2G, ... ; UN of them in flight
+            r = lo;
+            const int q = staged ? (s_base[lo] + p)
+                                 : (__ldg(a.adj_p + __ldg(a.nodes + lo)) + (p - ptr[lo]));
+            c = __ldg(a.adj_i + q);
+            w = __ldg(a.adj_w + q);
+        }
+    };
+
+    V acc[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) acc[k] = T::zero();
+    int cur = -1;                                                 // row this group is accumulating
+    int r_n, c_n;
+    float w_n;
+    load_meta(p0, r_n, c_n, w_n);
+    for (int pb = p0; pb < p1; pb += 32) {
+        const int r = r_n, c = c_n;
+        const float w = w_n;
+        if (pb + 32 < p1) load_meta(pb + 32, r_n, c_n, w_n);      // prefetch the next sub-chunk
+        const int cnt = min(32, p1 - pb);
+        const int r_first = __shfl_sync(0xffffffffu, r, 0);
+        const int r_last = __shfl_sync(0xffffffffu, r, cnt - 1);
+        if (r_first == r_last) {
+            // the whole sub-chunk feeds one output row: no per-edge row tracking
+            if (r_first != cur) {
+                if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
+                cur = r_first;
+            }
             for (int j0 = 0; j0 < cnt; j0 += G * UN) {
                 V v[UN][VPL];
-                int rj[UN];
                 float wj[UN];
 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
+                    const int j = j0 + u * G + g;
+                    const int jj = min(j, 31);
+                    const int cj = __shfl_sync(0xffffffffu, c, jj);
+                    wj[u] = (j < cnt) ? __shfl_sync(0xffffffffu, w, jj) : 0.f;   // w = 0 beyond the end
+                    if (j >= cnt) wj[u] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) {
+                        const int off = (gl + k * LPR) * T::W;
+                        v[u][k] = (off < a.D) ? T::ld_stream(a.hist + (int64_t)cj * a.ld_h + off) : T::zero();
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u)
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) T::fma(acc[k], wj[u], v[u][k]);
+            }
+        } else {
+            for (int j0 = 0; j0 < cnt; j0 += G * US) {
+                V v[US][VPL];
+                int rj[US];
+                float wj[US];
+#pragma unroll
+                for (int u = 0; u < US; ++u) {
                     const int j = j0 + u * G + g;
                     const int jj = min(j, 31);
                     const int cj = __shfl_sync(0xffffffffu, c, jj);
@@ -284,7 +351,7 @@ full_mean_kernel(const FullArgs a) {
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < UN; ++u) {
+                for (int u = 0; u < US; ++u) {
                     if (rj[u] < 0) continue;
                     if (rj[u] != cur) {
                         if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
@@ -295,8 +362,8 @@ full_mean_kernel(const FullArgs a) {
                 }
             }
         }
-        if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
     }
+    if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
 }
 
 // ---- dispatch -----------------------------------------------------------------------------------
@@ -382,7 +449,8 @@ int sgcn_spmm_csr(const int32_t* rowptr, const int32_t* cols, const float* vals,
 int sgcn_cv_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
                         const int32_t* tgt, int32_t n_out, const int32_t* n_out_dev,
                         const float* x, int64_t ld_x, const float* hist, int64_t ld_h, int32_t D,
-                        float* y, int64_t ld_y, float* self, int64_t ld_self, void* stream) {
+                        float* y, int64_t ld_y, float* self, int64_t ld_self, int32_t accumulate,
+                        void* stream) {
     SGCN_REQUIRE(n_out >= 0 && D >= 0, "cv_sampled_fwd: negative size");
     if (n_out == 0 || D == 0) return SGCN_OK;
     SGCN_REQUIRE(rowptr && x && hist && y, "cv_sampled_fwd: null pointer");
@@ -391,7 +459,7 @@ int sgcn_cv_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float*
     SampledArgs a{};
     a.rowptr = rowptr; a.cols = cols; a.vals = vals; a.map = tgt;
     a.n_out = n_out; a.n_out_dev = n_out_dev; a.x = x; a.ld_x = ld_x; a.hist = hist; a.ld_h = ld_h;
-    a.y = y; a.ld_y = ld_y; a.self0 = self; a.ld_s0 = ld_self;
+    a.y = y; a.ld_y = ld_y; a.self0 = self; a.ld_s0 = ld_self; a.accumulate = accumulate;
     const bool vec_ok = D % 4 == 0 && ld_x % 4 == 0 && ld_h % 4 == 0 && ld_y % 4 == 0 &&
                         aligned16(x) && aligned16(hist) && aligned16(y) &&
                         (!self || (ld_self % 4 == 0 && aligned16(self)));
@@ -404,7 +472,7 @@ int sgcn_cvd_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float
                          const float* mu, int64_t ld_mu, const float* hist, int64_t ld_h,
                          int32_t D, float* yh, int64_t ld_yh, float* ymu, int64_t ld_ymu,
                          float* self_h, int64_t ld_sh, float* self_mu, int64_t ld_sm,
-                         void* stream) {
+                         int32_t accumulate, void* stream) {
     SGCN_REQUIRE(n_out >= 0 && D >= 0, "cvd_sampled_fwd: negative size");
     if (n_out == 0 || D == 0) return SGCN_OK;
     SGCN_REQUIRE(rowptr && scale && h && mu && hist && yh && ymu, "cvd_sampled_fwd: null pointer");
@@ -415,7 +483,7 @@ int sgcn_cvd_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float
     a.rowptr = rowptr; a.cols = cols; a.vals = vals; a.map = tgt; a.scale = scale;
     a.n_out = n_out; a.n_out_dev = n_out_dev; a.x = h; a.ld_x = ld_hh; a.mu = mu; a.ld_mu = ld_mu;
     a.hist = hist; a.ld_h = ld_h; a.y = yh; a.ld_y = ld_yh; a.ymu = ymu; a.ld_ymu = ld_ymu;
-    a.self0 = self_h; a.ld_s0 = ld_sh; a.self1 = self_mu; a.ld_s1 = ld_sm;
+    a.self0 = self_h; a.ld_s0 = ld_sh; a.self1 = self_mu; a.ld_s1 = ld_sm; a.accumulate = accumulate;
     const bool vec_ok = D % 4 == 0 && ld_hh % 4 == 0 && ld_mu % 4 == 0 && ld_h % 4 == 0 &&
                         ld_yh % 4 == 0 && ld_ymu % 4 == 0 && aligned16(h) && aligned16(mu) &&
                         aligned16(hist) && aligned16(yh) && aligned16(ymu) &&

@@ -15,6 +15,7 @@
 // round-trip (buffers are sized from upper bounds: |field| <= n_out (1+degree), nnz_s <= n_out
 // degree).  Only the optional reference-format full-neighbour COO (ffield / fedg_*) and the
 // importance branch synchronise, because their sizes (sum of full degrees) have no useful bound.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -84,6 +85,7 @@ struct sgcn_sampler {
     uint32_t* engine_is = nullptr;
     // batch
     DevBuf batch_ids, batch_meta;
+    const int32_t* batch_src = nullptr;   // level-0 field: batch_ids (host path) or the caller's buffer
     int batch_n = -1;
     int cur = 0;                 // number of expands since start_batch
     std::vector<Level> levels;
@@ -155,16 +157,17 @@ __global__ void importance_kernel(const float* __restrict__ adj_w, const int32_t
 
 // ---- pass 1: per-row degree / sample count / scale; old field becomes the prefix -----------------
 __global__ void __launch_bounds__(256)
-row_setup_kernel(const int32_t* __restrict__ field_in, const int32_t* __restrict__ n_ptr, int nb,
-                 const int32_t* __restrict__ adj_p, int N, int degree, int want_deg, int want_scales,
+row_setup_kernel(const int32_t* __restrict__ field_in, const int32_t* __restrict__ n_ptr, int n_host,
+                 int nb, const int32_t* __restrict__ adj_p, int N, int degree, int want_deg, int want_scales,
                  int32_t* __restrict__ take, int32_t* __restrict__ deg_out,
                  float* __restrict__ scales, int32_t* __restrict__ field_out,
                  int32_t* __restrict__ slot, int32_t* __restrict__ meta) {
-    const int n_out = min(*n_ptr, nb);
+    const int n_raw = n_ptr ? *n_ptr : n_host;
+    const int n_out = min(n_raw, nb);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {   // meta was zeroed by the memset that precedes this launch
         meta[M_NOUT] = n_out;
-        if (*n_ptr > nb) atomicOr(meta + M_STATUS, ST_OVERFLOW);
+        if (n_raw > nb) atomicOr(meta + M_STATUS, ST_OVERFLOW);
     }
     if (i >= n_out) return;
     const int node = field_in[i];
@@ -501,6 +504,216 @@ __global__ void set_meta_kernel(int32_t* meta, int n) {
     }
 }
 
+
+// ---- fused single-CTA expand (uniform branch) ------------------------------------------------------
+// At training batch sizes (B = 512, degree <= 2) every pass above is a few hundred threads of
+// work and the chain is pure launch + dependent-load latency.  One CTA of 1024 threads runs the
+// whole expand with block barriers in place of kernel boundaries: rows -> scans -> MT19937 draws
+// (into shared memory) -> Fisher-Yates -> first-occurrence numbering -> slot reset.  Values that
+// other threads update with L2 atomics (slot[]) are read with ld.global.cg so that a stale L1 line
+// is never observed inside the kernel.
+constexpr int kFusedThreads = 1024;
+constexpr int kFusedMaxRows = 4096;
+constexpr int kFusedMaxEdges = 8192;
+constexpr size_t kFusedSmemBytes =
+    sizeof(int32_t) * ((size_t)kFusedMaxRows + 1 + 2 * (size_t)kFusedMaxEdges + kMtN + 64);
+
+struct FusedArgs {
+    const int32_t* field_in; const int32_t* n_ptr; int n_host, nb, sb;
+    const int32_t* adj_p; int32_t* adj_i; float* adj_w; int N, degree, cv;
+    uint32_t* engine; int32_t* slot;
+    int32_t* field; int32_t* rowptr_s; int32_t* rowptr_f; int32_t* edg_s; int32_t* edg_t;
+    int32_t* tgt; float* edg_w; float* medg_w; float* scales; int32_t* meta;
+};
+
+__device__ __forceinline__ int block_scan_excl_1024(int v, int* total, int* s_warp /*33 ints*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = s_warp[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    const int excl = inc - v + s_warp[warp];
+    *total = s_warp[32];
+    __syncthreads();
+    return excl;
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+expand_fused_kernel(const FusedArgs a) {
+    extern __shared__ int32_t smem[];
+    int32_t* s_rowptr = smem;                                  // kFusedMaxRows + 1
+    int32_t* s_tgt = s_rowptr + kFusedMaxRows + 1;             // kFusedMaxEdges
+    uint32_t* s_u = (uint32_t*)(s_tgt + kFusedMaxEdges);       // draws, later the first-occurrence ranks
+    uint32_t* s_mt = s_u + kFusedMaxEdges;                     // kMtN
+    int32_t* s_warp = (int32_t*)(s_mt + kMtN);                 // 33
+    __shared__ int s_status, s_pos;
+    const int tid = threadIdx.x;
+
+    const int n_raw = a.n_ptr ? *a.n_ptr : a.n_host;
+    const int n_out = min(n_raw, a.nb);
+    if (tid == 0) {
+        s_status = n_raw > a.nb ? ST_OVERFLOW : 0;
+        s_pos = (int)a.engine[kMtN];
+    }
+    for (int i = tid; i < kMtN; i += kFusedThreads) s_mt[i] = a.engine[i];
+    __syncthreads();
+
+    // rows + both prefix sums, 1024 rows per sweep with a carry
+    int carry_s = 0, carry_f = 0;
+    for (int base = 0; base < n_out; base += kFusedThreads) {
+        const int i = base + tid;
+        int take = 0, d = 0;
+        if (i < n_out) {
+            const int node = a.field_in[i];
+            a.field[i] = node;
+            if (node < 0 || node >= a.N) {
+                atomicOr(&s_status, ST_RANGE);
+                a.scales[i] = 1.f;
+            } else {
+                const int b = a.adj_p[node];
+                d = a.adj_p[node + 1] - b;
+                take = min(d, a.degree);
+                const float scale = (d == 0) ? 1.f : __fdiv_rn((float)d, (float)take);
+                a.scales[i] = (float)(1.0 / (double)__fsqrt_rn(scale));
+                a.slot[node] = i;
+            }
+        }
+        int tot_s, tot_f;
+        const int ex_s = block_scan_excl_1024(take, &tot_s, s_warp);
+        const int ex_f = block_scan_excl_1024(a.cv ? d : 0, &tot_f, s_warp);
+        if (i < n_out) {
+            s_rowptr[i] = carry_s + ex_s;
+            a.rowptr_s[i] = carry_s + ex_s;
+            a.rowptr_f[i] = carry_f + ex_f;
+        }
+        carry_s += tot_s;
+        carry_f += tot_f;
+    }
+    if (tid == 0) {
+        s_rowptr[n_out] = carry_s;
+        a.rowptr_s[n_out] = carry_s;
+        a.rowptr_f[n_out] = carry_f;
+        if (carry_s > a.sb) s_status |= ST_OVERFLOW;
+    }
+    const int nnz = min(carry_s, a.sb);
+
+    // the next nnz engine outputs -> shared memory
+    {
+        int pos = s_pos, produced = 0;
+        while (produced < nnz) {
+            if (pos >= kMtN) {
+                mt_regen_block(s_mt);
+                pos = 0;
+            }
+            const int avail = min(kMtN - pos, nnz - produced);
+            for (int i = tid; i < avail; i += kFusedThreads) s_u[produced + i] = mt_temper(s_mt[pos + i]);
+            pos += avail;
+            produced += avail;
+        }
+        __syncthreads();
+        for (int i = tid; i < kMtN; i += kFusedThreads) a.engine[i] = s_mt[i];
+        if (tid == 0) a.engine[kMtN] = (uint32_t)pos;
+    }
+
+    // per-row partial Fisher-Yates on the stored row (rows of one field are disjoint)
+    for (int i = tid; i < n_out; i += kFusedThreads) {
+        const int e0 = s_rowptr[i];
+        const int take = s_rowptr[i + 1] - e0;
+        if (take <= 0 || e0 + take > a.sb) continue;
+        const int node = a.field_in[i];
+        const int base = a.adj_p[node];
+        const int d = a.adj_p[node + 1] - base;
+        int32_t* rc = a.adj_i + base;
+        float* rw = a.adj_w + base;
+        const float scale = __fdiv_rn((float)d, (float)take);
+        for (int k = 0; k < take; ++k) {
+            const float u = mt_canonical(s_u[e0 + k]);
+            const float where = __fadd_rn((float)k, __fmul_rn((float)(d - k), u));
+            int j = (int)where;
+            if (j > d - 1) j = d - 1;
+            const int ck = rc[k], cj = rc[j];
+            const float wk = rw[k], wj = rw[j];
+            rc[k] = cj; rc[j] = ck;
+            rw[k] = wj; rw[j] = wk;
+            const float w = __fmul_rn(wj, scale);
+            const int e = e0 + k;
+            a.edg_s[e] = i;
+            a.tgt[e] = cj;
+            s_tgt[e] = cj;
+            a.edg_w[e] = w;
+            if (a.cv) a.medg_w[e] = __fmul_rn(wj, w);
+            if (__ldcg(a.slot + cj) >= n_out) atomicMin(a.slot + cj, n_out + e);
+        }
+    }
+    __syncthreads();
+
+    // first-occurrence flags -> ranks (reuse the draw buffer)
+    int32_t* s_rank = (int32_t*)s_u;
+    int n_new = 0;
+    for (int base = 0; base < nnz; base += kFusedThreads) {
+        const int e = base + tid;
+        const int f = (e < nnz && __ldcg(a.slot + s_tgt[e]) == n_out + e) ? 1 : 0;
+        int tot;
+        const int ex = block_scan_excl_1024(f, &tot, s_warp);
+        if (e < nnz) s_rank[e] = n_new + ex;
+        n_new += tot;
+    }
+    __syncthreads();
+    for (int e = tid; e < nnz; e += kFusedThreads) {
+        const int t = s_tgt[e];
+        const int sl = __ldcg(a.slot + t);
+        if (sl < n_out) {
+            a.edg_t[e] = sl;
+        } else {
+            const int e_first = sl - n_out;
+            const int pos = n_out + s_rank[e_first];
+            a.edg_t[e] = pos;
+            if (e_first == e) a.field[pos] = t;
+        }
+    }
+    // duplicate batch ids leave slot[node] != position for at least one of the copies
+    for (int j = tid; j < n_out; j += kFusedThreads) {
+        const int node = a.field_in[j];
+        if (node >= 0 && node < a.N && __ldcg(a.slot + node) != j) atomicOr(&s_status, ST_DUPLICATE);
+    }
+    __syncthreads();
+    for (int j = tid; j < n_out; j += kFusedThreads) {
+        const int node = a.field_in[j];
+        if (node >= 0 && node < a.N) a.slot[node] = kUnseen;
+    }
+    for (int e = tid; e < nnz; e += kFusedThreads) a.slot[s_tgt[e]] = kUnseen;
+    if (tid == 0) {
+        a.meta[M_NOUT] = n_out;
+        a.meta[M_NIN] = n_out + n_new;
+        a.meta[M_NNZS] = nnz;
+        a.meta[M_NNZF] = carry_f;
+        a.meta[M_NFF] = 0;
+        a.meta[M_STATUS] = s_status;
+        a.meta[M_AUX] = 0;
+    }
+}
+
+static bool fused_sampler_enabled() {
+    const char* e = getenv("SGCN_NO_FUSED_SAMPLER");
+    return !(e && e[0] == '1');
+}
+
 static int fill_int(int32_t* p, int64_t n, int32_t v, cudaStream_t st) {
     if (n <= 0) return SGCN_OK;
     fill_int_kernel<<<(int)std::min<int64_t>((n + 255) / 256, kNumSMs * 8), 256, 0, st>>>(p, n, v);
@@ -602,9 +815,31 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
     int32_t* meta = lv.meta.as<int32_t>();
     const int nbl = std::max(nb, 1);
 
+    if (!exact && nb <= kFusedMaxRows && sb <= kFusedMaxEdges && fused_sampler_enabled()) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kFusedSmemBytes));
+            attr_set = true;
+        }
+        FusedArgs fa{field_in, n_ptr, nb, nb, (int)sb, s->adj_p, s->adj_i, s->adj_w, s->N, degree,
+                     s->cv ? 1 : 0, s->engine, s->slot, lv.field.as<int32_t>(), lv.rowptr_s.as<int32_t>(),
+                     lv.rowptr_f.as<int32_t>(), lv.edg_s.as<int32_t>(), lv.edg_t.as<int32_t>(),
+                     lv.tgt.as<int32_t>(), lv.edg_w.as<float>(), lv.medg_w.as<float>(),
+                     lv.scales.as<float>(), meta};
+        expand_fused_kernel<<<1, kFusedThreads, kFusedSmemBytes, st>>>(fa);
+        SGCN_LAUNCHED();
+        lv.full_materialized = false;
+        if (s->cv && materialize) {
+            SGCN_TRY(read_meta(s, meta));
+            SGCN_TRY(materialize_full(s, lv, s->host_meta[M_NOUT], s->host_meta[M_NNZF]));
+        }
+        return SGCN_OK;
+    }
+
     SGCN_CUDA(cudaMemsetAsync(meta, 0, sizeof(int32_t) * kMetaInts, st));
     row_setup_kernel<<<div_up(nbl, 256), 256, 0, st>>>(
-        field_in, n_ptr, nb, s->adj_p, s->N, degree, s->cv ? 1 : 0, 1, s->take.as<int32_t>(),
+        field_in, n_ptr, nb, nb, s->adj_p, s->N, degree, s->cv ? 1 : 0, 1, s->take.as<int32_t>(),
         s->deg.as<int32_t>(), lv.scales.as<float>(), lv.field.as<int32_t>(), s->slot, meta);
     SGCN_LAUNCHED();
     scan_take_deg_kernel<<<1, kScanThreads, 0, st>>>(s->take.as<int32_t>(), s->deg.as<int32_t>(),
@@ -671,7 +906,7 @@ static int expand_importance(sgcn_sampler* s, Level& lv, const int32_t* field_in
     // reference leaves `scales` empty in this branch (scheduler.cpp:63-123 never pushes).
     SGCN_CUDA(cudaMemsetAsync(meta, 0, sizeof(int32_t) * kMetaInts, st));
     row_setup_kernel<<<div_up(nbl, 256), 256, 0, st>>>(
-        field_in, n_ptr, nb, s->adj_p, s->N, 0, 1, 0, s->take.as<int32_t>(), s->deg.as<int32_t>(),
+        field_in, n_ptr, nb, nb, s->adj_p, s->N, 0, 1, 0, s->take.as<int32_t>(), s->deg.as<int32_t>(),
         lv.scales.as<float>(), lv.field.as<int32_t>(), s->slot, meta);
     SGCN_LAUNCHED();
     scan_take_deg_kernel<<<1, kScanThreads, 0, st>>>(s->take.as<int32_t>(), s->deg.as<int32_t>(),
@@ -940,13 +1175,17 @@ static int start_batch_common(sgcn_sampler* s, int32_t n, const int32_t* ids, cu
     SGCN_REQUIRE(s, "sampler_start_batch: null sampler");
     SGCN_REQUIRE(n >= 0 && (n == 0 || ids), "sampler_start_batch: bad ids");
     DeviceGuard guard(s->device);
-    SGCN_TRY(s->batch_ids.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
-    SGCN_TRY(s->batch_meta.ensure(sizeof(int32_t) * kMetaInts));
-    if (n > 0)
-        SGCN_CUDA(cudaMemcpyAsync(s->batch_ids.p, ids, sizeof(int32_t) * (size_t)n, kind, s->stream));
-    set_meta_kernel<<<1, 32, 0, s->stream>>>(s->batch_meta.as<int32_t>(), n);
-    SGCN_LAUNCHED();
-    if (kind == cudaMemcpyHostToDevice) SGCN_CUDA(cudaStreamSynchronize(s->stream));  // ids may be pageable
+    if (kind == cudaMemcpyHostToDevice) {
+        SGCN_TRY(s->batch_ids.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
+        if (n > 0) {
+            SGCN_CUDA(cudaMemcpyAsync(s->batch_ids.p, ids, sizeof(int32_t) * (size_t)n, kind, s->stream));
+            SGCN_CUDA(cudaStreamSynchronize(s->stream));   // ids may be pageable host memory
+        }
+        s->batch_src = s->batch_ids.as<int32_t>();
+    } else {
+        // device ids are BORROWED, not copied: one launch less on the per-step critical path
+        s->batch_src = ids;
+    }
     s->batch_n = n;
     s->cur = 0;
     for (Level& lv : s->levels) lv.done = false;
@@ -972,9 +1211,10 @@ int sgcn_sampler_expand(sgcn_sampler* s, int32_t degree, int32_t materialize_ful
     const int k = s->cur;
     if ((int)s->levels.size() <= k) s->levels.resize((size_t)k + 1);
     Level& lv = s->levels[(size_t)k];
-    const int32_t* field_in = k == 0 ? s->batch_ids.as<int32_t>() : s->levels[(size_t)k - 1].field.as<int32_t>();
-    const int32_t* n_ptr = k == 0 ? s->batch_meta.as<int32_t>() + M_NIN
-                                  : s->levels[(size_t)k - 1].meta.as<int32_t>() + M_NIN;
+    const int32_t* field_in = k == 0 ? s->batch_src : s->levels[(size_t)k - 1].field.as<int32_t>();
+    // level 0: the batch size is a host value (n_ptr == NULL, count = nb); deeper levels read the
+    // previous level's |field| from its device meta block
+    const int32_t* n_ptr = k == 0 ? nullptr : s->levels[(size_t)k - 1].meta.as<int32_t>() + M_NIN;
     const int nb = k == 0 ? s->batch_n : s->levels[(size_t)k - 1].n_in_bound;
     int rc = s->is ? expand_importance(s, lv, field_in, n_ptr, nb, degree)
                    : expand_uniform(s, lv, field_in, n_ptr, nb, degree, materialize_full);

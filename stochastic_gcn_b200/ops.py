@@ -129,19 +129,19 @@ def full_history_mean(nodes, rowptr_f, n_out, adj_p, adj_i, adj_w, hist, y0, y1=
     return y0
 
 
-def cv_sampled_fwd(rowptr, cols, vals, tgt, n_out, x, hist, y, self_out=None, n_out_dev=None):
+def cv_sampled_fwd(rowptr, cols, vals, tgt, n_out, x, hist, y, self_out=None, n_out_dev=None, accumulate=False):
     """y[r] = sum_e vals[e] (x[cols[e]] - hist[tgt[e]]); self_out[r] = x[r]  (gcn/layers.py:350-362)."""
     _f32(x, "x"); _f32(hist, "hist"); _f32(y, "y")
     d = x.shape[1]
     check(_lib.load().sgcn_cv_sampled_fwd(ptr(rowptr), ptr(cols), ptr(vals), ptr(tgt), n_out, ptr(n_out_dev),
                                           ptr(x), _ld(x), ptr(hist), _ld(hist), d, ptr(y), _ld(y),
                                           ptr(self_out), _ld(self_out) if self_out is not None else 0,
-                                          stream_ptr()))
+                                          1 if accumulate else 0, stream_ptr()))
     return y
 
 
 def cvd_sampled_fwd(rowptr, cols, vals, tgt, scale, n_out, h, mu, hist, yh, ymu, self_h=None, self_mu=None,
-                    n_out_dev=None):
+                    n_out_dev=None, accumulate=False):
     """CVD sampled part (gcn/layers.py:298-319); see include/sgcn_b200.h:sgcn_cvd_sampled_fwd."""
     _f32(h, "h"); _f32(mu, "mu"); _f32(hist, "hist"); _f32(yh, "yh"); _f32(ymu, "ymu")
     d = h.shape[1]
@@ -149,5 +149,5 @@ def cvd_sampled_fwd(rowptr, cols, vals, tgt, scale, n_out, h, mu, hist, yh, ymu,
         ptr(rowptr), ptr(cols), ptr(vals), ptr(tgt), ptr(scale), n_out, ptr(n_out_dev), ptr(h), _ld(h),
         ptr(mu), _ld(mu), ptr(hist), _ld(hist), d, ptr(yh), _ld(yh), ptr(ymu), _ld(ymu),
         ptr(self_h), _ld(self_h) if self_h is not None else 0,
-        ptr(self_mu), _ld(self_mu) if self_mu is not None else 0, stream_ptr()))
+        ptr(self_mu), _ld(self_mu) if self_mu is not None else 0, 1 if accumulate else 0, stream_ptr()))
     return yh, ymu

@@ -58,6 +58,8 @@ class HotPathStep:
         self._views = None
         self._pinned_out = None
         self._probe = None          # (start_event, end_event) around the dominant kernel, when timing it
+        self._s_b = torch.cuda.Stream(device=self.dev)   # side streams of the fork/join in _pass
+        self._s_c = torch.cuda.Stream(device=self.dev)
 
     # -- pieces ----------------------------------------------------------------------------------
     def _sample(self):
@@ -73,54 +75,89 @@ class HotPathStep:
         return self._views
 
     def _pass(self):
-        v = self._sample()
+        """sampler -> { gather -> sampled aggregate | full-neighbour history mean | backward } -> write-back.
+
+        The three middle branches are independent once the sampled sub-adjacency exists (both
+        aggregate kernels add into a pre-zeroed output with 128-bit reductions, so they commute);
+        they are forked onto side streams, which a CUDA-graph capture turns into parallel branches.
+        """
         H, B = self.hidden, self.B
+        main = torch.cuda.current_stream(self.dev)
+        if getattr(self.sampler, "_stream", None) is None or self.sampler._stream.cuda_stream != main.cuda_stream:
+            self.sampler.use_stream(main)
         probe = self._probe
-        if probe and self.mode == "ns":
-            probe[0].record()
-        ops.gather_rows(self.features, v["field"], out=self.x0, n_dev=v["n_in_dev"])
-        if probe and self.mode == "ns":
-            probe[1].record()
-        x = self.x0[:, :H]
+        cv = self.mode != "ns"
         nb = self.out[:, H:] if self.concat else self.out
         slf = self.out[:, :H] if self.concat else None
+        nb_mu = None
+        if cv:   # zero the neighbour halves the two aggregate kernels accumulate into
+            ops.copy_rows_pad(None, 0, nb)
+            if self.mode == "cvd":
+                nb_mu = self.out_mu[:, H:] if self.concat else self.out_mu
+                ops.copy_rows_pad(None, 0, nb_mu)
+        v = self._sample()
+        ev_sampled = torch.cuda.Event()
+        ev_sampled.record(main)
+
+        # branch B: full-neighbour history mean (the dominant kernel)
+        ev_b = None
+        if cv:
+            with torch.cuda.stream(self._s_b):
+                self._s_b.wait_event(ev_sampled)
+                if probe:
+                    probe[0].record(self._s_b)
+                if self.mode == "cv":
+                    ops.full_history_mean(v["field"], v["rowptr_f"], B, v["adj_p"], v["adj_i"], v["adj_w"],
+                                          self.history, nb, n_out_dev=v["n_out_dev"])
+                else:
+                    ops.full_history_mean(v["field"], v["rowptr_f"], B, v["adj_p"], v["adj_i"], v["adj_w"],
+                                          self.history, nb_mu, nb, n_out_dev=v["n_out_dev"])
+                if probe:
+                    probe[1].record(self._s_b)
+                ev_b = torch.cuda.Event()
+                ev_b.record(self._s_b)
+
+        # branch C: backward of the aggregate, dX = adj^T (dZ_nb * scale) (+ dZ_self on the first B rows)
+        with torch.cuda.stream(self._s_c):
+            self._s_c.wait_event(ev_sampled)
+            d_nb = self.d_out[:, H:] if self.concat else self.d_out
+            if self.concat:
+                ops.copy_rows_pad(self.d_out[:, :H], B, self.dx, n_dev=v["n_out_dev"])
+            else:
+                ops.copy_rows_pad(None, 0, self.dx)
+            ops.spmm_csr_bwd(v["rowptr_s"], v["edg_t"], v["edg_w"], d_nb, self.dx, B,
+                             rscale=v["scales"] if self.mode == "cvd" else None, n_out_dev=v["n_out_dev"])
+            ev_c = torch.cuda.Event()
+            ev_c.record(self._s_c)
+
+        # branch A (main): feature-row gather, then the sampled part of the aggregate
+        if probe and not cv:
+            probe[0].record(main)
+        ops.gather_rows(self.features, v["field"], out=self.x0, n_dev=v["n_in_dev"])
+        if probe and not cv:
+            probe[1].record(main)
+        x = self.x0[:, :H]
+        new_hist = None
         if self.mode == "ns":
             ops.spmm_csr(v["rowptr_s"], v["edg_t"], v["edg_w"], x, B, out=nb, n_out_dev=v["n_out_dev"])
             if self.concat:
                 ops.copy_rows_pad(x, B, slf, n_dev=v["n_out_dev"])
-            rscale, new_hist = None, None
         elif self.mode == "cv":
             ops.cv_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], B, x, self.history, nb,
-                               self_out=slf, n_out_dev=v["n_out_dev"])
-            if probe:
-                probe[0].record()
-            ops.full_history_mean(v["field"], v["rowptr_f"], B, v["adj_p"], v["adj_i"], v["adj_w"], self.history,
-                                  nb, n_out_dev=v["n_out_dev"])
-            if probe:
-                probe[1].record()
-            rscale, new_hist = None, x
+                               self_out=slf, n_out_dev=v["n_out_dev"], accumulate=True)
+            new_hist = x
         else:
             mu = self.x0[:, H:2 * H]
-            nb_mu = self.out_mu[:, H:] if self.concat else self.out_mu
             ops.cvd_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], v["scales"], B, x, mu,
                                 self.history, nb, nb_mu, self_h=slf,
-                                self_mu=self.out_mu[:, :H] if self.concat else None, n_out_dev=v["n_out_dev"])
-            if probe:
-                probe[0].record()
-            ops.full_history_mean(v["field"], v["rowptr_f"], B, v["adj_p"], v["adj_i"], v["adj_w"], self.history,
-                                  nb_mu, nb, n_out_dev=v["n_out_dev"])
-            if probe:
-                probe[1].record()
-            rscale, new_hist = v["scales"], mu
-        # backward of the aggregate: dX = adj^T (dZ_nb * scale) (+ dZ_self on the first B rows)
-        d_nb = self.d_out[:, H:] if self.concat else self.d_out
-        if self.concat:
-            ops.copy_rows_pad(self.d_out[:, :H], B, self.dx, n_dev=v["n_out_dev"])
-        else:
-            ops.copy_rows_pad(None, 0, self.dx)
-        ops.spmm_csr_bwd(v["rowptr_s"], v["edg_t"], v["edg_w"], d_nb, self.dx, B, rscale=rscale,
-                         n_out_dev=v["n_out_dev"])
-        # history write-back after the forward read (models.py:186-194)
+                                self_mu=self.out_mu[:, :H] if self.concat else None, n_out_dev=v["n_out_dev"],
+                                accumulate=True)
+            new_hist = mu
+
+        # join, then the history write-back (after every forward read of history, models.py:186-194)
+        if ev_b is not None:
+            main.wait_event(ev_b)
+        main.wait_event(ev_c)
         if new_hist is not None:
             ops.history_update(self.history, v["field"], new_hist, n_dev=v["n_in_dev"])
 
@@ -139,7 +176,7 @@ class HotPathStep:
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=self.dev)
-        self.sampler.use_stream(side)
+        self.sampler.use_stream(side)      # outside the capture: set_stream synchronises the old stream
         with torch.cuda.graph(g, stream=side):
             self._pass()
         self.graph = g

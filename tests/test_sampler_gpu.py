@@ -22,7 +22,18 @@ def make(g, cv, importance, seed, L=2):
     return s
 
 
-def test_golden_cases_bit_exact(sampler_golden):
+@pytest.fixture(params=["fused", "general"])
+def sampler_path(request, monkeypatch):
+    """libsgcn_b200 picks the single-CTA fused expand for small batches; SGCN_NO_FUSED_SAMPLER=1
+    forces the general multi-kernel path so that both are held to the same bit-exact bar."""
+    if request.param == "general":
+        monkeypatch.setenv("SGCN_NO_FUSED_SAMPLER", "1")
+    else:
+        monkeypatch.delenv("SGCN_NO_FUSED_SAMPLER", raising=False)
+    return request.param
+
+
+def test_golden_cases_bit_exact(sampler_golden, sampler_path):
     for name, case in sampler_golden.items():
         g = graph_from_tag(case["graph"])
         s = make(g, case["cv"], case["importance"], case["seed"], L=len(case["degrees"]))
@@ -40,7 +51,7 @@ def test_golden_cases_bit_exact(sampler_golden):
 
 
 @pytest.mark.parametrize("cv,importance", [(False, False), (True, False), (False, True)])
-def test_fresh_graphs_vs_oracle_many_batches(cv, importance):
+def test_fresh_graphs_vs_oracle_many_batches(cv, importance, sampler_path):
     for gseed in range(3):
         n = 400 + 300 * gseed
         g = random_graph(n, 8 + 4 * gseed, 500 + gseed)
@@ -62,7 +73,7 @@ def test_fresh_graphs_vs_oracle_many_batches(cv, importance):
         s.close()
 
 
-def test_mt19937_stream_and_rng_checkpoint():
+def test_mt19937_stream_and_rng_checkpoint(sampler_path):
     """std::mt19937 on device: 3000 draws across block boundaries, and get/set_rng round trip."""
     g = random_graph(2000, 30, 3)
     s = make(g, False, False, 12345)
@@ -87,7 +98,7 @@ def test_mt19937_stream_and_rng_checkpoint():
     assert 0 <= pos <= 624 and st.shape == (624,)
 
 
-def test_edge_cases():
+def test_edge_cases(sampler_path):
     from stochastic_gcn_b200._lib import SgcnError
     g = tree11()
     s = make(g, True, False, 0)
@@ -154,7 +165,8 @@ def test_pyscheduler_feed_dict_matches_reference_format():
                     assert np.array_equal(np.asarray(fa[k]), np.asarray(fb[k])), k
 
 
-def test_large_graph_properties():
+@pytest.mark.parametrize("batch", [4096, 20000])
+def test_large_graph_properties(batch):
     """Full-size-ish properties that do not need the oracle: old field is the prefix, sampled
     targets are real neighbours, no duplicates per row, weights = row weight * deg/take, the row
     multiset is preserved by the in-place permutation."""
@@ -165,7 +177,7 @@ def test_large_graph_properties():
     s = DeviceSampler(g.data, g.indices, g.indptr, cv=True)
     s.seed(1)
     before_sorted = torch.sort(g.indices.long() + g.row_ids().long() * g.n)[0]
-    ids = torch.randperm(g.n, device="cuda")[:4096].to(torch.int32)
+    ids = torch.randperm(g.n, device="cuda")[:batch].to(torch.int32)
     for _ in range(3):
         s.start_batch(ids)
         s.expand(2)
