@@ -211,14 +211,22 @@ spmm_coo_kernel(const int2* __restrict__ idx2, const float* __restrict__ vals, i
 // Position p of the concatenated neighbour list belongs to output row r = upper_bound(rowptr_f, p)-1
 // and is entry adj[adj_p[nodes[r]] + p - rowptr_f[r]] of the sampler's CSR.
 //
-// Each warp owns one contiguous span of positions (nnz_f / #warps, rounded to 32).  Per 32
-// positions: the lanes fetch (row, column id, weight) in parallel -- row pointers come from a
-// shared-memory copy staged once per CTA, column ids / weights are one coalesced load each and
-// are prefetched one sub-chunk ahead -- then the warp walks the 32 edges with UN independent
-// 16-byte-per-lane history-row loads in flight.  A sub-chunk that lies inside one output row (the
-// common case: rows average hundreds of entries) takes a branch-free path; partial sums stay in
-// registers across the span and leave through one 128-bit RED per lane per row segment.
+// Each warp owns one contiguous span of positions (nnz_f / #warps, rounded to 32) and walks it in
+// macro-chunks of 64:
+//   stage   the lanes resolve (row, column id, weight) for 64 positions in parallel -- row pointers
+//           come from a shared-memory copy made once per CTA, column ids / weights are coalesced
+//           loads -- and park {history-row offset, weight, row} in shared memory;
+//   stream  the 64 edges are consumed in groups of UN with TWO register buffers: the loads of group
+//           i+1 are in flight while group i is multiplied in, so every warp keeps UN..2UN
+//           independent 16-byte-per-lane row loads outstanding (the kernel is latency-bound, not
+//           issue-bound: bytes in flight per SM are what buys HBM bandwidth);
+//   reduce  per-edge operands are warp-uniform shared-memory broadcasts (no shuffles, no
+//           divergence bookkeeping); a group that lies inside one output row takes a branch-free
+//           path; partial sums stay in registers across the span and leave through one 128-bit RED
+//           per lane per row segment.
 constexpr int kFullStageRows = 4096;   // row pointers are staged in shared memory up to this many rows
+constexpr int kFullMacro = 64;         // positions staged per warp per macro-chunk
+constexpr int kFullWarps = kAggThreads / 32;
 
 struct FullArgs {
     const int32_t* nodes; const int32_t* rowptr_f; int n_out; const int32_t* n_out_dev;
@@ -242,14 +250,17 @@ __device__ __forceinline__ void full_flush(const FullArgs& a, int row, int gl, V
 }
 
 template <typename V, int LPR, int VPL>
-__global__ void __launch_bounds__(kAggThreads)
+__global__ void __launch_bounds__(kAggThreads, 2)
 full_mean_kernel(const FullArgs a) {
     using T = VT<V>;
     constexpr int G = 32 / LPR;                                  // groups per warp
-    constexpr int UN = (VPL >= 4) ? 2 : ((VPL == 2) ? 4 : 8);    // row loads in flight per group
-    constexpr int US = 2;                                        // same, on the rare multi-row path
+    constexpr int UN = (VPL >= 8) ? 1 : ((VPL == 4) ? 2 : ((VPL == 2) ? 4 : 8));   // row loads per buffer
+    constexpr int STEP = G * UN;                                 // positions per group-iteration
     __shared__ int32_t s_ptr[kFullStageRows + 1];                // rowptr_f
     __shared__ int32_t s_base[kFullStageRows];                   // adj_p[nodes[r]] - rowptr_f[r]
+    __shared__ int64_t s_off[kFullWarps][kFullMacro];            // adj_i * ld_h (element offset of the row)
+    __shared__ float s_w[kFullWarps][kFullMacro];
+    __shared__ int32_t s_r[kFullWarps][kFullMacro];
     const int n_out = dev_count(a.n_out_dev, a.n_out);
     if (n_out <= 0) return;
     const bool staged = n_out <= kFullStageRows;
@@ -261,7 +272,7 @@ full_mean_kernel(const FullArgs a) {
     }
     const int32_t* ptr = staged ? s_ptr : a.rowptr_f;
     const int nnz = ptr[n_out];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gl = lane % LPR, g = lane / LPR;
     const int warp = (blockIdx.x * kAggThreads + threadIdx.x) >> 5;
     const int warps = (gridDim.x * kAggThreads) >> 5;
@@ -269,98 +280,99 @@ full_mean_kernel(const FullArgs a) {
     const int p0 = warp * span;
     const int p1 = min(p0 + span, nnz);
     if (p0 >= p1) return;
+    int64_t* my_off = s_off[wib];
+    float* my_w = s_w[wib];
+    int32_t* my_r = s_r[wib];
 
-    // lane-parallel metadata of 32 consecutive positions starting at pb
-    auto load_meta = [&](int pb, int& r, int& c, float& w) {
-        const int p = pb + lane;
-        r = -1; c = 0; w = 0.f;
-        if (p < p1) {
-            int lo = 0, hi = n_out;                               // last r with ptr[r] <= p
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (ptr[mid] <= p) lo = mid; else hi = mid;
-            }
-            r = lo;
-            const int q = staged ? (s_base[lo] + p)
-                                 : (__ldg(a.adj_p + __ldg(a.nodes + lo)) + (p - ptr[lo]));
-            c = __ldg(a.adj_i + q);
-            w = __ldg(a.adj_w + q);
-        }
-    };
-
+    bool ok[VPL];
+    const float* hist_lane[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int off = (gl + k * LPR) * T::W;
+        ok[k] = off < a.D;
+        hist_lane[k] = a.hist + (ok[k] ? off : 0);
+    }
     V acc[VPL];
 #pragma unroll
     for (int k = 0; k < VPL; ++k) acc[k] = T::zero();
     int cur = -1;                                                 // row this group is accumulating
-    int r_n, c_n;
-    float w_n;
-    load_meta(p0, r_n, c_n, w_n);
-    for (int pb = p0; pb < p1; pb += 32) {
-        const int r = r_n, c = c_n;
-        const float w = w_n;
-        if (pb + 32 < p1) load_meta(pb + 32, r_n, c_n, w_n);      // prefetch the next sub-chunk
-        const int cnt = min(32, p1 - pb);
-        const int r_first = __shfl_sync(0xffffffffu, r, 0);
-        const int r_last = __shfl_sync(0xffffffffu, r, cnt - 1);
-        if (r_first == r_last) {
-            // the whole sub-chunk feeds one output row: no per-edge row tracking
-            if (r_first != cur) {
-                if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
-                cur = r_first;
+
+    for (int pm = p0; pm < p1; pm += kFullMacro) {
+        // ---- stage: metadata of up to 64 positions, two per lane ----
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < kFullMacro / 32; ++t) {
+            const int p = pm + t * 32 + lane;
+            int r = -1;
+            int64_t off = 0;
+            float w = 0.f;
+            if (p < p1) {
+                int lo = 0, hi = n_out;                           // last r with ptr[r] <= p
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (ptr[mid] <= p) lo = mid; else hi = mid;
+                }
+                r = lo;
+                const int q = staged ? (s_base[lo] + p)
+                                     : (__ldg(a.adj_p + __ldg(a.nodes + lo)) + (p - ptr[lo]));
+                off = (int64_t)__ldg(a.adj_i + q) * a.ld_h;
+                w = __ldg(a.adj_w + q);
             }
-            for (int j0 = 0; j0 < cnt; j0 += G * UN) {
-                V v[UN][VPL];
-                float wj[UN];
+            my_off[t * 32 + lane] = off;
+            my_w[t * 32 + lane] = w;
+            my_r[t * 32 + lane] = r;
+        }
+        __syncwarp();
+        const int cnt = min(kFullMacro, p1 - pm);
+        const int ng = (cnt + STEP - 1) / STEP;
+
+        auto issue = [&](V (&buf)[UN][VPL], int gi) {
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int64_t off = my_off[gi * STEP + u * G + g];
+#pragma unroll
+                for (int k = 0; k < VPL; ++k)
+                    buf[u][k] = ok[k] ? T::ld_stream(hist_lane[k] + off) : T::zero();
+            }
+        };
+        auto consume = [&](V (&buf)[UN][VPL], int gi) {
+            const int jf = gi * STEP + g;
+            const int rf = my_r[jf], rl = my_r[jf + (UN - 1) * G];
+            if (rf == rl && rf >= 0) {                            // whole group inside one output row
+                if (rf != cur) {
+                    if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
+                    cur = rf;
+                }
 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
-                    const int j = j0 + u * G + g;
-                    const int jj = min(j, 31);
-                    const int cj = __shfl_sync(0xffffffffu, c, jj);
-                    wj[u] = (j < cnt) ? __shfl_sync(0xffffffffu, w, jj) : 0.f;   // w = 0 beyond the end
-                    if (j >= cnt) wj[u] = 0.f;
+                    const float w = my_w[jf + u * G];
 #pragma unroll
-                    for (int k = 0; k < VPL; ++k) {
-                        const int off = (gl + k * LPR) * T::W;
-                        v[u][k] = (off < a.D) ? T::ld_stream(a.hist + (int64_t)cj * a.ld_h + off) : T::zero();
-                    }
+                    for (int k = 0; k < VPL; ++k) T::fma(acc[k], w, buf[u][k]);
                 }
+            } else {
 #pragma unroll
-                for (int u = 0; u < UN; ++u)
-#pragma unroll
-                    for (int k = 0; k < VPL; ++k) T::fma(acc[k], wj[u], v[u][k]);
-            }
-        } else {
-            for (int j0 = 0; j0 < cnt; j0 += G * US) {
-                V v[US][VPL];
-                int rj[US];
-                float wj[US];
-#pragma unroll
-                for (int u = 0; u < US; ++u) {
-                    const int j = j0 + u * G + g;
-                    const int jj = min(j, 31);
-                    const int cj = __shfl_sync(0xffffffffu, c, jj);
-                    wj[u] = __shfl_sync(0xffffffffu, w, jj);
-                    rj[u] = __shfl_sync(0xffffffffu, r, jj);
-                    if (j >= cnt) rj[u] = -1;
-#pragma unroll
-                    for (int k = 0; k < VPL; ++k) {
-                        const int off = (gl + k * LPR) * T::W;
-                        v[u][k] = (rj[u] >= 0 && off < a.D)
-                                      ? T::ld_stream(a.hist + (int64_t)cj * a.ld_h + off)
-                                      : T::zero();
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < US; ++u) {
-                    if (rj[u] < 0) continue;
-                    if (rj[u] != cur) {
+                for (int u = 0; u < UN; ++u) {
+                    const int r = my_r[jf + u * G];
+                    if (r < 0) continue;
+                    if (r != cur) {
                         if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
-                        cur = rj[u];
+                        cur = r;
                     }
+                    const float w = my_w[jf + u * G];
 #pragma unroll
-                    for (int k = 0; k < VPL; ++k) T::fma(acc[k], wj[u], v[u][k]);
+                    for (int k = 0; k < VPL; ++k) T::fma(acc[k], w, buf[u][k]);
                 }
             }
+        };
+
+        // ---- stream: two register buffers, loads of group i+1 in flight while group i is consumed ----
+        V bufA[UN][VPL], bufB[UN][VPL];
+        issue(bufA, 0);
+        for (int gi = 0; gi < ng; gi += 2) {
+            if (gi + 1 < ng) issue(bufB, gi + 1);
+            consume(bufA, gi);
+            if (gi + 2 < ng) issue(bufA, gi + 2);
+            if (gi + 1 < ng) consume(bufB, gi + 1);
         }
     }
     if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
@@ -556,8 +568,17 @@ int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_
     for (int c0 = 0; c0 < D; c0 += sh.tile) {
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist + c0, ld_h,
                    std::min(sh.tile, D - c0), y0 + c0, ld_y0, y1 ? y1 + c0 : nullptr, ld_y1};
-        const int grid = kNumSMs * 4;    // persistent, edge-strided: 4736 warps
-#define CALL(V, L, P) full_mean_kernel<V, L, P><<<grid, kAggThreads, 0, st>>>(a)
+        // one resident wave: every CTA the SMs can hold at once, spans cut accordingly
+#define CALL(V, L, P)                                                                        \
+    do {                                                                                     \
+        static int per_sm = 0;                                                               \
+        if (per_sm == 0) {                                                                   \
+            SGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                         \
+                &per_sm, full_mean_kernel<V, L, P>, kAggThreads, 0));                        \
+            if (per_sm < 1) per_sm = 1;                                                      \
+        }                                                                                    \
+        full_mean_kernel<V, L, P><<<kNumSMs * per_sm, kAggThreads, 0, st>>>(a);              \
+    } while (0)
         SGCN_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
         SGCN_LAUNCHED();

@@ -509,19 +509,22 @@ __global__ void set_meta_kernel(int32_t* meta, int n) {
 // At training batch sizes (B = 512, degree <= 2) every pass above is a few hundred threads of
 // work and the chain is pure launch + dependent-load latency.  One CTA of 1024 threads runs the
 // whole expand with block barriers in place of kernel boundaries: rows -> scans -> MT19937 draws
-// (into shared memory) -> Fisher-Yates -> first-occurrence numbering -> slot reset.  Values that
-// other threads update with L2 atomics (slot[]) are read with ld.global.cg so that a stale L1 line
-// is never observed inside the kernel.
+// (into shared memory) -> Fisher-Yates -> first-occurrence numbering.  The visited[] table of the
+// reference becomes an open-addressing hash table in SHARED memory (node id -> smallest position
+// that claimed it), so the numbering needs no global round-trips and leaves nothing to reset; the
+// only global traffic on the critical path is ids -> row pointers -> the touched row entries.
 constexpr int kFusedThreads = 1024;
 constexpr int kFusedMaxRows = 4096;
 constexpr int kFusedMaxEdges = 8192;
+constexpr int kFusedHashMax = 16384;                       // >= (rows + edges) / 0.75
 constexpr size_t kFusedSmemBytes =
-    sizeof(int32_t) * ((size_t)kFusedMaxRows + 1 + 2 * (size_t)kFusedMaxEdges + kMtN + 64);
+    sizeof(int32_t) * ((size_t)kFusedMaxRows + 1 + 2 * (size_t)kFusedMaxEdges + 2 * (size_t)kFusedHashMax +
+                       kMtN + 64);
 
 struct FusedArgs {
     const int32_t* field_in; const int32_t* n_ptr; int n_host, nb, sb;
     const int32_t* adj_p; int32_t* adj_i; float* adj_w; int N, degree, cv;
-    uint32_t* engine; int32_t* slot;
+    uint32_t* engine;
     int32_t* field; int32_t* rowptr_s; int32_t* rowptr_f; int32_t* edg_s; int32_t* edg_t;
     int32_t* tgt; float* edg_w; float* medg_w; float* scales; int32_t* meta;
 };
@@ -554,27 +557,47 @@ __device__ __forceinline__ int block_scan_excl_1024(int v, int* total, int* s_wa
     return excl;
 }
 
+// find-or-insert `node` in the shared-memory table; returns its slot
+__device__ __forceinline__ int hash_claim(int32_t* keys, int mask, int shift, int node) {
+    unsigned h = ((unsigned)node * 2654435761u) >> shift;
+    for (;;) {
+        const int old = atomicCAS(keys + h, -1, node);
+        if (old == -1 || old == node) return (int)h;
+        h = (h + 1) & (unsigned)mask;
+    }
+}
+
 __global__ void __launch_bounds__(kFusedThreads, 1)
 expand_fused_kernel(const FusedArgs a) {
     extern __shared__ int32_t smem[];
     int32_t* s_rowptr = smem;                                  // kFusedMaxRows + 1
-    int32_t* s_tgt = s_rowptr + kFusedMaxRows + 1;             // kFusedMaxEdges
-    uint32_t* s_u = (uint32_t*)(s_tgt + kFusedMaxEdges);       // draws, later the first-occurrence ranks
-    uint32_t* s_mt = s_u + kFusedMaxEdges;                     // kMtN
+    int32_t* s_eslot = s_rowptr + kFusedMaxRows + 1;           // hash slot of each edge's target
+    uint32_t* s_u = (uint32_t*)(s_eslot + kFusedMaxEdges);     // draws, later the first-occurrence ranks
+    int32_t* s_keys = (int32_t*)(s_u + kFusedMaxEdges);        // node id or -1
+    int32_t* s_vals = s_keys + kFusedHashMax;                  // smallest claiming position
+    uint32_t* s_mt = (uint32_t*)(s_vals + kFusedHashMax);      // kMtN
     int32_t* s_warp = (int32_t*)(s_mt + kMtN);                 // 33
     __shared__ int s_status, s_pos;
     const int tid = threadIdx.x;
 
     const int n_raw = a.n_ptr ? *a.n_ptr : a.n_host;
     const int n_out = min(n_raw, a.nb);
+    // table sized to >= 2x the entries it can receive (old field + one per sampled edge)
+    int hbits = 10;
+    while ((1 << hbits) < 2 * (n_out + a.sb) && (1 << hbits) < kFusedHashMax) ++hbits;
+    const int hsize = 1 << hbits, hmask = hsize - 1, hshift = 32 - hbits;
     if (tid == 0) {
         s_status = n_raw > a.nb ? ST_OVERFLOW : 0;
         s_pos = (int)a.engine[kMtN];
     }
     for (int i = tid; i < kMtN; i += kFusedThreads) s_mt[i] = a.engine[i];
+    for (int i = tid; i < hsize; i += kFusedThreads) {
+        s_keys[i] = -1;
+        s_vals[i] = kUnseen;
+    }
     __syncthreads();
 
-    // rows + both prefix sums, 1024 rows per sweep with a carry
+    // rows + both prefix sums, 1024 rows per sweep with a carry; old field -> table (value = position)
     int carry_s = 0, carry_f = 0;
     for (int base = 0; base < n_out; base += kFusedThreads) {
         const int i = base + tid;
@@ -591,7 +614,8 @@ expand_fused_kernel(const FusedArgs a) {
                 take = min(d, a.degree);
                 const float scale = (d == 0) ? 1.f : __fdiv_rn((float)d, (float)take);
                 a.scales[i] = (float)(1.0 / (double)__fsqrt_rn(scale));
-                a.slot[node] = i;
+                const int h = hash_claim(s_keys, hmask, hshift, node);
+                if (atomicMin(s_vals + h, i) != kUnseen) atomicOr(&s_status, ST_DUPLICATE);
             }
         }
         int tot_s, tot_f;
@@ -642,23 +666,70 @@ expand_fused_kernel(const FusedArgs a) {
         int32_t* rc = a.adj_i + base;
         float* rw = a.adj_w + base;
         const float scale = __fdiv_rn((float)d, (float)take);
-        for (int k = 0; k < take; ++k) {
+        auto draw_index = [&](int k) {
+            // idx = min((int)(it + num_remaining * u01(generator)), adj_range-1)  (scheduler.cpp:141-143)
             const float u = mt_canonical(s_u[e0 + k]);
-            const float where = __fadd_rn((float)k, __fmul_rn((float)(d - k), u));
-            int j = (int)where;
-            if (j > d - 1) j = d - 1;
-            const int ck = rc[k], cj = rc[j];
-            const float wk = rw[k], wj = rw[j];
-            rc[k] = cj; rc[j] = ck;
-            rw[k] = wj; rw[j] = wk;
-            const float w = __fmul_rn(wj, scale);
+            const int j = (int)__fadd_rn((float)k, __fmul_rn((float)(d - k), u));
+            return min(j, d - 1);
+        };
+        auto emit = [&](int k, int t, float wv) {
+            const float w = __fmul_rn(wv, scale);
             const int e = e0 + k;
             a.edg_s[e] = i;
-            a.tgt[e] = cj;
-            s_tgt[e] = cj;
+            a.tgt[e] = t;
             a.edg_w[e] = w;
-            if (a.cv) a.medg_w[e] = __fmul_rn(wj, w);
-            if (__ldcg(a.slot + cj) >= n_out) atomicMin(a.slot + cj, n_out + e);
+            if (a.cv) a.medg_w[e] = __fmul_rn(wv, w);
+            const int h = hash_claim(s_keys, hmask, hshift, t);
+            atomicMin(s_vals + h, n_out + e);
+            s_eslot[e] = h;
+        };
+        if (take <= 2) {
+            // every touched position is known from the draws alone: fetch them all at once, replay
+            // the <= 2 swaps on the local copy, store once (one DRAM round trip instead of one per swap)
+            const int j0 = draw_index(0);
+            const int j1 = take == 2 ? draw_index(1) : j0;
+            int pos[4] = {0, j0, take == 2 ? 1 : 0, j1};
+            int cv4[4];
+            float wv4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                cv4[q] = rc[pos[q]];
+                wv4[q] = rw[pos[q]];
+            }
+            auto rd = [&](int x, int& c, float& w) {
+#pragma unroll
+                for (int q = 3; q >= 0; --q)
+                    if (pos[q] == x) { c = cv4[q]; w = wv4[q]; }
+            };
+            auto wr = [&](int x, int c, float w) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (pos[q] == x) { cv4[q] = c; wv4[q] = w; }
+            };
+            for (int k = 0; k < take; ++k) {
+                const int j = k == 0 ? j0 : j1;
+                int ck = 0, cj = 0;
+                float wk = 0.f, wj = 0.f;
+                rd(k, ck, wk);
+                rd(j, cj, wj);
+                wr(k, cj, wj);
+                wr(j, ck, wk);
+                emit(k, cj, wj);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                rc[pos[q]] = cv4[q];
+                rw[pos[q]] = wv4[q];
+            }
+        } else {
+            for (int k = 0; k < take; ++k) {
+                const int j = draw_index(k);
+                const int ck = rc[k], cj = rc[j];
+                const float wk = rw[k], wj = rw[j];
+                rc[k] = cj; rc[j] = ck;
+                rw[k] = wj; rw[j] = wk;
+                emit(k, cj, wj);
+            }
         }
     }
     __syncthreads();
@@ -668,7 +739,7 @@ expand_fused_kernel(const FusedArgs a) {
     int n_new = 0;
     for (int base = 0; base < nnz; base += kFusedThreads) {
         const int e = base + tid;
-        const int f = (e < nnz && __ldcg(a.slot + s_tgt[e]) == n_out + e) ? 1 : 0;
+        const int f = (e < nnz && s_vals[s_eslot[e]] == n_out + e) ? 1 : 0;
         int tot;
         const int ex = block_scan_excl_1024(f, &tot, s_warp);
         if (e < nnz) s_rank[e] = n_new + ex;
@@ -676,28 +747,17 @@ expand_fused_kernel(const FusedArgs a) {
     }
     __syncthreads();
     for (int e = tid; e < nnz; e += kFusedThreads) {
-        const int t = s_tgt[e];
-        const int sl = __ldcg(a.slot + t);
+        const int h = s_eslot[e];
+        const int sl = s_vals[h];
         if (sl < n_out) {
             a.edg_t[e] = sl;
         } else {
             const int e_first = sl - n_out;
             const int pos = n_out + s_rank[e_first];
             a.edg_t[e] = pos;
-            if (e_first == e) a.field[pos] = t;
+            if (e_first == e) a.field[pos] = s_keys[h];
         }
     }
-    // duplicate batch ids leave slot[node] != position for at least one of the copies
-    for (int j = tid; j < n_out; j += kFusedThreads) {
-        const int node = a.field_in[j];
-        if (node >= 0 && node < a.N && __ldcg(a.slot + node) != j) atomicOr(&s_status, ST_DUPLICATE);
-    }
-    __syncthreads();
-    for (int j = tid; j < n_out; j += kFusedThreads) {
-        const int node = a.field_in[j];
-        if (node >= 0 && node < a.N) a.slot[node] = kUnseen;
-    }
-    for (int e = tid; e < nnz; e += kFusedThreads) a.slot[s_tgt[e]] = kUnseen;
     if (tid == 0) {
         a.meta[M_NOUT] = n_out;
         a.meta[M_NIN] = n_out + n_new;
@@ -823,7 +883,7 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
             attr_set = true;
         }
         FusedArgs fa{field_in, n_ptr, nb, nb, (int)sb, s->adj_p, s->adj_i, s->adj_w, s->N, degree,
-                     s->cv ? 1 : 0, s->engine, s->slot, lv.field.as<int32_t>(), lv.rowptr_s.as<int32_t>(),
+                     s->cv ? 1 : 0, s->engine, lv.field.as<int32_t>(), lv.rowptr_s.as<int32_t>(),
                      lv.rowptr_f.as<int32_t>(), lv.edg_s.as<int32_t>(), lv.edg_t.as<int32_t>(),
                      lv.tgt.as<int32_t>(), lv.edg_w.as<float>(), lv.medg_w.as<float>(),
                      lv.scales.as<float>(), meta};
