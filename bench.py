@@ -266,7 +266,7 @@ def run_ours(args, w):
     if world > 1:
         from stochastic_gcn_b200.sharding import ShardedHotPathStep
         step = ShardedHotPathStep(g, feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"],
-                                  seed=args.seed + rank, rank=rank, world=world)
+                                  seed=args.seed + rank, rank=rank, world=world, transport=args.transport)
         lo, hi = step.lo, step.hi
     else:
         step = HotPathStep(g, feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"], seed=args.seed)
@@ -337,7 +337,8 @@ def run_ours(args, w):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, w, {"nodes": g.n, "stored_edges": g.nnz,
                                                 "last_step_sizes": sizes_last,
-                                                "parallelism": "row-range shards x%d" % world if world > 1 else "single GPU"}),
+                                                "parallelism": ("row-range shards x%d, history replicas synced by %s write-back exchange"
+                                                                % (world, args.transport)) if world > 1 else "single GPU"}),
             "sampled_edges_per_s": s_edges / (ms * 1e-3),
             "step_hbm": {"algorithmic_bytes_per_step": alg["total"],
                          "achieved_gbs": alg["total"] * world / (ms / args.steps * 1e-3) / 1e9 / world,
@@ -375,6 +376,8 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU write-back exchange: NVLink peer stores (default) or NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = WORKLOADS[args.workload]

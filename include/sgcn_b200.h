@@ -211,6 +211,48 @@ int sgcn_history_update(float* hist, int64_t ld_h, const int32_t* idx, int32_t n
 int sgcn_copy_rows_pad(const float* src, int64_t ld_src, int32_t n, const int32_t* n_dev,
                        int32_t n_total, int32_t D, float* dst, int64_t ld_dst, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU write-back exchange (no counterpart in the single-process reference).
+ * Every rank holds a full history replica; per step each rank publishes the rows it refreshed
+ * (tf.scatter_update's operands, gcn/models.py:160-166) as a payload
+ *     int32 header[4] = {count, step, 0, 0} | int32 ids[n_bound] (16-byte padded) | float rows[n_bound*D]
+ * and every rank applies all payloads.  When several ranks refreshed the same node in one step the
+ * highest (rank, position) wins as a whole row (deterministic).
+ * ------------------------------------------------------------------------------------------ */
+int64_t sgcn_wb_payload_bytes(int32_t n_bound, int32_t D);
+/* pack field[0..*n_dev) and rows into n_dst destination buffers (own send buffer and / or the
+ * peers' NVLink-mapped receive slots): dst is a HOST array of n_dst device pointers */
+int sgcn_wb_pack(const int32_t* field, const int32_t* n_dev, int32_t n_bound, const float* rows,
+                 int64_t ld_rows, int32_t D, void* const* dst /*HOST*/, int32_t n_dst, int32_t step,
+                 void* stream);
+/* Peer transport (NVLink-mapped memory, no collective launch; capturable in a CUDA graph).
+ * Every rank owns, in cudaIpc-exported memory: two receive areas (even / odd epochs) of `world`
+ * slots, a flag array int32[world] and a device epoch counter.
+ * push: packs this rank's payload into slot `my_rank` of the (epoch+1)-parity receive area of EVERY
+ * rank (dst_even / dst_odd: HOST arrays of n_dst device pointers, own slot included), then advances
+ * *epoch and publishes it as flags[my_rank] in every rank (peer_flags: HOST array of n_dst pointers
+ * to the ranks' flag arrays).  Two areas suffice: a rank can only push epoch e+1 after every rank
+ * pushed e, i.e. after every rank finished applying e-1. */
+int sgcn_wb_push(const int32_t* field, const int32_t* n_dev, int32_t n_bound, const float* rows,
+                 int64_t ld_rows, int32_t D, void* const* dst_even /*HOST*/, void* const* dst_odd /*HOST*/,
+                 int32_t n_dst, void* const* peer_flags /*HOST*/, int32_t my_rank, int32_t* epoch,
+                 void* stream);
+/* wait_apply: spins (bounded, ~2 s: sets *timeout_flag != 0 instead of hanging) until this rank's
+ * flags[0..world) >= *epoch, then merges the `world` payloads of the epoch's receive area */
+int sgcn_wb_wait_apply(float* hist, int64_t ld_h, int32_t D, const void* recv_even, const void* recv_odd,
+                       int64_t slot_bytes, int32_t world, int32_t n_bound, int32_t* owner,
+                       const int32_t* flags, const int32_t* epoch, int32_t* timeout_flag, void* stream);
+/* merge `world` payloads (slot r at gathered + r*slot_bytes) into hist; owner is an int32[N]
+ * scratch table that must hold -1 everywhere on entry and does again on exit */
+int sgcn_wb_apply(float* hist, int64_t ld_h, int32_t D, const void* gathered, int64_t slot_bytes,
+                  int32_t world, int32_t n_bound, int32_t* owner, void* stream);
+/* cudaMalloc'd buffers that other processes can map over NVLink (cudaIpc*): handle64 = 64 bytes */
+int sgcn_ipc_alloc(void** ptr /*HOST out*/, int64_t bytes, int32_t zero);
+int sgcn_ipc_free(void* ptr);
+int sgcn_ipc_export(void* ptr, void* handle64 /*HOST out*/);
+int sgcn_ipc_open(const void* handle64 /*HOST*/, void** ptr /*HOST out*/);
+int sgcn_ipc_close(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

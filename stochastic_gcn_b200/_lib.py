@@ -60,6 +60,17 @@ SIGNATURES = {
                                     _i64, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
     "sgcn_history_update": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _i32, _vp]),
     "sgcn_copy_rows_pad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "sgcn_wb_payload_bytes": (_i64, [_i32, _i32]),
+    "sgcn_wb_pack": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), _i32, _i32, _vp]),
+    "sgcn_wb_push": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), C.POINTER(_vp), _i32,
+                            C.POINTER(_vp), _i32, _vp, _vp]),
+    "sgcn_wb_wait_apply": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "sgcn_wb_apply": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "sgcn_ipc_alloc": (_i32, [C.POINTER(_vp), _i64, _i32]),
+    "sgcn_ipc_free": (_i32, [_vp]),
+    "sgcn_ipc_export": (_i32, [_vp, _vp]),
+    "sgcn_ipc_open": (_i32, [_vp, C.POINTER(_vp)]),
+    "sgcn_ipc_close": (_i32, [_vp]),
 }
 
 _lib = None

@@ -519,11 +519,21 @@ constexpr int kFusedMaxEdges = 8192;
 constexpr int kFusedHashMax = 16384;                       // >= (rows + edges) / 0.75
 constexpr size_t kFusedSmemBytes =
     sizeof(int32_t) * ((size_t)kFusedMaxRows + 1 + 2 * (size_t)kFusedMaxEdges + 2 * (size_t)kFusedHashMax +
-                       kMtN + 64);
+                       kMtN + 64);   // worst case, the opt-in limit set on the kernel
+
+static int fused_hash_bits(int nb, int sb) {
+    int hbits = 10;   // table holds the old field + one entry per sampled edge at load <= 0.75
+    while ((1 << hbits) < 2 * (nb + sb) && (1 << hbits) < kFusedHashMax) ++hbits;
+    return hbits;
+}
+static size_t fused_smem_bytes(int nb, int sb, int hbits) {
+    return sizeof(int32_t) * ((size_t)nb + 1 + 2 * (size_t)sb + 2 * ((size_t)1 << hbits) + kMtN + 64);
+}
 
 struct FusedArgs {
     const int32_t* field_in; const int32_t* n_ptr; int n_host, nb, sb;
     const int32_t* adj_p; int32_t* adj_i; float* adj_w; int N, degree, cv;
+    int hbits;               // log2 of the shared-memory hash table size (>= 2 (nb + sb) entries)
     uint32_t* engine;
     int32_t* field; int32_t* rowptr_s; int32_t* rowptr_f; int32_t* edg_s; int32_t* edg_t;
     int32_t* tgt; float* edg_w; float* medg_w; float* scales; int32_t* meta;
@@ -570,22 +580,21 @@ __device__ __forceinline__ int hash_claim(int32_t* keys, int mask, int shift, in
 __global__ void __launch_bounds__(kFusedThreads, 1)
 expand_fused_kernel(const FusedArgs a) {
     extern __shared__ int32_t smem[];
-    int32_t* s_rowptr = smem;                                  // kFusedMaxRows + 1
-    int32_t* s_eslot = s_rowptr + kFusedMaxRows + 1;           // hash slot of each edge's target
-    uint32_t* s_u = (uint32_t*)(s_eslot + kFusedMaxEdges);     // draws, later the first-occurrence ranks
-    int32_t* s_keys = (int32_t*)(s_u + kFusedMaxEdges);        // node id or -1
-    int32_t* s_vals = s_keys + kFusedHashMax;                  // smallest claiming position
-    uint32_t* s_mt = (uint32_t*)(s_vals + kFusedHashMax);      // kMtN
+    // carved to the launch's own bounds (fused_smem_bytes): a 512 x 2 batch needs ~46 KB, not the
+    // 211 KB worst case, which keeps the SM's L1/shared carve-out where the neighbouring kernels want it
+    const int hsize = 1 << a.hbits, hmask = hsize - 1, hshift = 32 - a.hbits;
+    int32_t* s_rowptr = smem;                                  // nb + 1
+    int32_t* s_eslot = s_rowptr + a.nb + 1;                    // sb: hash slot of each edge's target
+    uint32_t* s_u = (uint32_t*)(s_eslot + a.sb);               // sb: draws, later the first-occurrence ranks
+    int32_t* s_keys = (int32_t*)(s_u + a.sb);                  // hsize: node id or -1
+    int32_t* s_vals = s_keys + hsize;                          // hsize: smallest claiming position
+    uint32_t* s_mt = (uint32_t*)(s_vals + hsize);              // kMtN
     int32_t* s_warp = (int32_t*)(s_mt + kMtN);                 // 33
     __shared__ int s_status, s_pos;
     const int tid = threadIdx.x;
 
     const int n_raw = a.n_ptr ? *a.n_ptr : a.n_host;
     const int n_out = min(n_raw, a.nb);
-    // table sized to >= 2x the entries it can receive (old field + one per sampled edge)
-    int hbits = 10;
-    while ((1 << hbits) < 2 * (n_out + a.sb) && (1 << hbits) < kFusedHashMax) ++hbits;
-    const int hsize = 1 << hbits, hmask = hsize - 1, hshift = 32 - hbits;
     if (tid == 0) {
         s_status = n_raw > a.nb ? ST_OVERFLOW : 0;
         s_pos = (int)a.engine[kMtN];
@@ -882,12 +891,13 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
                                            (int)kFusedSmemBytes));
             attr_set = true;
         }
+        const int hbits = fused_hash_bits(nb, (int)sb);
         FusedArgs fa{field_in, n_ptr, nb, nb, (int)sb, s->adj_p, s->adj_i, s->adj_w, s->N, degree,
-                     s->cv ? 1 : 0, s->engine, lv.field.as<int32_t>(), lv.rowptr_s.as<int32_t>(),
+                     s->cv ? 1 : 0, hbits, s->engine, lv.field.as<int32_t>(), lv.rowptr_s.as<int32_t>(),
                      lv.rowptr_f.as<int32_t>(), lv.edg_s.as<int32_t>(), lv.edg_t.as<int32_t>(),
                      lv.tgt.as<int32_t>(), lv.edg_w.as<float>(), lv.medg_w.as<float>(),
                      lv.scales.as<float>(), meta};
-        expand_fused_kernel<<<1, kFusedThreads, kFusedSmemBytes, st>>>(fa);
+        expand_fused_kernel<<<1, kFusedThreads, fused_smem_bytes(nb, (int)sb, hbits), st>>>(fa);
         SGCN_LAUNCHED();
         lv.full_materialized = false;
         if (s->cv && materialize) {

@@ -1,0 +1,226 @@
+"""Row-range sharding of the hot path across the GPUs of one node.
+
+One process per GPU (torchrun).  Rank r owns the contiguous node range [lo, hi): it holds only
+those rows of the adjacency (its sampler permutes only its own rows, so shards never conflict) and
+draws its batches from that range, which keeps ``expand`` local for the 2-layer + preprocessing
+models the reference trains (L = 1 after PP, gcn/train.py:86).  What a batch needs from OTHER
+shards are history rows and input-feature rows of its neighbours.
+
+B200-first layout decision: with 180 GB per GPU the history table (119 MB at Reddit shape, 1 GB
+at 2M nodes) and the PP feature matrix (1.1 GB / 4 GB) are REPLICATED, and the replicas are kept
+coherent by exchanging only what changes -- each rank's per-step write-back rows (<= B(1+d) rows,
+0.8 MB) -- instead of fetching the ~150k distinct neighbour rows (75 MB) a Reddit-shaped batch
+would need from remote shards every step.  Two transports for that exchange:
+
+  "nccl"  pack -> ``all_gather_into_tensor`` -> apply                     (baseline)
+  "peer"  pack straight into every peer's NVLink-mapped receive slot + flag, then wait + apply;
+          no collective launch, the whole step stays one CUDA graph       (default)
+
+Parity definition: rank r is bit-identical (sampled indices) to a reference ``Scheduler`` built on
+the same global CSR, seeded ``seed + r`` and fed rank r's batches; history semantics are those of
+R reference processes sharing one table with synchronous steps (every rank reads the pre-step
+table; write-backs are applied in rank order, the highest rank winning a contended row).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import check, ptr, stream_ptr
+from .graphs import CSRGraph
+from .step import HotPathStep
+
+HEADER_INTS = 4
+
+
+def row_range(n, rank, world):
+    """Contiguous node range of `rank`: [n*rank//world, n*(rank+1)//world)."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def restrict_rows(graph, lo, hi):
+    """The global CSR with every row outside [lo, hi) emptied (column ids stay global): what rank
+    [lo, hi) stores.  Row pointers keep all N+1 entries so node ids need no translation."""
+    indptr = graph.indptr.long()
+    a, b = int(indptr[lo]), int(indptr[hi])
+    local = (indptr.clamp(min=a, max=b) - a).to(torch.int32)
+    return CSRGraph(graph.data[a:b].contiguous(), graph.indices[a:b].contiguous(), local.contiguous(), graph.n)
+
+
+def payload_layout(n_bound, d):
+    """Byte offsets of one write-back payload (mirrors csrc/exchange.cu): (ids, rows, total)."""
+    ids = HEADER_INTS * 4
+    rows = ids + ((n_bound * 4 + 15) & ~15)
+    total = (rows + n_bound * d * 4 + 255) & ~255
+    return ids, rows, total
+
+
+def unpack_payload(buf, n_bound, d):
+    """(ids, rows) views of one payload held in a uint8 array (host-side helper for tests / debugging)."""
+    buf = np.asarray(buf, dtype=np.uint8)
+    ids_off, rows_off, _ = payload_layout(n_bound, d)
+    count = int(buf[:4].view(np.int32)[0])
+    ids = buf[ids_off:ids_off + 4 * count].view(np.int32)
+    rows = buf[rows_off:rows_off + 4 * count * d].view(np.float32).reshape(count, d)
+    return ids, rows
+
+
+def merge_payloads(history, payloads, n_bound, d):
+    """Host restatement of the apply rule (rank order, highest rank wins): used by the CPU tests."""
+    for buf in payloads:
+        ids, rows = unpack_payload(buf, n_bound, d)
+        history[ids] = rows
+    return history
+
+
+class _DevBytes:
+    def __init__(self, addr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "|u1", "data": (int(addr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerExchange:
+    """cudaIpc plumbing of the peer transport: one exported allocation per rank holding
+    [flags int32[64] | epoch, timeout int32[64] | receive area even | receive area odd]."""
+
+    def __init__(self, rank, world, slot_bytes, device):
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.lib, self.rank, self.world, self.slot = lib, rank, world, int(slot_bytes)
+        self.off_ctl, self.off_even = 256, 512
+        self.off_odd = self.off_even + world * self.slot
+        total = self.off_odd + world * self.slot
+        base = C.c_void_p()
+        check(lib.sgcn_ipc_alloc(C.byref(base), total, 1))
+        self.base, self.total = base.value, total
+        handle = (C.c_ubyte * 64)()
+        check(lib.sgcn_ipc_export(C.c_void_p(self.base), handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle))
+        self.peer_base = []
+        for r in range(world):
+            if r == rank:
+                self.peer_base.append(self.base)
+            else:
+                p = C.c_void_p()
+                h = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                check(lib.sgcn_ipc_open(h, C.byref(p)))
+                self.peer_base.append(p.value)
+        arr = lambda vals: (C.c_void_p * world)(*[C.c_void_p(v) for v in vals])
+        self.dst_even = arr([b + self.off_even + rank * self.slot for b in self.peer_base])
+        self.dst_odd = arr([b + self.off_odd + rank * self.slot for b in self.peer_base])
+        self.peer_flags = arr(self.peer_base)
+        self.flags = C.c_void_p(self.base)
+        self.epoch = C.c_void_p(self.base + self.off_ctl)
+        self.timeout = C.c_void_p(self.base + self.off_ctl + 4)
+        self.recv_even = C.c_void_p(self.base + self.off_even)
+        self.recv_odd = C.c_void_p(self.base + self.off_odd)
+        self._ctl = torch.as_tensor(_DevBytes(self.base, 512), device=device).view(torch.int32)
+        dist.barrier()
+
+    def control(self):
+        """(flags[world], epoch, timeout_flag) read back from the device (synchronises)."""
+        c = self._ctl.cpu()
+        return c[:self.world].tolist(), int(c[64]), int(c[65])
+
+    def close(self):
+        for r, b in enumerate(self.peer_base):
+            if r != self.rank and b:
+                self.lib.sgcn_ipc_close(C.c_void_p(b))
+        if self.base:
+            self.lib.sgcn_ipc_free(C.c_void_p(self.base))
+            self.base = 0
+
+
+class ShardedHotPathStep(HotPathStep):
+    """HotPathStep over one row-range shard, with the cross-GPU history write-back exchange."""
+
+    def __init__(self, graph, features, hidden, batch_size, degree, mode="cv", normalization="graphsage",
+                 seed=1, rank=0, world=1, transport="peer"):
+        if transport not in ("nccl", "peer"):
+            raise ValueError("transport must be 'nccl' or 'peer'")
+        self.rank, self.world, self.transport = int(rank), int(world), transport
+        self.lo, self.hi = row_range(graph.n, rank, world)
+        local = restrict_rows(graph, self.lo, self.hi)
+        super().__init__(local, features, hidden, batch_size, degree, mode=mode, normalization=normalization,
+                         seed=seed)
+        self._exchange = None
+        if self.mode == "ns":
+            return     # plain neighbour sampling keeps no history: shards are independent
+        lib = _lib.load()
+        nb = self.sampler_n_in_bound()
+        self.slot_bytes = int(lib.sgcn_wb_payload_bytes(nb, self.hidden))
+        self.wb_bound = nb
+        self.owner = torch.full((graph.n,), -1, dtype=torch.int32, device=self.dev)
+        if transport == "nccl":
+            self.send = torch.zeros(self.slot_bytes, dtype=torch.uint8, device=self.dev)
+            self.recv = torch.zeros(self.slot_bytes * world, dtype=torch.uint8, device=self.dev)
+            self._send_ptr = (C.c_void_p * 1)(C.c_void_p(self.send.data_ptr()))
+        else:
+            self._exchange = PeerExchange(rank, world, self.slot_bytes, self.dev)
+
+    def sampler_n_in_bound(self):
+        return min(self.B * (1 + self.degree), max(self.n_nodes, self.B))
+
+    # HotPathStep._pass calls this instead of the local scatter-store
+    def _write_back(self, v, new_hist):
+        lib, D = _lib.load(), self.hidden
+        ld = new_hist.stride(0)
+        if self.transport == "peer":
+            x = self._exchange
+            check(lib.sgcn_wb_push(ptr(v["field"]), ptr(v["n_in_dev"]), self.wb_bound, ptr(new_hist), ld, D,
+                                   x.dst_even, x.dst_odd, self.world, x.peer_flags, self.rank, x.epoch,
+                                   stream_ptr()))
+            check(lib.sgcn_wb_wait_apply(ptr(self.history), self.history.stride(0), D, x.recv_even, x.recv_odd,
+                                         self.slot_bytes, self.world, self.wb_bound, ptr(self.owner), x.flags,
+                                         x.epoch, x.timeout, stream_ptr()))
+        else:
+            check(lib.sgcn_wb_pack(ptr(v["field"]), ptr(v["n_in_dev"]), self.wb_bound, ptr(new_hist), ld, D,
+                                   self._send_ptr, 1, 0, stream_ptr()))
+            self._pending_exchange = True
+
+    def _finish_exchange(self):
+        """NCCL transport: the collective and the merge run eagerly after the (captured) pass."""
+        if self.transport == "nccl" and self.mode != "ns":
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.recv, self.send)
+            check(_lib.load().sgcn_wb_apply(ptr(self.history), self.history.stride(0), self.hidden, ptr(self.recv),
+                                            self.slot_bytes, self.world, self.wb_bound, ptr(self.owner),
+                                            stream_ptr()))
+
+    def run(self, ids):
+        out = super().run(ids)
+        self._finish_exchange()
+        return out
+
+    def replay(self, ids):
+        out = super().replay(ids)
+        self._finish_exchange()
+        return out
+
+    def step_host(self, ids_pinned):
+        if self._pinned_out is None:
+            self._pinned_out = torch.empty(self.out.shape, dtype=torch.float32, pin_memory=True)
+        self.ids.copy_(ids_pinned, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._pass()
+        self._finish_exchange()
+        self._pinned_out.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self._pinned_out
+
+    def check_exchange(self):
+        """Raise if a peer never arrived (bounded spin in wb_wait_kernel timed out)."""
+        if self._exchange is not None:
+            flags, epoch, timeout = self._exchange.control()
+            if timeout:
+                raise _lib.SgcnError(_lib.SGCN_EDATA, "peer exchange timed out waiting for rank %d (epoch %d, flags %s)"
+                                     % (timeout - 1, epoch, flags))
+
+    def close(self):
+        if self._exchange is not None:
+            self._exchange.close()
+            self._exchange = None

@@ -90,11 +90,21 @@ class HotPathStep:
         nb = self.out[:, H:] if self.concat else self.out
         slf = self.out[:, :H] if self.concat else None
         nb_mu = None
-        if cv:   # zero the neighbour halves the two aggregate kernels accumulate into
-            ops.copy_rows_pad(None, 0, nb)
-            if self.mode == "cvd":
-                nb_mu = self.out_mu[:, H:] if self.concat else self.out_mu
-                ops.copy_rows_pad(None, 0, nb_mu)
+        if self.mode == "cvd":
+            nb_mu = self.out_mu[:, H:] if self.concat else self.out_mu
+        # fork at the root: the output halves the two aggregate kernels accumulate into are zeroed
+        # on a side stream while the sampler runs
+        ev_root = torch.cuda.Event()
+        ev_root.record(main)
+        ev_zero = None
+        if cv:
+            with torch.cuda.stream(self._s_b):
+                self._s_b.wait_event(ev_root)
+                ops.copy_rows_pad(None, 0, nb)
+                if nb_mu is not None:
+                    ops.copy_rows_pad(None, 0, nb_mu)
+                ev_zero = torch.cuda.Event()
+                ev_zero.record(self._s_b)
         v = self._sample()
         ev_sampled = torch.cuda.Event()
         ev_sampled.record(main)
@@ -143,11 +153,13 @@ class HotPathStep:
             if self.concat:
                 ops.copy_rows_pad(x, B, slf, n_dev=v["n_out_dev"])
         elif self.mode == "cv":
+            main.wait_event(ev_zero)
             ops.cv_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], B, x, self.history, nb,
                                self_out=slf, n_out_dev=v["n_out_dev"], accumulate=True)
             new_hist = x
         else:
             mu = self.x0[:, H:2 * H]
+            main.wait_event(ev_zero)
             ops.cvd_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], v["scales"], B, x, mu,
                                 self.history, nb, nb_mu, self_h=slf,
                                 self_mu=self.out_mu[:, :H] if self.concat else None, n_out_dev=v["n_out_dev"],
@@ -159,7 +171,11 @@ class HotPathStep:
             main.wait_event(ev_b)
         main.wait_event(ev_c)
         if new_hist is not None:
-            ops.history_update(self.history, v["field"], new_hist, n_dev=v["n_in_dev"])
+            self._write_back(v, new_hist)
+
+    def _write_back(self, v, new_hist):
+        """tf.scatter_update(history, fields[0], new_history); the sharded subclass exchanges instead"""
+        ops.history_update(self.history, v["field"], new_hist, n_dev=v["n_in_dev"])
 
     # -- drivers ---------------------------------------------------------------------------------
     def run(self, ids):
