@@ -231,7 +231,7 @@ def run_reference(args, w):
                                        "reference (1 thread, as shipped), the TensorFlow aggregate is the C port "
                                        "with OpenMP on %d threads" % cpu.threads},
             "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, w, extra):
@@ -360,12 +360,29 @@ def run_ours(args, w):
     if world == 1 and not args.no_cpu:
         host_batches = [b.cpu().numpy() for b in make_batches(g.n, w["batch"], 4000, args.seed + 99, dev)]
         line["cpu_baseline"] = cpu_leg(w, g, feats, args.seed, host_batches, args.cpu_seconds, 3)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else (NCCL banners, library
+    chatter) was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)            # NCCL prints its version banner on fd 1: keep stdout for the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
