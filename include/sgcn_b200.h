@@ -112,6 +112,15 @@ int sgcn_sampler_vec(sgcn_sampler* s, int32_t level, int32_t which, void** ptr /
 /* copy the first `count` elements (4 bytes each) of a vector to HOST memory (synchronises) */
 int sgcn_sampler_copy_vec(sgcn_sampler* s, int32_t level, int32_t which, void* dst /*HOST*/,
                           int64_t count);
+/* Cross-step pipelining.  The sampler keeps two sets of per-batch buffers; set_slot selects the set
+ * that start_batch / expand / sizes / vec address, so batch i+1 can be sampled (on another stream)
+ * while the kernels of batch i still read the other set.  With pipeline enabled, an expand whose
+ * batch shares a node with the previous slot's batch first waits (on the device, bounded) until
+ * every earlier consumer pass has called sgcn_sampler_mark_consumed -- the in-place row permutation
+ * must not race the full-neighbour reads of the previous batch.  Disjoint batches never wait. */
+int sgcn_sampler_set_slot(sgcn_sampler* s, int32_t slot /*0|1*/);
+int sgcn_sampler_pipeline(sgcn_sampler* s, int32_t enable);
+int sgcn_sampler_mark_consumed(sgcn_sampler* s, void* stream);
 /* the stream expand() runs on (cudaStream_t as void*); set to share the caller's stream */
 int sgcn_sampler_set_stream(sgcn_sampler* s, void* stream);
 /* std::mt19937 state (624 words) + cursor, for checkpointing (absent in the reference) */
@@ -170,11 +179,14 @@ int sgcn_spmm_csr_bwd(const int32_t* rowptr, const int32_t* cols, const float* v
  *   y0[r,:] += sum_{q in [adj_p[s], adj_p[s+1])} adj_w[q] * hist[adj_i[q], :]   (and y1 if given)
  * = dot(fadj, gather(history, ffield)) of layers.py:305,309,354,357 without materialising
  * ffield / fadj / the gathered rows.  rowptr_f[n_out+1] is the exclusive scan of the row
- * lengths (SGCN_VEC_ROWPTR_F). */
+ * lengths (SGCN_VEC_ROWPTR_F).  work_counter: NULL = one contiguous span per warp; otherwise a
+ * device int32 that is 0 on entry (the sampler zeroes meta[6] of every level for this purpose) from
+ * which warps pull 64-edge chunks -- keeps all SMs busy when another kernel runs concurrently. */
 int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
                            const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
                            const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
-                           float* y0, int64_t ld_y0, float* y1, int64_t ld_y1, void* stream);
+                           float* y0, int64_t ld_y0, float* y1, int64_t ld_y1, int32_t* work_counter,
+                           void* stream);
 
 /* VRAggregator CV branch, sampled part (layers.py:350-362):
  *   y[r,:] (+)= sum_e vals[e] * (x[cols[e],:] - hist[tgt[e],:])

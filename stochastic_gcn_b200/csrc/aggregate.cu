@@ -233,6 +233,7 @@ struct FullArgs {
     const int32_t* adj_p; const int32_t* adj_i; const float* adj_w;
     const float* hist; int64_t ld_h; int D;
     float* y0; int64_t ld_y0; float* y1; int64_t ld_y1;
+    int32_t* work;   // optional: device counter (0 on entry) for dynamic 64-position chunk scheduling
 };
 
 template <typename V, int LPR, int VPL>
@@ -276,9 +277,19 @@ full_mean_kernel(const FullArgs a) {
     const int gl = lane % LPR, g = lane / LPR;
     const int warp = (blockIdx.x * kAggThreads + threadIdx.x) >> 5;
     const int warps = (gridDim.x * kAggThreads) >> 5;
+    // static schedule: one contiguous span per warp.  dynamic schedule (a.work): warps pull
+    // 64-position chunks from a device counter, which keeps every SM busy when some SMs are held
+    // by a concurrently running kernel (the next batch's sampler in the pipelined step)
     const int span = max(32, (((nnz + warps - 1) / warps) + 31) & ~31);
-    const int p0 = warp * span;
-    const int p1 = min(p0 + span, nnz);
+    int p0 = warp * span;
+    int p1 = min(p0 + span, nnz);
+    if (a.work) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(a.work, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        p0 = c * kFullMacro;
+        p1 = min(p0 + kFullMacro, nnz);
+    }
     if (p0 >= p1) return;
     int64_t* my_off = s_off[wib];
     float* my_w = s_w[wib];
@@ -297,6 +308,11 @@ full_mean_kernel(const FullArgs a) {
     for (int k = 0; k < VPL; ++k) acc[k] = T::zero();
     int cur = -1;                                                 // row this group is accumulating
 
+  for (;;) {
+    int next_chunk = 0;
+    if (a.work) {                                                 // claim the next chunk early
+        if (lane == 0) next_chunk = atomicAdd(a.work, 1);
+    }
     for (int pm = p0; pm < p1; pm += kFullMacro) {
         // ---- stage: metadata of up to 64 positions, two per lane ----
         __syncwarp();
@@ -375,6 +391,12 @@ full_mean_kernel(const FullArgs a) {
             if (gi + 1 < ng) consume(bufB, gi + 1);
         }
     }
+    if (!a.work) break;
+    next_chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
+    p0 = next_chunk * kFullMacro;
+    if (p0 >= nnz) break;
+    p1 = min(p0 + kFullMacro, nnz);
+  }
     if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
 }
 
@@ -554,7 +576,8 @@ int sgcn_spmm_coo(const int32_t* idx2, const float* vals, int32_t nnz, const flo
 int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
                            const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
                            const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
-                           float* y0, int64_t ld_y0, float* y1, int64_t ld_y1, void* stream) {
+                           float* y0, int64_t ld_y0, float* y1, int64_t ld_y1, int32_t* work_counter,
+                           void* stream) {
     SGCN_REQUIRE(n_out >= 0 && D >= 0, "full_history_mean: negative size");
     if (n_out == 0 || D == 0) return SGCN_OK;
     SGCN_REQUIRE(nodes && rowptr_f && adj_p && adj_i && adj_w && hist && y0,
@@ -567,7 +590,8 @@ int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_
     cudaStream_t st = (cudaStream_t)stream;
     for (int c0 = 0; c0 < D; c0 += sh.tile) {
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist + c0, ld_h,
-                   std::min(sh.tile, D - c0), y0 + c0, ld_y0, y1 ? y1 + c0 : nullptr, ld_y1};
+                   std::min(sh.tile, D - c0), y0 + c0, ld_y0, y1 ? y1 + c0 : nullptr, ld_y1,
+                   D <= sh.tile ? work_counter : nullptr};   // one launch per counter reset
         // one resident wave: every CTA the SMs can hold at once, spans cut accordingly
 #define CALL(V, L, P)                                                                        \
     do {                                                                                     \

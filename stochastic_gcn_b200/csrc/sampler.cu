@@ -83,12 +83,22 @@ struct sgcn_sampler {
     float* importance = nullptr;
     uint32_t* engine = nullptr;  // kMtWords
     uint32_t* engine_is = nullptr;
-    // batch
-    DevBuf batch_ids, batch_meta;
-    const int32_t* batch_src = nullptr;   // level-0 field: batch_ids (host path) or the caller's buffer
-    int batch_n = -1;
-    int cur = 0;                 // number of expands since start_batch
-    std::vector<Level> levels;
+    // per-batch state, double-buffered: slot p can be filled for batch i+1 while the kernels of
+    // batch i still read slot 1-p (cross-step pipelining, sgcn_sampler_set_slot)
+    struct Slot {
+        DevBuf batch_ids;
+        const int32_t* batch_src = nullptr;   // level-0 field: batch_ids (host path) or the caller's buffer
+        int batch_n = -1;
+        int cur = 0;                          // number of expands since start_batch
+        std::vector<Level> levels;
+    };
+    Slot slots[2];
+    int cur_slot = 0;
+    Slot& sl() { return slots[cur_slot]; }
+    DevBuf batch_meta;
+    bool pipeline = false;
+    // pipelining guards (device): {number of expands finished, number of consumer passes finished}
+    int32_t* pipe_counters = nullptr;
     // scratch
     DevBuf take, deg, draws, rank, tile_sums, pool_mass, tree, hits;
     int32_t* host_meta = nullptr;   // pinned
@@ -534,6 +544,8 @@ struct FusedArgs {
     const int32_t* field_in; const int32_t* n_ptr; int n_host, nb, sb;
     const int32_t* adj_p; int32_t* adj_i; float* adj_w; int N, degree, cv;
     int hbits;               // log2 of the shared-memory hash table size (>= 2 (nb + sb) entries)
+    const int32_t* prev_ids; int prev_n;   // pipelining: the batch whose consumer pass may still run
+    int32_t* pipe;                         // {expands finished, consumer passes finished} or NULL
     uint32_t* engine;
     int32_t* field; int32_t* rowptr_s; int32_t* rowptr_f; int32_t* edg_s; int32_t* edg_t;
     int32_t* tgt; float* edg_w; float* medg_w; float* scales; int32_t* meta;
@@ -577,6 +589,16 @@ __device__ __forceinline__ int hash_claim(int32_t* keys, int mask, int shift, in
     }
 }
 
+__device__ __forceinline__ bool hash_has(const int32_t* keys, int mask, int shift, int node) {
+    unsigned h = ((unsigned)node * 2654435761u) >> shift;
+    for (;;) {
+        const int k = keys[h];
+        if (k == node) return true;
+        if (k == -1) return false;
+        h = (h + 1) & (unsigned)mask;
+    }
+}
+
 __global__ void __launch_bounds__(kFusedThreads, 1)
 expand_fused_kernel(const FusedArgs a) {
     extern __shared__ int32_t smem[];
@@ -590,7 +612,7 @@ expand_fused_kernel(const FusedArgs a) {
     int32_t* s_vals = s_keys + hsize;                          // hsize: smallest claiming position
     uint32_t* s_mt = (uint32_t*)(s_vals + hsize);              // kMtN
     int32_t* s_warp = (int32_t*)(s_mt + kMtN);                 // 33
-    __shared__ int s_status, s_pos;
+    __shared__ int s_status, s_pos, s_conflict;
     const int tid = threadIdx.x;
 
     const int n_raw = a.n_ptr ? *a.n_ptr : a.n_host;
@@ -598,6 +620,7 @@ expand_fused_kernel(const FusedArgs a) {
     if (tid == 0) {
         s_status = n_raw > a.nb ? ST_OVERFLOW : 0;
         s_pos = (int)a.engine[kMtN];
+        s_conflict = 0;
     }
     for (int i = tid; i < kMtN; i += kFusedThreads) s_mt[i] = a.engine[i];
     for (int i = tid; i < hsize; i += kFusedThreads) {
@@ -662,6 +685,29 @@ expand_fused_kernel(const FusedArgs a) {
         __syncthreads();
         for (int i = tid; i < kMtN; i += kFusedThreads) a.engine[i] = s_mt[i];
         if (tid == 0) a.engine[kMtN] = (uint32_t)pos;
+    }
+
+    // Pipelined steps: the previous batch's consumer pass may still be reading adjacency rows.  The
+    // rows this expand permutes are those of ITS batch, so only a node shared with the previous
+    // batch can race: if one exists, wait until every earlier consumer pass has finished.
+    if (a.pipe) {
+        const int seq = a.pipe[0];
+        for (int j = tid; j < a.prev_n; j += kFusedThreads)
+            if (hash_has(s_keys, hmask, hshift, a.prev_ids[j])) s_conflict = 1;
+        __syncthreads();
+        if (s_conflict && tid == 0) {
+            volatile int32_t* done = (volatile int32_t*)(a.pipe + 1);
+            long long spins = 0;
+            while (*done < seq) {
+                if (++spins > 20000000LL) {       // ~2 s: report instead of hanging the GPU
+                    s_status |= ST_OVERFLOW;
+                    break;
+                }
+                __nanosleep(100);
+            }
+            __threadfence();
+        }
+        __syncthreads();
     }
 
     // per-row partial Fisher-Yates on the stored row (rows of one field are disjoint)
@@ -775,6 +821,14 @@ expand_fused_kernel(const FusedArgs a) {
         a.meta[M_NFF] = 0;
         a.meta[M_STATUS] = s_status;
         a.meta[M_AUX] = 0;
+        if (a.pipe) a.pipe[0] = a.pipe[0] + 1;
+    }
+}
+
+__global__ void mark_consumed_kernel(int32_t* pipe) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        __threadfence();
+        atomicAdd(pipe + 1, 1);
     }
 }
 
@@ -892,8 +946,14 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
             attr_set = true;
         }
         const int hbits = fused_hash_bits(nb, (int)sb);
+        const sgcn_sampler::Slot& other = s->slots[1 - s->cur_slot];
+        const bool piped = s->pipeline && s->sl().cur == 0;
         FusedArgs fa{field_in, n_ptr, nb, nb, (int)sb, s->adj_p, s->adj_i, s->adj_w, s->N, degree,
-                     s->cv ? 1 : 0, hbits, s->engine, lv.field.as<int32_t>(), lv.rowptr_s.as<int32_t>(),
+                     s->cv ? 1 : 0, hbits,
+                     piped && other.batch_n > 0 ? other.batch_src : nullptr,
+                     piped && other.batch_n > 0 ? other.batch_n : 0,
+                     piped ? s->pipe_counters : nullptr,
+                     s->engine, lv.field.as<int32_t>(), lv.rowptr_s.as<int32_t>(),
                      lv.rowptr_f.as<int32_t>(), lv.edg_s.as<int32_t>(), lv.edg_t.as<int32_t>(),
                      lv.tgt.as<int32_t>(), lv.edg_w.as<float>(), lv.medg_w.as<float>(),
                      lv.scales.as<float>(), meta};
@@ -1121,6 +1181,8 @@ static int create_common(sgcn_sampler** out, const float* adj_w, const int32_t* 
     CK(cudaMalloc(&s->engine, sizeof(uint32_t) * kMtWords));
     CK(cudaMalloc(&s->engine_is, sizeof(uint32_t) * kMtWords));
     CK(cudaMallocHost(&s->host_meta, sizeof(int32_t) * kMetaInts));
+    CK(cudaMalloc(&s->pipe_counters, sizeof(int32_t) * 4));
+    CK(cudaMemset(s->pipe_counters, 0, sizeof(int32_t) * 4));
     if (num_edges > 0) {
         CK(cudaMemcpyAsync(s->adj_w, adj_w, sizeof(float) * (size_t)num_edges, kind, s->stream));
         CK(cudaMemcpyAsync(s->adj_i, adj_i, sizeof(int32_t) * (size_t)num_edges, kind, s->stream));
@@ -1153,15 +1215,15 @@ static int create_common(sgcn_sampler** out, const float* adj_w, const int32_t* 
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaGetLastError());
 #undef CK
-    s->levels.resize((size_t)s->L);
+    for (auto& slt : s->slots) slt.levels.resize((size_t)s->L);
     *out = s;
     return SGCN_OK;
 }
 
 static Level* level_at(sgcn_sampler* s, int32_t level) {
-    if (level < 0) level = s->cur - 1;
-    if (level < 0 || level >= s->cur || level >= (int)s->levels.size()) return nullptr;
-    return &s->levels[(size_t)level];
+    if (level < 0) level = s->sl().cur - 1;
+    if (level < 0 || level >= s->sl().cur || level >= (int)s->sl().levels.size()) return nullptr;
+    return &s->sl().levels[(size_t)level];
 }
 
 }  // namespace sgcn
@@ -1184,8 +1246,12 @@ void sgcn_sampler_destroy(sgcn_sampler* s) {
     if (!s) return;
     DeviceGuard guard(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    for (Level& lv : s->levels) lv.release();
-    for (DevBuf* b : {&s->batch_ids, &s->batch_meta, &s->take, &s->deg, &s->draws, &s->rank,
+    for (auto& slt : s->slots) {
+        for (Level& lv : slt.levels) lv.release();
+        slt.batch_ids.release();
+    }
+    cudaFree(s->pipe_counters);
+    for (DevBuf* b : {&s->batch_meta, &s->take, &s->deg, &s->draws, &s->rank,
                       &s->tile_sums, &s->pool_mass, &s->tree, &s->hits})
         b->release();
     cudaFree(s->adj_w);
@@ -1211,6 +1277,29 @@ int sgcn_sampler_seed(sgcn_sampler* s, int32_t seed) {
     return SGCN_OK;
 }
 
+int sgcn_sampler_set_slot(sgcn_sampler* s, int32_t slot) {
+    SGCN_REQUIRE(s && (slot == 0 || slot == 1), "sampler_set_slot: slot must be 0 or 1");
+    s->cur_slot = slot;
+    return SGCN_OK;
+}
+
+int sgcn_sampler_pipeline(sgcn_sampler* s, int32_t enable) {
+    SGCN_REQUIRE(s, "sampler_pipeline: null sampler");
+    DeviceGuard guard(s->device);
+    SGCN_CUDA(cudaStreamSynchronize(s->stream));
+    SGCN_CUDA(cudaMemset(s->pipe_counters, 0, sizeof(int32_t) * 4));
+    s->pipeline = enable != 0;
+    return SGCN_OK;
+}
+
+int sgcn_sampler_mark_consumed(sgcn_sampler* s, void* stream) {
+    SGCN_REQUIRE(s, "sampler_mark_consumed: null sampler");
+    DeviceGuard guard(s->device);
+    mark_consumed_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(s->pipe_counters);
+    SGCN_LAUNCHED();
+    return SGCN_OK;
+}
+
 int sgcn_sampler_set_stream(sgcn_sampler* s, void* stream) {
     SGCN_REQUIRE(s, "sampler_set_stream: null sampler");
     DeviceGuard guard(s->device);
@@ -1227,12 +1316,12 @@ int sgcn_sampler_reserve(sgcn_sampler* s, int32_t max_batch, const int32_t* degr
                  "sampler_reserve: bad argument");
     (void)materialize_full;   // the full COO has no useful size bound; it is grown on demand
     DeviceGuard guard(s->device);
-    SGCN_TRY(s->batch_ids.ensure(sizeof(int32_t) * (size_t)std::max(max_batch, 1)));
+    SGCN_TRY(s->sl().batch_ids.ensure(sizeof(int32_t) * (size_t)std::max(max_batch, 1)));
     SGCN_TRY(s->batch_meta.ensure(sizeof(int32_t) * kMetaInts));
-    if ((int)s->levels.size() < n_degrees) s->levels.resize((size_t)n_degrees);
+    if ((int)s->sl().levels.size() < n_degrees) s->sl().levels.resize((size_t)n_degrees);
     int nb = max_batch;
     for (int k = 0; k < n_degrees; ++k) {
-        Level& lv = s->levels[(size_t)k];
+        Level& lv = s->sl().levels[(size_t)k];
         const bool exact = s->is || degrees[k] > kExactSizingDegree;
         SGCN_TRY(ensure_level(s, lv, nb, exact ? 0 : sample_bound(s, nb, degrees[k]), !s->is));
         if (exact) break;   // deeper bounds are unknown without running
@@ -1246,19 +1335,19 @@ static int start_batch_common(sgcn_sampler* s, int32_t n, const int32_t* ids, cu
     SGCN_REQUIRE(n >= 0 && (n == 0 || ids), "sampler_start_batch: bad ids");
     DeviceGuard guard(s->device);
     if (kind == cudaMemcpyHostToDevice) {
-        SGCN_TRY(s->batch_ids.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
+        SGCN_TRY(s->sl().batch_ids.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
         if (n > 0) {
-            SGCN_CUDA(cudaMemcpyAsync(s->batch_ids.p, ids, sizeof(int32_t) * (size_t)n, kind, s->stream));
+            SGCN_CUDA(cudaMemcpyAsync(s->sl().batch_ids.p, ids, sizeof(int32_t) * (size_t)n, kind, s->stream));
             SGCN_CUDA(cudaStreamSynchronize(s->stream));   // ids may be pageable host memory
         }
-        s->batch_src = s->batch_ids.as<int32_t>();
+        s->sl().batch_src = s->sl().batch_ids.as<int32_t>();
     } else {
         // device ids are BORROWED, not copied: one launch less on the per-step critical path
-        s->batch_src = ids;
+        s->sl().batch_src = ids;
     }
-    s->batch_n = n;
-    s->cur = 0;
-    for (Level& lv : s->levels) lv.done = false;
+    s->sl().batch_n = n;
+    s->sl().cur = 0;
+    for (Level& lv : s->sl().levels) lv.done = false;
     return SGCN_OK;
 }
 
@@ -1272,25 +1361,25 @@ int sgcn_sampler_start_batch_device(sgcn_sampler* s, int32_t n, const int32_t* i
 
 int sgcn_sampler_expand(sgcn_sampler* s, int32_t degree, int32_t materialize_full) {
     SGCN_REQUIRE(s, "sampler_expand: null sampler");
-    if (s->batch_n < 0) {
+    if (s->sl().batch_n < 0) {
         set_error("sampler_expand called before sampler_start_batch");
         return SGCN_ESTATE;
     }
     SGCN_REQUIRE(degree >= 0, "sampler_expand: negative degree");
     DeviceGuard guard(s->device);
-    const int k = s->cur;
-    if ((int)s->levels.size() <= k) s->levels.resize((size_t)k + 1);
-    Level& lv = s->levels[(size_t)k];
-    const int32_t* field_in = k == 0 ? s->batch_src : s->levels[(size_t)k - 1].field.as<int32_t>();
+    const int k = s->sl().cur;
+    if ((int)s->sl().levels.size() <= k) s->sl().levels.resize((size_t)k + 1);
+    Level& lv = s->sl().levels[(size_t)k];
+    const int32_t* field_in = k == 0 ? s->sl().batch_src : s->sl().levels[(size_t)k - 1].field.as<int32_t>();
     // level 0: the batch size is a host value (n_ptr == NULL, count = nb); deeper levels read the
     // previous level's |field| from its device meta block
-    const int32_t* n_ptr = k == 0 ? nullptr : s->levels[(size_t)k - 1].meta.as<int32_t>() + M_NIN;
-    const int nb = k == 0 ? s->batch_n : s->levels[(size_t)k - 1].n_in_bound;
+    const int32_t* n_ptr = k == 0 ? nullptr : s->sl().levels[(size_t)k - 1].meta.as<int32_t>() + M_NIN;
+    const int nb = k == 0 ? s->sl().batch_n : s->sl().levels[(size_t)k - 1].n_in_bound;
     int rc = s->is ? expand_importance(s, lv, field_in, n_ptr, nb, degree)
                    : expand_uniform(s, lv, field_in, n_ptr, nb, degree, materialize_full);
     if (rc != SGCN_OK) return rc;
     lv.done = true;
-    s->cur = k + 1;
+    s->sl().cur = k + 1;
     return SGCN_OK;
 }
 

@@ -117,7 +117,8 @@ def spmm_csr_bwd(rowptr, cols, vals, dy, dx, n_out, rscale=None, n_out_dev=None)
     return dx
 
 
-def full_history_mean(nodes, rowptr_f, n_out, adj_p, adj_i, adj_w, hist, y0, y1=None, n_out_dev=None):
+def full_history_mean(nodes, rowptr_f, n_out, adj_p, adj_i, adj_w, hist, y0, y1=None, n_out_dev=None,
+                      work_counter=None):
     """y0[r] (+= and y1[r] +=) sum over the stored row of nodes[r] of adj_w * hist[adj_i]."""
     _i32(nodes, "nodes"); _i32(rowptr_f, "rowptr_f"); _f32(hist, "hist"); _f32(y0, "y0")
     d = hist.shape[1]
@@ -125,7 +126,8 @@ def full_history_mean(nodes, rowptr_f, n_out, adj_p, adj_i, adj_w, hist, y0, y1=
         raise ValueError("outputs must have hist's width")
     check(_lib.load().sgcn_full_history_mean(ptr(nodes), ptr(rowptr_f), n_out, ptr(n_out_dev), ptr(adj_p),
                                              ptr(adj_i), ptr(adj_w), ptr(hist), _ld(hist), d, ptr(y0), _ld(y0),
-                                             ptr(y1), _ld(y1) if y1 is not None else 0, stream_ptr()))
+                                             ptr(y1), _ld(y1) if y1 is not None else 0, ptr(work_counter),
+                                             stream_ptr()))
     return y0
 
 

@@ -105,6 +105,18 @@ class DeviceSampler:
     def expand(self, degree, materialize_full=False):
         check(self._lib.sgcn_sampler_expand(self._h, int(degree), int(materialize_full)))
 
+    def set_slot(self, slot):
+        """Select which of the two per-batch buffer sets start_batch / expand / view / sizes address."""
+        check(self._lib.sgcn_sampler_set_slot(self._h, int(slot)))
+
+    def pipeline(self, enable=True):
+        """Arm the device-side guard that lets batch i+1 be sampled while batch i is still consumed."""
+        check(self._lib.sgcn_sampler_pipeline(self._h, int(bool(enable))))
+
+    def mark_consumed(self, stream=None):
+        """Tell the guard that one consumer pass has finished reading the adjacency rows."""
+        check(self._lib.sgcn_sampler_mark_consumed(self._h, _lib.stream_ptr(stream)))
+
     def use_stream(self, stream):
         """Run expand() on a torch stream (e.g. the current one, for CUDA-graph capture)."""
         check(self._lib.sgcn_sampler_set_stream(self._h, C.c_void_p(stream.cuda_stream)))

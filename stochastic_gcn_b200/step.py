@@ -47,32 +47,38 @@ class HotPathStep:
         f = features.shape[1]
         width = self.hidden * (2 if self.concat else 1)
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.dev)
-        self.ids = torch.zeros(self.B, dtype=torch.int32, device=self.dev)
+        self.ids2 = [torch.zeros(self.B, dtype=torch.int32, device=self.dev) for _ in range(2)]
+        self.ids = self.ids2[0]
+        self.dynamic_full = False    # warps of full_mean_kernel pull chunks from a device counter
         self.x0 = z(self.n_in_bound, f)                 # gathered input rows
         self.out = z(self.B, width)                     # aggregated h (or the only output)
         self.out_mu = z(self.B, width) if mode == "cvd" else None
         self.d_out = z(self.B, width)                   # upstream gradient (synthetic, resident)
         self.dx = z(self.n_in_bound, self.hidden)
         self.graph = None
+        self.graph_host = None
         self.launches_per_step = None
-        self._views = None
+        self._views = [None, None]
         self._pinned_out = None
-        self._probe = None          # (start_event, end_event) around the dominant kernel, when timing it
+        self._pipe = None           # graphs + events of the cross-step pipelined driver
+        self._pipeline_on = False
+        self._last_slot = 0
         self._s_b = torch.cuda.Stream(device=self.dev)   # side streams of the fork/join in _pass
         self._s_c = torch.cuda.Stream(device=self.dev)
 
     # -- pieces ----------------------------------------------------------------------------------
-    def _sample(self):
+    def _sample(self, slot=0):
         s = self.sampler
-        s.start_batch(self.ids)
+        s.set_slot(slot)
+        s.start_batch(self.ids2[slot])
         s.expand(self.degree, materialize_full=False)
-        if self._views is None:
+        if self._views[slot] is None:
             names = ("field", "rowptr_s", "rowptr_f", "edg_t", "tgt", "edg_w", "scales", "meta")
             v = {k: s.view(k) for k in names}
             v["adj_p"], v["adj_i"], v["adj_w"] = s.view("adj_p"), s.view("adj_i"), s.view("adj_w")
-            v["n_out_dev"], v["n_in_dev"] = v["meta"][0:1], v["meta"][1:2]
-            self._views = v
-        return self._views
+            v["n_out_dev"], v["n_in_dev"], v["work"] = v["meta"][0:1], v["meta"][1:2], v["meta"][6:7]
+            self._views[slot] = v
+        return self._views[slot]
 
     def _pass(self):
         """sampler -> { gather -> sampled aggregate | full-neighbour history mean | backward } -> write-back.
@@ -81,51 +87,64 @@ class HotPathStep:
         aggregate kernels add into a pre-zeroed output with 128-bit reductions, so they commute);
         they are forked onto side streams, which a CUDA-graph capture turns into parallel branches.
         """
-        H, B = self.hidden, self.B
         main = torch.cuda.current_stream(self.dev)
         if getattr(self.sampler, "_stream", None) is None or self.sampler._stream.cuda_stream != main.cuda_stream:
             self.sampler.use_stream(main)
-        probe = self._probe
-        cv = self.mode != "ns"
+        ev_zero = self._fork_zero(main)          # runs beside the sampler
+        v = self._sample(0)
+        self._last_slot = 0
+        self._rest(v, main, ev_zero)
+
+    def _out_views(self):
+        H = self.hidden
         nb = self.out[:, H:] if self.concat else self.out
         slf = self.out[:, :H] if self.concat else None
         nb_mu = None
         if self.mode == "cvd":
             nb_mu = self.out_mu[:, H:] if self.concat else self.out_mu
-        # fork at the root: the output halves the two aggregate kernels accumulate into are zeroed
-        # on a side stream while the sampler runs
+        return nb, slf, nb_mu
+
+    def _fork_zero(self, main):
+        """Zero the output halves the two aggregate kernels accumulate into, on a side stream."""
+        if self.mode == "ns":
+            return None
+        nb, _, nb_mu = self._out_views()
         ev_root = torch.cuda.Event()
         ev_root.record(main)
-        ev_zero = None
-        if cv:
-            with torch.cuda.stream(self._s_b):
-                self._s_b.wait_event(ev_root)
-                ops.copy_rows_pad(None, 0, nb)
-                if nb_mu is not None:
-                    ops.copy_rows_pad(None, 0, nb_mu)
-                ev_zero = torch.cuda.Event()
-                ev_zero.record(self._s_b)
-        v = self._sample()
+        with torch.cuda.stream(self._s_b):
+            self._s_b.wait_event(ev_root)
+            ops.copy_rows_pad(None, 0, nb)
+            if nb_mu is not None:
+                ops.copy_rows_pad(None, 0, nb_mu)
+            ev_zero = torch.cuda.Event()
+            ev_zero.record(self._s_b)
+        return ev_zero
+
+    def _rest(self, v, main, ev_zero):
+        """Everything after the sampler, as three parallel branches joined by the write-back."""
+        pipelined = self._pipeline_on        # the sampler's device guard counts consumer passes
+        H, B = self.hidden, self.B
+        cv = self.mode != "ns"
+        nb, slf, nb_mu = self._out_views()
         ev_sampled = torch.cuda.Event()
         ev_sampled.record(main)
+        work = v["work"] if (pipelined or self.dynamic_full) else None
 
         # branch B: full-neighbour history mean (the dominant kernel)
         ev_b = None
         if cv:
             with torch.cuda.stream(self._s_b):
-                self._s_b.wait_event(ev_sampled)
-                if probe:
-                    probe[0].record(self._s_b)
-                if self.mode == "cv":
-                    ops.full_history_mean(v["field"], v["rowptr_f"], B, v["adj_p"], v["adj_i"], v["adj_w"],
-                                          self.history, nb, n_out_dev=v["n_out_dev"])
-                else:
-                    ops.full_history_mean(v["field"], v["rowptr_f"], B, v["adj_p"], v["adj_i"], v["adj_w"],
-                                          self.history, nb_mu, nb, n_out_dev=v["n_out_dev"])
-                if probe:
-                    probe[1].record(self._s_b)
+                self._s_b.wait_event(ev_sampled)     # the zeroing precedes it on this same stream
+                ops.full_history_mean(v["field"], v["rowptr_f"], B, v["adj_p"], v["adj_i"], v["adj_w"],
+                                      self.history, nb_mu if self.mode == "cvd" else nb,
+                                      nb if self.mode == "cvd" else None, n_out_dev=v["n_out_dev"],
+                                      work_counter=work)
+                if pipelined:                        # adjacency rows of this batch are no longer read
+                    self.sampler.mark_consumed(self._s_b)
                 ev_b = torch.cuda.Event()
                 ev_b.record(self._s_b)
+        elif pipelined:
+            self.sampler.mark_consumed(main)
 
         # branch C: backward of the aggregate, dX = adj^T (dZ_nb * scale) (+ dZ_self on the first B rows)
         with torch.cuda.stream(self._s_c):
@@ -141,11 +160,7 @@ class HotPathStep:
             ev_c.record(self._s_c)
 
         # branch A (main): feature-row gather, then the sampled part of the aggregate
-        if probe and not cv:
-            probe[0].record(main)
         ops.gather_rows(self.features, v["field"], out=self.x0, n_dev=v["n_in_dev"])
-        if probe and not cv:
-            probe[1].record(main)
         x = self.x0[:, :H]
         new_hist = None
         if self.mode == "ns":
@@ -204,10 +219,35 @@ class HotPathStep:
         self.graph.replay()
         return self.out
 
+    def capture_host(self):
+        """Second graph for the host-buffer API: H2D of the pinned ids, the pass, D2H of the result
+        -- the copies are memcpy nodes of the same graph, so a step is ONE launch + ONE sync."""
+        width = self.out.shape[1]
+        self._pin_ids = torch.zeros(self.B, dtype=torch.int32).pin_memory()
+        self._pinned_out = torch.empty((self.B, width), dtype=torch.float32).pin_memory()
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        side = getattr(self, "_capture_stream", None) or torch.cuda.Stream(device=self.dev)
+        self.sampler.use_stream(side)
+        with torch.cuda.graph(g, stream=side):
+            self.ids.copy_(self._pin_ids, non_blocking=True)
+            self._pass()
+            self._pinned_out.copy_(self.out, non_blocking=True)
+        self.graph_host = g
+        self._capture_stream = side
+        return g
+
     def step_host(self, ids_pinned):
-        """End-to-end call with HOST buffers: pinned int32 ids in, aggregated rows out (pinned)."""
+        """End-to-end call with HOST buffers: int32 ids in (host memory), aggregated rows out (pinned
+        host memory).  Per call: a 2 KB host copy into the staging buffer, one graph launch (H2D +
+        pass + D2H), one stream synchronise."""
+        if getattr(self, "graph_host", None) is not None:
+            self._pin_ids.copy_(ids_pinned)
+            self.graph_host.replay()
+            torch.cuda.current_stream(self.dev).synchronize()
+            return self._pinned_out
         if self._pinned_out is None:
-            self._pinned_out = torch.empty(self.out.shape, dtype=torch.float32, pin_memory=True)
+            self._pinned_out = torch.empty(self.out.shape, dtype=torch.float32).pin_memory()
         self.ids.copy_(ids_pinned, non_blocking=True)
         if self.graph is not None:
             self.graph.replay()
@@ -217,6 +257,77 @@ class HotPathStep:
         torch.cuda.current_stream(self.dev).synchronize()
         return self._pinned_out
 
+    # -- cross-step pipelining --------------------------------------------------------------------
+    def capture_pipelined(self, warm0, warm1):
+        """Two graphs per slot: G_s[p] = sampler of a batch into buffer set p, G_r[p] = the rest of the
+        pass reading set p.  The driver keeps batch i+1's sampler (one CTA, latency-bound) in flight
+        on its own stream while batch i's aggregate streams history rows on the other SMs: the
+        sampler leaves the critical path.  Sampler order, RNG stream, history reads and write-backs
+        stay exactly sequential; the in-place row permutation is guarded on the device against the
+        one possible race (a node shared by consecutive batches, see sgcn_sampler_pipeline)."""
+        main = torch.cuda.current_stream(self.dev)
+        for p, ids in ((0, warm0), (1, warm1)):       # eager warm-up of both buffer sets
+            self.sampler.use_stream(main)
+            self.ids2[p].copy_(ids)
+            ev_zero = self._fork_zero(main)
+            v = self._sample(p)
+            self._rest(v, main, ev_zero)
+            self._last_slot = p
+        torch.cuda.synchronize(self.dev)
+        self.sampler.pipeline(True)
+        self._pipeline_on = True
+        side = torch.cuda.Stream(device=self.dev)
+        self.sampler.use_stream(side)
+        g_s, g_r = [], []
+        for p in (0, 1):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._sample(p)
+            g_s.append(g)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                ev_zero = self._fork_zero(side)
+                self._rest(self._views[p], side, ev_zero)
+            g_r.append(g)
+        self._pipe = {"g_s": g_s, "g_r": g_r, "s": torch.cuda.Stream(device=self.dev),
+                      "ev_s": [torch.cuda.Event(), torch.cuda.Event()],
+                      "ev_r": [torch.cuda.Event(), torch.cuda.Event()], "n": 0}
+        return self._pipe
+
+    def run_pipelined(self, batches, on_result=None):
+        """Run len(batches) consecutive passes with one-batch lookahead.  ``batches[i]`` are int32 id
+        tensors (CUDA, or pinned host memory for the end-to-end path).  ``on_result(i, step)`` is
+        called after pass i has been enqueued on the current stream (e.g. to copy ``step.out``)."""
+        pipe = self._pipe
+        main, S = torch.cuda.current_stream(self.dev), pipe["s"]
+        n = len(batches)
+        start = torch.cuda.Event()
+        start.record(main)
+        S.wait_event(start)
+
+        def launch_sample(i):
+            p = i & 1
+            with torch.cuda.stream(S):
+                if i >= 2:
+                    S.wait_event(pipe["ev_r"][p])        # buffer set p is free once pass i-2 is done
+                self.ids2[p].copy_(batches[i], non_blocking=True)
+                pipe["g_s"][p].replay()
+                pipe["ev_s"][p].record(S)
+
+        if n:
+            launch_sample(0)
+        for i in range(n):
+            p = i & 1
+            if i + 1 < n:
+                launch_sample(i + 1)
+            main.wait_event(pipe["ev_s"][p])
+            pipe["g_r"][p].replay()
+            pipe["ev_r"][p].record(main)
+            self._last_slot = p
+            if on_result is not None:
+                on_result(i, self)
+        return self.out
+
     def time_dominant_kernel(self, batches):
         """Device time of the dominant kernel -- the edge-balanced full-neighbour history mean for
         CV/CVD, the feature-row gather for NS -- launched back to back on ONE stream over the inputs
@@ -224,7 +335,7 @@ class HotPathStep:
         one batch), CUDA events around the train of launches; returns the average per launch and the
         algorithmic bytes of exactly those launches."""
         dev, B, H = self.dev, self.B, self.hidden
-        v = self._views
+        v = self._views[0]
         deg = (v["adj_p"][1:] - v["adj_p"][:-1])
         scratch = torch.zeros_like(self.out)
         total_bytes, calls = 0, []
@@ -265,7 +376,7 @@ class HotPathStep:
 
     def sizes(self):
         """(n_out, n_in, nnz_s, nnz_f) of the last pass (synchronises)."""
-        m = self._views["meta"].cpu().tolist()
+        m = self._views[getattr(self, "_last_slot", 0)]["meta"].cpu().tolist()
         if m[5]:
             raise _lib.SgcnError(_lib.SGCN_EDATA, "sampler status %d" % m[5])
         return {"n_out": m[0], "n_in": m[1], "nnz_s": m[2], "nnz_f": m[3]}
