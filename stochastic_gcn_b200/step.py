@@ -65,6 +65,7 @@ class HotPathStep:
         self._last_slot = 0
         self._s_b = torch.cuda.Stream(device=self.dev)   # side streams of the fork/join in _pass
         self._s_c = torch.cuda.Stream(device=self.dev)
+        self._s_samp = torch.cuda.Stream(device=self.dev)   # sampler branch of the pipelined graphs
 
     # -- pieces ----------------------------------------------------------------------------------
     def _sample(self, slot=0):
@@ -258,13 +259,16 @@ class HotPathStep:
         return self._pinned_out
 
     # -- cross-step pipelining --------------------------------------------------------------------
-    def capture_pipelined(self, warm0, warm1):
-        """Two graphs per slot: G_s[p] = sampler of a batch into buffer set p, G_r[p] = the rest of the
-        pass reading set p.  The driver keeps batch i+1's sampler (one CTA, latency-bound) in flight
-        on its own stream while batch i's aggregate streams history rows on the other SMs: the
-        sampler leaves the critical path.  Sampler order, RNG stream, history reads and write-backs
-        stay exactly sequential; the in-place row permutation is guarded on the device against the
-        one possible race (a node shared by consecutive batches, see sgcn_sampler_pipeline)."""
+    def capture_pipelined(self, warm0, warm1, host_io=False):
+        """One graph per step with TWO parallel branches: the rest of pass i (reading buffer set p) and
+        the sampler of batch i+1 (filling set 1-p).  The sampler is one latency-bound CTA; run beside
+        the aggregate that streams history rows on the other SMs it leaves the critical path.
+        Sampler order, RNG stream, history reads and write-backs stay exactly sequential; the
+        in-place row permutation is guarded on the device against the one possible race (a node
+        shared by consecutive batches, see sgcn_sampler_pipeline).
+
+        host_io=True adds the H2D copy of the next batch's ids (from pinned staging) and the D2H copy
+        of the aggregated rows (to pinned memory) as memcpy nodes of the same graphs."""
         main = torch.cuda.current_stream(self.dev)
         for p, ids in ((0, warm0), (1, warm1)):       # eager warm-up of both buffer sets
             self.sampler.use_stream(main)
@@ -274,55 +278,71 @@ class HotPathStep:
             self._rest(v, main, ev_zero)
             self._last_slot = p
         torch.cuda.synchronize(self.dev)
-        self.sampler.pipeline(True)
-        self._pipeline_on = True
+        if not self._pipeline_on:
+            self.sampler.pipeline(True)
+            self._pipeline_on = True
+        if host_io:
+            width = self.out.shape[1]
+            self._pin_ids2 = [torch.zeros(self.B, dtype=torch.int32).pin_memory() for _ in range(2)]
+            self._pinned_out = torch.empty((self.B, width), dtype=torch.float32).pin_memory()
+        s_samp = self._s_samp
+        self.sampler.use_stream(s_samp)               # outside any capture: set_stream synchronises
         side = torch.cuda.Stream(device=self.dev)
-        self.sampler.use_stream(side)
-        g_s, g_r = [], []
+
+        def sample_branch(slot):
+            if host_io:
+                self.ids2[slot].copy_(self._pin_ids2[slot], non_blocking=True)
+            self._sample(slot)
+
+        def rest_branch(slot, stream):
+            ev_zero = self._fork_zero(stream)
+            self._rest(self._views[slot], stream, ev_zero)
+            if host_io:
+                self._pinned_out.copy_(self.out, non_blocking=True)
+
+        first = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(first, stream=s_samp):
+            sample_branch(0)
+        both, last = [], []
         for p in (0, 1):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
-                self._sample(p)
-            g_s.append(g)
+                ev_root = torch.cuda.Event()
+                ev_root.record(side)
+                with torch.cuda.stream(s_samp):
+                    s_samp.wait_event(ev_root)
+                    sample_branch(1 - p)
+                    ev_s = torch.cuda.Event()
+                    ev_s.record(s_samp)
+                rest_branch(p, side)
+                side.wait_event(ev_s)
+            both.append(g)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
-                ev_zero = self._fork_zero(side)
-                self._rest(self._views[p], side, ev_zero)
-            g_r.append(g)
-        self._pipe = {"g_s": g_s, "g_r": g_r, "s": torch.cuda.Stream(device=self.dev),
-                      "ev_s": [torch.cuda.Event(), torch.cuda.Event()],
-                      "ev_r": [torch.cuda.Event(), torch.cuda.Event()], "n": 0}
+                rest_branch(p, side)
+            last.append(g)
+        self._pipe = {"first": first, "both": both, "last": last, "host_io": host_io}
         return self._pipe
 
     def run_pipelined(self, batches, on_result=None):
-        """Run len(batches) consecutive passes with one-batch lookahead.  ``batches[i]`` are int32 id
-        tensors (CUDA, or pinned host memory for the end-to-end path).  ``on_result(i, step)`` is
-        called after pass i has been enqueued on the current stream (e.g. to copy ``step.out``)."""
+        """Run len(batches) consecutive passes with one-batch sampler lookahead on the current stream:
+        per step one ids copy and ONE graph launch.  ``batches[i]``: int32 ids (CUDA tensors, or host
+        tensors when captured with host_io=True).  ``on_result(i, step)`` is called after pass i has
+        been enqueued (host_io: ``step._pinned_out`` holds the rows once the stream is synchronised)."""
         pipe = self._pipe
-        main, S = torch.cuda.current_stream(self.dev), pipe["s"]
         n = len(batches)
-        start = torch.cuda.Event()
-        start.record(main)
-        S.wait_event(start)
-
-        def launch_sample(i):
-            p = i & 1
-            with torch.cuda.stream(S):
-                if i >= 2:
-                    S.wait_event(pipe["ev_r"][p])        # buffer set p is free once pass i-2 is done
-                self.ids2[p].copy_(batches[i], non_blocking=True)
-                pipe["g_s"][p].replay()
-                pipe["ev_s"][p].record(S)
-
-        if n:
-            launch_sample(0)
+        if n == 0:
+            return self.out
+        stage = self._pin_ids2 if pipe["host_io"] else self.ids2
+        stage[0].copy_(batches[0], non_blocking=not pipe["host_io"])
+        pipe["first"].replay()
         for i in range(n):
             p = i & 1
             if i + 1 < n:
-                launch_sample(i + 1)
-            main.wait_event(pipe["ev_s"][p])
-            pipe["g_r"][p].replay()
-            pipe["ev_r"][p].record(main)
+                stage[1 - p].copy_(batches[i + 1], non_blocking=not pipe["host_io"])
+                pipe["both"][p].replay()
+            else:
+                pipe["last"][p].replay()
             self._last_slot = p
             if on_result is not None:
                 on_result(i, self)
