@@ -307,7 +307,7 @@ def run_ours(args, w):
     pipelined = not args.no_pipeline
     ms = ms_serial
     if pipelined:
-        step.capture_pipelined(batches[0], batches[1])
+        step.capture_pipelined(batches[0], batches[1], steps_per_graph=args.steps_per_graph)
         launches_per_step += 1                       # + mark_consumed
         step.run_pipelined(batches[2:args.warmup + 2])
         torch.cuda.synchronize(dev)
@@ -323,16 +323,17 @@ def run_ours(args, w):
     pinned = [b.cpu().pin_memory() for b in timed]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if pipelined:
-        step.capture_pipelined(batches[0], batches[1], host_io=True)   # H2D ids / D2H rows as graph nodes
+        # H2D of every step's ids and D2H of every step's rows are memcpy nodes of the chunk graphs
+        step.capture_pipelined(batches[0], batches[1], host_io=True, steps_per_graph=args.steps_per_graph)
         stream = torch.cuda.current_stream(dev)
-        out_host = step._pinned_out
+        out_host = step._pipe["pin_out"][0][0]
 
-        def fetch(i, st):
-            stream.synchronize()          # the caller waits for (and may read) every step's result
-        step.run_pipelined(pinned[:3], on_result=fetch)
+        def fetch(first, count, st):
+            stream.synchronize()          # the caller waits for (and may read) the results chunk by chunk
+        step.run_pipelined(pinned[:args.steps_per_graph], on_chunk=fetch)
         barrier()
         e0.record()
-        step.run_pipelined(pinned, on_result=fetch)
+        step.run_pipelined(pinned, on_chunk=fetch)
         e1.record()
         barrier()
     else:
@@ -375,8 +376,10 @@ def run_ours(args, w):
                                                                 % (world, args.transport)) if world > 1 else "single GPU"}),
             "sampled_edges_per_s": s_edges / (ms * 1e-3),
             "schedule": {"pipelined": pipelined,
-                         "what": "batch i+1's sampler graph runs on its own stream while batch i's aggregate graph "
-                                 "runs (one-batch lookahead, same sequential semantics)" if pipelined else
+                         "steps_per_graph": args.steps_per_graph if pipelined else 1,
+                         "what": "CUDA graphs of %d steps; inside a step batch k+1's sampler (1 CTA) runs beside "
+                                 "batch k's aggregate (one-batch lookahead, same sequential semantics)"
+                                 % args.steps_per_graph if pipelined else
                                  "one CUDA graph per step, back to back",
                          "ms_per_step_one_graph_back_to_back": ms_serial / args.steps},
             "step_hbm": {"algorithmic_bytes_per_step": alg["total"],
@@ -433,6 +436,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="time one graph per step, no sampler lookahead")
+    ap.add_argument("--steps-per-graph", type=int, default=8)
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU write-back exchange: NVLink peer stores (default) or NCCL all-gather")
     args = ap.parse_args()

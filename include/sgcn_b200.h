@@ -32,6 +32,12 @@ int sgcn_abi_version(void);
 const char* sgcn_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t sgcn_launch_count(void);
+/* Device timeline (profiling aid).  buf16 = device uint64[16] or NULL (off).  Kernels launched (or
+ * captured into a graph) while it is set stamp %globaltimer: buf[2k] = min block start (initialise
+ * to ~0), buf[2k+1] = max block end (initialise to 0) for kernel class k: 0 sampler, 1 full-neighbour
+ * mean, 2 row gather, 3 sampled aggregate, 4 SpMM backward, 5 history write-back, 6 copy/zero-pad,
+ * 7 write-back exchange. */
+int sgcn_trace_set(void* buf16);
 
 /* ------------------------------------------------------------------------------------------
  * Neighbour sampler.  Replaces `class Scheduler` (gcn/scheduler.h:6-28, gcn/scheduler.cpp:11-189)

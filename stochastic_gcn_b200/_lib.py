@@ -32,6 +32,7 @@ SIGNATURES = {
     "sgcn_abi_version": (_i32, []),
     "sgcn_last_error": (C.c_char_p, []),
     "sgcn_launch_count": (_i64, []),
+    "sgcn_trace_set": (_i32, [_vp]),
     "sgcn_sampler_create": (_i32, [C.POINTER(_vp), _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32]),
     "sgcn_sampler_create_device": (_i32, [C.POINTER(_vp), _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32]),
     "sgcn_sampler_destroy": (None, [_vp]),

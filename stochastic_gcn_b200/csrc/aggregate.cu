@@ -70,12 +70,14 @@ struct SampledArgs {
     float* self1; int64_t ld_s1;       // CVD: copy of mu[:n_out]
     int accumulate;                    // 0: overwrite y; 1: y += (PLAIN: read-modify-write by the row's
                                        // owner; CV/CVD: 128-bit RED, commutes with full_mean_kernel)
+    unsigned long long* trace;
 };
 
 template <typename V, int LPR, int VPL, int MODE>
 __global__ void __launch_bounds__(kAggThreads)
 sampled_rows_kernel(const SampledArgs a) {
     using T = VT<V>;
+    TraceScope ts(a.trace, TR_SAMPLED);
     const int n_out = dev_count(a.n_out_dev, a.n_out);
     const int gl = threadIdx.x % LPR;                      // lane within the group
     const int groups = (gridDim.x * kAggThreads) / LPR;
@@ -154,12 +156,14 @@ struct BwdArgs {
     const int32_t* rowptr; const int32_t* cols; const float* vals; const float* rscale;
     int n_out; const int32_t* n_out_dev;
     const float* dy; int64_t ld_dy; int D; float* dx; int64_t ld_dx;
+    unsigned long long* trace;
 };
 
 template <typename V, int LPR, int VPL>
 __global__ void __launch_bounds__(kAggThreads)
 spmm_bwd_kernel(const BwdArgs a) {
     using T = VT<V>;
+    TraceScope ts(a.trace, TR_BWD);
     const int n_out = dev_count(a.n_out_dev, a.n_out);
     const int gl = threadIdx.x % LPR;
     const int groups = (gridDim.x * kAggThreads) / LPR;
@@ -234,6 +238,8 @@ struct FullArgs {
     const float* hist; int64_t ld_h; int D;
     float* y0; int64_t ld_y0; float* y1; int64_t ld_y1;
     int32_t* work;   // optional: device counter (0 on entry) for dynamic 64-position chunk scheduling
+    int stage_rows;  // row pointers of up to this many output rows are staged in shared memory
+    unsigned long long* trace;
 };
 
 template <typename V, int LPR, int VPL>
@@ -251,20 +257,22 @@ __device__ __forceinline__ void full_flush(const FullArgs& a, int row, int gl, V
 }
 
 template <typename V, int LPR, int VPL>
-__global__ void __launch_bounds__(kAggThreads, 2)
+__global__ void __maxnreg__(96)      // 2 CTAs x 256 threads x 96 regs leave 16K registers per SM free
 full_mean_kernel(const FullArgs a) {
     using T = VT<V>;
+    TraceScope ts(a.trace, TR_FULL);
     constexpr int G = 32 / LPR;                                  // groups per warp
     constexpr int UN = (VPL >= 8) ? 1 : ((VPL == 4) ? 2 : ((VPL == 2) ? 4 : 8));   // row loads per buffer
     constexpr int STEP = G * UN;                                 // positions per group-iteration
-    __shared__ int32_t s_ptr[kFullStageRows + 1];                // rowptr_f
-    __shared__ int32_t s_base[kFullStageRows];                   // adj_p[nodes[r]] - rowptr_f[r]
+    extern __shared__ int32_t s_dyn[];                           // sized to the launch's row bound
+    int32_t* s_ptr = s_dyn;                                      // rowptr_f            [stage_rows + 1]
+    int32_t* s_base = s_dyn + a.stage_rows + 1;                  // adj_p[nodes[r]] - rowptr_f[r]
     __shared__ int64_t s_off[kFullWarps][kFullMacro];            // adj_i * ld_h (element offset of the row)
     __shared__ float s_w[kFullWarps][kFullMacro];
     __shared__ int32_t s_r[kFullWarps][kFullMacro];
     const int n_out = dev_count(a.n_out_dev, a.n_out);
     if (n_out <= 0) return;
-    const bool staged = n_out <= kFullStageRows;
+    const bool staged = n_out <= a.stage_rows;
     if (staged) {
         for (int i = threadIdx.x; i <= n_out; i += kAggThreads) s_ptr[i] = __ldg(a.rowptr_f + i);
         for (int i = threadIdx.x; i < n_out; i += kAggThreads)
@@ -441,6 +449,7 @@ static int launch_sampled(SampledArgs a, int D, bool vec_ok, cudaStream_t st) {
     const Shape sh = pick_shape(D, vec_ok);
     for (int c0 = 0; c0 < D; c0 += sh.tile) {
         SampledArgs t = a;
+        t.trace = g_trace;
         t.D = std::min(sh.tile, D - c0);
         t.x = a.x + c0;
         if (a.mu) t.mu = a.mu + c0;
@@ -539,7 +548,7 @@ int sgcn_spmm_csr_bwd(const int32_t* rowptr, const int32_t* cols, const float* v
     cudaStream_t st = (cudaStream_t)stream;
     for (int c0 = 0; c0 < D; c0 += sh.tile) {
         BwdArgs a{rowptr, cols, vals, rscale, n_out, n_out_dev, dy + c0, ld_dy,
-                  std::min(sh.tile, D - c0), dx + c0, ld_dx};
+                  std::min(sh.tile, D - c0), dx + c0, ld_dx, g_trace};
         const int grid = grid_for_groups(n_out, sh.lpr);
 #define CALL(V, L, P) spmm_bwd_kernel<V, L, P><<<grid, kAggThreads, 0, st>>>(a)
         SGCN_DISPATCH_SHAPE(sh, CALL);
@@ -591,17 +600,20 @@ int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_
     for (int c0 = 0; c0 < D; c0 += sh.tile) {
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist + c0, ld_h,
                    std::min(sh.tile, D - c0), y0 + c0, ld_y0, y1 ? y1 + c0 : nullptr, ld_y1,
-                   D <= sh.tile ? work_counter : nullptr};   // one launch per counter reset
+                   D <= sh.tile ? work_counter : nullptr,    // one launch per counter reset
+                   std::min(n_out, kFullStageRows), g_trace};
+        const size_t dyn = sizeof(int32_t) * (2 * (size_t)a.stage_rows + 2);
         // one resident wave: every CTA the SMs can hold at once, spans cut accordingly
 #define CALL(V, L, P)                                                                        \
     do {                                                                                     \
         static int per_sm = 0;                                                               \
         if (per_sm == 0) {                                                                   \
             SGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                         \
-                &per_sm, full_mean_kernel<V, L, P>, kAggThreads, 0));                        \
+                &per_sm, full_mean_kernel<V, L, P>, kAggThreads,                             \
+                sizeof(int32_t) * (2 * (size_t)kFullStageRows + 2)));                        \
             if (per_sm < 1) per_sm = 1;                                                      \
         }                                                                                    \
-        full_mean_kernel<V, L, P><<<kNumSMs * per_sm, kAggThreads, 0, st>>>(a);              \
+        full_mean_kernel<V, L, P><<<kNumSMs * per_sm, kAggThreads, dyn, st>>>(a);            \
     } while (0)
         SGCN_DISPATCH_SHAPE(sh, CALL);
 #undef CALL

@@ -17,6 +17,11 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
 void set_error(const std::string& msg);
 extern std::atomic<int64_t> g_launches;
+// optional device timeline: trace[2*id] = earliest block start, trace[2*id+1] = latest block end
+// (globaltimer ns) of kernel class `id`; NULL = tracing off (sgcn_trace_set)
+extern unsigned long long* g_trace;
+enum { TR_SAMPLER = 0, TR_FULL = 1, TR_GATHER = 2, TR_SAMPLED = 3, TR_BWD = 4, TR_UPDATE = 5, TR_PAD = 6,
+       TR_EXCHANGE = 7, TR_CLASSES = 8 };
 
 inline int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     char buf[512];
@@ -70,6 +75,22 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
     acc.z = fmaf(w, v.z, acc.z);
     acc.w = fmaf(w, v.w, acc.w);
 }
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// RAII-style block stamps: construct at kernel entry, call end() (or let it go out of scope) at exit
+struct TraceScope {
+    unsigned long long* t;
+    __device__ __forceinline__ TraceScope(unsigned long long* trace, int id) : t(trace ? trace + 2 * id : nullptr) {
+        if (t && threadIdx.x == 0) atomicMin(t, global_ns());
+    }
+    __device__ __forceinline__ ~TraceScope() {
+        if (t && threadIdx.x == 0) atomicMax(t + 1, global_ns());
+    }
+};
 
 __device__ __forceinline__ int dev_count(const int32_t* n_dev, int n_host) {
     return n_dev ? min(*n_dev, n_host) : n_host;

@@ -25,7 +25,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kRowThreads)
 move_rows_vec4_kernel(const float* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ idx,
                       int n_host, const int32_t* __restrict__ n_dev, int n_total, int c4,
-                      float* __restrict__ dst, int64_t ld_dst) {
+                      float* __restrict__ dst, int64_t ld_dst, unsigned long long* trace) {
+    TraceScope ts(trace, MODE == 0 ? TR_GATHER : (MODE == 1 ? TR_UPDATE : TR_PAD));
     const int n = dev_count(n_dev, n_host);
     const int rows = MODE == 2 ? n_total : n;
     const int64_t total = (int64_t)rows * c4;
@@ -96,7 +97,7 @@ static int launch_move_rows(const float* src, int64_t ld_src, const int32_t* idx
                                                 ((int64_t)kRowThreads * kRowUnroll), max_blocks);
         if (blocks < 1) blocks = 1;
         move_rows_vec4_kernel<MODE><<<blocks, kRowThreads, 0, st>>>(src, ld_src, idx, n, n_dev,
-                                                                   n_total, c4, dst, ld_dst);
+                                                                   n_total, c4, dst, ld_dst, g_trace);
     } else {
         const int64_t total = (int64_t)rows * C;
         int blocks = (int)std::min<int64_t>((total + kRowThreads - 1) / kRowThreads, max_blocks);

@@ -546,12 +546,15 @@ struct FusedArgs {
     int hbits;               // log2 of the shared-memory hash table size (>= 2 (nb + sb) entries)
     const int32_t* prev_ids; int prev_n;   // pipelining: the batch whose consumer pass may still run
     int32_t* pipe;                         // {expands finished, consumer passes finished} or NULL
+    unsigned long long* trace;
     uint32_t* engine;
     int32_t* field; int32_t* rowptr_s; int32_t* rowptr_f; int32_t* edg_s; int32_t* edg_t;
     int32_t* tgt; float* edg_w; float* medg_w; float* scales; int32_t* meta;
 };
 
-__device__ __forceinline__ int block_scan_excl_1024(int v, int* total, int* s_warp /*33 ints*/) {
+template <int NT>
+__device__ __forceinline__ int block_scan_excl_nt(int v, int* total, int* s_warp /*33 ints*/) {
+    constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int inc = v;
 #pragma unroll
@@ -562,14 +565,14 @@ __device__ __forceinline__ int block_scan_excl_1024(int v, int* total, int* s_wa
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        const int w = s_warp[lane];
+        const int w = lane < NW ? s_warp[lane] : 0;
         int winc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int n = __shfl_up_sync(0xffffffffu, winc, o);
             if (lane >= o) winc += n;
         }
-        s_warp[lane] = winc - w;
+        if (lane < NW) s_warp[lane] = winc - w;
         if (lane == 31) s_warp[32] = winc;
     }
     __syncthreads();
@@ -599,7 +602,11 @@ __device__ __forceinline__ bool hash_has(const int32_t* keys, int mask, int shif
     }
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 1)
+// NT = 1024: fastest stand-alone.  NT = 256 (<= 48 registers): small enough to sit in the registers
+// two resident full_mean_kernel CTAs leave free on an SM, so that in the pipelined step the next
+// batch's sampler really runs BESIDE the aggregate instead of waiting for an empty SM.
+template <int NT, int MIN_BLOCKS>
+__global__ void __launch_bounds__(NT, MIN_BLOCKS)
 expand_fused_kernel(const FusedArgs a) {
     extern __shared__ int32_t smem[];
     // carved to the launch's own bounds (fused_smem_bytes): a 512 x 2 batch needs ~46 KB, not the
@@ -614,6 +621,7 @@ expand_fused_kernel(const FusedArgs a) {
     int32_t* s_warp = (int32_t*)(s_mt + kMtN);                 // 33
     __shared__ int s_status, s_pos, s_conflict;
     const int tid = threadIdx.x;
+    TraceScope ts(a.trace, TR_SAMPLER);
 
     const int n_raw = a.n_ptr ? *a.n_ptr : a.n_host;
     const int n_out = min(n_raw, a.nb);
@@ -622,8 +630,8 @@ expand_fused_kernel(const FusedArgs a) {
         s_pos = (int)a.engine[kMtN];
         s_conflict = 0;
     }
-    for (int i = tid; i < kMtN; i += kFusedThreads) s_mt[i] = a.engine[i];
-    for (int i = tid; i < hsize; i += kFusedThreads) {
+    for (int i = tid; i < kMtN; i += NT) s_mt[i] = a.engine[i];
+    for (int i = tid; i < hsize; i += NT) {
         s_keys[i] = -1;
         s_vals[i] = kUnseen;
     }
@@ -631,7 +639,7 @@ expand_fused_kernel(const FusedArgs a) {
 
     // rows + both prefix sums, 1024 rows per sweep with a carry; old field -> table (value = position)
     int carry_s = 0, carry_f = 0;
-    for (int base = 0; base < n_out; base += kFusedThreads) {
+    for (int base = 0; base < n_out; base += NT) {
         const int i = base + tid;
         int take = 0, d = 0;
         if (i < n_out) {
@@ -651,8 +659,8 @@ expand_fused_kernel(const FusedArgs a) {
             }
         }
         int tot_s, tot_f;
-        const int ex_s = block_scan_excl_1024(take, &tot_s, s_warp);
-        const int ex_f = block_scan_excl_1024(a.cv ? d : 0, &tot_f, s_warp);
+        const int ex_s = block_scan_excl_nt<NT>(take, &tot_s, s_warp);
+        const int ex_f = block_scan_excl_nt<NT>(a.cv ? d : 0, &tot_f, s_warp);
         if (i < n_out) {
             s_rowptr[i] = carry_s + ex_s;
             a.rowptr_s[i] = carry_s + ex_s;
@@ -678,12 +686,12 @@ expand_fused_kernel(const FusedArgs a) {
                 pos = 0;
             }
             const int avail = min(kMtN - pos, nnz - produced);
-            for (int i = tid; i < avail; i += kFusedThreads) s_u[produced + i] = mt_temper(s_mt[pos + i]);
+            for (int i = tid; i < avail; i += NT) s_u[produced + i] = mt_temper(s_mt[pos + i]);
             pos += avail;
             produced += avail;
         }
         __syncthreads();
-        for (int i = tid; i < kMtN; i += kFusedThreads) a.engine[i] = s_mt[i];
+        for (int i = tid; i < kMtN; i += NT) a.engine[i] = s_mt[i];
         if (tid == 0) a.engine[kMtN] = (uint32_t)pos;
     }
 
@@ -692,7 +700,7 @@ expand_fused_kernel(const FusedArgs a) {
     // batch can race: if one exists, wait until every earlier consumer pass has finished.
     if (a.pipe) {
         const int seq = a.pipe[0];
-        for (int j = tid; j < a.prev_n; j += kFusedThreads)
+        for (int j = tid; j < a.prev_n; j += NT)
             if (hash_has(s_keys, hmask, hshift, a.prev_ids[j])) s_conflict = 1;
         __syncthreads();
         if (s_conflict && tid == 0) {
@@ -711,7 +719,7 @@ expand_fused_kernel(const FusedArgs a) {
     }
 
     // per-row partial Fisher-Yates on the stored row (rows of one field are disjoint)
-    for (int i = tid; i < n_out; i += kFusedThreads) {
+    for (int i = tid; i < n_out; i += NT) {
         const int e0 = s_rowptr[i];
         const int take = s_rowptr[i + 1] - e0;
         if (take <= 0 || e0 + take > a.sb) continue;
@@ -792,16 +800,16 @@ expand_fused_kernel(const FusedArgs a) {
     // first-occurrence flags -> ranks (reuse the draw buffer)
     int32_t* s_rank = (int32_t*)s_u;
     int n_new = 0;
-    for (int base = 0; base < nnz; base += kFusedThreads) {
+    for (int base = 0; base < nnz; base += NT) {
         const int e = base + tid;
         const int f = (e < nnz && s_vals[s_eslot[e]] == n_out + e) ? 1 : 0;
         int tot;
-        const int ex = block_scan_excl_1024(f, &tot, s_warp);
+        const int ex = block_scan_excl_nt<NT>(f, &tot, s_warp);
         if (e < nnz) s_rank[e] = n_new + ex;
         n_new += tot;
     }
     __syncthreads();
-    for (int e = tid; e < nnz; e += kFusedThreads) {
+    for (int e = tid; e < nnz; e += NT) {
         const int h = s_eslot[e];
         const int sl = s_vals[h];
         if (sl < n_out) {
@@ -941,8 +949,10 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
     if (!exact && nb <= kFusedMaxRows && sb <= kFusedMaxEdges && fused_sampler_enabled()) {
         static bool attr_set = false;
         if (!attr_set) {
-            SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)kFusedSmemBytes));
+            SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel<1024, 1>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes));
+            SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel<256, 5>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes));
             attr_set = true;
         }
         const int hbits = fused_hash_bits(nb, (int)sb);
@@ -952,12 +962,15 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
                      s->cv ? 1 : 0, hbits,
                      piped && other.batch_n > 0 ? other.batch_src : nullptr,
                      piped && other.batch_n > 0 ? other.batch_n : 0,
-                     piped ? s->pipe_counters : nullptr,
+                     piped ? s->pipe_counters : nullptr, g_trace,
                      s->engine, lv.field.as<int32_t>(), lv.rowptr_s.as<int32_t>(),
                      lv.rowptr_f.as<int32_t>(), lv.edg_s.as<int32_t>(), lv.edg_t.as<int32_t>(),
                      lv.tgt.as<int32_t>(), lv.edg_w.as<float>(), lv.medg_w.as<float>(),
                      lv.scales.as<float>(), meta};
-        expand_fused_kernel<<<1, kFusedThreads, fused_smem_bytes(nb, (int)sb, hbits), st>>>(fa);
+        if (s->pipeline)
+            expand_fused_kernel<256, 5><<<1, 256, fused_smem_bytes(nb, (int)sb, hbits), st>>>(fa);
+        else
+            expand_fused_kernel<1024, 1><<<1, 1024, fused_smem_bytes(nb, (int)sb, hbits), st>>>(fa);
         SGCN_LAUNCHED();
         lv.full_materialized = false;
         if (s->cv && materialize) {

@@ -68,10 +68,10 @@ class HotPathStep:
         self._s_samp = torch.cuda.Stream(device=self.dev)   # sampler branch of the pipelined graphs
 
     # -- pieces ----------------------------------------------------------------------------------
-    def _sample(self, slot=0):
+    def _sample(self, slot=0, ids=None):
         s = self.sampler
         s.set_slot(slot)
-        s.start_batch(self.ids2[slot])
+        s.start_batch(self.ids2[slot] if ids is None else ids)
         s.expand(self.degree, materialize_full=False)
         if self._views[slot] is None:
             names = ("field", "rowptr_s", "rowptr_f", "edg_t", "tgt", "edg_w", "scales", "meta")
@@ -129,7 +129,7 @@ class HotPathStep:
         nb, slf, nb_mu = self._out_views()
         ev_sampled = torch.cuda.Event()
         ev_sampled.record(main)
-        work = v["work"] if (pipelined or self.dynamic_full) else None
+        work = v["work"] if self.dynamic_full else None
 
         # branch B: full-neighbour history mean (the dominant kernel)
         ev_b = None
@@ -259,93 +259,129 @@ class HotPathStep:
         return self._pinned_out
 
     # -- cross-step pipelining --------------------------------------------------------------------
-    def capture_pipelined(self, warm0, warm1, host_io=False):
-        """One graph per step with TWO parallel branches: the rest of pass i (reading buffer set p) and
-        the sampler of batch i+1 (filling set 1-p).  The sampler is one latency-bound CTA; run beside
-        the aggregate that streams history rows on the other SMs it leaves the critical path.
+    def capture_pipelined(self, warm0, warm1, host_io=False, steps_per_graph=8):
+        """Graphs of S consecutive steps; inside a step two parallel branches: the rest of pass k
+        (reading buffer set k&1) and the sampler of batch k+1 (filling the other set).  The sampler is
+        one latency-bound CTA (a 256-thread, 48-register variant that fits beside two resident
+        full_mean CTAs); next to the aggregate that streams history rows it leaves the critical
+        path, and chaining S steps per launch amortises the ~10 us graph-to-graph turnaround.
         Sampler order, RNG stream, history reads and write-backs stay exactly sequential; the
         in-place row permutation is guarded on the device against the one possible race (a node
         shared by consecutive batches, see sgcn_sampler_pipeline).
 
-        host_io=True adds the H2D copy of the next batch's ids (from pinned staging) and the D2H copy
-        of the aggregated rows (to pinned memory) as memcpy nodes of the same graphs."""
+        host_io=True adds, as memcpy nodes, the H2D copy of the chunk's ids (from pinned staging)
+        and the D2H copy of every step's aggregated rows (to pinned memory)."""
+        S = int(steps_per_graph)
+        if S < 2 or S % 2:
+            raise ValueError("steps_per_graph must be even and >= 2")
         main = torch.cuda.current_stream(self.dev)
         for p, ids in ((0, warm0), (1, warm1)):       # eager warm-up of both buffer sets
             self.sampler.use_stream(main)
             self.ids2[p].copy_(ids)
-            ev_zero = self._fork_zero(main)
-            v = self._sample(p)
-            self._rest(v, main, ev_zero)
-            self._last_slot = p
+            self._eager_step(p, sample=True)
         torch.cuda.synchronize(self.dev)
         if not self._pipeline_on:
             self.sampler.pipeline(True)
             self._pipeline_on = True
+        B, width = self.B, self.out.shape[1]
+        # tab[c][k] = ids of the batch that step k of a parity-c chunk samples AHEAD (batch k+1 of the
+        # chunk; row S-1 is the first batch of the next chunk)
+        tab = [torch.zeros((S, B), dtype=torch.int32, device=self.dev) for _ in range(2)]
+        pin_tab = pin_out = None
         if host_io:
-            width = self.out.shape[1]
-            self._pin_ids2 = [torch.zeros(self.B, dtype=torch.int32).pin_memory() for _ in range(2)]
-            self._pinned_out = torch.empty((self.B, width), dtype=torch.float32).pin_memory()
+            pin_tab = [torch.zeros((S, B), dtype=torch.int32).pin_memory() for _ in range(2)]
+            pin_out = [torch.empty((S, B, width), dtype=torch.float32).pin_memory() for _ in range(2)]
         s_samp = self._s_samp
         self.sampler.use_stream(s_samp)               # outside any capture: set_stream synchronises
         side = torch.cuda.Stream(device=self.dev)
 
-        def sample_branch(slot):
-            if host_io:
-                self.ids2[slot].copy_(self._pin_ids2[slot], non_blocking=True)
-            self._sample(slot)
+        def set_prev(slot, ids_row):
+            """host bookkeeping only: the batch held by `slot` lives at ids_row when the graph replays"""
+            self.sampler.set_slot(slot)
+            self.sampler.start_batch(ids_row)
 
-        def rest_branch(slot, stream):
-            ev_zero = self._fork_zero(stream)
-            self._rest(self._views[slot], stream, ev_zero)
-            if host_io:
-                self._pinned_out.copy_(self.out, non_blocking=True)
+        def capture_chunk(c, closed):
+            g = torch.cuda.CUDAGraph()
+            set_prev(0, tab[1 - c][S - 1])            # slot 0 was sampled from the previous chunk's last row
+            with torch.cuda.graph(g, stream=side):
+                if host_io:
+                    tab[c].copy_(pin_tab[c], non_blocking=True)
+                for k in range(S):
+                    slot_r, slot_s = k & 1, 1 - (k & 1)
+                    ev_s = None
+                    if not (closed and k == S - 1):
+                        ev_root = torch.cuda.Event()
+                        ev_root.record(side)
+                        with torch.cuda.stream(s_samp):
+                            s_samp.wait_event(ev_root)
+                            self._sample(slot_s, tab[c][k])
+                            ev_s = torch.cuda.Event()
+                            ev_s.record(s_samp)
+                    ev_zero = self._fork_zero(side)
+                    self._rest(self._views[slot_r], side, ev_zero)
+                    if host_io:
+                        pin_out[c][k].copy_(self.out, non_blocking=True)
+                    if ev_s is not None:
+                        side.wait_event(ev_s)
+            return g
 
         first = torch.cuda.CUDAGraph()
         with torch.cuda.graph(first, stream=s_samp):
-            sample_branch(0)
-        both, last = [], []
-        for p in (0, 1):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
-                ev_root = torch.cuda.Event()
-                ev_root.record(side)
-                with torch.cuda.stream(s_samp):
-                    s_samp.wait_event(ev_root)
-                    sample_branch(1 - p)
-                    ev_s = torch.cuda.Event()
-                    ev_s.record(s_samp)
-                rest_branch(p, side)
-                side.wait_event(ev_s)
-            both.append(g)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
-                rest_branch(p, side)
-            last.append(g)
-        self._pipe = {"first": first, "both": both, "last": last, "host_io": host_io}
+            if host_io:
+                tab[1][S - 1].copy_(pin_tab[1][S - 1], non_blocking=True)
+            self._sample(0, tab[1][S - 1])
+        self._pipe = {"S": S, "first": first, "tab": tab, "pin_tab": pin_tab, "pin_out": pin_out,
+                      "host_io": host_io,
+                      "open": [capture_chunk(0, False), capture_chunk(1, False)],
+                      "closed": [capture_chunk(0, True), capture_chunk(1, True)]}
         return self._pipe
 
-    def run_pipelined(self, batches, on_result=None):
-        """Run len(batches) consecutive passes with one-batch sampler lookahead on the current stream:
-        per step one ids copy and ONE graph launch.  ``batches[i]``: int32 ids (CUDA tensors, or host
-        tensors when captured with host_io=True).  ``on_result(i, step)`` is called after pass i has
-        been enqueued (host_io: ``step._pinned_out`` holds the rows once the stream is synchronised)."""
+    def _eager_step(self, slot, sample):
+        main = torch.cuda.current_stream(self.dev)
+        if self.sampler._stream.cuda_stream != main.cuda_stream:
+            self.sampler.use_stream(main)
+        ev_zero = self._fork_zero(main)
+        if sample:
+            self._sample(slot, self.ids2[slot])
+        self._last_slot = slot
+        self._rest(self._views[slot], main, ev_zero)
+
+    def run_pipelined(self, batches, on_chunk=None):
+        """Run len(batches) consecutive passes with one-batch sampler lookahead on the current stream.
+        Per chunk of S steps: one ids copy and ONE graph launch.  ``batches``: int32 id tensors (CUDA;
+        host tensors when captured with host_io=True).  ``on_chunk(first_step, count, step)`` is
+        called after a chunk has been enqueued (host_io: ``step._pipe["pin_out"][c][:count]`` holds
+        the rows of those steps once the stream is synchronised; c = chunk parity)."""
         pipe = self._pipe
-        n = len(batches)
+        S, n = pipe["S"], len(batches)
         if n == 0:
             return self.out
-        stage = self._pin_ids2 if pipe["host_io"] else self.ids2
-        stage[0].copy_(batches[0], non_blocking=not pipe["host_io"])
-        pipe["first"].replay()
-        for i in range(n):
-            p = i & 1
-            if i + 1 < n:
-                stage[1 - p].copy_(batches[i + 1], non_blocking=not pipe["host_io"])
-                pipe["both"][p].replay()
-            else:
-                pipe["last"][p].replay()
-            self._last_slot = p
-            if on_result is not None:
-                on_result(i, self)
+        host_io = pipe["host_io"]
+        stage = pipe["pin_tab"] if host_io else pipe["tab"]
+        full, rem = divmod(n, S)
+        stage[1][S - 1].copy_(batches[0], non_blocking=not host_io)
+        pipe["first"].replay()                                  # sample batch 0 into buffer set 0
+        for c in range(full):
+            par = c & 1
+            base = c * S
+            closed = rem == 0 and c == full - 1
+            ahead = batches[base + 1: base + S + (0 if closed else 1)]
+            dst = stage[par]
+            for k, ids in enumerate(ahead):
+                dst[k].copy_(ids, non_blocking=not host_io)
+            pipe["closed" if closed else "open"][par].replay()
+            self._last_slot = (S - 1) & 1
+            if on_chunk is not None:
+                on_chunk(base, S, self)
+        if rem:                                                 # tail shorter than a chunk: eager passes
+            base = full * S
+            for j in range(rem):
+                slot = j & 1
+                if j > 0:
+                    self.ids2[slot].copy_(batches[base + j], non_blocking=True)
+                self._eager_step(slot, sample=j > 0)            # batch `base` was already sampled ahead
+                if on_chunk is not None:
+                    on_chunk(base + j, 1, self)
         return self.out
 
     def time_dominant_kernel(self, batches):

@@ -121,27 +121,40 @@ def test_pipelined_driver_matches_oracle_incl_overlapping_batches(mode, deg):
     batches[4] = torch.cat((batches[3][:20], batches[4][20:])).contiguous()     # shares 20 nodes with batch 3
     batches[5] = batches[4].flip(0).contiguous()                                # same nodes as batch 4
     # warm-up passes of capture_pipelined execute batches 0 and 1 eagerly
-    step.capture_pipelined(batches[0], batches[1])
+    step.capture_pipelined(batches[0], batches[1], host_io=True, steps_per_graph=4)
     for ids in batches[:2]:
         oracle_step(o, mode, deg, ids.cpu().numpy(), fh, hist, D, d_out)
     got = []
 
-    def grab(i, st):
+    def grab(first, count, st):
         torch.cuda.current_stream().synchronize()
-        got.append((st.out.cpu().numpy().copy(), st.dx.cpu().numpy().copy(), st.sizes()))
-    step.run_pipelined(batches[2:], on_result=grab)
+        if count > 1:      # a chunk graph: per-step rows were copied to pinned memory by the graph
+            c = (first // st._pipe["S"]) & 1
+            for k in range(count):
+                got.append(st._pipe["pin_out"][c][k].numpy().copy())
+        else:              # eager tail step
+            got.append(st.out.cpu().numpy().copy())
+    host_batches = [b.cpu() for b in batches[2:]]            # 7 steps = one chunk of 4 + a tail of 3
+    step.run_pipelined(host_batches, on_chunk=grab)
     torch.cuda.synchronize()
     for i, ids in enumerate(batches[2:]):
         oh, om, dx, s = oracle_step(o, mode, deg, ids.cpu().numpy(), fh, hist, D, d_out)
-        out, dxg, z = got[i]
-        assert z["n_in"] == len(s["field"]) and z["nnz_s"] == len(s["edg_s"]), "batch %d sizes" % i
-        close(out, oh, "pipelined batch %d out" % i)
-        close(dxg[:z["n_in"]], dx, "pipelined batch %d dx" % i)
+        close(got[i], oh, "pipelined batch %d out" % i)
+    z = step.sizes()
+    assert z["n_in"] == len(s["field"]) and z["nnz_s"] == len(s["edg_s"])
+    close(step.dx.cpu().numpy()[:z["n_in"]], dx, "pipelined last dx")
     if mode != "ns":
         assert np.array_equal(step.history.cpu().numpy(), hist)
     assert np.array_equal(step.sampler.host("adj_i", step.sampler.num_edges), o.vec("adj_i"))
-    # a second pipelined run and a plain eager pass keep working afterwards
-    step.run_pipelined(batches[:3])
+    # closed chunks (n a multiple of S), a second run and a plain eager pass keep working afterwards
+    seq2 = host_batches[:4] + host_batches[3:7]              # 8 steps = an open + a closed chunk
+    for ids in seq2:
+        oracle_step(o, mode, deg, ids.numpy(), fh, hist, D, d_out)
+    step.run_pipelined(seq2)
+    torch.cuda.synchronize()
+    if mode != "ns":
+        assert np.array_equal(step.history.cpu().numpy(), hist)
+    assert np.array_equal(step.sampler.host("adj_i", step.sampler.num_edges), o.vec("adj_i"))
     step.run(batches[6])
     torch.cuda.synchronize()
     assert step.sizes()["n_out"] == B

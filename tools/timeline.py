@@ -1,0 +1,67 @@
+"""Device timeline of one step (globaltimer stamps written by the kernels themselves, see
+sgcn_trace_set): start / end of every kernel class relative to the first kernel of the graph.
+Usage: python tools/timeline.py [serial|pipelined] [n_steps]"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from stochastic_gcn_b200 import _lib
+from stochastic_gcn_b200.step import HotPathStep
+
+NAMES = ["sampler", "full_mean", "gather", "sampled_fwd", "spmm_bwd", "history_update", "copy/zero", "exchange"]
+
+
+def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else "serial"
+    n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+    w = bench.WORKLOADS["reddit_cv"]
+    dev = torch.device("cuda", 0)
+    g, feats = bench.build_inputs(w, 1, dev, 1.0)
+    step = HotPathStep(g, feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"], seed=1)
+    batches = bench.make_batches(g.n, w["batch"], 64, 1, dev)
+    step.d_out.normal_()
+    trace = torch.zeros(16, dtype=torch.int64, device=dev)
+    _lib.load().sgcn_trace_set(C.c_void_p(trace.data_ptr()))       # before capture: baked into the graphs
+    init = torch.tensor([-1, 0] * 8, dtype=torch.int64, device=dev)  # min slots = ~0 (as uint64), max slots = 0
+    step.capture(batches[0])
+    if mode == "pipelined":
+        step.capture_pipelined(batches[0], batches[1])
+    for b in batches[2:12]:
+        step.replay(b) if mode == "serial" else None
+    if mode == "pipelined":
+        step.run_pipelined(batches[2:12])
+    torch.cuda.synchronize()
+    rows = []
+    if mode == "serial":
+        for b in batches[12:12 + n_steps]:
+            trace.copy_(init); torch.cuda.synchronize()
+            step.replay(b); torch.cuda.synchronize()
+            rows.append(trace.cpu().tolist())
+    else:
+        pipe = step._pipe
+        step.ids2[0].copy_(batches[12]); pipe["first"].replay(); torch.cuda.synchronize()
+        for i in range(n_steps):
+            p = i & 1
+            step.ids2[1 - p].copy_(batches[13 + i])
+            trace.copy_(init); torch.cuda.synchronize()
+            pipe["both"][p].replay(); torch.cuda.synchronize()
+            rows.append(trace.cpu().tolist())
+    for k, t in enumerate(rows):
+        starts = [t[2 * i] for i in range(8) if t[2 * i + 1] > 0]
+        t0 = min(starts)
+        end = max(t[2 * i + 1] for i in range(8))
+        print("step %d: graph span %.1f us" % (k, (end - t0) / 1e3))
+        for i in range(8):
+            if t[2 * i + 1] > 0:
+                print("    %-15s start %6.1f  end %6.1f  (%.1f us)" % (NAMES[i], (t[2 * i] - t0) / 1e3,
+                                                                      (t[2 * i + 1] - t0) / 1e3,
+                                                                      (t[2 * i + 1] - t[2 * i]) / 1e3))
+    _lib.load().sgcn_trace_set(None)
+
+
+if __name__ == "__main__":
+    main()
