@@ -32,12 +32,13 @@ int sgcn_abi_version(void);
 const char* sgcn_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t sgcn_launch_count(void);
-/* Device timeline (profiling aid).  buf16 = device uint64[16] or NULL (off).  Kernels launched (or
- * captured into a graph) while it is set stamp %globaltimer: buf[2k] = min block start (initialise
- * to ~0), buf[2k+1] = max block end (initialise to 0) for kernel class k: 0 sampler, 1 full-neighbour
- * mean, 2 row gather, 3 sampled aggregate, 4 SpMM backward, 5 history write-back, 6 copy/zero-pad,
- * 7 write-back exchange. */
-int sgcn_trace_set(void* buf16);
+/* Device timeline (profiling aid).  buf = device uint64[17 + 2*1024] or NULL (off).  Kernels launched
+ * (or captured into a graph) while it is set stamp %globaltimer: buf[2k] = min block start
+ * (initialise to ~0), buf[2k+1] = max block end (initialise to 0) for kernel class k: 0 sampler,
+ * 1 full-neighbour mean, 2 row gather, 3 sampled aggregate, 4 SpMM backward, 5 history write-back,
+ * 6 copy/zero-pad, 7 write-back exchange; buf[16] = event-log cursor (initialise to 0), then pairs
+ * (class << 1 | is_end, time) stamped by block 0 of every launch. */
+int sgcn_trace_set(void* buf);
 
 /* ------------------------------------------------------------------------------------------
  * Neighbour sampler.  Replaces `class Scheduler` (gcn/scheduler.h:6-28, gcn/scheduler.cpp:11-189)
@@ -129,6 +130,9 @@ int sgcn_sampler_pipeline(sgcn_sampler* s, int32_t enable);
 int sgcn_sampler_mark_consumed(sgcn_sampler* s, void* stream);
 /* the stream expand() runs on (cudaStream_t as void*); set to share the caller's stream */
 int sgcn_sampler_set_stream(sgcn_sampler* s, void* stream);
+/* same without synchronising the previous stream (legal during CUDA-graph capture; the caller
+ * orders the streams with events) */
+int sgcn_sampler_set_stream_async(sgcn_sampler* s, void* stream);
 /* std::mt19937 state (624 words) + cursor, for checkpointing (absent in the reference) */
 int sgcn_sampler_get_rng(sgcn_sampler* s, uint32_t state[624] /*HOST*/, int32_t* pos /*HOST*/);
 int sgcn_sampler_set_rng(sgcn_sampler* s, const uint32_t state[624] /*HOST*/, int32_t pos);

@@ -45,6 +45,7 @@ SIGNATURES = {
     "sgcn_sampler_vec": (_i32, [_vp, _i32, _i32, C.POINTER(_vp), C.POINTER(_i64)]),
     "sgcn_sampler_copy_vec": (_i32, [_vp, _i32, _i32, _vp, _i64]),
     "sgcn_sampler_set_stream": (_i32, [_vp, _vp]),
+    "sgcn_sampler_set_stream_async": (_i32, [_vp, _vp]),
     "sgcn_sampler_get_rng": (_i32, [_vp, _vp, C.POINTER(_i32)]),
     "sgcn_sampler_set_rng": (_i32, [_vp, _vp, _i32]),
     "sgcn_gather_rows": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _vp, _i64, _vp]),

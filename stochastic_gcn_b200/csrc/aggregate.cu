@@ -608,6 +608,11 @@ int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_
     do {                                                                                     \
         static int per_sm = 0;                                                               \
         if (per_sm == 0) {                                                                   \
+            /* ask for a ~100 KB shared-memory carve-out although two CTAs need far less: the next  \
+               batch's sampler CTA (up to ~47 KB) can then join an SM that runs this kernel without \
+               waiting for the SM to drain and re-partition its L1 / shared memory */            \
+            SGCN_CUDA(cudaFuncSetAttribute(full_mean_kernel<V, L, P>,                        \
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, 44)); \
             SGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                         \
                 &per_sm, full_mean_kernel<V, L, P>, kAggThreads,                             \
                 sizeof(int32_t) * (2 * (size_t)kFullStageRows + 2)));                        \

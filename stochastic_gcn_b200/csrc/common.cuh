@@ -81,14 +81,35 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// RAII-style block stamps: construct at kernel entry, call end() (or let it go out of scope) at exit
+// RAII-style stamps: construct at kernel entry; the destructor stamps the exit.
+// trace[0..15]: per-class min block start / max block end.  trace[16]: event-log cursor;
+// trace[17 + 2i], trace[18 + 2i]: (class << 1 | is_end, time) of block 0 of every launch (i < 1024).
+constexpr int kTraceLogCap = 1024;
 struct TraceScope {
     unsigned long long* t;
-    __device__ __forceinline__ TraceScope(unsigned long long* trace, int id) : t(trace ? trace + 2 * id : nullptr) {
-        if (t && threadIdx.x == 0) atomicMin(t, global_ns());
+    int id;
+    __device__ __forceinline__ void log(int is_end, unsigned long long now) {
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
+            const unsigned long long i = atomicAdd(t + 16, 1ull);
+            if (i < (unsigned long long)kTraceLogCap) {
+                t[17 + 2 * i] = (unsigned long long)((id << 1) | is_end);
+                t[18 + 2 * i] = now;
+            }
+        }
+    }
+    __device__ __forceinline__ TraceScope(unsigned long long* trace, int id_) : t(trace), id(id_) {
+        if (t && threadIdx.x == 0) {
+            const unsigned long long now = global_ns();
+            atomicMin(t + 2 * id, now);
+            log(0, now);
+        }
     }
     __device__ __forceinline__ ~TraceScope() {
-        if (t && threadIdx.x == 0) atomicMax(t + 1, global_ns());
+        if (t && threadIdx.x == 0) {
+            const unsigned long long now = global_ns();
+            atomicMax(t + 2 * id + 1, now);
+            log(1, now);
+        }
     }
 };
 

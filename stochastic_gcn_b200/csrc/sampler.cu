@@ -953,6 +953,10 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes));
             SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel<256, 5>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes));
+            // same ~100 KB carve-out as full_mean_kernel: whichever of the two reaches an SM first,
+            // the other can join it without a re-partition
+            SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel<256, 5>,
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, 44));
             attr_set = true;
         }
         const int hbits = fused_hash_bits(nb, (int)sb);
@@ -1310,6 +1314,16 @@ int sgcn_sampler_mark_consumed(sgcn_sampler* s, void* stream) {
     DeviceGuard guard(s->device);
     mark_consumed_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(s->pipe_counters);
     SGCN_LAUNCHED();
+    return SGCN_OK;
+}
+
+int sgcn_sampler_set_stream_async(sgcn_sampler* s, void* stream) {
+    SGCN_REQUIRE(s, "sampler_set_stream_async: null sampler");
+    if (s->own_stream && s->stream) {
+        set_error("sampler_set_stream_async: call sgcn_sampler_set_stream once first (the private stream must be retired with a synchronise)");
+        return SGCN_ESTATE;
+    }
+    s->stream = (cudaStream_t)stream;
     return SGCN_OK;
 }
 

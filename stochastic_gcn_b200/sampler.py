@@ -117,9 +117,11 @@ class DeviceSampler:
         """Tell the guard that one consumer pass has finished reading the adjacency rows."""
         check(self._lib.sgcn_sampler_mark_consumed(self._h, _lib.stream_ptr(stream)))
 
-    def use_stream(self, stream):
-        """Run expand() on a torch stream (e.g. the current one, for CUDA-graph capture)."""
-        check(self._lib.sgcn_sampler_set_stream(self._h, C.c_void_p(stream.cuda_stream)))
+    def use_stream(self, stream, sync=True):
+        """Run expand() on a torch stream (e.g. the current one, for CUDA-graph capture).  sync=False
+        skips the synchronisation of the previous stream (needed while a capture is in progress)."""
+        fn = self._lib.sgcn_sampler_set_stream if sync else self._lib.sgcn_sampler_set_stream_async
+        check(fn(self._h, C.c_void_p(stream.cuda_stream)))
         self._stream = stream
 
     # -- results ---------------------------------------------------------------------------------

@@ -9,13 +9,24 @@ per-step sequence (gcn/train.py:190,207; gcn/vrgcn.py:39-84; gcn/models.py:160-1
 
 All buffers are sized from upper bounds (|field| <= B(1+degree)) and every data-dependent length
 is read by the kernels from the sampler's device meta block, so the whole pass is a fixed launch
-sequence: it is captured once into a CUDA graph and replayed per batch.
+sequence that is captured into CUDA graphs and replayed per batch.
 
 The dense layers between the gather and the aggregate (``X = relu(LN(input @ W))``) are not part
 of the hot path: the aggregator input X is taken as the first ``hidden`` columns of
 the gathered feature rows (CVD: h = columns [0,hidden), mu = columns [hidden, 2 hidden)), and the
 upstream gradient dZ is a resident synthetic tensor, so the data dependencies gather -> aggregate
 -> backward -> write-back are the real ones.
+
+Launch topology (measured on B200, tools/graph_overhead.py + tools/timeline.py): inside a CUDA
+graph a dependent kernel starts ~0.8 us after its predecessor on the same branch and ~3 us after
+one on another branch.  The pass therefore keeps its dominant kernel and the write-back that must
+follow it on ONE chain,
+
+    main :  full_mean ─► history_update ─► (next step) full_mean ─► ...
+    side :  gather ─► sampled aggregate ─► dX init ─► SpMM backward ─► zero(next step's output)
+    samp :  sampler of the NEXT batch (one CTA, into the other buffer set)
+
+and everything short rides on branches that are long finished when the chain needs them.
 """
 import torch
 
@@ -40,7 +51,10 @@ class HotPathStep:
         self.n_nodes = graph.n
         self.sampler = DeviceSampler(graph.data, graph.indices, graph.indptr, L=1, cv=mode != "ns")
         self.sampler.seed(seed)
-        self.sampler.reserve(self.B, [self.degree])
+        for slot in (0, 1):                          # both per-batch buffer sets, sized once
+            self.sampler.set_slot(slot)
+            self.sampler.reserve(self.B, [self.degree])
+        self.sampler.set_slot(0)
         self.history = history if history is not None else torch.zeros(
             (graph.n, self.hidden), dtype=torch.float32, device=self.dev)     # vrgcn.py:23-36: zero-init
         self.n_in_bound = min(self.B * (1 + self.degree), max(graph.n, self.B))
@@ -51,8 +65,9 @@ class HotPathStep:
         self.ids = self.ids2[0]
         self.dynamic_full = False    # warps of full_mean_kernel pull chunks from a device counter
         self.x0 = z(self.n_in_bound, f)                 # gathered input rows
-        self.out = z(self.B, width)                     # aggregated h (or the only output)
-        self.out_mu = z(self.B, width) if mode == "cvd" else None
+        # aggregated rows, one buffer per sampler buffer set: the set not in use is zeroed one step ahead
+        self.outs = [z(self.B, width), z(self.B, width)]
+        self.outs_mu = [z(self.B, width), z(self.B, width)] if mode == "cvd" else [None, None]
         self.d_out = z(self.B, width)                   # upstream gradient (synthetic, resident)
         self.dx = z(self.n_in_bound, self.hidden)
         self.graph = None
@@ -60,12 +75,21 @@ class HotPathStep:
         self.launches_per_step = None
         self._views = [None, None]
         self._pinned_out = None
-        self._pipe = None           # graphs + events of the cross-step pipelined driver
+        self._pipe = None           # graphs of the cross-step pipelined driver
         self._pipeline_on = False
         self._last_slot = 0
-        self._s_b = torch.cuda.Stream(device=self.dev)   # side streams of the fork/join in _pass
-        self._s_c = torch.cuda.Stream(device=self.dev)
+        self._s_b = torch.cuda.Stream(device=self.dev)      # side branch of the pass
         self._s_samp = torch.cuda.Stream(device=self.dev)   # sampler branch of the pipelined graphs
+        self._s_chain = torch.cuda.Stream(device=self.dev)  # main chain of the pipelined graphs
+
+    @property
+    def out(self):
+        """aggregated rows of the most recent pass"""
+        return self.outs[self._last_slot]
+
+    @property
+    def out_mu(self):
+        return self.outs_mu[self._last_slot]
 
     # -- pieces ----------------------------------------------------------------------------------
     def _sample(self, slot=0, ids=None):
@@ -81,75 +105,76 @@ class HotPathStep:
             self._views[slot] = v
         return self._views[slot]
 
-    def _pass(self):
-        """sampler -> { gather -> sampled aggregate | full-neighbour history mean | backward } -> write-back.
-
-        The three middle branches are independent once the sampled sub-adjacency exists (both
-        aggregate kernels add into a pre-zeroed output with 128-bit reductions, so they commute);
-        they are forked onto side streams, which a CUDA-graph capture turns into parallel branches.
-        """
-        main = torch.cuda.current_stream(self.dev)
-        if getattr(self.sampler, "_stream", None) is None or self.sampler._stream.cuda_stream != main.cuda_stream:
-            self.sampler.use_stream(main)
-        ev_zero = self._fork_zero(main)          # runs beside the sampler
-        v = self._sample(0)
-        self._last_slot = 0
-        self._rest(v, main, ev_zero)
-
-    def _out_views(self):
+    def _out_views(self, slot):
         H = self.hidden
-        nb = self.out[:, H:] if self.concat else self.out
-        slf = self.out[:, :H] if self.concat else None
-        nb_mu = None
+        out, out_mu = self.outs[slot], self.outs_mu[slot]
+        nb = out[:, H:] if self.concat else out
+        slf = out[:, :H] if self.concat else None
+        nb_mu = slf_mu = None
         if self.mode == "cvd":
-            nb_mu = self.out_mu[:, H:] if self.concat else self.out_mu
-        return nb, slf, nb_mu
+            nb_mu = out_mu[:, H:] if self.concat else out_mu
+            slf_mu = out_mu[:, :H] if self.concat else None
+        return nb, slf, nb_mu, slf_mu
 
-    def _fork_zero(self, main):
-        """Zero the output halves the two aggregate kernels accumulate into, on a side stream."""
+    def _zero_out(self, slot):
+        """Zero the halves of outs[slot] that the two aggregate kernels accumulate into."""
         if self.mode == "ns":
-            return None
-        nb, _, nb_mu = self._out_views()
-        ev_root = torch.cuda.Event()
-        ev_root.record(main)
-        with torch.cuda.stream(self._s_b):
-            self._s_b.wait_event(ev_root)
-            ops.copy_rows_pad(None, 0, nb)
-            if nb_mu is not None:
-                ops.copy_rows_pad(None, 0, nb_mu)
-            ev_zero = torch.cuda.Event()
-            ev_zero.record(self._s_b)
-        return ev_zero
+            return
+        nb, _, nb_mu, _ = self._out_views(slot)
+        ops.copy_rows_pad(None, 0, nb)
+        if nb_mu is not None:
+            ops.copy_rows_pad(None, 0, nb_mu)
 
-    def _rest(self, v, main, ev_zero):
-        """Everything after the sampler, as three parallel branches joined by the write-back."""
+    def _rest(self, slot, main, zero_next=False, after=None, fork=None, side=None):
+        """Everything after the sampler for the batch held by buffer set `slot`.
+
+        outs[slot] must already be zero.  zero_next: also zero outs[1-slot] (for the next step) at the
+        end of the side branch.  after(side_stream): optional extra work enqueued on the side branch
+        once the aggregate is complete (e.g. the D2H copy of the step's result)."""
+        v = self._views[slot]
         pipelined = self._pipeline_on        # the sampler's device guard counts consumer passes
         H, B = self.hidden, self.B
         cv = self.mode != "ns"
-        nb, slf, nb_mu = self._out_views()
-        ev_sampled = torch.cuda.Event()
-        ev_sampled.record(main)
-        work = v["work"] if self.dynamic_full else None
+        nb, slf, nb_mu, slf_mu = self._out_views(slot)
+        side = side or self._s_b
+        ev_start = torch.cuda.Event()
+        ev_start.record(main)
 
-        # branch B: full-neighbour history mean (the dominant kernel)
-        ev_b = None
+        # main chain first (capture order = the order the driver feeds its hardware queues): the
+        # full-neighbour history mean (dominant); the write-back follows below
         if cv:
-            with torch.cuda.stream(self._s_b):
-                self._s_b.wait_event(ev_sampled)     # the zeroing precedes it on this same stream
-                ops.full_history_mean(v["field"], v["rowptr_f"], B, v["adj_p"], v["adj_i"], v["adj_w"],
-                                      self.history, nb_mu if self.mode == "cvd" else nb,
-                                      nb if self.mode == "cvd" else None, n_out_dev=v["n_out_dev"],
-                                      work_counter=work)
-                if pipelined:                        # adjacency rows of this batch are no longer read
-                    self.sampler.mark_consumed(self._s_b)
-                ev_b = torch.cuda.Event()
-                ev_b.record(self._s_b)
-        elif pipelined:
-            self.sampler.mark_consumed(main)
+            ops.full_history_mean(v["field"], v["rowptr_f"], B, v["adj_p"], v["adj_i"], v["adj_w"],
+                                  self.history, nb_mu if self.mode == "cvd" else nb,
+                                  nb if self.mode == "cvd" else None, n_out_dev=v["n_out_dev"],
+                                  work_counter=v["work"] if self.dynamic_full else None)
+        ev_full = torch.cuda.Event()
+        ev_full.record(main)
+        if fork is not None:
+            fork(ev_start)                       # e.g. the next batch's sampler branch
 
-        # branch C: backward of the aggregate, dX = adj^T (dZ_nb * scale) (+ dZ_self on the first B rows)
-        with torch.cuda.stream(self._s_c):
-            self._s_c.wait_event(ev_sampled)
+        # side branch: feature-row gather, sampled part of the aggregate, backward, next step's zeroing
+        with torch.cuda.stream(side):
+            side.wait_event(ev_start)
+            ops.gather_rows(self.features, v["field"], out=self.x0, n_dev=v["n_in_dev"])
+            x = self.x0[:, :H]
+            new_hist = None
+            if self.mode == "ns":
+                ops.spmm_csr(v["rowptr_s"], v["edg_t"], v["edg_w"], x, B, out=nb, n_out_dev=v["n_out_dev"])
+                if self.concat:
+                    ops.copy_rows_pad(x, B, slf, n_dev=v["n_out_dev"])
+            elif self.mode == "cv":
+                ops.cv_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], B, x, self.history, nb,
+                                   self_out=slf, n_out_dev=v["n_out_dev"], accumulate=True)
+                new_hist = x
+            else:
+                mu = self.x0[:, H:2 * H]
+                ops.cvd_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], v["scales"], B, x, mu,
+                                    self.history, nb, nb_mu, self_h=slf, self_mu=slf_mu,
+                                    n_out_dev=v["n_out_dev"], accumulate=True)
+                new_hist = mu
+            ev_fwd = torch.cuda.Event()          # last read of history on this branch
+            ev_fwd.record(side)
+            # dX = adj^T (dZ_nb * scale) (+ dZ_self on the first B rows)
             d_nb = self.d_out[:, H:] if self.concat else self.d_out
             if self.concat:
                 ops.copy_rows_pad(self.d_out[:, :H], B, self.dx, n_dev=v["n_out_dev"])
@@ -157,41 +182,36 @@ class HotPathStep:
                 ops.copy_rows_pad(None, 0, self.dx)
             ops.spmm_csr_bwd(v["rowptr_s"], v["edg_t"], v["edg_w"], d_nb, self.dx, B,
                              rscale=v["scales"] if self.mode == "cvd" else None, n_out_dev=v["n_out_dev"])
-            ev_c = torch.cuda.Event()
-            ev_c.record(self._s_c)
+            if zero_next:
+                self._zero_out(1 - slot)
 
-        # branch A (main): feature-row gather, then the sampled part of the aggregate
-        ops.gather_rows(self.features, v["field"], out=self.x0, n_dev=v["n_in_dev"])
-        x = self.x0[:, :H]
-        new_hist = None
-        if self.mode == "ns":
-            ops.spmm_csr(v["rowptr_s"], v["edg_t"], v["edg_w"], x, B, out=nb, n_out_dev=v["n_out_dev"])
-            if self.concat:
-                ops.copy_rows_pad(x, B, slf, n_dev=v["n_out_dev"])
-        elif self.mode == "cv":
-            main.wait_event(ev_zero)
-            ops.cv_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], B, x, self.history, nb,
-                               self_out=slf, n_out_dev=v["n_out_dev"], accumulate=True)
-            new_hist = x
-        else:
-            mu = self.x0[:, H:2 * H]
-            main.wait_event(ev_zero)
-            ops.cvd_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], v["scales"], B, x, mu,
-                                self.history, nb, nb_mu, self_h=slf,
-                                self_mu=self.out_mu[:, :H] if self.concat else None, n_out_dev=v["n_out_dev"],
-                                accumulate=True)
-            new_hist = mu
-
-        # join, then the history write-back (after every forward read of history, models.py:186-194)
-        if ev_b is not None:
-            main.wait_event(ev_b)
-        main.wait_event(ev_c)
-        if new_hist is not None:
+        main.wait_event(ev_fwd)                  # every forward read of history precedes the write-back
+        if new_hist is not None:                 # (models.py:186-194)
             self._write_back(v, new_hist)
+
+        with torch.cuda.stream(side):
+            side.wait_event(ev_full)
+            if pipelined:                        # adjacency rows of this batch are no longer read
+                self.sampler.mark_consumed(side)
+            if after is not None:
+                after(side)
+            ev_side = torch.cuda.Event()
+            ev_side.record(side)
+        main.wait_event(ev_side)
 
     def _write_back(self, v, new_hist):
         """tf.scatter_update(history, fields[0], new_history); the sharded subclass exchanges instead"""
         ops.history_update(self.history, v["field"], new_hist, n_dev=v["n_in_dev"])
+
+    def _pass(self):
+        """One whole pass on the current stream: zero -> sampler -> rest (buffer set 0)."""
+        main = torch.cuda.current_stream(self.dev)
+        if getattr(self.sampler, "_stream", None) is None or self.sampler._stream.cuda_stream != main.cuda_stream:
+            self.sampler.use_stream(main)
+        self._zero_out(0)
+        self._sample(0)
+        self._last_slot = 0
+        self._rest(0, main)
 
     # -- drivers ---------------------------------------------------------------------------------
     def run(self, ids):
@@ -217,13 +237,14 @@ class HotPathStep:
 
     def replay(self, ids):
         self.ids.copy_(ids, non_blocking=True)
+        self._last_slot = 0
         self.graph.replay()
         return self.out
 
     def capture_host(self):
         """Second graph for the host-buffer API: H2D of the pinned ids, the pass, D2H of the result
         -- the copies are memcpy nodes of the same graph, so a step is ONE launch + ONE sync."""
-        width = self.out.shape[1]
+        width = self.outs[0].shape[1]
         self._pin_ids = torch.zeros(self.B, dtype=torch.int32).pin_memory()
         self._pinned_out = torch.empty((self.B, width), dtype=torch.float32).pin_memory()
         torch.cuda.synchronize(self.dev)
@@ -233,7 +254,7 @@ class HotPathStep:
         with torch.cuda.graph(g, stream=side):
             self.ids.copy_(self._pin_ids, non_blocking=True)
             self._pass()
-            self._pinned_out.copy_(self.out, non_blocking=True)
+            self._pinned_out.copy_(self.outs[0], non_blocking=True)
         self.graph_host = g
         self._capture_stream = side
         return g
@@ -242,30 +263,31 @@ class HotPathStep:
         """End-to-end call with HOST buffers: int32 ids in (host memory), aggregated rows out (pinned
         host memory).  Per call: a 2 KB host copy into the staging buffer, one graph launch (H2D +
         pass + D2H), one stream synchronise."""
-        if getattr(self, "graph_host", None) is not None:
+        self._last_slot = 0
+        if self.graph_host is not None:
             self._pin_ids.copy_(ids_pinned)
             self.graph_host.replay()
             torch.cuda.current_stream(self.dev).synchronize()
             return self._pinned_out
         if self._pinned_out is None:
-            self._pinned_out = torch.empty(self.out.shape, dtype=torch.float32).pin_memory()
+            self._pinned_out = torch.empty(self.outs[0].shape, dtype=torch.float32).pin_memory()
         self.ids.copy_(ids_pinned, non_blocking=True)
         if self.graph is not None:
             self.graph.replay()
         else:
             self._pass()
-        self._pinned_out.copy_(self.out, non_blocking=True)
+        self._pinned_out.copy_(self.outs[0], non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
         return self._pinned_out
 
     # -- cross-step pipelining --------------------------------------------------------------------
     def capture_pipelined(self, warm0, warm1, host_io=False, steps_per_graph=8):
-        """Graphs of S consecutive steps; inside a step two parallel branches: the rest of pass k
-        (reading buffer set k&1) and the sampler of batch k+1 (filling the other set).  The sampler is
-        one latency-bound CTA (a 256-thread, 48-register variant that fits beside two resident
-        full_mean CTAs); next to the aggregate that streams history rows it leaves the critical
-        path, and chaining S steps per launch amortises the ~10 us graph-to-graph turnaround.
-        Sampler order, RNG stream, history reads and write-backs stay exactly sequential; the
+        """Graphs of S consecutive steps.  Inside step k three branches run side by side: the main
+        chain (full-neighbour mean -> write-back) and the side branch of pass k, both reading buffer
+        set k&1, and the sampler of batch k+1 filling the other set.  The sampler is one
+        latency-bound CTA (a 256-thread, 48-register variant that fits beside two resident
+        full_mean CTAs): next to the aggregate that streams history rows it leaves the critical
+        path.  Sampler order, RNG stream, history reads and write-backs stay exactly sequential; the
         in-place row permutation is guarded on the device against the one possible race (a node
         shared by consecutive batches, see sgcn_sampler_pipeline).
 
@@ -276,14 +298,13 @@ class HotPathStep:
             raise ValueError("steps_per_graph must be even and >= 2")
         main = torch.cuda.current_stream(self.dev)
         for p, ids in ((0, warm0), (1, warm1)):       # eager warm-up of both buffer sets
-            self.sampler.use_stream(main)
             self.ids2[p].copy_(ids)
             self._eager_step(p, sample=True)
         torch.cuda.synchronize(self.dev)
         if not self._pipeline_on:
             self.sampler.pipeline(True)
             self._pipeline_on = True
-        B, width = self.B, self.out.shape[1]
+        B, width = self.B, self.outs[0].shape[1]
         # tab[c][k] = ids of the batch that step k of a parity-c chunk samples AHEAD (batch k+1 of the
         # chunk; row S-1 is the first batch of the next chunk)
         tab = [torch.zeros((S, B), dtype=torch.int32, device=self.dev) for _ in range(2)]
@@ -295,6 +316,9 @@ class HotPathStep:
         self.sampler.use_stream(s_samp)               # outside any capture: set_stream synchronises
         side = torch.cuda.Stream(device=self.dev)
 
+        pools = [[torch.cuda.Stream(device=self.dev) for _ in range(S)] for _ in range(2)]
+        self._stream_pools = pools
+
         def set_prev(slot, ids_row):
             """host bookkeeping only: the batch held by `slot` lives at ids_row when the graph replays"""
             self.sampler.set_slot(slot)
@@ -303,32 +327,47 @@ class HotPathStep:
         def capture_chunk(c, closed):
             g = torch.cuda.CUDAGraph()
             set_prev(0, tab[1 - c][S - 1])            # slot 0 was sampled from the previous chunk's last row
+            chain = self._s_chain
             with torch.cuda.graph(g, stream=side):
-                if host_io:
-                    tab[c].copy_(pin_tab[c], non_blocking=True)
-                for k in range(S):
-                    slot_r, slot_s = k & 1, 1 - (k & 1)
-                    ev_s = None
-                    if not (closed and k == S - 1):
-                        ev_root = torch.cuda.Event()
-                        ev_root.record(side)
-                        with torch.cuda.stream(s_samp):
-                            s_samp.wait_event(ev_root)
-                            self._sample(slot_s, tab[c][k])
-                            ev_s = torch.cuda.Event()
-                            ev_s.record(s_samp)
-                    ev_zero = self._fork_zero(side)
-                    self._rest(self._views[slot_r], side, ev_zero)
+                # the capture-origin stream only forks and joins: on this driver the first kernel of
+                # the ORIGIN stream starts tens of microseconds after those of forked streams
+                ev_in = torch.cuda.Event()
+                ev_in.record(side)
+                with torch.cuda.stream(chain):
+                    chain.wait_event(ev_in)
                     if host_io:
-                        pin_out[c][k].copy_(self.out, non_blocking=True)
-                    if ev_s is not None:
-                        side.wait_event(ev_s)
+                        tab[c].copy_(pin_tab[c], non_blocking=True)
+                    for k in range(S):
+                        slot_r, slot_s = k & 1, 1 - (k & 1)
+                        ev_box = []
+
+                        def fork(ev_start, slot_s=slot_s, k=k, ev_box=ev_box):
+                            st = pools[0][k]                   # a stream of its own per step: the driver
+                            self.sampler.use_stream(st, sync=False)   # feeds its queues in capture order
+                            with torch.cuda.stream(st):
+                                st.wait_event(ev_start)
+                                self._sample(slot_s, tab[c][k])
+                                ev_s = torch.cuda.Event()
+                                ev_s.record(st)
+                                ev_box.append(ev_s)
+                        after = None
+                        if host_io:
+                            dst, src = pin_out[c][k], self.outs[slot_r]
+                            after = lambda st, dst=dst, src=src: dst.copy_(src, non_blocking=True)
+                        self._rest(slot_r, chain, zero_next=True, after=after,
+                                   fork=None if (closed and k == S - 1) else fork, side=pools[1][k])
+                        if ev_box:
+                            chain.wait_event(ev_box[0])
+                    ev_out = torch.cuda.Event()
+                    ev_out.record(chain)
+                side.wait_event(ev_out)
             return g
 
         first = torch.cuda.CUDAGraph()
         with torch.cuda.graph(first, stream=s_samp):
             if host_io:
                 tab[1][S - 1].copy_(pin_tab[1][S - 1], non_blocking=True)
+            self._zero_out(0)
             self._sample(0, tab[1][S - 1])
         self._pipe = {"S": S, "first": first, "tab": tab, "pin_tab": pin_tab, "pin_out": pin_out,
                       "host_io": host_io,
@@ -340,18 +379,18 @@ class HotPathStep:
         main = torch.cuda.current_stream(self.dev)
         if self.sampler._stream.cuda_stream != main.cuda_stream:
             self.sampler.use_stream(main)
-        ev_zero = self._fork_zero(main)
         if sample:
+            self._zero_out(slot)
             self._sample(slot, self.ids2[slot])
         self._last_slot = slot
-        self._rest(self._views[slot], main, ev_zero)
+        self._rest(slot, main, zero_next=True)
 
     def run_pipelined(self, batches, on_chunk=None):
         """Run len(batches) consecutive passes with one-batch sampler lookahead on the current stream.
-        Per chunk of S steps: one ids copy and ONE graph launch.  ``batches``: int32 id tensors (CUDA;
-        host tensors when captured with host_io=True).  ``on_chunk(first_step, count, step)`` is
-        called after a chunk has been enqueued (host_io: ``step._pipe["pin_out"][c][:count]`` holds
-        the rows of those steps once the stream is synchronised; c = chunk parity)."""
+        Per chunk of S steps: the ids copies and ONE graph launch.  ``batches``: int32 id tensors
+        (CUDA; host tensors when captured with host_io=True).  ``on_chunk(first_step, count, step)``
+        is called after a chunk has been enqueued (host_io: ``step._pipe["pin_out"][c][:count]``
+        holds the rows of those steps once the stream is synchronised; c = chunk parity)."""
         pipe = self._pipe
         S, n = pipe["S"], len(batches)
         if n == 0:
@@ -360,7 +399,7 @@ class HotPathStep:
         stage = pipe["pin_tab"] if host_io else pipe["tab"]
         full, rem = divmod(n, S)
         stage[1][S - 1].copy_(batches[0], non_blocking=not host_io)
-        pipe["first"].replay()                                  # sample batch 0 into buffer set 0
+        pipe["first"].replay()                                  # zero outs[0]; sample batch 0 into set 0
         for c in range(full):
             par = c & 1
             base = c * S
@@ -393,7 +432,7 @@ class HotPathStep:
         dev, B, H = self.dev, self.B, self.hidden
         v = self._views[0]
         deg = (v["adj_p"][1:] - v["adj_p"][:-1])
-        scratch = torch.zeros_like(self.out)
+        scratch = torch.zeros_like(self.outs[0])
         total_bytes, calls = 0, []
         if self.mode == "ns":
             for b in batches:
@@ -432,7 +471,7 @@ class HotPathStep:
 
     def sizes(self):
         """(n_out, n_in, nnz_s, nnz_f) of the last pass (synchronises)."""
-        m = self._views[getattr(self, "_last_slot", 0)]["meta"].cpu().tolist()
+        m = self._views[self._last_slot]["meta"].cpu().tolist()
         if m[5]:
             raise _lib.SgcnError(_lib.SGCN_EDATA, "sampler status %d" % m[5])
         return {"n_out": m[0], "n_in": m[1], "nnz_s": m[2], "nnz_f": m[3]}

@@ -24,16 +24,16 @@ def main():
     step = HotPathStep(g, feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"], seed=1)
     batches = bench.make_batches(g.n, w["batch"], 64, 1, dev)
     step.d_out.normal_()
-    trace = torch.zeros(16, dtype=torch.int64, device=dev)
+    LOG = 17 + 2 * 1024
+    trace = torch.zeros(LOG, dtype=torch.int64, device=dev)
     _lib.load().sgcn_trace_set(C.c_void_p(trace.data_ptr()))       # before capture: baked into the graphs
-    init = torch.tensor([-1, 0] * 8, dtype=torch.int64, device=dev)  # min slots = ~0 (as uint64), max slots = 0
+    init = torch.zeros(LOG, dtype=torch.int64, device=dev)           # min slots = ~0 (as uint64), max slots = 0
+    init[0:16:2] = -1
     step.capture(batches[0])
     if mode == "pipelined":
-        step.capture_pipelined(batches[0], batches[1])
+        step.capture_pipelined(batches[0], batches[1], steps_per_graph=n_steps)
     for b in batches[2:12]:
         step.replay(b) if mode == "serial" else None
-    if mode == "pipelined":
-        step.run_pipelined(batches[2:12])
     torch.cuda.synchronize()
     rows = []
     if mode == "serial":
@@ -43,13 +43,30 @@ def main():
             rows.append(trace.cpu().tolist())
     else:
         pipe = step._pipe
-        step.ids2[0].copy_(batches[12]); pipe["first"].replay(); torch.cuda.synchronize()
-        for i in range(n_steps):
-            p = i & 1
-            step.ids2[1 - p].copy_(batches[13 + i])
-            trace.copy_(init); torch.cuda.synchronize()
-            pipe["both"][p].replay(); torch.cuda.synchronize()
-            rows.append(trace.cpu().tolist())
+        S = pipe["S"]
+        step.run_pipelined(batches[12:12 + S])                       # settle
+        tab = pipe["tab"]
+        tab[1][S - 1].copy_(batches[30]); pipe["first"].replay()
+        for k in range(S):
+            tab[0][k].copy_(batches[31 + k])
+        trace.copy_(init); torch.cuda.synchronize()
+        pipe["open"][0].replay(); torch.cuda.synchronize()
+        t = trace.cpu().tolist()
+        n = min(t[16], 1024)
+        ev = sorted((t[18 + 2 * i], t[17 + 2 * i]) for i in range(n))
+        t0 = ev[0][0]
+        print("one open chunk of %d steps: %d events, span %.1f us (%.1f us / step)" % (
+            S, n, (ev[-1][0] - t0) / 1e3, (ev[-1][0] - t0) / 1e3 / S))
+        open_at = {}
+        for tm, code in ev:
+            cls, is_end = code >> 1, code & 1
+            if not is_end:
+                open_at[cls] = tm
+            else:
+                print("    %-15s %7.1f -> %7.1f  (%.1f us)" % (NAMES[cls], (open_at.get(cls, tm) - t0) / 1e3,
+                                                               (tm - t0) / 1e3, (tm - open_at.get(cls, tm)) / 1e3))
+        _lib.load().sgcn_trace_set(None)
+        return
     for k, t in enumerate(rows):
         starts = [t[2 * i] for i in range(8) if t[2 * i + 1] > 0]
         t0 = min(starts)
