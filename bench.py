@@ -328,12 +328,19 @@ def run_ours(args, w):
         stream = torch.cuda.current_stream(dev)
         out_host = step._pipe["pin_out"][0][0]
 
-        def fetch(first, count, st):
-            stream.synchronize()          # the caller waits for (and may read) the results chunk by chunk
+        pending = []
+
+        def fetch(first, count, st, done):
+            # the caller waits for (and may read) every step's rows, one chunk behind the launches
+            if pending:
+                pending.pop().synchronize()
+            pending.append(done)
         step.run_pipelined(pinned[:args.steps_per_graph], on_chunk=fetch)
+        pending.pop().synchronize()
         barrier()
         e0.record()
         step.run_pipelined(pinned, on_chunk=fetch)
+        pending.pop().synchronize()
         e1.record()
         barrier()
     else:

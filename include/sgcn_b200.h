@@ -107,6 +107,7 @@ enum {
     SGCN_VEC_ROWPTR_F = 11,/* int32  CSR row pointers of the full-neighbour adjacency [n_out+1] */
     SGCN_VEC_TGT = 12,     /* int32  sampled edge col as GLOBAL node id               [nnz_s] */
     SGCN_VEC_META = 13,    /* int32  device copy of the 6 sizes of sgcn_sampler_sizes [6]     */
+    SGCN_VEC_PIPE = 14,    /* int32  pipelining counters {expands finished, consumer passes} [2] */
     SGCN_VEC_SCALES = 100, /* float  scales                                           [n_out] */
     SGCN_VEC_EDG_W = 101,  /* float                                                   [nnz_s] */
     SGCN_VEC_MEDG_W = 102, /* float                                                   [nnz_s] */
@@ -226,7 +227,10 @@ int sgcn_cvd_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float
  *   hist[idx[i], :] = rows[i, :]   (idx distinct) */
 int sgcn_history_update(float* hist, int64_t ld_h, const int32_t* idx, int32_t n,
                         const int32_t* n_dev, const float* rows, int64_t ld_rows, int32_t D,
-                        void* stream);
+                        int32_t* done_counter, void* stream);
+/* done_counter (optional device int32): incremented once when the kernel starts, i.e. when everything
+ * stream-ordered before the write-back has finished -- the pipelined step passes the sampler's
+ * consumer counter (SGCN_VEC_PIPE[1]) instead of a separate sgcn_sampler_mark_consumed launch. */
 
 /* dst[i, :] = src[i, :] for i < n (strided 2-D copy; self-row gradient / concat halves) and
  * dst[i, :] = 0 for n <= i < n_total */
@@ -274,6 +278,32 @@ int sgcn_ipc_free(void* ptr);
 int sgcn_ipc_export(void* ptr, void* handle64 /*HOST out*/);
 int sgcn_ipc_open(const void* handle64 /*HOST*/, void** ptr /*HOST out*/);
 int sgcn_ipc_close(void* ptr);
+
+/* ------------------------------------------------------------------------------------------
+ * Step-level fusions (fewer CUDA-graph nodes per training step; same arithmetic as the pieces).
+ * ------------------------------------------------------------------------------------------ */
+/* two independent sgcn_copy_rows_pad jobs in one launch (a NULL dst skips a job) */
+int sgcn_copy_rows_pad_pair(const float* src0, int64_t ld_src0, int32_t n0, const int32_t* n0_dev,
+                            int32_t n_total0, int32_t D0, float* dst0, int64_t ld_dst0,
+                            const float* src1, int64_t ld_src1, int32_t n1, const int32_t* n1_dev,
+                            int32_t n_total1, int32_t D1, float* dst1, int64_t ld_dst1, void* stream);
+/* sgcn_cv_sampled_fwd / sgcn_cvd_sampled_fwd followed, row by row in the same kernel, by the
+ * backward scatter of sgcn_spmm_csr_bwd (dx[cols[e]] += vals[e] * (scale[r]) * dy[r]; dx initialised
+ * by the caller).  The forward never reads dx and the backward never reads y, so fusing them only
+ * saves a launch. */
+int sgcn_cv_sampled_fwd_bwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                            const int32_t* tgt, int32_t n_out, const int32_t* n_out_dev,
+                            const float* x, int64_t ld_x, const float* hist, int64_t ld_h, int32_t D,
+                            float* y, int64_t ld_y, float* self, int64_t ld_self, int32_t accumulate,
+                            const float* dy, int64_t ld_dy, float* dx, int64_t ld_dx, void* stream);
+int sgcn_cvd_sampled_fwd_bwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                             const int32_t* tgt, const float* scale, int32_t n_out,
+                             const int32_t* n_out_dev, const float* h, int64_t ld_hh,
+                             const float* mu, int64_t ld_mu, const float* hist, int64_t ld_h,
+                             int32_t D, float* yh, int64_t ld_yh, float* ymu, int64_t ld_ymu,
+                             float* self_h, int64_t ld_sh, float* self_mu, int64_t ld_sm,
+                             int32_t accumulate, const float* dy, int64_t ld_dy, float* dx,
+                             int64_t ld_dx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ SGCN_OK, SGCN_EINVAL, SGCN_ECUDA, SGCN_ESTATE, SGCN_EDATA = 0, -1, -2, -3, -4
 # vector ids of sgcn_sampler_vec (include/sgcn_b200.h)
 VEC_FIELD, VEC_FFIELD, VEC_EDG_S, VEC_EDG_T, VEC_FEDG_S, VEC_FEDG_T = 0, 1, 2, 3, 4, 5
 VEC_ADJ_I, VEC_ADJ_P, VEC_ROWPTR_S, VEC_ROWPTR_F, VEC_TGT, VEC_META = 6, 7, 10, 11, 12, 13
+VEC_PIPE = 14
 VEC_SCALES, VEC_EDG_W, VEC_MEDG_W, VEC_FEDG_W, VEC_ADJ_W, VEC_IMPORTANCE = 100, 101, 102, 103, 104, 105
 FLOAT_VECS = {VEC_SCALES, VEC_EDG_W, VEC_MEDG_W, VEC_FEDG_W, VEC_ADJ_W, VEC_IMPORTANCE}
 
@@ -63,7 +64,14 @@ SIGNATURES = {
                                    _i64, _vp, _i64, _i32, _vp]),
     "sgcn_cvd_sampled_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _vp,
                                     _i64, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
-    "sgcn_history_update": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _i32, _vp]),
+    "sgcn_history_update": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "sgcn_copy_rows_pad_pair": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64,
+                                       _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "sgcn_cv_sampled_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i32, _vp,
+                                       _i64, _vp, _i64, _i32, _vp, _i64, _vp, _i64, _vp]),
+    "sgcn_cvd_sampled_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _vp,
+                                        _i64, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32,
+                                        _vp, _i64, _vp, _i64, _vp]),
     "sgcn_copy_rows_pad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "sgcn_wb_payload_bytes": (_i64, [_i32, _i32]),
     "sgcn_wb_pack": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), _i32, _i32, _vp]),

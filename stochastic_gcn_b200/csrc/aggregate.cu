@@ -71,6 +71,8 @@ struct SampledArgs {
     int accumulate;                    // 0: overwrite y; 1: y += (PLAIN: read-modify-write by the row's
                                        // owner; CV/CVD: 128-bit RED, commutes with full_mean_kernel)
     unsigned long long* trace;
+    // optional fused backward of the same sampled adjacency: dx[cols[e]] += vals[e] * bscale[r] * dy[r]
+    const float* dy; int64_t ld_dy; float* dx; int64_t ld_dx; const float* bscale;
 };
 
 template <typename V, int LPR, int VPL, int MODE>
@@ -146,6 +148,21 @@ sampled_rows_kernel(const SampledArgs a) {
                                    T::ld(a.x + (int64_t)r * a.ld_x + off[k]));
                 if (a.self1) T::st(a.self1 + (int64_t)r * a.ld_s1 + off[k],
                                    T::ld(a.mu + (int64_t)r * a.ld_mu + off[k]));
+            }
+        }
+        if (a.dx && e1 > e0) {
+            // backward of this row while its edge list is hot (dx was initialised by the caller)
+            const float s = a.bscale ? a.bscale[r] : 1.f;
+            V g[VPL];
+#pragma unroll
+            for (int k = 0; k < VPL; ++k)
+                g[k] = ok[k] ? T::mul(T::ld(a.dy + (int64_t)r * a.ld_dy + off[k]), s) : T::zero();
+            for (int e = e0; e < e1; ++e) {
+                const int64_t c = __ldg(a.cols + e);
+                const float w = __ldg(a.vals + e);
+#pragma unroll
+                for (int k = 0; k < VPL; ++k)
+                    if (ok[k]) T::red(a.dx + c * a.ld_dx + off[k], T::mul(g[k], w));
             }
         }
     }
@@ -458,6 +475,7 @@ static int launch_sampled(SampledArgs a, int D, bool vec_ok, cudaStream_t st) {
         if (a.ymu) t.ymu = a.ymu + c0;
         if (a.self0) t.self0 = a.self0 + c0;
         if (a.self1) t.self1 = a.self1 + c0;
+        if (a.dx) { t.dy = a.dy + c0; t.dx = a.dx + c0; }
         const int grid = grid_for_groups(a.n_out, sh.lpr);
 #define CALL(V, L, P) sampled_rows_kernel<V, L, P, MODE><<<grid, kAggThreads, 0, st>>>(t)
         SGCN_DISPATCH_SHAPE(sh, CALL);
@@ -532,6 +550,62 @@ int sgcn_cvd_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float
                         aligned16(hist) && aligned16(yh) && aligned16(ymu) &&
                         (!self_h || (ld_sh % 4 == 0 && aligned16(self_h))) &&
                         (!self_mu || (ld_sm % 4 == 0 && aligned16(self_mu)));
+    return launch_sampled<MODE_CVD>(a, D, vec_ok, (cudaStream_t)stream);
+}
+
+static bool bwd_ok(const float* dy, int64_t ld_dy, const float* dx, int64_t ld_dx, int32_t D) {
+    return dy && dx && ld_dy >= D && ld_dx >= D;
+}
+static bool bwd_vec(const float* dy, int64_t ld_dy, const float* dx, int64_t ld_dx) {
+    return ld_dy % 4 == 0 && ld_dx % 4 == 0 && aligned16(dy) && aligned16(dx);
+}
+
+int sgcn_cv_sampled_fwd_bwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                            const int32_t* tgt, int32_t n_out, const int32_t* n_out_dev,
+                            const float* x, int64_t ld_x, const float* hist, int64_t ld_h, int32_t D,
+                            float* y, int64_t ld_y, float* self, int64_t ld_self, int32_t accumulate,
+                            const float* dy, int64_t ld_dy, float* dx, int64_t ld_dx, void* stream) {
+    SGCN_REQUIRE(n_out >= 0 && D >= 0, "cv_sampled_fwd_bwd: negative size");
+    if (n_out == 0 || D == 0) return SGCN_OK;
+    SGCN_REQUIRE(rowptr && x && hist && y, "cv_sampled_fwd_bwd: null pointer");
+    SGCN_REQUIRE(ld_x >= D && ld_h >= D && ld_y >= D && (!self || ld_self >= D) && bwd_ok(dy, ld_dy, dx, ld_dx, D),
+                 "cv_sampled_fwd_bwd: bad row stride or null gradient buffers");
+    SampledArgs a{};
+    a.rowptr = rowptr; a.cols = cols; a.vals = vals; a.map = tgt;
+    a.n_out = n_out; a.n_out_dev = n_out_dev; a.x = x; a.ld_x = ld_x; a.hist = hist; a.ld_h = ld_h;
+    a.y = y; a.ld_y = ld_y; a.self0 = self; a.ld_s0 = ld_self; a.accumulate = accumulate;
+    a.dy = dy; a.ld_dy = ld_dy; a.dx = dx; a.ld_dx = ld_dx;
+    const bool vec_ok = D % 4 == 0 && ld_x % 4 == 0 && ld_h % 4 == 0 && ld_y % 4 == 0 &&
+                        aligned16(x) && aligned16(hist) && aligned16(y) &&
+                        (!self || (ld_self % 4 == 0 && aligned16(self))) && bwd_vec(dy, ld_dy, dx, ld_dx);
+    return launch_sampled<MODE_CV>(a, D, vec_ok, (cudaStream_t)stream);
+}
+
+int sgcn_cvd_sampled_fwd_bwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                             const int32_t* tgt, const float* scale, int32_t n_out,
+                             const int32_t* n_out_dev, const float* h, int64_t ld_hh,
+                             const float* mu, int64_t ld_mu, const float* hist, int64_t ld_h,
+                             int32_t D, float* yh, int64_t ld_yh, float* ymu, int64_t ld_ymu,
+                             float* self_h, int64_t ld_sh, float* self_mu, int64_t ld_sm,
+                             int32_t accumulate, const float* dy, int64_t ld_dy, float* dx,
+                             int64_t ld_dx, void* stream) {
+    SGCN_REQUIRE(n_out >= 0 && D >= 0, "cvd_sampled_fwd_bwd: negative size");
+    if (n_out == 0 || D == 0) return SGCN_OK;
+    SGCN_REQUIRE(rowptr && scale && h && mu && hist && yh && ymu, "cvd_sampled_fwd_bwd: null pointer");
+    SGCN_REQUIRE(ld_hh >= D && ld_mu >= D && ld_h >= D && ld_yh >= D && ld_ymu >= D &&
+                     (!self_h || ld_sh >= D) && (!self_mu || ld_sm >= D) && bwd_ok(dy, ld_dy, dx, ld_dx, D),
+                 "cvd_sampled_fwd_bwd: bad row stride or null gradient buffers");
+    SampledArgs a{};
+    a.rowptr = rowptr; a.cols = cols; a.vals = vals; a.map = tgt; a.scale = scale;
+    a.n_out = n_out; a.n_out_dev = n_out_dev; a.x = h; a.ld_x = ld_hh; a.mu = mu; a.ld_mu = ld_mu;
+    a.hist = hist; a.ld_h = ld_h; a.y = yh; a.ld_y = ld_yh; a.ymu = ymu; a.ld_ymu = ld_ymu;
+    a.self0 = self_h; a.ld_s0 = ld_sh; a.self1 = self_mu; a.ld_s1 = ld_sm; a.accumulate = accumulate;
+    a.dy = dy; a.ld_dy = ld_dy; a.dx = dx; a.ld_dx = ld_dx; a.bscale = scale;
+    const bool vec_ok = D % 4 == 0 && ld_hh % 4 == 0 && ld_mu % 4 == 0 && ld_h % 4 == 0 &&
+                        ld_yh % 4 == 0 && ld_ymu % 4 == 0 && aligned16(h) && aligned16(mu) &&
+                        aligned16(hist) && aligned16(yh) && aligned16(ymu) &&
+                        (!self_h || (ld_sh % 4 == 0 && aligned16(self_h))) &&
+                        (!self_mu || (ld_sm % 4 == 0 && aligned16(self_mu))) && bwd_vec(dy, ld_dy, dx, ld_dx);
     return launch_sampled<MODE_CVD>(a, D, vec_ok, (cudaStream_t)stream);
 }
 

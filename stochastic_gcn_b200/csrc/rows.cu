@@ -25,8 +25,11 @@ template <int MODE>
 __global__ void __launch_bounds__(kRowThreads)
 move_rows_vec4_kernel(const float* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ idx,
                       int n_host, const int32_t* __restrict__ n_dev, int n_total, int c4,
-                      float* __restrict__ dst, int64_t ld_dst, unsigned long long* trace) {
+                      float* __restrict__ dst, int64_t ld_dst, unsigned long long* trace,
+                      int32_t* done_counter) {
     TraceScope ts(trace, MODE == 0 ? TR_GATHER : (MODE == 1 ? TR_UPDATE : TR_PAD));
+    // optional: count this launch as "everything stream-ordered before it has finished"
+    if (done_counter && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(done_counter, 1);
     const int n = dev_count(n_dev, n_host);
     const int rows = MODE == 2 ? n_total : n;
     const int64_t total = (int64_t)rows * c4;
@@ -61,7 +64,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kRowThreads)
 move_rows_scalar_kernel(const float* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ idx,
                         int n_host, const int32_t* __restrict__ n_dev, int n_total, int C,
-                        float* __restrict__ dst, int64_t ld_dst) {
+                        float* __restrict__ dst, int64_t ld_dst, int32_t* done_counter) {
+    if (done_counter && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(done_counter, 1);
     const int n = dev_count(n_dev, n_host);
     const int rows = MODE == 2 ? n_total : n;
     const int64_t total = (int64_t)rows * C;
@@ -86,7 +90,7 @@ static bool vec4_ok(const void* a, int64_t lda, const void* b, int64_t ldb, int 
 template <int MODE>
 static int launch_move_rows(const float* src, int64_t ld_src, const int32_t* idx, int n,
                             const int32_t* n_dev, int n_total, int C, float* dst, int64_t ld_dst,
-                            cudaStream_t st) {
+                            cudaStream_t st, int32_t* done_counter = nullptr) {
     const int rows = MODE == 2 ? n_total : n;
     if (rows <= 0 || C <= 0) return SGCN_OK;
     const int max_blocks = kNumSMs * 8;
@@ -97,15 +101,50 @@ static int launch_move_rows(const float* src, int64_t ld_src, const int32_t* idx
                                                 ((int64_t)kRowThreads * kRowUnroll), max_blocks);
         if (blocks < 1) blocks = 1;
         move_rows_vec4_kernel<MODE><<<blocks, kRowThreads, 0, st>>>(src, ld_src, idx, n, n_dev,
-                                                                   n_total, c4, dst, ld_dst, g_trace);
+                                                                   n_total, c4, dst, ld_dst, g_trace,
+                                                                   done_counter);
     } else {
         const int64_t total = (int64_t)rows * C;
         int blocks = (int)std::min<int64_t>((total + kRowThreads - 1) / kRowThreads, max_blocks);
         move_rows_scalar_kernel<MODE><<<blocks, kRowThreads, 0, st>>>(src, ld_src, idx, n, n_dev,
-                                                                     n_total, C, dst, ld_dst);
+                                                                     n_total, C, dst, ld_dst, done_counter);
     }
     SGCN_LAUNCHED();
     return SGCN_OK;
+}
+
+// two independent copy+zero-pad jobs in one launch (blockIdx.y picks the job): the step driver
+// initialises dX and pre-zeroes the next step's output with a single graph node
+struct PadJob { const float* src; int64_t ld_src; int n; const int32_t* n_dev; int n_total; int C;
+                float* dst; int64_t ld_dst; };
+struct PadPair { PadJob j[2]; };
+
+__global__ void __launch_bounds__(kRowThreads)
+pad_pair_kernel(const PadPair p, unsigned long long* trace) {
+    TraceScope ts(trace, TR_PAD);
+    const PadJob& a = p.j[blockIdx.y];
+    if (!a.dst || a.n_total <= 0 || a.C <= 0) return;
+    const int n = dev_count(a.n_dev, a.n);
+    const bool vec = (a.C & 3) == 0 && (a.ld_dst & 3) == 0 && (((uintptr_t)a.dst) & 15) == 0 &&
+                     (a.n == 0 || ((a.ld_src & 3) == 0 && (((uintptr_t)a.src) & 15) == 0));
+    const int64_t stride = (int64_t)gridDim.x * kRowThreads;
+    if (vec) {
+        const int c4 = a.C >> 2;
+        const int64_t total = (int64_t)a.n_total * c4;
+        for (int64_t t = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; t < total; t += stride) {
+            const int r = (int)(t / c4);
+            const int c = (int)(t - (int64_t)r * c4) * 4;
+            const float4 v = r < n ? ldg_stream4(a.src + (int64_t)r * a.ld_src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            stg_stream4(a.dst + (int64_t)r * a.ld_dst + c, v);
+        }
+    } else {
+        const int64_t total = (int64_t)a.n_total * a.C;
+        for (int64_t t = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; t < total; t += stride) {
+            const int r = (int)(t / a.C);
+            const int c = (int)(t - (int64_t)r * a.C);
+            a.dst[(int64_t)r * a.ld_dst + c] = r < n ? a.src[(int64_t)r * a.ld_src + c] : 0.f;
+        }
+    }
 }
 
 // ---- CSR row slicer -------------------------------------------------------------------------
@@ -155,11 +194,12 @@ int sgcn_gather_rows(const float* src, int64_t ld_src, const int32_t* idx, int32
 
 int sgcn_history_update(float* hist, int64_t ld_h, const int32_t* idx, int32_t n,
                         const int32_t* n_dev, const float* rows, int64_t ld_rows, int32_t D,
-                        void* stream) {
+                        int32_t* done_counter, void* stream) {
     SGCN_REQUIRE(n >= 0 && D >= 0, "history_update: negative size");
     SGCN_REQUIRE(n == 0 || D == 0 || (hist && idx && rows), "history_update: null pointer");
     SGCN_REQUIRE(ld_h >= D && ld_rows >= D, "history_update: row stride smaller than width");
-    return launch_move_rows<1>(rows, ld_rows, idx, n, n_dev, 0, D, hist, ld_h, (cudaStream_t)stream);
+    return launch_move_rows<1>(rows, ld_rows, idx, n, n_dev, 0, D, hist, ld_h, (cudaStream_t)stream,
+                               done_counter);
 }
 
 int sgcn_copy_rows_pad(const float* src, int64_t ld_src, int32_t n, const int32_t* n_dev,
@@ -171,6 +211,25 @@ int sgcn_copy_rows_pad(const float* src, int64_t ld_src, int32_t n, const int32_
     if (n == 0) { src = dst; ld_src = ld_dst; }   // never dereferenced: every row is padding
     return launch_move_rows<2>(src, ld_src, nullptr, n, n_dev, n_total, D, dst, ld_dst,
                                (cudaStream_t)stream);
+}
+
+int sgcn_copy_rows_pad_pair(const float* src0, int64_t ld_src0, int32_t n0, const int32_t* n0_dev,
+                            int32_t n_total0, int32_t D0, float* dst0, int64_t ld_dst0,
+                            const float* src1, int64_t ld_src1, int32_t n1, const int32_t* n1_dev,
+                            int32_t n_total1, int32_t D1, float* dst1, int64_t ld_dst1, void* stream) {
+    SGCN_REQUIRE(n0 >= 0 && n1 >= 0 && n_total0 >= 0 && n_total1 >= 0 && D0 >= 0 && D1 >= 0,
+                 "copy_rows_pad_pair: negative size");
+    SGCN_REQUIRE((n0 == 0 || src0) && (n1 == 0 || src1), "copy_rows_pad_pair: null src");
+    SGCN_REQUIRE((!dst0 || ld_dst0 >= D0) && (!dst1 || ld_dst1 >= D1) && (n0 == 0 || ld_src0 >= D0) &&
+                     (n1 == 0 || ld_src1 >= D1), "copy_rows_pad_pair: row stride smaller than width");
+    PadPair p{};
+    p.j[0] = PadJob{src0, ld_src0, n0, n0_dev, n_total0, D0, dst0, ld_dst0};
+    p.j[1] = PadJob{src1, ld_src1, n1, n1_dev, n_total1, D1, dst1, ld_dst1};
+    const int64_t work = std::max<int64_t>(std::max((int64_t)n_total0 * D0, (int64_t)n_total1 * D1) / 4, 1);
+    dim3 grid((unsigned)std::min<int64_t>((work + kRowThreads - 1) / kRowThreads, kNumSMs * 2), 2);
+    pad_pair_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(p, g_trace);
+    SGCN_LAUNCHED();
+    return SGCN_OK;
 }
 
 int sgcn_csr_slice_indptr(const int32_t* a_p, const int32_t* r, int32_t n, int32_t* o_p,

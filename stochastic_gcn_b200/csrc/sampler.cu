@@ -1433,6 +1433,7 @@ int sgcn_sampler_vec(sgcn_sampler* s, int32_t level, int32_t which, void** ptr, 
         case SGCN_VEC_ADJ_P: *ptr = s->adj_p; *len = (int64_t)s->N + 1; return SGCN_OK;
         case SGCN_VEC_ADJ_W: *ptr = s->adj_w; *len = s->E; return SGCN_OK;
         case SGCN_VEC_IMPORTANCE: *ptr = s->importance; *len = s->N; return SGCN_OK;
+        case SGCN_VEC_PIPE: *ptr = s->pipe_counters; *len = 2; return SGCN_OK;
         default: break;
     }
     Level* lv = level_at(s, level);

@@ -44,14 +44,14 @@ def gather_rows(src, idx, out=None, n_dev=None):
     return out
 
 
-def history_update(hist, idx, rows, n_dev=None):
+def history_update(hist, idx, rows, n_dev=None, done_counter=None):
     """hist[idx[i], :] = rows[i, :]  -- tf.scatter_update (gcn/models.py:160-166)."""
     _f32(hist, "hist"); _i32(idx, "idx"); _f32(rows, "rows")
     n = idx.numel()
     if rows.shape[0] < n or rows.shape[1] != hist.shape[1]:
         raise ValueError("rows must be [>=len(idx), hist.shape[1]]")
     check(_lib.load().sgcn_history_update(ptr(hist), _ld(hist), ptr(idx), n, ptr(n_dev), ptr(rows), _ld(rows),
-                                          hist.shape[1], stream_ptr()))
+                                          hist.shape[1], ptr(done_counter), stream_ptr()))
     return hist
 
 
@@ -152,4 +152,44 @@ def cvd_sampled_fwd(rowptr, cols, vals, tgt, scale, n_out, h, mu, hist, yh, ymu,
         ptr(mu), _ld(mu), ptr(hist), _ld(hist), d, ptr(yh), _ld(yh), ptr(ymu), _ld(ymu),
         ptr(self_h), _ld(self_h) if self_h is not None else 0,
         ptr(self_mu), _ld(self_mu) if self_mu is not None else 0, 1 if accumulate else 0, stream_ptr()))
+    return yh, ymu
+
+
+def copy_rows_pad_pair(src0, n0, out0, src1, n1, out1, n0_dev=None, n1_dev=None):
+    """Two copy_rows_pad jobs in one launch (out1 may be None)."""
+    _f32(out0, "out0")
+    a = (ptr(src0) if n0 > 0 else None, _ld(src0) if n0 > 0 else 0, n0, ptr(n0_dev), out0.shape[0], out0.shape[1],
+         ptr(out0), _ld(out0))
+    if out1 is None:
+        b = (None, 0, 0, None, 0, 0, None, 0)
+    else:
+        _f32(out1, "out1")
+        b = (ptr(src1) if n1 > 0 else None, _ld(src1) if n1 > 0 else 0, n1, ptr(n1_dev), out1.shape[0],
+             out1.shape[1], ptr(out1), _ld(out1))
+    check(_lib.load().sgcn_copy_rows_pad_pair(*a, *b, stream_ptr()))
+
+
+def cv_sampled_fwd_bwd(rowptr, cols, vals, tgt, n_out, x, hist, y, dy, dx, self_out=None, n_out_dev=None,
+                       accumulate=False):
+    """cv_sampled_fwd fused with the backward scatter dx[cols[e]] += vals[e] * dy[r] (dx pre-initialised)."""
+    _f32(x, "x"); _f32(hist, "hist"); _f32(y, "y"); _f32(dy, "dy"); _f32(dx, "dx")
+    d = x.shape[1]
+    check(_lib.load().sgcn_cv_sampled_fwd_bwd(
+        ptr(rowptr), ptr(cols), ptr(vals), ptr(tgt), n_out, ptr(n_out_dev), ptr(x), _ld(x), ptr(hist), _ld(hist),
+        d, ptr(y), _ld(y), ptr(self_out), _ld(self_out) if self_out is not None else 0, 1 if accumulate else 0,
+        ptr(dy), _ld(dy), ptr(dx), _ld(dx), stream_ptr()))
+    return y
+
+
+def cvd_sampled_fwd_bwd(rowptr, cols, vals, tgt, scale, n_out, h, mu, hist, yh, ymu, dy, dx, self_h=None,
+                        self_mu=None, n_out_dev=None, accumulate=False):
+    """cvd_sampled_fwd fused with dx[cols[e]] += vals[e] * scale[r] * dy[r] (dx pre-initialised)."""
+    _f32(h, "h"); _f32(mu, "mu"); _f32(hist, "hist"); _f32(yh, "yh"); _f32(ymu, "ymu"); _f32(dy, "dy"); _f32(dx, "dx")
+    d = h.shape[1]
+    check(_lib.load().sgcn_cvd_sampled_fwd_bwd(
+        ptr(rowptr), ptr(cols), ptr(vals), ptr(tgt), ptr(scale), n_out, ptr(n_out_dev), ptr(h), _ld(h),
+        ptr(mu), _ld(mu), ptr(hist), _ld(hist), d, ptr(yh), _ld(yh), ptr(ymu), _ld(ymu),
+        ptr(self_h), _ld(self_h) if self_h is not None else 0,
+        ptr(self_mu), _ld(self_mu) if self_mu is not None else 0, 1 if accumulate else 0,
+        ptr(dy), _ld(dy), ptr(dx), _ld(dx), stream_ptr()))
     return yh, ymu

@@ -16,6 +16,7 @@ _NAMES = {
     "field": _lib.VEC_FIELD, "ffield": _lib.VEC_FFIELD, "edg_s": _lib.VEC_EDG_S, "edg_t": _lib.VEC_EDG_T,
     "fedg_s": _lib.VEC_FEDG_S, "fedg_t": _lib.VEC_FEDG_T, "adj_i": _lib.VEC_ADJ_I, "adj_p": _lib.VEC_ADJ_P,
     "rowptr_s": _lib.VEC_ROWPTR_S, "rowptr_f": _lib.VEC_ROWPTR_F, "tgt": _lib.VEC_TGT, "meta": _lib.VEC_META,
+    "pipe": _lib.VEC_PIPE,
     "scales": _lib.VEC_SCALES, "edg_w": _lib.VEC_EDG_W, "medg_w": _lib.VEC_MEDG_W, "fedg_w": _lib.VEC_FEDG_W,
     "adj_w": _lib.VEC_ADJ_W, "importance": _lib.VEC_IMPORTANCE,
 }

@@ -164,7 +164,7 @@ class ShardedHotPathStep(HotPathStep):
         return min(self.B * (1 + self.degree), max(self.n_nodes, self.B))
 
     # HotPathStep._pass calls this instead of the local scatter-store
-    def _write_back(self, v, new_hist):
+    def _write_back(self, v, new_hist, done_counter=None):
         lib, D = _lib.load(), self.hidden
         ld = new_hist.stride(0)
         if self.transport == "peer":
@@ -179,6 +179,7 @@ class ShardedHotPathStep(HotPathStep):
             check(lib.sgcn_wb_pack(ptr(v["field"]), ptr(v["n_in_dev"]), self.wb_bound, ptr(new_hist), ld, D,
                                    self._send_ptr, 1, 0, stream_ptr()))
             self._pending_exchange = True
+        return False
 
     def _finish_exchange(self):
         """NCCL transport: the collective and the merge run eagerly after the (captured) pass."""

@@ -77,6 +77,7 @@ class HotPathStep:
         self._pinned_out = None
         self._pipe = None           # graphs of the cross-step pipelined driver
         self._pipeline_on = False
+        self._pipe_done = None
         self._last_slot = 0
         self._s_b = torch.cuda.Stream(device=self.dev)      # side branch of the pass
         self._s_samp = torch.cuda.Stream(device=self.dev)   # sampler branch of the pipelined graphs
@@ -152,9 +153,17 @@ class HotPathStep:
         if fork is not None:
             fork(ev_start)                       # e.g. the next batch's sampler branch
 
-        # side branch: feature-row gather, sampled part of the aggregate, backward, next step's zeroing
+        # side branch: dX init (+ next step's output zeroing), feature-row gather, then the sampled part
+        # of the aggregate fused with its backward -- three graph nodes
         with torch.cuda.stream(side):
             side.wait_event(ev_start)
+            d_nb = self.d_out[:, H:] if self.concat else self.d_out
+            d_self = self.d_out[:, :H] if self.concat else None
+            nxt = self._out_views(1 - slot) if (zero_next and cv) else None
+            ops.copy_rows_pad_pair(d_self, B if self.concat else 0, self.dx, None, 0,
+                                   nxt[0] if nxt else None, n0_dev=v["n_out_dev"] if self.concat else None)
+            if nxt and nxt[2] is not None:
+                ops.copy_rows_pad(None, 0, nxt[2])
             ops.gather_rows(self.features, v["field"], out=self.x0, n_dev=v["n_in_dev"])
             x = self.x0[:, :H]
             new_hist = None
@@ -162,46 +171,39 @@ class HotPathStep:
                 ops.spmm_csr(v["rowptr_s"], v["edg_t"], v["edg_w"], x, B, out=nb, n_out_dev=v["n_out_dev"])
                 if self.concat:
                     ops.copy_rows_pad(x, B, slf, n_dev=v["n_out_dev"])
+                ops.spmm_csr_bwd(v["rowptr_s"], v["edg_t"], v["edg_w"], d_nb, self.dx, B, n_out_dev=v["n_out_dev"])
             elif self.mode == "cv":
-                ops.cv_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], B, x, self.history, nb,
-                                   self_out=slf, n_out_dev=v["n_out_dev"], accumulate=True)
+                ops.cv_sampled_fwd_bwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], B, x, self.history, nb,
+                                       d_nb, self.dx, self_out=slf, n_out_dev=v["n_out_dev"], accumulate=True)
                 new_hist = x
             else:
                 mu = self.x0[:, H:2 * H]
-                ops.cvd_sampled_fwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], v["scales"], B, x, mu,
-                                    self.history, nb, nb_mu, self_h=slf, self_mu=slf_mu,
-                                    n_out_dev=v["n_out_dev"], accumulate=True)
+                ops.cvd_sampled_fwd_bwd(v["rowptr_s"], v["edg_t"], v["edg_w"], v["tgt"], v["scales"], B, x, mu,
+                                        self.history, nb, nb_mu, d_nb, self.dx, self_h=slf, self_mu=slf_mu,
+                                        n_out_dev=v["n_out_dev"], accumulate=True)
                 new_hist = mu
             ev_fwd = torch.cuda.Event()          # last read of history on this branch
             ev_fwd.record(side)
-            # dX = adj^T (dZ_nb * scale) (+ dZ_self on the first B rows)
-            d_nb = self.d_out[:, H:] if self.concat else self.d_out
-            if self.concat:
-                ops.copy_rows_pad(self.d_out[:, :H], B, self.dx, n_dev=v["n_out_dev"])
-            else:
-                ops.copy_rows_pad(None, 0, self.dx)
-            ops.spmm_csr_bwd(v["rowptr_s"], v["edg_t"], v["edg_w"], d_nb, self.dx, B,
-                             rscale=v["scales"] if self.mode == "cvd" else None, n_out_dev=v["n_out_dev"])
-            if zero_next:
-                self._zero_out(1 - slot)
 
         main.wait_event(ev_fwd)                  # every forward read of history precedes the write-back
+        marked = False
         if new_hist is not None:                 # (models.py:186-194)
-            self._write_back(v, new_hist)
-
-        with torch.cuda.stream(side):
-            side.wait_event(ev_full)
-            if pipelined:                        # adjacency rows of this batch are no longer read
-                self.sampler.mark_consumed(side)
-            if after is not None:
+            marked = self._write_back(v, new_hist, self._pipe_done if pipelined else None)
+        if pipelined and not marked:             # adjacency rows of this batch are no longer read
+            self.sampler.mark_consumed(main)
+        if after is not None:
+            with torch.cuda.stream(side):
+                side.wait_event(ev_full)
                 after(side)
-            ev_side = torch.cuda.Event()
-            ev_side.record(side)
-        main.wait_event(ev_side)
+                ev_side = torch.cuda.Event()
+                ev_side.record(side)
+            main.wait_event(ev_side)
 
-    def _write_back(self, v, new_hist):
-        """tf.scatter_update(history, fields[0], new_history); the sharded subclass exchanges instead"""
-        ops.history_update(self.history, v["field"], new_hist, n_dev=v["n_in_dev"])
+    def _write_back(self, v, new_hist, done_counter=None):
+        """tf.scatter_update(history, fields[0], new_history); the sharded subclass exchanges instead.
+        Returns True when it also bumped the pipelining guard's consumer counter (done_counter)."""
+        ops.history_update(self.history, v["field"], new_hist, n_dev=v["n_in_dev"], done_counter=done_counter)
+        return done_counter is not None
 
     def _pass(self):
         """One whole pass on the current stream: zero -> sampler -> rest (buffer set 0)."""
@@ -304,6 +306,7 @@ class HotPathStep:
         if not self._pipeline_on:
             self.sampler.pipeline(True)
             self._pipeline_on = True
+            self._pipe_done = self.sampler.view("pipe")[1:2]    # the guard's consumer counter
         B, width = self.B, self.outs[0].shape[1]
         # tab[c][k] = ids of the batch that step k of a parity-c chunk samples AHEAD (batch k+1 of the
         # chunk; row S-1 is the first batch of the next chunk)
@@ -388,9 +391,11 @@ class HotPathStep:
     def run_pipelined(self, batches, on_chunk=None):
         """Run len(batches) consecutive passes with one-batch sampler lookahead on the current stream.
         Per chunk of S steps: the ids copies and ONE graph launch.  ``batches``: int32 id tensors
-        (CUDA; host tensors when captured with host_io=True).  ``on_chunk(first_step, count, step)``
-        is called after a chunk has been enqueued (host_io: ``step._pipe["pin_out"][c][:count]``
-        holds the rows of those steps once the stream is synchronised; c = chunk parity)."""
+        (CUDA; host tensors when captured with host_io=True).  ``on_chunk(first_step, count, step,
+        done_event)`` is called after a chunk has been enqueued (host_io: once ``done_event`` has
+        completed, ``step._pipe["pin_out"][c][:count]`` holds the rows of those steps, c = chunk
+        parity; that buffer is rewritten by chunk c+2, so wait for the event before launching it --
+        waiting one chunk behind keeps the GPU busy while the host consumes results)."""
         pipe = self._pipe
         S, n = pipe["S"], len(batches)
         if n == 0:
@@ -406,12 +411,17 @@ class HotPathStep:
             closed = rem == 0 and c == full - 1
             ahead = batches[base + 1: base + S + (0 if closed else 1)]
             dst = stage[par]
+            if host_io and pipe.get("done", [None, None])[par] is not None:
+                pipe["done"][par].synchronize()                 # chunk c-2 has consumed this staging buffer
             for k, ids in enumerate(ahead):
                 dst[k].copy_(ids, non_blocking=not host_io)
             pipe["closed" if closed else "open"][par].replay()
             self._last_slot = (S - 1) & 1
+            ev = torch.cuda.Event()
+            ev.record()
+            pipe.setdefault("done", [None, None])[par] = ev
             if on_chunk is not None:
-                on_chunk(base, S, self)
+                on_chunk(base, S, self, ev)
         if rem:                                                 # tail shorter than a chunk: eager passes
             base = full * S
             for j in range(rem):
@@ -420,7 +430,9 @@ class HotPathStep:
                     self.ids2[slot].copy_(batches[base + j], non_blocking=True)
                 self._eager_step(slot, sample=j > 0)            # batch `base` was already sampled ahead
                 if on_chunk is not None:
-                    on_chunk(base + j, 1, self)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    on_chunk(base + j, 1, self, ev)
         return self.out
 
     def time_dominant_kernel(self, batches):

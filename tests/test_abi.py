@@ -42,7 +42,7 @@ def test_argument_validation_needs_no_gpu():
     assert lib.sgcn_gather_rows(None, 4, None, 0, None, 4, None, 4, None) == 0
     assert lib.sgcn_spmm_coo(None, None, 0, None, 4, 4, None, 4, 0, None) == 0
     with pytest.raises(_lib.SgcnError):
-        _lib.check(lib.sgcn_history_update(None, 1, None, 2, None, None, 1, 4, None))
+        _lib.check(lib.sgcn_history_update(None, 1, None, 2, None, None, 1, 4, None, None))
 
 
 def test_product_never_imports_the_oracle():

@@ -126,8 +126,8 @@ def test_pipelined_driver_matches_oracle_incl_overlapping_batches(mode, deg):
         oracle_step(o, mode, deg, ids.cpu().numpy(), fh, hist, D, d_out)
     got = []
 
-    def grab(first, count, st):
-        torch.cuda.current_stream().synchronize()
+    def grab(first, count, st, done):
+        done.synchronize()
         if count > 1:      # a chunk graph: per-step rows were copied to pinned memory by the graph
             c = (first // st._pipe["S"]) & 1
             for k in range(count):
