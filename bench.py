@@ -304,7 +304,8 @@ def run_ours(args, w):
     sizes_last = step.sizes()
 
     # ---- (2) timed region of record: exactly K steps with one-batch sampler lookahead ----
-    pipelined = not args.no_pipeline
+    # the NCCL transport runs its collective eagerly between graph replays: no multi-step graphs there
+    pipelined = not args.no_pipeline and not (world > 1 and args.transport == "nccl")
     ms = ms_serial
     if pipelined:
         step.capture_pipelined(batches[0], batches[1], steps_per_graph=args.steps_per_graph)

@@ -21,12 +21,13 @@ from stochastic_gcn_b200.sharding import ShardedHotPathStep, row_range   # noqa:
 def main():
     transport, mode = sys.argv[1], sys.argv[2]
     use_graph = len(sys.argv) > 3 and sys.argv[3] == "graph"
+    pipelined = len(sys.argv) > 3 and sys.argv[3] == "pipelined"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     deg = 2 if mode == "cv" else 1
-    D, B, steps, seed = 32, 24, 5, 3
+    D, B, steps, seed = 32, 24, (8 if pipelined else 5), 3
     g = graphs.powerlaw_graph(1500, 60_000, seed=4, device=dev, max_degree=300)
     gen = torch.Generator(device=dev).manual_seed(0)
     feats = torch.randn((g.n, 80), generator=gen, device=dev)
@@ -73,6 +74,18 @@ def main():
             hist[ids] = rows
         want_out.append(outs[rank])
 
+    if pipelined:
+        # multi-step graphs (2 steps each) with sampler lookahead and the peer exchange inside the graphs;
+        # capture_pipelined runs the first two batches as eager warm-up passes
+        dev_batches = [torch.from_numpy(b).to(dev) for b in batches[rank]]
+        step.capture_pipelined(dev_batches[0], dev_batches[1], steps_per_graph=2)
+        step.run_pipelined(dev_batches[2:])
+        torch.cuda.synchronize()
+        step.check_exchange()
+        out = step.out.cpu().numpy()
+        err = np.abs(out - want_out[-1]).max() / max(np.abs(want_out[-1]).max(), 1e-30)
+        assert err < 1e-4, "rank %d: last pipelined out differs by %g" % (rank, err)
+        steps = 0
     for s in range(steps):
         ids = torch.from_numpy(batches[rank][s]).to(dev)
         if use_graph and s == 0:

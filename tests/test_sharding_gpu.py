@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("transport,mode,graph", [("nccl", "cv", ""), ("peer", "cv", ""), ("peer", "cvd", "graph"),
-                                                  ("nccl", "cvd", "graph")])
+                                                  ("nccl", "cvd", "graph"), ("peer", "cv", "pipelined")])
 def test_two_rank_pass_matches_oracle(transport, mode, graph):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
