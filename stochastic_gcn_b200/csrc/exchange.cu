@@ -105,40 +105,60 @@ __global__ void wb_wait_kernel(const int32_t* flags, int world, const int32_t* e
 
 // claim: owner[node] = max over (rank, position) codes of the ranks that refreshed `node`
 __global__ void __launch_bounds__(256)
-wb_claim_kernel(const char* __restrict__ g_even, const char* __restrict__ g_odd,
+wb_claim_kernel(const char* g_even, const char* g_odd,
                 const int32_t* __restrict__ epoch, int64_t slot_bytes, int world, int n_bound,
-                int32_t* __restrict__ owner) {
+                int32_t* __restrict__ owner, const int32_t* flags, int32_t* timeout_flag,
+                long long max_spins) {
+    if (flags) {
+        // peer transport: every block first waits (bounded) until all ranks have published this epoch
+        if (threadIdx.x < world) {
+            const int step = *epoch;
+            volatile const int32_t* f = (volatile const int32_t*)flags;
+            long long spins = 0;
+            while (f[threadIdx.x] < step) {
+                if (++spins > max_spins) {
+                    atomicExch(timeout_flag, 1 + threadIdx.x);
+                    break;
+                }
+                __nanosleep(100);
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     const int r = blockIdx.y;
     const char* gathered = (epoch && (*epoch & 1)) ? g_odd : g_even;
     const char* slot = gathered + (int64_t)r * slot_bytes;
-    const int n = min(((const int32_t*)slot)[0], n_bound);
+    // payloads were written by other GPUs while this kernel may already have been resident: read
+    // them through L2 (ld.global.cg / volatile), never through a possibly stale L1 / read-only path
+    const int n = min(__ldcg((const int32_t*)slot), n_bound);
     const int32_t* ids = (const int32_t*)(slot + wb_ids_offset());
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
-        atomicMax(owner + ids[j], r * n_bound + j);
+        atomicMax(owner + __ldcg(ids + j), r * n_bound + j);
 }
 
 // copy: the winning (rank, position) of each node writes its whole row, then releases the claim
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-wb_copy_kernel(const char* __restrict__ g_even, const char* __restrict__ g_odd,
+wb_copy_kernel(const char* g_even, const char* g_odd,
                const int32_t* __restrict__ epoch, int64_t slot_bytes, int world, int n_bound,
                int32_t* __restrict__ owner, float* __restrict__ hist, int64_t ld_h, int D) {
     const int r = blockIdx.y;
     const char* gathered = (epoch && (*epoch & 1)) ? g_odd : g_even;
     const char* slot = gathered + (int64_t)r * slot_bytes;
-    const int n = min(((const int32_t*)slot)[0], n_bound);
+    const int n = min(__ldcg((const int32_t*)slot), n_bound);
     const int32_t* ids = (const int32_t*)(slot + wb_ids_offset());
     const float* rows = (const float*)(slot + wb_rows_offset(n_bound));
     constexpr int W = VEC ? 4 : 1;
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
-        const int node = ids[j];
+        const int node = __ldcg(ids + j);
         const bool mine = owner[node] == r * n_bound + j;         // uniform across the warp
         if (mine) {
             for (int c = lane * W; c < D; c += 32 * W) {
-                if (VEC) *(float4*)(hist + (int64_t)node * ld_h + c) = *(const float4*)(rows + (int64_t)j * D + c);
-                else hist[(int64_t)node * ld_h + c] = rows[(int64_t)j * D + c];
+                if (VEC) *(float4*)(hist + (int64_t)node * ld_h + c) = __ldcg((const float4*)(rows + (int64_t)j * D + c));
+                else hist[(int64_t)node * ld_h + c] = __ldcg(rows + (int64_t)j * D + c);
             }
         }
         __syncwarp();
@@ -210,10 +230,12 @@ int sgcn_wb_push(const int32_t* field, const int32_t* n_dev, int32_t n_bound, co
 
 static int launch_apply(float* hist, int64_t ld_h, int32_t D, const void* g_even, const void* g_odd,
                         const int32_t* epoch, int64_t slot_bytes, int32_t world, int32_t n_bound,
-                        int32_t* owner, cudaStream_t st) {
+                        int32_t* owner, cudaStream_t st, const int32_t* flags = nullptr,
+                        int32_t* timeout_flag = nullptr) {
     dim3 g1(std::min(div_up(std::max(n_bound, 1), 256), 64), world);
+    // ~2 s at 100 ns per spin: a peer that never arrives raises the flag instead of hanging the GPU
     wb_claim_kernel<<<g1, 256, 0, st>>>((const char*)g_even, (const char*)g_odd, epoch, slot_bytes, world,
-                                        n_bound, owner);
+                                        n_bound, owner, flags, timeout_flag, 20000000LL);
     SGCN_LAUNCHED();
     dim3 g2(std::min(div_up(std::max(n_bound, 1), 8), kNumSMs), world);
     const bool vec = D % 4 == 0 && ld_h % 4 == 0 && (((uintptr_t)hist) & 15) == 0 && slot_bytes % 16 == 0 &&
@@ -248,11 +270,14 @@ int sgcn_wb_wait_apply(float* hist, int64_t ld_h, int32_t D, const void* recv_ev
     SGCN_REQUIRE(slot_bytes >= wb_payload_bytes(n_bound, D), "wb_wait_apply: slot smaller than a payload");
     SGCN_REQUIRE((int64_t)world * std::max(n_bound, 1) < 0x7fffffff, "wb_wait_apply: world * n_bound overflows");
     cudaStream_t st = (cudaStream_t)stream;
-    // ~2 s at 100 ns per spin: a peer that never arrives raises the flag instead of hanging the GPU
-    wb_wait_kernel<<<1, 32, 0, st>>>(flags, world, epoch, timeout_flag, 20000000LL);
-    SGCN_LAUNCHED();
-    if (n_bound == 0) return SGCN_OK;
-    return launch_apply(hist, ld_h, D, recv_even, recv_odd, epoch, slot_bytes, world, n_bound, owner, st);
+    if (n_bound == 0) {
+        wb_wait_kernel<<<1, 32, 0, st>>>(flags, world, epoch, timeout_flag, 20000000LL);
+        SGCN_LAUNCHED();
+        return SGCN_OK;
+    }
+    // the wait is fused into the claim pass (every block polls the flags before touching a payload)
+    return launch_apply(hist, ld_h, D, recv_even, recv_odd, epoch, slot_bytes, world, n_bound, owner, st,
+                        flags, timeout_flag);
 }
 
 // ---- peer memory plumbing (cudaIpc): plain cudaMalloc'd buffers that other ranks can map -----

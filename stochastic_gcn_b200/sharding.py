@@ -163,8 +163,10 @@ class ShardedHotPathStep(HotPathStep):
     def sampler_n_in_bound(self):
         return min(self.B * (1 + self.degree), max(self.n_nodes, self.B))
 
-    # HotPathStep._pass calls this instead of the local scatter-store
-    def _write_back(self, v, new_hist, done_counter=None):
+    # hooks called by HotPathStep._rest ---------------------------------------------------------
+    def _publish_write_back(self, v, new_hist):
+        """Side branch, right after the gather: the rows this rank will write back already exist, so
+        they cross NVLink (or are packed for NCCL) while the full-neighbour mean is still running."""
         lib, D = _lib.load(), self.hidden
         ld = new_hist.stride(0)
         if self.transport == "peer":
@@ -172,13 +174,18 @@ class ShardedHotPathStep(HotPathStep):
             check(lib.sgcn_wb_push(ptr(v["field"]), ptr(v["n_in_dev"]), self.wb_bound, ptr(new_hist), ld, D,
                                    x.dst_even, x.dst_odd, self.world, x.peer_flags, self.rank, x.epoch,
                                    stream_ptr()))
-            check(lib.sgcn_wb_wait_apply(ptr(self.history), self.history.stride(0), D, x.recv_even, x.recv_odd,
-                                         self.slot_bytes, self.world, self.wb_bound, ptr(self.owner), x.flags,
-                                         x.epoch, x.timeout, stream_ptr()))
         else:
             check(lib.sgcn_wb_pack(ptr(v["field"]), ptr(v["n_in_dev"]), self.wb_bound, ptr(new_hist), ld, D,
                                    self._send_ptr, 1, 0, stream_ptr()))
-            self._pending_exchange = True
+
+    def _write_back(self, v, new_hist, done_counter=None):
+        """Main chain, after every forward read of history: merge all ranks' payloads."""
+        if self.transport == "peer":
+            x = self._exchange
+            check(_lib.load().sgcn_wb_wait_apply(ptr(self.history), self.history.stride(0), self.hidden,
+                                                 x.recv_even, x.recv_odd, self.slot_bytes, self.world,
+                                                 self.wb_bound, ptr(self.owner), x.flags, x.epoch, x.timeout,
+                                                 stream_ptr()))
         return False
 
     def _finish_exchange(self):

@@ -167,6 +167,8 @@ class HotPathStep:
             ops.gather_rows(self.features, v["field"], out=self.x0, n_dev=v["n_in_dev"])
             x = self.x0[:, :H]
             new_hist = None
+            if cv:      # the rows that will be written back exist now: a sharded step publishes them early
+                self._publish_write_back(v, x if self.mode == "cv" else self.x0[:, H:2 * H])
             if self.mode == "ns":
                 ops.spmm_csr(v["rowptr_s"], v["edg_t"], v["edg_w"], x, B, out=nb, n_out_dev=v["n_out_dev"])
                 if self.concat:
@@ -198,6 +200,9 @@ class HotPathStep:
                 ev_side = torch.cuda.Event()
                 ev_side.record(side)
             main.wait_event(ev_side)
+
+    def _publish_write_back(self, v, new_hist):
+        """Hook, on the side branch right after the gather: nothing to do on one GPU."""
 
     def _write_back(self, v, new_hist, done_counter=None):
         """tf.scatter_update(history, fields[0], new_history); the sharded subclass exchanges instead.
