@@ -307,9 +307,23 @@ def run_ours(args, w):
     # the NCCL transport runs its collective eagerly between graph replays: no multi-step graphs there
     pipelined = not args.no_pipeline and not (world > 1 and args.transport == "nccl")
     ms = ms_serial
-    if pipelined:
+    native_drv = pipelined and args.driver == "native"
+    if native_drv:
+        before = _lib.launch_count()
+        step.run_native(torch.stack(batches[:args.warmup]))
+        launches_per_step = (_lib.launch_count() - before) / args.warmup
+        timed_table = torch.stack(timed)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ev0.record()
+        step.run_native(timed_table)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        sizes_last = step.sizes()
+    elif pipelined:
         step.capture_pipelined(batches[0], batches[1], steps_per_graph=args.steps_per_graph)
-        launches_per_step += 1                       # + mark_consumed
+        launches_per_step -= 2                       # fused dX-init/zero and forward+backward, mark in write-back
         step.run_pipelined(batches[2:args.warmup + 2])
         torch.cuda.synchronize(dev)
         barrier()
@@ -323,7 +337,18 @@ def run_ours(args, w):
     # ---- e2e: same K steps through the host-buffer API (pinned ids in, aggregated rows out) ----
     pinned = [b.cpu().pin_memory() for b in timed]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if pipelined:
+    if native_drv:
+        # pinned [K, B] ids in, pinned [K, B, width] rows out; H2D / D2H issued step by step by the driver
+        ids_host = torch.stack([p for p in pinned]).pin_memory()
+        out_host = torch.empty((len(pinned), w["batch"], step.out.shape[1]), dtype=torch.float32).pin_memory()
+        step.run_native(ids_host[:4], out_host=out_host[:4])
+        barrier()
+        e0.record()
+        step.run_native(ids_host, out_host=out_host)
+        torch.cuda.current_stream(dev).synchronize()          # the caller reads the rows
+        e1.record()
+        barrier()
+    elif pipelined:
         # H2D of every step's ids and D2H of every step's rows are memcpy nodes of the chunk graphs
         step.capture_pipelined(batches[0], batches[1], host_io=True, steps_per_graph=args.steps_per_graph)
         stream = torch.cuda.current_stream(dev)
@@ -383,7 +408,8 @@ def run_ours(args, w):
                                                 "parallelism": ("row-range shards x%d, history replicas synced by %s write-back exchange"
                                                                 % (world, args.transport)) if world > 1 else "single GPU"}),
             "sampled_edges_per_s": s_edges / (ms * 1e-3),
-            "schedule": {"pipelined": pipelined,
+            "schedule": {"pipelined": pipelined, "driver": ("native (csrc/step.cu, stream launches)" if native_drv
+                                                             else "cuda-graph") if pipelined else "cuda-graph",
                          "steps_per_graph": args.steps_per_graph if pipelined else 1,
                          "what": "CUDA graphs of %d steps; inside a step batch k+1's sampler (1 CTA) runs beside "
                                  "batch k's aggregate (one-batch lookahead, same sequential semantics)"
@@ -398,8 +424,8 @@ def run_ours(args, w):
                     "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(pinned[0].numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4)},
-            "gpu_launches": int(launches_per_step * args.steps),
-            "launches_per_step": int(launches_per_step),
+            "gpu_launches": int(round(launches_per_step * args.steps)),
+            "launches_per_step": float(launches_per_step),
             "clocks": clock_info}
     if kern is not None:
         line["roofline"] = {"bound": "hbm", "kernel": kern["kernel"], "achieved": kern["bytes"] / kern["sec"] / 1e9,
@@ -445,6 +471,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="time one graph per step, no sampler lookahead")
     ap.add_argument("--steps-per-graph", type=int, default=8)
+    ap.add_argument("--driver", default="native", choices=["native", "graph"],
+                    help="pipelined schedule: native C++ stream launches (default) or multi-step CUDA graphs")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU write-back exchange: NVLink peer stores (default) or NCCL all-gather")
     args = ap.parse_args()

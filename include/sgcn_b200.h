@@ -262,12 +262,14 @@ int sgcn_wb_pack(const int32_t* field, const int32_t* n_dev, int32_t n_bound, co
 int sgcn_wb_push(const int32_t* field, const int32_t* n_dev, int32_t n_bound, const float* rows,
                  int64_t ld_rows, int32_t D, void* const* dst_even /*HOST*/, void* const* dst_odd /*HOST*/,
                  int32_t n_dst, void* const* peer_flags /*HOST*/, int32_t my_rank, int32_t* epoch,
+                 int32_t* block_counter /*device scratch int32 = 0, or NULL: signal from a 2nd launch*/,
                  void* stream);
 /* wait_apply: spins (bounded, ~2 s: sets *timeout_flag != 0 instead of hanging) until this rank's
  * flags[0..world) >= *epoch, then merges the `world` payloads of the epoch's receive area */
 int sgcn_wb_wait_apply(float* hist, int64_t ld_h, int32_t D, const void* recv_even, const void* recv_odd,
                        int64_t slot_bytes, int32_t world, int32_t n_bound, int32_t* owner,
-                       const int32_t* flags, const int32_t* epoch, int32_t* timeout_flag, void* stream);
+                       const int32_t* flags, const int32_t* epoch, int32_t* timeout_flag,
+                       int32_t* done_counter /*optional, as sgcn_history_update*/, void* stream);
 /* merge `world` payloads (slot r at gathered + r*slot_bytes) into hist; owner is an int32[N]
  * scratch table that must hold -1 everywhere on entry and does again on exit */
 int sgcn_wb_apply(float* hist, int64_t ld_h, int32_t D, const void* gathered, int64_t slot_bytes,
@@ -304,6 +306,44 @@ int sgcn_cvd_sampled_fwd_bwd(const int32_t* rowptr, const int32_t* cols, const f
                              float* self_h, int64_t ld_sh, float* self_mu, int64_t ld_sm,
                              int32_t accumulate, const float* dy, int64_t ld_dy, float* dx,
                              int64_t ld_dx, void* stream);
+
+/* level-0 buffer of one of the sampler's two buffer sets, valid once sgcn_sampler_reserve has run
+ * for that slot (before any expand) -- which: SGCN_VEC_FIELD / EDG_* / TGT / ROWPTR_* / SCALES / META */
+int sgcn_sampler_slot_vec(sgcn_sampler* s, int32_t slot, int32_t which, void** ptr /*HOST out*/);
+
+/* ------------------------------------------------------------------------------------------
+ * Native step driver: n consecutive passes (gcn/train.py:187-209 inner loop: minibatch ->
+ * run_one_step) issued from C++ onto three internal streams, the sampler of batch k+1 running
+ * beside the aggregate of batch k.  Same results as n sequential passes.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sgcn_step sgcn_step;
+typedef struct {
+    int32_t mode;              /* 0 = NS / plain, 1 = CV, 2 = CVD  (gcn/layers.py:214-362) */
+    int32_t concat;            /* graphsage normalisation: output rows = [self | neighbour] */
+    int32_t batch, degree, hidden, feat_dim;
+    int32_t x0_rows;           /* rows of x0 / dx: >= batch * (1 + degree) */
+    int32_t world, rank, wb_bound;   /* multi-GPU peer exchange (world <= 1: single GPU) */
+    const float* features; int64_t ld_feat;      /* [N, feat_dim] input (PP) features */
+    float* history; int64_t ld_hist;             /* [N, hidden] (CV / CVD) */
+    float* x0; int64_t ld_x0;                    /* [x0_rows, feat_dim] gathered input rows */
+    float* out[2]; float* out_mu[2]; int64_t ld_out;   /* [batch, hidden * (1 + concat)] per buffer set */
+    const float* d_out; int64_t ld_dout;         /* upstream gradient, same shape as out */
+    float* dx; int64_t ld_dx;                    /* [x0_rows, hidden] */
+    int64_t slot_bytes;
+    void* dst_even[16]; void* dst_odd[16]; void* peer_flags[16];
+    void* recv_even; void* recv_odd; const int32_t* flags;
+    int32_t* epoch; int32_t* timeout_flag; int32_t* block_counter; int32_t* owner;
+} sgcn_step_desc;
+int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_desc* desc /*HOST*/);
+void sgcn_step_destroy(sgcn_step* st);
+/* ids: int32 [n][batch], device memory (ids_on_host = 0; borrowed until the run has finished) or
+ * PINNED host memory (1: copied H2D step by step on the sampler stream).  out_host: NULL, or pinned
+ * float [n][batch][hidden * (1 + concat)] receiving every pass's aggregated rows (D2H per pass).
+ * The run is ordered after the work already on `stream`, and `stream` waits for its completion.
+ * The sampler must be in pipeline mode (sgcn_sampler_pipeline) and have had sgcn_sampler_set_stream
+ * called once. */
+int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -73,11 +73,15 @@ SIGNATURES = {
                                         _i64, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32,
                                         _vp, _i64, _vp, _i64, _vp]),
     "sgcn_copy_rows_pad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "sgcn_sampler_slot_vec": (_i32, [_vp, _i32, _i32, C.POINTER(_vp)]),
+    "sgcn_step_create": (_i32, [C.POINTER(_vp), _vp, _vp]),
+    "sgcn_step_destroy": (None, [_vp]),
+    "sgcn_step_run": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "sgcn_wb_payload_bytes": (_i64, [_i32, _i32]),
     "sgcn_wb_pack": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), _i32, _i32, _vp]),
     "sgcn_wb_push": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), C.POINTER(_vp), _i32,
-                            C.POINTER(_vp), _i32, _vp, _vp]),
-    "sgcn_wb_wait_apply": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+                            C.POINTER(_vp), _i32, _vp, _vp, _vp]),
+    "sgcn_wb_wait_apply": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgcn_wb_apply": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp]),
     "sgcn_ipc_alloc": (_i32, [C.POINTER(_vp), _i64, _i32]),
     "sgcn_ipc_free": (_i32, [_vp]),
@@ -85,6 +89,18 @@ SIGNATURES = {
     "sgcn_ipc_open": (_i32, [_vp, C.POINTER(_vp)]),
     "sgcn_ipc_close": (_i32, [_vp]),
 }
+
+class StepDesc(C.Structure):
+    """mirror of sgcn_step_desc (include/sgcn_b200.h)"""
+    _fields_ = [("mode", _i32), ("concat", _i32), ("batch", _i32), ("degree", _i32), ("hidden", _i32),
+                ("feat_dim", _i32), ("x0_rows", _i32), ("world", _i32), ("rank", _i32), ("wb_bound", _i32),
+                ("features", _vp), ("ld_feat", _i64), ("history", _vp), ("ld_hist", _i64),
+                ("x0", _vp), ("ld_x0", _i64), ("out", _vp * 2), ("out_mu", _vp * 2), ("ld_out", _i64),
+                ("d_out", _vp), ("ld_dout", _i64), ("dx", _vp), ("ld_dx", _i64), ("slot_bytes", _i64),
+                ("dst_even", _vp * 16), ("dst_odd", _vp * 16), ("peer_flags", _vp * 16),
+                ("recv_even", _vp), ("recv_odd", _vp), ("flags", _vp), ("epoch", _vp), ("timeout_flag", _vp),
+                ("block_counter", _vp), ("owner", _vp)]
+
 
 _lib = None
 

@@ -34,7 +34,8 @@ struct PeerPtrs { char* p[kMaxPeers]; };
 __global__ void __launch_bounds__(256)
 wb_pack_kernel(const int32_t* __restrict__ field, const int32_t* __restrict__ n_dev, int n_bound,
                const float* __restrict__ rows, int64_t ld_rows, int D, PeerPtrs dst_even, PeerPtrs dst_odd,
-               int n_dst, int step, const int32_t* __restrict__ epoch) {
+               int n_dst, int step, int32_t* epoch, PeerPtrs flags, int my_rank,
+               int32_t* block_counter) {
     // peer transport: this push belongs to epoch *epoch + 1 and lands in the slot set of its parity
     if (epoch) step = *epoch + 1;
     const PeerPtrs& dst = (epoch && (step & 1)) ? dst_odd : dst_even;
@@ -67,6 +68,24 @@ wb_pack_kernel(const int32_t* __restrict__ field, const int32_t* __restrict__ n_
             const int c = (int)(t - r * D);
             const float v = rows[r * ld_rows + c];
             for (int k = 0; k < n_dst; ++k) *(float*)(dst.p[k] + rows_off + (r * D + c) * 4) = v;
+        }
+    }
+    if (block_counter) {
+        // fused signal: the last block to finish advances the epoch and publishes it to every rank
+        __shared__ int s_last;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(block_counter, 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (s_last && threadIdx.x == 0) {
+            *block_counter = 0;
+            *epoch = step;
+            __threadfence_system();
+            for (int k = 0; k < n_dst; ++k) {
+                volatile int32_t* f = (volatile int32_t*)flags.p[k];
+                f[my_rank] = step;
+            }
+            __threadfence_system();
         }
     }
 }
@@ -108,7 +127,10 @@ __global__ void __launch_bounds__(256)
 wb_claim_kernel(const char* g_even, const char* g_odd,
                 const int32_t* __restrict__ epoch, int64_t slot_bytes, int world, int n_bound,
                 int32_t* __restrict__ owner, const int32_t* flags, int32_t* timeout_flag,
-                long long max_spins) {
+                long long max_spins, int32_t* done_counter) {
+    // optional: count this launch as "everything stream-ordered before it has finished" (see
+    // sgcn_history_update: the pipelined step's consumer mark)
+    if (done_counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(done_counter, 1);
     if (flags) {
         // peer transport: every block first waits (bounded) until all ranks have published this epoch
         if (threadIdx.x < world) {
@@ -203,14 +225,15 @@ int sgcn_wb_pack(const int32_t* field, const int32_t* n_dev, int32_t n_bound, co
     int rc = fill_ptrs(p, dst, n_dst, "wb_pack");
     if (rc != SGCN_OK) return rc;
     wb_pack_kernel<<<pack_blocks(n_bound, D), 256, 0, (cudaStream_t)stream>>>(
-        field, n_dev, n_bound, rows, ld_rows, D, p, p, n_dst, step, nullptr);
+        field, n_dev, n_bound, rows, ld_rows, D, p, p, n_dst, step, nullptr, p, 0, nullptr);
     SGCN_LAUNCHED();
     return SGCN_OK;
 }
 
 int sgcn_wb_push(const int32_t* field, const int32_t* n_dev, int32_t n_bound, const float* rows,
                  int64_t ld_rows, int32_t D, void* const* dst_even, void* const* dst_odd, int32_t n_dst,
-                 void* const* peer_flags, int32_t my_rank, int32_t* epoch, void* stream) {
+                 void* const* peer_flags, int32_t my_rank, int32_t* epoch, int32_t* block_counter,
+                 void* stream) {
     SGCN_REQUIRE(field && n_dev && rows && dst_even && dst_odd && peer_flags && epoch, "wb_push: null pointer");
     SGCN_REQUIRE(n_bound >= 0 && D > 0 && ld_rows >= D, "wb_push: bad size");
     SGCN_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers && my_rank >= 0 && my_rank < kMaxPeers, "wb_push: 1..16 ranks");
@@ -221,21 +244,23 @@ int sgcn_wb_push(const int32_t* field, const int32_t* n_dev, int32_t n_bound, co
     if (rc != SGCN_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     wb_pack_kernel<<<pack_blocks(n_bound, D), 256, 0, st>>>(field, n_dev, n_bound, rows, ld_rows, D, pe, po,
-                                                           n_dst, 0, epoch);
+                                                           n_dst, 0, epoch, pf, my_rank, block_counter);
     SGCN_LAUNCHED();
-    wb_signal_kernel<<<1, 32, 0, st>>>(pf, n_dst, my_rank, epoch);
-    SGCN_LAUNCHED();
+    if (!block_counter) {      // no scratch counter given: publish from a second, stream-ordered launch
+        wb_signal_kernel<<<1, 32, 0, st>>>(pf, n_dst, my_rank, epoch);
+        SGCN_LAUNCHED();
+    }
     return SGCN_OK;
 }
 
 static int launch_apply(float* hist, int64_t ld_h, int32_t D, const void* g_even, const void* g_odd,
                         const int32_t* epoch, int64_t slot_bytes, int32_t world, int32_t n_bound,
                         int32_t* owner, cudaStream_t st, const int32_t* flags = nullptr,
-                        int32_t* timeout_flag = nullptr) {
+                        int32_t* timeout_flag = nullptr, int32_t* done_counter = nullptr) {
     dim3 g1(std::min(div_up(std::max(n_bound, 1), 256), 64), world);
     // ~2 s at 100 ns per spin: a peer that never arrives raises the flag instead of hanging the GPU
     wb_claim_kernel<<<g1, 256, 0, st>>>((const char*)g_even, (const char*)g_odd, epoch, slot_bytes, world,
-                                        n_bound, owner, flags, timeout_flag, 20000000LL);
+                                        n_bound, owner, flags, timeout_flag, 20000000LL, done_counter);
     SGCN_LAUNCHED();
     dim3 g2(std::min(div_up(std::max(n_bound, 1), 8), kNumSMs), world);
     const bool vec = D % 4 == 0 && ld_h % 4 == 0 && (((uintptr_t)hist) & 15) == 0 && slot_bytes % 16 == 0 &&
@@ -263,7 +288,8 @@ int sgcn_wb_apply(float* hist, int64_t ld_h, int32_t D, const void* gathered, in
 
 int sgcn_wb_wait_apply(float* hist, int64_t ld_h, int32_t D, const void* recv_even, const void* recv_odd,
                        int64_t slot_bytes, int32_t world, int32_t n_bound, int32_t* owner,
-                       const int32_t* flags, const int32_t* epoch, int32_t* timeout_flag, void* stream) {
+                       const int32_t* flags, const int32_t* epoch, int32_t* timeout_flag,
+                       int32_t* done_counter, void* stream) {
     SGCN_REQUIRE(hist && recv_even && recv_odd && owner && flags && epoch && timeout_flag,
                  "wb_wait_apply: null pointer");
     SGCN_REQUIRE(world >= 1 && world <= 32 && n_bound >= 0 && D > 0 && ld_h >= D, "wb_wait_apply: bad size");
@@ -277,7 +303,7 @@ int sgcn_wb_wait_apply(float* hist, int64_t ld_h, int32_t D, const void* recv_ev
     }
     // the wait is fused into the claim pass (every block polls the flags before touching a payload)
     return launch_apply(hist, ld_h, D, recv_even, recv_odd, epoch, slot_bytes, world, n_bound, owner, st,
-                        flags, timeout_flag);
+                        flags, timeout_flag, done_counter);
 }
 
 // ---- peer memory plumbing (cudaIpc): plain cudaMalloc'd buffers that other ranks can map -----

@@ -1467,6 +1467,37 @@ int sgcn_sampler_vec(sgcn_sampler* s, int32_t level, int32_t which, void** ptr, 
     return SGCN_OK;
 }
 
+int sgcn_sampler_slot_vec(sgcn_sampler* s, int32_t slot, int32_t which, void** ptr) {
+    SGCN_REQUIRE(s && ptr && (slot == 0 || slot == 1), "sampler_slot_vec: bad argument");
+    *ptr = nullptr;
+    auto& sl = s->slots[slot];
+    if (sl.levels.empty()) {
+        set_error("sampler_slot_vec: slot has no reserved level (call sgcn_sampler_reserve first)");
+        return SGCN_ESTATE;
+    }
+    Level& lv = sl.levels[0];
+    switch (which) {
+        case SGCN_VEC_FIELD: *ptr = lv.field.p; break;
+        case SGCN_VEC_EDG_S: *ptr = lv.edg_s.p; break;
+        case SGCN_VEC_EDG_T: *ptr = lv.edg_t.p; break;
+        case SGCN_VEC_TGT: *ptr = lv.tgt.p; break;
+        case SGCN_VEC_EDG_W: *ptr = lv.edg_w.p; break;
+        case SGCN_VEC_MEDG_W: *ptr = lv.medg_w.p; break;
+        case SGCN_VEC_ROWPTR_S: *ptr = lv.rowptr_s.p; break;
+        case SGCN_VEC_ROWPTR_F: *ptr = lv.rowptr_f.p; break;
+        case SGCN_VEC_SCALES: *ptr = lv.scales.p; break;
+        case SGCN_VEC_META: *ptr = lv.meta.p; break;
+        default:
+            set_error("sampler_slot_vec: unknown vector id");
+            return SGCN_EINVAL;
+    }
+    if (!*ptr) {
+        set_error("sampler_slot_vec: buffer not allocated (call sgcn_sampler_reserve for this slot first)");
+        return SGCN_ESTATE;
+    }
+    return SGCN_OK;
+}
+
 int sgcn_sampler_copy_vec(sgcn_sampler* s, int32_t level, int32_t which, void* dst, int64_t count) {
     SGCN_REQUIRE(s && (dst || count == 0) && count >= 0, "sampler_copy_vec: bad argument");
     void* p = nullptr;

@@ -1,0 +1,264 @@
+// Native step driver: n consecutive passes of the hot path issued from C++ onto three CUDA streams,
+// with the sampler of batch k+1 running beside the aggregate of batch k.
+//
+// Why not only CUDA graphs: on this driver a graph launch expands its nodes on the device at ~1.8 us
+// per kernel node, branch by branch, AFTER the previous launch on the stream has finished
+// (tools/graph_overhead.py, tools/timeline.py) -- for a step of six short kernels next to one 20 us
+// kernel that is ~10 us of pure turnaround per step.  Plain stream launches keep every queue fed in
+// step order: the CPU costs ~15 us per step and runs ahead of the ~25 us the GPU needs.
+//
+//   chain : [wait sampler k] full_mean(k) ─► [wait fwd k] history_update(k) ─► ...
+//   side  : [wait sampler k, rest k-1] dX init + zero(out k+1) ─► gather(k) ─► (publish) ─► fwd+bwd(k) ─► D2H(k)
+//   samp  : [wait rest k-1] (H2D ids k+1) ─► expand(k+1) into the other buffer set
+//
+// Semantics are exactly those of n sequential passes (same sampler order and RNG stream, every
+// forward read of history before the write-back, write-back k before any read of pass k+1); the
+// in-place row permutation is guarded on the device (sgcn_sampler_pipeline).
+#include <vector>
+
+#include "common.cuh"
+
+struct sgcn_step {
+    sgcn_sampler* sampler = nullptr;
+    sgcn_step_desc d{};
+    cudaStream_t chain = nullptr, side = nullptr, samp = nullptr;
+    int32_t* ids_dev[2] = {nullptr, nullptr};      // staging of host ids
+    // level-0 buffers of the sampler's two slots
+    struct Lv { int32_t *field, *rowptr_s, *rowptr_f, *edg_t, *tgt, *meta; float *edg_w, *scales; } lv[2]{};
+    const int32_t* adj_p = nullptr; const int32_t* adj_i = nullptr; const float* adj_w = nullptr;
+    int32_t* pipe = nullptr;
+    static constexpr int kRing = 4;
+    cudaEvent_t ev_samp[kRing]{}, ev_full[kRing]{}, ev_fwd[kRing]{}, ev_rest[kRing]{}, ev_begin = nullptr,
+                ev_side_end = nullptr, ev_samp_end = nullptr, ev_zero0 = nullptr;
+    int device = 0;
+};
+
+namespace sgcn {
+#define STEP_TRY(expr)                     \
+    do {                                   \
+        int rc__ = (expr);                 \
+        if (rc__ != SGCN_OK) return rc__;  \
+    } while (0)
+
+static int get_slot_vec(sgcn_sampler* s, int slot, int which, void** p) { return sgcn_sampler_slot_vec(s, slot, which, p); }
+}  // namespace sgcn
+
+using namespace sgcn;
+
+extern "C" {
+
+int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_desc* desc) {
+    SGCN_REQUIRE(out && sampler && desc, "step_create: null argument");
+    *out = nullptr;
+    const sgcn_step_desc& d = *desc;
+    SGCN_REQUIRE(d.mode >= 0 && d.mode <= 2 && d.batch > 0 && d.degree >= 0 && d.hidden > 0 && d.feat_dim > 0,
+                 "step_create: bad sizes");
+    SGCN_REQUIRE(d.features && d.x0 && d.out[0] && d.out[1] && d.d_out && d.dx, "step_create: null buffer");
+    SGCN_REQUIRE(d.mode == 0 || d.history, "step_create: CV / CVD need a history table");
+    SGCN_REQUIRE(d.mode != 2 || (d.out_mu[0] && d.out_mu[1] && d.feat_dim >= 2 * d.hidden),
+                 "step_create: CVD needs out_mu buffers and 2*hidden feature columns");
+    SGCN_REQUIRE(d.world <= 16, "step_create: at most 16 ranks");
+    sgcn_step* st = new sgcn_step();
+    st->sampler = sampler;
+    st->d = d;
+    SGCN_CUDA(cudaGetDevice(&st->device));
+    auto fail = [&](int rc) {
+        sgcn_step_destroy(st);
+        return rc;
+    };
+    // both buffer sets of the sampler, sized once; their level-0 pointers never move afterwards
+    for (int slot = 0; slot < 2; ++slot) {
+        int rc = sgcn_sampler_set_slot(sampler, slot);
+        if (rc == SGCN_OK) rc = sgcn_sampler_reserve(sampler, d.batch, &d.degree, 1, 0);
+        void* p = nullptr;
+#define GET(which, field, T)                                                     \
+    if (rc == SGCN_OK) { rc = get_slot_vec(sampler, slot, which, &p); st->lv[slot].field = (T*)p; }
+        GET(SGCN_VEC_FIELD, field, int32_t)
+        GET(SGCN_VEC_ROWPTR_S, rowptr_s, int32_t)
+        GET(SGCN_VEC_ROWPTR_F, rowptr_f, int32_t)
+        GET(SGCN_VEC_EDG_T, edg_t, int32_t)
+        GET(SGCN_VEC_TGT, tgt, int32_t)
+        GET(SGCN_VEC_META, meta, int32_t)
+        GET(SGCN_VEC_EDG_W, edg_w, float)
+        GET(SGCN_VEC_SCALES, scales, float)
+#undef GET
+        if (rc != SGCN_OK) return fail(rc);
+    }
+    sgcn_sampler_set_slot(sampler, 0);
+    void* p = nullptr;
+    int64_t len = 0;
+    int rc = sgcn_sampler_vec(sampler, 0, SGCN_VEC_ADJ_P, &p, &len); st->adj_p = (const int32_t*)p;
+    if (rc == SGCN_OK) { rc = sgcn_sampler_vec(sampler, 0, SGCN_VEC_ADJ_I, &p, &len); st->adj_i = (const int32_t*)p; }
+    if (rc == SGCN_OK) { rc = sgcn_sampler_vec(sampler, 0, SGCN_VEC_ADJ_W, &p, &len); st->adj_w = (const float*)p; }
+    if (rc == SGCN_OK) { rc = sgcn_sampler_vec(sampler, 0, SGCN_VEC_PIPE, &p, &len); st->pipe = (int32_t*)p; }
+    if (rc != SGCN_OK) return fail(rc);
+#define CK(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) return fail(cuda_fail(e__, #call, __FILE__, __LINE__)); \
+    } while (0)
+    CK(cudaStreamCreateWithFlags(&st->chain, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&st->samp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&st->ids_dev[i], sizeof(int32_t) * (size_t)d.batch));
+    for (int i = 0; i < sgcn_step::kRing; ++i) {
+        CK(cudaEventCreateWithFlags(&st->ev_samp[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&st->ev_full[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&st->ev_fwd[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&st->ev_rest[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&st->ev_begin, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&st->ev_side_end, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&st->ev_samp_end, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&st->ev_zero0, cudaEventDisableTiming));
+#undef CK
+    *out = st;
+    return SGCN_OK;
+}
+
+void sgcn_step_destroy(sgcn_step* st) {
+    if (!st) return;
+    for (cudaStream_t s : {st->chain, st->side, st->samp})
+        if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (int i = 0; i < 2; ++i) cudaFree(st->ids_dev[i]);
+    for (int i = 0; i < sgcn_step::kRing; ++i)
+        for (cudaEvent_t e : {st->ev_samp[i], st->ev_full[i], st->ev_fwd[i], st->ev_rest[i]})
+            if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {st->ev_begin, st->ev_side_end, st->ev_samp_end, st->ev_zero0})
+        if (e) cudaEventDestroy(e);
+    delete st;
+}
+
+int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
+                  void* stream) {
+    SGCN_REQUIRE(st && n >= 0 && (n == 0 || ids), "step_run: bad argument");
+    if (n == 0) return SGCN_OK;
+    const sgcn_step_desc& d = st->d;
+    sgcn_sampler* smp = st->sampler;
+    const int B = d.batch, H = d.hidden, R = sgcn_step::kRing;
+    const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0, multi = d.world > 1 && cv;
+    const int width = H * (concat ? 2 : 1);
+    cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp;
+
+    // the neighbour half of out[slot] (and of out_mu[slot]); the self half when concatenating
+    auto nb = [&](float* base) { return base + (concat ? H : 0); };
+
+    SGCN_CUDA(cudaEventRecord(st->ev_begin, user));
+    for (cudaStream_t s : {chain, side, samp}) SGCN_CUDA(cudaStreamWaitEvent(s, st->ev_begin, 0));
+
+    auto sample = [&](int k) -> int {         // sampler of batch k into slot k&1, on the samp stream
+        const int slot = k & 1;
+        const int32_t* src = ids + (int64_t)k * B;
+        if (ids_on_host) {
+            SGCN_CUDA(cudaMemcpyAsync(st->ids_dev[slot], src, sizeof(int32_t) * (size_t)B,
+                                      cudaMemcpyHostToDevice, samp));
+            src = st->ids_dev[slot];
+        }
+        STEP_TRY(sgcn_sampler_set_slot(smp, slot));
+        STEP_TRY(sgcn_sampler_start_batch_device(smp, B, src));
+        STEP_TRY(sgcn_sampler_expand(smp, d.degree, 0));
+        SGCN_CUDA(cudaEventRecord(st->ev_samp[k % R], samp));
+        return SGCN_OK;
+    };
+
+    STEP_TRY(sgcn_sampler_set_stream_async(smp, samp));
+    // outputs of pass 0 start from zero (later passes: zeroed one step ahead on the side stream)
+    if (cv) {
+        STEP_TRY(sgcn_copy_rows_pad_pair(nullptr, 0, 0, nullptr, B, H, nb(d.out[0]), d.ld_out, nullptr, 0, 0, nullptr,
+                                         cvd ? B : 0, H, cvd ? nb(d.out_mu[0]) : nullptr, d.ld_out, chain));
+        SGCN_CUDA(cudaEventRecord(st->ev_zero0, chain));
+        SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_zero0, 0));     // pass 0's sampled part adds into it too
+    }
+    STEP_TRY(sample(0));
+
+    for (int k = 0; k < n; ++k) {
+        const int r = k & 1, s = 1 - r;
+        const sgcn_step::Lv& v = st->lv[r];
+        const int32_t* n_out_dev = v.meta + 0;
+        const int32_t* n_in_dev = v.meta + 1;
+        float* out_r = d.out[r];
+        float* outmu_r = d.out_mu[r];
+
+        // ---- chain: the full-neighbour history mean of pass k ----
+        SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_samp[k % R], 0));
+        if (cv) {
+            STEP_TRY(sgcn_full_history_mean(v.field, v.rowptr_f, B, n_out_dev, st->adj_p, st->adj_i, st->adj_w,
+                                            d.history, d.ld_hist, H, cvd ? nb(outmu_r) : nb(out_r), d.ld_out,
+                                            cvd ? nb(out_r) : nullptr, d.ld_out, nullptr, chain));
+        }
+        SGCN_CUDA(cudaEventRecord(st->ev_full[k % R], chain));
+
+        // ---- samp: sampler of batch k+1 into the other buffer set (free once pass k-1 has finished) ----
+        if (k + 1 < n) {
+            if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(samp, st->ev_rest[(k - 1) % R], 0));
+            STEP_TRY(sample(k + 1));
+        }
+
+        // ---- side: dX init + next output zeroing, gather, (publish), sampled aggregate + backward ----
+        SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_samp[k % R], 0));
+        if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_rest[(k - 1) % R], 0));   // x0 / out[s] are free
+        const bool zero_next = cv && k + 1 < n;
+        STEP_TRY(sgcn_copy_rows_pad_pair(concat ? d.d_out : nullptr, d.ld_dout, concat ? B : 0,
+                                         concat ? n_out_dev : nullptr, d.x0_rows, H, d.dx, d.ld_dx,
+                                         nullptr, 0, 0, nullptr, zero_next ? B : 0, H,
+                                         zero_next ? nb(d.out[s]) : nullptr, d.ld_out, side));
+        if (zero_next && cvd)
+            STEP_TRY(sgcn_copy_rows_pad(nullptr, 0, 0, nullptr, B, H, nb(d.out_mu[s]), d.ld_out, side));
+        STEP_TRY(sgcn_gather_rows(d.features, d.ld_feat, v.field, d.x0_rows, n_in_dev, d.feat_dim, d.x0, d.ld_x0, side));
+        const float* x = d.x0;
+        const float* mu = d.x0 + H;
+        const float* new_hist = cvd ? mu : x;
+        const float* d_nb = d.d_out + (concat ? H : 0);
+        if (multi)
+            STEP_TRY(sgcn_wb_push(v.field, n_in_dev, d.wb_bound, new_hist, d.ld_x0, H, d.dst_even, d.dst_odd,
+                                  d.world, d.peer_flags, d.rank, d.epoch, d.block_counter, side));
+        if (d.mode == 0) {
+            STEP_TRY(sgcn_spmm_csr(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, x, d.ld_x0, H, nb(out_r),
+                                   d.ld_out, 0, side));
+            if (concat)
+                STEP_TRY(sgcn_copy_rows_pad(x, d.ld_x0, B, n_out_dev, B, H, out_r, d.ld_out, side));
+            STEP_TRY(sgcn_spmm_csr_bwd(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, d_nb, d.ld_dout, H, d.dx,
+                                       d.ld_dx, side));
+        } else if (!cvd) {
+            STEP_TRY(sgcn_cv_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, B, n_out_dev, x, d.ld_x0, d.history,
+                                             d.ld_hist, H, nb(out_r), d.ld_out, concat ? out_r : nullptr, d.ld_out, 1,
+                                             d_nb, d.ld_dout, d.dx, d.ld_dx, side));
+        } else {
+            STEP_TRY(sgcn_cvd_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, v.scales, B, n_out_dev, x, d.ld_x0,
+                                              mu, d.ld_x0, d.history, d.ld_hist, H, nb(out_r), d.ld_out,
+                                              nb(outmu_r), d.ld_out, concat ? out_r : nullptr, d.ld_out,
+                                              concat ? outmu_r : nullptr, d.ld_out, 1, d_nb, d.ld_dout, d.dx,
+                                              d.ld_dx, side));
+        }
+        SGCN_CUDA(cudaEventRecord(st->ev_fwd[k % R], side));
+
+        // ---- chain: write-back after every forward read of history (gcn/models.py:186-194) ----
+        SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_fwd[k % R], 0));
+        if (!cv) {
+            STEP_TRY(sgcn_sampler_mark_consumed(smp, chain));
+        } else if (multi) {
+            STEP_TRY(sgcn_wb_wait_apply(d.history, d.ld_hist, H, d.recv_even, d.recv_odd, d.slot_bytes, d.world,
+                                        d.wb_bound, d.owner, d.flags, d.epoch, d.timeout_flag, st->pipe + 1, chain));
+        } else {
+            STEP_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
+                                         st->pipe + 1, chain));
+        }
+        SGCN_CUDA(cudaEventRecord(st->ev_rest[k % R], chain));
+
+        // ---- side: the step's aggregated rows to pinned host memory ----
+        if (out_host) {
+            SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_full[k % R], 0));
+            SGCN_CUDA(cudaMemcpy2DAsync(out_host + (int64_t)k * B * width, sizeof(float) * (size_t)width, out_r,
+                                        sizeof(float) * (size_t)d.ld_out, sizeof(float) * (size_t)width, (size_t)B,
+                                        cudaMemcpyDeviceToHost, side));
+        }
+    }
+    SGCN_CUDA(cudaEventRecord(st->ev_side_end, side));
+    SGCN_CUDA(cudaEventRecord(st->ev_samp_end, samp));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_rest[(n - 1) % R], 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));
+    return SGCN_OK;
+}
+
+}  // extern "C"

@@ -114,6 +114,7 @@ class PeerExchange:
         self.flags = C.c_void_p(self.base)
         self.epoch = C.c_void_p(self.base + self.off_ctl)
         self.timeout = C.c_void_p(self.base + self.off_ctl + 4)
+        self.block_counter = C.c_void_p(self.base + self.off_ctl + 8)   # scratch of the fused pack + signal
         self.recv_even = C.c_void_p(self.base + self.off_even)
         self.recv_odd = C.c_void_p(self.base + self.off_odd)
         self._ctl = torch.as_tensor(_DevBytes(self.base, 512), device=device).view(torch.int32)
@@ -173,7 +174,7 @@ class ShardedHotPathStep(HotPathStep):
             x = self._exchange
             check(lib.sgcn_wb_push(ptr(v["field"]), ptr(v["n_in_dev"]), self.wb_bound, ptr(new_hist), ld, D,
                                    x.dst_even, x.dst_odd, self.world, x.peer_flags, self.rank, x.epoch,
-                                   stream_ptr()))
+                                   x.block_counter, stream_ptr()))
         else:
             check(lib.sgcn_wb_pack(ptr(v["field"]), ptr(v["n_in_dev"]), self.wb_bound, ptr(new_hist), ld, D,
                                    self._send_ptr, 1, 0, stream_ptr()))
@@ -185,8 +186,23 @@ class ShardedHotPathStep(HotPathStep):
             check(_lib.load().sgcn_wb_wait_apply(ptr(self.history), self.history.stride(0), self.hidden,
                                                  x.recv_even, x.recv_odd, self.slot_bytes, self.world,
                                                  self.wb_bound, ptr(self.owner), x.flags, x.epoch, x.timeout,
-                                                 stream_ptr()))
+                                                 ptr(done_counter), stream_ptr()))
+            return done_counter is not None
         return False
+
+    def _step_desc(self):
+        d = super()._step_desc()
+        if self._exchange is not None:
+            x = self._exchange
+            d.world, d.rank, d.wb_bound, d.slot_bytes = self.world, self.rank, self.wb_bound, self.slot_bytes
+            for i in range(self.world):
+                d.dst_even[i], d.dst_odd[i], d.peer_flags[i] = x.dst_even[i], x.dst_odd[i], x.peer_flags[i]
+            d.recv_even, d.recv_odd, d.flags = x.recv_even.value, x.recv_odd.value, x.flags.value
+            d.epoch, d.timeout_flag, d.block_counter = x.epoch.value, x.timeout.value, x.block_counter.value
+            d.owner = self.owner.data_ptr()
+        elif self.mode != "ns" and self.world > 1:
+            raise RuntimeError("the native step driver needs the peer transport for multi-GPU runs")
+        return d
 
     def _finish_exchange(self):
         """NCCL transport: the collective and the merge run eagerly after the (captured) pass."""

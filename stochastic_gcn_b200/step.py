@@ -308,10 +308,7 @@ class HotPathStep:
             self.ids2[p].copy_(ids)
             self._eager_step(p, sample=True)
         torch.cuda.synchronize(self.dev)
-        if not self._pipeline_on:
-            self.sampler.pipeline(True)
-            self._pipeline_on = True
-            self._pipe_done = self.sampler.view("pipe")[1:2]    # the guard's consumer counter
+        self._enable_pipeline_guard()
         B, width = self.B, self.outs[0].shape[1]
         # tab[c][k] = ids of the batch that step k of a parity-c chunk samples AHEAD (batch k+1 of the
         # chunk; row S-1 is the first batch of the next chunk)
@@ -385,7 +382,7 @@ class HotPathStep:
 
     def _eager_step(self, slot, sample):
         main = torch.cuda.current_stream(self.dev)
-        if self.sampler._stream.cuda_stream != main.cuda_stream:
+        if getattr(self.sampler, "_stream", None) is None or self.sampler._stream.cuda_stream != main.cuda_stream:
             self.sampler.use_stream(main)
         if sample:
             self._zero_out(slot)
@@ -438,6 +435,66 @@ class HotPathStep:
                     ev = torch.cuda.Event()
                     ev.record()
                     on_chunk(base + j, 1, self, ev)
+        return self.out
+
+    # -- native driver ----------------------------------------------------------------------------
+    def _enable_pipeline_guard(self):
+        if not self._pipeline_on:
+            self.sampler.pipeline(True)
+            self._pipeline_on = True
+            self._pipe_done = self.sampler.view("pipe")[1:2]    # the guard's consumer counter
+
+    def _step_desc(self):
+        """sgcn_step_desc of this step (the sharded subclass adds the exchange fields)."""
+        d = _lib.StepDesc()
+        d.mode = MODES.index(self.mode)
+        d.concat = int(self.concat)
+        d.batch, d.degree, d.hidden, d.feat_dim = self.B, self.degree, self.hidden, self.features.shape[1]
+        d.x0_rows = self.x0.shape[0]
+        d.world, d.rank, d.wb_bound = 1, 0, 0
+        d.features, d.ld_feat = self.features.data_ptr(), self.features.stride(0)
+        d.history, d.ld_hist = self.history.data_ptr(), self.history.stride(0)
+        d.x0, d.ld_x0 = self.x0.data_ptr(), self.x0.stride(0)
+        for i in (0, 1):
+            d.out[i] = self.outs[i].data_ptr()
+            d.out_mu[i] = self.outs_mu[i].data_ptr() if self.outs_mu[i] is not None else None
+        d.ld_out = self.outs[0].stride(0)
+        d.d_out, d.ld_dout = self.d_out.data_ptr(), self.d_out.stride(0)
+        d.dx, d.ld_dx = self.dx.data_ptr(), self.dx.stride(0)
+        return d
+
+    def run_native(self, batches, out_host=None):
+        """Run len(batches) consecutive passes through the native step driver (csrc/step.cu): plain
+        stream launches from C++ on three streams, the sampler of batch k+1 beside the aggregate of
+        batch k -- one ctypes call for the whole run.  ``batches``: an int32 [n, B] tensor or a list
+        of [B] tensors, on the GPU or in (pinned) host memory.  ``out_host``: optional pinned float32
+        [n, B, width] tensor that receives every pass's aggregated rows."""
+        import ctypes as C
+        lib = _lib.load()
+        if getattr(self, "_native_h", None) is None:
+            self._enable_pipeline_guard()
+            desc = self._step_desc()
+            h = C.c_void_p()
+            _lib.check(lib.sgcn_step_create(C.byref(h), self.sampler._h, C.byref(desc)))
+            self._native_h, self._native_desc = h, desc
+        table = batches if isinstance(batches, torch.Tensor) else torch.stack(list(batches))
+        table = table.to(torch.int32).contiguous()
+        n = int(table.shape[0])
+        if n == 0:
+            return self.out
+        if table.shape[1] != self.B:
+            raise ValueError("every batch must hold exactly %d ids" % self.B)
+        on_host = not table.is_cuda
+        if on_host and not table.is_pinned():
+            table = table.pin_memory()
+        if out_host is not None and not (out_host.is_pinned() and out_host.is_contiguous()
+                                         and tuple(out_host.shape) == (n, self.B, self.outs[0].shape[1])):
+            raise ValueError("out_host must be a pinned contiguous [n, B, width] float32 tensor")
+        self._native_keep = (table, out_host)          # borrowed by the driver until the run completes
+        _lib.check(lib.sgcn_step_run(self._native_h, _lib.ptr(table), int(on_host), n,
+                                     _lib.ptr(out_host) if out_host is not None else None, _lib.stream_ptr()))
+        self._last_slot = (n - 1) & 1
+        self.sampler._stream = None                    # the driver left the sampler on its own stream
         return self.out
 
     def time_dominant_kernel(self, batches):

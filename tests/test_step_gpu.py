@@ -158,3 +158,57 @@ def test_pipelined_driver_matches_oracle_incl_overlapping_batches(mode, deg):
     step.run(batches[6])
     torch.cuda.synchronize()
     assert step.sizes()["n_out"] == B
+
+
+@pytest.mark.parametrize("mode,deg,norm", [("cv", 2, "graphsage"), ("cvd", 1, "graphsage"), ("ns", 1, "graphsage"),
+                                           ("cvd", 1, "gcn"), ("cv", 2, "gcn")])
+@pytest.mark.parametrize("host_io", [False, True])
+def test_native_driver_matches_oracle(mode, deg, norm, host_io):
+    """csrc/step.cu: n passes from one C call (three streams, sampler lookahead) == n sequential
+    oracle passes, incl. batches that share nodes with their predecessor; 'gcn' normalisation is the
+    PubMed / Cora form (no self-concat, BASELINE configs[0-1])."""
+    from stochastic_gcn_b200 import graphs
+    from stochastic_gcn_b200.step import HotPathStep
+    gs = norm != "gcn"
+    g = graphs.powerlaw_graph(3000, 120_000, seed=4, device="cuda", max_degree=600)
+    D, B = 32, 48
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    feats = torch.randn((g.n, 80), generator=gen, device="cuda")
+    step = HotPathStep(g, feats, D, B, deg, mode=mode, seed=5, normalization=norm)
+    step.history.normal_(generator=gen)
+    step.d_out.normal_(generator=gen)
+    hist = step.history.cpu().numpy().copy()
+    o = native.OracleSampler(g.data.cpu().numpy(), g.indices.cpu().numpy(), g.indptr.cpu().numpy(), cv=mode != "ns")
+    o.seed(5)
+    fh, d_out = feats.cpu().numpy(), step.d_out.cpu().numpy()
+    perm = torch.randperm(g.n, generator=gen, device="cuda").to(torch.int32)
+    batches = [perm[i * B:(i + 1) * B].contiguous() for i in range(7)]
+    batches[3] = torch.cat((batches[2][:20], batches[3][20:])).contiguous()     # shares 20 nodes with batch 2
+    batches[4] = batches[3].flip(0).contiguous()                                # same nodes as batch 3
+    table = torch.stack(batches)
+    width = step.outs[0].shape[1]
+    outs = torch.empty((len(batches), B, width), dtype=torch.float32).pin_memory() if host_io else None
+    step.run_native(table.cpu() if host_io else table, out_host=outs)
+    torch.cuda.synchronize()
+    for i, ids in enumerate(batches):
+        oh, om, dx, s = oracle_step(o, mode, deg, ids.cpu().numpy(), fh, hist, D, d_out, graphsage=gs)
+        if host_io:
+            close(outs[i].numpy(), oh, "native batch %d out" % i)
+    z = step.sizes()
+    assert z["n_in"] == len(s["field"]) and z["nnz_s"] == len(s["edg_s"])
+    close(step.out.cpu().numpy(), oh, "native last out")
+    if om is not None:
+        close(step.out_mu.cpu().numpy(), om, "native last out_mu")
+    close(step.dx.cpu().numpy()[:z["n_in"]], dx, "native last dx")
+    if mode != "ns":
+        assert np.array_equal(step.history.cpu().numpy(), hist)
+    assert np.array_equal(step.sampler.host("adj_i", step.sampler.num_edges), o.vec("adj_i"))
+    # a second native run, then a plain eager pass, continue the same sequence
+    step.run_native(batches[:2])
+    step.run(batches[5])
+    torch.cuda.synchronize()
+    for ids in batches[:2] + [batches[5]]:
+        oh, om, dx, s = oracle_step(o, mode, deg, ids.cpu().numpy(), fh, hist, D, d_out, graphsage=gs)
+    close(step.out.cpu().numpy(), oh, "eager pass after native runs")
+    if mode != "ns":
+        assert np.array_equal(step.history.cpu().numpy(), hist)
