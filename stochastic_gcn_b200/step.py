@@ -98,7 +98,13 @@ class HotPathStep:
         s.set_slot(slot)
         s.start_batch(self.ids2[slot] if ids is None else ids)
         s.expand(self.degree, materialize_full=False)
+        return self._ensure_views(slot)
+
+    def _ensure_views(self, slot):
+        """zero-copy views of the sampler's buffer set `slot` (the addresses never change once reserved)"""
         if self._views[slot] is None:
+            s = self.sampler
+            s.set_slot(slot)
             names = ("field", "rowptr_s", "rowptr_f", "edg_t", "tgt", "edg_w", "scales", "meta")
             v = {k: s.view(k) for k in names}
             v["adj_p"], v["adj_i"], v["adj_w"] = s.view("adj_p"), s.view("adj_i"), s.view("adj_w")
@@ -132,7 +138,7 @@ class HotPathStep:
         outs[slot] must already be zero.  zero_next: also zero outs[1-slot] (for the next step) at the
         end of the side branch.  after(side_stream): optional extra work enqueued on the side branch
         once the aggregate is complete (e.g. the D2H copy of the step's result)."""
-        v = self._views[slot]
+        v = self._ensure_views(slot)
         pipelined = self._pipeline_on        # the sampler's device guard counts consumer passes
         H, B = self.hidden, self.B
         cv = self.mode != "ns"
@@ -504,7 +510,7 @@ class HotPathStep:
         one batch), CUDA events around the train of launches; returns the average per launch and the
         algorithmic bytes of exactly those launches."""
         dev, B, H = self.dev, self.B, self.hidden
-        v = self._views[0]
+        v = self._ensure_views(0)
         deg = (v["adj_p"][1:] - v["adj_p"][:-1])
         scratch = torch.zeros_like(self.outs[0])
         total_bytes, calls = 0, []
@@ -545,7 +551,7 @@ class HotPathStep:
 
     def sizes(self):
         """(n_out, n_in, nnz_s, nnz_f) of the last pass (synchronises)."""
-        m = self._views[self._last_slot]["meta"].cpu().tolist()
+        m = self._ensure_views(self._last_slot)["meta"].cpu().tolist()
         if m[5]:
             raise _lib.SgcnError(_lib.SGCN_EDATA, "sampler status %d" % m[5])
         return {"n_out": m[0], "n_in": m[1], "nnz_s": m[2], "nnz_f": m[3]}
