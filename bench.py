@@ -423,7 +423,7 @@ def run_ours(args, w):
             "e2e": {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s",
                     "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(pinned[0].numel() * 4),
-                    "d2h_bytes_per_step": int(out_host.numel() * 4)},
+                    "d2h_bytes_per_step": int(w["batch"] * step.out.shape[1] * 4)},
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "launches_per_step": float(launches_per_step),
             "clocks": clock_info}

@@ -120,13 +120,14 @@ int sgcn_sampler_vec(sgcn_sampler* s, int32_t level, int32_t which, void** ptr /
 /* copy the first `count` elements (4 bytes each) of a vector to HOST memory (synchronises) */
 int sgcn_sampler_copy_vec(sgcn_sampler* s, int32_t level, int32_t which, void* dst /*HOST*/,
                           int64_t count);
-/* Cross-step pipelining.  The sampler keeps two sets of per-batch buffers; set_slot selects the set
- * that start_batch / expand / sizes / vec address, so batch i+1 can be sampled (on another stream)
- * while the kernels of batch i still read the other set.  With pipeline enabled, an expand whose
- * batch shares a node with the previous slot's batch first waits (on the device, bounded) until
- * every earlier consumer pass has called sgcn_sampler_mark_consumed -- the in-place row permutation
- * must not race the full-neighbour reads of the previous batch.  Disjoint batches never wait. */
-int sgcn_sampler_set_slot(sgcn_sampler* s, int32_t slot /*0|1*/);
+/* Cross-step pipelining.  The sampler keeps three sets of per-batch buffers; set_slot selects the set
+ * that start_batch / expand / sizes / vec address, so batches i+1 and i+2 can be sampled (on another
+ * stream) while the kernels of batch i still read their own set.  With pipeline enabled, an expand
+ * whose batch shares a node with a batch held by another set first waits (on the device, bounded)
+ * until every earlier consumer pass has been marked finished (sgcn_sampler_mark_consumed, or the
+ * done_counter of sgcn_history_update / sgcn_wb_wait_apply) -- the in-place row permutation must
+ * not race the full-neighbour reads of an earlier batch.  Disjoint batches never wait. */
+int sgcn_sampler_set_slot(sgcn_sampler* s, int32_t slot /*0|1|2*/);
 int sgcn_sampler_pipeline(sgcn_sampler* s, int32_t enable);
 int sgcn_sampler_mark_consumed(sgcn_sampler* s, void* stream);
 /* the stream expand() runs on (cudaStream_t as void*); set to share the caller's stream */

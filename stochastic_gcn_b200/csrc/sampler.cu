@@ -92,7 +92,8 @@ struct sgcn_sampler {
         int cur = 0;                          // number of expands since start_batch
         std::vector<Level> levels;
     };
-    Slot slots[2];
+    static constexpr int kSlots = 3;      // lookahead of up to two batches
+    Slot slots[kSlots];
     int cur_slot = 0;
     Slot& sl() { return slots[cur_slot]; }
     DevBuf batch_meta;
@@ -544,7 +545,8 @@ struct FusedArgs {
     const int32_t* field_in; const int32_t* n_ptr; int n_host, nb, sb;
     const int32_t* adj_p; int32_t* adj_i; float* adj_w; int N, degree, cv;
     int hbits;               // log2 of the shared-memory hash table size (>= 2 (nb + sb) entries)
-    const int32_t* prev_ids; int prev_n;   // pipelining: the batch whose consumer pass may still run
+    const int32_t* prev_ids; int prev_n;   // pipelining: the batches whose consumer passes may still run
+    const int32_t* prev_ids2; int prev_n2;
     int32_t* pipe;                         // {expands finished, consumer passes finished} or NULL
     unsigned long long* trace;
     uint32_t* engine;
@@ -702,6 +704,8 @@ expand_fused_kernel(const FusedArgs a) {
         const int seq = a.pipe[0];
         for (int j = tid; j < a.prev_n; j += NT)
             if (hash_has(s_keys, hmask, hshift, a.prev_ids[j])) s_conflict = 1;
+        for (int j = tid; j < a.prev_n2; j += NT)
+            if (hash_has(s_keys, hmask, hshift, a.prev_ids2[j])) s_conflict = 1;
         __syncthreads();
         if (s_conflict && tid == 0) {
             volatile int32_t* done = (volatile int32_t*)(a.pipe + 1);
@@ -960,12 +964,15 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
             attr_set = true;
         }
         const int hbits = fused_hash_bits(nb, (int)sb);
-        const sgcn_sampler::Slot& other = s->slots[1 - s->cur_slot];
+        const sgcn_sampler::Slot& other = s->slots[(s->cur_slot + 2) % sgcn_sampler::kSlots];
+        const sgcn_sampler::Slot& other2 = s->slots[(s->cur_slot + 1) % sgcn_sampler::kSlots];
         const bool piped = s->pipeline && s->sl().cur == 0;
         FusedArgs fa{field_in, n_ptr, nb, nb, (int)sb, s->adj_p, s->adj_i, s->adj_w, s->N, degree,
                      s->cv ? 1 : 0, hbits,
                      piped && other.batch_n > 0 ? other.batch_src : nullptr,
                      piped && other.batch_n > 0 ? other.batch_n : 0,
+                     piped && other2.batch_n > 0 ? other2.batch_src : nullptr,
+                     piped && other2.batch_n > 0 ? other2.batch_n : 0,
                      piped ? s->pipe_counters : nullptr, g_trace,
                      s->engine, lv.field.as<int32_t>(), lv.rowptr_s.as<int32_t>(),
                      lv.rowptr_f.as<int32_t>(), lv.edg_s.as<int32_t>(), lv.edg_t.as<int32_t>(),
@@ -1295,7 +1302,7 @@ int sgcn_sampler_seed(sgcn_sampler* s, int32_t seed) {
 }
 
 int sgcn_sampler_set_slot(sgcn_sampler* s, int32_t slot) {
-    SGCN_REQUIRE(s && (slot == 0 || slot == 1), "sampler_set_slot: slot must be 0 or 1");
+    SGCN_REQUIRE(s && slot >= 0 && slot < sgcn_sampler::kSlots, "sampler_set_slot: slot must be 0, 1 or 2");
     s->cur_slot = slot;
     return SGCN_OK;
 }
@@ -1468,7 +1475,7 @@ int sgcn_sampler_vec(sgcn_sampler* s, int32_t level, int32_t which, void** ptr, 
 }
 
 int sgcn_sampler_slot_vec(sgcn_sampler* s, int32_t slot, int32_t which, void** ptr) {
-    SGCN_REQUIRE(s && ptr && (slot == 0 || slot == 1), "sampler_slot_vec: bad argument");
+    SGCN_REQUIRE(s && ptr && slot >= 0 && slot < sgcn_sampler::kSlots, "sampler_slot_vec: bad argument");
     *ptr = nullptr;
     auto& sl = s->slots[slot];
     if (sl.levels.empty()) {

@@ -1,5 +1,5 @@
 // Native step driver: n consecutive passes of the hot path issued from C++ onto three CUDA streams,
-// with the sampler of batch k+1 running beside the aggregate of batch k.
+// with the samplers of batches k+1 / k+2 running beside the aggregate of batch k.
 //
 // Why not only CUDA graphs: on this driver a graph launch expands its nodes on the device at ~1.8 us
 // per kernel node, branch by branch, AFTER the previous launch on the stream has finished
@@ -9,7 +9,7 @@
 //
 //   chain : [wait sampler k] full_mean(k) ─► [wait fwd k] history_update(k) ─► ...
 //   side  : [wait sampler k, rest k-1] dX init + zero(out k+1) ─► gather(k) ─► (publish) ─► fwd+bwd(k) ─► D2H(k)
-//   samp  : [wait rest k-1] (H2D ids k+1) ─► expand(k+1) into the other buffer set
+//   samp  : [wait rest k-1] (H2D ids k+2) ─► expand(k+2) into the buffer set pass k-1 used
 //
 // Semantics are exactly those of n sequential passes (same sampler order and RNG stream, every
 // forward read of history before the write-back, write-back k before any read of pass k+1); the
@@ -22,9 +22,10 @@ struct sgcn_step {
     sgcn_sampler* sampler = nullptr;
     sgcn_step_desc d{};
     cudaStream_t chain = nullptr, side = nullptr, samp = nullptr;
-    int32_t* ids_dev[2] = {nullptr, nullptr};      // staging of host ids
-    // level-0 buffers of the sampler's two slots
-    struct Lv { int32_t *field, *rowptr_s, *rowptr_f, *edg_t, *tgt, *meta; float *edg_w, *scales; } lv[2]{};
+    static constexpr int kSlots = 3;               // sampler buffer sets: two batches of lookahead
+    int32_t* ids_dev[kSlots] = {nullptr, nullptr, nullptr};      // staging of host ids
+    // level-0 buffers of the sampler's slots
+    struct Lv { int32_t *field, *rowptr_s, *rowptr_f, *edg_t, *tgt, *meta; float *edg_w, *scales; } lv[kSlots]{};
     const int32_t* adj_p = nullptr; const int32_t* adj_i = nullptr; const float* adj_w = nullptr;
     int32_t* pipe = nullptr;
     static constexpr int kRing = 4;
@@ -67,7 +68,7 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
         return rc;
     };
     // both buffer sets of the sampler, sized once; their level-0 pointers never move afterwards
-    for (int slot = 0; slot < 2; ++slot) {
+    for (int slot = 0; slot < sgcn_step::kSlots; ++slot) {
         int rc = sgcn_sampler_set_slot(sampler, slot);
         if (rc == SGCN_OK) rc = sgcn_sampler_reserve(sampler, d.batch, &d.degree, 1, 0);
         void* p = nullptr;
@@ -100,7 +101,7 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
     CK(cudaStreamCreateWithFlags(&st->chain, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&st->samp, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&st->ids_dev[i], sizeof(int32_t) * (size_t)d.batch));
+    for (int i = 0; i < sgcn_step::kSlots; ++i) CK(cudaMalloc(&st->ids_dev[i], sizeof(int32_t) * (size_t)d.batch));
     for (int i = 0; i < sgcn_step::kRing; ++i) {
         CK(cudaEventCreateWithFlags(&st->ev_samp[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st->ev_full[i], cudaEventDisableTiming));
@@ -120,7 +121,7 @@ void sgcn_step_destroy(sgcn_step* st) {
     if (!st) return;
     for (cudaStream_t s : {st->chain, st->side, st->samp})
         if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
-    for (int i = 0; i < 2; ++i) cudaFree(st->ids_dev[i]);
+    for (int i = 0; i < sgcn_step::kSlots; ++i) cudaFree(st->ids_dev[i]);
     for (int i = 0; i < sgcn_step::kRing; ++i)
         for (cudaEvent_t e : {st->ev_samp[i], st->ev_full[i], st->ev_fwd[i], st->ev_rest[i]})
             if (e) cudaEventDestroy(e);
@@ -146,8 +147,9 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
     SGCN_CUDA(cudaEventRecord(st->ev_begin, user));
     for (cudaStream_t s : {chain, side, samp}) SGCN_CUDA(cudaStreamWaitEvent(s, st->ev_begin, 0));
 
-    auto sample = [&](int k) -> int {         // sampler of batch k into slot k&1, on the samp stream
-        const int slot = k & 1;
+    constexpr int NS = sgcn_step::kSlots;
+    auto sample = [&](int k) -> int {         // sampler of batch k into buffer set k % 3, on the samp stream
+        const int slot = k % NS;
         const int32_t* src = ids + (int64_t)k * B;
         if (ids_on_host) {
             SGCN_CUDA(cudaMemcpyAsync(st->ids_dev[slot], src, sizeof(int32_t) * (size_t)B,
@@ -162,6 +164,11 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
     };
 
     STEP_TRY(sgcn_sampler_set_stream_async(smp, samp));
+    // forget the batches of earlier runs: the device guard must not chase ids buffers that are gone
+    for (int slot = 0; slot < sgcn_step::kSlots; ++slot) {
+        STEP_TRY(sgcn_sampler_set_slot(smp, slot));
+        STEP_TRY(sgcn_sampler_start_batch_device(smp, 0, nullptr));
+    }
     // outputs of pass 0 start from zero (later passes: zeroed one step ahead on the side stream)
     if (cv) {
         STEP_TRY(sgcn_copy_rows_pad_pair(nullptr, 0, 0, nullptr, B, H, nb(d.out[0]), d.ld_out, nullptr, 0, 0, nullptr,
@@ -170,10 +177,11 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
         SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_zero0, 0));     // pass 0's sampled part adds into it too
     }
     STEP_TRY(sample(0));
+    if (n > 1) STEP_TRY(sample(1));
 
     for (int k = 0; k < n; ++k) {
-        const int r = k & 1, s = 1 - r;
-        const sgcn_step::Lv& v = st->lv[r];
+        const int r = k & 1, s = 1 - r;                      // output buffers alternate
+        const sgcn_step::Lv& v = st->lv[k % NS];             // sampler buffer sets rotate over three
         const int32_t* n_out_dev = v.meta + 0;
         const int32_t* n_in_dev = v.meta + 1;
         float* out_r = d.out[r];
@@ -188,10 +196,11 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
         }
         SGCN_CUDA(cudaEventRecord(st->ev_full[k % R], chain));
 
-        // ---- samp: sampler of batch k+1 into the other buffer set (free once pass k-1 has finished) ----
-        if (k + 1 < n) {
+        // ---- samp: sampler of batch k+2 into the buffer set pass k-1 used (free once it has finished):
+        //      two batches of lookahead keep the sampler's latency off the chain entirely ----
+        if (k + 2 < n) {
             if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(samp, st->ev_rest[(k - 1) % R], 0));
-            STEP_TRY(sample(k + 1));
+            STEP_TRY(sample(k + 2));
         }
 
         // ---- side: dX init + next output zeroing, gather, (publish), sampled aggregate + backward ----

@@ -51,7 +51,7 @@ class HotPathStep:
         self.n_nodes = graph.n
         self.sampler = DeviceSampler(graph.data, graph.indices, graph.indptr, L=1, cv=mode != "ns")
         self.sampler.seed(seed)
-        for slot in (0, 1):                          # both per-batch buffer sets, sized once
+        for slot in (0, 1, 2):                       # every per-batch buffer set, sized once
             self.sampler.set_slot(slot)
             self.sampler.reserve(self.B, [self.degree])
         self.sampler.set_slot(0)
@@ -73,7 +73,8 @@ class HotPathStep:
         self.graph = None
         self.graph_host = None
         self.launches_per_step = None
-        self._views = [None, None]
+        self._views = [None, None, None]
+        self._last_sampler_slot = None      # set by the native driver (its sampler sets rotate over three)
         self._pinned_out = None
         self._pipe = None           # graphs of the cross-step pipelined driver
         self._pipeline_on = False
@@ -223,7 +224,7 @@ class HotPathStep:
             self.sampler.use_stream(main)
         self._zero_out(0)
         self._sample(0)
-        self._last_slot = 0
+        self._last_slot, self._last_sampler_slot = 0, None
         self._rest(0, main)
 
     # -- drivers ---------------------------------------------------------------------------------
@@ -250,7 +251,7 @@ class HotPathStep:
 
     def replay(self, ids):
         self.ids.copy_(ids, non_blocking=True)
-        self._last_slot = 0
+        self._last_slot, self._last_sampler_slot = 0, None
         self.graph.replay()
         return self.out
 
@@ -276,7 +277,7 @@ class HotPathStep:
         """End-to-end call with HOST buffers: int32 ids in (host memory), aggregated rows out (pinned
         host memory).  Per call: a 2 KB host copy into the staging buffer, one graph launch (H2D +
         pass + D2H), one stream synchronise."""
-        self._last_slot = 0
+        self._last_slot, self._last_sampler_slot = 0, None
         if self.graph_host is not None:
             self._pin_ids.copy_(ids_pinned)
             self.graph_host.replay()
@@ -393,7 +394,7 @@ class HotPathStep:
         if sample:
             self._zero_out(slot)
             self._sample(slot, self.ids2[slot])
-        self._last_slot = slot
+        self._last_slot, self._last_sampler_slot = slot, None
         self._rest(slot, main, zero_next=True)
 
     def run_pipelined(self, batches, on_chunk=None):
@@ -424,7 +425,7 @@ class HotPathStep:
             for k, ids in enumerate(ahead):
                 dst[k].copy_(ids, non_blocking=not host_io)
             pipe["closed" if closed else "open"][par].replay()
-            self._last_slot = (S - 1) & 1
+            self._last_slot, self._last_sampler_slot = (S - 1) & 1, None
             ev = torch.cuda.Event()
             ev.record()
             pipe.setdefault("done", [None, None])[par] = ev
@@ -499,7 +500,8 @@ class HotPathStep:
         self._native_keep = (table, out_host)          # borrowed by the driver until the run completes
         _lib.check(lib.sgcn_step_run(self._native_h, _lib.ptr(table), int(on_host), n,
                                      _lib.ptr(out_host) if out_host is not None else None, _lib.stream_ptr()))
-        self._last_slot = (n - 1) & 1
+        self._last_slot = (n - 1) & 1                  # output buffers alternate ...
+        self._last_sampler_slot = (n - 1) % 3          # ... sampler buffer sets rotate over three
         self.sampler._stream = None                    # the driver left the sampler on its own stream
         return self.out
 
@@ -551,7 +553,8 @@ class HotPathStep:
 
     def sizes(self):
         """(n_out, n_in, nnz_s, nnz_f) of the last pass (synchronises)."""
-        m = self._ensure_views(self._last_slot)["meta"].cpu().tolist()
+        slot = self._last_sampler_slot if self._last_sampler_slot is not None else self._last_slot
+        m = self._ensure_views(slot)["meta"].cpu().tolist()
         if m[5]:
             raise _lib.SgcnError(_lib.SGCN_EDATA, "sampler status %d" % m[5])
         return {"n_out": m[0], "n_in": m[1], "nnz_s": m[2], "nnz_f": m[3]}
