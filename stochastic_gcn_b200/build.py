@@ -64,7 +64,7 @@ def build_library(force=False, verbose=False):
     with open(os.path.join(build_dir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     cmd = [_nvcc(), "-shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-pthread", "-o", LIB] + objs
+           "-o", LIB] + objs
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("link failed:\n" + out.stdout + out.stderr)

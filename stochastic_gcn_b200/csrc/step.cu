@@ -14,10 +14,6 @@
 // Semantics are exactly those of n sequential passes (same sampler order and RNG stream, every
 // forward read of history before the write-back, write-back k before any read of pass k+1); the
 // in-place row permutation is guarded on the device (sgcn_sampler_pipeline).
-#include <atomic>
-#include <mutex>
-#include <string>
-#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -25,7 +21,7 @@
 struct sgcn_step {
     sgcn_sampler* sampler = nullptr;
     sgcn_step_desc d{};
-    cudaStream_t chain = nullptr, side = nullptr, samp = nullptr;
+    cudaStream_t chain = nullptr, side = nullptr, samp = nullptr, copy = nullptr;
     static constexpr int kSlots = 3;               // sampler buffer sets: two batches of lookahead
     int32_t* ids_dev[kSlots] = {nullptr, nullptr, nullptr};      // staging of host ids
     // level-0 buffers of the sampler's slots
@@ -33,7 +29,7 @@ struct sgcn_step {
     const int32_t* adj_p = nullptr; const int32_t* adj_i = nullptr; const float* adj_w = nullptr;
     int32_t* pipe = nullptr;
     static constexpr int kRing = 4;
-    cudaEvent_t ev_samp[kRing]{}, ev_full[kRing]{}, ev_fwd[kRing]{}, ev_rest[kRing]{}, ev_begin = nullptr,
+    cudaEvent_t ev_samp[kRing]{}, ev_full[kRing]{}, ev_fwd[kRing]{}, ev_rest[kRing]{}, ev_d2h[kRing]{}, ev_begin = nullptr,
                 ev_side_end = nullptr, ev_samp_end = nullptr, ev_zero0 = nullptr;
     int device = 0;
 };
@@ -105,12 +101,14 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
     CK(cudaStreamCreateWithFlags(&st->chain, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&st->samp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&st->copy, cudaStreamNonBlocking));
     for (int i = 0; i < sgcn_step::kSlots; ++i) CK(cudaMalloc(&st->ids_dev[i], sizeof(int32_t) * (size_t)d.batch));
     for (int i = 0; i < sgcn_step::kRing; ++i) {
         CK(cudaEventCreateWithFlags(&st->ev_samp[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st->ev_full[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st->ev_fwd[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st->ev_rest[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&st->ev_d2h[i], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&st->ev_begin, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&st->ev_side_end, cudaEventDisableTiming));
@@ -123,11 +121,11 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
 
 void sgcn_step_destroy(sgcn_step* st) {
     if (!st) return;
-    for (cudaStream_t s : {st->chain, st->side, st->samp})
+    for (cudaStream_t s : {st->chain, st->side, st->samp, st->copy})
         if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     for (int i = 0; i < sgcn_step::kSlots; ++i) cudaFree(st->ids_dev[i]);
     for (int i = 0; i < sgcn_step::kRing; ++i)
-        for (cudaEvent_t e : {st->ev_samp[i], st->ev_full[i], st->ev_fwd[i], st->ev_rest[i]})
+        for (cudaEvent_t e : {st->ev_samp[i], st->ev_full[i], st->ev_fwd[i], st->ev_rest[i], st->ev_d2h[i]})
             if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {st->ev_begin, st->ev_side_end, st->ev_samp_end, st->ev_zero0})
         if (e) cudaEventDestroy(e);
@@ -141,17 +139,36 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
     const sgcn_step_desc& d = st->d;
     sgcn_sampler* smp = st->sampler;
     const int B = d.batch, H = d.hidden, R = sgcn_step::kRing;
-    constexpr int NS = sgcn_step::kSlots;
     const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0, multi = d.world > 1 && cv;
     const int width = H * (concat ? 2 : 1);
-    cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp;
-    auto nb = [&](float* base) { return base + (concat ? H : 0); };   // neighbour half of an output row
+    cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp,
+                 copy = st->copy;
+
+    // the neighbour half of out[slot] (and of out_mu[slot]); the self half when concatenating
+    auto nb = [&](float* base) { return base + (concat ? H : 0); };
 
     SGCN_CUDA(cudaEventRecord(st->ev_begin, user));
-    for (cudaStream_t s : {chain, side, samp}) SGCN_CUDA(cudaStreamWaitEvent(s, st->ev_begin, 0));
+    for (cudaStream_t s : {chain, side, samp, copy}) SGCN_CUDA(cudaStreamWaitEvent(s, st->ev_begin, 0));
+
+    constexpr int NS = sgcn_step::kSlots;
+    auto sample = [&](int k) -> int {         // sampler of batch k into buffer set k % 3, on the samp stream
+        const int slot = k % NS;
+        const int32_t* src = ids + (int64_t)k * B;
+        if (ids_on_host) {
+            SGCN_CUDA(cudaMemcpyAsync(st->ids_dev[slot], src, sizeof(int32_t) * (size_t)B,
+                                      cudaMemcpyHostToDevice, samp));
+            src = st->ids_dev[slot];
+        }
+        STEP_TRY(sgcn_sampler_set_slot(smp, slot));
+        STEP_TRY(sgcn_sampler_start_batch_device(smp, B, src));
+        STEP_TRY(sgcn_sampler_expand(smp, d.degree, 0));
+        SGCN_CUDA(cudaEventRecord(st->ev_samp[k % R], samp));
+        return SGCN_OK;
+    };
+
     STEP_TRY(sgcn_sampler_set_stream_async(smp, samp));
     // forget the batches of earlier runs: the device guard must not chase ids buffers that are gone
-    for (int slot = 0; slot < NS; ++slot) {
+    for (int slot = 0; slot < sgcn_step::kSlots; ++slot) {
         STEP_TRY(sgcn_sampler_set_slot(smp, slot));
         STEP_TRY(sgcn_sampler_start_batch_device(smp, 0, nullptr));
     }
@@ -162,182 +179,109 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
         SGCN_CUDA(cudaEventRecord(st->ev_zero0, chain));
         SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_zero0, 0));     // pass 0's sampled part adds into it too
     }
+    STEP_TRY(sample(0));
+    if (n > 1) STEP_TRY(sample(1));
 
-    // One host thread per stream: a pass needs ~20 driver calls (~25 us of CPU), more than the
-    // ~25 us the GPU needs -- issued from one thread the launches arrive late and the streams
-    // starve.  A cudaStreamWaitEvent must be CALLED after the cudaEventRecord it refers to, so the
-    // threads publish how many passes of each event they have recorded (rec_*) and a waiter spins on
-    // that counter first.  Events live in rings of 4; the data dependencies themselves keep any
-    // thread from lapping a ring slot that still has an un-issued wait (see the comments below).
-    struct Shared {
-        std::atomic<int> rec_samp{0}, rec_full{0}, rec_fwd{0}, rec_rest{0};
-        std::atomic<int> failed{0};
-        std::mutex mu;
-        std::string msg;
-        int rc = SGCN_OK;
-    } sh;
-    auto fail = [&](int rc) {
-        std::lock_guard<std::mutex> lock(sh.mu);
-        if (sh.rc == SGCN_OK) {
-            sh.rc = rc;
-            sh.msg = sgcn_last_error();
-        }
-        sh.failed.store(1);
-    };
-    auto wait_rec = [&](std::atomic<int>& a, int need) {
-        while (a.load(std::memory_order_acquire) < need) {
-            if (sh.failed.load(std::memory_order_relaxed)) return false;
-#if defined(__x86_64__)
-            __builtin_ia32_pause();
-#endif
-        }
-        return true;
-    };
-#define T_TRY(expr)                                 \
-    do {                                            \
-        int rc__ = (expr);                          \
-        if (rc__ != SGCN_OK) { fail(rc__); return; } \
-    } while (0)
-#define T_CUDA(call)                                                                            \
-    do {                                                                                        \
-        cudaError_t e__ = (call);                                                               \
-        if (e__ != cudaSuccess) { fail(cuda_fail(e__, #call, __FILE__, __LINE__)); return; }     \
-    } while (0)
+    for (int k = 0; k < n; ++k) {
+        const int r = k & 1, s = 1 - r;                      // output buffers alternate
+        const sgcn_step::Lv& v = st->lv[k % NS];             // sampler buffer sets rotate over three
+        const int32_t* n_out_dev = v.meta + 0;
+        const int32_t* n_in_dev = v.meta + 1;
+        float* out_r = d.out[r];
+        float* outmu_r = d.out_mu[r];
 
-    // ---- samp thread: (H2D ids) + expand of every batch, up to two batches ahead of the chain ----
-    auto samp_thread = [&]() {
-        if (cudaSetDevice(st->device) != cudaSuccess) { fail(SGCN_ECUDA); return; }
-        for (int j = 0; j < n; ++j) {
-            const int slot = j % NS;
-            if (j >= NS) {     // buffer set `slot` was last read by pass j-3
-                if (!wait_rec(sh.rec_rest, j - NS + 1)) return;
-                T_CUDA(cudaStreamWaitEvent(samp, st->ev_rest[(j - NS) % R], 0));
-            }
-            const int32_t* src = ids + (int64_t)j * B;
-            if (ids_on_host) {
-                T_CUDA(cudaMemcpyAsync(st->ids_dev[slot], src, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, samp));
-                src = st->ids_dev[slot];
-            }
-            T_TRY(sgcn_sampler_set_slot(smp, slot));
-            T_TRY(sgcn_sampler_start_batch_device(smp, B, src));
-            T_TRY(sgcn_sampler_expand(smp, d.degree, 0));
-            T_CUDA(cudaEventRecord(st->ev_samp[j % R], samp));
-            sh.rec_samp.store(j + 1, std::memory_order_release);
+        // ---- chain: the full-neighbour history mean of pass k ----
+        SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_samp[k % R], 0));
+        if (cv) {
+            STEP_TRY(sgcn_full_history_mean(v.field, v.rowptr_f, B, n_out_dev, st->adj_p, st->adj_i, st->adj_w,
+                                            d.history, d.ld_hist, H, cvd ? nb(outmu_r) : nb(out_r), d.ld_out,
+                                            cvd ? nb(out_r) : nullptr, d.ld_out, nullptr, chain));
         }
-        T_CUDA(cudaEventRecord(st->ev_samp_end, samp));
-    };
+        if (out_host) SGCN_CUDA(cudaEventRecord(st->ev_full[k % R], chain));
 
-    // ---- side thread: dX init + next output zeroing, gather, (publish), sampled aggregate + backward, D2H ----
-    auto side_thread = [&]() {
-        if (cudaSetDevice(st->device) != cudaSuccess) { fail(SGCN_ECUDA); return; }
-        for (int k = 0; k < n; ++k) {
-            const int r = k & 1, s = 1 - r;
-            const sgcn_step::Lv& v = st->lv[k % NS];
-            const int32_t* n_out_dev = v.meta + 0;
-            const int32_t* n_in_dev = v.meta + 1;
-            float* out_r = d.out[r];
-            float* outmu_r = d.out_mu[r];
-            if (!wait_rec(sh.rec_samp, k + 1)) return;
-            T_CUDA(cudaStreamWaitEvent(side, st->ev_samp[k % R], 0));
-            if (k >= 1) {      // x0, dx and out[s] are free once pass k-1 has written back
-                if (!wait_rec(sh.rec_rest, k)) return;
-                T_CUDA(cudaStreamWaitEvent(side, st->ev_rest[(k - 1) % R], 0));
-            }
-            const bool zero_next = cv && k + 1 < n;
-            T_TRY(sgcn_copy_rows_pad_pair(concat ? d.d_out : nullptr, d.ld_dout, concat ? B : 0,
-                                          concat ? n_out_dev : nullptr, d.x0_rows, H, d.dx, d.ld_dx,
-                                          nullptr, 0, 0, nullptr, zero_next ? B : 0, H,
-                                          zero_next ? nb(d.out[s]) : nullptr, d.ld_out, side));
-            if (zero_next && cvd)
-                T_TRY(sgcn_copy_rows_pad(nullptr, 0, 0, nullptr, B, H, nb(d.out_mu[s]), d.ld_out, side));
-            T_TRY(sgcn_gather_rows(d.features, d.ld_feat, v.field, d.x0_rows, n_in_dev, d.feat_dim, d.x0, d.ld_x0, side));
-            const float* x = d.x0;
-            const float* mu = d.x0 + H;
-            const float* new_hist = cvd ? mu : x;
-            const float* d_nb = d.d_out + (concat ? H : 0);
-            if (multi)
-                T_TRY(sgcn_wb_push(v.field, n_in_dev, d.wb_bound, new_hist, d.ld_x0, H, d.dst_even, d.dst_odd,
-                                   d.world, d.peer_flags, d.rank, d.epoch, d.block_counter, side));
-            if (d.mode == 0) {
-                T_TRY(sgcn_spmm_csr(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, x, d.ld_x0, H, nb(out_r),
-                                    d.ld_out, 0, side));
-                if (concat) T_TRY(sgcn_copy_rows_pad(x, d.ld_x0, B, n_out_dev, B, H, out_r, d.ld_out, side));
-                T_TRY(sgcn_spmm_csr_bwd(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, d_nb, d.ld_dout, H, d.dx,
-                                        d.ld_dx, side));
-            } else if (!cvd) {
-                T_TRY(sgcn_cv_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, B, n_out_dev, x, d.ld_x0, d.history,
-                                              d.ld_hist, H, nb(out_r), d.ld_out, concat ? out_r : nullptr, d.ld_out, 1,
-                                              d_nb, d.ld_dout, d.dx, d.ld_dx, side));
-            } else {
-                T_TRY(sgcn_cvd_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, v.scales, B, n_out_dev, x, d.ld_x0,
-                                               mu, d.ld_x0, d.history, d.ld_hist, H, nb(out_r), d.ld_out,
-                                               nb(outmu_r), d.ld_out, concat ? out_r : nullptr, d.ld_out,
-                                               concat ? outmu_r : nullptr, d.ld_out, 1, d_nb, d.ld_dout, d.dx,
-                                               d.ld_dx, side));
-            }
-            T_CUDA(cudaEventRecord(st->ev_fwd[k % R], side));
-            sh.rec_fwd.store(k + 1, std::memory_order_release);
-            if (out_host) {    // the pass's aggregated rows to pinned host memory, once the chain's part is in
-                if (!wait_rec(sh.rec_full, k + 1)) return;
-                T_CUDA(cudaStreamWaitEvent(side, st->ev_full[k % R], 0));
-                T_CUDA(cudaMemcpy2DAsync(out_host + (int64_t)k * B * width, sizeof(float) * (size_t)width, out_r,
-                                         sizeof(float) * (size_t)d.ld_out, sizeof(float) * (size_t)width, (size_t)B,
-                                         cudaMemcpyDeviceToHost, side));
-            }
+        // ---- samp: sampler of batch k+2 into the buffer set pass k-1 used (free once it has finished):
+        //      two batches of lookahead keep the sampler's latency off the chain entirely ----
+        if (k + 2 < n) {
+            if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(samp, st->ev_rest[(k - 1) % R], 0));
+            STEP_TRY(sample(k + 2));
         }
-        T_CUDA(cudaEventRecord(st->ev_side_end, side));
-    };
 
-    // ---- chain (this thread): full-neighbour history mean, then the write-back ----
-    auto chain_thread = [&]() {
-        for (int k = 0; k < n; ++k) {
-            const int r = k & 1;
-            const sgcn_step::Lv& v = st->lv[k % NS];
-            const int32_t* n_out_dev = v.meta + 0;
-            const int32_t* n_in_dev = v.meta + 1;
-            float* out_r = d.out[r];
-            float* outmu_r = d.out_mu[r];
-            const float* new_hist = cvd ? d.x0 + H : d.x0;
-            if (!wait_rec(sh.rec_samp, k + 1)) return;
-            T_CUDA(cudaStreamWaitEvent(chain, st->ev_samp[k % R], 0));
-            if (cv)
-                T_TRY(sgcn_full_history_mean(v.field, v.rowptr_f, B, n_out_dev, st->adj_p, st->adj_i, st->adj_w,
-                                             d.history, d.ld_hist, H, cvd ? nb(outmu_r) : nb(out_r), d.ld_out,
-                                             cvd ? nb(out_r) : nullptr, d.ld_out, nullptr, chain));
-            if (out_host) {
-                T_CUDA(cudaEventRecord(st->ev_full[k % R], chain));
-                sh.rec_full.store(k + 1, std::memory_order_release);
-            }
-            // write-back after every forward read of history (gcn/models.py:186-194)
-            if (!wait_rec(sh.rec_fwd, k + 1)) return;
-            T_CUDA(cudaStreamWaitEvent(chain, st->ev_fwd[k % R], 0));
-            if (!cv) {
-                T_TRY(sgcn_sampler_mark_consumed(smp, chain));
-            } else if (multi) {
-                T_TRY(sgcn_wb_wait_apply(d.history, d.ld_hist, H, d.recv_even, d.recv_odd, d.slot_bytes, d.world,
-                                         d.wb_bound, d.owner, d.flags, d.epoch, d.timeout_flag, st->pipe + 1, chain));
-            } else {
-                T_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
-                                          st->pipe + 1, chain));
-            }
-            T_CUDA(cudaEventRecord(st->ev_rest[k % R], chain));
-            sh.rec_rest.store(k + 1, std::memory_order_release);
+        // ---- side: dX init + next output zeroing, gather, (publish), sampled aggregate + backward ----
+        SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_samp[k % R], 0));
+        if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_rest[(k - 1) % R], 0));   // x0 / out[s] are free
+        const bool zero_next = cv && k + 1 < n;
+        // with host output the other buffer is still being copied out (pass k-1): zero it later, below
+        const bool zero_early = zero_next && !out_host;
+        STEP_TRY(sgcn_copy_rows_pad_pair(concat ? d.d_out : nullptr, d.ld_dout, concat ? B : 0,
+                                         concat ? n_out_dev : nullptr, d.x0_rows, H, d.dx, d.ld_dx,
+                                         nullptr, 0, 0, nullptr, zero_early ? B : 0, H,
+                                         zero_early ? nb(d.out[s]) : nullptr, d.ld_out, side));
+        if (zero_early && cvd)
+            STEP_TRY(sgcn_copy_rows_pad(nullptr, 0, 0, nullptr, B, H, nb(d.out_mu[s]), d.ld_out, side));
+        STEP_TRY(sgcn_gather_rows(d.features, d.ld_feat, v.field, d.x0_rows, n_in_dev, d.feat_dim, d.x0, d.ld_x0, side));
+        const float* x = d.x0;
+        const float* mu = d.x0 + H;
+        const float* new_hist = cvd ? mu : x;
+        const float* d_nb = d.d_out + (concat ? H : 0);
+        if (multi)
+            STEP_TRY(sgcn_wb_push(v.field, n_in_dev, d.wb_bound, new_hist, d.ld_x0, H, d.dst_even, d.dst_odd,
+                                  d.world, d.peer_flags, d.rank, d.epoch, d.block_counter, side));
+        if (d.mode == 0) {
+            STEP_TRY(sgcn_spmm_csr(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, x, d.ld_x0, H, nb(out_r),
+                                   d.ld_out, 0, side));
+            if (concat)
+                STEP_TRY(sgcn_copy_rows_pad(x, d.ld_x0, B, n_out_dev, B, H, out_r, d.ld_out, side));
+            STEP_TRY(sgcn_spmm_csr_bwd(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, d_nb, d.ld_dout, H, d.dx,
+                                       d.ld_dx, side));
+        } else if (!cvd) {
+            STEP_TRY(sgcn_cv_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, B, n_out_dev, x, d.ld_x0, d.history,
+                                             d.ld_hist, H, nb(out_r), d.ld_out, concat ? out_r : nullptr, d.ld_out, 1,
+                                             d_nb, d.ld_dout, d.dx, d.ld_dx, side));
+        } else {
+            STEP_TRY(sgcn_cvd_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, v.scales, B, n_out_dev, x, d.ld_x0,
+                                              mu, d.ld_x0, d.history, d.ld_hist, H, nb(out_r), d.ld_out,
+                                              nb(outmu_r), d.ld_out, concat ? out_r : nullptr, d.ld_out,
+                                              concat ? outmu_r : nullptr, d.ld_out, 1, d_nb, d.ld_dout, d.dx,
+                                              d.ld_dx, side));
         }
-    };
-#undef T_TRY
-#undef T_CUDA
+        if (zero_next && !zero_early) {
+            // out[s] held pass k-1's rows: zero it for pass k+1 once their D2H copy has finished
+            if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_d2h[(k - 1) % R], 0));
+            STEP_TRY(sgcn_copy_rows_pad_pair(nullptr, 0, 0, nullptr, B, H, nb(d.out[s]), d.ld_out, nullptr, 0, 0,
+                                             nullptr, cvd ? B : 0, H, cvd ? nb(d.out_mu[s]) : nullptr, d.ld_out,
+                                             side));
+        }
+        SGCN_CUDA(cudaEventRecord(st->ev_fwd[k % R], side));
 
-    std::thread t_samp(samp_thread), t_side(side_thread);
-    chain_thread();
-    t_samp.join();
-    t_side.join();
-    if (sh.rc != SGCN_OK) {
-        set_error(sh.msg);
-        return sh.rc;
+        // ---- chain: write-back after every forward read of history (gcn/models.py:186-194) ----
+        SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_fwd[k % R], 0));
+        if (!cv) {
+            STEP_TRY(sgcn_sampler_mark_consumed(smp, chain));
+        } else if (multi) {
+            STEP_TRY(sgcn_wb_wait_apply(d.history, d.ld_hist, H, d.recv_even, d.recv_odd, d.slot_bytes, d.world,
+                                        d.wb_bound, d.owner, d.flags, d.epoch, d.timeout_flag, st->pipe + 1, chain));
+        } else {
+            STEP_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
+                                         st->pipe + 1, chain));
+        }
+        SGCN_CUDA(cudaEventRecord(st->ev_rest[k % R], chain));
+
+        // ---- copy stream: the pass's aggregated rows to pinned host memory (both aggregate kernels done) ----
+        if (out_host) {
+            SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_full[k % R], 0));
+            SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_fwd[k % R], 0));
+            SGCN_CUDA(cudaMemcpy2DAsync(out_host + (int64_t)k * B * width, sizeof(float) * (size_t)width, out_r,
+                                        sizeof(float) * (size_t)d.ld_out, sizeof(float) * (size_t)width, (size_t)B,
+                                        cudaMemcpyDeviceToHost, copy));
+            SGCN_CUDA(cudaEventRecord(st->ev_d2h[k % R], copy));
+        }
     }
+    SGCN_CUDA(cudaEventRecord(st->ev_side_end, side));
+    SGCN_CUDA(cudaEventRecord(st->ev_samp_end, samp));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_rest[(n - 1) % R], 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));
+    if (out_host) SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_d2h[(n - 1) % R], 0));
     return SGCN_OK;
 }
 
