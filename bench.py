@@ -471,8 +471,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="time one graph per step, no sampler lookahead")
     ap.add_argument("--steps-per-graph", type=int, default=8)
-    ap.add_argument("--driver", default="native", choices=["native", "graph"],
-                    help="pipelined schedule: native C++ stream launches (default) or multi-step CUDA graphs")
+    ap.add_argument("--driver", default="graph", choices=["native", "graph"],
+                    help="pipelined schedule: multi-step CUDA graphs (default) or native C++ stream launches")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU write-back exchange: NVLink peer stores (default) or NCCL all-gather")
     args = ap.parse_args()

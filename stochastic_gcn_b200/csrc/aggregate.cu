@@ -246,7 +246,7 @@ spmm_coo_kernel(const int2* __restrict__ idx2, const float* __restrict__ vals, i
 //           path; partial sums stay in registers across the span and leave through one 128-bit RED
 //           per lane per row segment.
 constexpr int kFullStageRows = 4096;   // row pointers are staged in shared memory up to this many rows
-constexpr int kFullMacro = 128;        // positions staged per warp per macro-chunk
+constexpr int kFullMacro = 64;         // positions staged per warp per macro-chunk
 constexpr int kFullWarps = kAggThreads / 32;
 
 struct FullArgs {
@@ -305,12 +305,9 @@ full_mean_kernel(const FullArgs a) {
     // static schedule: one contiguous span per warp.  dynamic schedule (a.work): warps pull
     // 64-position chunks from a device counter, which keeps every SM busy when some SMs are held
     // by a concurrently running kernel (the next batch's sampler in the pipelined step)
-    // 32-position chunks dealt out evenly: warp w gets q or q+1 consecutive chunks (a plain
-    // round-up of nnz / #warps to a multiple of 32 leaves up to a fifth of the warps without work)
-    const int chunks = (nnz + 31) >> 5;
-    const int q = chunks / warps, rem = chunks - q * warps;
-    int p0 = (warp * q + min(warp, rem)) << 5;
-    int p1 = min(p0 + ((q + (warp < rem ? 1 : 0)) << 5), nnz);
+    const int span = max(32, (((nnz + warps - 1) / warps) + 31) & ~31);
+    int p0 = warp * span;
+    int p1 = min(p0 + span, nnz);
     if (a.work) {
         int c = 0;
         if (lane == 0) c = atomicAdd(a.work, 1);
