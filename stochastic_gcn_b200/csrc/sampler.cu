@@ -18,6 +18,8 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "mt19937.cuh"
 #include "scan.cuh"
@@ -155,15 +157,28 @@ __global__ void fill_float_kernel(float* p, int64_t n, float v) {
         p[i] = v;
 }
 
-// importance[c] = 1e-6 + sum_r w_rc^2 accumulated in CSR order (scheduler.cpp:22-25).  fp32 sums
-// are order dependent, so one thread walks the matrix: constructor-time only, importance branch only.
-__global__ void importance_kernel(const float* __restrict__ adj_w, const int32_t* __restrict__ adj_i,
-                                  int E, float* __restrict__ imp) {
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        for (int e = 0; e < E; ++e) {
-            const float w = adj_w[e];
-            imp[adj_i[e]] += __fmul_rn(w, w);
-        }
+// importance[c] = 1e-6 + sum_r w_rc^2 accumulated in CSR order (scheduler.cpp:22-25).  fp32 sums are
+// order dependent, so the entries are first grouped by column WITHOUT changing their relative order
+// (stable radix sort of (column, w^2) pairs) and each column is then summed front to back by one
+// thread: the per-column order is exactly the reference's, the columns run in parallel.
+__global__ void square_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __fmul_rn(w[i], w[i]);
+}
+
+__global__ void importance_columns_kernel(const int32_t* __restrict__ cols_sorted,
+                                          const float* __restrict__ sq_sorted, int E, int N,
+                                          float* __restrict__ imp) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    int lo = 0, hi = E;                       // first entry with column >= c
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cols_sorted[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    float acc = (float)1e-6;
+    for (int e = lo; e < E && cols_sorted[e] == c; ++e) acc = __fadd_rn(acc, sq_sorted[e]);
+    imp[c] = acc;
 }
 
 // ---- pass 1: per-row degree / sample count / scale; old field becomes the prefix -----------------
@@ -1225,8 +1240,32 @@ static int create_common(sgcn_sampler** out, const float* adj_w, const int32_t* 
             s->importance, num_data, s->is ? (float)1e-6 : 1.0f);
         g_launches.fetch_add(1);
         if (s->is) {
-            importance_kernel<<<1, 32, 0, s->stream>>>(s->adj_w, s->adj_i, num_edges, s->importance);
-            g_launches.fetch_add(1);
+            if (num_edges > 0) {
+                DevBuf sq, keys_out, vals_out, tmp;
+                int irc = sq.ensure(sizeof(float) * ne);
+                if (irc == SGCN_OK) irc = keys_out.ensure(sizeof(int32_t) * ne);
+                if (irc == SGCN_OK) irc = vals_out.ensure(sizeof(float) * ne);
+                if (irc != SGCN_OK) return fail(irc);
+                square_kernel<<<std::min(div_up(num_edges, 256), kNumSMs * 8), 256, 0, s->stream>>>(
+                    s->adj_w, num_edges, sq.as<float>());
+                g_launches.fetch_add(1);
+                size_t tmp_bytes = 0;
+                int bits = 1;
+                while ((1ll << bits) < (long long)std::max(num_data, 2)) ++bits;
+                CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, s->adj_i, keys_out.as<int32_t>(),
+                                                   sq.as<float>(), vals_out.as<float>(), num_edges, 0, bits,
+                                                   s->stream));
+                irc = tmp.ensure(std::max<size_t>(tmp_bytes, 16));
+                if (irc != SGCN_OK) return fail(irc);
+                CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, s->adj_i, keys_out.as<int32_t>(),
+                                                   sq.as<float>(), vals_out.as<float>(), num_edges, 0, bits,
+                                                   s->stream));
+                importance_columns_kernel<<<div_up(num_data, 256), 256, 0, s->stream>>>(
+                    keys_out.as<int32_t>(), vals_out.as<float>(), num_edges, num_data, s->importance);
+                g_launches.fetch_add(1);
+                CK(cudaStreamSynchronize(s->stream));
+                sq.release(); keys_out.release(); vals_out.release(); tmp.release();
+            }
             rc = s->hits.ensure(sizeof(int32_t) * nn);
             if (rc != SGCN_OK) return fail(rc);
             CK(cudaMemsetAsync(s->hits.p, 0, sizeof(int32_t) * nn, s->stream));
