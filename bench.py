@@ -35,6 +35,23 @@ WORKLOADS = {
 METRIC = "aggregated edges/s (sampled + full-neighbour edges through SpMM fwd+bwd per step)"
 
 
+def load_traffic(kernel_name):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/rNN_*_ncu.json: dram__bytes_read.sum + dram__bytes_write.sum, averaged over the captured
+    launches); None when no capture of that kernel is committed."""
+    import glob
+    best = None
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu.json"))):
+        try:
+            with open(p) as f:
+                d = json.load(f)
+        except (OSError, ValueError):
+            continue
+        if kernel_name.split("<")[0].split(" ")[0] in d.get("kernel", "") and d.get("traffic_bytes_per_launch"):
+            best = {"bytes": float(d["traffic_bytes_per_launch"]), "source": os.path.relpath(p, ROOT)}
+    return best
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -55,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -428,9 +445,11 @@ def run_ours(args, w):
             "launches_per_step": float(launches_per_step),
             "clocks": clock_info}
     if kern is not None:
+        traffic = load_traffic(kern["kernel"])
         line["roofline"] = {"bound": "hbm", "kernel": kern["kernel"], "achieved": kern["bytes"] / kern["sec"] / 1e9,
                             "peak": peak, "unit": "GB/s", "frac": kern["bytes"] / kern["sec"] / 1e9 / peak,
-                            "traffic": kern.get("traffic"), "peak_source": peak_src,
+                            "traffic": traffic["bytes"] if traffic else None,
+                            "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
                             "us_per_launch": kern["sec"] * 1e6, "algorithmic_bytes_per_launch": kern["bytes"],
                             "how": kern["how"]}
     if world == 1 and not args.no_cpu:
@@ -461,7 +480,7 @@ def main():
     os.dup2(2, 1)            # NCCL prints its version banner on fd 1: keep stdout for the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=5000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="reddit_cv", choices=sorted(WORKLOADS))

@@ -53,12 +53,44 @@ template <> struct VT<float> {
 
 constexpr int kAggThreads = 256;
 
-enum { MODE_PLAIN = 0, MODE_CV = 1, MODE_CVD = 2 };
+enum { MODE_PLAIN = 0, MODE_CV = 1, MODE_CVD = 2, MODE_DET = 3 };
+
+template <typename V> __device__ __forceinline__ V vsqrt(V a);
+template <> __device__ __forceinline__ float vsqrt<float>(float a) { return sqrtf(a); }
+template <> __device__ __forceinline__ float4 vsqrt<float4>(float4 a) {
+    return make_float4(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z), sqrtf(a.w));
+}
+template <typename V> __device__ __forceinline__ V vmulv(V a, V b);
+template <> __device__ __forceinline__ float vmulv<float>(float a, float b) { return a * b; }
+template <> __device__ __forceinline__ float4 vmulv<float4>(float4 a, float4 b) {
+    return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+// relu(a) + 1e-10 (gcn/layers.py:341) ; gate(g, pre) = pre > 0 ? g : 0 (ReluGrad)
+template <typename V> __device__ __forceinline__ V vrelu_eps(V a);
+template <> __device__ __forceinline__ float vrelu_eps<float>(float a) { return fmaxf(a, 0.f) + 1e-10f; }
+template <> __device__ __forceinline__ float4 vrelu_eps<float4>(float4 a) {
+    return make_float4(fmaxf(a.x, 0.f) + 1e-10f, fmaxf(a.y, 0.f) + 1e-10f, fmaxf(a.z, 0.f) + 1e-10f,
+                       fmaxf(a.w, 0.f) + 1e-10f);
+}
+template <typename V> __device__ __forceinline__ V vgate(V g, V pre);
+template <> __device__ __forceinline__ float vgate<float>(float g, float pre) { return pre > 0.f ? g : 0.f; }
+template <> __device__ __forceinline__ float4 vgate<float4>(float4 g, float4 p) {
+    return make_float4(p.x > 0.f ? g.x : 0.f, p.y > 0.f ? g.y : 0.f, p.z > 0.f ? g.z : 0.f,
+                       p.w > 0.f ? g.w : 0.f);
+}
+template <typename V> __device__ __forceinline__ V vdivv(V a, V b);
+template <> __device__ __forceinline__ float vdivv<float>(float a, float b) { return a / b; }
+template <> __device__ __forceinline__ float4 vdivv<float4>(float4 a, float4 b) {
+    return make_float4(a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w);
+}
 
 struct SampledArgs {
     const int32_t* rowptr; const int32_t* cols; const float* vals;
-    const int32_t* map;      // PLAIN: optional row map of x;  CV/CVD: tgt (global ids into hist)
+    const int32_t* map;      // PLAIN: optional row map of x;  CV/CVD/DET: tgt (global ids into hist)
     const float* scale;      // CVD
+    const float* vals2;      // DET: madj weights (medg_w of the sampler, gcn/scheduler.cpp:164)
+    int square;              // PLAIN: use vals^2 (tf.square(adj), gcn/layers.py:242)
+    float* pre; int64_t ld_pre;   // DET: optional pre-relu values (the backward's gate)
     int n_out; const int32_t* n_out_dev;
     const float* x; int64_t ld_x;      // PLAIN/CV: x ; CVD: h
     const float* mu; int64_t ld_mu;    // CVD
@@ -98,8 +130,9 @@ sampled_rows_kernel(const SampledArgs a) {
 #pragma unroll 2
         for (int e = e0; e < e1; ++e) {
             const int c = __ldg(a.cols + e);
-            const float w = __ldg(a.vals + e);
+            float w = __ldg(a.vals + e);
             if (MODE == MODE_PLAIN) {
+                if (a.square) w *= w;
                 const int64_t src = a.map ? (int64_t)__ldg(a.map + c) : (int64_t)c;
 #pragma unroll
                 for (int k = 0; k < VPL; ++k)
@@ -113,6 +146,12 @@ sampled_rows_kernel(const SampledArgs a) {
                     if (MODE == MODE_CV) {
                         const V xv = T::ld(a.x + (int64_t)c * a.ld_x + off[k]);
                         T::fma(acc[k], w, T::sub(xv, hv));
+                    } else if (MODE == MODE_DET) {
+                        // adj^2 @ dsigma^2 + 2 madj @ (dsigma * sigma_bar)   (gcn/layers.py:331-339)
+                        const V sb = vsqrt<V>(hv);
+                        const V ds = T::sub(vsqrt<V>(T::ld(a.x + (int64_t)c * a.ld_x + off[k])), sb);
+                        T::fma(acc[k], w * w, vmulv<V>(ds, ds));
+                        T::fma(acc[k], 2.f * __ldg(a.vals2 + e), vmulv<V>(ds, sb));
                     } else {
                         const V hh = T::ld(a.x + (int64_t)c * a.ld_x + off[k]);
                         const V mv = T::ld(a.mu + (int64_t)c * a.ld_mu + off[k]);
@@ -130,6 +169,15 @@ sampled_rows_kernel(const SampledArgs a) {
                 float* yp = a.y + (int64_t)r * a.ld_y + off[k];
                 if (a.accumulate) acc[k] = T::add(acc[k], *(const V*)yp);
                 T::st(yp, acc[k]);
+            } else if (MODE == MODE_DET) {
+                // y holds fadj^2 @ var_history[ffield] already (accumulate) ; the row's owner finishes:
+                // var_neighbour = relu(sum) + 1e-10   (gcn/layers.py:341)
+                float* yp = a.y + (int64_t)r * a.ld_y + off[k];
+                if (a.accumulate) acc[k] = T::add(acc[k], *(const V*)yp);
+                if (a.pre) T::st(a.pre + (int64_t)r * a.ld_pre + off[k], acc[k]);
+                T::st(yp, vrelu_eps<V>(acc[k]));
+                if (a.self0) T::st(a.self0 + (int64_t)r * a.ld_s0 + off[k],
+                                   T::ld(a.x + (int64_t)r * a.ld_x + off[k]));
             } else if (MODE == MODE_CV) {
                 if (a.accumulate) T::red(a.y + (int64_t)r * a.ld_y + off[k], acc[k]);
                 else T::st(a.y + (int64_t)r * a.ld_y + off[k], acc[k]);
@@ -174,6 +222,7 @@ struct BwdArgs {
     int n_out; const int32_t* n_out_dev;
     const float* dy; int64_t ld_dy; int D; float* dx; int64_t ld_dx;
     unsigned long long* trace;
+    int square;              // use vals^2 (backward of tf.square(adj) @ var)
 };
 
 template <typename V, int LPR, int VPL>
@@ -196,11 +245,59 @@ spmm_bwd_kernel(const BwdArgs a) {
         }
         for (int e = e0; e < e1; ++e) {
             const int64_t c = __ldg(a.cols + e);
-            const float w = __ldg(a.vals + e);
+            float w = __ldg(a.vals + e);
+            if (a.square) w *= w;
 #pragma unroll
             for (int k = 0; k < VPL; ++k) {
                 const int off = (gl + k * LPR) * T::W;
                 if (off < a.D) T::red(a.dx + c * a.ld_dx + off, T::mul(g[k], w));
+            }
+        }
+    }
+}
+
+// ---- det-dropout variance backward (gcn/layers.py:331-341 under TF autodiff) --------------------
+// var_nb = relu(pre) + 1e-10, pre = sum_e w^2 ds_c^2 + 2 mw ds_c sb_c + (history term), with
+// ds_c = sqrt(var[c]) - sb_c, sb_c = sqrt(var_history[tgt]).  d var[c] += gate(dy[r], pre[r]) *
+// (w^2 ds_c + mw sb_c) / sqrt(var[c])    (= (2 w^2 ds + 2 mw sb) * 0.5 / sigma)
+struct DetBwdArgs {
+    const int32_t* rowptr; const int32_t* cols; const float* vals; const float* vals2;
+    const int32_t* tgt; int n_out; const int32_t* n_out_dev;
+    const float* var; int64_t ld_v; const float* hvar; int64_t ld_h; int D;
+    const float* dy; int64_t ld_dy; const float* pre; int64_t ld_pre; float* dvar; int64_t ld_dv;
+};
+
+template <typename V, int LPR, int VPL>
+__global__ void __launch_bounds__(kAggThreads)
+det_var_bwd_kernel(const DetBwdArgs a) {
+    using T = VT<V>;
+    const int n_out = dev_count(a.n_out_dev, a.n_out);
+    const int gl = threadIdx.x % LPR;
+    const int groups = (gridDim.x * kAggThreads) / LPR;
+    for (int r = (blockIdx.x * kAggThreads + threadIdx.x) / LPR; r < n_out; r += groups) {
+        const int e0 = a.rowptr[r], e1 = a.rowptr[r + 1];
+        if (e0 == e1) continue;
+        V g[VPL];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const int off = (gl + k * LPR) * T::W;
+            g[k] = off < a.D ? vgate<V>(T::ld(a.dy + (int64_t)r * a.ld_dy + off),
+                                        T::ld(a.pre + (int64_t)r * a.ld_pre + off)) : T::zero();
+        }
+        for (int e = e0; e < e1; ++e) {
+            const int64_t c = __ldg(a.cols + e);
+            const int64_t t = __ldg(a.tgt + e);
+            const float w = __ldg(a.vals + e);
+            const float mw = __ldg(a.vals2 + e);
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                const int off = (gl + k * LPR) * T::W;
+                if (off >= a.D) continue;
+                const V sg = vsqrt<V>(T::ld(a.var + c * a.ld_v + off));
+                const V sb = vsqrt<V>(T::ld_stream(a.hvar + t * a.ld_h + off));
+                V coef = T::mul(T::sub(sg, sb), w * w);
+                T::fma(coef, mw, sb);
+                T::red(a.dvar + c * a.ld_dv + off, vmulv<V>(g[k], vdivv<V>(coef, sg)));
             }
         }
     }
@@ -257,6 +354,7 @@ struct FullArgs {
     int32_t* work;   // optional: device counter (0 on entry) for dynamic 64-position chunk scheduling
     int stage_rows;  // row pointers of up to this many output rows are staged in shared memory
     unsigned long long* trace;
+    int square;      // use adj_w^2 (tf.square(fadj) @ var_history, gcn/layers.py:338)
 };
 
 template <typename V, int LPR, int VPL>
@@ -358,6 +456,7 @@ full_mean_kernel(const FullArgs a) {
                                      : (__ldg(a.adj_p + __ldg(a.nodes + lo)) + (p - ptr[lo]));
                 off = (int64_t)__ldg(a.adj_i + q) * a.ld_h;
                 w = __ldg(a.adj_w + q);
+                if (a.square) w *= w;
             }
             my_off[t * 32 + lane] = off;
             my_w[t * 32 + lane] = w;
