@@ -224,6 +224,47 @@ int sgcn_cvd_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float
                          float* self_h, int64_t ld_sh, float* self_mu, int64_t ld_sm,
                          int32_t accumulate, void* stream);
 
+/* ---- det-dropout (mu, var) aggregation: PlainAggregator tuple branch layers.py:238-247 and
+ * VRAggregator tuple branch layers.py:320-349 ------------------------------
+ * The mean stream reuses sgcn_spmm_csr / sgcn_cv_sampled_fwd with the mean history.  The variance
+ * stream needs the element-wise squared adjacencies tf.square(adj), tf.square(fadj): the *_sq entry
+ * points are the same kernels with vals[e]^2 in place of vals[e] (arguments as the plain versions). */
+int sgcn_spmm_csr_sq(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                     const int32_t* map, int32_t n_out, const int32_t* n_out_dev, const float* x,
+                     int64_t ld_x, int32_t D, float* y, int64_t ld_y, int32_t accumulate,
+                     void* stream);
+int sgcn_spmm_csr_bwd_sq(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                         const float* rscale, int32_t n_out, const int32_t* n_out_dev,
+                         const float* dy, int64_t ld_dy, int32_t D, float* dx, int64_t ld_dx,
+                         void* stream);
+int sgcn_full_history_mean_sq(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
+                              const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
+                              const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
+                              float* y0, int64_t ld_y0, float* y1, int64_t ld_y1,
+                              int32_t* work_counter, void* stream);
+
+/* VRAggregator det-dropout branch, variance stream, sampled part + finish (layers.py:331-341):
+ *   ds = sqrt(var[cols[e]]) - sqrt(hvar[tgt[e]]),  sb = sqrt(hvar[tgt[e]])
+ *   pre[r,:] = (accumulate ? y[r,:] : 0) + sum_e vals[e]^2 ds^2 + 2 mvals[e] ds sb
+ *   y[r,:]   = relu(pre[r,:]) + 1e-10 ;  self != NULL: self[r,:] = var[r,:]
+ * Run sgcn_full_history_mean_sq(hvar) into a zeroed y FIRST, then this with accumulate=1 (each
+ * output row is finished by its owner, no atomics).  pre (optional) keeps the pre-relu values, the
+ * gate of the backward.  mvals = the sampler's medg_w (madj, _scheduler.pyx:116). */
+int sgcn_det_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                         const float* mvals, const int32_t* tgt, int32_t n_out,
+                         const int32_t* n_out_dev, const float* var, int64_t ld_v,
+                         const float* hvar, int64_t ld_h, int32_t D, float* y, int64_t ld_y,
+                         float* pre, int64_t ld_pre, float* self, int64_t ld_self,
+                         int32_t accumulate, void* stream);
+/* its gradient w.r.t. var (TF autodiff of the lines above; var_history is not trainable):
+ *   dvar[cols[e],:] += (pre[r,:] > 0 ? dy[r,:] : 0) * (vals[e]^2 ds + mvals[e] sb) / sqrt(var[cols[e],:])
+ * dvar is initialised by the caller (zeros, or the gradient of the self half). */
+int sgcn_det_sampled_bwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                         const float* mvals, const int32_t* tgt, int32_t n_out,
+                         const int32_t* n_out_dev, const float* var, int64_t ld_v,
+                         const float* hvar, int64_t ld_h, int32_t D, const float* dy, int64_t ld_dy,
+                         const float* pre, int64_t ld_pre, float* dvar, int64_t ld_dv, void* stream);
+
 /* tf.scatter_update(history, fields[l], new_history)  models.py:160-166:
  *   hist[idx[i], :] = rows[i, :]   (idx distinct) */
 int sgcn_history_update(float* hist, int64_t ld_h, const int32_t* idx, int32_t n,

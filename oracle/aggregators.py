@@ -114,6 +114,70 @@ def cvd_backward_h(adj, scale, d_h_out, n_in, graphsage, dtype=np.float64):
     return dx
 
 
+def _sq(adj):
+    """tf.square(SparseTensor): element-wise square of the stored values (gcn/layers.py:242,337,338)."""
+    return (adj[0], np.asarray(adj[1], np.float64) ** 2, adj[2])
+
+
+def plain_forward_det(adj, mu, var, graphsage, dtype=np.float64):
+    """PlainAggregator._call, (mu, var) branch, gcn/layers.py:238-247."""
+    n_out = int(adj[2][0])
+    mu_nb = _coo_matmul(adj, mu, dtype)
+    var_nb = _coo_matmul(_sq(adj), var, np.float64).astype(dtype)
+    if graphsage:
+        return (np.concatenate((mu[:n_out].astype(dtype), mu_nb), axis=1),
+                np.concatenate((var[:n_out].astype(dtype), var_nb), axis=1))
+    return mu_nb, var_nb
+
+
+def det_forward(adj, fadj, madj, ifield, ffield, mu_history, var_history, mu, var, graphsage):
+    """VRAggregator._call, det-dropout branch (inputs a tuple, cvd False), gcn/layers.py:320-349, float64.
+
+    Returns ((mu_out, var_out), new_history=(mu, var), pre) where pre is the value under the relu."""
+    n_out = int(adj[2][0])
+    f8 = np.float64
+    mu, var = mu.astype(f8), var.astype(f8)
+    delta_mu = mu - mu_history[ifield].astype(f8)
+    mu_bar = mu_history[ffield].astype(f8)
+    sigma = np.sqrt(var)
+    sigma_bar = np.sqrt(var_history[ifield].astype(f8))
+    delta_sigma = sigma - sigma_bar
+    var_bar = var_history[ffield].astype(f8)
+    msigma = delta_sigma * sigma_bar
+    mu_nb = _coo_matmul(adj, delta_mu, f8) + _coo_matmul(fadj, mu_bar, f8)
+    pre = (_coo_matmul(_sq(adj), delta_sigma ** 2, f8) + _coo_matmul(_sq(fadj), var_bar, f8)
+           + 2 * _coo_matmul(madj, msigma, f8))
+    var_nb = np.maximum(pre, 0.0) + 1e-10
+    if graphsage:
+        out = (np.concatenate((mu[:n_out], mu_nb), axis=1), np.concatenate((var[:n_out], var_nb), axis=1))
+    else:
+        out = (mu_nb, var_nb)
+    return out, (mu, var), pre
+
+
+def det_backward_var(adj, madj, ifield, var_history, var, pre, d_var_out, graphsage):
+    """d(var) for det_forward under TF autodiff (history is not trainable): with G = d(var_nb) * [pre > 0],
+    d(delta_sigma) = 2 delta_sigma * (adj^2)^T G + 2 sigma_bar * madj^T G,  d(var) = d(delta_sigma) * 0.5 / sigma."""
+    n_out, n_in = int(adj[2][0]), var.shape[0]
+    f8 = np.float64
+    d = d_var_out.astype(f8)
+    if graphsage:
+        dim = d.shape[1] // 2
+        d_self, d_nb = d[:, :dim], d[:, dim:]
+    else:
+        d_self, d_nb = None, d
+    G = d_nb * (pre > 0)
+    sigma = np.sqrt(var.astype(f8))
+    sigma_bar = np.sqrt(var_history[ifield].astype(f8))
+    shape = (n_out, n_in)
+    d_ds = 2 * (sigma - sigma_bar) * _coo_matmul_t((adj[0], _sq(adj)[1], shape), G, f8) \
+        + 2 * sigma_bar * _coo_matmul_t((madj[0], madj[1], shape), G, f8)
+    dv = d_ds * 0.5 / sigma
+    if d_self is not None:
+        dv[:n_out] += d_self
+    return dv
+
+
 def history_update(history, ifield, new_rows):
     """tf.scatter_update(history, fields[l], new_history), gcn/models.py:160-166 (in place)."""
     history[np.asarray(ifield)] = new_rows

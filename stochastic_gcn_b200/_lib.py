@@ -57,6 +57,14 @@ SIGNATURES = {
     "sgcn_spmm_csr_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _vp]),
     "sgcn_full_history_mean": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,
                                       _vp, _i64, _vp, _vp]),
+    "sgcn_spmm_csr_sq": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp]),
+    "sgcn_spmm_csr_bwd_sq": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "sgcn_full_history_mean_sq": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,
+                                         _vp, _i64, _vp, _vp]),
+    "sgcn_det_sampled_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i32,
+                                    _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "sgcn_det_sampled_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i32,
+                                    _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "sgcn_sampler_set_slot": (_i32, [_vp, _i32]),
     "sgcn_sampler_pipeline": (_i32, [_vp, _i32]),
     "sgcn_sampler_mark_consumed": (_i32, [_vp, _vp]),

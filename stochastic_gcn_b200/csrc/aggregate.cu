@@ -572,6 +572,7 @@ static int launch_sampled(SampledArgs a, int D, bool vec_ok, cudaStream_t st) {
         if (a.hist) t.hist = a.hist + c0;
         t.y = a.y + c0;
         if (a.ymu) t.ymu = a.ymu + c0;
+        if (a.pre) t.pre = a.pre + c0;
         if (a.self0) t.self0 = a.self0 + c0;
         if (a.self1) t.self1 = a.self1 + c0;
         if (a.dx) { t.dy = a.dy + c0; t.dx = a.dx + c0; }
@@ -590,10 +591,10 @@ using namespace sgcn;
 
 extern "C" {
 
-int sgcn_spmm_csr(const int32_t* rowptr, const int32_t* cols, const float* vals,
-                  const int32_t* map, int32_t n_out, const int32_t* n_out_dev, const float* x,
-                  int64_t ld_x, int32_t D, float* y, int64_t ld_y, int32_t accumulate,
-                  void* stream) {
+static int spmm_csr_impl(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                         const int32_t* map, int32_t n_out, const int32_t* n_out_dev, const float* x,
+                         int64_t ld_x, int32_t D, float* y, int64_t ld_y, int32_t accumulate,
+                         int square, void* stream) {
     SGCN_REQUIRE(n_out >= 0 && D >= 0, "spmm_csr: negative size");
     if (n_out == 0 || D == 0) return SGCN_OK;
     SGCN_REQUIRE(rowptr && y, "spmm_csr: null pointer");
@@ -601,9 +602,74 @@ int sgcn_spmm_csr(const int32_t* rowptr, const int32_t* cols, const float* vals,
     SampledArgs a{};
     a.rowptr = rowptr; a.cols = cols; a.vals = vals; a.map = map;
     a.n_out = n_out; a.n_out_dev = n_out_dev; a.x = x; a.ld_x = ld_x;
-    a.y = y; a.ld_y = ld_y; a.accumulate = accumulate;
+    a.y = y; a.ld_y = ld_y; a.accumulate = accumulate; a.square = square;
     const bool vec_ok = D % 4 == 0 && ld_x % 4 == 0 && ld_y % 4 == 0 && aligned16(x) && aligned16(y);
     return launch_sampled<MODE_PLAIN>(a, D, vec_ok, (cudaStream_t)stream);
+}
+
+int sgcn_spmm_csr(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                  const int32_t* map, int32_t n_out, const int32_t* n_out_dev, const float* x,
+                  int64_t ld_x, int32_t D, float* y, int64_t ld_y, int32_t accumulate,
+                  void* stream) {
+    return spmm_csr_impl(rowptr, cols, vals, map, n_out, n_out_dev, x, ld_x, D, y, ld_y, accumulate, 0, stream);
+}
+
+int sgcn_spmm_csr_sq(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                     const int32_t* map, int32_t n_out, const int32_t* n_out_dev, const float* x,
+                     int64_t ld_x, int32_t D, float* y, int64_t ld_y, int32_t accumulate,
+                     void* stream) {
+    return spmm_csr_impl(rowptr, cols, vals, map, n_out, n_out_dev, x, ld_x, D, y, ld_y, accumulate, 1, stream);
+}
+
+int sgcn_det_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                         const float* mvals, const int32_t* tgt, int32_t n_out,
+                         const int32_t* n_out_dev, const float* var, int64_t ld_v,
+                         const float* hvar, int64_t ld_h, int32_t D, float* y, int64_t ld_y,
+                         float* pre, int64_t ld_pre, float* self, int64_t ld_self,
+                         int32_t accumulate, void* stream) {
+    SGCN_REQUIRE(n_out >= 0 && D >= 0, "det_sampled_fwd: negative size");
+    if (n_out == 0 || D == 0) return SGCN_OK;
+    SGCN_REQUIRE(rowptr && var && hvar && y, "det_sampled_fwd: null pointer");
+    SGCN_REQUIRE(ld_v >= D && ld_h >= D && ld_y >= D && (!pre || ld_pre >= D) && (!self || ld_self >= D),
+                 "det_sampled_fwd: row stride smaller than width");
+    SampledArgs a{};
+    a.rowptr = rowptr; a.cols = cols; a.vals = vals; a.vals2 = mvals; a.map = tgt;
+    a.n_out = n_out; a.n_out_dev = n_out_dev; a.x = var; a.ld_x = ld_v; a.hist = hvar; a.ld_h = ld_h;
+    a.y = y; a.ld_y = ld_y; a.pre = pre; a.ld_pre = ld_pre; a.self0 = self; a.ld_s0 = ld_self;
+    a.accumulate = accumulate;
+    const bool vec_ok = D % 4 == 0 && ld_v % 4 == 0 && ld_h % 4 == 0 && ld_y % 4 == 0 &&
+                        aligned16(var) && aligned16(hvar) && aligned16(y) &&
+                        (!pre || (ld_pre % 4 == 0 && aligned16(pre))) &&
+                        (!self || (ld_self % 4 == 0 && aligned16(self)));
+    return launch_sampled<MODE_DET>(a, D, vec_ok, (cudaStream_t)stream);
+}
+
+int sgcn_det_sampled_bwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                         const float* mvals, const int32_t* tgt, int32_t n_out,
+                         const int32_t* n_out_dev, const float* var, int64_t ld_v,
+                         const float* hvar, int64_t ld_h, int32_t D, const float* dy, int64_t ld_dy,
+                         const float* pre, int64_t ld_pre, float* dvar, int64_t ld_dv, void* stream) {
+    SGCN_REQUIRE(n_out >= 0 && D >= 0, "det_sampled_bwd: negative size");
+    if (n_out == 0 || D == 0) return SGCN_OK;
+    SGCN_REQUIRE(rowptr && cols && vals && mvals && tgt && var && hvar && dy && pre && dvar,
+                 "det_sampled_bwd: null pointer");
+    SGCN_REQUIRE(ld_v >= D && ld_h >= D && ld_dy >= D && ld_pre >= D && ld_dv >= D,
+                 "det_sampled_bwd: row stride smaller than width");
+    const bool vec_ok = D % 4 == 0 && ld_v % 4 == 0 && ld_h % 4 == 0 && ld_dy % 4 == 0 &&
+                        ld_pre % 4 == 0 && ld_dv % 4 == 0 && aligned16(var) && aligned16(hvar) &&
+                        aligned16(dy) && aligned16(pre) && aligned16(dvar);
+    const Shape sh = pick_shape(D, vec_ok);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int c0 = 0; c0 < D; c0 += sh.tile) {
+        DetBwdArgs a{rowptr, cols, vals, mvals, tgt, n_out, n_out_dev, var + c0, ld_v, hvar + c0, ld_h,
+                     std::min(sh.tile, D - c0), dy + c0, ld_dy, pre + c0, ld_pre, dvar + c0, ld_dv};
+        const int grid = grid_for_groups(n_out, sh.lpr);
+#define CALL(V, L, P) det_var_bwd_kernel<V, L, P><<<grid, kAggThreads, 0, st>>>(a)
+        SGCN_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+        SGCN_LAUNCHED();
+    }
+    return SGCN_OK;
 }
 
 int sgcn_cv_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
@@ -708,10 +774,10 @@ int sgcn_cvd_sampled_fwd_bwd(const int32_t* rowptr, const int32_t* cols, const f
     return launch_sampled<MODE_CVD>(a, D, vec_ok, (cudaStream_t)stream);
 }
 
-int sgcn_spmm_csr_bwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
-                      const float* rscale, int32_t n_out, const int32_t* n_out_dev,
-                      const float* dy, int64_t ld_dy, int32_t D, float* dx, int64_t ld_dx,
-                      void* stream) {
+static int spmm_csr_bwd_impl(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                             const float* rscale, int32_t n_out, const int32_t* n_out_dev,
+                             const float* dy, int64_t ld_dy, int32_t D, float* dx, int64_t ld_dx,
+                             int square, void* stream) {
     SGCN_REQUIRE(n_out >= 0 && D >= 0, "spmm_csr_bwd: negative size");
     if (n_out == 0 || D == 0) return SGCN_OK;
     SGCN_REQUIRE(rowptr && dy && dx, "spmm_csr_bwd: null pointer");
@@ -721,7 +787,7 @@ int sgcn_spmm_csr_bwd(const int32_t* rowptr, const int32_t* cols, const float* v
     cudaStream_t st = (cudaStream_t)stream;
     for (int c0 = 0; c0 < D; c0 += sh.tile) {
         BwdArgs a{rowptr, cols, vals, rscale, n_out, n_out_dev, dy + c0, ld_dy,
-                  std::min(sh.tile, D - c0), dx + c0, ld_dx, g_trace};
+                  std::min(sh.tile, D - c0), dx + c0, ld_dx, g_trace, square};
         const int grid = grid_for_groups(n_out, sh.lpr);
 #define CALL(V, L, P) spmm_bwd_kernel<V, L, P><<<grid, kAggThreads, 0, st>>>(a)
         SGCN_DISPATCH_SHAPE(sh, CALL);
@@ -729,6 +795,20 @@ int sgcn_spmm_csr_bwd(const int32_t* rowptr, const int32_t* cols, const float* v
         SGCN_LAUNCHED();
     }
     return SGCN_OK;
+}
+
+int sgcn_spmm_csr_bwd(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                      const float* rscale, int32_t n_out, const int32_t* n_out_dev,
+                      const float* dy, int64_t ld_dy, int32_t D, float* dx, int64_t ld_dx,
+                      void* stream) {
+    return spmm_csr_bwd_impl(rowptr, cols, vals, rscale, n_out, n_out_dev, dy, ld_dy, D, dx, ld_dx, 0, stream);
+}
+
+int sgcn_spmm_csr_bwd_sq(const int32_t* rowptr, const int32_t* cols, const float* vals,
+                         const float* rscale, int32_t n_out, const int32_t* n_out_dev,
+                         const float* dy, int64_t ld_dy, int32_t D, float* dx, int64_t ld_dx,
+                         void* stream) {
+    return spmm_csr_bwd_impl(rowptr, cols, vals, rscale, n_out, n_out_dev, dy, ld_dy, D, dx, ld_dx, 1, stream);
 }
 
 int sgcn_spmm_coo(const int32_t* idx2, const float* vals, int32_t nnz, const float* x,
@@ -755,11 +835,11 @@ int sgcn_spmm_coo(const int32_t* idx2, const float* vals, int32_t nnz, const flo
     return SGCN_OK;
 }
 
-int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
-                           const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
-                           const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
-                           float* y0, int64_t ld_y0, float* y1, int64_t ld_y1, int32_t* work_counter,
-                           void* stream) {
+static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
+                                  const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
+                                  const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
+                                  float* y0, int64_t ld_y0, float* y1, int64_t ld_y1,
+                                  int32_t* work_counter, int square, void* stream) {
     SGCN_REQUIRE(n_out >= 0 && D >= 0, "full_history_mean: negative size");
     if (n_out == 0 || D == 0) return SGCN_OK;
     SGCN_REQUIRE(nodes && rowptr_f && adj_p && adj_i && adj_w && hist && y0,
@@ -774,7 +854,7 @@ int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist + c0, ld_h,
                    std::min(sh.tile, D - c0), y0 + c0, ld_y0, y1 ? y1 + c0 : nullptr, ld_y1,
                    D <= sh.tile ? work_counter : nullptr,    // one launch per counter reset
-                   std::min(n_out, kFullStageRows), g_trace};
+                   std::min(n_out, kFullStageRows), g_trace, square};
         const size_t dyn = sizeof(int32_t) * (2 * (size_t)a.stage_rows + 2);
         // one resident wave: every CTA the SMs can hold at once, spans cut accordingly
 #define CALL(V, L, P)                                                                        \
@@ -798,6 +878,24 @@ int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_
         SGCN_LAUNCHED();
     }
     return SGCN_OK;
+}
+
+int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
+                           const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
+                           const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
+                           float* y0, int64_t ld_y0, float* y1, int64_t ld_y1, int32_t* work_counter,
+                           void* stream) {
+    return full_history_mean_impl(nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0,
+                                  ld_y0, y1, ld_y1, work_counter, 0, stream);
+}
+
+int sgcn_full_history_mean_sq(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
+                              const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
+                              const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
+                              float* y0, int64_t ld_y0, float* y1, int64_t ld_y1,
+                              int32_t* work_counter, void* stream) {
+    return full_history_mean_impl(nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0,
+                                  ld_y0, y1, ld_y1, work_counter, 1, stream);
 }
 
 }  // extern "C"

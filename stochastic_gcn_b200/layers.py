@@ -89,17 +89,18 @@ class FullNeighbours:
             np.ascontiguousarray(ffield, dtype=np.int32)).to(dev)
         return f
 
-    def add_history_mean(self, n_out, n_out_dev, hist, y0, y1=None):
-        """y0 (+y1) += fadj @ gather(history, ffield)   (gcn/layers.py:305,309,354,357)"""
+    def add_history_mean(self, n_out, n_out_dev, hist, y0, y1=None, square=False):
+        """y0 (+y1) += fadj @ gather(history, ffield)   (gcn/layers.py:305,309,354,357);
+        square: tf.square(fadj) @ gather(var_history, ffield)   (gcn/layers.py:338)"""
         if self.nodes is not None:
             ops.full_history_mean(self.nodes, self.rowptr_f, n_out, self.adj_p, self.adj_i, self.adj_w, hist,
-                                  y0, y1, n_out_dev=n_out_dev)
+                                  y0, y1, n_out_dev=n_out_dev, square=square)
         else:
             ops.spmm_csr(self.rowptr_f, self.cols, self.vals, hist, n_out, out=y0, row_map=self.ffield,
-                         accumulate=True, n_out_dev=n_out_dev)
+                         accumulate=True, n_out_dev=n_out_dev, square=square)
             if y1 is not None:
                 ops.spmm_csr(self.rowptr_f, self.cols, self.vals, hist, n_out, out=y1, row_map=self.ffield,
-                             accumulate=True, n_out_dev=n_out_dev)
+                             accumulate=True, n_out_dev=n_out_dev, square=square)
 
 
 def _split(d_out, dim, concat):
@@ -109,14 +110,21 @@ def _split(d_out, dim, concat):
     return None, d_out
 
 
-def _input_grad(adj, d_self, d_nb, n_rows, dim, rscale=None):
-    """dx = adj^T (d_nb * rscale) (+ d_self on the first n_out rows)  -- the SpMM backward."""
-    dx = torch.empty((n_rows, dim), dtype=torch.float32, device=d_nb.device)
+def _grad_init(adj, d_self, n_rows, dim, device):
+    """dx = [d_self ; 0]: the gradient of the self half of a concat output, zero elsewhere."""
+    dx = torch.empty((n_rows, dim), dtype=torch.float32, device=device)
     if d_self is not None:
         ops.copy_rows_pad(d_self, adj.n_out, dx, n_dev=adj.n_out_dev)
     else:
         ops.copy_rows_pad(None, 0, dx)
-    ops.spmm_csr_bwd(adj.rowptr, adj.cols, adj.vals, d_nb, dx, adj.n_out, rscale=rscale, n_out_dev=adj.n_out_dev)
+    return dx
+
+
+def _input_grad(adj, d_self, d_nb, n_rows, dim, rscale=None, square=False):
+    """dx = adj^T (d_nb * rscale) (+ d_self on the first n_out rows)  -- the SpMM backward."""
+    dx = _grad_init(adj, d_self, n_rows, dim, d_nb.device)
+    ops.spmm_csr_bwd(adj.rowptr, adj.cols, adj.vals, d_nb, dx, adj.n_out, rscale=rscale, n_out_dev=adj.n_out_dev,
+                     square=square)
     return dx
 
 
@@ -192,6 +200,57 @@ class _CVDFn(torch.autograd.Function):
         return grad_h, grad_mu, None, None, None, None, None
 
 
+class _PlainVarFn(torch.autograd.Function):
+    """var stream of PlainAggregator's (mu, var) branch: tf.square(adj) @ var  (gcn/layers.py:238-247)."""
+
+    @staticmethod
+    def forward(ctx, var, adj, concat):
+        dim = var.shape[1]
+        out = torch.empty((adj.n_out, dim * (2 if concat else 1)), dtype=torch.float32, device=var.device)
+        nb = out[:, dim:] if concat else out
+        ops.spmm_csr(adj.rowptr, adj.cols, adj.vals, var, adj.n_out, out=nb, n_out_dev=adj.n_out_dev, square=True)
+        if concat:
+            ops.copy_rows_pad(var, adj.n_out, out[:, :dim], n_dev=adj.n_out_dev)
+        ctx.adj, ctx.concat, ctx.shape = adj, concat, tuple(var.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        d_out = d_out.contiguous()
+        d_self, d_nb = _split(d_out, ctx.shape[1], ctx.concat)
+        return _input_grad(ctx.adj, d_self, d_nb, ctx.shape[0], ctx.shape[1], square=True), None, None
+
+
+class _DetVarFn(torch.autograd.Function):
+    """var stream of VRAggregator's det-dropout branch (gcn/layers.py:331-341):
+    relu(adj^2 @ dsigma^2 + fadj^2 @ var_history[ffield] + 2 madj @ (dsigma * sigma_bar)) + 1e-10."""
+
+    @staticmethod
+    def forward(ctx, var, adj, mvals, full, hvar, concat):
+        dim = var.shape[1]
+        out = torch.empty((adj.n_out, dim * (2 if concat else 1)), dtype=torch.float32, device=var.device)
+        nb = out[:, dim:] if concat else out
+        ops.copy_rows_pad(None, 0, nb)                       # zero: the history term adds with REDs
+        full.add_history_mean(adj.n_out, adj.n_out_dev, hvar, nb, square=True)
+        pre = torch.empty((adj.n_out, dim), dtype=torch.float32, device=var.device)
+        ops.det_sampled_fwd(adj.rowptr, adj.cols, adj.vals, mvals, adj.tgt, adj.n_out, var, hvar, nb, pre=pre,
+                            self_out=out[:, :dim] if concat else None, n_out_dev=adj.n_out_dev, accumulate=True)
+        ctx.adj, ctx.mvals, ctx.hvar, ctx.concat, ctx.shape = adj, mvals, hvar, concat, tuple(var.shape)
+        ctx.save_for_backward(var, pre)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        var, pre = ctx.saved_tensors
+        adj, dim = ctx.adj, ctx.shape[1]
+        d_out = d_out.contiguous()
+        d_self, d_nb = _split(d_out, dim, ctx.concat)
+        dvar = _grad_init(adj, d_self, ctx.shape[0], dim, d_out.device)
+        ops.det_sampled_bwd(adj.rowptr, adj.cols, adj.vals, ctx.mvals, adj.tgt, adj.n_out, var, ctx.hvar, d_nb, pre,
+                            dvar, n_out_dev=adj.n_out_dev)
+        return dvar, None, None, None, None, None
+
+
 class Layer:
     """Call protocol of gcn/layers.py:40-84 (``layer(inputs)`` -> ``_call``), without TF scoping."""
 
@@ -242,18 +301,21 @@ class PlainAggregator(Layer):
         self.adj = adj
 
     def _call(self, inputs):
-        if isinstance(inputs, tuple):
-            raise NotImplementedError("det-dropout (mu, var) aggregation is outside the hot path (SURVEY 8a a14)")
+        if isinstance(inputs, tuple):                      # det-dropout (mu, var), gcn/layers.py:238-247
+            mu, var = inputs
+            return (_PlainFn.apply(mu, self.adj, self._concat), _PlainVarFn.apply(var, self.adj, self._concat))
         return _PlainFn.apply(inputs, self.adj, self._concat)
 
 
 class VRAggregator(Layer):
     """Control-variate aggregator (gcn/layers.py:282-362), CV and CVD branches.
 
-    ``fadj``/``ffield`` are folded into one ``FullNeighbours`` descriptor; ``madj`` is only used by
-    the det-dropout branch and is accepted for signature parity.  ``history`` is a list with one
-    [N, dim] CUDA tensor; ``ifield`` is kept for the write-back (``adj.tgt`` already holds
-    ``ifield[cols]``)."""
+    ``fadj``/``ffield`` are folded into one ``FullNeighbours`` descriptor.  ``madj`` is only used by
+    the det-dropout branch (inputs = ``(mu, var)`` with ``cvd`` False, gcn/layers.py:320-349): the
+    weights of the sampler's ``medg_w`` as a CUDA float32 tensor aligned with ``adj.vals`` (or a
+    ``DeviceAdj`` / reference triple whose values are taken); there ``history`` holds TWO tables
+    (mean, variance).  Otherwise ``history`` is a list with one [N, dim] CUDA tensor.  ``ifield`` is
+    kept for the write-back (``adj.tgt`` already holds ``ifield[cols]``)."""
 
     def __init__(self, adj, fadj, madj, ifield, ffield, history, scale, cvd, **kwargs):
         super().__init__(**kwargs)
@@ -271,11 +333,26 @@ class VRAggregator(Layer):
             out = _CVDFn.apply(h, mu, self.adj, self.fadj, hist, self.scale, self._concat)
             self.new_history = [mu]
             return out
-        if isinstance(inputs, tuple):
-            raise NotImplementedError("det-dropout (mu, var) aggregation is outside the hot path (SURVEY 8a a14)")
+        if isinstance(inputs, tuple):                      # det-dropout, gcn/layers.py:320-349
+            mu, var = inputs
+            mu_hist, var_hist = self.history
+            out_mu = _CVFn.apply(mu, self.adj, self.fadj, mu_hist, self._concat)
+            out_var = _DetVarFn.apply(var, self.adj, self._madj_vals(), self.fadj, var_hist, self._concat)
+            self.new_history = (mu, var)
+            return out_mu, out_var
         out = _CVFn.apply(inputs, self.adj, self.fadj, hist, self._concat)
         self.new_history = [inputs]
         return out
+
+    def _madj_vals(self):
+        m = self.madj
+        if isinstance(m, torch.Tensor):
+            return m
+        if isinstance(m, DeviceAdj):
+            return m.vals
+        if m is None:
+            raise ValueError("the det-dropout branch needs madj (the sampler's medg_w)")
+        return torch.from_numpy(np.ascontiguousarray(m[1], dtype=np.float32)).to(self.adj.vals.device)
 
     def write_back(self, n_in_dev=None):
         """tf.scatter_update(history, fields[l], new_history) after the step (gcn/models.py:160-166,186-194)."""

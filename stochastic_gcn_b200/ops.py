@@ -81,16 +81,18 @@ def csr_slice(a_d, a_i, a_p, r):
     return idx2, val, o_p
 
 
-def spmm_csr(rowptr, cols, vals, x, n_out, out=None, row_map=None, accumulate=False, n_out_dev=None):
-    """out[r] (+)= sum_e vals[e] * x[row_map[cols[e]] or cols[e]]  (gcn/layers.py:31-37, CSR form)."""
+def spmm_csr(rowptr, cols, vals, x, n_out, out=None, row_map=None, accumulate=False, n_out_dev=None,
+             square=False):
+    """out[r] (+)= sum_e vals[e] * x[row_map[cols[e]] or cols[e]]  (gcn/layers.py:31-37, CSR form);
+    square=True uses vals[e]^2 (tf.square(adj), gcn/layers.py:242)."""
     _i32(rowptr, "rowptr"); _f32(x, "x")
     d = x.shape[1]
     if out is None:
         out = torch.empty((n_out, d), dtype=torch.float32, device=x.device)
     _f32(out, "out")
-    check(_lib.load().sgcn_spmm_csr(ptr(rowptr), ptr(cols), ptr(vals), ptr(row_map), n_out, ptr(n_out_dev),
-                                    ptr(x), _ld(x), d, ptr(out), _ld(out), 1 if accumulate else 0,
-                                    stream_ptr()))
+    fn = _lib.load().sgcn_spmm_csr_sq if square else _lib.load().sgcn_spmm_csr
+    check(fn(ptr(rowptr), ptr(cols), ptr(vals), ptr(row_map), n_out, ptr(n_out_dev),
+             ptr(x), _ld(x), d, ptr(out), _ld(out), 1 if accumulate else 0, stream_ptr()))
     return out
 
 
@@ -106,28 +108,30 @@ def spmm_coo(idx2, vals, x, n_rows, transpose=False, out=None):
     return out
 
 
-def spmm_csr_bwd(rowptr, cols, vals, dy, dx, n_out, rscale=None, n_out_dev=None):
-    """dx[cols[e]] += vals[e] * rscale[r] * dy[r]   (gradient of the sampled SpMM)."""
+def spmm_csr_bwd(rowptr, cols, vals, dy, dx, n_out, rscale=None, n_out_dev=None, square=False):
+    """dx[cols[e]] += vals[e] * rscale[r] * dy[r]   (gradient of the sampled SpMM; square: vals[e]^2)."""
     _i32(rowptr, "rowptr"); _f32(dy, "dy"); _f32(dx, "dx")
     d = dy.shape[1]
     if dx.shape[1] != d:
         raise ValueError("dx and dy must have the same width")
-    check(_lib.load().sgcn_spmm_csr_bwd(ptr(rowptr), ptr(cols), ptr(vals), ptr(rscale), n_out, ptr(n_out_dev),
-                                        ptr(dy), _ld(dy), d, ptr(dx), _ld(dx), stream_ptr()))
+    fn = _lib.load().sgcn_spmm_csr_bwd_sq if square else _lib.load().sgcn_spmm_csr_bwd
+    check(fn(ptr(rowptr), ptr(cols), ptr(vals), ptr(rscale), n_out, ptr(n_out_dev),
+             ptr(dy), _ld(dy), d, ptr(dx), _ld(dx), stream_ptr()))
     return dx
 
 
 def full_history_mean(nodes, rowptr_f, n_out, adj_p, adj_i, adj_w, hist, y0, y1=None, n_out_dev=None,
-                      work_counter=None):
-    """y0[r] (+= and y1[r] +=) sum over the stored row of nodes[r] of adj_w * hist[adj_i]."""
+                      work_counter=None, square=False):
+    """y0[r] (+= and y1[r] +=) sum over the stored row of nodes[r] of adj_w * hist[adj_i]
+    (square: adj_w^2, tf.square(fadj) of gcn/layers.py:338)."""
     _i32(nodes, "nodes"); _i32(rowptr_f, "rowptr_f"); _f32(hist, "hist"); _f32(y0, "y0")
     d = hist.shape[1]
     if y0.shape[1] != d or (y1 is not None and y1.shape[1] != d):
         raise ValueError("outputs must have hist's width")
-    check(_lib.load().sgcn_full_history_mean(ptr(nodes), ptr(rowptr_f), n_out, ptr(n_out_dev), ptr(adj_p),
-                                             ptr(adj_i), ptr(adj_w), ptr(hist), _ld(hist), d, ptr(y0), _ld(y0),
-                                             ptr(y1), _ld(y1) if y1 is not None else 0, ptr(work_counter),
-                                             stream_ptr()))
+    fn = _lib.load().sgcn_full_history_mean_sq if square else _lib.load().sgcn_full_history_mean
+    check(fn(ptr(nodes), ptr(rowptr_f), n_out, ptr(n_out_dev), ptr(adj_p),
+             ptr(adj_i), ptr(adj_w), ptr(hist), _ld(hist), d, ptr(y0), _ld(y0),
+             ptr(y1), _ld(y1) if y1 is not None else 0, ptr(work_counter), stream_ptr()))
     return y0
 
 
@@ -153,6 +157,29 @@ def cvd_sampled_fwd(rowptr, cols, vals, tgt, scale, n_out, h, mu, hist, yh, ymu,
         ptr(self_h), _ld(self_h) if self_h is not None else 0,
         ptr(self_mu), _ld(self_mu) if self_mu is not None else 0, 1 if accumulate else 0, stream_ptr()))
     return yh, ymu
+
+
+def det_sampled_fwd(rowptr, cols, vals, mvals, tgt, n_out, var, hvar, y, pre=None, self_out=None, n_out_dev=None,
+                    accumulate=True):
+    """variance stream of the det-dropout VRAggregator (gcn/layers.py:331-341); see
+    include/sgcn_b200.h:sgcn_det_sampled_fwd."""
+    _f32(var, "var"); _f32(hvar, "hvar"); _f32(y, "y"); _f32(vals, "vals", 1); _f32(mvals, "mvals", 1)
+    d = var.shape[1]
+    check(_lib.load().sgcn_det_sampled_fwd(
+        ptr(rowptr), ptr(cols), ptr(vals), ptr(mvals), ptr(tgt), n_out, ptr(n_out_dev), ptr(var), _ld(var),
+        ptr(hvar), _ld(hvar), d, ptr(y), _ld(y), ptr(pre), _ld(pre) if pre is not None else 0,
+        ptr(self_out), _ld(self_out) if self_out is not None else 0, 1 if accumulate else 0, stream_ptr()))
+    return y
+
+
+def det_sampled_bwd(rowptr, cols, vals, mvals, tgt, n_out, var, hvar, dy, pre, dvar, n_out_dev=None):
+    """dvar += gradient of det_sampled_fwd w.r.t. var (dvar pre-initialised)."""
+    _f32(var, "var"); _f32(hvar, "hvar"); _f32(dy, "dy"); _f32(pre, "pre"); _f32(dvar, "dvar")
+    d = var.shape[1]
+    check(_lib.load().sgcn_det_sampled_bwd(
+        ptr(rowptr), ptr(cols), ptr(vals), ptr(mvals), ptr(tgt), n_out, ptr(n_out_dev), ptr(var), _ld(var),
+        ptr(hvar), _ld(hvar), d, ptr(dy), _ld(dy), ptr(pre), _ld(pre), ptr(dvar), _ld(dvar), stream_ptr()))
+    return dvar
 
 
 def copy_rows_pad_pair(src0, n0, out0, src1, n1, out1, n0_dev=None, n1_dev=None):

@@ -150,6 +150,98 @@ def test_cvd_mu_gradient_against_torch_autograd():
     close(ht.grad, hr.grad.numpy(), "dh"); close(mt.grad, mr.grad.numpy(), "dmu")
 
 
+@pytest.mark.parametrize("d", [32, 128, 20, 260])
+@pytest.mark.parametrize("graphsage", [False, True])
+def test_plain_det_dropout_pair(d, graphsage):
+    """PlainAggregator on a (mu, var) pair: adj @ mu and tf.square(adj) @ var (gcn/layers.py:238-247)"""
+    from stochastic_gcn_b200.layers import DeviceAdj, PlainAggregator
+    g = random_graph(400, 12, 300 + d)
+    rng = np.random.RandomState(d)
+    ids = rng.choice(400, size=70, replace=False).astype(np.int32)
+    z, adj, _, _ = sample(g, ids, 3, False)
+    n_in = len(z["field"])
+    mu = rng.randn(n_in, d).astype(np.float32)
+    var = (rng.rand(n_in, d) + 0.05).astype(np.float32)
+    want_mu, want_var = agg.plain_forward_det(adj, mu, var, graphsage)
+    layer = PlainAggregator(DeviceAdj.from_coo(adj), normalization="graphsage" if graphsage else "gcn")
+    mt, vt = dev(mu).requires_grad_(True), dev(var).requires_grad_(True)
+    om, ov = layer((mt, vt))
+    close(om, want_mu, "plain det mu"); close(ov, want_var, "plain det var")
+    gm, gv = rng.randn(*want_mu.shape).astype(np.float32), rng.randn(*want_var.shape).astype(np.float32)
+    ((om * dev(gm)).sum() + (ov * dev(gv)).sum()).backward()
+    close(mt.grad, agg.plain_backward(adj, gm, n_in, graphsage), "plain det dmu")
+    close(vt.grad, agg.plain_backward(agg._sq(adj), gv, n_in, graphsage), "plain det dvar")
+
+
+@pytest.mark.parametrize("d", [32, 128, 20, 260])
+@pytest.mark.parametrize("graphsage", [False, True])
+@pytest.mark.parametrize("in_place", [False, True])
+def test_vr_det_dropout_forward_backward(d, graphsage, in_place):
+    """VRAggregator det-dropout branch (gcn/layers.py:320-349): two histories, madj, relu + 1e-10"""
+    from stochastic_gcn_b200.layers import DeviceAdj, FullNeighbours, VRAggregator
+    g = random_graph(500, 18, 400 + d)
+    rng = np.random.RandomState(d + 1)
+    ids = rng.choice(500, size=80, replace=False).astype(np.int32)
+    z, adj, fadj, s = sample(g, ids, 2, True)
+    n_in = len(z["field"])
+    madj = (adj[0], z["medg_w"], adj[2])
+    mu_hist = rng.randn(500, d).astype(np.float32)
+    var_hist = (rng.rand(500, d) + 0.05).astype(np.float32)
+    mu = (mu_hist[z["field"]] + 0.1 * rng.randn(n_in, d)).astype(np.float32)
+    var = (var_hist[z["field"]] * (0.5 + rng.rand(n_in, d))).astype(np.float32)
+    (want_mu, want_var), _, pre = agg.det_forward(adj, fadj, madj, z["field"], z["ffield"], mu_hist, var_hist,
+                                                  mu, var, graphsage)
+    mh, vh = dev(mu_hist), dev(var_hist)
+    if in_place:
+        rowptr_f = np.concatenate([[0], np.cumsum(np.diff(g.indptr)[ids])]).astype(np.int32)
+        full = FullNeighbours.in_place(dev(ids), dev(rowptr_f), dev(s.vec("adj_p")), dev(s.vec("adj_i")),
+                                       dev(s.vec("adj_w")))
+    else:
+        full = FullNeighbours.from_coo(fadj, z["ffield"])
+    layer = VRAggregator(DeviceAdj.from_coo(adj), full, madj, dev(z["field"]), None, [mh, vh], None, False,
+                         normalization="graphsage" if graphsage else "gcn")
+    mt, vt = dev(mu).requires_grad_(True), dev(var).requires_grad_(True)
+    om, ov = layer((mt, vt))
+    close(om, want_mu, "det mu"); close(ov, want_var, "det var")
+    assert float(ov.min()) >= 1e-10
+    gm, gv = rng.randn(*want_mu.shape).astype(np.float32), rng.randn(*want_var.shape).astype(np.float32)
+    ((om * dev(gm)).sum() + (ov * dev(gv)).sum()).backward()
+    close(mt.grad, agg.plain_backward(adj, gm, n_in, graphsage), "det dmu")
+    close(vt.grad, agg.det_backward_var(adj, madj, z["field"], var_hist, var, pre, gv, graphsage), "det dvar")
+    layer.write_back()
+    assert np.array_equal(mh.cpu().numpy(), agg.history_update(mu_hist.copy(), z["field"], mu))
+    assert np.array_equal(vh.cpu().numpy(), agg.history_update(var_hist.copy(), z["field"], var))
+
+
+def test_vr_det_dropout_relu_clamps():
+    """entries whose control-variate sum is negative are clamped to 1e-10 and pass no gradient.  With the
+    sampler's own madj the sum is a sum of squares (w ds + fw sigma_bar)^2 >= 0, so the clamp only ever
+    catches rounding; the test feeds a madj three times too large to drive it negative on purpose."""
+    from stochastic_gcn_b200.layers import DeviceAdj, FullNeighbours, VRAggregator
+    g = random_graph(300, 10, 77)
+    rng = np.random.RandomState(4)
+    ids = rng.choice(300, size=50, replace=False).astype(np.int32)
+    z, adj, fadj, s = sample(g, ids, 2, True)
+    n_in, d = len(z["field"]), 32
+    madj = (adj[0], (3.0 * z["medg_w"]).astype(np.float32), adj[2])
+    mu_hist = rng.randn(300, d).astype(np.float32)
+    var_hist = np.full((300, d), 1e-4, np.float32)
+    var_hist[z["field"]] = 4.0                              # big sigma_bar on the sampled rows only
+    mu = mu_hist[z["field"]].copy()
+    var = np.full((n_in, d), 0.01, np.float32)              # sigma << sigma_bar: the cross term is negative
+    (want_mu, want_var), _, pre = agg.det_forward(adj, fadj, madj, z["field"], z["ffield"], mu_hist, var_hist,
+                                                  mu, var, False)
+    assert (pre < 0).any() and (pre > 0).any()
+    layer = VRAggregator(DeviceAdj.from_coo(adj), FullNeighbours.from_coo(fadj, z["ffield"]), madj,
+                         dev(z["field"]), None, [dev(mu_hist), dev(var_hist)], None, False)
+    vt = dev(var).requires_grad_(True)
+    om, ov = layer((dev(mu), vt))
+    close(ov, want_var, "clamped var")
+    gv = rng.randn(*want_var.shape).astype(np.float32)
+    (ov * dev(gv)).sum().backward()
+    close(vt.grad, agg.det_backward_var(adj, madj, z["field"], var_hist, var, pre, gv, False), "clamped dvar")
+
+
 def test_coo_kernel_and_gather_layer():
     from stochastic_gcn_b200 import ops
     from stochastic_gcn_b200.layers import GatherAggregator
