@@ -342,10 +342,11 @@ def run_ours(args, w):
         step.capture_pipelined(batches[0], batches[1], steps_per_graph=args.steps_per_graph)
         launches_per_step -= 2                       # fused dX-init/zero and forward+backward, mark in write-back
         step.run_pipelined(batches[2:args.warmup + 2])
+        timed_table = torch.stack(timed)             # [K, B] ids resident in HBM: one copy per chunk
         torch.cuda.synchronize(dev)
         barrier()
         ev0.record()
-        step.run_pipelined(timed)
+        step.run_pipelined(timed_table)
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -378,11 +379,12 @@ def run_ours(args, w):
             if pending:
                 pending.pop().synchronize()
             pending.append(done)
-        step.run_pipelined(pinned[:args.steps_per_graph], on_chunk=fetch)
+        pinned_table = torch.stack(pinned).pin_memory()          # [K, B] ids in pinned HOST memory
+        step.run_pipelined(pinned_table[:args.steps_per_graph], on_chunk=fetch)
         pending.pop().synchronize()
         barrier()
         e0.record()
-        step.run_pipelined(pinned, on_chunk=fetch)
+        step.run_pipelined(pinned_table, on_chunk=fetch)
         pending.pop().synchronize()
         e1.record()
         barrier()
@@ -489,7 +491,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="time one graph per step, no sampler lookahead")
-    ap.add_argument("--steps-per-graph", type=int, default=8)
+    ap.add_argument("--steps-per-graph", type=int, default=16)
     ap.add_argument("--driver", default="graph", choices=["native", "graph"],
                     help="pipelined schedule: multi-step CUDA graphs (default) or native C++ stream launches")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],

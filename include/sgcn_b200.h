@@ -224,6 +224,25 @@ int sgcn_cvd_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float
                          float* self_h, int64_t ld_sh, float* self_mu, int64_t ld_sm,
                          int32_t accumulate, void* stream);
 
+/* Runtime tunables (process-wide, not thread-safe against concurrent launches).
+ *   SGCN_TUNE_FULL_VARIANT  0 = register-pipelined full_mean_kernel (metadata staged per warp per
+ *                           64 positions), 1 = bulk-copy (cp.async.bulk + mbarrier ring)
+ *                           full_mean_tma_kernel (D <= 128, 16-byte aligned rows), 2 = whole-span
+ *                           full_mean_span_kernel (metadata of the CTA's span resolved in one pass,
+ *                           register-pipelined rows; D <= one column tile).  1 and 2 need
+ *                           n_out <= 4096; other shapes always take variant 0
+ *   SGCN_TUNE_PDL           1 = launch the full-mean kernels with programmatic stream serialization:
+ *                           their preamble (everything before the first history-row load) overlaps
+ *                           the stream predecessor, e.g. the previous step's write-back, which
+ *                           releases them with griddepcontrol.launch_dependents
+ *   SGCN_TUNE_TMA_WARPS / _ROWS / _DEPTH  ring shape of variant 1: warps per CTA (1..16), history
+ *                           rows per stage (1..32), stages per warp (1..4; clipped to fit 226 KB)
+ *   SGCN_TUNE_TMA_GRID      CTAs of variant 1 (default 148 = one per SM; 147 leaves one SM to a kernel
+ *                           that runs beside it, e.g. the next batch's sampler) */
+enum { SGCN_TUNE_FULL_VARIANT = 0, SGCN_TUNE_TMA_WARPS = 1, SGCN_TUNE_TMA_ROWS = 2, SGCN_TUNE_TMA_DEPTH = 3,
+       SGCN_TUNE_TMA_GRID = 4, SGCN_TUNE_PDL = 5 };
+int sgcn_tune_set(int32_t key, int32_t value);
+
 /* ---- det-dropout (mu, var) aggregation: PlainAggregator tuple branch layers.py:238-247 and
  * VRAggregator tuple branch layers.py:320-349 ------------------------------
  * The mean stream reuses sgcn_spmm_csr / sgcn_cv_sampled_fwd with the mean history.  The variance
@@ -331,6 +350,15 @@ int sgcn_copy_rows_pad_pair(const float* src0, int64_t ld_src0, int32_t n0, cons
                             int32_t n_total0, int32_t D0, float* dst0, int64_t ld_dst0,
                             const float* src1, int64_t ld_src1, int32_t n1, const int32_t* n1_dev,
                             int32_t n_total1, int32_t D1, float* dst1, int64_t ld_dst1, void* stream);
+
+/* sgcn_gather_rows + sgcn_copy_rows_pad_pair in ONE launch (the step's side branch starts with these
+ * three independent row jobs; one graph node instead of two saves a dependent launch per step). */
+int sgcn_gather_pad_pair(const float* src, int64_t ld_src, const int32_t* idx, int32_t n,
+                         const int32_t* n_dev, int32_t C, float* dst, int64_t ld_dst,
+                         const float* src0, int64_t ld_src0, int32_t n0, const int32_t* n0_dev,
+                         int32_t n_total0, int32_t D0, float* dst0, int64_t ld_dst0,
+                         const float* src1, int64_t ld_src1, int32_t n1, const int32_t* n1_dev,
+                         int32_t n_total1, int32_t D1, float* dst1, int64_t ld_dst1, void* stream);
 /* sgcn_cv_sampled_fwd / sgcn_cvd_sampled_fwd followed, row by row in the same kernel, by the
  * backward scatter of sgcn_spmm_csr_bwd (dx[cols[e]] += vals[e] * (scale[r]) * dy[r]; dx initialised
  * by the caller).  The forward never reads dx and the backward never reads y, so fusing them only

@@ -57,6 +57,7 @@ SIGNATURES = {
     "sgcn_spmm_csr_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _vp]),
     "sgcn_full_history_mean": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,
                                       _vp, _i64, _vp, _vp]),
+    "sgcn_tune_set": (_i32, [_i32, _i32]),
     "sgcn_spmm_csr_sq": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp]),
     "sgcn_spmm_csr_bwd_sq": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _vp]),
     "sgcn_full_history_mean_sq": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,
@@ -75,6 +76,9 @@ SIGNATURES = {
     "sgcn_history_update": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp]),
     "sgcn_copy_rows_pad_pair": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64,
                                        _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "sgcn_gather_pad_pair": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _vp, _i64,
+                                    _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64,
+                                    _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "sgcn_cv_sampled_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i32, _vp,
                                        _i64, _vp, _i64, _i32, _vp, _i64, _vp, _i64, _vp]),
     "sgcn_cvd_sampled_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _vp,
@@ -127,6 +131,12 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    # optional overrides of the kernel tunables (include/sgcn_b200.h: SGCN_TUNE_*), for A/B runs
+    for key, env in enumerate(("SGCN_FULL_VARIANT", "SGCN_TMA_WARPS", "SGCN_TMA_ROWS", "SGCN_TMA_DEPTH",
+                               "SGCN_TMA_GRID", "SGCN_PDL")):
+        if os.environ.get(env, "") != "":
+            if lib.sgcn_tune_set(key, int(os.environ[env])) != SGCN_OK:
+                raise SgcnError(SGCN_EINVAL, "%s=%s: %s" % (env, os.environ[env], lib.sgcn_last_error().decode()))
     return lib
 
 

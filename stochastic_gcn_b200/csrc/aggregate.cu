@@ -55,6 +55,10 @@ constexpr int kAggThreads = 256;
 
 enum { MODE_PLAIN = 0, MODE_CV = 1, MODE_CVD = 2, MODE_DET = 3 };
 
+// programmatic dependent launch: no-ops unless the kernel was launched with the attribute
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 template <typename V> __device__ __forceinline__ V vsqrt(V a);
 template <> __device__ __forceinline__ float vsqrt<float>(float a) { return sqrtf(a); }
 template <> __device__ __forceinline__ float4 vsqrt<float4>(float4 a) {
@@ -112,6 +116,7 @@ __global__ void __launch_bounds__(kAggThreads)
 sampled_rows_kernel(const SampledArgs a) {
     using T = VT<V>;
     TraceScope ts(a.trace, TR_SAMPLED);
+    grid_dep_wait();      // (PDL) launched early behind the gather that writes x: nothing to do before it
     const int n_out = dev_count(a.n_out_dev, a.n_out);
     const int gl = threadIdx.x % LPR;                      // lane within the group
     const int groups = (gridDim.x * kAggThreads) / LPR;
@@ -376,6 +381,7 @@ __global__ void __maxnreg__(96)      // 2 CTAs x 256 threads x 96 regs leave 16K
 full_mean_kernel(const FullArgs a) {
     using T = VT<V>;
     TraceScope ts(a.trace, TR_FULL);
+    grid_dep_launch();                                           // (PDL) the write-back may get resident now
     constexpr int G = 32 / LPR;                                  // groups per warp
     constexpr int UN = (VPL >= 8) ? 1 : ((VPL == 4) ? 2 : ((VPL == 2) ? 4 : 8));   // row loads per buffer
     constexpr int STEP = G * UN;                                 // positions per group-iteration
@@ -430,6 +436,7 @@ full_mean_kernel(const FullArgs a) {
 #pragma unroll
     for (int k = 0; k < VPL; ++k) acc[k] = T::zero();
     int cur = -1;                                                 // row this group is accumulating
+    grid_dep_wait();                                              // (PDL) history rows: after the write-back
 
   for (;;) {
     int next_chunk = 0;
@@ -524,6 +531,314 @@ full_mean_kernel(const FullArgs a) {
     if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
 }
 
+// ---- full-neighbour history mean, bulk-copy (TMA engine) variant ---------------------------------
+// Same arithmetic as full_mean_kernel; different data movement.  The register variant above keeps
+// at most 16 row loads per warp in flight and pays its metadata staging per 64-position chunk, which
+// at Reddit shape (~100 positions per warp) leaves the kernel latency-bound at ~25 % of any memory
+// pipe (profiles/r01_full_mean_ncu.json).  Here one persistent CTA per SM
+//   1. resolves (row, column, weight) of its WHOLE contiguous span of positions in one parallel
+//      pass by all threads (one global round trip instead of one per chunk),
+//   2. then every warp walks its own contiguous slice of that span as a private ring of shared-
+//      memory stages filled by `cp.async.bulk` row copies (one 16-byte-aligned D*4-byte copy per
+//      history row, completion counted on an mbarrier): rows in flight cost no registers, so a CTA
+//      keeps its whole ring (up to ~190 KB) outstanding; the warp that drains a stage re-arms it
+//      itself (no producer warp, no empty barriers), reduces the rows from shared memory with
+//      warp-uniform (row, weight) broadcasts and leaves through one 128-bit RED per lane per row
+//      segment, exactly like the register variant.
+// ---- full-neighbour history mean, whole-span variant ----------------------------------------------
+// The register variant resolves metadata per warp per 64-position chunk: at Reddit shape a warp owns
+// ~100 positions, so it pays two dependent staging round trips (22 % of its stall samples,
+// profiles/r01_full_mean_ncu.json) during which none of its row loads are in flight.  Here the CTA
+// resolves (row, column, weight) of its whole contiguous span in ONE pass by all 256 threads (a
+// single round trip), then each warp streams its slice of the span with the same two-register-buffer
+// pipeline, reading per-edge operands from the CTA-wide shared-memory arrays.  Everything before the
+// first history-row load is independent of the previous step's write-back, so with programmatic
+// dependent launch (sgcn_tune_set SGCN_TUNE_PDL) that whole preamble overlaps the write-back kernel.
+constexpr int kSpanMeta = 1536;       // positions resolved per pass (24 KB of shared memory)
+constexpr int kSpanPad = 32;          // tail padding so that the stream loop needs no bounds logic
+
+template <typename V, int LPR, int VPL>
+__global__ void __maxnreg__(96)
+full_mean_span_kernel(const FullArgs a) {
+    using T = VT<V>;
+    TraceScope ts(a.trace, TR_FULL);
+    grid_dep_launch();
+    constexpr int G = 32 / LPR;
+    constexpr int UN = (VPL >= 8) ? 1 : ((VPL == 4) ? 2 : ((VPL == 2) ? 4 : 8));
+    constexpr int STEP = G * UN;
+    static_assert(STEP <= kSpanPad, "padding covers one group");
+    extern __shared__ int32_t s_dyn[];
+    int32_t* s_ptr = s_dyn;                                      // rowptr_f            [stage_rows + 1]
+    int32_t* s_base = s_dyn + a.stage_rows + 1;                  // adj_p[nodes[r]] - rowptr_f[r]
+    __shared__ int64_t m_off[kSpanMeta + kSpanPad];              // adj_i * ld_h (element offset of the row)
+    __shared__ float m_w[kSpanMeta + kSpanPad];
+    __shared__ int32_t m_row[kSpanMeta + kSpanPad];
+    const int n_out = dev_count(a.n_out_dev, a.n_out);
+    if (n_out <= 0) return;
+    const int tid = threadIdx.x;
+    for (int i = tid; i <= n_out; i += kAggThreads) s_ptr[i] = __ldg(a.rowptr_f + i);
+    for (int i = tid; i < n_out; i += kAggThreads)
+        s_base[i] = __ldg(a.adj_p + __ldg(a.nodes + i)) - __ldg(a.rowptr_f + i);
+    __syncthreads();
+    const int nnz = s_ptr[n_out];
+    const int span = max(32, (((nnz + (int)gridDim.x - 1) / (int)gridDim.x) + 31) & ~31);
+    const int p0 = blockIdx.x * span;
+    const int p1 = min(p0 + span, nnz);
+    if (p0 >= p1) return;
+    const int lane = tid & 31, wib = tid >> 5;
+    const int gl = lane % LPR, g = lane / LPR;
+    bool ok[VPL];
+    const float* hist_lane[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int off = (gl + k * LPR) * T::W;
+        ok[k] = off < a.D;
+        hist_lane[k] = a.hist + (ok[k] ? off : 0);
+    }
+    V acc[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) acc[k] = T::zero();
+    int cur = -1;
+
+    for (int sc = p0; sc < p1; sc += kSpanMeta) {
+        const int cnt = min(kSpanMeta, p1 - sc);
+        const int cnt_pad = (cnt + STEP - 1) / STEP * STEP;
+        // ---- pass 1: the whole CTA resolves cnt positions (independent of the history table) ----
+        for (int i = tid; i < cnt_pad; i += kAggThreads) {
+            int r = -1;
+            int64_t off = 0;
+            float w = 0.f;
+            if (i < cnt) {
+                const int p = sc + i;
+                int lo = 0, hi = n_out;                          // last r with ptr[r] <= p
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_ptr[mid] <= p) lo = mid; else hi = mid;
+                }
+                const int q = s_base[lo] + p;
+                w = __ldg(a.adj_w + q);
+                if (a.square) w *= w;
+                off = (int64_t)__ldg(a.adj_i + q) * a.ld_h;
+                r = lo;
+            }
+            m_off[i] = off;
+            m_w[i] = w;
+            m_row[i] = r;
+        }
+        __syncthreads();
+        if (sc == p0) grid_dep_wait();                           // history rows: after the write-back
+        // ---- pass 2: each warp streams its slice (a whole number of groups) ----
+        const int per = (((cnt_pad + kFullWarps - 1) / kFullWarps) + STEP - 1) / STEP * STEP;
+        const int w0 = min(wib * per, cnt_pad);
+        const int ng = (min(w0 + per, cnt_pad) - w0) / STEP;
+        const int64_t* my_off = m_off + w0;
+        const float* my_w = m_w + w0;
+        const int32_t* my_r = m_row + w0;
+
+        auto issue = [&](V (&buf)[UN][VPL], int gi) {
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int64_t off = my_off[gi * STEP + u * G + g];
+#pragma unroll
+                for (int k = 0; k < VPL; ++k)
+                    buf[u][k] = ok[k] ? T::ld_stream(hist_lane[k] + off) : T::zero();
+            }
+        };
+        auto consume = [&](V (&buf)[UN][VPL], int gi) {
+            const int jf = gi * STEP + g;
+            const int rf = my_r[jf], rl = my_r[jf + (UN - 1) * G];
+            if (rf == rl && rf >= 0) {                           // whole group inside one output row
+                if (rf != cur) {
+                    if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
+                    cur = rf;
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const float w = my_w[jf + u * G];
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) T::fma(acc[k], w, buf[u][k]);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int r = my_r[jf + u * G];
+                    if (r < 0) continue;
+                    if (r != cur) {
+                        if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
+                        cur = r;
+                    }
+                    const float w = my_w[jf + u * G];
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) T::fma(acc[k], w, buf[u][k]);
+                }
+            }
+        };
+        if (ng > 0) {
+            V bufA[UN][VPL], bufB[UN][VPL];
+            issue(bufA, 0);
+            for (int gi = 0; gi < ng; gi += 2) {
+                if (gi + 1 < ng) issue(bufB, gi + 1);
+                consume(bufA, gi);
+                if (gi + 2 < ng) issue(bufA, gi + 2);
+                if (gi + 1 < ng) consume(bufB, gi + 1);
+            }
+        }
+        if (sc + kSpanMeta < p1) __syncthreads();                // metadata is rewritten by the next pass
+    }
+    if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded: a copy that never lands (bad pointer) traps after ~1 s instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+constexpr int kTmaMeta = 2048;        // positions resolved per pass (24 KB of shared memory)
+constexpr int kTmaMaxWarps = 16;
+constexpr int kTmaMaxDepth = 4;
+
+struct FullTmaCfg { int warps, rows, depth; };   // warps per CTA, rows per stage (<= 32), stages per warp
+
+__global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
+full_mean_tma_kernel(const FullArgs a, const FullTmaCfg cfg) {
+    using T = VT<float4>;
+    TraceScope ts(a.trace, TR_FULL);
+    grid_dep_launch();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int n_out = dev_count(a.n_out_dev, a.n_out);
+    if (n_out <= 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+    const uint32_t row_bytes = (uint32_t)a.D * 4u;
+    const uint32_t stage_bytes = (uint32_t)cfg.rows * row_bytes;
+    const int n_stages = cfg.warps * cfg.depth;
+    unsigned char* s_data = smem_raw;
+    uint64_t* s_full = (uint64_t*)(smem_raw + (size_t)n_stages * stage_bytes);
+    int32_t* m_col = (int32_t*)(s_full + n_stages);
+    float* m_w = (float*)(m_col + kTmaMeta);
+    int32_t* m_row = (int32_t*)(m_w + kTmaMeta);
+    int32_t* s_ptr = m_row + kTmaMeta;                            // rowptr_f            [stage_rows + 1]
+    int32_t* s_base = s_ptr + a.stage_rows + 1;                   // adj_p[nodes[r]] - rowptr_f[r]
+
+    for (int i = tid; i <= n_out; i += nthreads) s_ptr[i] = __ldg(a.rowptr_f + i);
+    for (int i = tid; i < n_out; i += nthreads)
+        s_base[i] = __ldg(a.adj_p + __ldg(a.nodes + i)) - __ldg(a.rowptr_f + i);
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(smem_u32(s_full + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    const int nnz = s_ptr[n_out];
+    const int span = max(32, (((nnz + (int)gridDim.x - 1) / (int)gridDim.x) + 31) & ~31);
+    const int p0 = blockIdx.x * span;
+    const int p1 = min(p0 + span, nnz);
+    if (p0 >= p1) return;
+
+    const int gl = lane;
+    const bool ok = gl * 4 < a.D;
+    float4 acc[1] = {T::zero()};
+    int cur = -1;
+    uint32_t phase = 0;                                           // bit d: parity to wait for on my stage d
+    const uint32_t my_data = smem_u32(s_data) + (uint32_t)(warp * cfg.depth) * stage_bytes;
+    const uint32_t my_full = smem_u32(s_full + warp * cfg.depth);
+    const unsigned char* my_rows = s_data + (size_t)(warp * cfg.depth) * stage_bytes;
+
+    for (int sc = p0; sc < p1; sc += kTmaMeta) {
+        const int cnt = min(kTmaMeta, p1 - sc);
+        // ---- pass 1: all threads resolve the metadata of cnt positions ----
+        for (int i = tid; i < cnt; i += nthreads) {
+            const int p = sc + i;
+            int lo = 0, hi = n_out;                               // last r with ptr[r] <= p
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_ptr[mid] <= p) lo = mid; else hi = mid;
+            }
+            const int q = s_base[lo] + p;
+            float w = __ldg(a.adj_w + q);
+            if (a.square) w *= w;
+            m_col[i] = __ldg(a.adj_i + q);
+            m_w[i] = w;
+            m_row[i] = lo;
+        }
+        __syncthreads();
+        if (sc == p0) grid_dep_wait();
+        // ---- pass 2: each warp streams its contiguous slice through its private ring ----
+        const int per = (((cnt + cfg.warps - 1) / cfg.warps) + cfg.rows - 1) / cfg.rows * cfg.rows;
+        const int w0 = min(warp * per, cnt), w1 = min(w0 + per, cnt);
+        const int nch = (w1 - w0 + cfg.rows - 1) / cfg.rows;
+        auto issue = [&](int j) {                                 // chunk j of my slice -> stage j % depth
+            const int d = j % cfg.depth;
+            const int b = w0 + j * cfg.rows;
+            const int rows = min(cfg.rows, w1 - b);
+            if (lane == 0) mbar_expect_tx(my_full + 8u * d, (uint32_t)rows * row_bytes);
+            __syncwarp();
+            if (lane < rows)
+                bulk_g2s(my_data + (uint32_t)d * stage_bytes + (uint32_t)lane * row_bytes,
+                         a.hist + (int64_t)m_col[b + lane] * a.ld_h, row_bytes, my_full + 8u * d);
+        };
+        if (warp < cfg.warps) {
+            for (int j = 0; j < min(nch, cfg.depth); ++j) issue(j);
+            for (int j = 0; j < nch; ++j) {
+                const int d = j % cfg.depth;
+                const int b = w0 + j * cfg.rows;
+                const int rows = min(cfg.rows, w1 - b);
+                mbar_wait(my_full + 8u * d, (phase >> d) & 1u);
+                phase ^= 1u << d;
+                const unsigned char* base = my_rows + (size_t)d * stage_bytes + (size_t)gl * 16;
+#pragma unroll 4
+                for (int r = 0; r < rows; ++r) {
+                    const int row = m_row[b + r];
+                    const float w = m_w[b + r];
+                    if (row != cur) {
+                        if (cur >= 0) full_flush<float4, 32, 1>(a, cur, gl, acc);
+                        cur = row;
+                    }
+                    if (ok) T::fma(acc[0], w, *(const float4*)(base + (size_t)r * row_bytes));
+                }
+                if (j + cfg.depth < nch) {
+                    __syncwarp();
+                    fence_proxy_async_smem();                     // my reads of the stage before its refill
+                    issue(j + cfg.depth);
+                }
+            }
+        }
+        __syncthreads();                                          // metadata is rewritten by the next pass
+    }
+    if (cur >= 0) full_flush<float4, 32, 1>(a, cur, gl, acc);
+}
+
+// runtime tunables (sgcn_tune_set): which full-mean variant runs and the shape of its ring
+static int g_full_variant = 0;        // 0 = register variant, 1 = bulk-copy variant, 2 = whole-span variant
+static FullTmaCfg g_tma_cfg = {12, 16, 2};
+static int g_tma_grid = kNumSMs;      // CTAs (one per SM); 147 leaves an SM to a concurrently running sampler
+
 // ---- dispatch -----------------------------------------------------------------------------------
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -577,7 +892,11 @@ static int launch_sampled(SampledArgs a, int D, bool vec_ok, cudaStream_t st) {
         if (a.self1) t.self1 = a.self1 + c0;
         if (a.dx) { t.dy = a.dy + c0; t.dx = a.dx + c0; }
         const int grid = grid_for_groups(a.n_out, sh.lpr);
-#define CALL(V, L, P) sampled_rows_kernel<V, L, P, MODE><<<grid, kAggThreads, 0, st>>>(t)
+#define CALL(V, L, P)                                                       \
+    do {                                                                    \
+        SGCN_MATCH_CARVEOUT((sampled_rows_kernel<V, L, P, MODE>));          \
+        SGCN_CUDA(launch_pdl(sampled_rows_kernel<V, L, P, MODE>, dim3(grid), dim3(kAggThreads), 0, st, t)); \
+    } while (0)
         SGCN_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
         SGCN_LAUNCHED();
@@ -789,7 +1108,11 @@ static int spmm_csr_bwd_impl(const int32_t* rowptr, const int32_t* cols, const f
         BwdArgs a{rowptr, cols, vals, rscale, n_out, n_out_dev, dy + c0, ld_dy,
                   std::min(sh.tile, D - c0), dx + c0, ld_dx, g_trace, square};
         const int grid = grid_for_groups(n_out, sh.lpr);
-#define CALL(V, L, P) spmm_bwd_kernel<V, L, P><<<grid, kAggThreads, 0, st>>>(a)
+#define CALL(V, L, P)                                                  \
+    do {                                                               \
+        SGCN_MATCH_CARVEOUT((spmm_bwd_kernel<V, L, P>));               \
+        spmm_bwd_kernel<V, L, P><<<grid, kAggThreads, 0, st>>>(a);     \
+    } while (0)
         SGCN_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
         SGCN_LAUNCHED();
@@ -850,6 +1173,47 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
                         aligned16(y0) && (!y1 || (ld_y1 % 4 == 0 && aligned16(y1)));
     const Shape sh = pick_shape(D, vec_ok);
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_full_variant == 1 && vec_ok && D <= 128 && n_out <= kFullStageRows) {
+        FullTmaCfg cfg = g_tma_cfg;
+        FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0, ld_y0, y1, ld_y1,
+                   nullptr, n_out, g_trace, square};
+        const size_t fixed = 12 * (size_t)kTmaMeta + sizeof(int32_t) * (2 * (size_t)n_out + 2) + 128;
+        const size_t stage = (size_t)cfg.rows * D * 4;
+        while (cfg.depth > 1 && fixed + (size_t)cfg.warps * cfg.depth * (stage + 8) > 226 * 1024) --cfg.depth;
+        const size_t dyn = fixed + (size_t)cfg.warps * cfg.depth * (stage + 8);
+        SGCN_REQUIRE(dyn <= 227 * 1024, "full_history_mean: bulk-copy ring does not fit in shared memory");
+        static bool attr_set = false;
+        if (!attr_set) {
+            SGCN_CUDA(cudaFuncSetAttribute(full_mean_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           227 * 1024));
+            attr_set = true;
+        }
+        SGCN_CUDA(launch_pdl(full_mean_tma_kernel, g_tma_grid, cfg.warps * 32, dyn, st, a, cfg));
+        SGCN_LAUNCHED();
+        return SGCN_OK;
+    }
+    if (g_full_variant == 2 && D <= sh.tile && n_out <= kFullStageRows) {
+        FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0, ld_y0, y1, ld_y1,
+                   nullptr, n_out, g_trace, square};
+        const size_t dyn = sizeof(int32_t) * (2 * (size_t)n_out + 2);
+#define CALL(V, L, P)                                                                        \
+    do {                                                                                     \
+        static int per_sm = 0;                                                               \
+        if (per_sm == 0) {                                                                   \
+            SGCN_CUDA(cudaFuncSetAttribute(full_mean_span_kernel<V, L, P>,                   \
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, 44)); \
+            SGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                         \
+                &per_sm, full_mean_span_kernel<V, L, P>, kAggThreads,                        \
+                sizeof(int32_t) * (2 * (size_t)kFullStageRows + 2)));                        \
+            if (per_sm < 1) per_sm = 1;                                                      \
+        }                                                                                    \
+        SGCN_CUDA(launch_pdl(full_mean_span_kernel<V, L, P>, kNumSMs * per_sm, kAggThreads, dyn, st, a)); \
+    } while (0)
+        SGCN_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+        SGCN_LAUNCHED();
+        return SGCN_OK;
+    }
     for (int c0 = 0; c0 < D; c0 += sh.tile) {
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist + c0, ld_h,
                    std::min(sh.tile, D - c0), y0 + c0, ld_y0, y1 ? y1 + c0 : nullptr, ld_y1,
@@ -871,13 +1235,37 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
                 sizeof(int32_t) * (2 * (size_t)kFullStageRows + 2)));                        \
             if (per_sm < 1) per_sm = 1;                                                      \
         }                                                                                    \
-        full_mean_kernel<V, L, P><<<kNumSMs * per_sm, kAggThreads, dyn, st>>>(a);            \
+        SGCN_CUDA(launch_pdl(full_mean_kernel<V, L, P>, kNumSMs * per_sm, kAggThreads, dyn, st, a)); \
     } while (0)
         SGCN_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
         SGCN_LAUNCHED();
     }
     return SGCN_OK;
+}
+
+int sgcn_tune_set(int32_t key, int32_t value) {
+    switch (key) {
+        case SGCN_TUNE_FULL_VARIANT:
+            SGCN_REQUIRE(value >= 0 && value <= 2, "tune: full-mean variant is 0 (register), 1 (bulk copy) or 2 (whole span)");
+            g_full_variant = value; return SGCN_OK;
+        case SGCN_TUNE_TMA_WARPS:
+            SGCN_REQUIRE(value >= 1 && value <= kTmaMaxWarps, "tune: 1..16 warps");
+            g_tma_cfg.warps = value; return SGCN_OK;
+        case SGCN_TUNE_TMA_ROWS:
+            SGCN_REQUIRE(value >= 1 && value <= 32, "tune: 1..32 rows per stage");
+            g_tma_cfg.rows = value; return SGCN_OK;
+        case SGCN_TUNE_TMA_DEPTH:
+            SGCN_REQUIRE(value >= 1 && value <= kTmaMaxDepth, "tune: 1..4 stages per warp");
+            g_tma_cfg.depth = value; return SGCN_OK;
+        case SGCN_TUNE_PDL:
+            g_pdl = value != 0; return SGCN_OK;
+        case SGCN_TUNE_TMA_GRID:
+            SGCN_REQUIRE(value >= 1 && value <= 4 * kNumSMs, "tune: 1..592 CTAs");
+            g_tma_grid = value; return SGCN_OK;
+        default:
+            SGCN_REQUIRE(false, "tune: unknown key");
+    }
 }
 
 int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,

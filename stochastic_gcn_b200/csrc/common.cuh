@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "sgcn_b200.h"
@@ -47,6 +48,47 @@ inline int cuda_fail(cudaError_t e, const char* what, const char* file, int line
 #define SGCN_REQUIRE(cond, msg)                                                   \
     do {                                                                          \
         if (!(cond)) { ::sgcn::set_error(std::string("invalid argument: ") + (msg)); return SGCN_EINVAL; } \
+    } while (0)
+
+// (PDL) when set, the kernels of the step's main chain (full-neighbour mean -> history write-back ->
+// next full-neighbour mean) are launched with programmatic stream serialization: each starts while its
+// stream predecessor is still running, does the part of its work that does not depend on it, and
+// orders the rest with griddepcontrol.wait (sgcn_tune_set SGCN_TUNE_PDL)
+extern int g_pdl;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t dyn, cudaStream_t st,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// An SM re-partitions its L1 / shared memory only when idle: a kernel whose preferred carve-out differs
+// from that of the kernel occupying the SMs (the full-neighbour mean holds every SM for most of a
+// step) cannot join them and starts only once an SM drains.  Every kernel that runs beside it in the
+// step therefore asks for the SAME ~100 KB carve-out (44 %), whether or not it uses shared memory.
+constexpr int kStepCarveout = 44;
+template <typename K>
+inline void match_step_carveout(K kernel, bool* done) {
+    if (!*done) {
+        if (!getenv("SGCN_NO_MATCH_CARVEOUT"))       // A/B switch for the measurement in profiles/
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kStepCarveout);
+        *done = true;
+    }
+}
+#define SGCN_MATCH_CARVEOUT(kernel)                          \
+    do {                                                     \
+        static bool done__ = false;                          \
+        ::sgcn::match_step_carveout(kernel, &done__);        \
     } while (0)
 
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

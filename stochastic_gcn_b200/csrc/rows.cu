@@ -28,6 +28,12 @@ move_rows_vec4_kernel(const float* __restrict__ src, int64_t ld_src, const int32
                       float* __restrict__ dst, int64_t ld_dst, unsigned long long* trace,
                       int32_t* done_counter) {
     TraceScope ts(trace, MODE == 0 ? TR_GATHER : (MODE == 1 ? TR_UPDATE : TR_PAD));
+    // (PDL) a dependent launched with programmatic stream serialization may start its preamble now;
+    // it still waits for this whole grid (griddepcontrol.wait) before touching what is written here
+    asm volatile("griddepcontrol.launch_dependents;");
+    // ... and if THIS kernel was launched that way (the write-back behind the full-neighbour mean),
+    // nothing below may run before the predecessor grid has finished reading the history table
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // optional: count this launch as "everything stream-ordered before it has finished"
     if (done_counter && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(done_counter, 1);
     const int n = dev_count(n_dev, n_host);
@@ -100,9 +106,15 @@ static int launch_move_rows(const float* src, int64_t ld_src, const int32_t* idx
         int blocks = (int)std::min<int64_t>((total + (int64_t)kRowThreads * kRowUnroll - 1) /
                                                 ((int64_t)kRowThreads * kRowUnroll), max_blocks);
         if (blocks < 1) blocks = 1;
-        move_rows_vec4_kernel<MODE><<<blocks, kRowThreads, 0, st>>>(src, ld_src, idx, n, n_dev,
-                                                                   n_total, c4, dst, ld_dst, g_trace,
-                                                                   done_counter);
+        SGCN_MATCH_CARVEOUT(move_rows_vec4_kernel<MODE>);
+        if (MODE == 1) {      // history write-back: second link of the step's main chain (PDL when enabled)
+            SGCN_CUDA(launch_pdl(move_rows_vec4_kernel<MODE>, dim3(blocks), dim3(kRowThreads), 0, st, src, ld_src,
+                                 idx, n, n_dev, n_total, c4, dst, ld_dst, g_trace, done_counter));
+        } else {
+            move_rows_vec4_kernel<MODE><<<blocks, kRowThreads, 0, st>>>(src, ld_src, idx, n, n_dev,
+                                                                       n_total, c4, dst, ld_dst, g_trace,
+                                                                       done_counter);
+        }
     } else {
         const int64_t total = (int64_t)rows * C;
         int blocks = (int)std::min<int64_t>((total + kRowThreads - 1) / kRowThreads, max_blocks);
@@ -113,38 +125,78 @@ static int launch_move_rows(const float* src, int64_t ld_src, const int32_t* idx
     return SGCN_OK;
 }
 
-// two independent copy+zero-pad jobs in one launch (blockIdx.y picks the job): the step driver
-// initialises dX and pre-zeroes the next step's output with a single graph node
-struct PadJob { const float* src; int64_t ld_src; int n; const int32_t* n_dev; int n_total; int C;
-                float* dst; int64_t ld_dst; };
-struct PadPair { PadJob j[2]; };
+// up to three independent row jobs in one launch (blockIdx.y picks the job): the step driver
+// initialises dX, pre-zeroes the next step's output and gathers the step's input rows with a single
+// graph node -- every dependent launch that leaves a step's side branch is worth ~4 us while the
+// full-neighbour mean saturates the memory system (profiles/r01_timeline_*.txt).
+//   dst[r] = r < n ? src[idx ? idx[r] : r] : 0     for r < n_total   (pad = 1)
+//   dst[r] = src[idx ? idx[r] : r]                 for r < n         (pad = 0; rows >= n untouched)
+struct PadJob { const float* src; int64_t ld_src; const int32_t* idx; int n; const int32_t* n_dev; int n_total;
+                int C; float* dst; int64_t ld_dst; int pad; };
+constexpr int kPadJobs = 3;
+struct PadJobs { PadJob j[kPadJobs]; };
 
 __global__ void __launch_bounds__(kRowThreads)
-pad_pair_kernel(const PadPair p, unsigned long long* trace) {
-    TraceScope ts(trace, TR_PAD);
+pad_jobs_kernel(const PadJobs p, unsigned long long* trace) {
     const PadJob& a = p.j[blockIdx.y];
+    TraceScope ts(trace, a.idx ? TR_GATHER : TR_PAD);
+    asm volatile("griddepcontrol.launch_dependents;");          // (PDL) see move_rows_vec4_kernel
     if (!a.dst || a.n_total <= 0 || a.C <= 0) return;
     const int n = dev_count(a.n_dev, a.n);
+    const int rows = a.pad ? a.n_total : min(n, a.n_total);
     const bool vec = (a.C & 3) == 0 && (a.ld_dst & 3) == 0 && (((uintptr_t)a.dst) & 15) == 0 &&
                      (a.n == 0 || ((a.ld_src & 3) == 0 && (((uintptr_t)a.src) & 15) == 0));
     const int64_t stride = (int64_t)gridDim.x * kRowThreads;
     if (vec) {
         const int c4 = a.C >> 2;
-        const int64_t total = (int64_t)a.n_total * c4;
-        for (int64_t t = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; t < total; t += stride) {
-            const int r = (int)(t / c4);
-            const int c = (int)(t - (int64_t)r * c4) * 4;
-            const float4 v = r < n ? ldg_stream4(a.src + (int64_t)r * a.ld_src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            stg_stream4(a.dst + (int64_t)r * a.ld_dst + c, v);
+        const int64_t total = (int64_t)rows * c4;
+        for (int64_t base = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; base < total;
+             base += stride * kRowUnroll) {
+            float4 v[kRowUnroll];
+            int64_t off_dst[kRowUnroll];
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) {
+                const int64_t t = base + (int64_t)u * stride;
+                off_dst[u] = -1;
+                if (t < total) {
+                    const int r = (int)(t / c4);
+                    const int c = (int)(t - (int64_t)r * c4) * 4;
+                    off_dst[u] = (int64_t)r * a.ld_dst + c;
+                    if (r < n) {
+                        const int64_t rs = a.idx ? (int64_t)a.idx[r] : (int64_t)r;
+                        v[u] = ldg_stream4(a.src + rs * a.ld_src + c);
+                    } else {
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u)
+                if (off_dst[u] >= 0) stg_stream4(a.dst + off_dst[u], v[u]);
         }
     } else {
-        const int64_t total = (int64_t)a.n_total * a.C;
+        const int64_t total = (int64_t)rows * a.C;
         for (int64_t t = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; t < total; t += stride) {
             const int r = (int)(t / a.C);
             const int c = (int)(t - (int64_t)r * a.C);
-            a.dst[(int64_t)r * a.ld_dst + c] = r < n ? a.src[(int64_t)r * a.ld_src + c] : 0.f;
+            float v = 0.f;
+            if (r < n) v = a.src[(a.idx ? (int64_t)a.idx[r] : (int64_t)r) * a.ld_src + c];
+            a.dst[(int64_t)r * a.ld_dst + c] = v;
         }
     }
+}
+
+static int launch_pad_jobs(const PadJobs& p, int n_jobs, cudaStream_t st) {
+    int64_t work = 1;
+    for (int k = 0; k < n_jobs; ++k)
+        if (p.j[k].dst) work = std::max<int64_t>(work, (int64_t)p.j[k].n_total * p.j[k].C / 4);
+    const int64_t per_block = (int64_t)kRowThreads * kRowUnroll;
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((work + per_block - 1) / per_block, kNumSMs * 4)),
+              (unsigned)n_jobs);
+    SGCN_MATCH_CARVEOUT(pad_jobs_kernel);
+    pad_jobs_kernel<<<grid, kRowThreads, 0, st>>>(p, g_trace);
+    SGCN_LAUNCHED();
+    return SGCN_OK;
 }
 
 // ---- CSR row slicer -------------------------------------------------------------------------
@@ -222,14 +274,30 @@ int sgcn_copy_rows_pad_pair(const float* src0, int64_t ld_src0, int32_t n0, cons
     SGCN_REQUIRE((n0 == 0 || src0) && (n1 == 0 || src1), "copy_rows_pad_pair: null src");
     SGCN_REQUIRE((!dst0 || ld_dst0 >= D0) && (!dst1 || ld_dst1 >= D1) && (n0 == 0 || ld_src0 >= D0) &&
                      (n1 == 0 || ld_src1 >= D1), "copy_rows_pad_pair: row stride smaller than width");
-    PadPair p{};
-    p.j[0] = PadJob{src0, ld_src0, n0, n0_dev, n_total0, D0, dst0, ld_dst0};
-    p.j[1] = PadJob{src1, ld_src1, n1, n1_dev, n_total1, D1, dst1, ld_dst1};
-    const int64_t work = std::max<int64_t>(std::max((int64_t)n_total0 * D0, (int64_t)n_total1 * D1) / 4, 1);
-    dim3 grid((unsigned)std::min<int64_t>((work + kRowThreads - 1) / kRowThreads, kNumSMs * 2), 2);
-    pad_pair_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(p, g_trace);
-    SGCN_LAUNCHED();
-    return SGCN_OK;
+    PadJobs p{};
+    p.j[0] = PadJob{src0, ld_src0, nullptr, n0, n0_dev, n_total0, D0, dst0, ld_dst0, 1};
+    p.j[1] = PadJob{src1, ld_src1, nullptr, n1, n1_dev, n_total1, D1, dst1, ld_dst1, 1};
+    return launch_pad_jobs(p, 2, (cudaStream_t)stream);
+}
+
+int sgcn_gather_pad_pair(const float* src, int64_t ld_src, const int32_t* idx, int32_t n,
+                         const int32_t* n_dev, int32_t C, float* dst, int64_t ld_dst,
+                         const float* src0, int64_t ld_src0, int32_t n0, const int32_t* n0_dev,
+                         int32_t n_total0, int32_t D0, float* dst0, int64_t ld_dst0,
+                         const float* src1, int64_t ld_src1, int32_t n1, const int32_t* n1_dev,
+                         int32_t n_total1, int32_t D1, float* dst1, int64_t ld_dst1, void* stream) {
+    SGCN_REQUIRE(n >= 0 && C >= 0 && n0 >= 0 && n1 >= 0 && n_total0 >= 0 && n_total1 >= 0 && D0 >= 0 && D1 >= 0,
+                 "gather_pad_pair: negative size");
+    SGCN_REQUIRE(n == 0 || C == 0 || (src && idx && dst), "gather_pad_pair: null gather pointer");
+    SGCN_REQUIRE(ld_src >= C && ld_dst >= C, "gather_pad_pair: row stride smaller than width");
+    SGCN_REQUIRE((n0 == 0 || src0) && (n1 == 0 || src1), "gather_pad_pair: null src");
+    SGCN_REQUIRE((!dst0 || ld_dst0 >= D0) && (!dst1 || ld_dst1 >= D1) && (n0 == 0 || ld_src0 >= D0) &&
+                     (n1 == 0 || ld_src1 >= D1), "gather_pad_pair: row stride smaller than width");
+    PadJobs p{};
+    p.j[0] = PadJob{src, ld_src, idx, n, n_dev, n, C, n > 0 && C > 0 ? dst : nullptr, ld_dst, 0};
+    p.j[1] = PadJob{src0, ld_src0, nullptr, n0, n0_dev, n_total0, D0, dst0, ld_dst0, 1};
+    p.j[2] = PadJob{src1, ld_src1, nullptr, n1, n1_dev, n_total1, D1, dst1, ld_dst1, 1};
+    return launch_pad_jobs(p, 3, (cudaStream_t)stream);
 }
 
 int sgcn_csr_slice_indptr(const int32_t* a_p, const int32_t* r, int32_t n, int32_t* o_p,

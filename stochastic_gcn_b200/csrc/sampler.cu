@@ -625,6 +625,7 @@ __device__ __forceinline__ bool hash_has(const int32_t* keys, int mask, int shif
 template <int NT, int MIN_BLOCKS>
 __global__ void __launch_bounds__(NT, MIN_BLOCKS)
 expand_fused_kernel(const FusedArgs a) {
+    constexpr int IPT = NT >= 1024 ? 1 : 2;                    // rows per thread per sweep
     extern __shared__ int32_t smem[];
     // carved to the launch's own bounds (fused_smem_bytes): a 512 x 2 batch needs ~46 KB, not the
     // 211 KB worst case, which keeps the SM's L1/shared carve-out where the neighbouring kernels want it
@@ -654,34 +655,58 @@ expand_fused_kernel(const FusedArgs a) {
     }
     __syncthreads();
 
-    // rows + both prefix sums, 1024 rows per sweep with a carry; old field -> table (value = position)
+    // rows + both prefix sums, NT * IPT rows per sweep with a carry; old field -> table (value =
+    // position).  Every thread owns IPT CONSECUTIVE rows and issues their dependent loads together
+    // (ids -> row pointers), so the narrow co-resident variant pays one round trip per sweep, not IPT.
     int carry_s = 0, carry_f = 0;
-    for (int base = 0; base < n_out; base += NT) {
-        const int i = base + tid;
-        int take = 0, d = 0;
-        if (i < n_out) {
-            const int node = a.field_in[i];
-            a.field[i] = node;
-            if (node < 0 || node >= a.N) {
-                atomicOr(&s_status, ST_RANGE);
-                a.scales[i] = 1.f;
-            } else {
-                const int b = a.adj_p[node];
-                d = a.adj_p[node + 1] - b;
-                take = min(d, a.degree);
-                const float scale = (d == 0) ? 1.f : __fdiv_rn((float)d, (float)take);
-                a.scales[i] = (float)(1.0 / (double)__fsqrt_rn(scale));
-                const int h = hash_claim(s_keys, hmask, hshift, node);
-                if (atomicMin(s_vals + h, i) != kUnseen) atomicOr(&s_status, ST_DUPLICATE);
+    for (int base = 0; base < n_out; base += NT * IPT) {
+        int node[IPT], take[IPT], d[IPT], b0[IPT], b1[IPT];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int i = base + tid * IPT + q;
+            node[q] = i < n_out ? a.field_in[i] : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const bool in_range = node[q] >= 0 && node[q] < a.N;
+            b0[q] = in_range ? a.adj_p[node[q]] : 0;
+            b1[q] = in_range ? a.adj_p[node[q] + 1] : 0;
+        }
+        int sum_s = 0, sum_f = 0;
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int i = base + tid * IPT + q;
+            take[q] = 0; d[q] = 0;
+            if (i < n_out) {
+                a.field[i] = node[q];
+                if (node[q] < 0 || node[q] >= a.N) {
+                    atomicOr(&s_status, ST_RANGE);
+                    a.scales[i] = 1.f;
+                } else {
+                    d[q] = b1[q] - b0[q];
+                    take[q] = min(d[q], a.degree);
+                    const float scale = (d[q] == 0) ? 1.f : __fdiv_rn((float)d[q], (float)take[q]);
+                    a.scales[i] = (float)(1.0 / (double)__fsqrt_rn(scale));
+                    const int h = hash_claim(s_keys, hmask, hshift, node[q]);
+                    if (atomicMin(s_vals + h, i) != kUnseen) atomicOr(&s_status, ST_DUPLICATE);
+                }
             }
+            sum_s += take[q];
+            sum_f += a.cv ? d[q] : 0;
         }
         int tot_s, tot_f;
-        const int ex_s = block_scan_excl_nt<NT>(take, &tot_s, s_warp);
-        const int ex_f = block_scan_excl_nt<NT>(a.cv ? d : 0, &tot_f, s_warp);
-        if (i < n_out) {
-            s_rowptr[i] = carry_s + ex_s;
-            a.rowptr_s[i] = carry_s + ex_s;
-            a.rowptr_f[i] = carry_f + ex_f;
+        int ex_s = block_scan_excl_nt<NT>(sum_s, &tot_s, s_warp);
+        int ex_f = block_scan_excl_nt<NT>(sum_f, &tot_f, s_warp);
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int i = base + tid * IPT + q;
+            if (i < n_out) {
+                s_rowptr[i] = carry_s + ex_s;
+                a.rowptr_s[i] = carry_s + ex_s;
+                a.rowptr_f[i] = carry_f + ex_f;
+            }
+            ex_s += take[q];
+            ex_f += a.cv ? d[q] : 0;
         }
         carry_s += tot_s;
         carry_f += tot_f;
@@ -737,80 +762,108 @@ expand_fused_kernel(const FusedArgs a) {
         __syncthreads();
     }
 
-    // per-row partial Fisher-Yates on the stored row (rows of one field are disjoint)
-    for (int i = tid; i < n_out; i += NT) {
-        const int e0 = s_rowptr[i];
-        const int take = s_rowptr[i + 1] - e0;
-        if (take <= 0 || e0 + take > a.sb) continue;
-        const int node = a.field_in[i];
-        const int base = a.adj_p[node];
-        const int d = a.adj_p[node + 1] - base;
-        int32_t* rc = a.adj_i + base;
-        float* rw = a.adj_w + base;
-        const float scale = __fdiv_rn((float)d, (float)take);
-        auto draw_index = [&](int k) {
-            // idx = min((int)(it + num_remaining * u01(generator)), adj_range-1)  (scheduler.cpp:141-143)
-            const float u = mt_canonical(s_u[e0 + k]);
-            const int j = (int)__fadd_rn((float)k, __fmul_rn((float)(d - k), u));
-            return min(j, d - 1);
-        };
-        auto emit = [&](int k, int t, float wv) {
-            const float w = __fmul_rn(wv, scale);
-            const int e = e0 + k;
-            a.edg_s[e] = i;
-            a.tgt[e] = t;
-            a.edg_w[e] = w;
-            if (a.cv) a.medg_w[e] = __fmul_rn(wv, w);
-            const int h = hash_claim(s_keys, hmask, hshift, t);
-            atomicMin(s_vals + h, n_out + e);
-            s_eslot[e] = h;
-        };
-        if (take <= 2) {
-            // every touched position is known from the draws alone: fetch them all at once, replay
-            // the <= 2 swaps on the local copy, store once (one DRAM round trip instead of one per swap)
-            const int j0 = draw_index(0);
-            const int j1 = take == 2 ? draw_index(1) : j0;
-            int pos[4] = {0, j0, take == 2 ? 1 : 0, j1};
-            int cv4[4];
-            float wv4[4];
+    // per-row partial Fisher-Yates on the stored row (rows of one field are disjoint).  A thread walks
+    // IPT consecutive rows in three phases -- ids + row pointers, the touched row entries, swap +
+    // emit -- so the dependent global round trips of its rows overlap instead of queueing.
+    for (int base = 0; base < n_out; base += NT * IPT) {
+        int e0[IPT], take[IPT], d[IPT], rb[IPT];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                cv4[q] = rc[pos[q]];
-                wv4[q] = rw[pos[q]];
+        for (int q = 0; q < IPT; ++q) {
+            const int i = base + tid * IPT + q;
+            take[q] = 0; e0[q] = 0; d[q] = 0; rb[q] = 0;
+            if (i < n_out) {
+                e0[q] = s_rowptr[i];
+                take[q] = s_rowptr[i + 1] - e0[q];
+                if (take[q] <= 0 || e0[q] + take[q] > a.sb) take[q] = 0;
             }
-            auto rd = [&](int x, int& c, float& w) {
+        }
+        int node[IPT];
 #pragma unroll
-                for (int q = 3; q >= 0; --q)
-                    if (pos[q] == x) { c = cv4[q]; w = wv4[q]; }
+        for (int q = 0; q < IPT; ++q) node[q] = take[q] > 0 ? a.field_in[base + tid * IPT + q] : 0;
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            if (take[q] > 0) {
+                rb[q] = a.adj_p[node[q]];
+                d[q] = a.adj_p[node[q] + 1] - rb[q];
+            }
+        }
+        // draws of the rows that take <= 2 entries: every touched position is known from the draws
+        // alone -- fetch them all at once, replay the <= 2 swaps on the local copy, store once
+        int pos[IPT][4], cv4[IPT][4];
+        float wv4[IPT][4];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            if (take[q] > 0 && take[q] <= 2) {
+                auto draw_index = [&](int k) {
+                    // idx = min((int)(it + num_remaining * u01(generator)), adj_range-1)  (scheduler.cpp:141-143)
+                    const float u = mt_canonical(s_u[e0[q] + k]);
+                    const int j = (int)__fadd_rn((float)k, __fmul_rn((float)(d[q] - k), u));
+                    return min(j, d[q] - 1);
+                };
+                const int j0 = draw_index(0);
+                const int j1 = take[q] == 2 ? draw_index(1) : j0;
+                pos[q][0] = 0; pos[q][1] = j0; pos[q][2] = take[q] == 2 ? 1 : 0; pos[q][3] = j1;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    cv4[q][x] = a.adj_i[rb[q] + pos[q][x]];
+                    wv4[q][x] = a.adj_w[rb[q] + pos[q][x]];
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            if (take[q] <= 0) continue;
+            const int i = base + tid * IPT + q;
+            int32_t* rc = a.adj_i + rb[q];
+            float* rw = a.adj_w + rb[q];
+            const float scale = __fdiv_rn((float)d[q], (float)take[q]);
+            auto emit = [&](int k, int t, float wv) {
+                const float w = __fmul_rn(wv, scale);
+                const int e = e0[q] + k;
+                a.edg_s[e] = i;
+                a.tgt[e] = t;
+                a.edg_w[e] = w;
+                if (a.cv) a.medg_w[e] = __fmul_rn(wv, w);
+                const int h = hash_claim(s_keys, hmask, hshift, t);
+                atomicMin(s_vals + h, n_out + e);
+                s_eslot[e] = h;
             };
-            auto wr = [&](int x, int c, float w) {
+            if (take[q] <= 2) {
+                auto rd = [&](int x, int& c, float& w) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (pos[q] == x) { cv4[q] = c; wv4[q] = w; }
-            };
-            for (int k = 0; k < take; ++k) {
-                const int j = k == 0 ? j0 : j1;
-                int ck = 0, cj = 0;
-                float wk = 0.f, wj = 0.f;
-                rd(k, ck, wk);
-                rd(j, cj, wj);
-                wr(k, cj, wj);
-                wr(j, ck, wk);
-                emit(k, cj, wj);
-            }
+                    for (int y = 3; y >= 0; --y)
+                        if (pos[q][y] == x) { c = cv4[q][y]; w = wv4[q][y]; }
+                };
+                auto wr = [&](int x, int c, float w) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                rc[pos[q]] = cv4[q];
-                rw[pos[q]] = wv4[q];
-            }
-        } else {
-            for (int k = 0; k < take; ++k) {
-                const int j = draw_index(k);
-                const int ck = rc[k], cj = rc[j];
-                const float wk = rw[k], wj = rw[j];
-                rc[k] = cj; rc[j] = ck;
-                rw[k] = wj; rw[j] = wk;
-                emit(k, cj, wj);
+                    for (int y = 0; y < 4; ++y)
+                        if (pos[q][y] == x) { cv4[q][y] = c; wv4[q][y] = w; }
+                };
+                for (int k = 0; k < take[q]; ++k) {
+                    const int j = k == 0 ? pos[q][1] : pos[q][3];
+                    int ck = 0, cj = 0;
+                    float wk = 0.f, wj = 0.f;
+                    rd(k, ck, wk);
+                    rd(j, cj, wj);
+                    wr(k, cj, wj);
+                    wr(j, ck, wk);
+                    emit(k, cj, wj);
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    rc[pos[q][x]] = cv4[q][x];
+                    rw[pos[q][x]] = wv4[q][x];
+                }
+            } else {
+                for (int k = 0; k < take[q]; ++k) {
+                    const float u = mt_canonical(s_u[e0[q] + k]);
+                    const int j = min((int)__fadd_rn((float)k, __fmul_rn((float)(d[q] - k), u)), d[q] - 1);
+                    const int ck = rc[k], cj = rc[j];
+                    const float wk = rw[k], wj = rw[j];
+                    rc[k] = cj; rc[j] = ck;
+                    rw[k] = wj; rw[j] = wk;
+                    emit(k, cj, wj);
+                }
             }
         }
     }
@@ -819,12 +872,23 @@ expand_fused_kernel(const FusedArgs a) {
     // first-occurrence flags -> ranks (reuse the draw buffer)
     int32_t* s_rank = (int32_t*)s_u;
     int n_new = 0;
-    for (int base = 0; base < nnz; base += NT) {
-        const int e = base + tid;
-        const int f = (e < nnz && s_vals[s_eslot[e]] == n_out + e) ? 1 : 0;
+    constexpr int EPT = 4;                                     // consecutive edges per thread per sweep
+    for (int base = 0; base < nnz; base += NT * EPT) {
+        int f[EPT], sum = 0;
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const int e = base + tid * EPT + q;
+            f[q] = (e < nnz && s_vals[s_eslot[e]] == n_out + e) ? 1 : 0;
+            sum += f[q];
+        }
         int tot;
-        const int ex = block_scan_excl_nt<NT>(f, &tot, s_warp);
-        if (e < nnz) s_rank[e] = n_new + ex;
+        int ex = block_scan_excl_nt<NT>(sum, &tot, s_warp);
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const int e = base + tid * EPT + q;
+            if (e < nnz) s_rank[e] = n_new + ex;
+            ex += f[q];
+        }
         n_new += tot;
     }
     __syncthreads();
@@ -970,11 +1034,11 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
         if (!attr_set) {
             SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel<1024, 1>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes));
-            SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel<256, 5>,
+            SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel<256, 4>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes));
             // same ~100 KB carve-out as full_mean_kernel: whichever of the two reaches an SM first,
             // the other can join it without a re-partition
-            SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel<256, 5>,
+            SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel<256, 4>,
                                            cudaFuncAttributePreferredSharedMemoryCarveout, 44));
             attr_set = true;
         }
@@ -994,7 +1058,7 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
                      lv.tgt.as<int32_t>(), lv.edg_w.as<float>(), lv.medg_w.as<float>(),
                      lv.scales.as<float>(), meta};
         if (s->pipeline)
-            expand_fused_kernel<256, 5><<<1, 256, fused_smem_bytes(nb, (int)sb, hbits), st>>>(fa);
+            expand_fused_kernel<256, 4><<<1, 256, fused_smem_bytes(nb, (int)sb, hbits), st>>>(fa);
         else
             expand_fused_kernel<1024, 1><<<1, 1024, fused_smem_bytes(nb, (int)sb, hbits), st>>>(fa);
         SGCN_LAUNCHED();

@@ -196,6 +196,22 @@ def copy_rows_pad_pair(src0, n0, out0, src1, n1, out1, n0_dev=None, n1_dev=None)
     check(_lib.load().sgcn_copy_rows_pad_pair(*a, *b, stream_ptr()))
 
 
+def gather_pad_pair(src, idx, out, src0, n0, out0, src1, n1, out1, n_dev=None, n0_dev=None, n1_dev=None):
+    """gather_rows(src, idx) -> out fused with copy_rows_pad_pair (out1 may be None): one launch."""
+    _f32(src, "src"); _i32(idx, "idx"); _f32(out, "out"); _f32(out0, "out0")
+    a = (ptr(src0) if n0 > 0 else None, _ld(src0) if n0 > 0 else 0, n0, ptr(n0_dev), out0.shape[0], out0.shape[1],
+         ptr(out0), _ld(out0))
+    if out1 is None:
+        b = (None, 0, 0, None, 0, 0, None, 0)
+    else:
+        _f32(out1, "out1")
+        b = (ptr(src1) if n1 > 0 else None, _ld(src1) if n1 > 0 else 0, n1, ptr(n1_dev), out1.shape[0],
+             out1.shape[1], ptr(out1), _ld(out1))
+    check(_lib.load().sgcn_gather_pad_pair(ptr(src), _ld(src), ptr(idx), idx.numel(), ptr(n_dev), src.shape[1],
+                                           ptr(out), _ld(out), *a, *b, stream_ptr()))
+    return out
+
+
 def cv_sampled_fwd_bwd(rowptr, cols, vals, tgt, n_out, x, hist, y, dy, dx, self_out=None, n_out_dev=None,
                        accumulate=False):
     """cv_sampled_fwd fused with the backward scatter dx[cols[e]] += vals[e] * dy[r] (dx pre-initialised)."""

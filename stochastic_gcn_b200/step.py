@@ -133,12 +133,15 @@ class HotPathStep:
         if nb_mu is not None:
             ops.copy_rows_pad(None, 0, nb_mu)
 
-    def _rest(self, slot, main, zero_next=False, after=None, fork=None, side=None):
+    def _rest(self, slot, main, zero_next=False, after=None, fork=None, side=None, carry=None):
         """Everything after the sampler for the batch held by buffer set `slot`.
 
         outs[slot] must already be zero.  zero_next: also zero outs[1-slot] (for the next step) at the
         end of the side branch.  after(side_stream): optional extra work enqueued on the side branch
-        once the aggregate is complete (e.g. the D2H copy of the step's result)."""
+        once the aggregate is complete (e.g. the D2H copy of the step's result).  carry: a list used as a
+        mailbox between consecutive steps of one capture -- the event that ends `after` is left there
+        and awaited by the NEXT step's side branch (before it re-zeroes the buffer `after` reads) instead
+        of by this step's main chain; the caller waits for whatever is left at the end."""
         v = self._ensure_views(slot)
         pipelined = self._pipeline_on        # the sampler's device guard counts consumer passes
         H, B = self.hidden, self.B
@@ -164,14 +167,17 @@ class HotPathStep:
         # of the aggregate fused with its backward -- three graph nodes
         with torch.cuda.stream(side):
             side.wait_event(ev_start)
+            if carry:                            # the previous step's deferred `after` work (D2H of its rows)
+                side.wait_event(carry.pop())     # must precede this branch's zeroing of that buffer
             d_nb = self.d_out[:, H:] if self.concat else self.d_out
             d_self = self.d_out[:, :H] if self.concat else None
             nxt = self._out_views(1 - slot) if (zero_next and cv) else None
-            ops.copy_rows_pad_pair(d_self, B if self.concat else 0, self.dx, None, 0,
-                                   nxt[0] if nxt else None, n0_dev=v["n_out_dev"] if self.concat else None)
+            # dX init + next step's output zeroing + this step's feature-row gather: ONE graph node
+            ops.gather_pad_pair(self.features, v["field"], self.x0, d_self, B if self.concat else 0, self.dx,
+                                None, 0, nxt[0] if nxt else None, n_dev=v["n_in_dev"],
+                                n0_dev=v["n_out_dev"] if self.concat else None)
             if nxt and nxt[2] is not None:
                 ops.copy_rows_pad(None, 0, nxt[2])
-            ops.gather_rows(self.features, v["field"], out=self.x0, n_dev=v["n_in_dev"])
             x = self.x0[:, :H]
             new_hist = None
             if cv:      # the rows that will be written back exist now: a sharded step publishes them early
@@ -206,7 +212,10 @@ class HotPathStep:
                 after(side)
                 ev_side = torch.cuda.Event()
                 ev_side.record(side)
-            main.wait_event(ev_side)
+            if carry is not None:                # off the critical path: the next step's side branch waits
+                carry.append(ev_side)
+            else:
+                main.wait_event(ev_side)
 
     def _publish_write_back(self, v, new_hist):
         """Hook, on the side branch right after the gather: nothing to do on one GPU."""
@@ -349,6 +358,7 @@ class HotPathStep:
                     chain.wait_event(ev_in)
                     if host_io:
                         tab[c].copy_(pin_tab[c], non_blocking=True)
+                    carry = [] if host_io else None
                     for k in range(S):
                         slot_r, slot_s = k & 1, 1 - (k & 1)
                         ev_box = []
@@ -367,9 +377,11 @@ class HotPathStep:
                             dst, src = pin_out[c][k], self.outs[slot_r]
                             after = lambda st, dst=dst, src=src: dst.copy_(src, non_blocking=True)
                         self._rest(slot_r, chain, zero_next=True, after=after,
-                                   fork=None if (closed and k == S - 1) else fork, side=pools[1][k])
+                                   fork=None if (closed and k == S - 1) else fork, side=pools[1][k], carry=carry)
                         if ev_box:
                             chain.wait_event(ev_box[0])
+                    if carry:
+                        chain.wait_event(carry.pop())      # the last step's rows are on the host at graph end
                     ev_out = torch.cuda.Event()
                     ev_out.record(chain)
                 side.wait_event(ev_out)
@@ -399,14 +411,17 @@ class HotPathStep:
 
     def run_pipelined(self, batches, on_chunk=None):
         """Run len(batches) consecutive passes with one-batch sampler lookahead on the current stream.
-        Per chunk of S steps: the ids copies and ONE graph launch.  ``batches``: int32 id tensors
-        (CUDA; host tensors when captured with host_io=True).  ``on_chunk(first_step, count, step,
+        Per chunk of S steps: the ids copy and ONE graph launch.  ``batches``: a contiguous int32
+        [n, B] id table (one copy per chunk) or a list of [B] id tensors (one copy per step); CUDA, or
+        host memory when captured with host_io=True.  ``on_chunk(first_step, count, step,
         done_event)`` is called after a chunk has been enqueued (host_io: once ``done_event`` has
         completed, ``step._pipe["pin_out"][c][:count]`` holds the rows of those steps, c = chunk
         parity; that buffer is rewritten by chunk c+2, so wait for the event before launching it --
         waiting one chunk behind keeps the GPU busy while the host consumes results)."""
         pipe = self._pipe
-        S, n = pipe["S"], len(batches)
+        # a contiguous [n, B] id table moves a chunk's ids with ONE copy (a list costs one per step)
+        table = batches if isinstance(batches, torch.Tensor) and batches.dim() == 2 else None
+        S, n = pipe["S"], (table.shape[0] if table is not None else len(batches))
         if n == 0:
             return self.out
         host_io = pipe["host_io"]
@@ -422,8 +437,12 @@ class HotPathStep:
             dst = stage[par]
             if host_io and pipe.get("done", [None, None])[par] is not None:
                 pipe["done"][par].synchronize()                 # chunk c-2 has consumed this staging buffer
-            for k, ids in enumerate(ahead):
-                dst[k].copy_(ids, non_blocking=not host_io)
+            if table is not None:
+                if len(ahead):
+                    dst[:len(ahead)].copy_(ahead, non_blocking=not host_io)
+            else:
+                for k, ids in enumerate(ahead):
+                    dst[k].copy_(ids, non_blocking=not host_io)
             pipe["closed" if closed else "open"][par].replay()
             self._last_slot, self._last_sampler_slot = (S - 1) & 1, None
             ev = torch.cuda.Event()

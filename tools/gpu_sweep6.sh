@@ -1,0 +1,18 @@
+#!/bin/bash
+set -u
+OUT=gpurun_out/${1:-sweep7}
+mkdir -p "$OUT"
+timeout 300 python -m pytest tests/test_step_gpu.py -x -q > "$OUT/pytest.log" 2>&1; tail -2 "$OUT/pytest.log"
+for S in 8 16; do
+  echo "== steps/graph $S"
+  timeout 200 python bench.py --no-cpu --steps 4800 --steps-per-graph $S > "$OUT/bench_S$S.json" 2> "$OUT/bench_S$S.err"; echo "bench exit $?"
+  python - "$OUT/bench_S$S.json" <<'PY'
+import json,sys
+try:
+    d=json.load(open(sys.argv[1]))
+    print("ms/step %.5f serial %.5f e2e %.5f kern_us %.2f frac %.3f launches/step %.1f" % (d["ms_per_step"], d["schedule"]["ms_per_step_one_graph_back_to_back"], d["e2e"]["ms_per_step"], d["roofline"]["us_per_launch"], d["roofline"]["frac"], d["launches_per_step"]))
+except Exception as e:
+    print("no bench line", e)
+PY
+  tail -2 "$OUT/bench_S$S.err"
+done
