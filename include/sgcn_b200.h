@@ -225,16 +225,15 @@ int sgcn_cvd_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float
                          int32_t accumulate, void* stream);
 
 /* Runtime tunables (process-wide, not thread-safe against concurrent launches).
- *   SGCN_TUNE_FULL_VARIANT  0 = register-pipelined full_mean_kernel (metadata staged per warp per
- *                           64 positions), 1 = bulk-copy (cp.async.bulk + mbarrier ring)
- *                           full_mean_tma_kernel (D <= 128, 16-byte aligned rows), 2 = whole-span
- *                           full_mean_span_kernel (metadata of the CTA's span resolved in one pass,
- *                           register-pipelined rows; D <= one column tile).  1 and 2 need
- *                           n_out <= 4096; other shapes always take variant 0
- *   SGCN_TUNE_PDL           1 = launch the full-mean kernels with programmatic stream serialization:
- *                           their preamble (everything before the first history-row load) overlaps
- *                           the stream predecessor, e.g. the previous step's write-back, which
- *                           releases them with griddepcontrol.launch_dependents
+ *   SGCN_TUNE_FULL_VARIANT  0 = register-pipelined full_mean_kernel (default, fastest measured),
+ *                           1 = bulk-copy (cp.async.bulk + mbarrier ring) full_mean_tma_kernel
+ *                           (D <= 128, 16-byte aligned rows, n_out <= 4096; other shapes take 0)
+ *   SGCN_TUNE_PDL           1 (default) = the step's chain kernels (full-neighbour mean, history
+ *                           write-back, sampled aggregate) are launched with programmatic stream
+ *                           serialization: each becomes resident while its stream predecessor still
+ *                           runs, does what does not depend on it (the full mean: row pointers and
+ *                           the first chunk's metadata) and orders the rest with griddepcontrol.wait;
+ *                           0 = plain stream-ordered launches
  *   SGCN_TUNE_TMA_WARPS / _ROWS / _DEPTH  ring shape of variant 1: warps per CTA (1..16), history
  *                           rows per stage (1..32), stages per warp (1..4; clipped to fit 226 KB)
  *   SGCN_TUNE_TMA_GRID      CTAs of variant 1 (default 148 = one per SM; 147 leaves one SM to a kernel

@@ -532,162 +532,22 @@ full_mean_kernel(const FullArgs a) {
 }
 
 // ---- full-neighbour history mean, bulk-copy (TMA engine) variant ---------------------------------
-// Same arithmetic as full_mean_kernel; different data movement.  The register variant above keeps
-// at most 16 row loads per warp in flight and pays its metadata staging per 64-position chunk, which
-// at Reddit shape (~100 positions per warp) leaves the kernel latency-bound at ~25 % of any memory
-// pipe (profiles/r01_full_mean_ncu.json).  Here one persistent CTA per SM
+// Same arithmetic as full_mean_kernel; different data movement (sgcn_tune_set SGCN_TUNE_FULL_VARIANT
+// = 1; NOT the default).  One persistent CTA per SM
 //   1. resolves (row, column, weight) of its WHOLE contiguous span of positions in one parallel
-//      pass by all threads (one global round trip instead of one per chunk),
+//      pass by all threads,
 //   2. then every warp walks its own contiguous slice of that span as a private ring of shared-
 //      memory stages filled by `cp.async.bulk` row copies (one 16-byte-aligned D*4-byte copy per
-//      history row, completion counted on an mbarrier): rows in flight cost no registers, so a CTA
-//      keeps its whole ring (up to ~190 KB) outstanding; the warp that drains a stage re-arms it
-//      itself (no producer warp, no empty barriers), reduces the rows from shared memory with
-//      warp-uniform (row, weight) broadcasts and leaves through one 128-bit RED per lane per row
-//      segment, exactly like the register variant.
-// ---- full-neighbour history mean, whole-span variant ----------------------------------------------
-// The register variant resolves metadata per warp per 64-position chunk: at Reddit shape a warp owns
-// ~100 positions, so it pays two dependent staging round trips (22 % of its stall samples,
-// profiles/r01_full_mean_ncu.json) during which none of its row loads are in flight.  Here the CTA
-// resolves (row, column, weight) of its whole contiguous span in ONE pass by all 256 threads (a
-// single round trip), then each warp streams its slice of the span with the same two-register-buffer
-// pipeline, reading per-edge operands from the CTA-wide shared-memory arrays.  Everything before the
-// first history-row load is independent of the previous step's write-back, so with programmatic
-// dependent launch (sgcn_tune_set SGCN_TUNE_PDL) that whole preamble overlaps the write-back kernel.
-constexpr int kSpanMeta = 1536;       // positions resolved per pass (24 KB of shared memory)
-constexpr int kSpanPad = 32;          // tail padding so that the stream loop needs no bounds logic
-
-template <typename V, int LPR, int VPL>
-__global__ void __maxnreg__(96)
-full_mean_span_kernel(const FullArgs a) {
-    using T = VT<V>;
-    TraceScope ts(a.trace, TR_FULL);
-    grid_dep_launch();
-    constexpr int G = 32 / LPR;
-    constexpr int UN = (VPL >= 8) ? 1 : ((VPL == 4) ? 2 : ((VPL == 2) ? 4 : 8));
-    constexpr int STEP = G * UN;
-    static_assert(STEP <= kSpanPad, "padding covers one group");
-    extern __shared__ int32_t s_dyn[];
-    int32_t* s_ptr = s_dyn;                                      // rowptr_f            [stage_rows + 1]
-    int32_t* s_base = s_dyn + a.stage_rows + 1;                  // adj_p[nodes[r]] - rowptr_f[r]
-    __shared__ int64_t m_off[kSpanMeta + kSpanPad];              // adj_i * ld_h (element offset of the row)
-    __shared__ float m_w[kSpanMeta + kSpanPad];
-    __shared__ int32_t m_row[kSpanMeta + kSpanPad];
-    const int n_out = dev_count(a.n_out_dev, a.n_out);
-    if (n_out <= 0) return;
-    const int tid = threadIdx.x;
-    for (int i = tid; i <= n_out; i += kAggThreads) s_ptr[i] = __ldg(a.rowptr_f + i);
-    for (int i = tid; i < n_out; i += kAggThreads)
-        s_base[i] = __ldg(a.adj_p + __ldg(a.nodes + i)) - __ldg(a.rowptr_f + i);
-    __syncthreads();
-    const int nnz = s_ptr[n_out];
-    const int span = max(32, (((nnz + (int)gridDim.x - 1) / (int)gridDim.x) + 31) & ~31);
-    const int p0 = blockIdx.x * span;
-    const int p1 = min(p0 + span, nnz);
-    if (p0 >= p1) return;
-    const int lane = tid & 31, wib = tid >> 5;
-    const int gl = lane % LPR, g = lane / LPR;
-    bool ok[VPL];
-    const float* hist_lane[VPL];
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-        const int off = (gl + k * LPR) * T::W;
-        ok[k] = off < a.D;
-        hist_lane[k] = a.hist + (ok[k] ? off : 0);
-    }
-    V acc[VPL];
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) acc[k] = T::zero();
-    int cur = -1;
-
-    for (int sc = p0; sc < p1; sc += kSpanMeta) {
-        const int cnt = min(kSpanMeta, p1 - sc);
-        const int cnt_pad = (cnt + STEP - 1) / STEP * STEP;
-        // ---- pass 1: the whole CTA resolves cnt positions (independent of the history table) ----
-        for (int i = tid; i < cnt_pad; i += kAggThreads) {
-            int r = -1;
-            int64_t off = 0;
-            float w = 0.f;
-            if (i < cnt) {
-                const int p = sc + i;
-                int lo = 0, hi = n_out;                          // last r with ptr[r] <= p
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_ptr[mid] <= p) lo = mid; else hi = mid;
-                }
-                const int q = s_base[lo] + p;
-                w = __ldg(a.adj_w + q);
-                if (a.square) w *= w;
-                off = (int64_t)__ldg(a.adj_i + q) * a.ld_h;
-                r = lo;
-            }
-            m_off[i] = off;
-            m_w[i] = w;
-            m_row[i] = r;
-        }
-        __syncthreads();
-        if (sc == p0) grid_dep_wait();                           // history rows: after the write-back
-        // ---- pass 2: each warp streams its slice (a whole number of groups) ----
-        const int per = (((cnt_pad + kFullWarps - 1) / kFullWarps) + STEP - 1) / STEP * STEP;
-        const int w0 = min(wib * per, cnt_pad);
-        const int ng = (min(w0 + per, cnt_pad) - w0) / STEP;
-        const int64_t* my_off = m_off + w0;
-        const float* my_w = m_w + w0;
-        const int32_t* my_r = m_row + w0;
-
-        auto issue = [&](V (&buf)[UN][VPL], int gi) {
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                const int64_t off = my_off[gi * STEP + u * G + g];
-#pragma unroll
-                for (int k = 0; k < VPL; ++k)
-                    buf[u][k] = ok[k] ? T::ld_stream(hist_lane[k] + off) : T::zero();
-            }
-        };
-        auto consume = [&](V (&buf)[UN][VPL], int gi) {
-            const int jf = gi * STEP + g;
-            const int rf = my_r[jf], rl = my_r[jf + (UN - 1) * G];
-            if (rf == rl && rf >= 0) {                           // whole group inside one output row
-                if (rf != cur) {
-                    if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
-                    cur = rf;
-                }
-#pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    const float w = my_w[jf + u * G];
-#pragma unroll
-                    for (int k = 0; k < VPL; ++k) T::fma(acc[k], w, buf[u][k]);
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    const int r = my_r[jf + u * G];
-                    if (r < 0) continue;
-                    if (r != cur) {
-                        if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
-                        cur = r;
-                    }
-                    const float w = my_w[jf + u * G];
-#pragma unroll
-                    for (int k = 0; k < VPL; ++k) T::fma(acc[k], w, buf[u][k]);
-                }
-            }
-        };
-        if (ng > 0) {
-            V bufA[UN][VPL], bufB[UN][VPL];
-            issue(bufA, 0);
-            for (int gi = 0; gi < ng; gi += 2) {
-                if (gi + 1 < ng) issue(bufB, gi + 1);
-                consume(bufA, gi);
-                if (gi + 2 < ng) issue(bufA, gi + 2);
-                if (gi + 1 < ng) consume(bufB, gi + 1);
-            }
-        }
-        if (sc + kSpanMeta < p1) __syncthreads();                // metadata is rewritten by the next pass
-    }
-    if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
-}
-
+//      history row, completion counted on an mbarrier): rows in flight cost no registers; the warp
+//      that drains a stage re-arms it itself (no producer warp, no empty barriers), reduces the rows
+//      from shared memory with warp-uniform (row, weight) broadcasts and leaves through one 128-bit
+//      RED per lane per row segment.
+// Measured at Reddit shape (profiles/r01_full_mean_variants_sweep.jsonl): best ring 16 warps x 16
+// rows x 1 stage = 25.3 us per launch against 22.4 us for the register variant, and the time falls
+// with the number of issuing warps (8 warps 37 us, 12 warps 29 us): a 512-byte row per UBLKCP is too
+// small a unit for the copy engine -- ptxas serialises the per-lane issues (ELECT + R2UR + UBLKCP per
+// row) and the engine's per-request cost, not bytes in flight, bounds the kernel.  Kept, memcheck-
+// clean and parity-tested, as the measured alternative; rows of >= 2 KB would be its regime.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -835,7 +695,7 @@ full_mean_tma_kernel(const FullArgs a, const FullTmaCfg cfg) {
 }
 
 // runtime tunables (sgcn_tune_set): which full-mean variant runs and the shape of its ring
-static int g_full_variant = 0;        // 0 = register variant, 1 = bulk-copy variant, 2 = whole-span variant
+static int g_full_variant = 0;        // 0 = register variant, 1 = bulk-copy variant
 static FullTmaCfg g_tma_cfg = {12, 16, 2};
 static int g_tma_grid = kNumSMs;      // CTAs (one per SM); 147 leaves an SM to a concurrently running sampler
 
@@ -1192,28 +1052,6 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
         SGCN_LAUNCHED();
         return SGCN_OK;
     }
-    if (g_full_variant == 2 && D <= sh.tile && n_out <= kFullStageRows) {
-        FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0, ld_y0, y1, ld_y1,
-                   nullptr, n_out, g_trace, square};
-        const size_t dyn = sizeof(int32_t) * (2 * (size_t)n_out + 2);
-#define CALL(V, L, P)                                                                        \
-    do {                                                                                     \
-        static int per_sm = 0;                                                               \
-        if (per_sm == 0) {                                                                   \
-            SGCN_CUDA(cudaFuncSetAttribute(full_mean_span_kernel<V, L, P>,                   \
-                                           cudaFuncAttributePreferredSharedMemoryCarveout, 44)); \
-            SGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                         \
-                &per_sm, full_mean_span_kernel<V, L, P>, kAggThreads,                        \
-                sizeof(int32_t) * (2 * (size_t)kFullStageRows + 2)));                        \
-            if (per_sm < 1) per_sm = 1;                                                      \
-        }                                                                                    \
-        SGCN_CUDA(launch_pdl(full_mean_span_kernel<V, L, P>, kNumSMs * per_sm, kAggThreads, dyn, st, a)); \
-    } while (0)
-        SGCN_DISPATCH_SHAPE(sh, CALL);
-#undef CALL
-        SGCN_LAUNCHED();
-        return SGCN_OK;
-    }
     for (int c0 = 0; c0 < D; c0 += sh.tile) {
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist + c0, ld_h,
                    std::min(sh.tile, D - c0), y0 + c0, ld_y0, y1 ? y1 + c0 : nullptr, ld_y1,
@@ -1247,7 +1085,7 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
 int sgcn_tune_set(int32_t key, int32_t value) {
     switch (key) {
         case SGCN_TUNE_FULL_VARIANT:
-            SGCN_REQUIRE(value >= 0 && value <= 2, "tune: full-mean variant is 0 (register), 1 (bulk copy) or 2 (whole span)");
+            SGCN_REQUIRE(value == 0 || value == 1, "tune: full-mean variant is 0 (register) or 1 (bulk copy)");
             g_full_variant = value; return SGCN_OK;
         case SGCN_TUNE_TMA_WARPS:
             SGCN_REQUIRE(value >= 1 && value <= kTmaMaxWarps, "tune: 1..16 warps");
