@@ -224,6 +224,50 @@ int sgcn_cvd_sampled_fwd(const int32_t* rowptr, const int32_t* cols, const float
                          float* self_h, int64_t ld_sh, float* self_mu, int64_t ld_sm,
                          int32_t accumulate, void* stream);
 
+/* Pre-processing product over the whole graph (gcn/utils.py:168-169,321-322: train_adj.dot(feats),
+ * full_adj.dot(feats); stacked beside the self features by gcn/models.py:235-239):
+ *   y[r, 0:D] = sum over the stored row r of adj_w[e] * x[adj_i[e], 0:D]        (y overwritten)
+ * CSR (adj_p[n_rows+1] starting at 0, adj_i, adj_w) and x, y are DEVICE pointers; x and y may be
+ * column blocks of wider matrices (ld_x, ld_y in floats), e.g. y = columns [602, 1204) of the
+ * [N, 1204] model input whose columns [0, 602) hold x.  tile_cols: columns per launch (0 = 128):
+ * the [N, tile] block of x is what has to stay L2-resident while the adjacency streams through.
+ * Synchronises the stream once (reads the edge count): this is a one-off pre-processing call. */
+int sgcn_csr_spmm(const int32_t* adj_p, const int32_t* adj_i, const float* adj_w, int32_t n_rows,
+                  const float* x, int64_t ld_x, int32_t D, float* y, int64_t ld_y, int32_t tile_cols,
+                  void* stream);
+
+/* ---- dense layers around the aggregate --------------------------------------
+ * The products X @ W are library GEMMs issued by the host; these are the row-wise pieces.
+ *
+ * MyLayerNorm / MyLayerNorm2 + activation (layers.py:87-97,130-138,404-412):
+ *   mean, var = moments over the row (biased);  y = act((x - mean) * rsqrt(var + eps) * scale + offset)
+ * scale / offset: [D] device vectors or NULL (ones / zeros); relu != 0 applies max(., 0).
+ * stats: optional [n, 2] device buffer (8-byte aligned) receiving {mean, rstd} for the backward. */
+int sgcn_ln_act_fwd(const float* x, int64_t ld_x, int32_t n, const int32_t* n_dev, int32_t D,
+                    const float* scale, const float* offset, float eps, int32_t relu, float* y,
+                    int64_t ld_y, float* stats, void* stream);
+/* gradient of the above: dx (optional) is overwritten; dscale / doffset (optional, [D]) are ADDED to. */
+int sgcn_ln_act_bwd(const float* x, int64_t ld_x, const float* y, int64_t ld_y, const float* dy,
+                    int64_t ld_dy, int32_t n, const int32_t* n_dev, int32_t D, const float* scale,
+                    const float* stats, int32_t relu, float* dx, int64_t ld_dx, float* dscale,
+                    float* doffset, void* stream);
+/* tf.nn.dropout(x, keep_prob) (layers.py:396,415-433): y = kept ? x / keep_prob : 0.  The mask is
+ * either injected (mask_in, one byte per element, row-major [n, D]) or drawn from Philox-4x32-10
+ * keyed by `seed` with the element index + `offset` as counter; mask_out (optional) receives it.
+ * TensorFlow's own random stream is not reproducible here (TF absent): parity uses injected masks. */
+int sgcn_dropout(const float* x, int64_t ld_x, int32_t n, const int32_t* n_dev, int32_t D, float keep_prob,
+                 uint64_t seed, uint64_t offset, const uint8_t* mask_in, uint8_t* mask_out, float* y,
+                 int64_t ld_y, void* stream);
+/* loss (models.py:76-83): *loss += mean over rows of softmax_cross_entropy_with_logits (sigmoid != 0:
+ * mean over all entries of sigmoid_cross_entropy_with_logits);  dlogits (optional) = its gradient. */
+int sgcn_xent(const float* logits, int64_t ld_l, const float* labels, int64_t ld_t, int32_t n, int32_t C,
+              int32_t sigmoid, float* loss, float* dlogits, int64_t ld_d, void* stream);
+/* tf.train.AdamOptimizer step (models.py:50-51,187) on one flat parameter: g' = g + weight_decay * p
+ * (the gradient of weight_decay * l2_loss(p), models.py:68-74), m, v updated in place,
+ * p -= lr_t * m / (sqrt(v) + eps) with lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) computed by the caller. */
+int sgcn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1,
+                   float beta2, float eps, float weight_decay, void* stream);
+
 /* Runtime tunables (process-wide, not thread-safe against concurrent launches).
  *   SGCN_TUNE_FULL_VARIANT  0 = register-pipelined full_mean_kernel (default, fastest measured),
  *                           1 = bulk-copy (cp.async.bulk + mbarrier ring) full_mean_tma_kernel

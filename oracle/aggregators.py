@@ -182,3 +182,13 @@ def history_update(history, ifield, new_rows):
     """tf.scatter_update(history, fields[l], new_history), gcn/models.py:160-166 (in place)."""
     history[np.asarray(ifield)] = new_rows
     return history
+
+
+def preprocess_features(adj_csr, feats, graphsage, dtype=np.float64):
+    """Model input of the PP models: the reference computes ``train_adj.dot(feats)`` with SciPy
+    (gcn/utils.py:168-169,321-322) and stacks ``[feats | adj.dot(feats)]`` (graphsage) or uses
+    ``adj.dot(feats)`` alone (gcn) -- gcn/models.py:230-239.  adj_csr: scipy.sparse.csr_matrix."""
+    nbr = adj_csr.astype(dtype).dot(np.asarray(feats, dtype=dtype))
+    if graphsage:
+        return np.hstack((np.asarray(feats, dtype=dtype), nbr))
+    return nbr

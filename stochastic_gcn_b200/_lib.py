@@ -58,6 +58,15 @@ SIGNATURES = {
     "sgcn_full_history_mean": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,
                                       _vp, _i64, _vp, _vp]),
     "sgcn_tune_set": (_i32, [_i32, _i32]),
+    "sgcn_ln_act_fwd": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, C.c_float, _i32, _vp, _i64, _vp, _vp]),
+    "sgcn_ln_act_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i64,
+                               _vp, _vp, _vp]),
+    "sgcn_dropout": (_i32, [_vp, _i64, _i32, _vp, _i32, C.c_float, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _i64,
+                            _vp]),
+    "sgcn_xent": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "sgcn_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                              _vp]),
+    "sgcn_csr_spmm": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _vp]),
     "sgcn_spmm_csr_sq": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp]),
     "sgcn_spmm_csr_bwd_sq": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _vp]),
     "sgcn_full_history_mean_sq": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,

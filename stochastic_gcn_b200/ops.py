@@ -236,3 +236,31 @@ def cvd_sampled_fwd_bwd(rowptr, cols, vals, tgt, scale, n_out, h, mu, hist, yh, 
         ptr(self_mu), _ld(self_mu) if self_mu is not None else 0, 1 if accumulate else 0,
         ptr(dy), _ld(dy), ptr(dx), _ld(dx), stream_ptr()))
     return yh, ymu
+
+
+def csr_spmm(indptr, indices, data, x, out=None, tile_cols=0):
+    """out = A @ x for a whole CSR matrix on the device (the reference's ``adj.dot(feats)``,
+    gcn/utils.py:168-169,321-322).  x / out may be column views of wider row-major matrices."""
+    _i32(indptr, "indptr"); _i32(indices, "indices"); _f32(data, "data", 1); _f32(x, "x")
+    n = indptr.numel() - 1
+    if out is None:
+        out = torch.empty((n, x.shape[1]), dtype=torch.float32, device=x.device)
+    _f32(out, "out")
+    if out.shape[0] != n or out.shape[1] != x.shape[1]:
+        raise ValueError("out must be [n_rows, x.shape[1]]")
+    check(_lib.load().sgcn_csr_spmm(ptr(indptr), ptr(indices), ptr(data), n, ptr(x), _ld(x), x.shape[1],
+                                    ptr(out), _ld(out), int(tile_cols), stream_ptr()))
+    return out
+
+
+def preprocess_features(indptr, indices, data, feats, normalization="graphsage", tile_cols=0):
+    """Model input of the PP ('preprocess') models: ``[feats | A @ feats]`` for graphsage normalisation,
+    ``A @ feats`` for gcn (gcn/models.py:230-239 with FLAGS.pp_nbr; gcn/utils.py:168-169,321-322)."""
+    _f32(feats, "feats")
+    n, f = feats.shape
+    if normalization == "gcn":
+        return csr_spmm(indptr, indices, data, feats, tile_cols=tile_cols)
+    out = torch.empty((n, 2 * f), dtype=torch.float32, device=feats.device)
+    out[:, :f].copy_(feats)
+    csr_spmm(indptr, indices, data, feats, out=out[:, f:], tile_cols=tile_cols)
+    return out
