@@ -56,7 +56,8 @@ def test_reference_model_gradients_by_finite_differences():
     ref, l0 = loss_of(ws)
     l0.backward()
     for wi, idx in ((0, (2, 3)), (2, (1,)), (3, (4, 1))):
-        w2 = [w.copy() for w in ws]
-        w2[wi][idx] += 1e-6
-        fd = (float(loss_of(w2)[1].detach()) - float(l0.detach())) / 1e-6
-        assert abs(fd - float(ref.w[wi].grad[idx])) < 1e-5 * max(1.0, abs(fd))
+        wp, wm = [w.copy() for w in ws], [w.copy() for w in ws]
+        wp[wi][idx] += 1e-5
+        wm[wi][idx] -= 1e-5
+        fd = (float(loss_of(wp)[1].detach()) - float(loss_of(wm)[1].detach())) / 2e-5      # central difference
+        assert abs(fd - float(ref.w[wi].grad[idx])) < 1e-6 * max(1.0, abs(fd))
