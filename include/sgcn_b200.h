@@ -368,6 +368,17 @@ int sgcn_wb_push(const int32_t* field, const int32_t* n_dev, int32_t n_bound, co
                  int32_t n_dst, void* const* peer_flags /*HOST*/, int32_t my_rank, int32_t* epoch,
                  int32_t* block_counter /*device scratch int32 = 0, or NULL: signal from a 2nd launch*/,
                  void* stream);
+/* Fuse the next write-back push into the next sampled-aggregate launch: the arguments of sgcn_wb_push
+ * are remembered (per host thread) and the NEXT sgcn_cv_sampled_fwd[_bwd] / sgcn_cvd_sampled_fwd[_bwd]
+ * call on this thread carries the push as extra thread blocks of its own kernel -- both only need the
+ * gathered input rows, and every launch that leaves the step's side branch costs a dependent-launch
+ * latency while the full-neighbour mean saturates the GPU.  block_counter is required (the last push
+ * block publishes the epoch).  Same effect on memory as sgcn_wb_push issued on that call's stream. */
+int sgcn_wb_push_attach(const int32_t* field, const int32_t* n_dev, int32_t n_bound, const float* rows,
+                        int64_t ld_rows, int32_t D, void* const* dst_even, void* const* dst_odd,
+                        int32_t n_dst, void* const* peer_flags, int32_t my_rank, int32_t* epoch,
+                        int32_t* block_counter);
+
 /* wait_apply: spins (bounded, ~2 s: sets *timeout_flag != 0 instead of hanging) until this rank's
  * flags[0..world) >= *epoch, then merges the `world` payloads of the epoch's receive area */
 int sgcn_wb_wait_apply(float* hist, int64_t ld_h, int32_t D, const void* recv_even, const void* recv_odd,

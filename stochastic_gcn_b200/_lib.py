@@ -102,6 +102,8 @@ SIGNATURES = {
     "sgcn_wb_pack": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), _i32, _i32, _vp]),
     "sgcn_wb_push": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), C.POINTER(_vp), _i32,
                             C.POINTER(_vp), _i32, _vp, _vp, _vp]),
+    "sgcn_wb_push_attach": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), C.POINTER(_vp), _i32,
+                                   C.POINTER(_vp), _i32, _vp, _vp]),
     "sgcn_wb_wait_apply": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgcn_wb_apply": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp]),
     "sgcn_ipc_alloc": (_i32, [C.POINTER(_vp), _i64, _i32]),

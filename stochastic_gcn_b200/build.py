@@ -13,7 +13,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsgcn_b200.so")
 SOURCES = ["api.cu", "rows.cu", "aggregate.cu", "sampler.cu", "exchange.cu", "step.cu", "precompute.cu", "dense.cu"]
-HEADERS = ["common.cuh", "scan.cuh", "mt19937.cuh"]
+HEADERS = ["common.cuh", "scan.cuh", "mt19937.cuh", "exchange.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

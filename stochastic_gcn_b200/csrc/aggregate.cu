@@ -11,6 +11,7 @@
 //
 // All kernels are HBM-bound (0.5 flop/B): no tensor cores here by design.
 #include "common.cuh"
+#include "exchange.cuh"
 
 namespace sgcn {
 
@@ -109,6 +110,9 @@ struct SampledArgs {
     unsigned long long* trace;
     // optional fused backward of the same sampled adjacency: dx[cols[e]] += vals[e] * bscale[r] * dy[r]
     const float* dy; int64_t ld_dy; float* dx; int64_t ld_dx; const float* bscale;
+    // optional: the multi-GPU write-back push rides on this launch as the blocks with blockIdx.y == 1
+    // (both only need the gathered input rows; one launch instead of two on the step's side branch)
+    int has_push; WbPushArgs push;
 };
 
 template <typename V, int LPR, int VPL, int MODE>
@@ -117,6 +121,10 @@ sampled_rows_kernel(const SampledArgs a) {
     using T = VT<V>;
     TraceScope ts(a.trace, TR_SAMPLED);
     grid_dep_wait();      // (PDL) launched early behind the gather that writes x: nothing to do before it
+    if (a.has_push && blockIdx.y == 1) {
+        wb_pack_body(a.push, blockIdx.x, gridDim.x);
+        return;
+    }
     const int n_out = dev_count(a.n_out_dev, a.n_out);
     const int gl = threadIdx.x % LPR;                      // lane within the group
     const int groups = (gridDim.x * kAggThreads) / LPR;
@@ -734,6 +742,9 @@ static int grid_for_groups(int64_t n_groups, int lpr) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, kNumSMs * 8));
 }
 
+struct PendingPush { bool valid = false; WbPushArgs args; };
+static thread_local PendingPush t_pending_push;
+
 template <int MODE>
 static int launch_sampled(SampledArgs a, int D, bool vec_ok, cudaStream_t st) {
     if (a.n_out <= 0 || D <= 0) return SGCN_OK;
@@ -751,11 +762,19 @@ static int launch_sampled(SampledArgs a, int D, bool vec_ok, cudaStream_t st) {
         if (a.self0) t.self0 = a.self0 + c0;
         if (a.self1) t.self1 = a.self1 + c0;
         if (a.dx) { t.dy = a.dy + c0; t.dx = a.dx + c0; }
-        const int grid = grid_for_groups(a.n_out, sh.lpr);
+        int gx = grid_for_groups(a.n_out, sh.lpr);
+        t.has_push = 0;
+        if (c0 == 0 && t_pending_push.valid) {            // see sgcn_wb_push_attach
+            t.has_push = 1;
+            t.push = t_pending_push.args;
+            t_pending_push.valid = false;
+            gx = std::max(gx, 64);
+        }
+        const dim3 grid(gx, t.has_push ? 2 : 1);
 #define CALL(V, L, P)                                                       \
     do {                                                                    \
         SGCN_MATCH_CARVEOUT((sampled_rows_kernel<V, L, P, MODE>));          \
-        SGCN_CUDA(launch_pdl(sampled_rows_kernel<V, L, P, MODE>, dim3(grid), dim3(kAggThreads), 0, st, t)); \
+        SGCN_CUDA(launch_pdl(sampled_rows_kernel<V, L, P, MODE>, grid, dim3(kAggThreads), 0, st, t)); \
     } while (0)
         SGCN_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
@@ -1122,6 +1141,31 @@ int sgcn_full_history_mean_sq(const int32_t* nodes, const int32_t* rowptr_f, int
                               int32_t* work_counter, void* stream) {
     return full_history_mean_impl(nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0,
                                   ld_y0, y1, ld_y1, work_counter, 1, stream);
+}
+
+int sgcn_wb_push_attach(const int32_t* field, const int32_t* n_dev, int32_t n_bound, const float* rows,
+                        int64_t ld_rows, int32_t D, void* const* dst_even, void* const* dst_odd,
+                        int32_t n_dst, void* const* peer_flags, int32_t my_rank, int32_t* epoch,
+                        int32_t* block_counter) {
+    SGCN_REQUIRE(field && n_dev && rows && dst_even && dst_odd && peer_flags && epoch && block_counter,
+                 "wb_push_attach: null pointer");
+    SGCN_REQUIRE(n_bound >= 0 && D > 0 && ld_rows >= D, "wb_push_attach: bad size");
+    SGCN_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers && my_rank >= 0 && my_rank < kMaxPeers,
+                 "wb_push_attach: 1..16 ranks");
+    WbPushArgs a{};
+    a.field = field; a.n_dev = n_dev; a.n_bound = n_bound; a.rows = rows; a.ld_rows = ld_rows; a.D = D;
+    for (int k = 0; k < n_dst; ++k) {
+        SGCN_REQUIRE(dst_even[k] && dst_odd[k] && peer_flags[k], "wb_push_attach: null peer pointer");
+        SGCN_REQUIRE((((uintptr_t)dst_even[k]) & 15) == 0 && (((uintptr_t)dst_odd[k]) & 15) == 0,
+                     "wb_push_attach: receive slots must be 16-byte aligned");
+        a.dst_even.p[k] = (char*)dst_even[k];
+        a.dst_odd.p[k] = (char*)dst_odd[k];
+        a.flags.p[k] = (char*)peer_flags[k];
+    }
+    a.n_dst = n_dst; a.step = 0; a.epoch = epoch; a.my_rank = my_rank; a.block_counter = block_counter;
+    t_pending_push.args = a;
+    t_pending_push.valid = true;
+    return SGCN_OK;
 }
 
 }  // extern "C"

@@ -22,7 +22,9 @@ extern std::atomic<int64_t> g_launches;
 // (globaltimer ns) of kernel class `id`; NULL = tracing off (sgcn_trace_set)
 extern unsigned long long* g_trace;
 enum { TR_SAMPLER = 0, TR_FULL = 1, TR_GATHER = 2, TR_SAMPLED = 3, TR_BWD = 4, TR_UPDATE = 5, TR_PAD = 6,
-       TR_EXCHANGE = 7, TR_CLASSES = 8 };
+       TR_EXCHANGE = 7, TR_CLASSES = 8,
+       // event-log only (no min / max slots): the three kernels of the multi-GPU write-back exchange
+       TR_WB_PUSH = 8, TR_WB_CLAIM = 9, TR_WB_COPY = 10 };
 
 inline int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     char buf[512];
@@ -142,14 +144,14 @@ struct TraceScope {
     __device__ __forceinline__ TraceScope(unsigned long long* trace, int id_) : t(trace), id(id_) {
         if (t && threadIdx.x == 0) {
             const unsigned long long now = global_ns();
-            atomicMin(t + 2 * id, now);
+            if (id < TR_CLASSES) atomicMin(t + 2 * id, now);
             log(0, now);
         }
     }
     __device__ __forceinline__ ~TraceScope() {
         if (t && threadIdx.x == 0) {
             const unsigned long long now = global_ns();
-            atomicMax(t + 2 * id + 1, now);
+            if (id < TR_CLASSES) atomicMax(t + 2 * id + 1, now);
             log(1, now);
         }
     }

@@ -14,80 +14,15 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "exchange.cuh"
 
 namespace sgcn {
 
-constexpr int kWbHeaderInts = 4;   // {count, step, 0, 0}: keeps ids 16-byte aligned
-
-__host__ __device__ inline int64_t wb_ids_offset() { return kWbHeaderInts * 4; }
-__host__ __device__ inline int64_t wb_rows_offset(int n_bound) {
-    return wb_ids_offset() + (((int64_t)n_bound * 4 + 15) & ~int64_t(15));
-}
-__host__ __device__ inline int64_t wb_payload_bytes(int n_bound, int D) {
-    return (wb_rows_offset(n_bound) + (int64_t)n_bound * D * 4 + 255) & ~int64_t(255);
-}
-
-constexpr int kMaxPeers = 16;
-struct PeerPtrs { char* p[kMaxPeers]; };
-
 // pack {count, ids, rows} into up to `n_dst` destinations (own buffer and/or peers' receive slots)
 __global__ void __launch_bounds__(256)
-wb_pack_kernel(const int32_t* __restrict__ field, const int32_t* __restrict__ n_dev, int n_bound,
-               const float* __restrict__ rows, int64_t ld_rows, int D, PeerPtrs dst_even, PeerPtrs dst_odd,
-               int n_dst, int step, int32_t* epoch, PeerPtrs flags, int my_rank,
-               int32_t* block_counter) {
-    // peer transport: this push belongs to epoch *epoch + 1 and lands in the slot set of its parity
-    if (epoch) step = *epoch + 1;
-    const PeerPtrs& dst = (epoch && (step & 1)) ? dst_odd : dst_even;
-    const int n = min(*n_dev, n_bound);
-    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t ids_off = wb_ids_offset(), rows_off = wb_rows_offset(n_bound);
-    if (t0 == 0)
-        for (int k = 0; k < n_dst; ++k) {
-            int32_t* h = (int32_t*)dst.p[k];
-            h[0] = n; h[1] = step; h[2] = 0; h[3] = 0;
-        }
-    for (int64_t i = t0; i < n; i += stride) {
-        const int32_t id = field[i];
-        for (int k = 0; k < n_dst; ++k) ((int32_t*)(dst.p[k] + ids_off))[i] = id;
-    }
-    if ((D & 3) == 0 && (ld_rows & 3) == 0 && (((uintptr_t)rows) & 15) == 0) {
-        const int d4 = D >> 2;
-        const int64_t total = (int64_t)n * d4;
-        for (int64_t t = t0; t < total; t += stride) {
-            const int64_t r = t / d4;
-            const int c = (int)(t - r * d4) * 4;
-            const float4 v = ldg_stream4(rows + r * ld_rows + c);
-            for (int k = 0; k < n_dst; ++k) *(float4*)(dst.p[k] + rows_off + (r * D + c) * 4) = v;
-        }
-    } else {
-        const int64_t total = (int64_t)n * D;
-        for (int64_t t = t0; t < total; t += stride) {
-            const int64_t r = t / D;
-            const int c = (int)(t - r * D);
-            const float v = rows[r * ld_rows + c];
-            for (int k = 0; k < n_dst; ++k) *(float*)(dst.p[k] + rows_off + (r * D + c) * 4) = v;
-        }
-    }
-    if (block_counter) {
-        // fused signal: the last block to finish advances the epoch and publishes it to every rank
-        __shared__ int s_last;
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(block_counter, 1) == (int)gridDim.x - 1;
-        __syncthreads();
-        if (s_last && threadIdx.x == 0) {
-            *block_counter = 0;
-            *epoch = step;
-            __threadfence_system();
-            for (int k = 0; k < n_dst; ++k) {
-                volatile int32_t* f = (volatile int32_t*)flags.p[k];
-                f[my_rank] = step;
-            }
-            __threadfence_system();
-        }
-    }
+wb_pack_kernel(const WbPushArgs a, unsigned long long* trace) {
+    TraceScope ts(trace, TR_WB_PUSH);
+    wb_pack_body(a, blockIdx.x, gridDim.x);
 }
 
 // after every CTA of the pack has finished: advance the local epoch and publish it as
@@ -127,10 +62,14 @@ __global__ void __launch_bounds__(256)
 wb_claim_kernel(const char* g_even, const char* g_odd,
                 const int32_t* __restrict__ epoch, int64_t slot_bytes, int world, int n_bound,
                 int32_t* __restrict__ owner, const int32_t* flags, int32_t* timeout_flag,
-                long long max_spins, int32_t* done_counter) {
-    // optional: count this launch as "everything stream-ordered before it has finished" (see
-    // sgcn_history_update: the pipelined step's consumer mark)
-    if (done_counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(done_counter, 1);
+                long long max_spins, int32_t* done_counter, unsigned long long* trace) {
+    TraceScope ts(trace, TR_WB_CLAIM);
+    // (PDL) this kernel is launched while its stream predecessor -- the full-neighbour mean -- is still
+    // running: waiting for the peers' payloads and the claim pass touch nothing the mean reads, so they
+    // overlap it; the dependent copy kernel may become resident right away
+    asm volatile("griddepcontrol.launch_dependents;");
+    // without flags (NCCL transport) the payloads come from the stream predecessor itself: order first
+    if (!flags) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (flags) {
         // peer transport: every block first waits (bounded) until all ranks have published this epoch
         if (threadIdx.x < world) {
@@ -157,6 +96,12 @@ wb_claim_kernel(const char* g_even, const char* g_odd,
     const int32_t* ids = (const int32_t*)(slot + wb_ids_offset());
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
         atomicMax(owner + __ldcg(ids + j), r * n_bound + j);
+    // (PDL) completion of this grid must imply completion of the predecessor (the copy kernel orders
+    // its history writes behind THIS grid only): wait for it here, after the independent work
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // optional: count this launch as "everything stream-ordered before it has finished" (see
+    // sgcn_history_update: the pipelined step's consumer mark)
+    if (done_counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(done_counter, 1);
 }
 
 // copy: the winning (rank, position) of each node writes its whole row, then releases the claim
@@ -164,7 +109,11 @@ template <bool VEC>
 __global__ void __launch_bounds__(256)
 wb_copy_kernel(const char* g_even, const char* g_odd,
                const int32_t* __restrict__ epoch, int64_t slot_bytes, int world, int n_bound,
-               int32_t* __restrict__ owner, float* __restrict__ hist, int64_t ld_h, int D) {
+               int32_t* __restrict__ owner, float* __restrict__ hist, int64_t ld_h, int D,
+               unsigned long long* trace) {
+    TraceScope ts(trace, TR_WB_COPY);
+    asm volatile("griddepcontrol.launch_dependents;");     // (PDL) the next full-neighbour mean's preamble
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // (PDL) claims final, history no longer read
     const int r = blockIdx.y;
     const char* gathered = (epoch && (*epoch & 1)) ? g_odd : g_even;
     const char* slot = gathered + (int64_t)r * slot_bytes;
@@ -172,19 +121,35 @@ wb_copy_kernel(const char* g_even, const char* g_odd,
     const int32_t* ids = (const int32_t*)(slot + wb_ids_offset());
     const float* rows = (const float*)(slot + wb_rows_offset(n_bound));
     constexpr int W = VEC ? 4 : 1;
+    constexpr int R = 4;                                          // rows a warp moves per round trip
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
-        const int node = __ldcg(ids + j);
-        const bool mine = owner[node] == r * n_bound + j;         // uniform across the warp
-        if (mine) {
-            for (int c = lane * W; c < D; c += 32 * W) {
-                if (VEC) *(float4*)(hist + (int64_t)node * ld_h + c) = __ldcg((const float4*)(rows + (int64_t)j * D + c));
-                else hist[(int64_t)node * ld_h + c] = __ldcg(rows + (int64_t)j * D + c);
+    for (int j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R; j0 < n; j0 += warps * R) {
+        int node[R];
+        bool mine[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) node[q] = j0 + q < n ? __ldcg(ids + j0 + q) : -1;
+#pragma unroll
+        for (int q = 0; q < R; ++q) mine[q] = node[q] >= 0 && owner[node[q]] == r * n_bound + j0 + q;   // warp-uniform
+        for (int c = lane * W; c < D; c += 32 * W) {
+            if (VEC) {
+                float4 v[R];
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (mine[q]) v[q] = __ldcg((const float4*)(rows + (int64_t)(j0 + q) * D + c));
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (mine[q]) *(float4*)(hist + (int64_t)node[q] * ld_h + c) = v[q];
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (mine[q]) hist[(int64_t)node[q] * ld_h + c] = __ldcg(rows + (int64_t)(j0 + q) * D + c);
             }
         }
         __syncwarp();
-        if (mine && lane == 0) owner[node] = -1;                  // losers only ever compare for equality
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+            if (mine[q] && lane == 0) owner[node[q]] = -1;        // losers only ever compare for equality
     }
 }
 
@@ -224,8 +189,8 @@ int sgcn_wb_pack(const int32_t* field, const int32_t* n_dev, int32_t n_bound, co
     PeerPtrs p{};
     int rc = fill_ptrs(p, dst, n_dst, "wb_pack");
     if (rc != SGCN_OK) return rc;
-    wb_pack_kernel<<<pack_blocks(n_bound, D), 256, 0, (cudaStream_t)stream>>>(
-        field, n_dev, n_bound, rows, ld_rows, D, p, p, n_dst, step, nullptr, p, 0, nullptr);
+    WbPushArgs a{field, n_dev, n_bound, rows, ld_rows, D, p, p, n_dst, step, nullptr, p, 0, nullptr};
+    wb_pack_kernel<<<pack_blocks(n_bound, D), 256, 0, (cudaStream_t)stream>>>(a, g_trace);
     SGCN_LAUNCHED();
     return SGCN_OK;
 }
@@ -243,8 +208,8 @@ int sgcn_wb_push(const int32_t* field, const int32_t* n_dev, int32_t n_bound, co
     if (rc == SGCN_OK) rc = fill_ptrs(pf, peer_flags, n_dst, "wb_push");
     if (rc != SGCN_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    wb_pack_kernel<<<pack_blocks(n_bound, D), 256, 0, st>>>(field, n_dev, n_bound, rows, ld_rows, D, pe, po,
-                                                           n_dst, 0, epoch, pf, my_rank, block_counter);
+    WbPushArgs a{field, n_dev, n_bound, rows, ld_rows, D, pe, po, n_dst, 0, epoch, pf, my_rank, block_counter};
+    wb_pack_kernel<<<pack_blocks(n_bound, D), 256, 0, st>>>(a, g_trace);
     SGCN_LAUNCHED();
     if (!block_counter) {      // no scratch counter given: publish from a second, stream-ordered launch
         wb_signal_kernel<<<1, 32, 0, st>>>(pf, n_dst, my_rank, epoch);
@@ -259,18 +224,20 @@ static int launch_apply(float* hist, int64_t ld_h, int32_t D, const void* g_even
                         int32_t* timeout_flag = nullptr, int32_t* done_counter = nullptr) {
     dim3 g1(std::min(div_up(std::max(n_bound, 1), 256), 64), world);
     // ~2 s at 100 ns per spin: a peer that never arrives raises the flag instead of hanging the GPU
-    wb_claim_kernel<<<g1, 256, 0, st>>>((const char*)g_even, (const char*)g_odd, epoch, slot_bytes, world,
-                                        n_bound, owner, flags, timeout_flag, 20000000LL, done_counter);
+    SGCN_CUDA(launch_pdl(wb_claim_kernel, g1, dim3(256), 0, st, (const char*)g_even, (const char*)g_odd, epoch,
+                         slot_bytes, world, n_bound, owner, flags, timeout_flag, 20000000LL, done_counter, g_trace));
     SGCN_LAUNCHED();
-    dim3 g2(std::min(div_up(std::max(n_bound, 1), 8), kNumSMs), world);
+    // few CTAs: with PDL they sit resident beside the full-neighbour mean, and the next batch's sampler
+    // CTA still has to find an SM with registers to spare
+    dim3 g2(std::max(1, std::min(div_up(std::max(n_bound, 1), 32), 96 / std::max(world, 1))), world);
     const bool vec = D % 4 == 0 && ld_h % 4 == 0 && (((uintptr_t)hist) & 15) == 0 && slot_bytes % 16 == 0 &&
                      (((uintptr_t)g_even) & 15) == 0 && (((uintptr_t)g_odd) & 15) == 0;
     if (vec)
-        wb_copy_kernel<true><<<g2, 256, 0, st>>>((const char*)g_even, (const char*)g_odd, epoch, slot_bytes,
-                                                 world, n_bound, owner, hist, ld_h, D);
+        SGCN_CUDA(launch_pdl(wb_copy_kernel<true>, g2, dim3(256), 0, st, (const char*)g_even, (const char*)g_odd,
+                             epoch, slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace));
     else
-        wb_copy_kernel<false><<<g2, 256, 0, st>>>((const char*)g_even, (const char*)g_odd, epoch, slot_bytes,
-                                                  world, n_bound, owner, hist, ld_h, D);
+        SGCN_CUDA(launch_pdl(wb_copy_kernel<false>, g2, dim3(256), 0, st, (const char*)g_even, (const char*)g_odd,
+                             epoch, slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace));
     SGCN_LAUNCHED();
     return SGCN_OK;
 }

@@ -22,6 +22,7 @@ R reference processes sharing one table with synchronous steps (every rank reads
 table; write-backs are applied in rank order, the highest rank winning a contended row).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -149,6 +150,10 @@ class ShardedHotPathStep(HotPathStep):
         self._exchange = None
         if self.mode == "ns":
             return     # plain neighbour sampling keeps no history: shards are independent
+        # peer transport: the push is carried by the sampled-aggregate launch (sgcn_wb_push_attach) unless
+        # SGCN_FUSE_PUSH=0, in which case -- as for NCCL's pack -- it runs on a branch of its own
+        self._fuse_push = transport == "peer" and os.environ.get("SGCN_FUSE_PUSH", "1") != "0"
+        self._publish_stream = None if self._fuse_push else torch.cuda.Stream(device=self.dev)
         lib = _lib.load()
         nb = self.sampler_n_in_bound()
         self.slot_bytes = int(lib.sgcn_wb_payload_bytes(nb, self.hidden))
@@ -178,6 +183,14 @@ class ShardedHotPathStep(HotPathStep):
         else:
             check(lib.sgcn_wb_pack(ptr(v["field"]), ptr(v["n_in_dev"]), self.wb_bound, ptr(new_hist), ld, D,
                                    self._send_ptr, 1, 0, stream_ptr()))
+
+    def _attach_write_back_push(self, v, new_hist):
+        if not self._fuse_push:
+            return
+        x = self._exchange
+        check(_lib.load().sgcn_wb_push_attach(ptr(v["field"]), ptr(v["n_in_dev"]), self.wb_bound, ptr(new_hist),
+                                              new_hist.stride(0), self.hidden, x.dst_even, x.dst_odd, self.world,
+                                              x.peer_flags, self.rank, x.epoch, x.block_counter))
 
     def _write_back(self, v, new_hist, done_counter=None):
         """Main chain, after every forward read of history: merge all ranks' payloads."""

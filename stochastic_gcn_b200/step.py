@@ -83,6 +83,7 @@ class HotPathStep:
         self._s_b = torch.cuda.Stream(device=self.dev)      # side branch of the pass
         self._s_samp = torch.cuda.Stream(device=self.dev)   # sampler branch of the pipelined graphs
         self._s_chain = torch.cuda.Stream(device=self.dev)  # main chain of the pipelined graphs
+        self._publish_stream = None                         # sharded steps: branch of the early write-back push
 
     @property
     def out(self):
@@ -180,8 +181,20 @@ class HotPathStep:
                 ops.copy_rows_pad(None, 0, nxt[2])
             x = self.x0[:, :H]
             new_hist = None
-            if cv:      # the rows that will be written back exist now: a sharded step publishes them early
-                self._publish_write_back(v, x if self.mode == "cv" else self.x0[:, H:2 * H])
+            ev_pub = None
+            if cv and self._publish_stream is not None:
+                # the rows that will be written back exist now: a sharded step publishes them to its peers
+                # on a branch of its own, beside the sampled aggregate (the peers need the payload by the
+                # end of THEIR full-neighbour mean; the local write-back joins this branch)
+                ev_g = torch.cuda.Event()
+                ev_g.record(side)
+                with torch.cuda.stream(self._publish_stream):
+                    self._publish_stream.wait_event(ev_g)
+                    self._publish_write_back(v, x if self.mode == "cv" else self.x0[:, H:2 * H])
+                    ev_pub = torch.cuda.Event()
+                    ev_pub.record(self._publish_stream)
+            if cv:      # sharded + peer transport: the push rides on the sampled launch below (host-side only)
+                self._attach_write_back_push(v, x if self.mode == "cv" else self.x0[:, H:2 * H])
             if self.mode == "ns":
                 ops.spmm_csr(v["rowptr_s"], v["edg_t"], v["edg_w"], x, B, out=nb, n_out_dev=v["n_out_dev"])
                 if self.concat:
@@ -201,6 +214,8 @@ class HotPathStep:
             ev_fwd.record(side)
 
         main.wait_event(ev_fwd)                  # every forward read of history precedes the write-back
+        if ev_pub is not None:
+            main.wait_event(ev_pub)
         marked = False
         if new_hist is not None:                 # (models.py:186-194)
             marked = self._write_back(v, new_hist, self._pipe_done if pipelined else None)
@@ -219,6 +234,9 @@ class HotPathStep:
 
     def _publish_write_back(self, v, new_hist):
         """Hook, on the side branch right after the gather: nothing to do on one GPU."""
+
+    def _attach_write_back_push(self, v, new_hist):
+        """Hook, right before the sampled-aggregate launch: nothing to do on one GPU."""
 
     def _write_back(self, v, new_hist, done_counter=None):
         """tf.scatter_update(history, fields[0], new_history); the sharded subclass exchanges instead.
