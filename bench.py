@@ -251,6 +251,14 @@ def run_reference(args, w):
     emit(line)
 
 
+def pick_steps_per_graph(k, cap):
+    """Chunk length (even, <= cap) for K timed steps: whole chunks replay as CUDA graphs, the K mod S
+    left-over steps run eagerly, so S trades graph-to-graph gaps (~8 us each) against eager steps
+    (~40 us extra each) -- S = cap for long runs, a divisor of K (or K - 1) for short ones."""
+    cap = max(2, min(int(cap), int(k)) // 2 * 2)
+    return min(range(cap, 1, -2), key=lambda s: (k // s) * 8 + (k % s) * 40)
+
+
 def workload_config(args, w, extra):
     c = {"workload": "%s: synthetic %s-shaped graph, %s+PP degree %d, batch %d/GPU, hidden %d, PP input %d-d"
                      % (args.workload, w["shape"], w["mode"].upper(), w["degree"], w["batch"], w["hidden"], w["feat"]),
@@ -305,6 +313,7 @@ def run_ours(args, w):
         torch.cuda.synchronize(dev)
 
     timed = batches[args.warmup:]
+    args.steps_per_graph = pick_steps_per_graph(args.steps, args.steps_per_graph)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -491,7 +500,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="time one graph per step, no sampler lookahead")
-    ap.add_argument("--steps-per-graph", type=int, default=16)
+    ap.add_argument("--steps-per-graph", type=int, default=16,
+                    help="upper bound on the steps captured per CUDA graph (the largest even divisor of --steps "
+                         "below it is used)")
     ap.add_argument("--driver", default="graph", choices=["native", "graph"],
                     help="pipelined schedule: multi-step CUDA graphs (default) or native C++ stream launches")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
