@@ -256,6 +256,31 @@ class Dropout(Layer):
         return dropout(inputs, self.keep_prob, self.mask, self.dropout_state)
 
 
+# ---- data-parallel gradient exchange --------------------------------------------------------------------
+def allreduce_gradients(params, group=None):
+    """the dense weights are replicated on every rank of a row-range sharded run; their
+    gradients (<= 1204x128 + 256x128 + 128x41 floats ~ 0.8 MB at Reddit shape) are AVERAGED over the ranks
+    -- every rank's loss is a mean over its own equally sized batch, so the average is the gradient of the
+    mean over the global batch -- in ONE flattened all-reduce (NCCL on GPUs; any torch.distributed backend).
+    A parameter that got no gradient on some rank contributes zeros there.  No-op without a process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    params = list(params)
+    grads = [p.data.grad if p.data.grad is not None else torch.zeros_like(p.data) for p in params]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= world
+    off = 0
+    for p, g in zip(params, grads):
+        n = g.numel()
+        p.data.grad = flat[off:off + n].view_as(g).clone()
+        off += n
+
+
 # ---- optimiser ------------------------------------------------------------------------------------------
 class Adam:
     """tf.train.AdamOptimizer(learning_rate, beta1, beta2) (gcn/models.py:50-51): epsilon = 1e-8 outside
@@ -269,7 +294,9 @@ class Adam:
         for p in self.params:
             p.data.grad = None
 
-    def step(self):
+    def step(self, group=None):
+        """One update; in a multi-process run the gradients are averaged over ``group`` first."""
+        allreduce_gradients(self.params, group)
         self.t += 1
         lr_t = self.lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
         lib = _lib.load()

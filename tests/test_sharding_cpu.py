@@ -105,3 +105,40 @@ def test_unpack_round_trip():
     rows = rng.randn(13, 20).astype(np.float32)
     i2, r2 = unpack_payload(make_payload(ids, rows, 32, 20), 32, 20)
     assert np.array_equal(i2, ids) and np.array_equal(r2, rows)
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from stochastic_gcn_b200 import nn
+
+    class P:                                        # the two fields allreduce_gradients touches
+        def __init__(self, shape, seed):
+            self.data = torch.zeros(shape, requires_grad=True)
+            self.data.grad = torch.from_numpy(np.random.RandomState(seed).randn(*shape).astype(np.float32))
+
+    params = [P((7, 5), 100 + rank), P((5,), 200 + rank), P((3, 2), 300 + rank)]
+    if rank == 1:
+        params[1].data.grad = None                 # no gradient on this rank: counts as zeros
+    nn.allreduce_gradients(params)
+    ret[rank] = [p.data.grad.numpy().copy() for p in params]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dense_gradient_allreduce_two_gloo_ranks():
+    """replicated dense weights, gradients averaged over the ranks in one flat all-reduce"""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    world = 2
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
+        g0, g1 = ret[0], ret[1]
+    shapes, seeds = [(7, 5), (5,), (3, 2)], [100, 200, 300]
+    for k, (shape, seed) in enumerate(zip(shapes, seeds)):
+        a = np.random.RandomState(seed).randn(*shape).astype(np.float32)
+        b = np.random.RandomState(seed + 1).randn(*shape).astype(np.float32)
+        if k == 1:
+            b = np.zeros(shape, np.float32)
+        want = (a + b) / 2
+        assert np.allclose(g0[k], want, atol=1e-7) and np.array_equal(g0[k], g1[k])
