@@ -100,6 +100,7 @@ def ref_lib():
         lib.ref_sched_seed.argtypes = [C.c_void_p, C.c_int]
         lib.ref_sched_start_batch.argtypes = [C.c_void_p, C.c_int, _i32p]
         lib.ref_sched_expand.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_sched_expand.restype = C.c_int
         lib.ref_sched_int_vec.argtypes = [C.c_void_p, C.c_int, C.POINTER(_i32p)]
         lib.ref_sched_float_vec.argtypes = [C.c_void_p, C.c_int, C.POINTER(_f32p)]
         lib.ref_mult_create.restype = C.c_void_p
@@ -198,8 +199,7 @@ class RefSampler(_SamplerBase):
         self._lib.ref_sched_start_batch(self._h, len(ids), _ip(ids))
 
     def expand(self, degree):
-        self._lib.ref_sched_expand(self._h, int(degree))
-        return 0
+        return int(self._lib.ref_sched_expand(self._h, int(degree)))
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -26,7 +26,18 @@ void ref_sched_seed(void* h, int seed) { static_cast<Scheduler*>(h)->seed(seed);
 void ref_sched_start_batch(void* h, int n, int* data) {
     static_cast<Scheduler*>(h)->start_batch(n, data);
 }
-void ref_sched_expand(void* h, int degree) { static_cast<Scheduler*>(h)->expand(degree); }
+// The reference throws std::runtime_error from expand ("nan", scheduler.cpp:114-115; "Prob is empty",
+// mult.cpp:17-18), which would std::terminate through Cython (_scheduler.pyx:12-13 declares `except +`
+// on the constructors only).  The shim turns it into a status so that a fuzzer can walk over such inputs:
+// 0 = ok, -4 = the reference threw (the Scheduler is then in an unspecified state).
+int ref_sched_expand(void* h, int degree) {
+    try {
+        static_cast<Scheduler*>(h)->expand(degree);
+        return 0;
+    } catch (...) {
+        return -4;
+    }
+}
 
 // which: 0 field, 1 ffield, 2 edg_s, 3 edg_t, 4 fedg_s, 5 fedg_t, 6 adj_i, 7 adj_p, 8 visited, 9 fvisited
 int ref_sched_int_vec(void* h, int which, const int** out) {
