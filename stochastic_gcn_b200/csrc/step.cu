@@ -21,7 +21,7 @@
 struct sgcn_step {
     sgcn_sampler* sampler = nullptr;
     sgcn_step_desc d{};
-    cudaStream_t chain = nullptr, side = nullptr, samp = nullptr, copy = nullptr;
+    cudaStream_t chain = nullptr, side = nullptr, samp = nullptr, copy = nullptr, pre = nullptr;
     static constexpr int kSlots = 3;               // sampler buffer sets: two batches of lookahead
     int32_t* ids_dev[kSlots] = {nullptr, nullptr, nullptr};      // staging of host ids
     // level-0 buffers of the sampler's slots
@@ -29,7 +29,8 @@ struct sgcn_step {
     const int32_t* adj_p = nullptr; const int32_t* adj_i = nullptr; const float* adj_w = nullptr;
     int32_t* pipe = nullptr;
     static constexpr int kRing = 4;
-    cudaEvent_t ev_samp[kRing]{}, ev_full[kRing]{}, ev_fwd[kRing]{}, ev_rest[kRing]{}, ev_d2h[kRing]{}, ev_begin = nullptr,
+    cudaEvent_t ev_samp[kRing]{}, ev_full[kRing]{}, ev_fwd[kRing]{}, ev_rest[kRing]{}, ev_d2h[kRing]{}, ev_pre[kRing]{},
+                ev_pre_end = nullptr, ev_begin = nullptr,
                 ev_side_end = nullptr, ev_samp_end = nullptr, ev_zero0 = nullptr;
     int device = 0;
 };
@@ -102,6 +103,7 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
     CK(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&st->samp, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&st->copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&st->pre, cudaStreamNonBlocking));
     for (int i = 0; i < sgcn_step::kSlots; ++i) CK(cudaMalloc(&st->ids_dev[i], sizeof(int32_t) * (size_t)d.batch));
     for (int i = 0; i < sgcn_step::kRing; ++i) {
         CK(cudaEventCreateWithFlags(&st->ev_samp[i], cudaEventDisableTiming));
@@ -109,8 +111,10 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
         CK(cudaEventCreateWithFlags(&st->ev_fwd[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st->ev_rest[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st->ev_d2h[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&st->ev_pre[i], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&st->ev_begin, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&st->ev_pre_end, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&st->ev_side_end, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&st->ev_samp_end, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&st->ev_zero0, cudaEventDisableTiming));
@@ -121,13 +125,13 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
 
 void sgcn_step_destroy(sgcn_step* st) {
     if (!st) return;
-    for (cudaStream_t s : {st->chain, st->side, st->samp, st->copy})
+    for (cudaStream_t s : {st->chain, st->side, st->samp, st->copy, st->pre})
         if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     for (int i = 0; i < sgcn_step::kSlots; ++i) cudaFree(st->ids_dev[i]);
     for (int i = 0; i < sgcn_step::kRing; ++i)
-        for (cudaEvent_t e : {st->ev_samp[i], st->ev_full[i], st->ev_fwd[i], st->ev_rest[i], st->ev_d2h[i]})
+        for (cudaEvent_t e : {st->ev_samp[i], st->ev_full[i], st->ev_fwd[i], st->ev_rest[i], st->ev_d2h[i], st->ev_pre[i]})
             if (e) cudaEventDestroy(e);
-    for (cudaEvent_t e : {st->ev_begin, st->ev_side_end, st->ev_samp_end, st->ev_zero0})
+    for (cudaEvent_t e : {st->ev_begin, st->ev_side_end, st->ev_samp_end, st->ev_zero0, st->ev_pre_end})
         if (e) cudaEventDestroy(e);
     delete st;
 }
@@ -282,6 +286,137 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));
     if (out_host) SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_d2h[(n - 1) % R], 0));
+    return SGCN_OK;
+}
+
+// ---- "gather ahead" schedule (parity-green on a B200 at the end of round 1 -- tests/ahead_check.py --
+// but NOT TIMED yet: bench.py --driver ahead selects it, the default driver is unchanged) ----
+// sgcn_step_run's side branch per pass is [dX init + zero + gather] -> sampled aggregate, and under load
+// every dependent launch there costs 4-8 us, so the write-back (which must follow the sampled aggregate)
+// starts ~8 us after the full-neighbour mean has ended (profiles/r01_timeline_after.txt).  Here the
+// gather / dX init / output zeroing of pass k+1 run one pass AHEAD on a stream of their own, into second
+// copies of x0 / dx, so that pass k's side branch is the sampled aggregate alone:
+//   chain : [sampler k] full_mean(k) ═PDL═► history_update(k) ═PDL═► full_mean(k+1) ...
+//   side  : [ahead k, rest k-1] sampled fwd+bwd(k)
+//   pre   : [sampler k+1, rest k-1] gather(k+1) + dX init(k+1) + zero out(k+1)      (buffers of parity k+1)
+//   samp  : [rest k-1] expand(k+2)
+// Same arithmetic, same order of history reads and writes as n sequential passes.  Device ids only, no
+// host output, single GPU; every internal stream forks from and joins `stream`, so a call can be captured
+// into a CUDA graph (that is how it is meant to be used: graph-to-graph gaps instead of host launches).
+int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32_t* ids, int32_t n,
+                        void* stream) {
+    SGCN_REQUIRE(st && x0_alt && dx_alt && n >= 0 && (n == 0 || ids), "step_run_ahead: bad argument");
+    if (n == 0) return SGCN_OK;
+    const sgcn_step_desc& d = st->d;
+    SGCN_REQUIRE(d.world <= 1, "step_run_ahead: single GPU only");
+    sgcn_sampler* smp = st->sampler;
+    const int B = d.batch, H = d.hidden, R = sgcn_step::kRing;
+    const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0;
+    cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp, pre = st->pre;
+    float* x0b[2] = {d.x0, x0_alt};
+    float* dxb[2] = {d.dx, dx_alt};
+    auto nb = [&](float* base) { return base + (concat ? H : 0); };
+    constexpr int NS = sgcn_step::kSlots;
+
+    SGCN_CUDA(cudaEventRecord(st->ev_begin, user));
+    for (cudaStream_t s : {chain, side, samp, pre}) SGCN_CUDA(cudaStreamWaitEvent(s, st->ev_begin, 0));
+
+    auto sample = [&](int k) -> int {
+        STEP_TRY(sgcn_sampler_set_slot(smp, k % NS));
+        STEP_TRY(sgcn_sampler_start_batch_device(smp, B, ids + (int64_t)k * B));
+        STEP_TRY(sgcn_sampler_expand(smp, d.degree, 0));
+        SGCN_CUDA(cudaEventRecord(st->ev_samp[k % R], samp));
+        return SGCN_OK;
+    };
+    // gather + dX init + output zeroing of pass k, into the buffers of parity k & 1
+    auto ahead = [&](int k) -> int {
+        const sgcn_step::Lv& v = st->lv[k % NS];
+        const int r = k & 1;
+        SGCN_CUDA(cudaStreamWaitEvent(pre, st->ev_samp[k % R], 0));
+        if (k >= 2) SGCN_CUDA(cudaStreamWaitEvent(pre, st->ev_rest[(k - 2) % R], 0));   // pass k-2 used these buffers
+        STEP_TRY(sgcn_gather_pad_pair(d.features, d.ld_feat, v.field, d.x0_rows, v.meta + 1, d.feat_dim, x0b[r], d.ld_x0,
+                                      concat ? d.d_out : nullptr, d.ld_dout, concat ? B : 0,
+                                      concat ? v.meta + 0 : nullptr, d.x0_rows, H, dxb[r], d.ld_dx,
+                                      nullptr, 0, 0, nullptr, cv ? B : 0, H, cv ? nb(d.out[r]) : nullptr, d.ld_out, pre));
+        if (cvd) STEP_TRY(sgcn_copy_rows_pad(nullptr, 0, 0, nullptr, B, H, nb(d.out_mu[r]), d.ld_out, pre));
+        SGCN_CUDA(cudaEventRecord(st->ev_pre[k % R], pre));
+        return SGCN_OK;
+    };
+
+    STEP_TRY(sgcn_sampler_set_stream_async(smp, samp));
+    for (int slot = 0; slot < NS; ++slot) {          // forget the batches of earlier runs (see sgcn_step_run)
+        STEP_TRY(sgcn_sampler_set_slot(smp, slot));
+        STEP_TRY(sgcn_sampler_start_batch_device(smp, 0, nullptr));
+    }
+    STEP_TRY(sample(0));
+    if (n > 1) STEP_TRY(sample(1));
+    STEP_TRY(ahead(0));
+
+    for (int k = 0; k < n; ++k) {
+        const int r = k & 1;
+        const sgcn_step::Lv& v = st->lv[k % NS];
+        const int32_t* n_out_dev = v.meta + 0;
+        const int32_t* n_in_dev = v.meta + 1;
+        float* out_r = d.out[r];
+        float* outmu_r = d.out_mu[r];
+        const float* x = x0b[r];
+        const float* mu = x0b[r] + H;
+        const float* new_hist = cvd ? mu : x;
+        const float* d_nb = d.d_out + (concat ? H : 0);
+
+        // ---- chain: the full-neighbour history mean of pass k (its output was zeroed by ahead(k)) ----
+        SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_samp[k % R], 0));
+        SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_pre[k % R], 0));
+        if (cv) {
+            STEP_TRY(sgcn_full_history_mean(v.field, v.rowptr_f, B, n_out_dev, st->adj_p, st->adj_i, st->adj_w,
+                                            d.history, d.ld_hist, H, cvd ? nb(outmu_r) : nb(out_r), d.ld_out,
+                                            cvd ? nb(out_r) : nullptr, d.ld_out, nullptr, chain));
+        }
+        // ---- samp: sampler of batch k+2 into the buffer set pass k-1 used ----
+        if (k + 2 < n) {
+            if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(samp, st->ev_rest[(k - 1) % R], 0));
+            STEP_TRY(sample(k + 2));
+        }
+        // ---- pre: everything of pass k+1 that does not read the history ----
+        if (k + 1 < n) STEP_TRY(ahead(k + 1));
+        // ---- side: the sampled aggregate + backward of pass k (history as of write-back k-1) ----
+        SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_pre[k % R], 0));
+        if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_rest[(k - 1) % R], 0));
+        if (d.mode == 0) {
+            STEP_TRY(sgcn_spmm_csr(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, x, d.ld_x0, H, nb(out_r),
+                                   d.ld_out, 0, side));
+            if (concat) STEP_TRY(sgcn_copy_rows_pad(x, d.ld_x0, B, n_out_dev, B, H, out_r, d.ld_out, side));
+            STEP_TRY(sgcn_spmm_csr_bwd(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, d_nb, d.ld_dout, H, dxb[r],
+                                       d.ld_dx, side));
+        } else if (!cvd) {
+            STEP_TRY(sgcn_cv_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, B, n_out_dev, x, d.ld_x0, d.history,
+                                             d.ld_hist, H, nb(out_r), d.ld_out, concat ? out_r : nullptr, d.ld_out, 1,
+                                             d_nb, d.ld_dout, dxb[r], d.ld_dx, side));
+        } else {
+            STEP_TRY(sgcn_cvd_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, v.scales, B, n_out_dev, x, d.ld_x0,
+                                              mu, d.ld_x0, d.history, d.ld_hist, H, nb(out_r), d.ld_out,
+                                              nb(outmu_r), d.ld_out, concat ? out_r : nullptr, d.ld_out,
+                                              concat ? outmu_r : nullptr, d.ld_out, 1, d_nb, d.ld_dout, dxb[r],
+                                              d.ld_dx, side));
+        }
+        SGCN_CUDA(cudaEventRecord(st->ev_fwd[k % R], side));
+        // ---- chain: write-back after every forward read of history (gcn/models.py:186-194) ----
+        SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_fwd[k % R], 0));
+        if (!cv) {
+            STEP_TRY(sgcn_sampler_mark_consumed(smp, chain));
+        } else {
+            STEP_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
+                                         st->pipe + 1, chain));
+        }
+        SGCN_CUDA(cudaEventRecord(st->ev_rest[k % R], chain));
+    }
+    SGCN_CUDA(cudaEventRecord(st->ev_side_end, side));
+    SGCN_CUDA(cudaEventRecord(st->ev_samp_end, samp));
+    SGCN_CUDA(cudaEventRecord(st->ev_pre_end, pre));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_rest[(n - 1) % R], 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_pre_end, 0));
     return SGCN_OK;
 }
 

@@ -515,12 +515,7 @@ class HotPathStep:
         [n, B, width] tensor that receives every pass's aggregated rows."""
         import ctypes as C
         lib = _lib.load()
-        if getattr(self, "_native_h", None) is None:
-            self._enable_pipeline_guard()
-            desc = self._step_desc()
-            h = C.c_void_p()
-            _lib.check(lib.sgcn_step_create(C.byref(h), self.sampler._h, C.byref(desc)))
-            self._native_h, self._native_desc = h, desc
+        self._native_handle()
         table = batches if isinstance(batches, torch.Tensor) else torch.stack(list(batches))
         table = table.to(torch.int32).contiguous()
         n = int(table.shape[0])
@@ -540,6 +535,60 @@ class HotPathStep:
         self._last_slot = (n - 1) & 1                  # output buffers alternate ...
         self._last_sampler_slot = (n - 1) % 3          # ... sampler buffer sets rotate over three
         self.sampler._stream = None                    # the driver left the sampler on its own stream
+        return self.out
+
+    # -- "gather ahead" schedule, eager or as CUDA graphs (csrc/step.cu:sgcn_step_run_ahead; parity-tested on
+    #    hardware, not timed yet) ---------------------------------------------------------------------------
+    def _native_handle(self):
+        import ctypes as C
+        if getattr(self, "_native_h", None) is None:
+            self._enable_pipeline_guard()
+            desc = self._step_desc()
+            h = C.c_void_p()
+            _lib.check(_lib.load().sgcn_step_create(C.byref(h), self.sampler._h, C.byref(desc)))
+            self._native_h, self._native_desc = h, desc
+        return self._native_h
+
+    def run_ahead(self, table):
+        """n passes through sgcn_step_run_ahead on the current stream (plain stream launches).
+        ``table``: contiguous int32 [n, B] ids on the GPU."""
+        if getattr(self, "_ahead_bufs", None) is None:
+            self._ahead_bufs = (torch.zeros_like(self.x0), torch.zeros_like(self.dx))
+        x0_alt, dx_alt = self._ahead_bufs
+        n = int(table.shape[0])
+        _lib.check(_lib.load().sgcn_step_run_ahead(self._native_handle(), _lib.ptr(x0_alt), _lib.ptr(dx_alt),
+                                                   _lib.ptr(table), n, _lib.stream_ptr()))
+        self._last_slot, self._last_sampler_slot = (n - 1) & 1, (n - 1) % 3
+        self.sampler._stream = None
+        return self.out
+
+    def capture_ahead(self, warm_table, steps_per_graph=32):
+        """Capture S passes of the gather-ahead schedule into ONE CUDA graph over a fixed [S, B] id table
+        (five streams whatever S is).  ``warm_table``: [S, B] ids for the eager warm-up run."""
+        S = int(steps_per_graph)
+        if tuple(warm_table.shape) != (S, self.B):
+            raise ValueError("warm_table must be [steps_per_graph, batch]")
+        tab = warm_table.to(torch.int32).contiguous().clone()
+        self.run_ahead(tab)                                       # sizes everything, warms the allocators
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=self.dev)
+        with torch.cuda.graph(g, stream=cap):
+            self.run_ahead(tab)
+        self._ahead = {"S": S, "tab": tab, "graph": g}
+        return g
+
+    def replay_ahead(self, table):
+        """K = m * S passes: per chunk one id-table copy and one graph launch."""
+        a = self._ahead
+        S = a["S"]
+        n = int(table.shape[0])
+        if n % S:
+            raise ValueError("the number of passes must be a multiple of steps_per_graph")
+        for c in range(n // S):
+            a["tab"].copy_(table[c * S:(c + 1) * S], non_blocking=True)
+            a["graph"].replay()
+        self._last_slot, self._last_sampler_slot = (S - 1) & 1, (S - 1) % 3
         return self.out
 
     def time_dominant_kernel(self, batches):
