@@ -334,7 +334,24 @@ def run_ours(args, w):
     pipelined = not args.no_pipeline and not (world > 1 and args.transport == "nccl")
     ms = ms_serial
     native_drv = pipelined and args.driver == "native"
-    if native_drv:
+    ahead_drv = pipelined and args.driver == "ahead" and world == 1
+    if ahead_drv:
+        # gather-ahead schedule captured as CUDA graphs of S passes (parity-tested)
+        S = max(2, min(args.steps_per_graph, len(batches)))
+        before = _lib.launch_count()
+        step.capture_ahead(torch.stack(batches[:S]), steps_per_graph=S)       # eager warm-up run of S passes
+        launches_per_step = (_lib.launch_count() - before) / (2.0 * S)           # counted twice: warm-up + capture
+        timed_table = torch.stack(timed)
+        step.replay_ahead(timed_table[:S])
+        torch.cuda.synchronize(dev)
+        barrier()
+        ev0.record()
+        step.replay_ahead(timed_table)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        sizes_last = step.sizes()
+    elif native_drv:
         before = _lib.launch_count()
         step.run_native(torch.stack(batches[:args.warmup]))
         launches_per_step = (_lib.launch_count() - before) / args.warmup
@@ -437,6 +454,7 @@ def run_ours(args, w):
                                                                 % (world, args.transport)) if world > 1 else "single GPU"}),
             "sampled_edges_per_s": s_edges / (ms * 1e-3),
             "schedule": {"pipelined": pipelined, "driver": ("native (csrc/step.cu, stream launches)" if native_drv
+                                                             else "gather-ahead graphs (sgcn_step_run_ahead)" if ahead_drv
                                                              else "cuda-graph") if pipelined else "cuda-graph",
                          "steps_per_graph": args.steps_per_graph if pipelined else 1,
                          "what": "CUDA graphs of %d steps; inside a step batch k+1's sampler (1 CTA) runs beside "
@@ -503,8 +521,9 @@ def main():
     ap.add_argument("--steps-per-graph", type=int, default=16,
                     help="upper bound on the steps captured per CUDA graph (the largest even divisor of --steps "
                          "below it is used)")
-    ap.add_argument("--driver", default="graph", choices=["native", "graph"],
-                    help="pipelined schedule: multi-step CUDA graphs (default) or native C++ stream launches")
+    ap.add_argument("--driver", default="graph", choices=["native", "graph", "ahead"],
+                    help="pipelined schedule: multi-step CUDA graphs (default), native C++ stream launches, or the "
+                         "gather-ahead schedule as CUDA graphs (device-resident leg only; parity-tested, not timed yet)")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU write-back exchange: NVLink peer stores (default) or NCCL all-gather")
     args = ap.parse_args()

@@ -579,16 +579,18 @@ class HotPathStep:
         return g
 
     def replay_ahead(self, table):
-        """K = m * S passes: per chunk one id-table copy and one graph launch."""
+        """n passes: per chunk of S one id-table copy and one graph launch; the n mod S left-over passes run
+        through run_ahead (plain stream launches)."""
         a = self._ahead
         S = a["S"]
         n = int(table.shape[0])
-        if n % S:
-            raise ValueError("the number of passes must be a multiple of steps_per_graph")
-        for c in range(n // S):
+        full = n // S
+        for c in range(full):
             a["tab"].copy_(table[c * S:(c + 1) * S], non_blocking=True)
             a["graph"].replay()
         self._last_slot, self._last_sampler_slot = (S - 1) & 1, (S - 1) % 3
+        if n % S:
+            self.run_ahead(table[full * S:].contiguous())
         return self.out
 
     def time_dominant_kernel(self, batches):
