@@ -76,8 +76,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // An SM re-partitions its L1 / shared memory only when idle: a kernel whose preferred carve-out differs
 // from that of the kernel occupying the SMs (the full-neighbour mean holds every SM for most of a
-// step) cannot join them and starts only once an SM drains.  Every kernel that runs beside it in the
-// step therefore asks for the SAME ~100 KB carve-out (44 %), whether or not it uses shared memory.
+// step) may have to wait for an SM to drain.  For the sampler / full-mean pair that cost 13 us per step
+// (DESIGN section 3); the other kernels that run beside the mean ask for the SAME ~100 KB carve-out (44 %)
+// as a precaution -- an A/B on the side-branch kernels (SGCN_NO_MATCH_CARVEOUT=1) showed no measurable
+// difference in round 1, their late starts are dependent-launch latency under load, not re-partitioning.
 constexpr int kStepCarveout = 44;
 template <typename K>
 inline void match_step_carveout(K kernel, bool* done) {
