@@ -98,7 +98,7 @@ SIGNATURES = {
     "sgcn_step_create": (_i32, [C.POINTER(_vp), _vp, _vp]),
     "sgcn_step_destroy": (None, [_vp]),
     "sgcn_step_run": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
-    "sgcn_step_run_ahead": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp]),
+    "sgcn_step_run_ahead": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "sgcn_wb_payload_bytes": (_i64, [_i32, _i32]),
     "sgcn_wb_pack": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), _i32, _i32, _vp]),
     "sgcn_wb_push": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), C.POINTER(_vp), _i32,

@@ -300,11 +300,11 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
 //   side  : [ahead k, rest k-1] sampled fwd+bwd(k)
 //   pre   : [sampler k+1, rest k-1] gather(k+1) + dX init(k+1) + zero out(k+1)      (buffers of parity k+1)
 //   samp  : [rest k-1] expand(k+2)
-// Same arithmetic, same order of history reads and writes as n sequential passes.  Device ids only, no
-// host output, single GPU; every internal stream forks from and joins `stream`, so a call can be captured
+// Same arithmetic, same order of history reads and writes as n sequential passes.  ids / out_host as in
+// sgcn_step_run (the host-buffer form is newer than the parity run recorded above).  Single GPU; every internal stream forks from and joins `stream`, so a call can be captured
 // into a CUDA graph (that is how it is meant to be used: graph-to-graph gaps instead of host launches).
-int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32_t* ids, int32_t n,
-                        void* stream) {
+int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32_t* ids, int32_t ids_on_host,
+                        int32_t n, float* out_host, void* stream) {
     SGCN_REQUIRE(st && x0_alt && dx_alt && n >= 0 && (n == 0 || ids), "step_run_ahead: bad argument");
     if (n == 0) return SGCN_OK;
     const sgcn_step_desc& d = st->d;
@@ -312,7 +312,9 @@ int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32
     sgcn_sampler* smp = st->sampler;
     const int B = d.batch, H = d.hidden, R = sgcn_step::kRing;
     const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0;
-    cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp, pre = st->pre;
+    const int width = H * (concat ? 2 : 1);
+    cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp, pre = st->pre,
+                 copy = st->copy;
     float* x0b[2] = {d.x0, x0_alt};
     float* dxb[2] = {d.dx, dx_alt};
     auto nb = [&](float* base) { return base + (concat ? H : 0); };
@@ -320,10 +322,18 @@ int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32
 
     SGCN_CUDA(cudaEventRecord(st->ev_begin, user));
     for (cudaStream_t s : {chain, side, samp, pre}) SGCN_CUDA(cudaStreamWaitEvent(s, st->ev_begin, 0));
+    // (under stream capture a forked stream must be joined again: the copy stream forks only when it has work)
+    if (out_host) SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_begin, 0));
 
     auto sample = [&](int k) -> int {
+        const int32_t* src = ids + (int64_t)k * B;
+        if (ids_on_host) {                       // pinned host ids: staged per pass on the sampler stream
+            SGCN_CUDA(cudaMemcpyAsync(st->ids_dev[k % NS], src, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice,
+                                      samp));
+            src = st->ids_dev[k % NS];
+        }
         STEP_TRY(sgcn_sampler_set_slot(smp, k % NS));
-        STEP_TRY(sgcn_sampler_start_batch_device(smp, B, ids + (int64_t)k * B));
+        STEP_TRY(sgcn_sampler_start_batch_device(smp, B, src));
         STEP_TRY(sgcn_sampler_expand(smp, d.degree, 0));
         SGCN_CUDA(cudaEventRecord(st->ev_samp[k % R], samp));
         return SGCN_OK;
@@ -334,6 +344,7 @@ int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32
         const int r = k & 1;
         SGCN_CUDA(cudaStreamWaitEvent(pre, st->ev_samp[k % R], 0));
         if (k >= 2) SGCN_CUDA(cudaStreamWaitEvent(pre, st->ev_rest[(k - 2) % R], 0));   // pass k-2 used these buffers
+        if (k >= 2 && out_host) SGCN_CUDA(cudaStreamWaitEvent(pre, st->ev_d2h[(k - 2) % R], 0));   // ... its rows are out
         STEP_TRY(sgcn_gather_pad_pair(d.features, d.ld_feat, v.field, d.x0_rows, v.meta + 1, d.feat_dim, x0b[r], d.ld_x0,
                                       concat ? d.d_out : nullptr, d.ld_dout, concat ? B : 0,
                                       concat ? v.meta + 0 : nullptr, d.x0_rows, H, dxb[r], d.ld_dx,
@@ -372,6 +383,7 @@ int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32
                                             d.history, d.ld_hist, H, cvd ? nb(outmu_r) : nb(out_r), d.ld_out,
                                             cvd ? nb(out_r) : nullptr, d.ld_out, nullptr, chain));
         }
+        if (out_host) SGCN_CUDA(cudaEventRecord(st->ev_full[k % R], chain));
         // ---- samp: sampler of batch k+2 into the buffer set pass k-1 used ----
         if (k + 2 < n) {
             if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(samp, st->ev_rest[(k - 1) % R], 0));
@@ -409,10 +421,20 @@ int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32
                                          st->pipe + 1, chain));
         }
         SGCN_CUDA(cudaEventRecord(st->ev_rest[k % R], chain));
+        // ---- copy: the pass's aggregated rows to pinned host memory (both aggregate kernels done) ----
+        if (out_host) {
+            SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_full[k % R], 0));
+            SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_fwd[k % R], 0));
+            SGCN_CUDA(cudaMemcpy2DAsync(out_host + (int64_t)k * B * width, sizeof(float) * (size_t)width, out_r,
+                                        sizeof(float) * (size_t)d.ld_out, sizeof(float) * (size_t)width, (size_t)B,
+                                        cudaMemcpyDeviceToHost, copy));
+            SGCN_CUDA(cudaEventRecord(st->ev_d2h[k % R], copy));
+        }
     }
     SGCN_CUDA(cudaEventRecord(st->ev_side_end, side));
     SGCN_CUDA(cudaEventRecord(st->ev_samp_end, samp));
     SGCN_CUDA(cudaEventRecord(st->ev_pre_end, pre));
+    if (out_host) SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_d2h[(n - 1) % R], 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_rest[(n - 1) % R], 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));
