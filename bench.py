@@ -335,6 +335,7 @@ def run_ours(args, w):
     ms = ms_serial
     native_drv = pipelined and args.driver == "native"
     ahead_drv = pipelined and args.driver == "ahead" and world == 1
+    S = args.steps_per_graph
     if ahead_drv:
         # gather-ahead schedule captured as CUDA graphs of S passes (parity-tested)
         S = max(2, min(args.steps_per_graph, len(batches)))
@@ -381,7 +382,25 @@ def run_ours(args, w):
     # ---- e2e: same K steps through the host-buffer API (pinned ids in, aggregated rows out) ----
     pinned = [b.cpu().pin_memory() for b in timed]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if native_drv:
+    if ahead_drv and args.steps % S == 0:
+        # two alternating graphs of S passes, each bound to a pinned staging set (ids in, every pass's rows out)
+        step.capture_ahead(torch.stack(batches[:S]), steps_per_graph=S, host_io=True)
+        pinned_table = torch.stack(pinned).pin_memory()
+        pending = []
+
+        def fetch(first, count, rows, done):
+            if pending:
+                pending.pop().synchronize()          # the caller reads every chunk's rows, one chunk behind
+            pending.append(done)
+        step.replay_ahead(pinned_table[:S], on_chunk=fetch)
+        pending.pop().synchronize()
+        barrier()
+        e0.record()
+        step.replay_ahead(pinned_table, on_chunk=fetch)
+        pending.pop().synchronize()
+        e1.record()
+        barrier()
+    elif native_drv:
         # pinned [K, B] ids in, pinned [K, B, width] rows out; H2D / D2H issued step by step by the driver
         ids_host = torch.stack([p for p in pinned]).pin_memory()
         out_host = torch.empty((len(pinned), w["batch"], step.out.shape[1]), dtype=torch.float32).pin_memory()
@@ -523,7 +542,8 @@ def main():
                          "below it is used)")
     ap.add_argument("--driver", default="graph", choices=["native", "graph", "ahead"],
                     help="pipelined schedule: multi-step CUDA graphs (default), native C++ stream launches, or the "
-                         "gather-ahead schedule as CUDA graphs (device-resident leg only; parity-tested, not timed yet)")
+                         "gather-ahead schedule as CUDA graphs (parity-tested, not timed yet; its host-buffer leg "
+                         "needs --steps to be a multiple of the chunk length)")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU write-back exchange: NVLink peer stores (default) or NCCL all-gather")
     args = ap.parse_args()
