@@ -31,6 +31,9 @@ WORKLOADS = {
     "reddit_cvd": dict(shape="reddit", mode="cvd", degree=1, batch=512, hidden=128, feat=1204),     # configs[3]
     "powerlaw_ns": dict(shape="powerlaw2m", mode="ns", degree=1, batch=512, hidden=128, feat=512),  # configs[4]
     "pubmed_cvd": dict(shape="pubmed", mode="cvd", degree=1, batch=60, hidden=32, feat=500),        # configs[1]
+    # large-batch stress points of SURVEY 8d (the headline batch of 512 is latency-bound by construction)
+    "reddit_cv_b4096": dict(shape="reddit", mode="cv", degree=2, batch=4096, hidden=128, feat=1204),
+    "reddit_cv_b32768": dict(shape="reddit", mode="cv", degree=2, batch=32768, hidden=128, feat=1204),
 }
 METRIC = "aggregated edges/s (sampled + full-neighbour edges through SpMM fwd+bwd per step)"
 
