@@ -473,7 +473,8 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
  * the same n passes with the gather / dX init / output zeroing of pass k+1 issued one pass AHEAD into
  * second copies of x0 / dx (x0_alt, dx_alt: same shapes and strides as desc.x0 / desc.dx), so that a
  * pass's side branch is the sampled aggregate alone and the write-back can follow the full-neighbour
- * mean immediately.  ids / ids_on_host / out_host as for sgcn_step_run.  Single GPU.  Every internal stream
+ * mean immediately.  ids / ids_on_host / out_host and the multi-GPU exchange fields as for sgcn_step_run
+ * (the single-GPU device-buffer form is the one parity-tested on hardware so far).  Every internal stream
  * forks from and joins `stream`: the call may be captured into a CUDA graph.  Pass k's aggregated rows
  * are in desc.out[k & 1], its gathered rows in (k & 1 ? x0_alt : desc.x0). */
 int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32_t* ids, int32_t ids_on_host,

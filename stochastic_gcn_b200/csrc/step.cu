@@ -301,17 +301,16 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
 //   pre   : [sampler k+1, rest k-1] gather(k+1) + dX init(k+1) + zero out(k+1)      (buffers of parity k+1)
 //   samp  : [rest k-1] expand(k+2)
 // Same arithmetic, same order of history reads and writes as n sequential passes.  ids / out_host as in
-// sgcn_step_run (the host-buffer form is newer than the parity run recorded above).  Single GPU; every internal stream forks from and joins `stream`, so a call can be captured
+// sgcn_step_run (the host-buffer and multi-GPU forms are newer than the parity run recorded above); every internal stream forks from and joins `stream`, so a call can be captured
 // into a CUDA graph (that is how it is meant to be used: graph-to-graph gaps instead of host launches).
 int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32_t* ids, int32_t ids_on_host,
                         int32_t n, float* out_host, void* stream) {
     SGCN_REQUIRE(st && x0_alt && dx_alt && n >= 0 && (n == 0 || ids), "step_run_ahead: bad argument");
     if (n == 0) return SGCN_OK;
     const sgcn_step_desc& d = st->d;
-    SGCN_REQUIRE(d.world <= 1, "step_run_ahead: single GPU only");
     sgcn_sampler* smp = st->sampler;
     const int B = d.batch, H = d.hidden, R = sgcn_step::kRing;
-    const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0;
+    const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0, multi = d.world > 1 && cv;
     const int width = H * (concat ? 2 : 1);
     cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp, pre = st->pre,
                  copy = st->copy;
@@ -401,10 +400,16 @@ int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32
             STEP_TRY(sgcn_spmm_csr_bwd(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, d_nb, d.ld_dout, H, dxb[r],
                                        d.ld_dx, side));
         } else if (!cvd) {
+            if (multi)      // the write-back push rides on the sampled launch (see sgcn_wb_push_attach)
+                STEP_TRY(sgcn_wb_push_attach(v.field, n_in_dev, d.wb_bound, new_hist, d.ld_x0, H, d.dst_even, d.dst_odd,
+                                             d.world, d.peer_flags, d.rank, d.epoch, d.block_counter));
             STEP_TRY(sgcn_cv_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, B, n_out_dev, x, d.ld_x0, d.history,
                                              d.ld_hist, H, nb(out_r), d.ld_out, concat ? out_r : nullptr, d.ld_out, 1,
                                              d_nb, d.ld_dout, dxb[r], d.ld_dx, side));
         } else {
+            if (multi)
+                STEP_TRY(sgcn_wb_push_attach(v.field, n_in_dev, d.wb_bound, new_hist, d.ld_x0, H, d.dst_even, d.dst_odd,
+                                             d.world, d.peer_flags, d.rank, d.epoch, d.block_counter));
             STEP_TRY(sgcn_cvd_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, v.scales, B, n_out_dev, x, d.ld_x0,
                                               mu, d.ld_x0, d.history, d.ld_hist, H, nb(out_r), d.ld_out,
                                               nb(outmu_r), d.ld_out, concat ? out_r : nullptr, d.ld_out,
@@ -416,6 +421,9 @@ int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32
         SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_fwd[k % R], 0));
         if (!cv) {
             STEP_TRY(sgcn_sampler_mark_consumed(smp, chain));
+        } else if (multi) {
+            STEP_TRY(sgcn_wb_wait_apply(d.history, d.ld_hist, H, d.recv_even, d.recv_odd, d.slot_bytes, d.world,
+                                        d.wb_bound, d.owner, d.flags, d.epoch, d.timeout_flag, st->pipe + 1, chain));
         } else {
             STEP_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
                                          st->pipe + 1, chain));

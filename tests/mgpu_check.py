@@ -22,12 +22,13 @@ def main():
     transport, mode = sys.argv[1], sys.argv[2]
     use_graph = len(sys.argv) > 3 and sys.argv[3] == "graph"
     pipelined = len(sys.argv) > 3 and sys.argv[3] == "pipelined"
+    ahead = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] in ("ahead", "ahead-graph") else None
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     deg = 2 if mode == "cv" else 1
-    D, B, steps, seed = 32, 24, (8 if pipelined else 5), 3
+    D, B, steps, seed = 32, 24, (8 if pipelined else 12 if ahead else 5), 3
     g = graphs.powerlaw_graph(1500, 60_000, seed=4, device=dev, max_degree=300)
     gen = torch.Generator(device=dev).manual_seed(0)
     feats = torch.randn((g.n, 80), generator=gen, device=dev)
@@ -85,6 +86,20 @@ def main():
         out = step.out.cpu().numpy()
         err = np.abs(out - want_out[-1]).max() / max(np.abs(want_out[-1]).max(), 1e-30)
         assert err < 1e-4, "rank %d: last pipelined out differs by %g" % (rank, err)
+        steps = 0
+    if ahead:
+        # gather-ahead schedule (sgcn_step_run_ahead) with the peer exchange: eager, or 4 passes per CUDA graph
+        table = torch.from_numpy(np.stack(batches[rank])).to(dev)
+        if ahead == "ahead":
+            step.run_ahead(table)
+        else:
+            step.capture_ahead(table[:4], steps_per_graph=4)      # eager warm-up run = passes 0 .. 3
+            step.replay_ahead(table[4:])
+        torch.cuda.synchronize()
+        step.check_exchange()
+        out = step.out.cpu().numpy()
+        err = np.abs(out - want_out[-1]).max() / max(np.abs(want_out[-1]).max(), 1e-30)
+        assert err < 1e-4, "rank %d: last gather-ahead out differs by %g" % (rank, err)
         steps = 0
     for s in range(steps):
         ids = torch.from_numpy(batches[rank][s]).to(dev)
