@@ -243,7 +243,7 @@ def run_reference(args, w):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "edges/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, w, None),
+            "config": workload_config(args, w),
             "sampled_edges_per_s": s_tot / dt,
             "cpu_baseline": {"value": val, "unit": "edges/s", "cores": cpu.threads,
                              "kind": "reference" if cpu.kind_native == "reference" else "port",
@@ -254,29 +254,105 @@ def run_reference(args, w):
     emit(line)
 
 
-def pick_steps_per_graph(k, cap):
-    """Chunk length (even, <= cap) for K timed steps: whole chunks replay as CUDA graphs, the K mod S
-    left-over steps run eagerly, so S trades graph-to-graph gaps (~8 us each) against eager steps
-    (~40 us extra each) -- S = cap for long runs, a divisor of K (or K - 1) for short ones."""
-    cap = max(2, min(int(cap), int(k)) // 2 * 2)
-    return min(range(cap, 1, -2), key=lambda s: (k // s) * 8 + (k % s) * 40)
+def pick_graph_passes(k, cap):
+    """Passes per captured CUDA graph for K timed steps: ONE graph of K passes when K <= cap (the driver's
+    20-step run is one graph launch), otherwise the largest divisor of K that is <= cap and >= cap / 2, or
+    cap with the K mod cap left-over passes issued as plain stream launches by the same native driver."""
+    k, cap = int(k), max(2, int(cap))
+    if k <= cap:
+        return k
+    for s in range(cap, cap // 2 - 1, -1):
+        if k % s == 0:
+            return s
+    return cap
 
 
-def workload_config(args, w, extra):
-    c = {"workload": "%s: synthetic %s-shaped graph, %s+PP degree %d, batch %d/GPU, hidden %d, PP input %d-d"
-                     % (args.workload, w["shape"], w["mode"].upper(), w["degree"], w["batch"], w["hidden"], w["feat"]),
-         "scale": args.scale, "seed": args.seed,
-         "l2": "inputs larger than L2 (adjacency + features + history > 2 GB, a fresh random batch every step); "
-               "no explicit flush"}
-    if extra:
-        c.update(extra)
-    return c
+def workload_config(args, w):
+    """`config` of the JSON line: identical in both arms (the driver compares them)."""
+    return {"workload": "%s: synthetic %s-shaped graph, %s+PP degree %d, batch %d/GPU, hidden %d, PP input %d-d"
+                        % (args.workload, w["shape"], w["mode"].upper(), w["degree"], w["batch"], w["hidden"], w["feat"]),
+            "scale": args.scale, "seed": args.seed,
+            "l2": "inputs larger than L2 (adjacency + features + history > 2 GB, a fresh random batch every step); "
+                  "no explicit flush"}
+
+
+class Rig:
+    """One workload set up on this rank: graph, features, the step object, its batches."""
+
+    def __init__(self, args, name, w, world, rank, dev, n_batches):
+        from stochastic_gcn_b200.step import HotPathStep
+        self.w, self.name, self.world, self.rank, self.dev = w, name, world, rank, dev
+        self.g, self.feats = build_inputs(w, args.seed, dev, args.scale)
+        if world > 1:
+            from stochastic_gcn_b200.sharding import ShardedHotPathStep
+            self.step = ShardedHotPathStep(self.g, self.feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"],
+                                           seed=args.seed + rank, rank=rank, world=world, transport=args.transport)
+            lo, hi = self.step.lo, self.step.hi
+        else:
+            self.step = HotPathStep(self.g, self.feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"],
+                                    seed=args.seed)
+            lo, hi = 0, self.g.n
+        self.step.train = args.train
+        self.step.overlap_write_back = not args.no_overlap_write_back
+        gen = torch.Generator(device=dev).manual_seed(7)
+        self.step.d_out.normal_(generator=gen)
+        self.step.history.normal_(generator=gen)      # a warm history table (zero rows would skip reductions)
+        self.batches = make_batches(self.g.n, w["batch"], n_batches, args.seed + rank, dev, lo, hi)
+
+    def close(self):
+        if hasattr(self.step, "close"):
+            self.step.close()
+
+
+def time_trains(rig, args, timed, warm, barrier, host_io):
+    """K = len(timed) passes of the trains schedule as CUDA graph replays (+ a plain-launch remainder);
+    returns (ms, passes per graph, launches per pass).  host_io: pinned ids in, every pass's rows out."""
+    from stochastic_gcn_b200 import _lib
+    step, dev = rig.step, rig.dev
+    K = len(timed)
+    S = pick_graph_passes(K, args.graph_passes)
+    full = (K // S) * S
+    before = _lib.launch_count()
+    step.capture_trains(S, torch.stack(warm[:S]), host_io=host_io, first_train=args.first_train)
+    launches = (_lib.launch_count() - before) / ((3.0 if host_io else 2.0) * S)   # eager warm-up + capture(s)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    table = torch.stack(timed).contiguous()
+    if not host_io:
+        step.replay_trains(torch.stack(warm[:S]))              # first launch of the graph (upload) untimed
+        barrier()
+        e0.record()
+        step.replay_trains(table[:full])
+        if full < K:
+            step.run_trains(table[full:].contiguous(), first_train=args.first_train)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), S, launches
+    pinned = table.cpu().pin_memory()
+    width = step.outs[0].shape[1]
+    tail_rows = torch.empty((K - full, rig.w["batch"], width), dtype=torch.float32).pin_memory() if full < K else None
+    pending = []
+
+    def fetch(first, count, rows, done):
+        if pending:
+            pending.pop().synchronize()              # the caller reads every replay's rows, one replay behind
+        pending.append(done)
+    step.replay_trains(torch.stack(warm[:S]).cpu().pin_memory().repeat(2, 1), on_chunk=fetch)   # both graphs once
+    pending.pop().synchronize()
+    barrier()
+    e0.record()
+    step.replay_trains(pinned[:full], on_chunk=fetch)
+    if full < K:
+        step.run_trains(pinned[full:], out_host=tail_rows, first_train=args.first_train)
+    pending.pop().synchronize()
+    torch.cuda.current_stream(dev).synchronize()     # the caller has every pass's rows
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1), S, launches
 
 
 def run_ours(args, w):
     import torch.distributed as dist
     from stochastic_gcn_b200 import _lib
-    from stochastic_gcn_b200.step import HotPathStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -289,39 +365,40 @@ def run_ours(args, w):
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
-    g, feats = build_inputs(w, args.seed, dev, args.scale)
-    n_total = args.steps + args.warmup
-    if world > 1:
-        from stochastic_gcn_b200.sharding import ShardedHotPathStep
-        step = ShardedHotPathStep(g, feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"],
-                                  seed=args.seed + rank, rank=rank, world=world, transport=args.transport)
-        lo, hi = step.lo, step.hi
-    else:
-        step = HotPathStep(g, feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"], seed=args.seed)
-        lo, hi = 0, g.n
-    batches = make_batches(g.n, w["batch"], n_total, args.seed + rank, dev, lo, hi)
-    step.d_out.normal_(generator=torch.Generator(device=dev).manual_seed(7))
-    s_edges, f_edges = edge_counts(g, batches[args.warmup:], w["degree"], w["mode"] != "ns")
-
-    # warm-up: the first pass is eager (sizes buffers, counts launches), then graph replays
-    step.capture(batches[0])
-    launches_per_step = step.launches_per_step
-    for b in batches[1:args.warmup]:
-        step.replay(b)
-    torch.cuda.synchronize(dev)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    timed = batches[args.warmup:]
-    args.steps_per_graph = pick_steps_per_graph(args.steps, args.steps_per_graph)
+    def reduce_times(vals):
+        """(max over ranks, sum over ranks) of a list of floats"""
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world == 1:
+            return t.tolist(), t.tolist()
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        return tmax.tolist(), tsum.tolist()
+
+    K, W = args.steps, args.warmup
+    S_max = min(max(K, 2), args.graph_passes)
+    rig = Rig(args, args.workload, w, world, rank, dev, W + K + S_max)
+    step, g, batches = rig.step, rig.g, rig.batches
+    timed, warm = batches[W:W + K], batches[W + K:]
+    s_edges, f_edges = edge_counts(g, timed, w["degree"], w["mode"] != "ns")
+
+    # warm-up: the first pass is eager (sizes buffers, counts launches), then one-pass graph replays
+    step.capture(batches[0])
+    launches_per_step = step.launches_per_step
+    for b in batches[1:W]:
+        step.replay(b)
+    torch.cuda.synchronize(dev)
+
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
 
-    # ---- (1) one graph per step, steps strictly back to back (no cross-step overlap) ----
+    # ---- (1) one graph per step, steps strictly back to back (no cross-step overlap): reference point ----
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -332,35 +409,18 @@ def run_ours(args, w):
     ms_serial = ev0.elapsed_time(ev1)
     sizes_last = step.sizes()
 
-    # ---- (2) timed region of record: exactly K steps with one-batch sampler lookahead ----
-    # the NCCL transport runs its collective eagerly between graph replays: no multi-step graphs there
-    pipelined = not args.no_pipeline and not (world > 1 and args.transport == "nccl")
-    ms = ms_serial
-    native_drv = pipelined and args.driver == "native"
-    ahead_drv = pipelined and args.driver == "ahead" and world == 1
-    S = args.steps_per_graph
-    if ahead_drv:
-        # gather-ahead schedule captured as CUDA graphs of S passes (parity-tested)
-        S = max(2, min(args.steps_per_graph, len(batches)))
-        before = _lib.launch_count()
-        step.capture_ahead(torch.stack(batches[:S]), steps_per_graph=S)       # eager warm-up run of S passes
-        launches_per_step = (_lib.launch_count() - before) / (2.0 * S)           # counted twice: warm-up + capture
-        timed_table = torch.stack(timed)
-        step.replay_ahead(timed_table[:S])
-        torch.cuda.synchronize(dev)
-        barrier()
-        ev0.record()
-        step.replay_ahead(timed_table)
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
+    # ---- (2) timed region of record: exactly K passes ----
+    nccl_multi = world > 1 and args.transport == "nccl"      # collective runs eagerly between one-pass graphs
+    driver = "one-graph-per-step" if (args.no_pipeline or nccl_multi) else args.driver
+    ms, S = ms_serial, 1
+    if driver == "trains":
+        ms, S, launches_per_step = time_trains(rig, args, timed, warm, barrier, host_io=False)
         sizes_last = step.sizes()
-    elif native_drv:
+    elif driver == "native":
         before = _lib.launch_count()
-        step.run_native(torch.stack(batches[:args.warmup]))
-        launches_per_step = (_lib.launch_count() - before) / args.warmup
+        step.run_native(torch.stack(batches[:W]))
+        launches_per_step = (_lib.launch_count() - before) / W
         timed_table = torch.stack(timed)
-        torch.cuda.synchronize(dev)
         barrier()
         ev0.record()
         step.run_native(timed_table)
@@ -368,12 +428,12 @@ def run_ours(args, w):
         barrier()
         ms = ev0.elapsed_time(ev1)
         sizes_last = step.sizes()
-    elif pipelined:
-        step.capture_pipelined(batches[0], batches[1], steps_per_graph=args.steps_per_graph)
+    elif driver == "graph":
+        S = pick_graph_passes(K, 16) // 2 * 2 or 2
+        step.capture_pipelined(batches[0], batches[1], steps_per_graph=S)
         launches_per_step -= 2                       # fused dX-init/zero and forward+backward, mark in write-back
-        step.run_pipelined(batches[2:args.warmup + 2])
+        step.run_pipelined(batches[2:W + 2])
         timed_table = torch.stack(timed)             # [K, B] ids resident in HBM: one copy per chunk
-        torch.cuda.synchronize(dev)
         barrier()
         ev0.record()
         step.run_pipelined(timed_table)
@@ -382,31 +442,14 @@ def run_ours(args, w):
         ms = ev0.elapsed_time(ev1)
         sizes_last = step.sizes()
 
-    # ---- e2e: same K steps through the host-buffer API (pinned ids in, aggregated rows out) ----
+    # ---- e2e: the same K passes through the host-buffer API (pinned ids in, aggregated rows out) ----
     pinned = [b.cpu().pin_memory() for b in timed]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if ahead_drv and args.steps % S == 0:
-        # two alternating graphs of S passes, each bound to a pinned staging set (ids in, every pass's rows out)
-        step.capture_ahead(torch.stack(batches[:S]), steps_per_graph=S, host_io=True)
-        pinned_table = torch.stack(pinned).pin_memory()
-        pending = []
-
-        def fetch(first, count, rows, done):
-            if pending:
-                pending.pop().synchronize()          # the caller reads every chunk's rows, one chunk behind
-            pending.append(done)
-        step.replay_ahead(pinned_table[:S], on_chunk=fetch)
-        pending.pop().synchronize()
-        barrier()
-        e0.record()
-        step.replay_ahead(pinned_table, on_chunk=fetch)
-        pending.pop().synchronize()
-        e1.record()
-        barrier()
-    elif native_drv:
-        # pinned [K, B] ids in, pinned [K, B, width] rows out; H2D / D2H issued step by step by the driver
-        ids_host = torch.stack([p for p in pinned]).pin_memory()
-        out_host = torch.empty((len(pinned), w["batch"], step.out.shape[1]), dtype=torch.float32).pin_memory()
+    if driver == "trains":
+        ms_e2e, _, _ = time_trains(rig, args, timed, warm, barrier, host_io=True)
+    elif driver == "native":
+        ids_host = torch.stack(pinned).pin_memory()
+        out_host = torch.empty((K, w["batch"], step.out.shape[1]), dtype=torch.float32).pin_memory()
         step.run_native(ids_host[:4], out_host=out_host[:4])
         barrier()
         e0.record()
@@ -414,21 +457,17 @@ def run_ours(args, w):
         torch.cuda.current_stream(dev).synchronize()          # the caller reads the rows
         e1.record()
         barrier()
-    elif pipelined:
-        # H2D of every step's ids and D2H of every step's rows are memcpy nodes of the chunk graphs
-        step.capture_pipelined(batches[0], batches[1], host_io=True, steps_per_graph=args.steps_per_graph)
-        stream = torch.cuda.current_stream(dev)
-        out_host = step._pipe["pin_out"][0][0]
-
+        ms_e2e = e0.elapsed_time(e1)
+    elif driver == "graph":
+        step.capture_pipelined(batches[0], batches[1], host_io=True, steps_per_graph=S)
         pending = []
 
         def fetch(first, count, st, done):
-            # the caller waits for (and may read) every step's rows, one chunk behind the launches
             if pending:
                 pending.pop().synchronize()
             pending.append(done)
-        pinned_table = torch.stack(pinned).pin_memory()          # [K, B] ids in pinned HOST memory
-        step.run_pipelined(pinned_table[:args.steps_per_graph], on_chunk=fetch)
+        pinned_table = torch.stack(pinned).pin_memory()
+        step.run_pipelined(pinned_table[:S], on_chunk=fetch)
         pending.pop().synchronize()
         barrier()
         e0.record()
@@ -436,28 +475,63 @@ def run_ours(args, w):
         pending.pop().synchronize()
         e1.record()
         barrier()
+        ms_e2e = e0.elapsed_time(e1)
     else:
         if world == 1:
             step.capture_host()
-        out_host = step.step_host(pinned[0])
+        step.step_host(pinned[0])
         barrier()
         e0.record()
         for p in pinned:
-            out_host = step.step_host(p)
+            step.step_host(p)
         e1.record()
         barrier()
-    ms_e2e = e0.elapsed_time(e1)
+        ms_e2e = e0.elapsed_time(e1)
     clock_info = clocks.stop() if rank == 0 else None
 
     # ---- dominant kernel, timed alone on its launch stream over the same K batches ----
-    kern = step.time_dominant_kernel(batches[args.warmup:]) if hasattr(step, "time_dominant_kernel") else None
+    kern = step.time_dominant_kernel(timed)
 
-    t = torch.tensor([ms, ms_e2e, float(s_edges), float(f_edges), ms_serial], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, ms_e2e, ms_serial = float(tmax[0]), float(tmax[1]), float(tmax[4])
-        s_edges, f_edges = float(tsum[2]), float(tsum[3])
+    (ms, ms_e2e, ms_serial, _, _), (_, _, _, s_edges, f_edges) = reduce_times(
+        [ms, ms_e2e, ms_serial, float(s_edges), float(f_edges)])
+    alg = step.algorithmic_bytes(sizes_last)
+    detail = {"nodes": g.n, "stored_edges": g.nnz, "last_step_sizes": sizes_last,
+              "parallelism": ("row-range shards x%d, history replicas synced by %s write-back exchange"
+                              % (world, args.transport)) if world > 1 else "single GPU"}
+    rig.close()
+    del rig, step, g, batches
+
+    # ---- the other BASELINE configurations, device-resident leg only (extra keys; the headline stays configs[2]) ----
+    also = {}
+    for name in ([] if args.no_also else [n for n in ("reddit_cvd", "powerlaw_ns") if n != args.workload]):
+        try:
+            w2 = WORKLOADS[name]
+            k2 = min(K, 64)
+            r2 = Rig(args, name, w2, world, rank, dev, W + k2 + min(k2, args.graph_passes))
+            t2, wm2 = r2.batches[W:W + k2], r2.batches[W + k2:]
+            r2.step.capture(r2.batches[0])
+            se, fe = edge_counts(r2.g, t2, w2["degree"], w2["mode"] != "ns")
+            if nccl_multi:
+                barrier(); ev0.record()
+                for b in t2:
+                    r2.step.replay(b)
+                ev1.record(); barrier()
+                m2 = ev0.elapsed_time(ev1)
+            else:
+                m2, _, _ = time_trains(r2, args, t2, wm2, barrier, host_io=False)
+            z2 = r2.step.sizes()
+            a2 = r2.step.algorithmic_bytes(z2)
+            (m2,), _ = reduce_times([m2])
+            _, (se, fe) = reduce_times([float(se), float(fe)])
+            also[name] = {"config": workload_config(argparse.Namespace(workload=name, scale=args.scale, seed=args.seed), w2)["workload"],
+                          "steps": k2, "ms_per_step": m2 / k2, "value": (se + fe) / (m2 * 1e-3), "unit": "edges/s",
+                          "sampled_edges_per_s": se / (m2 * 1e-3), "nodes": r2.g.n, "stored_edges": r2.g.nnz,
+                          "last_step_sizes": z2, "algorithmic_bytes_per_step": a2["total"],
+                          "frac_of_hbm_peak": a2["total"] / (m2 / k2 * 1e-3) / 1e9 / load_peaks()[0]}
+            r2.close()
+            del r2
+        except Exception as exc:      # an extra key must never cost the headline line
+            also[name] = {"error": repr(exc)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -466,49 +540,56 @@ def run_ours(args, w):
     peak, peak_src = load_peaks()
     total_edges = s_edges + f_edges
     value = total_edges / (ms * 1e-3)
-    alg = step.algorithmic_bytes(sizes_last)
-    line = {"metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+    what = {"trains": "CUDA graph(s) of %d passes of the trains schedule: trains of %d batches sampled by one launch a "
+                      "train ahead, gather one pass ahead, full-neighbour means back to back%s" % (
+                          S, args.train, "" if args.no_overlap_write_back or world > 1 else
+                          " (write-back off the chain: row override)"),
+            "graph": "CUDA graphs of %d steps; batch k+1's sampler (1 CTA) runs beside batch k's aggregate" % S,
+            "native": "plain stream launches from C++ on three streams, two batches of sampler lookahead",
+            "one-graph-per-step": "one CUDA graph per step, back to back"}[driver]
+    line = {"metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, w, {"nodes": g.n, "stored_edges": g.nnz,
-                                                "last_step_sizes": sizes_last,
-                                                "parallelism": ("row-range shards x%d, history replicas synced by %s write-back exchange"
-                                                                % (world, args.transport)) if world > 1 else "single GPU"}),
+            "config": workload_config(args, w), "workload_detail": detail,
             "sampled_edges_per_s": s_edges / (ms * 1e-3),
-            "schedule": {"pipelined": pipelined, "driver": ("native (csrc/step.cu, stream launches)" if native_drv
-                                                             else "gather-ahead graphs (sgcn_step_run_ahead)" if ahead_drv
-                                                             else "cuda-graph") if pipelined else "cuda-graph",
-                         "steps_per_graph": args.steps_per_graph if pipelined else 1,
-                         "what": "CUDA graphs of %d steps; inside a step batch k+1's sampler (1 CTA) runs beside "
-                                 "batch k's aggregate (one-batch lookahead, same sequential semantics)"
-                                 % args.steps_per_graph if pipelined else
-                                 "one CUDA graph per step, back to back",
-                         "ms_per_step_one_graph_back_to_back": ms_serial / args.steps},
+            "schedule": {"driver": driver, "passes_per_graph": S, "what": what,
+                         "ms_per_step_one_graph_back_to_back": ms_serial / K},
             "step_hbm": {"algorithmic_bytes_per_step": alg["total"],
-                         "achieved_gbs": alg["total"] * world / (ms / args.steps * 1e-3) / 1e9 / world,
-                         "frac_of_peak": alg["total"] / (ms / args.steps * 1e-3) / 1e9 / peak,
+                         "achieved_gbs": alg["total"] / (ms / K * 1e-3) / 1e9,
+                         "frac_of_peak": alg["total"] / (ms / K * 1e-3) / 1e9 / peak,
                          "stages": {k: v for k, v in alg.items() if k != "total"}},
             "e2e": {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s",
-                    "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(pinned[0].numel() * 4),
-                    "d2h_bytes_per_step": int(w["batch"] * step.out.shape[1] * 4)},
-            "gpu_launches": int(round(launches_per_step * args.steps)),
+                    "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": int(w["batch"] * 4),
+                    "d2h_bytes_per_step": int(w["batch"] * alg_width(w) * 4),
+                    "how": "pinned host id table in (H2D copy of each train's ids inside the graphs), every pass's "
+                           "aggregated rows out to pinned host memory (one D2H copy per pass inside the graphs); the "
+                           "caller waits for each graph's rows one replay behind the launches"},
+            "gpu_launches": int(round(launches_per_step * K)),
             "launches_per_step": float(launches_per_step),
             "clocks": clock_info}
+    if also:
+        line["also"] = also
     if kern is not None:
         traffic = load_traffic(kern["kernel"])
         line["roofline"] = {"bound": "hbm", "kernel": kern["kernel"], "achieved": kern["bytes"] / kern["sec"] / 1e9,
                             "peak": peak, "unit": "GB/s", "frac": kern["bytes"] / kern["sec"] / 1e9 / peak,
                             "traffic": traffic["bytes"] if traffic else None,
+                            "frac_dram": (traffic["bytes"] / kern["sec"] / 1e9 / peak) if traffic else None,
                             "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
                             "us_per_launch": kern["sec"] * 1e6, "algorithmic_bytes_per_launch": kern["bytes"],
                             "how": kern["how"]}
     if world == 1 and not args.no_cpu:
-        host_batches = [b.cpu().numpy() for b in make_batches(g.n, w["batch"], 4000, args.seed + 99, dev)]
-        line["cpu_baseline"] = cpu_leg(w, g, feats, args.seed, host_batches, args.cpu_seconds, 3)
+        g_cpu, feats_cpu = build_inputs(w, args.seed, dev, args.scale)
+        host_batches = [b.cpu().numpy() for b in make_batches(g_cpu.n, w["batch"], 4000, args.seed + 99, dev)]
+        line["cpu_baseline"] = cpu_leg(w, g_cpu, feats_cpu, args.seed, host_batches, args.cpu_seconds, 3)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def alg_width(w):
+    return w["hidden"] * 2            # [self | neighbour] rows (graphsage normalisation: every bench workload)
 
 
 _REAL_STDOUT = None
@@ -540,13 +621,18 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="time one graph per step, no sampler lookahead")
-    ap.add_argument("--steps-per-graph", type=int, default=16,
-                    help="upper bound on the steps captured per CUDA graph (the largest even divisor of --steps "
-                         "below it is used)")
-    ap.add_argument("--driver", default="graph", choices=["native", "graph", "ahead"],
-                    help="pipelined schedule: multi-step CUDA graphs (default), native C++ stream launches, or the "
-                         "gather-ahead schedule as CUDA graphs (parity-tested, not timed yet; its host-buffer leg "
-                         "needs --steps to be a multiple of the chunk length)")
+    ap.add_argument("--graph-passes", type=int, default=64,
+                    help="upper bound on the passes captured per CUDA graph (K <= this: one graph of K passes)")
+    ap.add_argument("--train", type=int, default=16, help="batches sampled per launch by the trains schedule (2..32)")
+    ap.add_argument("--first-train", type=int, default=4,
+                    help="length of the first train of a graph (short: smaller start-up bubble)")
+    ap.add_argument("--no-overlap-write-back", action="store_true",
+                    help="keep the history write-back on the critical chain (A/B of the row override)")
+    ap.add_argument("--no-also", action="store_true", help="skip the extra keys for the other BASELINE configurations")
+    ap.add_argument("--driver", default="trains", choices=["trains", "native", "graph"],
+                    help="schedule of the timed region: trains (default; csrc/step.cu:sgcn_step_run_trains as CUDA "
+                         "graphs), native (round-1 C++ driver, plain stream launches), graph (round-1 multi-step "
+                         "torch-captured graphs)")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU write-back exchange: NVLink peer stores (default) or NCCL all-gather")
     args = ap.parse_args()

@@ -127,9 +127,26 @@ int sgcn_sampler_copy_vec(sgcn_sampler* s, int32_t level, int32_t which, void* d
  * until every earlier consumer pass has been marked finished (sgcn_sampler_mark_consumed, or the
  * done_counter of sgcn_history_update / sgcn_wb_wait_apply) -- the in-place row permutation must
  * not race the full-neighbour reads of an earlier batch.  Disjoint batches never wait. */
-int sgcn_sampler_set_slot(sgcn_sampler* s, int32_t slot /*0|1|2*/);
+int sgcn_sampler_set_slot(sgcn_sampler* s, int32_t slot /*0 .. 127*/);
 int sgcn_sampler_pipeline(sgcn_sampler* s, int32_t enable);
 int sgcn_sampler_mark_consumed(sgcn_sampler* s, void* stream);
+/* Trains of batches.  `Scheduler::expand` is sequential (one mt19937 stream, rows permuted in place,
+ * scheduler.cpp:125-189), but consecutive batches depend on each other only through the stream OFFSET
+ * (the number of draws of the earlier batches) and through the stored row of a node that occurs in two
+ * of them -- so when the ids of the next n batches are known (the reference shuffles the whole epoch up
+ * front, _scheduler.pyx:50-53,129-135) they are sampled by ONE launch of n thread blocks with exactly
+ * the results of n sequential start_batch + expand(degree) calls.
+ *   reserve_sets: sizes buffer sets 0 .. n_sets-1 (sgcn_sampler_set_slot ids) for batches of exactly
+ *                 `batch` ids expanded once with `degree` (uniform branch, batch <= 4096, degree <= 32).
+ *   expand_train: ids = DEVICE int32 [n][batch] (borrowed until the consumer passes have run); batch j
+ *                 goes to buffer set (first_set + j) % n_sets, level 0.  n <= min(64, n_sets).
+ *                 prev_ids / prev_n: the ids of batches sampled earlier whose consumer passes may still be
+ *                 reading the adjacency (pipeline mode): a batch sharing a node with them waits on the
+ *                 device until SGCN_VEC_PIPE[1] has caught up with the batches sampled before this train.
+ *                 Asynchronous on `stream`; afterwards sizes / vec / slot_vec address the sets as usual. */
+int sgcn_sampler_reserve_sets(sgcn_sampler* s, int32_t n_sets, int32_t batch, int32_t degree);
+int sgcn_sampler_expand_train(sgcn_sampler* s, const int32_t* ids, int32_t n, int32_t first_set,
+                              const int32_t* prev_ids, int32_t prev_n, void* stream);
 /* the stream expand() runs on (cudaStream_t as void*); set to share the caller's stream */
 int sgcn_sampler_set_stream(sgcn_sampler* s, void* stream);
 /* same without synchronising the previous stream (legal during CUDA-graph capture; the caller
@@ -457,6 +474,11 @@ typedef struct {
     void* dst_even[16]; void* dst_odd[16]; void* peer_flags[16];
     void* recv_even; void* recv_odd; const int32_t* flags;
     int32_t* epoch; int32_t* timeout_flag; int32_t* block_counter; int32_t* owner;
+    /* sgcn_step_run_trains only (may be NULL / 0 otherwise): two more copies of x0 and one more of dx (same
+     * shapes and strides), the number of batches sampled per launch (2 .. 32, 0 = 16) and whether the
+     * history write-back leaves the critical path (row override in the next pass's full-neighbour mean) */
+    float* x0_alt[2]; float* dx_alt;
+    int32_t train; int32_t overlap_write_back;
 } sgcn_step_desc;
 int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_desc* desc /*HOST*/);
 void sgcn_step_destroy(sgcn_step* st);
@@ -479,6 +501,34 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
  * are in desc.out[k & 1], its gathered rows in (k & 1 ? x0_alt : desc.x0). */
 int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32_t* ids, int32_t ids_on_host,
                         int32_t n, float* out_host, void* stream);
+
+/* sgcn_full_history_mean with a row override: history rows of the nodes ov_ids[0 .. *ov_n_dev) (distinct,
+ * at most ov_bound <= 4096) are read from ov_rows[i, :] (row stride ld_ov) instead of hist -- i.e. the
+ * result is what sgcn_history_update(hist, ov_ids, ov_rows) followed by sgcn_full_history_mean would give,
+ * without waiting for that write-back (which may run concurrently: it only writes rows this kernel does
+ * not read).  Each thread block hashes the id list into shared memory; one probe per neighbour. */
+int sgcn_full_history_mean_ov(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
+                              const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
+                              const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
+                              float* y0, int64_t ld_y0, float* y1, int64_t ld_y1,
+                              const int32_t* ov_ids, const int32_t* ov_n_dev, int32_t ov_bound,
+                              const float* ov_rows, int64_t ld_ov, void* stream);
+
+/* The schedule bench.py times: n passes with
+ *   samp  : trains of `train` batches sampled by ONE launch each (sgcn_sampler_expand_train), one train ahead
+ *           of the passes that consume them (first_train: length of the first train, 0 = `train`; a short
+ *           first train shortens the start-up bubble)
+ *   pre   : gather + dX init + output zeroing of pass k+1 while pass k runs (three x0 copies, two dx copies)
+ *   chain : full-neighbour mean(k) back to back with full-neighbour mean(k+1)
+ *   side  : write-back(k-1) -> sampled aggregate + backward(k) -> write-back(k) ...
+ * With desc.overlap_write_back the full-neighbour mean of pass k+1 does not wait for write-back k: it reads
+ * the rows of pass k's input field from that pass's gathered rows (sgcn_full_history_mean_ov), and write-back
+ * k only has to land before pass k+2.  Same results as n sequential passes.  ids / ids_on_host / out_host as
+ * sgcn_step_run; every internal stream forks from and joins `stream` (capturable into a CUDA graph).  Pass k:
+ * aggregated rows in desc.out[k & 1], gathered rows in x0 copy k % 3 (desc.x0, x0_alt[0], x0_alt[1]), dX in
+ * (k & 1 ? dx_alt : desc.dx), sampler buffer set  ((train index & 1) * train + position in the train). */
+int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
+                         int32_t first_train, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,12 +17,19 @@ import numpy as np
 from . import native
 
 
+_SCIPY_ABOVE = 50_000
+
+
 def _coo_matmul(adj, x, dtype):
     """dot(adj, x, sparse=True), gcn/layers.py:31-37."""
     idx, val, shape = adj
     idx = np.asarray(idx).reshape(-1, 2)
     if dtype == np.float32:
         return native.spmm_coo(idx, val, shape, x)
+    if len(val) > _SCIPY_ABOVE:       # full-size cases: same float64 sums through SciPy's CSR product
+        from scipy.sparse import coo_matrix
+        a = coo_matrix((np.asarray(val, np.float64), (idx[:, 0], idx[:, 1])), shape=(int(shape[0]), int(shape[1])))
+        return np.asarray(a.tocsr() @ x.astype(np.float64))
     y = np.zeros((int(shape[0]), x.shape[1]), dtype=np.float64)
     np.add.at(y, idx[:, 0], np.asarray(val, np.float64)[:, None] * x.astype(np.float64)[idx[:, 1]])
     return y

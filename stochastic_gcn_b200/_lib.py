@@ -76,6 +76,8 @@ SIGNATURES = {
     "sgcn_det_sampled_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i32,
                                     _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "sgcn_sampler_set_slot": (_i32, [_vp, _i32]),
+    "sgcn_sampler_reserve_sets": (_i32, [_vp, _i32, _i32, _i32]),
+    "sgcn_sampler_expand_train": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp]),
     "sgcn_sampler_pipeline": (_i32, [_vp, _i32]),
     "sgcn_sampler_mark_consumed": (_i32, [_vp, _vp]),
     "sgcn_cv_sampled_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i32, _vp,
@@ -99,6 +101,9 @@ SIGNATURES = {
     "sgcn_step_destroy": (None, [_vp]),
     "sgcn_step_run": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "sgcn_step_run_ahead": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "sgcn_step_run_trains": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp]),
+    "sgcn_full_history_mean_ov": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,
+                                         _vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
     "sgcn_wb_payload_bytes": (_i64, [_i32, _i32]),
     "sgcn_wb_pack": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), _i32, _i32, _vp]),
     "sgcn_wb_push": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), C.POINTER(_vp), _i32,
@@ -123,7 +128,8 @@ class StepDesc(C.Structure):
                 ("d_out", _vp), ("ld_dout", _i64), ("dx", _vp), ("ld_dx", _i64), ("slot_bytes", _i64),
                 ("dst_even", _vp * 16), ("dst_odd", _vp * 16), ("peer_flags", _vp * 16),
                 ("recv_even", _vp), ("recv_odd", _vp), ("flags", _vp), ("epoch", _vp), ("timeout_flag", _vp),
-                ("block_counter", _vp), ("owner", _vp)]
+                ("block_counter", _vp), ("owner", _vp),
+                ("x0_alt", _vp * 2), ("dx_alt", _vp), ("train", _i32), ("overlap_write_back", _i32)]
 
 
 _lib = None

@@ -356,6 +356,7 @@ spmm_coo_kernel(const int2* __restrict__ idx2, const float* __restrict__ vals, i
 //           path; partial sums stay in registers across the span and leave through one 128-bit RED
 //           per lane per row segment.
 constexpr int kFullStageRows = 4096;   // row pointers are staged in shared memory up to this many rows
+constexpr int kFullOvMax = 4096;       // override rows (sgcn_full_history_mean_ov) the shared-memory table holds
 constexpr int kFullMacro = 64;         // positions staged per warp per macro-chunk
 constexpr int kFullWarps = kAggThreads / 32;
 
@@ -368,7 +369,14 @@ struct FullArgs {
     int stage_rows;  // row pointers of up to this many output rows are staged in shared memory
     unsigned long long* trace;
     int square;      // use adj_w^2 (tf.square(fadj) @ var_history, gcn/layers.py:338)
+    // row override (sgcn_full_history_mean_ov): history rows of the nodes ov_ids[0 .. *ov_n_dev) are read
+    // from ov_rows instead -- the previous pass's write-back, applied on the fly
+    const int32_t* ov_ids; const int32_t* ov_n_dev; int ov_bound, ov_bits;
+    const float* ov_rows; int64_t ld_ov;
 };
+
+constexpr unsigned short kOvEmpty = 0xffffu;
+__device__ __forceinline__ unsigned ov_hash(int node, int bits) { return ((unsigned)node * 2654435761u) >> (32 - bits); }
 
 template <typename V, int LPR, int VPL>
 __device__ __forceinline__ void full_flush(const FullArgs& a, int row, int gl, V (&acc)[VPL]) {
@@ -402,12 +410,30 @@ full_mean_kernel(const FullArgs a) {
     const int n_out = dev_count(a.n_out_dev, a.n_out);
     if (n_out <= 0) return;
     const bool staged = n_out <= a.stage_rows;
+    // override table (open addressing, 16-bit slots = index into the id list kept beside it)
+    int32_t* s_ovid = s_dyn + 2 * a.stage_rows + 2;
+    unsigned short* s_ovtab = (unsigned short*)(s_ovid + a.ov_bound);
+    const int ov_n = a.ov_ids ? min(*a.ov_n_dev, a.ov_bound) : 0;
+    const unsigned ov_mask = (1u << a.ov_bits) - 1u;
+    if (ov_n > 0) {
+        for (int i = threadIdx.x; i < (1 << a.ov_bits); i += kAggThreads) s_ovtab[i] = kOvEmpty;
+        for (int i = threadIdx.x; i < ov_n; i += kAggThreads) s_ovid[i] = __ldg(a.ov_ids + i);
+    }
     if (staged) {
         for (int i = threadIdx.x; i <= n_out; i += kAggThreads) s_ptr[i] = __ldg(a.rowptr_f + i);
         for (int i = threadIdx.x; i < n_out; i += kAggThreads)
             s_base[i] = __ldg(a.adj_p + __ldg(a.nodes + i)) - __ldg(a.rowptr_f + i);
+    }
+    if (staged || ov_n > 0) __syncthreads();
+    if (ov_n > 0) {
+        for (int i = threadIdx.x; i < ov_n; i += kAggThreads) {      // ids are distinct
+            unsigned h = ov_hash(s_ovid[i], a.ov_bits);
+            while (atomicCAS(s_ovtab + h, kOvEmpty, (unsigned short)i) != kOvEmpty) h = (h + 1) & ov_mask;
+        }
         __syncthreads();
     }
+    // element offset (relative to hist) of override row i
+    const int64_t ov_base = a.ov_rows ? (int64_t)(((intptr_t)a.ov_rows - (intptr_t)a.hist) / (intptr_t)sizeof(float)) : 0;
     const int32_t* ptr = staged ? s_ptr : a.rowptr_f;
     const int nnz = ptr[n_out];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -444,7 +470,10 @@ full_mean_kernel(const FullArgs a) {
 #pragma unroll
     for (int k = 0; k < VPL; ++k) acc[k] = T::zero();
     int cur = -1;                                                 // row this group is accumulating
-    grid_dep_wait();                                              // (PDL) history rows: after the write-back
+    // (PDL) history rows: after the write-back.  With the row override the stream predecessor is the
+    // previous pass's full-neighbour mean, which writes nothing this kernel reads: the wait moves to
+    // the end (completion order only) and the two kernels overlap tail to head.
+    if (!a.ov_ids) grid_dep_wait();
 
   for (;;) {
     int next_chunk = 0;
@@ -469,7 +498,17 @@ full_mean_kernel(const FullArgs a) {
                 r = lo;
                 const int q = staged ? (s_base[lo] + p)
                                      : (__ldg(a.adj_p + __ldg(a.nodes + lo)) + (p - ptr[lo]));
-                off = (int64_t)__ldg(a.adj_i + q) * a.ld_h;
+                const int col = __ldg(a.adj_i + q);
+                off = (int64_t)col * a.ld_h;
+                if (ov_n > 0) {
+                    unsigned h = ov_hash(col, a.ov_bits);
+                    for (;;) {
+                        const unsigned short sl = s_ovtab[h];
+                        if (sl == kOvEmpty) break;
+                        if (s_ovid[sl] == col) { off = ov_base + (int64_t)sl * a.ld_ov; break; }
+                        h = (h + 1) & ov_mask;
+                    }
+                }
                 w = __ldg(a.adj_w + q);
                 if (a.square) w *= w;
             }
@@ -537,6 +576,7 @@ full_mean_kernel(const FullArgs a) {
     p1 = min(p0 + kFullMacro, nnz);
   }
     if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
+    if (a.ov_ids) grid_dep_wait();
 }
 
 // ---- full-neighbour history mean, bulk-copy (TMA engine) variant ---------------------------------
@@ -1041,7 +1081,9 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
                                   const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
                                   const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
                                   float* y0, int64_t ld_y0, float* y1, int64_t ld_y1,
-                                  int32_t* work_counter, int square, void* stream) {
+                                  int32_t* work_counter, int square, void* stream,
+                                  const int32_t* ov_ids = nullptr, const int32_t* ov_n_dev = nullptr,
+                                  int ov_bound = 0, const float* ov_rows = nullptr, int64_t ld_ov = 0) {
     SGCN_REQUIRE(n_out >= 0 && D >= 0, "full_history_mean: negative size");
     if (n_out == 0 || D == 0) return SGCN_OK;
     SGCN_REQUIRE(nodes && rowptr_f && adj_p && adj_i && adj_w && hist && y0,
@@ -1052,10 +1094,19 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
                         aligned16(y0) && (!y1 || (ld_y1 % 4 == 0 && aligned16(y1)));
     const Shape sh = pick_shape(D, vec_ok);
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_full_variant == 1 && vec_ok && D <= 128 && n_out <= kFullStageRows) {
+    int ov_bits = 0;
+    if (ov_ids) {
+        SGCN_REQUIRE(ov_n_dev && ov_rows && ov_bound > 0 && ov_bound <= kFullOvMax && ld_ov >= D,
+                     "full_history_mean_ov: bad override arguments (at most 4096 override rows)");
+        SGCN_REQUIRE(vec_ok ? (ld_ov % 4 == 0 && aligned16(ov_rows)) : true,
+                     "full_history_mean_ov: override rows must be aligned like the history rows");
+        ov_bits = 4;
+        while ((1 << ov_bits) < 2 * ov_bound) ++ov_bits;
+    }
+    if (g_full_variant == 1 && vec_ok && D <= 128 && n_out <= kFullStageRows && !ov_ids) {
         FullTmaCfg cfg = g_tma_cfg;
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0, ld_y0, y1, ld_y1,
-                   nullptr, n_out, g_trace, square};
+                   nullptr, n_out, g_trace, square, nullptr, nullptr, 0, 0, nullptr, 0};
         const size_t fixed = 12 * (size_t)kTmaMeta + sizeof(int32_t) * (2 * (size_t)n_out + 2) + 128;
         const size_t stage = (size_t)cfg.rows * D * 4;
         while (cfg.depth > 1 && fixed + (size_t)cfg.warps * cfg.depth * (stage + 8) > 226 * 1024) --cfg.depth;
@@ -1075,8 +1126,10 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist + c0, ld_h,
                    std::min(sh.tile, D - c0), y0 + c0, ld_y0, y1 ? y1 + c0 : nullptr, ld_y1,
                    D <= sh.tile ? work_counter : nullptr,    // one launch per counter reset
-                   std::min(n_out, kFullStageRows), g_trace, square};
-        const size_t dyn = sizeof(int32_t) * (2 * (size_t)a.stage_rows + 2);
+                   std::min(n_out, kFullStageRows), g_trace, square,
+                   ov_ids, ov_n_dev, ov_ids ? ov_bound : 0, ov_bits, ov_rows ? ov_rows + c0 : nullptr, ld_ov};
+        const size_t dyn = sizeof(int32_t) * (2 * (size_t)a.stage_rows + 2) +
+                           (ov_ids ? sizeof(int32_t) * (size_t)ov_bound + sizeof(unsigned short) * ((size_t)1 << ov_bits) : 0);
         // one resident wave: every CTA the SMs can hold at once, spans cut accordingly
 #define CALL(V, L, P)                                                                        \
     do {                                                                                     \
@@ -1089,7 +1142,7 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
                                            cudaFuncAttributePreferredSharedMemoryCarveout, 44)); \
             SGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                         \
                 &per_sm, full_mean_kernel<V, L, P>, kAggThreads,                             \
-                sizeof(int32_t) * (2 * (size_t)kFullStageRows + 2)));                        \
+                sizeof(int32_t) * (2 * (size_t)kFullStageRows + 2 + kFullOvMax) + 2 * 2 * kFullOvMax)); \
             if (per_sm < 1) per_sm = 1;                                                      \
         }                                                                                    \
         SGCN_CUDA(launch_pdl(full_mean_kernel<V, L, P>, kNumSMs * per_sm, kAggThreads, dyn, st, a)); \
@@ -1132,6 +1185,17 @@ int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_
                            void* stream) {
     return full_history_mean_impl(nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0,
                                   ld_y0, y1, ld_y1, work_counter, 0, stream);
+}
+
+int sgcn_full_history_mean_ov(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
+                              const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
+                              const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
+                              float* y0, int64_t ld_y0, float* y1, int64_t ld_y1,
+                              const int32_t* ov_ids, const int32_t* ov_n_dev, int32_t ov_bound,
+                              const float* ov_rows, int64_t ld_ov, void* stream) {
+    SGCN_REQUIRE(ov_ids, "full_history_mean_ov: null override id list");
+    return full_history_mean_impl(nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0,
+                                  ld_y0, y1, ld_y1, nullptr, 0, stream, ov_ids, ov_n_dev, ov_bound, ov_rows, ld_ov);
 }
 
 int sgcn_full_history_mean_sq(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,

@@ -94,7 +94,7 @@ struct sgcn_sampler {
         int cur = 0;                          // number of expands since start_batch
         std::vector<Level> levels;
     };
-    static constexpr int kSlots = 3;      // lookahead of up to two batches
+    static constexpr int kSlots = 128;    // buffer sets: 3 for one- / two-batch lookahead, 2 x train for trains
     Slot slots[kSlots];
     int cur_slot = 0;
     Slot& sl() { return slots[cur_slot]; }
@@ -102,6 +102,11 @@ struct sgcn_sampler {
     bool pipeline = false;
     // pipelining guards (device): {number of expands finished, number of consumer passes finished}
     int32_t* pipe_counters = nullptr;
+    // trains of batches (sgcn_sampler_expand_train): device copies of the sets' level-0 pointers, the raw
+    // engine stream and the control block
+    DevBuf train_sets, train_raw, train_ctl;
+    int train_n_sets = 0, train_batch = 0, train_degree = 0;
+    std::vector<void*> train_field_ptrs;     // host copy of the field pointers (stale-pointer check)
     // scratch
     DevBuf take, deg, draws, rank, tile_sums, pool_mass, tree, hits;
     int32_t* host_meta = nullptr;   // pinned
@@ -619,6 +624,249 @@ __device__ __forceinline__ bool hash_has(const int32_t* keys, int mask, int shif
     }
 }
 
+// The fused expand is written as three block-wide phases over a context of shared-memory scratch,
+// inputs and outputs, so that the one-batch kernel (expand_fused_kernel) and the many-batch kernel
+// (expand_train_kernel: one CTA per batch of a whole train of batches) run the very same code.
+struct FusedCtx {
+    // shared-memory scratch
+    int32_t* s_rowptr;       // nb + 1
+    int32_t* s_eslot;        // sb: hash slot of each edge's target
+    uint32_t* s_u;           // sb: draws, later the first-occurrence ranks
+    int32_t* s_keys;         // hsize: node id or -1
+    int32_t* s_vals;         // hsize: smallest claiming position
+    int32_t* s_warp;         // 33
+    int* s_status;
+    int hmask, hshift;
+    // inputs
+    const int32_t* field_in; int n_out, sb;
+    const int32_t* adj_p; int32_t* adj_i; float* adj_w; int N, degree, cv;
+    // outputs
+    int32_t* field; int32_t* rowptr_s; int32_t* rowptr_f; int32_t* edg_s; int32_t* edg_t;
+    int32_t* tgt; float* edg_w; float* medg_w; float* scales;
+};
+
+// rows + both prefix sums, NT * IPT rows per sweep with a carry; old field -> table (value =
+// position).  Every thread owns IPT CONSECUTIVE rows and issues their dependent loads together
+// (ids -> row pointers), so the narrow co-resident variant pays one round trip per sweep, not IPT.
+template <int NT, int IPT>
+__device__ __forceinline__ void fused_rows_phase(const FusedCtx& c, int& carry_s, int& carry_f) {
+    const int tid = threadIdx.x;
+    carry_s = 0; carry_f = 0;
+    for (int base = 0; base < c.n_out; base += NT * IPT) {
+        int node[IPT], take[IPT], d[IPT], b0[IPT], b1[IPT];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int i = base + tid * IPT + q;
+            node[q] = i < c.n_out ? c.field_in[i] : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const bool in_range = node[q] >= 0 && node[q] < c.N;
+            b0[q] = in_range ? c.adj_p[node[q]] : 0;
+            b1[q] = in_range ? c.adj_p[node[q] + 1] : 0;
+        }
+        int sum_s = 0, sum_f = 0;
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int i = base + tid * IPT + q;
+            take[q] = 0; d[q] = 0;
+            if (i < c.n_out) {
+                c.field[i] = node[q];
+                if (node[q] < 0 || node[q] >= c.N) {
+                    atomicOr(c.s_status, ST_RANGE);
+                    c.scales[i] = 1.f;
+                } else {
+                    d[q] = b1[q] - b0[q];
+                    take[q] = min(d[q], c.degree);
+                    const float scale = (d[q] == 0) ? 1.f : __fdiv_rn((float)d[q], (float)take[q]);
+                    c.scales[i] = (float)(1.0 / (double)__fsqrt_rn(scale));
+                    const int h = hash_claim(c.s_keys, c.hmask, c.hshift, node[q]);
+                    if (atomicMin(c.s_vals + h, i) != kUnseen) atomicOr(c.s_status, ST_DUPLICATE);
+                }
+            }
+            sum_s += take[q];
+            sum_f += c.cv ? d[q] : 0;
+        }
+        int tot_s, tot_f;
+        int ex_s = block_scan_excl_nt<NT>(sum_s, &tot_s, c.s_warp);
+        int ex_f = block_scan_excl_nt<NT>(sum_f, &tot_f, c.s_warp);
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int i = base + tid * IPT + q;
+            if (i < c.n_out) {
+                c.s_rowptr[i] = carry_s + ex_s;
+                c.rowptr_s[i] = carry_s + ex_s;
+                c.rowptr_f[i] = carry_f + ex_f;
+            }
+            ex_s += take[q];
+            ex_f += c.cv ? d[q] : 0;
+        }
+        carry_s += tot_s;
+        carry_f += tot_f;
+    }
+    if (tid == 0) {
+        c.s_rowptr[c.n_out] = carry_s;
+        c.rowptr_s[c.n_out] = carry_s;
+        c.rowptr_f[c.n_out] = carry_f;
+        if (carry_s > c.sb) *c.s_status |= ST_OVERFLOW;
+    }
+}
+
+// per-row partial Fisher-Yates on the stored row (rows of one field are disjoint).  A thread walks
+// IPT consecutive rows in three phases -- ids + row pointers, the touched row entries, swap +
+// emit -- so the dependent global round trips of its rows overlap instead of queueing.
+// (the draws of this batch are in c.s_u[0 .. nnz))
+template <int NT, int IPT>
+__device__ __forceinline__ void fused_shuffle_phase(const FusedCtx& c) {
+    const int tid = threadIdx.x;
+    const int n_out = c.n_out;
+    for (int base = 0; base < n_out; base += NT * IPT) {
+        int e0[IPT], take[IPT], d[IPT], rb[IPT];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int i = base + tid * IPT + q;
+            take[q] = 0; e0[q] = 0; d[q] = 0; rb[q] = 0;
+            if (i < n_out) {
+                e0[q] = c.s_rowptr[i];
+                take[q] = c.s_rowptr[i + 1] - e0[q];
+                if (take[q] <= 0 || e0[q] + take[q] > c.sb) take[q] = 0;
+            }
+        }
+        int node[IPT];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) node[q] = take[q] > 0 ? c.field_in[base + tid * IPT + q] : 0;
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            if (take[q] > 0) {
+                rb[q] = c.adj_p[node[q]];
+                d[q] = c.adj_p[node[q] + 1] - rb[q];
+            }
+        }
+        // draws of the rows that take <= 2 entries: every touched position is known from the draws
+        // alone -- fetch them all at once, replay the <= 2 swaps on the local copy, store once
+        int pos[IPT][4], cv4[IPT][4];
+        float wv4[IPT][4];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            if (take[q] > 0 && take[q] <= 2) {
+                auto draw_index = [&](int k) {
+                    // idx = min((int)(it + num_remaining * u01(generator)), adj_range-1)  (scheduler.cpp:141-143)
+                    const float u = mt_canonical(c.s_u[e0[q] + k]);
+                    const int j = (int)__fadd_rn((float)k, __fmul_rn((float)(d[q] - k), u));
+                    return min(j, d[q] - 1);
+                };
+                const int j0 = draw_index(0);
+                const int j1 = take[q] == 2 ? draw_index(1) : j0;
+                pos[q][0] = 0; pos[q][1] = j0; pos[q][2] = take[q] == 2 ? 1 : 0; pos[q][3] = j1;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    cv4[q][x] = c.adj_i[rb[q] + pos[q][x]];
+                    wv4[q][x] = c.adj_w[rb[q] + pos[q][x]];
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            if (take[q] <= 0) continue;
+            const int i = base + tid * IPT + q;
+            int32_t* rc = c.adj_i + rb[q];
+            float* rw = c.adj_w + rb[q];
+            const float scale = __fdiv_rn((float)d[q], (float)take[q]);
+            auto emit = [&](int k, int t, float wv) {
+                const float w = __fmul_rn(wv, scale);
+                const int e = e0[q] + k;
+                c.edg_s[e] = i;
+                c.tgt[e] = t;
+                c.edg_w[e] = w;
+                if (c.cv) c.medg_w[e] = __fmul_rn(wv, w);
+                const int h = hash_claim(c.s_keys, c.hmask, c.hshift, t);
+                atomicMin(c.s_vals + h, n_out + e);
+                c.s_eslot[e] = h;
+            };
+            if (take[q] <= 2) {
+                auto rd = [&](int x, int& cc, float& w) {
+#pragma unroll
+                    for (int y = 3; y >= 0; --y)
+                        if (pos[q][y] == x) { cc = cv4[q][y]; w = wv4[q][y]; }
+                };
+                auto wr = [&](int x, int cc, float w) {
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+                        if (pos[q][y] == x) { cv4[q][y] = cc; wv4[q][y] = w; }
+                };
+                for (int k = 0; k < take[q]; ++k) {
+                    const int j = k == 0 ? pos[q][1] : pos[q][3];
+                    int ck = 0, cj = 0;
+                    float wk = 0.f, wj = 0.f;
+                    rd(k, ck, wk);
+                    rd(j, cj, wj);
+                    wr(k, cj, wj);
+                    wr(j, ck, wk);
+                    emit(k, cj, wj);
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    rc[pos[q][x]] = cv4[q][x];
+                    rw[pos[q][x]] = wv4[q][x];
+                }
+            } else {
+                for (int k = 0; k < take[q]; ++k) {
+                    const float u = mt_canonical(c.s_u[e0[q] + k]);
+                    const int j = min((int)__fadd_rn((float)k, __fmul_rn((float)(d[q] - k), u)), d[q] - 1);
+                    const int ck = rc[k], cj = rc[j];
+                    const float wk = rw[k], wj = rw[j];
+                    rc[k] = cj; rc[j] = ck;
+                    rw[k] = wj; rw[j] = wk;
+                    emit(k, cj, wj);
+                }
+            }
+        }
+    }
+}
+
+// first-occurrence flags -> ranks (reuse the draw buffer) -> column indices + the grown field.
+// Returns the number of newly met nodes.
+template <int NT>
+__device__ __forceinline__ int fused_number_phase(const FusedCtx& c, int nnz) {
+    const int tid = threadIdx.x;
+    const int n_out = c.n_out;
+    int32_t* s_rank = (int32_t*)c.s_u;
+    int n_new = 0;
+    constexpr int EPT = 4;                                     // consecutive edges per thread per sweep
+    for (int base = 0; base < nnz; base += NT * EPT) {
+        int f[EPT], sum = 0;
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const int e = base + tid * EPT + q;
+            f[q] = (e < nnz && c.s_vals[c.s_eslot[e]] == n_out + e) ? 1 : 0;
+            sum += f[q];
+        }
+        int tot;
+        int ex = block_scan_excl_nt<NT>(sum, &tot, c.s_warp);
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const int e = base + tid * EPT + q;
+            if (e < nnz) s_rank[e] = n_new + ex;
+            ex += f[q];
+        }
+        n_new += tot;
+    }
+    __syncthreads();
+    for (int e = tid; e < nnz; e += NT) {
+        const int h = c.s_eslot[e];
+        const int sl = c.s_vals[h];
+        if (sl < n_out) {
+            c.edg_t[e] = sl;
+        } else {
+            const int e_first = sl - n_out;
+            const int pos = n_out + s_rank[e_first];
+            c.edg_t[e] = pos;
+            if (e_first == e) c.field[pos] = c.s_keys[h];
+        }
+    }
+    return n_new;
+}
+
 // NT = 1024: fastest stand-alone.  NT = 256 (<= 48 registers): small enough to sit in the registers
 // two resident full_mean_kernel CTAs leave free on an SM, so that in the pipelined step the next
 // batch's sampler really runs BESIDE the aggregate instead of waiting for an empty SM.
@@ -655,68 +903,11 @@ expand_fused_kernel(const FusedArgs a) {
     }
     __syncthreads();
 
-    // rows + both prefix sums, NT * IPT rows per sweep with a carry; old field -> table (value =
-    // position).  Every thread owns IPT CONSECUTIVE rows and issues their dependent loads together
-    // (ids -> row pointers), so the narrow co-resident variant pays one round trip per sweep, not IPT.
-    int carry_s = 0, carry_f = 0;
-    for (int base = 0; base < n_out; base += NT * IPT) {
-        int node[IPT], take[IPT], d[IPT], b0[IPT], b1[IPT];
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            const int i = base + tid * IPT + q;
-            node[q] = i < n_out ? a.field_in[i] : -1;
-        }
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            const bool in_range = node[q] >= 0 && node[q] < a.N;
-            b0[q] = in_range ? a.adj_p[node[q]] : 0;
-            b1[q] = in_range ? a.adj_p[node[q] + 1] : 0;
-        }
-        int sum_s = 0, sum_f = 0;
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            const int i = base + tid * IPT + q;
-            take[q] = 0; d[q] = 0;
-            if (i < n_out) {
-                a.field[i] = node[q];
-                if (node[q] < 0 || node[q] >= a.N) {
-                    atomicOr(&s_status, ST_RANGE);
-                    a.scales[i] = 1.f;
-                } else {
-                    d[q] = b1[q] - b0[q];
-                    take[q] = min(d[q], a.degree);
-                    const float scale = (d[q] == 0) ? 1.f : __fdiv_rn((float)d[q], (float)take[q]);
-                    a.scales[i] = (float)(1.0 / (double)__fsqrt_rn(scale));
-                    const int h = hash_claim(s_keys, hmask, hshift, node[q]);
-                    if (atomicMin(s_vals + h, i) != kUnseen) atomicOr(&s_status, ST_DUPLICATE);
-                }
-            }
-            sum_s += take[q];
-            sum_f += a.cv ? d[q] : 0;
-        }
-        int tot_s, tot_f;
-        int ex_s = block_scan_excl_nt<NT>(sum_s, &tot_s, s_warp);
-        int ex_f = block_scan_excl_nt<NT>(sum_f, &tot_f, s_warp);
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            const int i = base + tid * IPT + q;
-            if (i < n_out) {
-                s_rowptr[i] = carry_s + ex_s;
-                a.rowptr_s[i] = carry_s + ex_s;
-                a.rowptr_f[i] = carry_f + ex_f;
-            }
-            ex_s += take[q];
-            ex_f += a.cv ? d[q] : 0;
-        }
-        carry_s += tot_s;
-        carry_f += tot_f;
-    }
-    if (tid == 0) {
-        s_rowptr[n_out] = carry_s;
-        a.rowptr_s[n_out] = carry_s;
-        a.rowptr_f[n_out] = carry_f;
-        if (carry_s > a.sb) s_status |= ST_OVERFLOW;
-    }
+    const FusedCtx c{s_rowptr, s_eslot, s_u, s_keys, s_vals, s_warp, &s_status, hmask, hshift,
+                     a.field_in, n_out, a.sb, a.adj_p, a.adj_i, a.adj_w, a.N, a.degree, a.cv,
+                     a.field, a.rowptr_s, a.rowptr_f, a.edg_s, a.edg_t, a.tgt, a.edg_w, a.medg_w, a.scales};
+    int carry_s, carry_f;
+    fused_rows_phase<NT, IPT>(c, carry_s, carry_f);
     const int nnz = min(carry_s, a.sb);
 
     // the next nnz engine outputs -> shared memory
@@ -762,148 +953,9 @@ expand_fused_kernel(const FusedArgs a) {
         __syncthreads();
     }
 
-    // per-row partial Fisher-Yates on the stored row (rows of one field are disjoint).  A thread walks
-    // IPT consecutive rows in three phases -- ids + row pointers, the touched row entries, swap +
-    // emit -- so the dependent global round trips of its rows overlap instead of queueing.
-    for (int base = 0; base < n_out; base += NT * IPT) {
-        int e0[IPT], take[IPT], d[IPT], rb[IPT];
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            const int i = base + tid * IPT + q;
-            take[q] = 0; e0[q] = 0; d[q] = 0; rb[q] = 0;
-            if (i < n_out) {
-                e0[q] = s_rowptr[i];
-                take[q] = s_rowptr[i + 1] - e0[q];
-                if (take[q] <= 0 || e0[q] + take[q] > a.sb) take[q] = 0;
-            }
-        }
-        int node[IPT];
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) node[q] = take[q] > 0 ? a.field_in[base + tid * IPT + q] : 0;
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            if (take[q] > 0) {
-                rb[q] = a.adj_p[node[q]];
-                d[q] = a.adj_p[node[q] + 1] - rb[q];
-            }
-        }
-        // draws of the rows that take <= 2 entries: every touched position is known from the draws
-        // alone -- fetch them all at once, replay the <= 2 swaps on the local copy, store once
-        int pos[IPT][4], cv4[IPT][4];
-        float wv4[IPT][4];
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            if (take[q] > 0 && take[q] <= 2) {
-                auto draw_index = [&](int k) {
-                    // idx = min((int)(it + num_remaining * u01(generator)), adj_range-1)  (scheduler.cpp:141-143)
-                    const float u = mt_canonical(s_u[e0[q] + k]);
-                    const int j = (int)__fadd_rn((float)k, __fmul_rn((float)(d[q] - k), u));
-                    return min(j, d[q] - 1);
-                };
-                const int j0 = draw_index(0);
-                const int j1 = take[q] == 2 ? draw_index(1) : j0;
-                pos[q][0] = 0; pos[q][1] = j0; pos[q][2] = take[q] == 2 ? 1 : 0; pos[q][3] = j1;
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    cv4[q][x] = a.adj_i[rb[q] + pos[q][x]];
-                    wv4[q][x] = a.adj_w[rb[q] + pos[q][x]];
-                }
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            if (take[q] <= 0) continue;
-            const int i = base + tid * IPT + q;
-            int32_t* rc = a.adj_i + rb[q];
-            float* rw = a.adj_w + rb[q];
-            const float scale = __fdiv_rn((float)d[q], (float)take[q]);
-            auto emit = [&](int k, int t, float wv) {
-                const float w = __fmul_rn(wv, scale);
-                const int e = e0[q] + k;
-                a.edg_s[e] = i;
-                a.tgt[e] = t;
-                a.edg_w[e] = w;
-                if (a.cv) a.medg_w[e] = __fmul_rn(wv, w);
-                const int h = hash_claim(s_keys, hmask, hshift, t);
-                atomicMin(s_vals + h, n_out + e);
-                s_eslot[e] = h;
-            };
-            if (take[q] <= 2) {
-                auto rd = [&](int x, int& c, float& w) {
-#pragma unroll
-                    for (int y = 3; y >= 0; --y)
-                        if (pos[q][y] == x) { c = cv4[q][y]; w = wv4[q][y]; }
-                };
-                auto wr = [&](int x, int c, float w) {
-#pragma unroll
-                    for (int y = 0; y < 4; ++y)
-                        if (pos[q][y] == x) { cv4[q][y] = c; wv4[q][y] = w; }
-                };
-                for (int k = 0; k < take[q]; ++k) {
-                    const int j = k == 0 ? pos[q][1] : pos[q][3];
-                    int ck = 0, cj = 0;
-                    float wk = 0.f, wj = 0.f;
-                    rd(k, ck, wk);
-                    rd(j, cj, wj);
-                    wr(k, cj, wj);
-                    wr(j, ck, wk);
-                    emit(k, cj, wj);
-                }
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    rc[pos[q][x]] = cv4[q][x];
-                    rw[pos[q][x]] = wv4[q][x];
-                }
-            } else {
-                for (int k = 0; k < take[q]; ++k) {
-                    const float u = mt_canonical(s_u[e0[q] + k]);
-                    const int j = min((int)__fadd_rn((float)k, __fmul_rn((float)(d[q] - k), u)), d[q] - 1);
-                    const int ck = rc[k], cj = rc[j];
-                    const float wk = rw[k], wj = rw[j];
-                    rc[k] = cj; rc[j] = ck;
-                    rw[k] = wj; rw[j] = wk;
-                    emit(k, cj, wj);
-                }
-            }
-        }
-    }
+    fused_shuffle_phase<NT, IPT>(c);
     __syncthreads();
-
-    // first-occurrence flags -> ranks (reuse the draw buffer)
-    int32_t* s_rank = (int32_t*)s_u;
-    int n_new = 0;
-    constexpr int EPT = 4;                                     // consecutive edges per thread per sweep
-    for (int base = 0; base < nnz; base += NT * EPT) {
-        int f[EPT], sum = 0;
-#pragma unroll
-        for (int q = 0; q < EPT; ++q) {
-            const int e = base + tid * EPT + q;
-            f[q] = (e < nnz && s_vals[s_eslot[e]] == n_out + e) ? 1 : 0;
-            sum += f[q];
-        }
-        int tot;
-        int ex = block_scan_excl_nt<NT>(sum, &tot, s_warp);
-#pragma unroll
-        for (int q = 0; q < EPT; ++q) {
-            const int e = base + tid * EPT + q;
-            if (e < nnz) s_rank[e] = n_new + ex;
-            ex += f[q];
-        }
-        n_new += tot;
-    }
-    __syncthreads();
-    for (int e = tid; e < nnz; e += NT) {
-        const int h = s_eslot[e];
-        const int sl = s_vals[h];
-        if (sl < n_out) {
-            a.edg_t[e] = sl;
-        } else {
-            const int e_first = sl - n_out;
-            const int pos = n_out + s_rank[e_first];
-            a.edg_t[e] = pos;
-            if (e_first == e) a.field[pos] = s_keys[h];
-        }
-    }
+    const int n_new = fused_number_phase<NT>(c, nnz);
     if (tid == 0) {
         a.meta[M_NOUT] = n_out;
         a.meta[M_NIN] = n_out + n_new;
@@ -913,6 +965,229 @@ expand_fused_kernel(const FusedArgs a) {
         a.meta[M_STATUS] = s_status;
         a.meta[M_AUX] = 0;
         if (a.pipe) a.pipe[0] = a.pipe[0] + 1;
+    }
+}
+
+// ---- a whole TRAIN of batches in one launch ---------------------------------------------------------
+// The reference's Scheduler is sequential: batch after batch consumes one mt19937 stream and permutes
+// the stored rows in place.  Between consecutive batches there are only two real dependencies: (1) the
+// stream offset of batch j = the number of draws of batches < j, known as soon as their row degrees are
+// (one load round trip), and (2) the stored row of a node that occurs in two batches.  So a train of n
+// batches is sampled by ONE launch of n CTAs (one batch each, the same three phases as above):
+//   * mt_stream_kernel first lays the next n * B * degree engine outputs out in HBM as raw state
+//     blocks (block 0 = the engine's current state, block b = its b-th regeneration);
+//   * a CTA takes a ticket j (order of arrival: it only ever waits for tickets < j, which are held by
+//     CTAs already running -- no co-residency assumption), runs the rows phase of batch j, publishes
+//     its draw count, sums the counts of tickets < j into its stream offset, tempers its draws out of
+//     the raw blocks, shuffles and numbers;
+//   * a batch that shares a node with an EARLIER batch of the train waits for those CTAs to finish
+//     (order of the in-place permutations); one that shares a node with a batch of the PREVIOUS train
+//     (which may still be read by its consumer passes) waits until pipe[1] says they are consumed;
+//   * the last CTA to finish commits the engine: state block + cursor after the train's total draws.
+// Results are bit-identical to n sequential expand calls.
+constexpr int kTrainMax = 64;                 // batches per train
+struct TrainSet {
+    int32_t* field; int32_t* rowptr_s; int32_t* rowptr_f; int32_t* edg_s; int32_t* edg_t; int32_t* tgt;
+    float* edg_w; float* medg_w; float* scales; int32_t* meta;
+};
+struct TrainCtl {
+    int ticket, done;
+    unsigned epoch;          // launches finished (the tag of cnt[] / fin[] entries is epoch + 1)
+    int pos0;                // engine cursor when the raw stream was laid out
+    int status;              // stream buffer too short etc.
+    int pad[3];
+    unsigned long long cnt[kTrainMax];     // (tag << 32) | draws of ticket j
+    unsigned fin[kTrainMax];               // tag once ticket j has finished
+};
+struct TrainArgs {
+    const int32_t* ids; int n, nb, sb;
+    const int32_t* adj_p; int32_t* adj_i; float* adj_w; int N, degree, cv, hbits;
+    const TrainSet* sets; int first_set, n_sets;
+    const uint32_t* raw; int raw_words;
+    TrainCtl* ctl; uint32_t* engine;
+    const int32_t* prev_ids; int prev_n;      // batches of the previous train (consumer passes may still run)
+    int32_t* pipe;                            // {batches sampled, consumer passes finished} or NULL
+    unsigned long long* trace;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// raw[b * 624 + i] = word i of the engine's state after b regenerations (b = 0: the current state), for
+// as many blocks as `need` further draws can touch.  One CTA.
+static __global__ void __launch_bounds__(kMtThreads)
+mt_stream_kernel(const uint32_t* __restrict__ engine, int need, uint32_t* __restrict__ raw, int raw_words,
+                 TrainCtl* __restrict__ ctl) {
+    __shared__ uint32_t x[kMtN];
+    for (int i = threadIdx.x; i < kMtN; i += kMtThreads) {
+        x[i] = engine[i];
+        raw[i] = x[i];
+    }
+    const int pos0 = (int)engine[kMtN];
+    __syncthreads();
+    const int blocks = (pos0 + need + kMtN - 1) / kMtN;        // blocks 0 .. blocks-1 are touched
+    int b = 1;
+    for (; b < blocks && (b + 1) * kMtN <= raw_words; ++b) {
+        mt_regen_block(x);
+        for (int i = threadIdx.x; i < kMtN; i += kMtThreads) raw[b * kMtN + i] = x[i];
+    }
+    if (threadIdx.x == 0) {
+        ctl->pos0 = pos0;
+        ctl->status = b < blocks ? ST_OVERFLOW : 0;
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 4)
+expand_train_kernel(const TrainArgs a) {
+    constexpr int IPT = 2;
+    extern __shared__ int32_t smem[];
+    const int hsize = 1 << a.hbits, hmask = hsize - 1, hshift = 32 - a.hbits;
+    int32_t* s_rowptr = smem;
+    int32_t* s_eslot = s_rowptr + a.nb + 1;
+    uint32_t* s_u = (uint32_t*)(s_eslot + a.sb);
+    int32_t* s_keys = (int32_t*)(s_u + a.sb);
+    int32_t* s_vals = s_keys + hsize;
+    int32_t* s_warp = s_vals + hsize;                          // 33
+    __shared__ int s_status, s_conflict, s_j, s_last, s_seq;
+    __shared__ unsigned s_tag;
+    const int tid = threadIdx.x;
+    TraceScope ts(a.trace, TR_SAMPLER);
+
+    if (tid == 0) {
+        s_tag = ld_acquire_u32(&a.ctl->epoch) + 1u;
+        s_j = atomicAdd(&a.ctl->ticket, 1);
+        s_status = a.ctl->status;
+        s_conflict = 0;
+        s_last = 0;
+        s_seq = a.pipe ? a.pipe[0] : 0;        // batches sampled before this train (stable until the commit)
+    }
+    for (int i = tid; i < hsize; i += NT) {
+        s_keys[i] = -1;
+        s_vals[i] = kUnseen;
+    }
+    __syncthreads();
+    const int j = s_j;
+    const unsigned tag = s_tag;
+    if (j >= a.n) return;
+    const TrainSet set = a.sets[(a.first_set + j) % a.n_sets];
+    const int32_t* field_in = a.ids + (size_t)j * a.nb;
+    const int n_out = a.nb;
+
+    const FusedCtx c{s_rowptr, s_eslot, s_u, s_keys, s_vals, s_warp, &s_status, hmask, hshift,
+                     field_in, n_out, a.sb, a.adj_p, a.adj_i, a.adj_w, a.N, a.degree, a.cv,
+                     set.field, set.rowptr_s, set.rowptr_f, set.edg_s, set.edg_t, set.tgt, set.edg_w,
+                     set.medg_w, set.scales};
+    int carry_s, carry_f;
+    fused_rows_phase<NT, IPT>(c, carry_s, carry_f);
+    const int nnz = min(carry_s, a.sb);
+    if (tid == 0) st_release_u64(&a.ctl->cnt[j], ((unsigned long long)tag << 32) | (unsigned)nnz);
+
+    // stream offset = draws of the tickets before mine
+    int part = 0;
+    for (int i = tid; i < j; i += NT) {
+        unsigned long long v;
+        long long spins = 0;
+        while ((unsigned)((v = ld_acquire_u64(&a.ctl->cnt[i])) >> 32) != tag) {
+            if (++spins > 20000000LL) { atomicOr(&s_status, ST_OVERFLOW); break; }
+            __nanosleep(40);
+        }
+        part += (int)(unsigned)(v & 0xffffffffull);
+    }
+    int off;
+    (void)block_scan_excl_nt<NT>(part, &off, s_warp);
+    const int pos0 = a.ctl->pos0;
+    if (pos0 + off + nnz > a.raw_words) {
+        if (tid == 0) s_status |= ST_OVERFLOW;
+    } else {
+        for (int e = tid; e < nnz; e += NT) s_u[e] = mt_temper(a.raw[pos0 + off + e]);
+    }
+
+    // shared nodes: with an earlier batch of this train (bit 0), with the previous train (bit 1)
+    {
+        const int n_before = j * a.nb;
+        int hit = 0;
+        for (int q = tid; q < n_before; q += NT)
+            if (hash_has(s_keys, hmask, hshift, a.ids[q])) hit |= 1;
+        if (a.pipe)
+            for (int q = tid; q < a.prev_n; q += NT)
+                if (hash_has(s_keys, hmask, hshift, a.prev_ids[q])) hit |= 2;
+        if (hit) atomicOr(&s_conflict, hit);
+    }
+    __syncthreads();
+    if (s_conflict & 1) {
+        for (int i = tid; i < j; i += NT) {
+            long long spins = 0;
+            while (ld_acquire_u32(&a.ctl->fin[i]) != tag) {
+                if (++spins > 20000000LL) { atomicOr(&s_status, ST_OVERFLOW); break; }
+                __nanosleep(100);
+            }
+        }
+    }
+    if ((s_conflict & 2) && tid == 0) {
+        const unsigned* done = (const unsigned*)(a.pipe + 1);
+        long long spins = 0;
+        while ((int)ld_acquire_u32(done) < s_seq) {
+            if (++spins > 20000000LL) { s_status |= ST_OVERFLOW; break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+
+    fused_shuffle_phase<NT, IPT>(c);
+    __syncthreads();
+    const int n_new = fused_number_phase<NT>(c, nnz);
+    __syncthreads();
+    if (tid == 0) {
+        set.meta[M_NOUT] = n_out;
+        set.meta[M_NIN] = n_out + n_new;
+        set.meta[M_NNZS] = nnz;
+        set.meta[M_NNZF] = carry_f;
+        set.meta[M_NFF] = 0;
+        set.meta[M_STATUS] = s_status;
+        set.meta[M_AUX] = 0;
+        __threadfence();                                       // my rows / outputs before my flag
+        st_release_u32(&a.ctl->fin[j], tag);
+        s_last = atomicAdd(&a.ctl->done, 1) == a.n - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // commit: every ticket has published its count before it bumped `done`
+    __threadfence();
+    int mine = 0;
+    for (int i = tid; i < a.n; i += NT) mine += (int)(unsigned)(ld_acquire_u64(&a.ctl->cnt[i]) & 0xffffffffull);
+    int total;
+    (void)block_scan_excl_nt<NT>(mine, &total, s_warp);
+    if (total > 0) {
+        const int p = pos0 + total;
+        int blk = p / kMtN, cur = p % kMtN;
+        if (cur == 0) { blk -= 1; cur = kMtN; }              // libstdc++ regenerates lazily: cursor stays at 624
+        if ((blk + 1) * kMtN <= a.raw_words) {
+            for (int i = tid; i < kMtN; i += NT) a.engine[i] = a.raw[blk * kMtN + i];
+            if (tid == 0) a.engine[kMtN] = (uint32_t)cur;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (a.pipe) a.pipe[0] = s_seq + a.n;
+        a.ctl->ticket = 0;
+        a.ctl->done = 0;
+        __threadfence();
+        st_release_u32(&a.ctl->epoch, tag);
     }
 }
 
@@ -1043,8 +1318,9 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
             attr_set = true;
         }
         const int hbits = fused_hash_bits(nb, (int)sb);
-        const sgcn_sampler::Slot& other = s->slots[(s->cur_slot + 2) % sgcn_sampler::kSlots];
-        const sgcn_sampler::Slot& other2 = s->slots[(s->cur_slot + 1) % sgcn_sampler::kSlots];
+        // the one- / two-batch lookahead drivers rotate over buffer sets 0..2
+        const sgcn_sampler::Slot& other = s->slots[(s->cur_slot + 2) % 3];
+        const sgcn_sampler::Slot& other2 = s->slots[(s->cur_slot + 1) % 3];
         const bool piped = s->pipeline && s->sl().cur == 0;
         FusedArgs fa{field_in, n_ptr, nb, nb, (int)sb, s->adj_p, s->adj_i, s->adj_w, s->N, degree,
                      s->cv ? 1 : 0, hbits,
@@ -1379,7 +1655,7 @@ void sgcn_sampler_destroy(sgcn_sampler* s) {
     }
     cudaFree(s->pipe_counters);
     for (DevBuf* b : {&s->batch_meta, &s->take, &s->deg, &s->draws, &s->rank,
-                      &s->tile_sums, &s->pool_mass, &s->tree, &s->hits})
+                      &s->tile_sums, &s->pool_mass, &s->tree, &s->hits, &s->train_sets, &s->train_raw, &s->train_ctl})
         b->release();
     cudaFree(s->adj_w);
     cudaFree(s->adj_i);
@@ -1405,7 +1681,7 @@ int sgcn_sampler_seed(sgcn_sampler* s, int32_t seed) {
 }
 
 int sgcn_sampler_set_slot(sgcn_sampler* s, int32_t slot) {
-    SGCN_REQUIRE(s && slot >= 0 && slot < sgcn_sampler::kSlots, "sampler_set_slot: slot must be 0, 1 or 2");
+    SGCN_REQUIRE(s && slot >= 0 && slot < sgcn_sampler::kSlots, "sampler_set_slot: no such buffer set");
     s->cur_slot = slot;
     return SGCN_OK;
 }
@@ -1517,6 +1793,99 @@ int sgcn_sampler_expand(sgcn_sampler* s, int32_t degree, int32_t materialize_ful
     if (rc != SGCN_OK) return rc;
     lv.done = true;
     s->sl().cur = k + 1;
+    return SGCN_OK;
+}
+
+
+int sgcn_sampler_reserve_sets(sgcn_sampler* s, int32_t n_sets, int32_t batch, int32_t degree) {
+    SGCN_REQUIRE(s && n_sets >= 1 && n_sets <= sgcn_sampler::kSlots && batch >= 1 && degree >= 0,
+                 "sampler_reserve_sets: bad argument");
+    SGCN_REQUIRE(!s->is, "sampler_reserve_sets: trains of batches exist for the uniform branch only");
+    const int64_t sb = sample_bound(s, batch, degree);
+    SGCN_REQUIRE(degree <= kExactSizingDegree && batch <= kFusedMaxRows && sb <= kFusedMaxEdges,
+                 "sampler_reserve_sets: batch / degree beyond the fused sampler's bounds");
+    DeviceGuard guard(s->device);
+    const int keep = s->cur_slot;
+    std::vector<TrainSet> sets((size_t)n_sets);
+    s->train_field_ptrs.assign((size_t)n_sets, nullptr);
+    for (int k = 0; k < n_sets; ++k) {
+        s->cur_slot = k;
+        if (s->sl().levels.empty()) s->sl().levels.resize(1);
+        Level& lv = s->sl().levels[0];
+        SGCN_TRY(s->sl().batch_ids.ensure(sizeof(int32_t) * (size_t)batch));
+        SGCN_TRY(ensure_level(s, lv, batch, sb, true));
+        SGCN_TRY(lv.medg_w.ensure(sizeof(float) * (size_t)std::max<int64_t>(sb, 1)));
+        sets[(size_t)k] = TrainSet{lv.field.as<int32_t>(), lv.rowptr_s.as<int32_t>(), lv.rowptr_f.as<int32_t>(),
+                                   lv.edg_s.as<int32_t>(), lv.edg_t.as<int32_t>(), lv.tgt.as<int32_t>(),
+                                   lv.edg_w.as<float>(), lv.medg_w.as<float>(), lv.scales.as<float>(),
+                                   lv.meta.as<int32_t>()};
+        s->train_field_ptrs[(size_t)k] = lv.field.p;
+    }
+    s->cur_slot = keep;
+    SGCN_TRY(s->batch_meta.ensure(sizeof(int32_t) * kMetaInts));
+    SGCN_TRY(s->train_sets.ensure(sizeof(TrainSet) * (size_t)n_sets));
+    SGCN_TRY(s->train_raw.ensure(sizeof(uint32_t) * ((size_t)kTrainMax * (size_t)std::max<int64_t>(sb, 1) + 3 * kMtN)));
+    if (!s->train_ctl.p) {
+        SGCN_TRY(s->train_ctl.ensure(sizeof(TrainCtl)));
+        SGCN_CUDA(cudaMemsetAsync(s->train_ctl.p, 0, sizeof(TrainCtl), s->stream));
+    }
+    SGCN_CUDA(cudaMemcpyAsync(s->train_sets.p, sets.data(), sizeof(TrainSet) * (size_t)n_sets, cudaMemcpyHostToDevice,
+                              s->stream));
+    SGCN_CUDA(cudaStreamSynchronize(s->stream));       // `sets` is a host temporary
+    s->train_n_sets = n_sets;
+    s->train_batch = batch;
+    s->train_degree = degree;
+    return SGCN_OK;
+}
+
+int sgcn_sampler_expand_train(sgcn_sampler* s, const int32_t* ids, int32_t n, int32_t first_set,
+                              const int32_t* prev_ids, int32_t prev_n, void* stream) {
+    SGCN_REQUIRE(s && n >= 0 && (n == 0 || ids) && prev_n >= 0 && (prev_n == 0 || prev_ids),
+                 "sampler_expand_train: bad argument");
+    if (n == 0) return SGCN_OK;
+    if (s->train_n_sets <= 0) {
+        set_error("sampler_expand_train: call sgcn_sampler_reserve_sets first");
+        return SGCN_ESTATE;
+    }
+    SGCN_REQUIRE(n <= kTrainMax && n <= s->train_n_sets && first_set >= 0 && first_set < s->train_n_sets,
+                 "sampler_expand_train: train longer than the reserved buffer sets (or than 64)");
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = s->train_batch, degree = s->train_degree;
+    const int sb = (int)sample_bound(s, B, degree);
+    for (int j = 0; j < n; ++j) {                      // buffers re-allocated since reserve_sets?
+        const int k = (first_set + j) % s->train_n_sets;
+        if (s->slots[k].levels.empty() || s->slots[k].levels[0].field.p != s->train_field_ptrs[(size_t)k]) {
+            set_error("sampler_expand_train: a buffer set was re-allocated; call sgcn_sampler_reserve_sets again");
+            return SGCN_ESTATE;
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SGCN_CUDA(cudaFuncSetAttribute(expand_train_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kFusedSmemBytes));
+        SGCN_CUDA(cudaFuncSetAttribute(expand_train_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, 44));
+        attr_set = true;
+    }
+    const int hbits = fused_hash_bits(B, sb);
+    const int raw_words = (int)(s->train_raw.cap / sizeof(uint32_t));
+    mt_stream_kernel<<<1, kMtThreads, 0, st>>>(s->engine, n * sb, s->train_raw.as<uint32_t>(), raw_words,
+                                              s->train_ctl.as<TrainCtl>());
+    SGCN_LAUNCHED();
+    TrainArgs ta{ids, n, B, sb, s->adj_p, s->adj_i, s->adj_w, s->N, degree, s->cv ? 1 : 0, hbits,
+                 s->train_sets.as<TrainSet>(), first_set, s->train_n_sets, s->train_raw.as<uint32_t>(), raw_words,
+                 s->train_ctl.as<TrainCtl>(), s->engine, s->pipeline ? prev_ids : nullptr, s->pipeline ? prev_n : 0,
+                 s->pipeline ? s->pipe_counters : nullptr, g_trace};
+    expand_train_kernel<256><<<n, 256, fused_smem_bytes(B, sb, hbits), st>>>(ta);
+    SGCN_LAUNCHED();
+    for (int j = 0; j < n; ++j) {                      // host bookkeeping: set k now holds batch j, level 0
+        sgcn_sampler::Slot& sl = s->slots[(first_set + j) % s->train_n_sets];
+        sl.batch_src = ids + (size_t)j * (size_t)B;
+        sl.batch_n = B;
+        sl.cur = 1;
+        sl.levels[0].done = true;
+        sl.levels[0].full_materialized = false;
+    }
     return SGCN_OK;
 }
 

@@ -33,6 +33,12 @@ struct sgcn_step {
                 ev_pre_end = nullptr, ev_begin = nullptr,
                 ev_side_end = nullptr, ev_samp_end = nullptr, ev_zero0 = nullptr;
     int device = 0;
+    // sgcn_step_run_trains
+    int train = 0;                                  // batches per train (0: trains unavailable for this sampler)
+    std::vector<Lv> tlv;                            // level-0 buffers of sampler sets 0 .. 2*train-1
+    int32_t* ids_stage[2] = {nullptr, nullptr};     // staging of host ids, one per train parity
+    static constexpr int kRing2 = 8;
+    cudaEvent_t t_pre[kRing2]{}, t_full[kRing2]{}, t_fwd[kRing2]{}, t_rest[kRing2]{}, t_d2h[kRing2]{}, t_train[4]{};
 };
 
 namespace sgcn {
@@ -113,6 +119,37 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
         CK(cudaEventCreateWithFlags(&st->ev_d2h[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st->ev_pre[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < sgcn_step::kRing2; ++i)
+        for (cudaEvent_t* e : {&st->t_pre[i], &st->t_full[i], &st->t_fwd[i], &st->t_rest[i], &st->t_d2h[i]})
+            CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&st->t_train[i], cudaEventDisableTiming));
+    {
+        // trains of batches: 2 x train buffer sets (the passes of one train run while the next is sampled)
+        const int T = d.train > 0 ? d.train : 16;
+        if (T >= 2 && T <= 32 && sgcn_sampler_reserve_sets(sampler, 2 * T, d.batch, d.degree) == SGCN_OK) {
+            st->train = T;
+            st->tlv.resize((size_t)2 * T);
+            for (int slot = 0; slot < 2 * T; ++slot) {
+                int rc2 = SGCN_OK;
+                void* q = nullptr;
+#define GET2(which, field, TY)                                                                   \
+    if (rc2 == SGCN_OK) { rc2 = get_slot_vec(sampler, slot, which, &q); st->tlv[(size_t)slot].field = (TY*)q; }
+                GET2(SGCN_VEC_FIELD, field, int32_t)
+                GET2(SGCN_VEC_ROWPTR_S, rowptr_s, int32_t)
+                GET2(SGCN_VEC_ROWPTR_F, rowptr_f, int32_t)
+                GET2(SGCN_VEC_EDG_T, edg_t, int32_t)
+                GET2(SGCN_VEC_TGT, tgt, int32_t)
+                GET2(SGCN_VEC_META, meta, int32_t)
+                GET2(SGCN_VEC_EDG_W, edg_w, float)
+                GET2(SGCN_VEC_SCALES, scales, float)
+#undef GET2
+                if (rc2 != SGCN_OK) return fail(rc2);
+            }
+            // the three-set drivers address sets 0..2, which reserve_sets may have re-sized
+            for (int slot = 0; slot < sgcn_step::kSlots; ++slot) st->lv[slot] = st->tlv[(size_t)slot];
+            for (int i = 0; i < 2; ++i) CK(cudaMalloc(&st->ids_stage[i], sizeof(int32_t) * (size_t)T * (size_t)d.batch));
+        }
+    }
     CK(cudaEventCreateWithFlags(&st->ev_begin, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&st->ev_pre_end, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&st->ev_side_end, cudaEventDisableTiming));
@@ -133,6 +170,11 @@ void sgcn_step_destroy(sgcn_step* st) {
             if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {st->ev_begin, st->ev_side_end, st->ev_samp_end, st->ev_zero0, st->ev_pre_end})
         if (e) cudaEventDestroy(e);
+    for (int i = 0; i < sgcn_step::kRing2; ++i)
+        for (cudaEvent_t e : {st->t_pre[i], st->t_full[i], st->t_fwd[i], st->t_rest[i], st->t_d2h[i]})
+            if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 4; ++i) if (st->t_train[i]) cudaEventDestroy(st->t_train[i]);
+    for (int i = 0; i < 2; ++i) cudaFree(st->ids_stage[i]);
     delete st;
 }
 
@@ -444,6 +486,204 @@ int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32
     SGCN_CUDA(cudaEventRecord(st->ev_pre_end, pre));
     if (out_host) SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_d2h[(n - 1) % R], 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_rest[(n - 1) % R], 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_pre_end, 0));
+    return SGCN_OK;
+}
+
+// ---- trains of batches + gather ahead + (optionally) the write-back off the critical path ----------------
+// What the device timelines of the two schedules above showed (profiles/r02_timeline_ahead.txt): with the
+// gather hoisted one pass ahead, the per-batch sampler became the critical path -- one CTA, 17-19 us per batch
+// under load, strictly serial from batch to batch (engine state), i.e. ~21 us per pass however far ahead it
+// runs.  Here a whole train of batches is sampled by ONE launch (sgcn_sampler_expand_train: one CTA per batch,
+// serial only in the prefix sum of the draw counts), one train ahead of the passes that consume it:
+//   samp  : [rest of train c-2] (H2D ids of train c) -> mt_stream -> expand_train(c)
+//   pre   : [train of pass k+1; x0 / dx / out copies free] gather(k+1) + dX init(k+1) + zero out(k+1)
+//   chain : [train, pre k, write-back k-2] full_mean(k) -PDL-> full_mean(k+1) ...        (overlap_write_back)
+//   side  : [pre k] sampled fwd+bwd(k) -> [full_mean k] write-back(k) -> sampled(k+1) ...
+// overlap_write_back: full_mean(k+1) reads the rows of field(k) from pass k's gathered rows instead of waiting
+// for write-back k (sgcn_full_history_mean_ov) -- the values are the same bits, so results do not change.
+// Without it (multi-GPU exchange, or > 4096 rows per write-back) the write-back stays on the chain:
+//   chain : full_mean(k) -> [sampled k] write-back(k) -> full_mean(k+1)
+int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
+                         int32_t first_train, void* stream) {
+    SGCN_REQUIRE(st && n >= 0 && (n == 0 || ids) && first_train >= 0, "step_run_trains: bad argument");
+    if (n == 0) return SGCN_OK;
+    if (st->train <= 0) {
+        set_error("step_run_trains: the sampler cannot sample trains of batches (importance sampling, batch or "
+                  "degree beyond the fused sampler's bounds); use sgcn_step_run");
+        return SGCN_ESTATE;
+    }
+    const sgcn_step_desc& d = st->d;
+    SGCN_REQUIRE(d.x0_alt[0] && d.x0_alt[1] && d.dx_alt, "step_run_trains: desc.x0_alt / dx_alt are required");
+    sgcn_sampler* smp = st->sampler;
+    const int B = d.batch, H = d.hidden, R = sgcn_step::kRing2, T = st->train;
+    const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0, multi = d.world > 1 && cv;
+    const bool overlap = cv && !multi && d.overlap_write_back != 0 && d.x0_rows <= 4096;
+    const int width = H * (concat ? 2 : 1);
+    cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp, pre = st->pre,
+                 copy = st->copy;
+    float* x0b[3] = {d.x0, d.x0_alt[0], d.x0_alt[1]};
+    float* dxb[2] = {d.dx, d.dx_alt};
+    auto nb = [&](float* base) { return base + (concat ? H : 0); };
+
+    // train c covers passes [tb(c), tb(c + 1)); its batches live in sampler sets (c & 1) * T + position
+    const int T0 = first_train > 0 ? std::min<int>(first_train, T) : T;
+    auto tb = [&](int c) { return c <= 0 ? 0 : std::min(n, T0 + (c - 1) * T); };
+    const int n_trains = n <= T0 ? 1 : 1 + (n - T0 + T - 1) / T;
+    auto train_of = [&](int k) { return k < T0 ? 0 : 1 + (k - T0) / T; };
+    auto set_of = [&](int k) { const int c = train_of(k); return (c & 1) * T + (k - tb(c)); };
+    auto ids_of = [&](int c) -> const int32_t* {         // where the kernels find the ids of train c
+        return ids_on_host ? st->ids_stage[c & 1] : ids + (int64_t)tb(c) * B;
+    };
+
+    SGCN_CUDA(cudaEventRecord(st->ev_begin, user));
+    for (cudaStream_t s : {chain, side, samp, pre}) SGCN_CUDA(cudaStreamWaitEvent(s, st->ev_begin, 0));
+    if (out_host) SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_begin, 0));
+
+    auto issue_train = [&](int c) -> int {
+        const int len = tb(c + 1) - tb(c);
+        // its buffer sets (and its id staging) were those of train c-2: every pass of that train has finished
+        if (c >= 2) SGCN_CUDA(cudaStreamWaitEvent(samp, st->t_rest[(tb(c - 1) - 1) % R], 0));
+        if (ids_on_host)
+            SGCN_CUDA(cudaMemcpyAsync(st->ids_stage[c & 1], ids + (int64_t)tb(c) * B, sizeof(int32_t) * (size_t)len * B,
+                                      cudaMemcpyHostToDevice, samp));
+        const bool prev = c >= 1 && cv;      // only the full-neighbour mean reads adjacency rows in place
+        STEP_TRY(sgcn_sampler_expand_train(smp, ids_of(c), len, (c & 1) * T, prev ? ids_of(c - 1) : nullptr,
+                                           prev ? (tb(c) - tb(c - 1)) * B : 0, samp));
+        SGCN_CUDA(cudaEventRecord(st->t_train[c % 4], samp));
+        return SGCN_OK;
+    };
+    // gather + dX init + output zeroing of pass k, into copies k % 3 (x0) and k & 1 (dx, out)
+    auto ahead = [&](int k) -> int {
+        const sgcn_step::Lv& v = st->tlv[(size_t)set_of(k)];
+        const int r = k & 1;
+        SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_train[train_of(k) % 4], 0));
+        if (k >= 2) {     // out / dx copy r: pass k-2 wrote them; its rows must also have left for the host
+            SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_full[(k - 2) % R], 0));
+            SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_fwd[(k - 2) % R], 0));
+            if (out_host) SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_d2h[(k - 2) % R], 0));
+        }
+        // x0 copy k % 3: read by sampled(k-3), write-back(k-3) and the override of full_mean(k-2)
+        if (k >= 3) SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_rest[(k - 3) % R], 0));
+        STEP_TRY(sgcn_gather_pad_pair(d.features, d.ld_feat, v.field, d.x0_rows, v.meta + 1, d.feat_dim, x0b[k % 3], d.ld_x0,
+                                      concat ? d.d_out : nullptr, d.ld_dout, concat ? B : 0,
+                                      concat ? v.meta + 0 : nullptr, d.x0_rows, H, dxb[r], d.ld_dx,
+                                      nullptr, 0, 0, nullptr, cv ? B : 0, H, cv ? nb(d.out[r]) : nullptr, d.ld_out, pre));
+        if (cvd) STEP_TRY(sgcn_copy_rows_pad(nullptr, 0, 0, nullptr, B, H, nb(d.out_mu[r]), d.ld_out, pre));
+        SGCN_CUDA(cudaEventRecord(st->t_pre[k % R], pre));
+        return SGCN_OK;
+    };
+
+    STEP_TRY(sgcn_sampler_set_stream_async(smp, samp));
+    for (int slot = 0; slot < 3; ++slot) {           // forget the batches of the three-set drivers' earlier runs
+        STEP_TRY(sgcn_sampler_set_slot(smp, slot));
+        STEP_TRY(sgcn_sampler_start_batch_device(smp, 0, nullptr));
+    }
+    STEP_TRY(issue_train(0));
+    if (n_trains > 1) STEP_TRY(issue_train(1));
+    STEP_TRY(ahead(0));
+
+    for (int k = 0; k < n; ++k) {
+        const int r = k & 1, c = train_of(k);
+        const sgcn_step::Lv& v = st->tlv[(size_t)set_of(k)];
+        const int32_t* n_out_dev = v.meta + 0;
+        const int32_t* n_in_dev = v.meta + 1;
+        float* out_r = d.out[r];
+        float* outmu_r = d.out_mu[r];
+        const float* x = x0b[k % 3];
+        const float* mu = x + H;
+        const float* new_hist = cvd ? mu : x;
+        const float* d_nb = d.d_out + (concat ? H : 0);
+
+        // ---- chain: the full-neighbour history mean of pass k ----
+        SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_train[c % 4], 0));
+        SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_pre[k % R], 0));
+        if (cv) {
+            if (overlap && k >= 1) {
+                // rows of field(k-1) come from pass k-1's gathered rows; everything older is in the table
+                if (k >= 2) SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_rest[(k - 2) % R], 0));
+                const sgcn_step::Lv& pv = st->tlv[(size_t)set_of(k - 1)];
+                const float* prow = x0b[(k - 1) % 3] + (cvd ? H : 0);
+                STEP_TRY(sgcn_full_history_mean_ov(v.field, v.rowptr_f, B, n_out_dev, st->adj_p, st->adj_i, st->adj_w,
+                                                   d.history, d.ld_hist, H, cvd ? nb(outmu_r) : nb(out_r), d.ld_out,
+                                                   cvd ? nb(out_r) : nullptr, d.ld_out, pv.field, pv.meta + 1,
+                                                   d.x0_rows, prow, d.ld_x0, chain));
+            } else {
+                STEP_TRY(sgcn_full_history_mean(v.field, v.rowptr_f, B, n_out_dev, st->adj_p, st->adj_i, st->adj_w,
+                                                d.history, d.ld_hist, H, cvd ? nb(outmu_r) : nb(out_r), d.ld_out,
+                                                cvd ? nb(out_r) : nullptr, d.ld_out, nullptr, chain));
+            }
+        }
+        SGCN_CUDA(cudaEventRecord(st->t_full[k % R], chain));
+        // ---- pre: everything of pass k+1 that does not read the history ----
+        if (k + 1 < n) STEP_TRY(ahead(k + 1));
+        // ---- side: the sampled aggregate + backward of pass k (history as of write-back k-1) ----
+        SGCN_CUDA(cudaStreamWaitEvent(side, st->t_pre[k % R], 0));
+        if (k >= 1 && !overlap) SGCN_CUDA(cudaStreamWaitEvent(side, st->t_rest[(k - 1) % R], 0));
+        if (d.mode == 0) {
+            STEP_TRY(sgcn_spmm_csr(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, x, d.ld_x0, H, nb(out_r),
+                                   d.ld_out, 0, side));
+            if (concat) STEP_TRY(sgcn_copy_rows_pad(x, d.ld_x0, B, n_out_dev, B, H, out_r, d.ld_out, side));
+            STEP_TRY(sgcn_spmm_csr_bwd(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, d_nb, d.ld_dout, H, dxb[r],
+                                       d.ld_dx, side));
+        } else if (!cvd) {
+            if (multi)      // the write-back push rides on the sampled launch (see sgcn_wb_push_attach)
+                STEP_TRY(sgcn_wb_push_attach(v.field, n_in_dev, d.wb_bound, new_hist, d.ld_x0, H, d.dst_even, d.dst_odd,
+                                             d.world, d.peer_flags, d.rank, d.epoch, d.block_counter));
+            STEP_TRY(sgcn_cv_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, B, n_out_dev, x, d.ld_x0, d.history,
+                                             d.ld_hist, H, nb(out_r), d.ld_out, concat ? out_r : nullptr, d.ld_out, 1,
+                                             d_nb, d.ld_dout, dxb[r], d.ld_dx, side));
+        } else {
+            if (multi)
+                STEP_TRY(sgcn_wb_push_attach(v.field, n_in_dev, d.wb_bound, new_hist, d.ld_x0, H, d.dst_even, d.dst_odd,
+                                             d.world, d.peer_flags, d.rank, d.epoch, d.block_counter));
+            STEP_TRY(sgcn_cvd_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, v.scales, B, n_out_dev, x, d.ld_x0,
+                                              mu, d.ld_x0, d.history, d.ld_hist, H, nb(out_r), d.ld_out,
+                                              nb(outmu_r), d.ld_out, concat ? out_r : nullptr, d.ld_out,
+                                              concat ? outmu_r : nullptr, d.ld_out, 1, d_nb, d.ld_dout, dxb[r],
+                                              d.ld_dx, side));
+        }
+        SGCN_CUDA(cudaEventRecord(st->t_fwd[k % R], side));
+        // ---- write-back after every forward read of history (gcn/models.py:186-194) ----
+        if (overlap) {
+            SGCN_CUDA(cudaStreamWaitEvent(side, st->t_full[k % R], 0));
+            STEP_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
+                                         st->pipe + 1, side));
+            SGCN_CUDA(cudaEventRecord(st->t_rest[k % R], side));
+        } else {
+            SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_fwd[k % R], 0));
+            if (!cv) {
+                STEP_TRY(sgcn_sampler_mark_consumed(smp, chain));
+            } else if (multi) {
+                STEP_TRY(sgcn_wb_wait_apply(d.history, d.ld_hist, H, d.recv_even, d.recv_odd, d.slot_bytes, d.world,
+                                            d.wb_bound, d.owner, d.flags, d.epoch, d.timeout_flag, st->pipe + 1, chain));
+            } else {
+                STEP_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
+                                             st->pipe + 1, chain));
+            }
+            SGCN_CUDA(cudaEventRecord(st->t_rest[k % R], chain));
+        }
+        // ---- copy: the pass's aggregated rows to pinned host memory (both aggregate kernels done) ----
+        if (out_host) {
+            SGCN_CUDA(cudaStreamWaitEvent(copy, st->t_full[k % R], 0));
+            SGCN_CUDA(cudaStreamWaitEvent(copy, st->t_fwd[k % R], 0));
+            SGCN_CUDA(cudaMemcpy2DAsync(out_host + (int64_t)k * B * width, sizeof(float) * (size_t)width, out_r,
+                                        sizeof(float) * (size_t)d.ld_out, sizeof(float) * (size_t)width, (size_t)B,
+                                        cudaMemcpyDeviceToHost, copy));
+            SGCN_CUDA(cudaEventRecord(st->t_d2h[k % R], copy));
+        }
+        // ---- samp: the train after next, once the last pass of this train has been issued ----
+        if (k + 1 == tb(c + 1) && c + 2 < n_trains) STEP_TRY(issue_train(c + 2));
+    }
+    SGCN_CUDA(cudaEventRecord(st->ev_side_end, side));
+    SGCN_CUDA(cudaEventRecord(st->ev_samp_end, samp));
+    SGCN_CUDA(cudaEventRecord(st->ev_pre_end, pre));
+    SGCN_CUDA(cudaEventRecord(st->ev_zero0, chain));
+    if (out_host) SGCN_CUDA(cudaStreamWaitEvent(user, st->t_d2h[(n - 1) % R], 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->t_rest[(n - 1) % R], 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_zero0, 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_pre_end, 0));

@@ -48,12 +48,15 @@ def _csr_from_sorted_keys(keys, n, device):
 
 
 def powerlaw_graph(n, nnz_target, seed=0, device="cuda", exponent=2.1, max_degree=None, normalization="graphsage",
-                   chunk=1 << 24):
+                   chunk=1 << 24, exact=False):
     """Undirected Chung-Lu power-law graph, symmetrised, duplicate- and self-loop-free.
 
     Endpoint i is drawn with probability proportional to w_i ~ Pareto(exponent-1) (capped so the
     expected maximum degree stays near ``max_degree``); ``nnz_target`` is the number of stored
-    entries (2 x undirected edges) aimed for before duplicate removal.
+    entries (2 x undirected edges) aimed for before duplicate removal.  ``exact``: top up with further
+    draws of the same distribution until at least ``nnz_target`` DISTINCT entries are stored, then drop
+    random undirected edges down to exactly ``nnz_target`` (rounded down to an even number) -- the
+    named shapes are quoted by their stored size (E = nnz AFTER de-duplication).
     """
     dev = torch.device(device)
     gen = torch.Generator(device=dev)
@@ -76,6 +79,30 @@ def powerlaw_graph(n, nnz_target, seed=0, device="cuda", exponent=2.1, max_degre
         parts.append(torch.cat((a * n + b, b * n + a)))
     keys = torch.unique(torch.cat(parts)) if parts else torch.zeros(0, dtype=torch.int64, device=dev)
     del parts
+    target = (nnz_target // 2) * 2
+    if exact and n * (n - 1) >= 2 * target:
+        for _ in range(16):
+            short = target - keys.numel()
+            if short <= 0:
+                break
+            k = short // 2 + short // 6 + 1024              # duplicates again: draw ~1.3x what is missing
+            a = torch.searchsorted(cdf, torch.rand(k, generator=gen, device=dev, dtype=torch.float64)).clamp_(max=n - 1)
+            b = torch.searchsorted(cdf, torch.rand(k, generator=gen, device=dev, dtype=torch.float64)).clamp_(max=n - 1)
+            keep = a != b
+            a, b = a[keep], b[keep]
+            keys = torch.unique(torch.cat((keys, a * n + b, b * n + a)))
+        surplus = (keys.numel() - target) // 2
+        if surplus > 0:                                       # drop whole undirected edges, both directions
+            r = torch.div(keys, n, rounding_mode="floor")
+            upper = keys[r < keys - r * n]
+            pick = torch.randperm(upper.numel(), generator=gen, device=dev)[:surplus]
+            drop = upper[pick]
+            dr = torch.div(drop, n, rounding_mode="floor")
+            mirror = (drop - dr * n) * n + dr
+            keep = torch.ones(keys.numel(), dtype=torch.bool, device=dev)
+            keep[torch.searchsorted(keys, torch.cat((drop, mirror)))] = False
+            keys = keys[keep]
+            del r, upper, pick, drop, dr, mirror, keep
     rows, cols, deg, indptr = _csr_from_sorted_keys(keys, n, dev)
     if normalization == "graphsage":
         data = (1.0 / deg.clamp(min=1).to(torch.float32))[rows]
@@ -114,5 +141,6 @@ def make_shape(name, seed=0, device="cuda", scale=1.0):
     s = SHAPES[name]
     n = max(16, int(s["n"] * scale))
     if "nnz" in s:
-        return powerlaw_graph(n, int(s["nnz"] * scale), seed=seed, device=device, max_degree=s["max_degree"])
+        return powerlaw_graph(n, int(s["nnz"] * scale), seed=seed, device=device, max_degree=s["max_degree"],
+                              exact=True)
     return gcn_normalized_graph(n, int(s["edges"] * scale), seed=seed, device=device)

@@ -106,6 +106,24 @@ class DeviceSampler:
     def expand(self, degree, materialize_full=False):
         check(self._lib.sgcn_sampler_expand(self._h, int(degree), int(materialize_full)))
 
+    def reserve_sets(self, n_sets, batch, degree):
+        """Size buffer sets 0 .. n_sets-1 for trains of batches (``expand_train``)."""
+        check(self._lib.sgcn_sampler_reserve_sets(self._h, int(n_sets), int(batch), int(degree)))
+        self._train_batch = int(batch)
+
+    def expand_train(self, table, first_set=0, prev=None, stream=None):
+        """Sample the n batches of ``table`` (CUDA int32 [n, batch]) with ONE launch: batch j lands in buffer
+        set (first_set + j) % n_sets exactly as n sequential start_batch + expand calls would leave it.
+        ``prev``: ids (CUDA int32, any shape) of earlier batches whose consumer passes may still run."""
+        if not (table.is_cuda and table.dtype == torch.int32 and table.is_contiguous() and table.dim() == 2
+                and table.shape[1] == self._train_batch):
+            raise ValueError("table must be a contiguous CUDA int32 [n, %d] tensor" % self._train_batch)
+        self._keep_train = (table, prev)
+        check(self._lib.sgcn_sampler_expand_train(self._h, ptr(table), int(table.shape[0]), int(first_set),
+                                                  ptr(prev) if prev is not None else None,
+                                                  int(prev.numel()) if prev is not None else 0,
+                                                  _lib.stream_ptr(stream)))
+
     def set_slot(self, slot):
         """Select which of the two per-batch buffer sets start_batch / expand / view / sizes address."""
         check(self._lib.sgcn_sampler_set_slot(self._h, int(slot)))

@@ -217,6 +217,21 @@ class ShardedHotPathStep(HotPathStep):
             raise RuntimeError("the native step driver needs the peer transport for multi-GPU runs")
         return d
 
+    def _no_nccl_inside_graphs(self, what):
+        """The NCCL transport runs its collective and the merge EAGERLY after each one-pass graph
+        (_finish_exchange); a multi-pass driver would never apply a write-back."""
+        if self.transport == "nccl" and self.mode != "ns":
+            raise RuntimeError("%s needs transport='peer': with transport='nccl' the history write-back exchange runs "
+                               "between one-pass replays (run / replay / step_host)" % what)
+
+    def capture_pipelined(self, *a, **k):
+        self._no_nccl_inside_graphs("capture_pipelined")
+        return super().capture_pipelined(*a, **k)
+
+    def run_pipelined(self, *a, **k):
+        self._no_nccl_inside_graphs("run_pipelined")
+        return super().run_pipelined(*a, **k)
+
     def _finish_exchange(self):
         """NCCL transport: the collective and the merge run eagerly after the (captured) pass."""
         if self.transport == "nccl" and self.mode != "ns":

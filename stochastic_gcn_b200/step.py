@@ -80,6 +80,10 @@ class HotPathStep:
         self._pipeline_on = False
         self._pipe_done = None
         self._last_slot = 0
+        self.train = 16                # batches sampled per launch by the trains schedule (run_trains)
+        self.overlap_write_back = True  # trains schedule: write-back off the chain (row override in the next mean)
+        self._trains = None            # captured graphs of the trains schedule
+        self._last_x0 = self._last_dx = None
         self._s_b = torch.cuda.Stream(device=self.dev)      # side branch of the pass
         self._s_samp = torch.cuda.Stream(device=self.dev)   # sampler branch of the pipelined graphs
         self._s_chain = torch.cuda.Stream(device=self.dev)  # main chain of the pipelined graphs
@@ -252,6 +256,7 @@ class HotPathStep:
         self._zero_out(0)
         self._sample(0)
         self._last_slot, self._last_sampler_slot = 0, None
+        self._last_x0 = self._last_dx = None
         self._rest(0, main)
 
     # -- drivers ---------------------------------------------------------------------------------
@@ -425,6 +430,7 @@ class HotPathStep:
             self._zero_out(slot)
             self._sample(slot, self.ids2[slot])
         self._last_slot, self._last_sampler_slot = slot, None
+        self._last_x0 = self._last_dx = None
         self._rest(slot, main, zero_next=True)
 
     def run_pipelined(self, batches, on_chunk=None):
@@ -445,8 +451,14 @@ class HotPathStep:
         host_io = pipe["host_io"]
         stage = pipe["pin_tab"] if host_io else pipe["tab"]
         full, rem = divmod(n, S)
+        done = pipe.setdefault("done", [None, None])
+        if host_io and done[1] is not None:
+            done[1].synchronize()                               # an earlier call's DMA may still read pin_tab[1]
         stage[1][S - 1].copy_(batches[0], non_blocking=not host_io)
         pipe["first"].replay()                                  # zero outs[0]; sample batch 0 into set 0
+        if host_io:                                             # its H2D reads pin_tab[1][S-1]: chunk 1 restages it
+            done[1] = torch.cuda.Event()
+            done[1].record()
         for c in range(full):
             par = c & 1
             base = c * S
@@ -505,6 +517,11 @@ class HotPathStep:
         d.ld_out = self.outs[0].stride(0)
         d.d_out, d.ld_dout = self.d_out.data_ptr(), self.d_out.stride(0)
         d.dx, d.ld_dx = self.dx.data_ptr(), self.dx.stride(0)
+        if getattr(self, "_alt_bufs", None) is None:   # trains schedule: three x0 copies, two dx copies
+            self._alt_bufs = (torch.zeros_like(self.x0), torch.zeros_like(self.x0), torch.zeros_like(self.dx))
+        d.x0_alt[0], d.x0_alt[1] = self._alt_bufs[0].data_ptr(), self._alt_bufs[1].data_ptr()
+        d.dx_alt = self._alt_bufs[2].data_ptr()
+        d.train, d.overlap_write_back = int(self.train), int(bool(self.overlap_write_back))
         return d
 
     def run_native(self, batches, out_host=None):
@@ -534,6 +551,7 @@ class HotPathStep:
                                      _lib.ptr(out_host) if out_host is not None else None, _lib.stream_ptr()))
         self._last_slot = (n - 1) & 1                  # output buffers alternate ...
         self._last_sampler_slot = (n - 1) % 3          # ... sampler buffer sets rotate over three
+        self._last_x0 = self._last_dx = None
         self.sampler._stream = None                    # the driver left the sampler on its own stream
         return self.out
 
@@ -637,6 +655,119 @@ class HotPathStep:
                 on_chunk(c * S, S, a["pin_out"][p], ev)
         self._last_slot, self._last_sampler_slot = (S - 1) & 1, (S - 1) % 3
         return self.out
+
+    # -- trains schedule (csrc/step.cu:sgcn_step_run_trains): the schedule bench.py times ------------------
+    def _check_io(self, table, out_host):
+        n = int(table.shape[0])
+        if table.dim() != 2 or table.shape[1] != self.B or table.dtype != torch.int32 or not table.is_contiguous():
+            raise ValueError("ids must be a contiguous int32 [n, %d] table" % self.B)
+        if not table.is_cuda and not table.is_pinned():
+            raise ValueError("host id tables must be pinned")
+        if out_host is not None and not (out_host.is_pinned() and out_host.is_contiguous()
+                                         and tuple(out_host.shape) == (n, self.B, self.outs[0].shape[1])):
+            raise ValueError("out_host must be a pinned contiguous [n, B, width] float32 tensor")
+        return n
+
+    def _trains_done(self, n, first_train):
+        """host bookkeeping after n passes of the trains schedule: where the last pass left its results"""
+        T = self.train
+        T0 = min(first_train, T) if first_train > 0 else T
+        k = n - 1
+        c = 0 if k < T0 else 1 + (k - T0) // T
+        base = 0 if c == 0 else T0 + (c - 1) * T
+        self._last_slot = k & 1
+        self._last_sampler_slot = (c & 1) * T + (k - base)
+        x0s = (self.x0,) + tuple(self._alt_bufs[:2])
+        self._last_x0, self._last_dx = x0s[k % 3], (self.dx, self._alt_bufs[2])[k & 1]
+        self.sampler._stream = None
+
+    def run_trains(self, table, out_host=None, first_train=0):
+        """n consecutive passes through sgcn_step_run_trains on the current stream: the sampler runs a TRAIN of
+        `self.train` batches per launch, one train ahead of the passes; gather / dX init / zeroing one pass
+        ahead; full-neighbour means back to back (write-back off the chain when self.overlap_write_back).
+        ``table``: contiguous int32 [n, B] ids on the GPU or in PINNED host memory; ``out_host``: optional pinned
+        float32 [n, B, width] receiving every pass's aggregated rows; ``first_train``: length of the first
+        train (0 = self.train; a short one shortens the start-up bubble).  Returns the last pass's rows."""
+        n = self._check_io(table, out_host)
+        if n == 0:
+            return self.out
+        h = self._native_handle()
+        self._trains_keep = (table, out_host)          # borrowed by the driver until the run completes
+        _lib.check(_lib.load().sgcn_step_run_trains(h, _lib.ptr(table), int(not table.is_cuda), n,
+                                                    _lib.ptr(out_host) if out_host is not None else None,
+                                                    int(first_train), _lib.stream_ptr()))
+        self._trains_done(n, first_train)
+        return self.out
+
+    def capture_trains(self, n, warm_table, host_io=False, first_train=4):
+        """Capture n passes of the trains schedule as CUDA graph(s) over fixed id tables.
+        host_io=False: ONE graph over a device [n, B] id table (``replay_trains`` copies the ids in).
+        host_io=True: TWO graphs, each bound to its own pinned staging set (ids in: one H2D copy per train;
+        every pass's rows out: one D2H copy per pass), alternated by ``replay_trains`` so that the host fills /
+        drains one set while the GPU runs the other.  ``warm_table``: [n, B] device ids for the eager warm-up."""
+        n = int(n)
+        if tuple(warm_table.shape) != (n, self.B):
+            raise ValueError("warm_table must be [n, batch]")
+        tab = warm_table.to(torch.int32).contiguous().clone()
+        self.run_trains(tab, first_train=first_train)             # sizes everything, warms the allocators
+        torch.cuda.synchronize(self.dev)
+        cap = torch.cuda.Stream(device=self.dev)
+        width = self.outs[0].shape[1]
+        if not host_io:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cap):
+                self.run_trains(tab, first_train=first_train)
+            self._trains = {"n": n, "tab": tab, "graph": g, "host_io": False, "first_train": first_train}
+            return g
+        pin_tab = [torch.zeros((n, self.B), dtype=torch.int32).pin_memory() for _ in range(2)]
+        pin_out = [torch.empty((n, self.B, width), dtype=torch.float32).pin_memory() for _ in range(2)]
+        graphs = []
+        for p in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cap):
+                self.run_trains(pin_tab[p], out_host=pin_out[p], first_train=first_train)
+            graphs.append(g)
+        self._trains = {"n": n, "pin_tab": pin_tab, "pin_out": pin_out, "graphs": graphs, "host_io": True,
+                        "done": [None, None], "first_train": first_train}
+        return graphs
+
+    def replay_trains(self, table, on_chunk=None):
+        """len(table) passes as replays of the captured graph(s); len(table) must be a multiple of the captured n.
+        Captured with host_io: ``table`` is a HOST [m, B] id table and ``on_chunk(first_pass, count, rows,
+        done_event)`` is called after each replay has been enqueued -- once ``done_event`` has completed,
+        ``rows`` ([n, B, width], pinned) holds those passes' rows; that staging set is refilled two replays
+        later, so consume it one replay behind the launches."""
+        t = self._trains
+        n = t["n"]
+        m = int(table.shape[0])
+        if m % n:
+            raise ValueError("the number of passes must be a multiple of the captured %d" % n)
+        for c in range(m // n):
+            if not t["host_io"]:
+                t["tab"].copy_(table[c * n:(c + 1) * n], non_blocking=True)
+                t["graph"].replay()
+                continue
+            p = c & 1
+            if t["done"][p] is not None:
+                t["done"][p].synchronize()                       # replay c-2 has left this staging set
+            t["pin_tab"][p].copy_(table[c * n:(c + 1) * n])      # host -> pinned host
+            t["graphs"][p].replay()
+            ev = torch.cuda.Event()
+            ev.record()
+            t["done"][p] = ev
+            if on_chunk is not None:
+                on_chunk(c * n, n, t["pin_out"][p], ev)
+        self._trains_done(n, t["first_train"])
+        return self.out
+
+    @property
+    def last_x0(self):
+        """gathered input rows of the most recent pass (the trains schedule rotates three copies)"""
+        return self._last_x0 if self._last_x0 is not None else self.x0
+
+    @property
+    def last_dx(self):
+        return self._last_dx if self._last_dx is not None else self.dx
 
     def time_dominant_kernel(self, batches):
         """Device time of the dominant kernel -- the edge-balanced full-neighbour history mean for

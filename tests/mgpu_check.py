@@ -23,12 +23,13 @@ def main():
     use_graph = len(sys.argv) > 3 and sys.argv[3] == "graph"
     pipelined = len(sys.argv) > 3 and sys.argv[3] == "pipelined"
     ahead = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] in ("ahead", "ahead-graph") else None
+    trains = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] in ("trains", "trains-graph") else None
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     deg = 2 if mode == "cv" else 1
-    D, B, steps, seed = 32, 24, (8 if pipelined else 12 if ahead else 5), 3
+    D, B, steps, seed = 32, 24, (8 if pipelined else 12 if ahead else 15 if trains else 5), 3
     g = graphs.powerlaw_graph(1500, 60_000, seed=4, device=dev, max_degree=300)
     gen = torch.Generator(device=dev).manual_seed(0)
     feats = torch.randn((g.n, 80), generator=gen, device=dev)
@@ -101,6 +102,27 @@ def main():
         err = np.abs(out - want_out[-1]).max() / max(np.abs(want_out[-1]).max(), 1e-30)
         assert err < 1e-4, "rank %d: last gather-ahead out differs by %g" % (rank, err)
         steps = 0
+    if trains:
+        # trains schedule (sgcn_step_run_trains) with the peer exchange: eager with every pass's rows read back,
+        # or 5 passes per CUDA graph; trains of 4 batches so that several trains are in flight
+        step.train = 4
+        table = torch.from_numpy(np.stack(batches[rank])).to(dev)
+        if trains == "trains":
+            rows = torch.empty((steps, B, step.outs[0].shape[1]), dtype=torch.float32).pin_memory()
+            step.run_trains(table, out_host=rows, first_train=2)
+            torch.cuda.synchronize()
+            for s in range(steps):
+                err = np.abs(rows[s].numpy() - want_out[s]).max() / max(np.abs(want_out[s]).max(), 1e-30)
+                assert err < 1e-4, "rank %d: trains pass %d differs by %g" % (rank, s, err)
+        else:
+            step.capture_trains(5, table[:5], first_train=2)      # eager warm-up run = passes 0 .. 4
+            step.replay_trains(table[5:])
+            torch.cuda.synchronize()
+        step.check_exchange()
+        out = step.out.cpu().numpy()
+        err = np.abs(out - want_out[-1]).max() / max(np.abs(want_out[-1]).max(), 1e-30)
+        assert err < 1e-4, "rank %d: last trains out differs by %g" % (rank, err)
+        steps = 0
     for s in range(steps):
         ids = torch.from_numpy(batches[rank][s]).to(dev)
         if use_graph and s == 0:
@@ -120,7 +142,8 @@ def main():
         rank, int((got_hist != hist).any(1).sum()))
     dist.barrier()
     if rank == 0:
-        print("mgpu_check ok: transport=%s mode=%s graph=%s world=%d" % (transport, mode, use_graph, world))
+        print("mgpu_check ok: transport=%s mode=%s form=%s world=%d" % (
+            transport, mode, sys.argv[3] if len(sys.argv) > 3 else "eager", world))
     step.close()
     dist.destroy_process_group()
 

@@ -17,15 +17,23 @@ def _bench():
     return mod
 
 
-def test_chunk_length_choice():
+def test_graph_length_choice():
     b = _bench()
-    for k in list(range(1, 70)) + [100, 200, 1000, 4992, 5000]:
-        s = b.pick_steps_per_graph(k, 16)
-        assert s % 2 == 0 and 2 <= s <= 16
-        cost = lambda c: (k // c) * 8 + (k % c) * 40
-        assert all(cost(s) <= cost(c) for c in range(2, min(16, max(k, 2)) + 1, 2))
-    assert b.pick_steps_per_graph(5000, 16) == 16 and b.pick_steps_per_graph(20, 16) == 10
-    assert b.pick_steps_per_graph(64, 8) == 8
+    for k in list(range(2, 70)) + [100, 200, 1000, 4992, 5000]:
+        s = b.pick_graph_passes(k, 64)
+        assert 2 <= s <= 64
+        if k <= 64:
+            assert s == k                                      # short runs: ONE graph of exactly K passes
+    assert b.pick_graph_passes(20, 64) == 20 and b.pick_graph_passes(5000, 64) == 50
+    assert b.pick_graph_passes(2048, 64) == 64 and b.pick_graph_passes(131, 64) == 64   # prime: remainder passes
+
+
+def test_both_arms_print_the_same_config():
+    b = _bench()
+    import argparse
+    a = argparse.Namespace(workload="reddit_cv", scale=1.0, seed=1)
+    c = b.workload_config(a, b.WORKLOADS["reddit_cv"])
+    assert set(c) == {"workload", "scale", "seed", "l2"} and "model" not in c
 
 
 def test_traffic_comes_from_the_committed_capture():

@@ -142,3 +142,18 @@ def test_dense_gradient_allreduce_two_gloo_ranks():
             b = np.zeros(shape, np.float32)
         want = (a + b) / 2
         assert np.allclose(g0[k], want, atol=1e-7) and np.array_equal(g0[k], g1[k])
+
+
+def test_nccl_transport_is_rejected_by_the_multi_pass_drivers():
+    """with transport='nccl' the write-back only happens in _finish_exchange; the multi-pass graph
+    driver must refuse instead of silently never updating the history."""
+    import pytest
+    from stochastic_gcn_b200.sharding import ShardedHotPathStep
+    s = ShardedHotPathStep.__new__(ShardedHotPathStep)
+    s.transport, s.mode = "nccl", "cv"
+    with pytest.raises(RuntimeError, match="transport='peer'"):
+        s.capture_pipelined(None, None)
+    with pytest.raises(RuntimeError, match="transport='peer'"):
+        s.run_pipelined([])
+    s.mode = "ns"
+    s._no_nccl_inside_graphs("x")          # plain sampling keeps no history: nothing to exchange

@@ -1,5 +1,7 @@
 """GPU (needs >= 2 devices, skipped otherwise): the sharded pass under torchrun, both transports,
-eager and CUDA-graph replay, against the multi-process oracle of tests/mgpu_check.py."""
+eager and CUDA-graph replay, against the multi-process oracle of tests/mgpu_check.py.  The multi-pass
+schedules run on every GPU of the box (world = torch.cuda.device_count()); each run leaves its last lines in
+gpurun_out/mgpu_check_<world>.log."""
 import os
 import subprocess
 import sys
@@ -24,16 +26,17 @@ def test_two_rank_pass_matches_oracle(transport, mode, graph):
     assert "mgpu_check ok" in out.stdout
 
 
-@pytest.mark.xfail(reason="multi-GPU form of the gather-ahead schedule: written after the round-1 GPU budget was spent, "
-                          "not yet run on hardware", strict=False)
-@pytest.mark.parametrize("form", ["ahead", "ahead-graph"])
-def test_two_rank_gather_ahead_matches_oracle(form):
-    if torch.cuda.device_count() < 2:
+@pytest.mark.parametrize("form,mode", [("trains", "cv"), ("trains-graph", "cv"), ("trains", "cvd"), ("ahead", "cv"),
+                                       ("ahead-graph", "cv")])
+def test_all_ranks_multi_pass_schedules_match_oracle(form, mode):
+    """the trains schedule (bench default) and the gather-ahead schedule on EVERY GPU of the box (2, 4 or 8 ranks)"""
+    world = torch.cuda.device_count()
+    if world < 2:
         pytest.skip("needs 2 GPUs")
     import signal
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
            "--master-addr", "127.0.0.1", "--master-port", "29537", os.path.join(ROOT, "tests", "mgpu_check.py"),
-           "peer", "cv", form]
+           "peer", mode, form]
     # a process group of its own: on a timeout every rank goes, not only the launcher
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
                             start_new_session=True)
@@ -43,4 +46,7 @@ def test_two_rank_gather_ahead_matches_oracle(form):
         os.killpg(proc.pid, signal.SIGKILL)
         proc.communicate()
         raise
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "mgpu_check_%d.log" % world), "a") as f:
+        f.write("%s %s world=%d rc=%d: %s\n" % (form, mode, world, proc.returncode, stdout.strip().splitlines()[-1:]))
     assert proc.returncode == 0 and "mgpu_check ok" in stdout, stdout[-3000:] + stderr[-3000:]

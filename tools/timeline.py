@@ -15,6 +15,24 @@ from stochastic_gcn_b200.step import HotPathStep
 NAMES = ["sampler", "full_mean", "gather", "sampled_fwd", "spmm_bwd", "history_update", "copy/zero", "exchange"]
 
 
+def dump_events(trace, S, what):
+    t = trace.cpu().tolist()
+    n = min(t[16], 1024)
+    ev = sorted((t[18 + 2 * i], t[17 + 2 * i]) for i in range(n))
+    t0 = ev[0][0]
+    print("%s of %d steps: %d events, span %.1f us (%.1f us / step)" % (
+        what, S, n, (ev[-1][0] - t0) / 1e3, (ev[-1][0] - t0) / 1e3 / S))
+    open_at = {}
+    for tm, code in ev:
+        cls, is_end = code >> 1, code & 1
+        if not is_end:
+            open_at.setdefault(cls, []).append(tm)
+        else:
+            st = open_at[cls].pop(0) if open_at.get(cls) else tm
+            print("    %-15s %7.1f -> %7.1f  (%.1f us)" % (NAMES[cls] if cls < len(NAMES) else "class%d" % cls,
+                                                           (st - t0) / 1e3, (tm - t0) / 1e3, (tm - st) / 1e3))
+
+
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "serial"
     n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
@@ -32,6 +50,29 @@ def main():
     step.capture(batches[0])
     if mode == "pipelined":
         step.capture_pipelined(batches[0], batches[1], steps_per_graph=n_steps)
+    if mode == "trains":                                             # the bench's schedule, one graph of n_steps
+        step.overlap_write_back = os.environ.get("OVERLAP", "1") != "0"
+        step.train = int(os.environ.get("TRAIN", "16"))
+        ft = int(os.environ.get("FIRST_TRAIN", "4"))
+        step.capture_trains(n_steps, torch.stack(batches[:n_steps]), first_train=ft)
+        step.replay_trains(torch.stack(batches[12:12 + n_steps]))
+        torch.cuda.synchronize()
+        step._trains["tab"].copy_(torch.stack(batches[30:30 + n_steps]))
+        trace.copy_(init); torch.cuda.synchronize()
+        step._trains["graph"].replay(); torch.cuda.synchronize()
+        dump_events(trace, n_steps, "one trains graph (train %d, first %d, overlap %s)" % (step.train, ft, step.overlap_write_back))
+        _lib.load().sgcn_trace_set(None)
+        return
+    if mode == "ahead":                                              # gather-ahead schedule, one graph of n_steps
+        step.capture_ahead(torch.stack(batches[:n_steps]), steps_per_graph=n_steps)
+        step.replay_ahead(torch.stack(batches[12:12 + n_steps]))
+        torch.cuda.synchronize()
+        step._ahead["tab"].copy_(torch.stack(batches[30:30 + n_steps]))
+        trace.copy_(init); torch.cuda.synchronize()
+        step._ahead["graph"].replay(); torch.cuda.synchronize()
+        dump_events(trace, n_steps, "one gather-ahead graph")
+        _lib.load().sgcn_trace_set(None)
+        return
     for b in batches[2:12]:
         step.replay(b) if mode == "serial" else None
     torch.cuda.synchronize()
