@@ -112,6 +112,9 @@ def ref_lib():
         lib.ref_c_indptr.argtypes = [C.c_int, _i32p, _i32p, _i32p]
         lib.ref_c_slice.argtypes = [C.c_int, _i32p, _f32p, _i32p, _i32p, _f32p, _i32p, _i32p]
         lib.ref_c_dense_slice.argtypes = [C.c_int, C.c_int, _i32p, _f32p, _f32p]
+        if hasattr(lib, "ref_compute_history"):
+            lib.ref_compute_history.argtypes = [_f32p, _i32p, _i32p, C.c_int, C.c_int, _i32p, C.c_int, _f32p,
+                                                C.c_int, _f32p]
         _ref = lib
     return _ref
 
@@ -320,6 +323,23 @@ def ref_dense_slice(a, r):
     r = np.ascontiguousarray(r, dtype=np.int32)
     out = np.zeros((len(r), a.shape[1]), dtype=np.float32)
     ref_lib().ref_c_dense_slice(len(r), a.shape[1], _ip(r), _fp(a), _fp(out))
+    return out
+
+
+def ref_compute_history(adj_w, adj_i, adj_p, rows, history):
+    """The reference's own (commented-out) CSR aggregation loop, gcn/history.cpp:10-37, compiled by
+    oracle/Makefile: output[i, :] = sum over the stored row rows[i] of adj_w * history[adj_i, :], fp32,
+    in storage order.  adj_p has N + 1 entries."""
+    lib = ref_lib()
+    if not hasattr(lib, "ref_compute_history"):
+        raise FileNotFoundError("oracle/_ref/libsgcn_ref.so was built without compute_history; run make -C oracle")
+    w = np.ascontiguousarray(adj_w, dtype=np.float32)
+    i = np.ascontiguousarray(adj_i, dtype=np.int32)
+    p = np.ascontiguousarray(adj_p, dtype=np.int32)
+    r = np.ascontiguousarray(rows, dtype=np.int32)
+    h = np.ascontiguousarray(history, dtype=np.float32)
+    out = np.zeros((len(r), h.shape[1]), dtype=np.float32)
+    lib.ref_compute_history(_fp(w), _ip(i), _ip(p), len(p) - 1, len(i), _ip(r), len(r), _fp(h), h.shape[1], _fp(out))
     return out
 
 

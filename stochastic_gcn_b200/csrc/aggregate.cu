@@ -1139,7 +1139,7 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
                batch's sampler CTA (up to ~47 KB) can then join an SM that runs this kernel without \
                waiting for the SM to drain and re-partition its L1 / shared memory */            \
             SGCN_CUDA(cudaFuncSetAttribute(full_mean_kernel<V, L, P>,                        \
-                                           cudaFuncAttributePreferredSharedMemoryCarveout, 44)); \
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, kStepCarveout)); \
             SGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                         \
                 &per_sm, full_mean_kernel<V, L, P>, kAggThreads,                             \
                 sizeof(int32_t) * (2 * (size_t)kFullStageRows + 2 + kFullOvMax) + 2 * 2 * kFullOvMax)); \

@@ -7,6 +7,7 @@ static thread_local std::string t_last_error;
 std::atomic<int64_t> g_launches{0};
 unsigned long long* g_trace = nullptr;
 int g_pdl = 1;      // on by default; SGCN_TUNE_PDL / env SGCN_PDL=0 turn it off
+thread_local int t_pdl_off = 0;
 
 void set_error(const std::string& msg) { t_last_error = msg; }
 

@@ -57,6 +57,16 @@ inline int cuda_fail(cudaError_t e, const char* what, const char* file, int line
 // stream predecessor is still running, does the part of its work that does not depend on it, and
 // orders the rest with griddepcontrol.wait (sgcn_tune_set SGCN_TUNE_PDL)
 extern int g_pdl;
+// per host thread: > 0 while a driver wants plain stream-ordered launches from the PDL-capable launch sites
+// (a kernel launched programmatically becomes resident as soon as its predecessors let it and then sits in
+// griddepcontrol.wait holding registers / shared memory -- right for the one kernel that continues the
+// critical chain, wrong for side-branch kernels whose inputs are a whole full-neighbour mean away)
+extern thread_local int t_pdl_off;
+struct PdlOff {
+    bool on;
+    explicit PdlOff(bool enable = true) : on(enable) { if (on) ++t_pdl_off; }
+    ~PdlOff() { if (on) --t_pdl_off; }
+};
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t dyn, cudaStream_t st,
@@ -70,17 +80,18 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_pdl ? 1 : 0;
+    cfg.numAttrs = (g_pdl && t_pdl_off == 0) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // An SM re-partitions its L1 / shared memory only when idle: a kernel whose preferred carve-out differs
 // from that of the kernel occupying the SMs (the full-neighbour mean holds every SM for most of a
 // step) may have to wait for an SM to drain.  For the sampler / full-mean pair that cost 13 us per step
-// (DESIGN section 3); the other kernels that run beside the mean ask for the SAME ~100 KB carve-out (44 %)
+// (DESIGN section 3); the other kernels that run beside the mean ask for the SAME 132 KB carve-out (58 %: two
+// full-mean CTAs with their override tables, 2 x 27 KB, plus one 47 KB train-sampler CTA must fit together)
 // as a precaution -- an A/B on the side-branch kernels (SGCN_NO_MATCH_CARVEOUT=1) showed no measurable
 // difference in round 1, their late starts are dependent-launch latency under load, not re-partitioning.
-constexpr int kStepCarveout = 44;
+constexpr int kStepCarveout = 58;
 template <typename K>
 inline void match_step_carveout(K kernel, bool* done) {
     if (!*done) {

@@ -1314,7 +1314,7 @@ static int expand_uniform(sgcn_sampler* s, Level& lv, const int32_t* field_in,
             // same ~100 KB carve-out as full_mean_kernel: whichever of the two reaches an SM first,
             // the other can join it without a re-partition
             SGCN_CUDA(cudaFuncSetAttribute(expand_fused_kernel<256, 4>,
-                                           cudaFuncAttributePreferredSharedMemoryCarveout, 44));
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, kStepCarveout));
             attr_set = true;
         }
         const int hbits = fused_hash_bits(nb, (int)sb);
@@ -1864,7 +1864,7 @@ int sgcn_sampler_expand_train(sgcn_sampler* s, const int32_t* ids, int32_t n, in
     if (!attr_set) {
         SGCN_CUDA(cudaFuncSetAttribute(expand_train_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kFusedSmemBytes));
-        SGCN_CUDA(cudaFuncSetAttribute(expand_train_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, 44));
+        SGCN_CUDA(cudaFuncSetAttribute(expand_train_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, kStepCarveout));
         attr_set = true;
     }
     const int hbits = fused_hash_bits(B, sb);

@@ -620,6 +620,10 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
         // ---- pre: everything of pass k+1 that does not read the history ----
         if (k + 1 < n) STEP_TRY(ahead(k + 1));
         // ---- side: the sampled aggregate + backward of pass k (history as of write-back k-1) ----
+        // plain launches: a programmatic launch here would sit resident in griddepcontrol.wait for most of a
+        // full-neighbour mean and keep the NEXT mean's thread blocks off those SMs (profiles/r02_timeline_*)
+        {
+        PdlOff side_plain;
         SGCN_CUDA(cudaStreamWaitEvent(side, st->t_pre[k % R], 0));
         if (k >= 1 && !overlap) SGCN_CUDA(cudaStreamWaitEvent(side, st->t_rest[(k - 1) % R], 0));
         if (d.mode == 0) {
@@ -652,7 +656,9 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
             STEP_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
                                          st->pipe + 1, side));
             SGCN_CUDA(cudaEventRecord(st->t_rest[k % R], side));
-        } else {
+        }
+        }
+        if (!overlap) {                  // on the chain (programmatic launch: it is the chain's next link)
             SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_fwd[k % R], 0));
             if (!cv) {
                 STEP_TRY(sgcn_sampler_mark_consumed(smp, chain));

@@ -73,7 +73,7 @@ class HotPathStep:
         self.graph = None
         self.graph_host = None
         self.launches_per_step = None
-        self._views = [None, None, None]
+        self._views = {}
         self._last_sampler_slot = None      # set by the native driver (its sampler sets rotate over three)
         self._pinned_out = None
         self._pipe = None           # graphs of the cross-step pipelined driver
@@ -108,7 +108,7 @@ class HotPathStep:
 
     def _ensure_views(self, slot):
         """zero-copy views of the sampler's buffer set `slot` (the addresses never change once reserved)"""
-        if self._views[slot] is None:
+        if self._views.get(slot) is None:
             s = self.sampler
             s.set_slot(slot)
             names = ("field", "rowptr_s", "rowptr_f", "edg_t", "tgt", "edg_w", "scales", "meta")

@@ -283,3 +283,36 @@ def test_full_mean_skewed_rows_and_empty_rows():
         y0 = torch.zeros((len(deg), d), device="cuda"); y1 = torch.ones((len(deg), d), device="cuda")
         ops.full_history_mean(dev(nodes), dev(indptr), len(deg), dev(indptr), dev(cols), dev(w), dev(hist), y0, y1)
         close(y0, want, "full mean d=%d" % d); close(y1, want + 1.0, "full mean second output")
+
+
+@pytest.mark.skipif(not native.have_ref(), reason="oracle/_ref not built (reference sources absent)")
+def test_full_mean_kernel_against_the_references_own_csr_loop():
+    """full_mean_kernel vs `compute_history` (gcn/history.cpp:10-37, the reference's commented-out CSR loop,
+    compiled into oracle/_ref by oracle/Makefile): same rows, same permuted adjacency; fp32 sums in a different
+    order, so within 1e-4 of the row scale element-wise; float64 torch.sparse.mm as the third opinion."""
+    from stochastic_gcn_b200 import graphs, ops
+    from stochastic_gcn_b200.sampler import DeviceSampler
+    g = graphs.powerlaw_graph(4000, 200_000, seed=6, device="cuda", max_degree=700)
+    D, B = 128, 200
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    hist = torch.randn((g.n, D), generator=gen, device="cuda")
+    s = DeviceSampler(g.data, g.indices, g.indptr, L=1, cv=True)
+    s.seed(3)
+    for _ in range(2):                                   # second batch: rows already permuted once
+        ids = torch.randperm(g.n, generator=gen, device="cuda")[:B].to(torch.int32)
+        s.start_batch(ids); s.expand(2)
+    y = torch.zeros((B, D), device="cuda")
+    ops.full_history_mean(s.view("field"), s.view("rowptr_f"), B, s.view("adj_p"), s.view("adj_i"), s.view("adj_w"),
+                          hist, y)
+    adj_i, adj_w = s.host("adj_i", s.num_edges), s.host("adj_w", s.num_edges)
+    adj_p = g.indptr.cpu().numpy()
+    ref = native.ref_compute_history(adj_w, adj_i, adj_p, ids.cpu().numpy(), hist.cpu().numpy()).astype(np.float64)
+    got = y.cpu().numpy().astype(np.float64)
+    rowscale = np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(got - ref) <= 1e-4 * np.abs(ref) + 1e-4 * rowscale).all()
+    rows = torch.repeat_interleave(torch.arange(B), torch.from_numpy(np.diff(adj_p)[ids.cpu().numpy()]))
+    pos = np.concatenate([np.arange(adj_p[i], adj_p[i + 1]) for i in ids.cpu().numpy()])
+    a = torch.sparse_coo_tensor(torch.stack([rows, torch.from_numpy(adj_i[pos].astype(np.int64))]),
+                                torch.from_numpy(adj_w[pos].astype(np.float64)), size=(B, g.n))
+    third = torch.sparse.mm(a, hist.cpu().double()).numpy()
+    assert np.abs(got - third).max() <= 1e-5 * np.abs(third).max()

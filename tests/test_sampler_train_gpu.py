@@ -129,8 +129,8 @@ def test_train_waits_for_consumers_of_the_previous_train():
     torch.cuda.synchronize()
     s.expand_train(d0, first_set=0, stream=a)
     s.expand_train(d1, first_set=4, prev=d0, stream=a)
-    torch.cuda._sleep(2_000_000)                # (default stream) keep the marks late
-    b.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(b):                  # (not the legacy default stream: it would wait for stream a)
+        torch.cuda._sleep(2_000_000)            # keep the marks ~1 ms late
     for _ in range(4):
         s.mark_consumed(b)
     torch.cuda.synchronize()
