@@ -402,6 +402,21 @@ int sgcn_wb_wait_apply(float* hist, int64_t ld_h, int32_t D, const void* recv_ev
                        int64_t slot_bytes, int32_t world, int32_t n_bound, int32_t* owner,
                        const int32_t* flags, const int32_t* epoch, int32_t* timeout_flag,
                        int32_t* done_counter /*optional, as sgcn_history_update*/, void* stream);
+/* Ring form of the peer transport (what sgcn_step_run_trains uses): `ring` receive areas instead of two, and
+ * separate counters for the epochs PUSHED (push_epoch, advanced by push_ring) and APPLIED (apply_epoch, advanced
+ * by wait_apply_ring), so that a rank can publish the rows of pass k as soon as they are gathered -- one pass
+ * ahead of the pass that applies them -- and fast ranks can run ahead of slow ones.  Epoch e lands in area
+ * e % ring: dst_base[k] (HOST array) = rank k's receive base + my_rank * slot_bytes, area a at + a * ring_stride;
+ * recv_base = this rank's receive base.  With the dependencies of sgcn_step_run_trains a rank is never more
+ * than 6 epochs ahead of the slowest rank's applies: ring = 8. */
+int sgcn_wb_push_ring(const int32_t* field, const int32_t* n_dev, int32_t n_bound, const float* rows,
+                      int64_t ld_rows, int32_t D, void* const* dst_base /*HOST*/, int32_t n_dst, int32_t ring,
+                      int64_t ring_stride, void* const* peer_flags /*HOST*/, int32_t my_rank, int32_t* push_epoch,
+                      int32_t* block_counter, void* stream);
+int sgcn_wb_wait_apply_ring(float* hist, int64_t ld_h, int32_t D, const void* recv_base, int64_t slot_bytes,
+                            int32_t world, int32_t n_bound, int32_t* owner, const int32_t* flags, int32_t ring,
+                            int64_t ring_stride, int32_t* apply_epoch, int32_t* apply_counter /*scratch = 0*/,
+                            int32_t* timeout_flag, int32_t* done_counter, void* stream);
 /* merge `world` payloads (slot r at gathered + r*slot_bytes) into hist; owner is an int32[N]
  * scratch table that must hold -1 everywhere on entry and does again on exit */
 int sgcn_wb_apply(float* hist, int64_t ld_h, int32_t D, const void* gathered, int64_t slot_bytes,
@@ -479,6 +494,13 @@ typedef struct {
      * history write-back leaves the critical path (row override in the next pass's full-neighbour mean) */
     float* x0_alt[2]; float* dx_alt;
     int32_t train; int32_t overlap_write_back;
+    /* ring form of the peer exchange, used by sgcn_step_run_trains when ring > 0 (sgcn_wb_push_ring /
+     * sgcn_wb_wait_apply_ring: the rows of pass k are pushed as soon as they are gathered, one pass ahead):
+     * ring_dst[k] = rank k's receive base + rank * slot_bytes, ring_recv = this rank's receive base,
+     * ring_peer_flags[k] = rank k's ring flag array, ring_flags = this rank's */
+    int32_t ring; int32_t pad0; int64_t ring_stride;
+    int32_t* push_epoch; int32_t* apply_epoch; int32_t* apply_stash; const int32_t* ring_flags;
+    void* ring_dst[16]; void* ring_peer_flags[16]; void* ring_recv;
 } sgcn_step_desc;
 int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_desc* desc /*HOST*/);
 void sgcn_step_destroy(sgcn_step* st);

@@ -112,6 +112,10 @@ SIGNATURES = {
                                    C.POINTER(_vp), _i32, _vp, _vp]),
     "sgcn_wb_wait_apply": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgcn_wb_apply": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "sgcn_wb_push_ring": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), _i32, _i32, _i64, C.POINTER(_vp),
+                                 _i32, _vp, _vp, _vp]),
+    "sgcn_wb_wait_apply_ring": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
+                                       _vp, _vp]),
     "sgcn_ipc_alloc": (_i32, [C.POINTER(_vp), _i64, _i32]),
     "sgcn_ipc_free": (_i32, [_vp]),
     "sgcn_ipc_export": (_i32, [_vp, _vp]),
@@ -129,7 +133,10 @@ class StepDesc(C.Structure):
                 ("dst_even", _vp * 16), ("dst_odd", _vp * 16), ("peer_flags", _vp * 16),
                 ("recv_even", _vp), ("recv_odd", _vp), ("flags", _vp), ("epoch", _vp), ("timeout_flag", _vp),
                 ("block_counter", _vp), ("owner", _vp),
-                ("x0_alt", _vp * 2), ("dx_alt", _vp), ("train", _i32), ("overlap_write_back", _i32)]
+                ("x0_alt", _vp * 2), ("dx_alt", _vp), ("train", _i32), ("overlap_write_back", _i32),
+                ("ring", _i32), ("pad0", _i32), ("ring_stride", _i64), ("push_epoch", _vp), ("apply_epoch", _vp),
+                ("apply_stash", _vp), ("ring_flags", _vp), ("ring_dst", _vp * 16), ("ring_peer_flags", _vp * 16),
+                ("ring_recv", _vp)]
 
 
 _lib = None

@@ -1134,16 +1134,20 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
 #define CALL(V, L, P)                                                                        \
     do {                                                                                     \
         static int per_sm = 0;                                                               \
-        if (per_sm == 0) {                                                                   \
-            /* ask for a ~100 KB shared-memory carve-out although two CTAs need far less: the next  \
-               batch's sampler CTA (up to ~47 KB) can then join an SM that runs this kernel without \
-               waiting for the SM to drain and re-partition its L1 / shared memory */            \
+        static size_t per_sm_dyn = 0;                                                        \
+        if (per_sm == 0 || dyn != per_sm_dyn) {                                              \
+            /* ask for a 132 KB shared-memory carve-out although two CTAs need far less: a train-sampler \
+               CTA (~47 KB) can then join an SM that runs this kernel without waiting for the SM  \
+               to drain and re-partition its L1 / shared memory.  Occupancy is asked for THIS    \
+               launch's dynamic shared memory (a worst-case figure halved it: 35 us per launch). */ \
             SGCN_CUDA(cudaFuncSetAttribute(full_mean_kernel<V, L, P>,                        \
                                            cudaFuncAttributePreferredSharedMemoryCarveout, kStepCarveout)); \
+            SGCN_CUDA(cudaFuncSetAttribute(full_mean_kernel<V, L, P>,                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
             SGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                         \
-                &per_sm, full_mean_kernel<V, L, P>, kAggThreads,                             \
-                sizeof(int32_t) * (2 * (size_t)kFullStageRows + 2 + kFullOvMax) + 2 * 2 * kFullOvMax)); \
+                &per_sm, full_mean_kernel<V, L, P>, kAggThreads, dyn));                      \
             if (per_sm < 1) per_sm = 1;                                                      \
+            per_sm_dyn = dyn;                                                                \
         }                                                                                    \
         SGCN_CUDA(launch_pdl(full_mean_kernel<V, L, P>, kNumSMs * per_sm, kAggThreads, dyn, st, a)); \
     } while (0)

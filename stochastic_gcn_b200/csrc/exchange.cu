@@ -62,8 +62,23 @@ __global__ void __launch_bounds__(256)
 wb_claim_kernel(const char* g_even, const char* g_odd,
                 const int32_t* __restrict__ epoch, int64_t slot_bytes, int world, int n_bound,
                 int32_t* __restrict__ owner, const int32_t* flags, int32_t* timeout_flag,
-                long long max_spins, int32_t* done_counter, unsigned long long* trace) {
+                long long max_spins, int32_t* done_counter, unsigned long long* trace,
+                int ring, int64_t ring_stride, int32_t* cur_stash) {
     TraceScope ts(trace, TR_WB_CLAIM);
+    // ring protocol: `epoch` counts the epochs APPLIED so far (the pushes run ahead on a counter of their own);
+    // this launch applies epoch *epoch + 1.  Under programmatic launches the only ordering between the kernels
+    // of the chain is "a dependent launches after EVERY block of its predecessor has executed
+    // launch_dependents", so each kernel reads the counter it needs BEFORE that instruction and publishes what
+    // its successor needs BEFORE it too: this kernel stashes the epoch for its copy kernel, the copy kernel
+    // advances *epoch for the next claim (which can only launch two kernels later).
+    const int cur = epoch ? (ring > 0 ? *(volatile const int32_t*)epoch + 1 : *epoch) : 0;
+    if (ring > 0) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+            *(volatile int32_t*)cur_stash = cur;
+            __threadfence();
+        }
+        __syncthreads();
+    }
     // (PDL) this kernel is launched while its stream predecessor -- the full-neighbour mean -- is still
     // running: waiting for the peers' payloads and the claim pass touch nothing the mean reads, so they
     // overlap it; the dependent copy kernel may become resident right away
@@ -73,7 +88,7 @@ wb_claim_kernel(const char* g_even, const char* g_odd,
     if (flags) {
         // peer transport: every block first waits (bounded) until all ranks have published this epoch
         if (threadIdx.x < world) {
-            const int step = *epoch;
+            const int step = cur;
             volatile const int32_t* f = (volatile const int32_t*)flags;
             long long spins = 0;
             while (f[threadIdx.x] < step) {
@@ -88,7 +103,7 @@ wb_claim_kernel(const char* g_even, const char* g_odd,
         __syncthreads();
     }
     const int r = blockIdx.y;
-    const char* gathered = (epoch && (*epoch & 1)) ? g_odd : g_even;
+    const char* gathered = ring > 0 ? g_even + (int64_t)(cur % ring) * ring_stride : ((cur & 1) ? g_odd : g_even);
     const char* slot = gathered + (int64_t)r * slot_bytes;
     // payloads were written by other GPUs while this kernel may already have been resident: read
     // them through L2 (ld.global.cg / volatile), never through a possibly stale L1 / read-only path
@@ -110,12 +125,23 @@ __global__ void __launch_bounds__(256)
 wb_copy_kernel(const char* g_even, const char* g_odd,
                const int32_t* __restrict__ epoch, int64_t slot_bytes, int world, int n_bound,
                int32_t* __restrict__ owner, float* __restrict__ hist, int64_t ld_h, int D,
-               unsigned long long* trace) {
+               unsigned long long* trace, int ring, int64_t ring_stride, int32_t* epoch_out,
+               const int32_t* cur_stash) {
     TraceScope ts(trace, TR_WB_COPY);
+    // ring protocol: the epoch being applied was stashed by the claim kernel; advance the applied-epoch
+    // counter for the NEXT claim before any dependent can launch (see wb_claim_kernel)
+    const int cur = ring > 0 ? *(volatile const int32_t*)cur_stash : (epoch ? *epoch : 0);
+    if (ring > 0) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+            *(volatile int32_t*)epoch_out = cur;
+            __threadfence();
+        }
+        __syncthreads();
+    }
     asm volatile("griddepcontrol.launch_dependents;");     // (PDL) the next full-neighbour mean's preamble
     asm volatile("griddepcontrol.wait;" ::: "memory");      // (PDL) claims final, history no longer read
     const int r = blockIdx.y;
-    const char* gathered = (epoch && (*epoch & 1)) ? g_odd : g_even;
+    const char* gathered = ring > 0 ? g_even + (int64_t)(cur % ring) * ring_stride : ((cur & 1) ? g_odd : g_even);
     const char* slot = gathered + (int64_t)r * slot_bytes;
     const int n = min(__ldcg((const int32_t*)slot), n_bound);
     const int32_t* ids = (const int32_t*)(slot + wb_ids_offset());
@@ -189,7 +215,7 @@ int sgcn_wb_pack(const int32_t* field, const int32_t* n_dev, int32_t n_bound, co
     PeerPtrs p{};
     int rc = fill_ptrs(p, dst, n_dst, "wb_pack");
     if (rc != SGCN_OK) return rc;
-    WbPushArgs a{field, n_dev, n_bound, rows, ld_rows, D, p, p, n_dst, step, nullptr, p, 0, nullptr};
+    WbPushArgs a{field, n_dev, n_bound, rows, ld_rows, D, p, p, n_dst, step, nullptr, p, 0, nullptr, 0, 0};
     wb_pack_kernel<<<pack_blocks(n_bound, D), 256, 0, (cudaStream_t)stream>>>(a, g_trace);
     SGCN_LAUNCHED();
     return SGCN_OK;
@@ -208,7 +234,7 @@ int sgcn_wb_push(const int32_t* field, const int32_t* n_dev, int32_t n_bound, co
     if (rc == SGCN_OK) rc = fill_ptrs(pf, peer_flags, n_dst, "wb_push");
     if (rc != SGCN_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    WbPushArgs a{field, n_dev, n_bound, rows, ld_rows, D, pe, po, n_dst, 0, epoch, pf, my_rank, block_counter};
+    WbPushArgs a{field, n_dev, n_bound, rows, ld_rows, D, pe, po, n_dst, 0, epoch, pf, my_rank, block_counter, 0, 0};
     wb_pack_kernel<<<pack_blocks(n_bound, D), 256, 0, st>>>(a, g_trace);
     SGCN_LAUNCHED();
     if (!block_counter) {      // no scratch counter given: publish from a second, stream-ordered launch
@@ -218,14 +244,36 @@ int sgcn_wb_push(const int32_t* field, const int32_t* n_dev, int32_t n_bound, co
     return SGCN_OK;
 }
 
+int sgcn_wb_push_ring(const int32_t* field, const int32_t* n_dev, int32_t n_bound, const float* rows,
+                      int64_t ld_rows, int32_t D, void* const* dst_base, int32_t n_dst, int32_t ring,
+                      int64_t ring_stride, void* const* peer_flags, int32_t my_rank, int32_t* push_epoch,
+                      int32_t* block_counter, void* stream) {
+    SGCN_REQUIRE(field && n_dev && rows && dst_base && peer_flags && push_epoch && block_counter,
+                 "wb_push_ring: null pointer");
+    SGCN_REQUIRE(n_bound >= 0 && D > 0 && ld_rows >= D, "wb_push_ring: bad size");
+    SGCN_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers && my_rank >= 0 && my_rank < kMaxPeers, "wb_push_ring: 1..16 ranks");
+    SGCN_REQUIRE(ring >= 2 && ring <= 64 && ring_stride > 0 && ring_stride % 16 == 0, "wb_push_ring: bad ring");
+    PeerPtrs pb{}, pf{};
+    int rc = fill_ptrs(pb, dst_base, n_dst, "wb_push_ring");
+    if (rc == SGCN_OK) rc = fill_ptrs(pf, peer_flags, n_dst, "wb_push_ring");
+    if (rc != SGCN_OK) return rc;
+    WbPushArgs a{field, n_dev, n_bound, rows, ld_rows, D, pb, pb, n_dst, 0, push_epoch, pf, my_rank, block_counter,
+                 ring, ring_stride};
+    wb_pack_kernel<<<pack_blocks(n_bound, D), 256, 0, (cudaStream_t)stream>>>(a, g_trace);
+    SGCN_LAUNCHED();
+    return SGCN_OK;
+}
+
 static int launch_apply(float* hist, int64_t ld_h, int32_t D, const void* g_even, const void* g_odd,
                         const int32_t* epoch, int64_t slot_bytes, int32_t world, int32_t n_bound,
                         int32_t* owner, cudaStream_t st, const int32_t* flags = nullptr,
-                        int32_t* timeout_flag = nullptr, int32_t* done_counter = nullptr) {
+                        int32_t* timeout_flag = nullptr, int32_t* done_counter = nullptr, int ring = 0,
+                        int64_t ring_stride = 0, int32_t* epoch_out = nullptr, int32_t* apply_counter = nullptr) {
     dim3 g1(std::min(div_up(std::max(n_bound, 1), 256), 64), world);
     // ~2 s at 100 ns per spin: a peer that never arrives raises the flag instead of hanging the GPU
     SGCN_CUDA(launch_pdl(wb_claim_kernel, g1, dim3(256), 0, st, (const char*)g_even, (const char*)g_odd, epoch,
-                         slot_bytes, world, n_bound, owner, flags, timeout_flag, 20000000LL, done_counter, g_trace));
+                         slot_bytes, world, n_bound, owner, flags, timeout_flag, 20000000LL, done_counter, g_trace,
+                         ring, ring_stride, apply_counter));
     SGCN_LAUNCHED();
     // few CTAs: with PDL they sit resident beside the full-neighbour mean, and the next batch's sampler
     // CTA still has to find an SM with registers to spare
@@ -234,10 +282,12 @@ static int launch_apply(float* hist, int64_t ld_h, int32_t D, const void* g_even
                      (((uintptr_t)g_even) & 15) == 0 && (((uintptr_t)g_odd) & 15) == 0;
     if (vec)
         SGCN_CUDA(launch_pdl(wb_copy_kernel<true>, g2, dim3(256), 0, st, (const char*)g_even, (const char*)g_odd,
-                             epoch, slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace));
+                             epoch, slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace, ring, ring_stride,
+                             epoch_out, apply_counter));
     else
         SGCN_CUDA(launch_pdl(wb_copy_kernel<false>, g2, dim3(256), 0, st, (const char*)g_even, (const char*)g_odd,
-                             epoch, slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace));
+                             epoch, slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace, ring, ring_stride,
+                             epoch_out, apply_counter));
     SGCN_LAUNCHED();
     return SGCN_OK;
 }
@@ -271,6 +321,22 @@ int sgcn_wb_wait_apply(float* hist, int64_t ld_h, int32_t D, const void* recv_ev
     // the wait is fused into the claim pass (every block polls the flags before touching a payload)
     return launch_apply(hist, ld_h, D, recv_even, recv_odd, epoch, slot_bytes, world, n_bound, owner, st,
                         flags, timeout_flag, done_counter);
+}
+
+int sgcn_wb_wait_apply_ring(float* hist, int64_t ld_h, int32_t D, const void* recv_base, int64_t slot_bytes,
+                            int32_t world, int32_t n_bound, int32_t* owner, const int32_t* flags, int32_t ring,
+                            int64_t ring_stride, int32_t* apply_epoch, int32_t* apply_counter,
+                            int32_t* timeout_flag, int32_t* done_counter, void* stream) {
+    SGCN_REQUIRE(hist && recv_base && owner && flags && apply_epoch && apply_counter && timeout_flag,
+                 "wb_wait_apply_ring: null pointer");
+    SGCN_REQUIRE(world >= 1 && world <= 32 && n_bound > 0 && D > 0 && ld_h >= D, "wb_wait_apply_ring: bad size");
+    SGCN_REQUIRE(slot_bytes >= wb_payload_bytes(n_bound, D), "wb_wait_apply_ring: slot smaller than a payload");
+    SGCN_REQUIRE(ring >= 2 && ring <= 64 && ring_stride >= (int64_t)world * slot_bytes && ring_stride % 16 == 0,
+                 "wb_wait_apply_ring: bad ring");
+    SGCN_REQUIRE((int64_t)world * n_bound < 0x7fffffff, "wb_wait_apply_ring: world * n_bound overflows");
+    return launch_apply(hist, ld_h, D, recv_base, recv_base, apply_epoch, slot_bytes, world, n_bound, owner,
+                        (cudaStream_t)stream, flags, timeout_flag, done_counter, ring, ring_stride, apply_epoch,
+                        apply_counter);
 }
 
 // ---- peer memory plumbing (cudaIpc): plain cudaMalloc'd buffers that other ranks can map -----

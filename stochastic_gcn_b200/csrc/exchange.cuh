@@ -24,6 +24,9 @@ struct WbPushArgs {
     const float* rows; int64_t ld_rows; int D;
     PeerPtrs dst_even, dst_odd; int n_dst; int step; int32_t* epoch; PeerPtrs flags; int my_rank;
     int32_t* block_counter;
+    // ring > 0: epoch e lands in receive area e % ring, at dst_even.p[k] + (e % ring) * ring_stride (dst_odd
+    // unused); ring == 0: the two-area (even / odd) protocol
+    int ring; int64_t ring_stride;
 };
 
 // pack {count, ids, rows} into up to `n_dst` destinations (own buffer and/or peers' receive slots);
@@ -32,7 +35,11 @@ __device__ __forceinline__ void wb_pack_body(const WbPushArgs& a, int bid, int n
     // peer transport: this push belongs to epoch *epoch + 1 and lands in the slot set of its parity
     int step = a.step;
     if (a.epoch) step = *a.epoch + 1;
-    const PeerPtrs& dst = (a.epoch && (step & 1)) ? a.dst_odd : a.dst_even;
+    PeerPtrs dst = (a.epoch && a.ring == 0 && (step & 1)) ? a.dst_odd : a.dst_even;
+    if (a.ring > 0) {
+        const int64_t off = (int64_t)(step % a.ring) * a.ring_stride;
+        for (int k = 0; k < a.n_dst; ++k) dst.p[k] += off;
+    }
     const int n = min(*a.n_dev, a.n_bound);
     const int D = a.D, n_dst = a.n_dst;
     const int64_t t0 = (int64_t)bid * blockDim.x + threadIdx.x;

@@ -521,6 +521,7 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
     const int B = d.batch, H = d.hidden, R = sgcn_step::kRing2, T = st->train;
     const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0, multi = d.world > 1 && cv;
     const bool overlap = cv && !multi && d.overlap_write_back != 0 && d.x0_rows <= 4096;
+    const bool ring = multi && d.ring > 0;
     const int width = H * (concat ? 2 : 1);
     cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp, pre = st->pre,
                  copy = st->copy;
@@ -573,6 +574,12 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
                                       nullptr, 0, 0, nullptr, cv ? B : 0, H, cv ? nb(d.out[r]) : nullptr, d.ld_out, pre));
         if (cvd) STEP_TRY(sgcn_copy_rows_pad(nullptr, 0, 0, nullptr, B, H, nb(d.out_mu[r]), d.ld_out, pre));
         SGCN_CUDA(cudaEventRecord(st->t_pre[k % R], pre));
+        // multi-GPU, ring form: the rows this pass will write back exist now -- publish them to every rank a
+        // whole pass before anybody applies them (their flags are long up when the claim pass looks)
+        if (ring)
+            STEP_TRY(sgcn_wb_push_ring(v.field, v.meta + 1, d.wb_bound, x0b[k % 3] + (cvd ? H : 0), d.ld_x0, H, d.ring_dst,
+                                       d.world, d.ring, d.ring_stride, d.ring_peer_flags, d.rank, d.push_epoch,
+                                       d.block_counter, pre));
         return SGCN_OK;
     };
 
@@ -633,14 +640,14 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
             STEP_TRY(sgcn_spmm_csr_bwd(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, d_nb, d.ld_dout, H, dxb[r],
                                        d.ld_dx, side));
         } else if (!cvd) {
-            if (multi)      // the write-back push rides on the sampled launch (see sgcn_wb_push_attach)
+            if (multi && !ring)      // two-area form: the push rides on the sampled launch (sgcn_wb_push_attach)
                 STEP_TRY(sgcn_wb_push_attach(v.field, n_in_dev, d.wb_bound, new_hist, d.ld_x0, H, d.dst_even, d.dst_odd,
                                              d.world, d.peer_flags, d.rank, d.epoch, d.block_counter));
             STEP_TRY(sgcn_cv_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, B, n_out_dev, x, d.ld_x0, d.history,
                                              d.ld_hist, H, nb(out_r), d.ld_out, concat ? out_r : nullptr, d.ld_out, 1,
                                              d_nb, d.ld_dout, dxb[r], d.ld_dx, side));
         } else {
-            if (multi)
+            if (multi && !ring)
                 STEP_TRY(sgcn_wb_push_attach(v.field, n_in_dev, d.wb_bound, new_hist, d.ld_x0, H, d.dst_even, d.dst_odd,
                                              d.world, d.peer_flags, d.rank, d.epoch, d.block_counter));
             STEP_TRY(sgcn_cvd_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, v.scales, B, n_out_dev, x, d.ld_x0,
@@ -662,6 +669,10 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
             SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_fwd[k % R], 0));
             if (!cv) {
                 STEP_TRY(sgcn_sampler_mark_consumed(smp, chain));
+            } else if (ring) {
+                STEP_TRY(sgcn_wb_wait_apply_ring(d.history, d.ld_hist, H, d.ring_recv, d.slot_bytes, d.world, d.wb_bound,
+                                                 d.owner, d.ring_flags, d.ring, d.ring_stride, d.apply_epoch,
+                                                 d.apply_stash, d.timeout_flag, st->pipe + 1, chain));
             } else if (multi) {
                 STEP_TRY(sgcn_wb_wait_apply(d.history, d.ld_hist, H, d.recv_even, d.recv_odd, d.slot_bytes, d.world,
                                             d.wb_bound, d.owner, d.flags, d.epoch, d.timeout_flag, st->pipe + 1, chain));

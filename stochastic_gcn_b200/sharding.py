@@ -81,17 +81,24 @@ class _DevBytes:
                                          "version": 2, "strides": None}
 
 
+RING = 8      # receive areas of the ring form (include/sgcn_b200.h: sgcn_wb_push_ring)
+
+
 class PeerExchange:
     """cudaIpc plumbing of the peer transport: one exported allocation per rank holding
-    [flags int32[64] | epoch, timeout int32[64] | receive area even | receive area odd]."""
+    [flags int32[64] | epoch, timeout, ... int32[64] | RING receive areas of `world` slots each].
+    The two-area (even / odd) protocol of the one-pass drivers uses areas 0 and 1, the ring protocol of the
+    trains schedule all RING of them (never both in one run: they share the flag array)."""
 
     def __init__(self, rank, world, slot_bytes, device):
         import torch.distributed as dist
         lib = _lib.load()
         self.lib, self.rank, self.world, self.slot = lib, rank, world, int(slot_bytes)
         self.off_ctl, self.off_even = 256, 512
-        self.off_odd = self.off_even + world * self.slot
-        total = self.off_odd + world * self.slot
+        self.off_ring_flags = 128                   # ring-form flags: ints 32 .. 47 of the flag block
+        self.ring, self.ring_stride = RING, world * self.slot
+        self.off_odd = self.off_even + self.ring_stride
+        total = self.off_even + self.ring * self.ring_stride
         base = C.c_void_p()
         check(lib.sgcn_ipc_alloc(C.byref(base), total, 1))
         self.base, self.total = base.value, total
@@ -116,6 +123,9 @@ class PeerExchange:
         self.epoch = C.c_void_p(self.base + self.off_ctl)
         self.timeout = C.c_void_p(self.base + self.off_ctl + 4)
         self.block_counter = C.c_void_p(self.base + self.off_ctl + 8)   # scratch of the fused pack + signal
+        self.apply_epoch = C.c_void_p(self.base + self.off_ctl + 12)    # ring form: epochs applied so far
+        self.apply_stash = C.c_void_p(self.base + self.off_ctl + 16)    # ring form: claim -> copy hand-over
+        self.push_epoch = C.c_void_p(self.base + self.off_ctl + 20)     # ring form: epochs pushed so far
         self.recv_even = C.c_void_p(self.base + self.off_even)
         self.recv_odd = C.c_void_p(self.base + self.off_odd)
         self._ctl = torch.as_tensor(_DevBytes(self.base, 512), device=device).view(torch.int32)
@@ -213,6 +223,13 @@ class ShardedHotPathStep(HotPathStep):
             d.recv_even, d.recv_odd, d.flags = x.recv_even.value, x.recv_odd.value, x.flags.value
             d.epoch, d.timeout_flag, d.block_counter = x.epoch.value, x.timeout.value, x.block_counter.value
             d.owner = self.owner.data_ptr()
+            if os.environ.get("SGCN_WB_RING", "1") != "0":      # trains schedule: ring form, pushes one pass ahead
+                d.ring, d.ring_stride = x.ring, x.ring_stride
+                d.push_epoch, d.apply_epoch, d.apply_stash = x.push_epoch.value, x.apply_epoch.value, x.apply_stash.value
+                d.ring_flags, d.ring_recv = x.base + x.off_ring_flags, x.base + x.off_even
+                for i in range(self.world):
+                    d.ring_dst[i] = x.peer_base[i] + x.off_even + self.rank * x.slot
+                    d.ring_peer_flags[i] = x.peer_base[i] + x.off_ring_flags
         elif self.mode != "ns" and self.world > 1:
             raise RuntimeError("the native step driver needs the peer transport for multi-GPU runs")
         return d

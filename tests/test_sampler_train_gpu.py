@@ -118,13 +118,17 @@ def test_train_waits_for_consumers_of_the_previous_train():
     s = make(g, True, 9)
     o.seed(9)
     s.reserve_sets(8, B, degree)
-    s.pipeline(True)
+    a, b = torch.cuda.Stream(), torch.cuda.Stream()
+    # first launch of the mark kernel here, NOT while a train is spinning: with CUDA's lazy module loading a
+    # kernel's first launch may have to wait for the device to go idle (the step drivers run warm-up passes)
+    s.mark_consumed(b)
+    torch.cuda.synchronize()
+    s.pipeline(True)                            # arms the guard, counters back to zero
     rng = np.random.RandomState(3)
     perm = rng.permutation(n).astype(np.int32)
     t0 = perm[:4 * B].reshape(4, B).copy()
     t1 = perm[4 * B:8 * B].reshape(4, B).copy()
     t1[2, :8] = t0[1, :8]                       # shared with the previous train
-    a, b = torch.cuda.Stream(), torch.cuda.Stream()
     d0, d1 = torch.from_numpy(t0).cuda(), torch.from_numpy(t1).cuda()
     torch.cuda.synchronize()
     s.expand_train(d0, first_set=0, stream=a)
