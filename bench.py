@@ -293,7 +293,7 @@ class Rig:
                                     seed=args.seed)
             lo, hi = 0, self.g.n
         self.step.train = args.train
-        self.step.overlap_write_back = not args.no_overlap_write_back
+        self.step.overlap_write_back = args.overlap_write_back
         gen = torch.Generator(device=dev).manual_seed(7)
         self.step.d_out.normal_(generator=gen)
         self.step.history.normal_(generator=gen)      # a warm history table (zero rows would skip reductions)
@@ -321,9 +321,12 @@ def time_trains(rig, args, timed, warm, barrier, host_io):
         step.replay_trains(torch.stack(warm[:S]))              # first launch of the graph (upload) untimed
         barrier()
         e0.record()
-        step.replay_trains(table[:full])
-        if full < K:
-            step.run_trains(table[full:].contiguous(), first_train=args.first_train)
+        if args.eager_trains:
+            step.run_trains(table, first_train=args.first_train)
+        else:
+            step.replay_trains(table[:full])
+            if full < K:
+                step.run_trains(table[full:].contiguous(), first_train=args.first_train)
         e1.record()
         barrier()
         return e0.elapsed_time(e1), S, launches
@@ -542,8 +545,8 @@ def run_ours(args, w):
     value = total_edges / (ms * 1e-3)
     what = {"trains": "CUDA graph(s) of %d passes of the trains schedule: trains of %d batches sampled by one launch a "
                       "train ahead, gather one pass ahead, full-neighbour means back to back%s" % (
-                          S, args.train, "" if args.no_overlap_write_back or world > 1 else
-                          " (write-back off the chain: row override)"),
+                          S, args.train, " (write-back off the chain: row override)"
+                          if args.overlap_write_back and world == 1 else ""),
             "graph": "CUDA graphs of %d steps; batch k+1's sampler (1 CTA) runs beside batch k's aggregate" % S,
             "native": "plain stream launches from C++ on three streams, two batches of sampler lookahead",
             "one-graph-per-step": "one CUDA graph per step, back to back"}[driver]
@@ -626,8 +629,11 @@ def main():
     ap.add_argument("--train", type=int, default=16, help="batches sampled per launch by the trains schedule (2..32)")
     ap.add_argument("--first-train", type=int, default=4,
                     help="length of the first train of a graph (short: smaller start-up bubble)")
-    ap.add_argument("--no-overlap-write-back", action="store_true",
-                    help="keep the history write-back on the critical chain (A/B of the row override)")
+    ap.add_argument("--overlap-write-back", action="store_true",
+                    help="take the history write-back off the critical chain (row override in the next pass's "
+                         "full-neighbour mean); measured slower inside CUDA graphs, see DESIGN section 1")
+    ap.add_argument("--eager-trains", action="store_true",
+                    help="trains driver as plain stream launches from C++ (no CUDA graphs): A/B of the graph overhead")
     ap.add_argument("--no-also", action="store_true", help="skip the extra keys for the other BASELINE configurations")
     ap.add_argument("--driver", default="trains", choices=["trains", "native", "graph"],
                     help="schedule of the timed region: trains (default; csrc/step.cu:sgcn_step_run_trains as CUDA "

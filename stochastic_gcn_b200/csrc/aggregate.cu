@@ -375,6 +375,12 @@ struct FullArgs {
     const float* ov_rows; int64_t ld_ov;
 };
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 constexpr unsigned short kOvEmpty = 0xffffu;
 __device__ __forceinline__ unsigned ov_hash(int node, int bits) { return ((unsigned)node * 2654435761u) >> (32 - bits); }
 
@@ -407,6 +413,9 @@ full_mean_kernel(const FullArgs a) {
     __shared__ int64_t s_off[kFullWarps][kFullMacro];            // adj_i * ld_h (element offset of the row)
     __shared__ float s_w[kFullWarps][kFullMacro];
     __shared__ int32_t s_r[kFullWarps][kFullMacro];
+    __shared__ int32_t s_lcol[kFullWarps][kFullMacro];           // landing buffers of the NEXT chunk's metadata
+    __shared__ float s_lw[kFullWarps][kFullMacro];
+    __shared__ int32_t s_lr[kFullWarps][kFullMacro];
     const int n_out = dev_count(a.n_out_dev, a.n_out);
     if (n_out <= 0) return;
     const bool staged = n_out <= a.stage_rows;
@@ -470,6 +479,66 @@ full_mean_kernel(const FullArgs a) {
 #pragma unroll
     for (int k = 0; k < VPL; ++k) acc[k] = T::zero();
     int cur = -1;                                                 // row this group is accumulating
+
+    // Metadata of a macro-chunk (row, column id, weight of 64 positions, two per lane) is FETCHED one
+    // macro-chunk ahead: the lanes resolve their positions' rows, then the column ids and weights go
+    // global -> shared memory as 4-byte asynchronous copies (cp.async / LDGSTS: no registers held while
+    // they fly) into a landing buffer, under the previous chunk's streaming history rows.  It is COMMITTED
+    // -- element offsets computed, override rows substituted -- right before its own rows are issued.
+    // ncu on the round-1 kernel: 22 % of the stall samples sat in this staging when it ran synchronously
+    // in front of every chunk (profiles/r01_full_mean_ncu.json).
+    int32_t* l_col = s_lcol[wib];
+    float* l_w = s_lw[wib];
+    int32_t* l_r = s_lr[wib];
+    auto fetch = [&](int pm, int pend) {
+#pragma unroll
+        for (int t = 0; t < kFullMacro / 32; ++t) {
+            const int j = t * 32 + lane;
+            const int p = pm + j;
+            if (p < pend) {
+                int lo = 0, hi = n_out;                           // last r with ptr[r] <= p
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (ptr[mid] <= p) lo = mid; else hi = mid;
+                }
+                l_r[j] = lo;
+                const int q = staged ? (s_base[lo] + p)
+                                     : (__ldg(a.adj_p + __ldg(a.nodes + lo)) + (p - ptr[lo]));
+                cp_async4(l_col + j, a.adj_i + q);
+                cp_async4(l_w + j, a.adj_w + q);
+            } else {
+                l_r[j] = -1;
+                l_col[j] = 0;
+                l_w[j] = 0.f;
+            }
+        }
+        cp_async_commit();
+    };
+    auto commit = [&]() {
+        cp_async_wait_all();
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < kFullMacro / 32; ++t) {
+            const int j = t * 32 + lane;
+            const int col = l_col[j];
+            const float w = l_w[j];
+            const int r = l_r[j];
+            int64_t off = (int64_t)col * a.ld_h;
+            if (ov_n > 0 && r >= 0) {
+                unsigned h = ov_hash(col, a.ov_bits);
+                for (;;) {
+                    const unsigned short sl = s_ovtab[h];
+                    if (sl == kOvEmpty) break;
+                    if (s_ovid[sl] == col) { off = ov_base + (int64_t)sl * a.ld_ov; break; }
+                    h = (h + 1) & ov_mask;
+                }
+            }
+            my_off[j] = off;
+            my_w[j] = a.square ? w * w : w;
+            my_r[j] = r;
+        }
+    };
+    fetch(p0, p1);                                                // (PDL) still under the stream predecessor
     // (PDL) history rows: after the write-back.  With the row override the stream predecessor is the
     // previous pass's full-neighbour mean, which writes nothing this kernel reads: the wait moves to
     // the end (completion order only) and the two kernels overlap tail to head.
@@ -481,41 +550,8 @@ full_mean_kernel(const FullArgs a) {
         if (lane == 0) next_chunk = atomicAdd(a.work, 1);
     }
     for (int pm = p0; pm < p1; pm += kFullMacro) {
-        // ---- stage: metadata of up to 64 positions, two per lane ----
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < kFullMacro / 32; ++t) {
-            const int p = pm + t * 32 + lane;
-            int r = -1;
-            int64_t off = 0;
-            float w = 0.f;
-            if (p < p1) {
-                int lo = 0, hi = n_out;                           // last r with ptr[r] <= p
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (ptr[mid] <= p) lo = mid; else hi = mid;
-                }
-                r = lo;
-                const int q = staged ? (s_base[lo] + p)
-                                     : (__ldg(a.adj_p + __ldg(a.nodes + lo)) + (p - ptr[lo]));
-                const int col = __ldg(a.adj_i + q);
-                off = (int64_t)col * a.ld_h;
-                if (ov_n > 0) {
-                    unsigned h = ov_hash(col, a.ov_bits);
-                    for (;;) {
-                        const unsigned short sl = s_ovtab[h];
-                        if (sl == kOvEmpty) break;
-                        if (s_ovid[sl] == col) { off = ov_base + (int64_t)sl * a.ld_ov; break; }
-                        h = (h + 1) & ov_mask;
-                    }
-                }
-                w = __ldg(a.adj_w + q);
-                if (a.square) w *= w;
-            }
-            my_off[t * 32 + lane] = off;
-            my_w[t * 32 + lane] = w;
-            my_r[t * 32 + lane] = r;
-        }
+        __syncwarp();                                             // the previous chunk's rows are consumed
+        commit();
         __syncwarp();
         const int cnt = min(kFullMacro, p1 - pm);
         const int ng = (cnt + STEP - 1) / STEP;
@@ -562,11 +598,13 @@ full_mean_kernel(const FullArgs a) {
         // ---- stream: two register buffers, loads of group i+1 in flight while group i is consumed ----
         V bufA[UN][VPL], bufB[UN][VPL];
         issue(bufA, 0);
+        if (ng > 1) issue(bufB, 1);
+        if (pm + kFullMacro < p1) fetch(pm + kFullMacro, p1);     // next chunk's metadata behind the first rows
         for (int gi = 0; gi < ng; gi += 2) {
-            if (gi + 1 < ng) issue(bufB, gi + 1);
             consume(bufA, gi);
             if (gi + 2 < ng) issue(bufA, gi + 2);
             if (gi + 1 < ng) consume(bufB, gi + 1);
+            if (gi + 3 < ng) issue(bufB, gi + 3);
         }
     }
     if (!a.work) break;
@@ -574,6 +612,7 @@ full_mean_kernel(const FullArgs a) {
     p0 = next_chunk * kFullMacro;
     if (p0 >= nnz) break;
     p1 = min(p0 + kFullMacro, nnz);
+    fetch(p0, p1);
   }
     if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
     if (a.ov_ids) grid_dep_wait();

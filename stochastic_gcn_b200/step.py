@@ -81,7 +81,7 @@ class HotPathStep:
         self._pipe_done = None
         self._last_slot = 0
         self.train = 16                # batches sampled per launch by the trains schedule (run_trains)
-        self.overlap_write_back = True  # trains schedule: write-back off the chain (row override in the next mean)
+        self.overlap_write_back = False  # trains schedule: write-back off the chain (row override in the next mean)
         self._trains = None            # captured graphs of the trains schedule
         self._last_x0 = self._last_dx = None
         self._s_b = torch.cuda.Stream(device=self.dev)      # side branch of the pass

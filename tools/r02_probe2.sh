@@ -9,13 +9,15 @@ echo "pytest new exit $?"; tail -15 "$OUT/pytest_new.log"
 timeout 300 python __graft_entry__.py --smoke > "$OUT/smoke.log" 2>&1; echo "smoke exit $?"; tail -3 "$OUT/smoke.log"
 b() { name=$1; shift; timeout 300 python bench.py "$@" > "$OUT/$name.json" 2> "$OUT/$name.err"; echo "$name exit $?"; cut -c1-300 "$OUT/$name.json"; tail -3 "$OUT/$name.err"; }
 b k20 --steps 20 --warmup 5 --no-cpu --no-also
-b k20_nooverlap --steps 20 --warmup 5 --no-cpu --no-also --no-overlap-write-back
+b k20_overlap --steps 20 --warmup 5 --no-cpu --no-also --overlap-write-back
 b k20_ft16 --steps 20 --warmup 5 --no-cpu --no-also --first-train 16
 b k20_t8 --steps 20 --warmup 5 --no-cpu --no-also --train 8 --first-train 2
 b k2048 --steps 2048 --warmup 5 --no-cpu --no-also
-b k2048_nooverlap --steps 2048 --warmup 5 --no-cpu --no-also --no-overlap-write-back
+b k2048_overlap --steps 2048 --warmup 5 --no-cpu --no-also --overlap-write-back
+b k2048_eager --steps 2048 --warmup 5 --no-cpu --no-also --eager-trains
+b k2048_eager_overlap --steps 2048 --warmup 5 --no-cpu --no-also --eager-trains --overlap-write-back
 SGCN_PDL=0 b k2048_nopdl --steps 2048 --warmup 5 --no-cpu --no-also
-for m in "1 4" "0 4"; do set -- $m
+for m in "0 4" "1 4"; do set -- $m
   OVERLAP=$1 FIRST_TRAIN=$2 timeout 120 python tools/timeline.py trains 20 > "$OUT/timeline_trains_ov$1.txt" 2>&1; echo "timeline exit $?"; head -70 "$OUT/timeline_trains_ov$1.txt"
 done
 timeout 600 python -m pytest tests/test_fullsize_gpu.py -x -q > "$OUT/pytest_fullsize.log" 2>&1
