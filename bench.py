@@ -286,8 +286,12 @@ class Rig:
         if world > 1:
             from stochastic_gcn_b200.sharding import ShardedHotPathStep
             self.step = ShardedHotPathStep(self.g, self.feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"],
-                                           seed=args.seed + rank, rank=rank, world=world, transport=args.transport)
+                                           seed=args.seed + rank, rank=rank, world=world, transport=args.transport,
+                                           tables=args.tables)
             lo, hi = self.step.lo, self.step.hi
+            if args.tables == "sharded":
+                self.feats = None            # the step keeps this rank's rows only; drop the full matrix
+                torch.cuda.empty_cache()
         else:
             self.step = HotPathStep(self.g, self.feats, w["hidden"], w["batch"], w["degree"], mode=w["mode"],
                                     seed=args.seed)
@@ -390,11 +394,14 @@ def run_ours(args, w):
     timed, warm = batches[W:W + K], batches[W + K:]
     s_edges, f_edges = edge_counts(g, timed, w["degree"], w["mode"] != "ns")
 
+    sharded_tables = world > 1 and args.tables == "sharded"     # only the trains schedule runs on sharded tables
     # warm-up: the first pass is eager (sizes buffers, counts launches), then one-pass graph replays
-    step.capture(batches[0])
-    launches_per_step = step.launches_per_step
-    for b in batches[1:W]:
-        step.replay(b)
+    launches_per_step = 0
+    if not sharded_tables:
+        step.capture(batches[0])
+        launches_per_step = step.launches_per_step
+        for b in batches[1:W]:
+            step.replay(b)
     torch.cuda.synchronize(dev)
 
     clocks = ClockSampler(local)
@@ -405,12 +412,13 @@ def run_ours(args, w):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for b in timed:
-        step.replay(b)
+    if not sharded_tables:
+        for b in timed:
+            step.replay(b)
     ev1.record()
     barrier()
     ms_serial = ev0.elapsed_time(ev1)
-    sizes_last = step.sizes()
+    sizes_last = step.sizes() if not sharded_tables else None
 
     # ---- (2) timed region of record: exactly K passes ----
     nccl_multi = world > 1 and args.transport == "nccl"      # collective runs eagerly between one-pass graphs
@@ -499,8 +507,11 @@ def run_ours(args, w):
         [ms, ms_e2e, ms_serial, float(s_edges), float(f_edges)])
     alg = step.algorithmic_bytes(sizes_last)
     detail = {"nodes": g.n, "stored_edges": g.nnz, "last_step_sizes": sizes_last,
-              "parallelism": ("row-range shards x%d, history replicas synced by %s write-back exchange"
-                              % (world, args.transport)) if world > 1 else "single GPU"}
+              "parallelism": ("single GPU" if world == 1 else
+                              "row-range shards x%d, history + feature tables SHARDED (remote rows read over NVLink), "
+                              "write-back rows exchanged by peer stores" % world if sharded_tables else
+                              "row-range shards x%d, history + feature replicas, write-back rows exchanged by %s"
+                              % (world, args.transport))}
     rig.close()
     del rig, step, g, batches
 
@@ -512,7 +523,8 @@ def run_ours(args, w):
             k2 = min(K, 64)
             r2 = Rig(args, name, w2, world, rank, dev, W + k2 + min(k2, args.graph_passes))
             t2, wm2 = r2.batches[W:W + k2], r2.batches[W + k2:]
-            r2.step.capture(r2.batches[0])
+            if not sharded_tables:
+                r2.step.capture(r2.batches[0])
             se, fe = edge_counts(r2.g, t2, w2["degree"], w2["mode"] != "ns")
             if nccl_multi:
                 barrier(); ev0.record()
@@ -639,6 +651,9 @@ def main():
                     help="schedule of the timed region: trains (default; csrc/step.cu:sgcn_step_run_trains as CUDA "
                          "graphs), native (round-1 C++ driver, plain stream launches), graph (round-1 multi-step "
                          "torch-captured graphs)")
+    ap.add_argument("--tables", default="replicated", choices=["replicated", "sharded"],
+                    help="multi-GPU: history + feature tables replicated on every GPU (default) or row-sharded with "
+                         "remote rows read over NVLink (SURVEY 8e (1)); sharded needs the trains driver")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU write-back exchange: NVLink peer stores (default) or NCCL all-gather")
     args = ap.parse_args()

@@ -417,6 +417,25 @@ int sgcn_wb_wait_apply_ring(float* hist, int64_t ld_h, int32_t D, const void* re
                             int32_t world, int32_t n_bound, int32_t* owner, const int32_t* flags, int32_t ring,
                             int64_t ring_stride, int32_t* apply_epoch, int32_t* apply_counter /*scratch = 0*/,
                             int32_t* timeout_flag, int32_t* done_counter, void* stream);
+/* Row-sharded tables ("boundary fetch").  Instead of replicating the history table and the PP
+ * feature matrix on every GPU, rank r keeps rows [r * rows_per_shard, (r + 1) * rows_per_shard) and maps every
+ * other rank's shard over NVLink (cudaIpc); the kernels that read history rows (full-neighbour mean, CV / CVD
+ * sampled aggregate) or gather feature rows then address row i at bases[i / rows_per_shard] + (i %
+ * rows_per_shard) * ld -- the rows a batch's receptive field needs from the other side of a cut cross NVLink as
+ * plain loads, exactly once each, and nothing else moves.  sgcn_shard_set arms that addressing for the calling
+ * host thread (which = 0 history, 1 features; bases = HOST array of `world` device pointers; world <= 1 turns it
+ * off); the `hist` / `src` pointer passed to those entry points is then this rank's own shard. */
+int sgcn_shard_set(int32_t which, int32_t world, int32_t rows_per_shard, const void* const* bases /*HOST*/);
+/* write-back with a sharded history: every rank still publishes its rows to every rank (sgcn_wb_push_ring), but
+ * applies only the rows it OWNS, to its shard.  Two handshakes replace the stream order a single table gave:
+ * nobody overwrites a row before every rank has finished the reads of the pass (reads flags), nobody reads a
+ * shard before its owner has applied the epoch (applied flags; the call returns on the device only then). */
+int sgcn_wb_wait_apply_sharded(float* hist_shard, int64_t ld_h, int32_t D, const void* recv_base, int64_t slot_bytes,
+                               int32_t world, int32_t rank, int32_t rows_per_shard, int32_t n_bound, int32_t* owner,
+                               const int32_t* flags, int32_t ring, int64_t ring_stride, int32_t* apply_epoch,
+                               int32_t* apply_stash, const int32_t* reads_flags, void* const* reads_peer_flags,
+                               const int32_t* applied_flags, void* const* applied_peer_flags, int32_t* shard_counter,
+                               int32_t* timeout_flag, int32_t* done_counter, void* stream);
 /* merge `world` payloads (slot r at gathered + r*slot_bytes) into hist; owner is an int32[N]
  * scratch table that must hold -1 everywhere on entry and does again on exit */
 int sgcn_wb_apply(float* hist, int64_t ld_h, int32_t D, const void* gathered, int64_t slot_bytes,
@@ -501,6 +520,15 @@ typedef struct {
     int32_t ring; int32_t pad0; int64_t ring_stride;
     int32_t* push_epoch; int32_t* apply_epoch; int32_t* apply_stash; const int32_t* ring_flags;
     void* ring_dst[16]; void* ring_peer_flags[16]; void* ring_recv;
+    /* row-sharded history and features (sgcn_step_run_trains, ring form only; shard_rows = 0: replicated):
+     * `history` / `features` above are then THIS rank's shards (rows [rank * shard_rows, ...)), hist_shards /
+     * feat_shards every rank's shard as mapped into this process (sgcn_shard_set), and the two flag arrays
+     * carry the "reads done" / "applied" handshakes of sgcn_wb_wait_apply_sharded */
+    int32_t shard_rows; int32_t pad1;
+    const void* hist_shards[16]; const void* feat_shards[16];
+    const int32_t* reads_flags; void* reads_peer_flags[16];
+    const int32_t* applied_flags; void* applied_peer_flags[16];
+    int32_t* shard_counter;
 } sgcn_step_desc;
 int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_desc* desc /*HOST*/);
 void sgcn_step_destroy(sgcn_step* st);

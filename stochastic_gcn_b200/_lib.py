@@ -112,6 +112,9 @@ SIGNATURES = {
                                    C.POINTER(_vp), _i32, _vp, _vp]),
     "sgcn_wb_wait_apply": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgcn_wb_apply": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "sgcn_shard_set": (_i32, [_i32, _i32, _i32, C.POINTER(_vp)]),
+    "sgcn_wb_wait_apply_sharded": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i64,
+                                          _vp, _vp, _vp, C.POINTER(_vp), _vp, C.POINTER(_vp), _vp, _vp, _vp, _vp]),
     "sgcn_wb_push_ring": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), _i32, _i32, _i64, C.POINTER(_vp),
                                  _i32, _vp, _vp, _vp]),
     "sgcn_wb_wait_apply_ring": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
@@ -136,7 +139,10 @@ class StepDesc(C.Structure):
                 ("x0_alt", _vp * 2), ("dx_alt", _vp), ("train", _i32), ("overlap_write_back", _i32),
                 ("ring", _i32), ("pad0", _i32), ("ring_stride", _i64), ("push_epoch", _vp), ("apply_epoch", _vp),
                 ("apply_stash", _vp), ("ring_flags", _vp), ("ring_dst", _vp * 16), ("ring_peer_flags", _vp * 16),
-                ("ring_recv", _vp)]
+                ("ring_recv", _vp),
+                ("shard_rows", _i32), ("pad1", _i32), ("hist_shards", _vp * 16), ("feat_shards", _vp * 16),
+                ("reads_flags", _vp), ("reads_peer_flags", _vp * 16), ("applied_flags", _vp),
+                ("applied_peer_flags", _vp * 16), ("shard_counter", _vp)]
 
 
 _lib = None

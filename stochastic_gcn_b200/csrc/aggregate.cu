@@ -113,6 +113,7 @@ struct SampledArgs {
     // optional: the multi-GPU write-back push rides on this launch as the blocks with blockIdx.y == 1
     // (both only need the gathered input rows; one launch instead of two on the step's side branch)
     int has_push; WbPushArgs push;
+    ShardMap hmap;   // row-sharded history (CV / CVD): hist rows are addressed by GLOBAL node id through it
 };
 
 template <typename V, int LPR, int VPL, int MODE>
@@ -155,7 +156,7 @@ sampled_rows_kernel(const SampledArgs a) {
 #pragma unroll
                 for (int k = 0; k < VPL; ++k) {
                     if (!ok[k]) continue;
-                    const V hv = T::ld_stream(a.hist + t * a.ld_h + off[k]);
+                    const V hv = T::ld_stream(shard_row(a.hmap, a.hist, t, a.ld_h) + off[k]);
                     if (MODE == MODE_CV) {
                         const V xv = T::ld(a.x + (int64_t)c * a.ld_x + off[k]);
                         T::fma(acc[k], w, T::sub(xv, hv));
@@ -373,6 +374,7 @@ struct FullArgs {
     // from ov_rows instead -- the previous pass's write-back, applied on the fly
     const int32_t* ov_ids; const int32_t* ov_n_dev; int ov_bound, ov_bits;
     const float* ov_rows; int64_t ld_ov;
+    ShardMap hmap;   // row-sharded history (world <= 1: hist is one local table)
 };
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -524,6 +526,9 @@ full_mean_kernel(const FullArgs a) {
             const float w = l_w[j];
             const int r = l_r[j];
             int64_t off = (int64_t)col * a.ld_h;
+            if (a.hmap.world > 1)          // a remote shard: the offset still is relative to a.hist
+                off = (int64_t)(((intptr_t)shard_row(a.hmap, a.hist, col, a.ld_h) - (intptr_t)a.hist) /
+                                (intptr_t)sizeof(float));
             if (ov_n > 0 && r >= 0) {
                 unsigned h = ov_hash(col, a.ov_bits);
                 for (;;) {
@@ -828,6 +833,10 @@ template <int MODE>
 static int launch_sampled(SampledArgs a, int D, bool vec_ok, cudaStream_t st) {
     if (a.n_out <= 0 || D <= 0) return SGCN_OK;
     const Shape sh = pick_shape(D, vec_ok);
+    if ((MODE == MODE_CV || MODE == MODE_CVD) && t_hist_map.world > 1) {
+        SGCN_REQUIRE(D <= sh.tile, "sharded history: the aggregated width must fit one column tile");
+        a.hmap = t_hist_map;
+    }
     for (int c0 = 0; c0 < D; c0 += sh.tile) {
         SampledArgs t = a;
         t.trace = g_trace;
@@ -1142,10 +1151,12 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
         ov_bits = 4;
         while ((1 << ov_bits) < 2 * ov_bound) ++ov_bits;
     }
-    if (g_full_variant == 1 && vec_ok && D <= 128 && n_out <= kFullStageRows && !ov_ids) {
+    const bool sharded = t_hist_map.world > 1;
+    if (sharded) SGCN_REQUIRE(D <= sh.tile, "sharded history: the aggregated width must fit one column tile");
+    if (g_full_variant == 1 && vec_ok && D <= 128 && n_out <= kFullStageRows && !ov_ids && !sharded) {
         FullTmaCfg cfg = g_tma_cfg;
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0, ld_y0, y1, ld_y1,
-                   nullptr, n_out, g_trace, square, nullptr, nullptr, 0, 0, nullptr, 0};
+                   nullptr, n_out, g_trace, square, nullptr, nullptr, 0, 0, nullptr, 0, ShardMap{}};
         const size_t fixed = 12 * (size_t)kTmaMeta + sizeof(int32_t) * (2 * (size_t)n_out + 2) + 128;
         const size_t stage = (size_t)cfg.rows * D * 4;
         while (cfg.depth > 1 && fixed + (size_t)cfg.warps * cfg.depth * (stage + 8) > 226 * 1024) --cfg.depth;
@@ -1166,7 +1177,8 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
                    std::min(sh.tile, D - c0), y0 + c0, ld_y0, y1 ? y1 + c0 : nullptr, ld_y1,
                    D <= sh.tile ? work_counter : nullptr,    // one launch per counter reset
                    std::min(n_out, kFullStageRows), g_trace, square,
-                   ov_ids, ov_n_dev, ov_ids ? ov_bound : 0, ov_bits, ov_rows ? ov_rows + c0 : nullptr, ld_ov};
+                   ov_ids, ov_n_dev, ov_ids ? ov_bound : 0, ov_bits, ov_rows ? ov_rows + c0 : nullptr, ld_ov,
+                   sharded ? t_hist_map : ShardMap{}};
         const size_t dyn = sizeof(int32_t) * (2 * (size_t)a.stage_rows + 2) +
                            (ov_ids ? sizeof(int32_t) * (size_t)ov_bound + sizeof(unsigned short) * ((size_t)1 << ov_bits) : 0);
         // one resident wave: every CTA the SMs can hold at once, spans cut accordingly

@@ -108,6 +108,22 @@ inline void match_step_carveout(K kernel, bool* done) {
 
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Row-sharded tables (multi-GPU): row i of a [N, ld] table lives on rank i / rows_per_shard at
+// base[i / rows_per_shard] + (i % rows_per_shard) * ld, where base[r] is rank r's shard mapped into this
+// process (cudaIpc over NVLink; base[own rank] is local HBM).  world <= 1: the table is one local array.
+struct ShardMap {
+    int world, rows;
+    const float* base[16];
+};
+// per host thread: the maps the next launches of the history-reading / feature-gathering kernels use
+// (sgcn_shard_set); world = 0 = off
+extern thread_local ShardMap t_hist_map, t_feat_map;
+__device__ __forceinline__ const float* shard_row(const ShardMap& m, const float* table, int64_t row, int64_t ld) {
+    if (m.world <= 1) return table + row * ld;
+    const int o = (int)row / m.rows;
+    return m.base[o] + (int64_t)((int)row - o * m.rows) * ld;
+}
+
 // ---- device-side helpers -------------------------------------------------------------------
 
 // 128-bit read-only global load that does not allocate in L1 (rows are read once per kernel).

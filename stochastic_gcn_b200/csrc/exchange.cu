@@ -63,7 +63,8 @@ wb_claim_kernel(const char* g_even, const char* g_odd,
                 const int32_t* __restrict__ epoch, int64_t slot_bytes, int world, int n_bound,
                 int32_t* __restrict__ owner, const int32_t* flags, int32_t* timeout_flag,
                 long long max_spins, int32_t* done_counter, unsigned long long* trace,
-                int ring, int64_t ring_stride, int32_t* cur_stash) {
+                int ring, int64_t ring_stride, int32_t* cur_stash,
+                int shard_rank, int shard_rows, PeerPtrs reads_peers, const int32_t* reads_flags) {
     TraceScope ts(trace, TR_WB_CLAIM);
     // ring protocol: `epoch` counts the epochs APPLIED so far (the pushes run ahead on a counter of their own);
     // this launch applies epoch *epoch + 1.  Under programmatic launches the only ordering between the kernels
@@ -102,6 +103,29 @@ wb_claim_kernel(const char* g_even, const char* g_odd,
         }
         __syncthreads();
     }
+    if (shard_rows > 0) {
+        // Sharded history (plain launch: everything stream-ordered before it has finished, i.e. this rank
+        // has read all it needs of the table as of the previous epoch): tell every rank, and do not touch
+        // a row before every rank has said the same -- their full-neighbour means read MY shard over NVLink.
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < world) {
+            volatile int32_t* f = (volatile int32_t*)reads_peers.p[threadIdx.x];
+            f[shard_rank] = cur;
+            __threadfence_system();
+        }
+        if (threadIdx.x < world) {
+            volatile const int32_t* f = (volatile const int32_t*)reads_flags;
+            long long spins = 0;
+            while (f[threadIdx.x] < cur) {
+                if (++spins > max_spins) {
+                    atomicExch(timeout_flag, 1 + threadIdx.x);
+                    break;
+                }
+                __nanosleep(100);
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     const int r = blockIdx.y;
     const char* gathered = ring > 0 ? g_even + (int64_t)(cur % ring) * ring_stride : ((cur & 1) ? g_odd : g_even);
     const char* slot = gathered + (int64_t)r * slot_bytes;
@@ -109,8 +133,14 @@ wb_claim_kernel(const char* g_even, const char* g_odd,
     // them through L2 (ld.global.cg / volatile), never through a possibly stale L1 / read-only path
     const int n = min(__ldcg((const int32_t*)slot), n_bound);
     const int32_t* ids = (const int32_t*)(slot + wb_ids_offset());
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
-        atomicMax(owner + __ldcg(ids + j), r * n_bound + j);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        int node = __ldcg(ids + j);
+        if (shard_rows > 0) {                       // only the rows this rank owns, by local row index
+            if (node / shard_rows != shard_rank) continue;
+            node -= shard_rank * shard_rows;
+        }
+        atomicMax(owner + node, r * n_bound + j);
+    }
     // (PDL) completion of this grid must imply completion of the predecessor (the copy kernel orders
     // its history writes behind THIS grid only): wait for it here, after the independent work
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -126,7 +156,8 @@ wb_copy_kernel(const char* g_even, const char* g_odd,
                const int32_t* __restrict__ epoch, int64_t slot_bytes, int world, int n_bound,
                int32_t* __restrict__ owner, float* __restrict__ hist, int64_t ld_h, int D,
                unsigned long long* trace, int ring, int64_t ring_stride, int32_t* epoch_out,
-               const int32_t* cur_stash) {
+               const int32_t* cur_stash, int shard_rank, int shard_rows, PeerPtrs applied_peers,
+               int32_t* apply_counter) {
     TraceScope ts(trace, TR_WB_COPY);
     // ring protocol: the epoch being applied was stashed by the claim kernel; advance the applied-epoch
     // counter for the NEXT claim before any dependent can launch (see wb_claim_kernel)
@@ -154,7 +185,11 @@ wb_copy_kernel(const char* g_even, const char* g_odd,
         int node[R];
         bool mine[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) node[q] = j0 + q < n ? __ldcg(ids + j0 + q) : -1;
+        for (int q = 0; q < R; ++q) {
+            node[q] = j0 + q < n ? __ldcg(ids + j0 + q) : -1;
+            if (shard_rows > 0 && node[q] >= 0)      // sharded history: local row index, or not mine at all
+                node[q] = node[q] / shard_rows == shard_rank ? node[q] - shard_rank * shard_rows : -1;
+        }
 #pragma unroll
         for (int q = 0; q < R; ++q) mine[q] = node[q] >= 0 && owner[node[q]] == r * n_bound + j0 + q;   // warp-uniform
         for (int c = lane * W; c < D; c += 32 * W) {
@@ -176,6 +211,19 @@ wb_copy_kernel(const char* g_even, const char* g_odd,
 #pragma unroll
         for (int q = 0; q < R; ++q)
             if (mine[q] && lane == 0) owner[node[q]] = -1;        // losers only ever compare for equality
+    }
+    if (shard_rows > 0) {      // sharded history: the last block to finish tells every rank "my shard holds epoch cur"
+        __shared__ int s_last;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(apply_counter, 1) == (int)(gridDim.x * gridDim.y) - 1;
+        __syncthreads();
+        if (s_last && threadIdx.x < world) {
+            if (threadIdx.x == 0) *apply_counter = 0;
+            volatile int32_t* f = (volatile int32_t*)applied_peers.p[threadIdx.x];
+            f[shard_rank] = cur;
+            __threadfence_system();
+        }
     }
 }
 
@@ -268,12 +316,17 @@ static int launch_apply(float* hist, int64_t ld_h, int32_t D, const void* g_even
                         const int32_t* epoch, int64_t slot_bytes, int32_t world, int32_t n_bound,
                         int32_t* owner, cudaStream_t st, const int32_t* flags = nullptr,
                         int32_t* timeout_flag = nullptr, int32_t* done_counter = nullptr, int ring = 0,
-                        int64_t ring_stride = 0, int32_t* epoch_out = nullptr, int32_t* apply_counter = nullptr) {
+                        int64_t ring_stride = 0, int32_t* epoch_out = nullptr, int32_t* apply_counter = nullptr,
+                        int shard_rank = 0, int shard_rows = 0, const PeerPtrs* reads_peers = nullptr,
+                        const int32_t* reads_flags = nullptr, const PeerPtrs* applied_peers = nullptr,
+                        int32_t* shard_counter = nullptr) {
+    const PeerPtrs none{};
     dim3 g1(std::min(div_up(std::max(n_bound, 1), 256), 64), world);
     // ~2 s at 100 ns per spin: a peer that never arrives raises the flag instead of hanging the GPU
     SGCN_CUDA(launch_pdl(wb_claim_kernel, g1, dim3(256), 0, st, (const char*)g_even, (const char*)g_odd, epoch,
                          slot_bytes, world, n_bound, owner, flags, timeout_flag, 20000000LL, done_counter, g_trace,
-                         ring, ring_stride, apply_counter));
+                         ring, ring_stride, apply_counter, shard_rank, shard_rows, reads_peers ? *reads_peers : none,
+                         reads_flags));
     SGCN_LAUNCHED();
     // few CTAs: with PDL they sit resident beside the full-neighbour mean, and the next batch's sampler
     // CTA still has to find an SM with registers to spare
@@ -283,11 +336,13 @@ static int launch_apply(float* hist, int64_t ld_h, int32_t D, const void* g_even
     if (vec)
         SGCN_CUDA(launch_pdl(wb_copy_kernel<true>, g2, dim3(256), 0, st, (const char*)g_even, (const char*)g_odd,
                              epoch, slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace, ring, ring_stride,
-                             epoch_out, apply_counter));
+                             epoch_out, apply_counter, shard_rank, shard_rows, applied_peers ? *applied_peers : none,
+                             shard_counter));
     else
         SGCN_CUDA(launch_pdl(wb_copy_kernel<false>, g2, dim3(256), 0, st, (const char*)g_even, (const char*)g_odd,
                              epoch, slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace, ring, ring_stride,
-                             epoch_out, apply_counter));
+                             epoch_out, apply_counter, shard_rank, shard_rows, applied_peers ? *applied_peers : none,
+                             shard_counter));
     SGCN_LAUNCHED();
     return SGCN_OK;
 }
@@ -337,6 +392,36 @@ int sgcn_wb_wait_apply_ring(float* hist, int64_t ld_h, int32_t D, const void* re
     return launch_apply(hist, ld_h, D, recv_base, recv_base, apply_epoch, slot_bytes, world, n_bound, owner,
                         (cudaStream_t)stream, flags, timeout_flag, done_counter, ring, ring_stride, apply_epoch,
                         apply_counter);
+}
+
+int sgcn_wb_wait_apply_sharded(float* hist_shard, int64_t ld_h, int32_t D, const void* recv_base, int64_t slot_bytes,
+                               int32_t world, int32_t rank, int32_t rows_per_shard, int32_t n_bound, int32_t* owner,
+                               const int32_t* flags, int32_t ring, int64_t ring_stride, int32_t* apply_epoch,
+                               int32_t* apply_stash, const int32_t* reads_flags, void* const* reads_peer_flags,
+                               const int32_t* applied_flags, void* const* applied_peer_flags, int32_t* shard_counter,
+                               int32_t* timeout_flag, int32_t* done_counter, void* stream) {
+    SGCN_REQUIRE(hist_shard && recv_base && owner && flags && apply_epoch && apply_stash && reads_flags &&
+                     reads_peer_flags && applied_flags && applied_peer_flags && shard_counter && timeout_flag,
+                 "wb_wait_apply_sharded: null pointer");
+    SGCN_REQUIRE(world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world && rows_per_shard > 0 && n_bound > 0 &&
+                     D > 0 && ld_h >= D, "wb_wait_apply_sharded: bad size");
+    SGCN_REQUIRE(slot_bytes >= wb_payload_bytes(n_bound, D), "wb_wait_apply_sharded: slot smaller than a payload");
+    SGCN_REQUIRE(ring >= 2 && ring <= 64 && ring_stride >= (int64_t)world * slot_bytes && ring_stride % 16 == 0,
+                 "wb_wait_apply_sharded: bad ring");
+    PeerPtrs pr{}, pa{};
+    int rc = fill_ptrs(pr, reads_peer_flags, world, "wb_wait_apply_sharded");
+    if (rc == SGCN_OK) rc = fill_ptrs(pa, applied_peer_flags, world, "wb_wait_apply_sharded");
+    if (rc != SGCN_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    PdlOff plain;      // the handshakes below rely on "everything stream-ordered before this launch has finished"
+    rc = launch_apply(hist_shard, ld_h, D, recv_base, recv_base, apply_epoch, slot_bytes, world, n_bound, owner, st,
+                      flags, timeout_flag, done_counter, ring, ring_stride, apply_epoch, apply_stash, rank,
+                      rows_per_shard, &pr, reads_flags, &pa, shard_counter);
+    if (rc != SGCN_OK) return rc;
+    // nobody reads a shard before its owner has applied this epoch: wait for every rank's "applied" flag
+    wb_wait_kernel<<<1, 32, 0, st>>>(applied_flags, world, apply_epoch, timeout_flag, 20000000LL);
+    SGCN_LAUNCHED();
+    return SGCN_OK;
 }
 
 // ---- peer memory plumbing (cudaIpc): plain cudaMalloc'd buffers that other ranks can map -----

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(kRowThreads)
 move_rows_vec4_kernel(const float* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ idx,
                       int n_host, const int32_t* __restrict__ n_dev, int n_total, int c4,
                       float* __restrict__ dst, int64_t ld_dst, unsigned long long* trace,
-                      int32_t* done_counter) {
+                      int32_t* done_counter, const ShardMap smap) {
     TraceScope ts(trace, MODE == 0 ? TR_GATHER : (MODE == 1 ? TR_UPDATE : TR_PAD));
     // (PDL) a dependent launched with programmatic stream serialization may start its preamble now;
     // it still waits for this whole grid (griddepcontrol.wait) before touching what is written here
@@ -56,7 +56,7 @@ move_rows_vec4_kernel(const float* __restrict__ src, int64_t ld_src, const int32
                 if (MODE == 1) rd = idx[r];
                 off_dst[u] = rd * ld_dst + c;
                 if (MODE == 2 && r >= n) v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                else v[u] = ldg_stream4(src + rs * ld_src + c);
+                else v[u] = ldg_stream4((MODE == 0 ? shard_row(smap, src, rs, ld_src) : src + rs * ld_src) + c);
             }
         }
 #pragma unroll
@@ -109,13 +109,14 @@ static int launch_move_rows(const float* src, int64_t ld_src, const int32_t* idx
         SGCN_MATCH_CARVEOUT(move_rows_vec4_kernel<MODE>);
         if (MODE == 1) {      // history write-back: second link of the step's main chain (PDL when enabled)
             SGCN_CUDA(launch_pdl(move_rows_vec4_kernel<MODE>, dim3(blocks), dim3(kRowThreads), 0, st, src, ld_src,
-                                 idx, n, n_dev, n_total, c4, dst, ld_dst, g_trace, done_counter));
+                                 idx, n, n_dev, n_total, c4, dst, ld_dst, g_trace, done_counter, ShardMap{}));
         } else {
             move_rows_vec4_kernel<MODE><<<blocks, kRowThreads, 0, st>>>(src, ld_src, idx, n, n_dev,
                                                                        n_total, c4, dst, ld_dst, g_trace,
-                                                                       done_counter);
+                                                                       done_counter, MODE == 0 ? t_feat_map : ShardMap{});
         }
     } else {
+        SGCN_REQUIRE(!(MODE == 0 && t_feat_map.world > 1), "sharded features need 16-byte aligned rows");
         const int64_t total = (int64_t)rows * C;
         int blocks = (int)std::min<int64_t>((total + kRowThreads - 1) / kRowThreads, max_blocks);
         move_rows_scalar_kernel<MODE><<<blocks, kRowThreads, 0, st>>>(src, ld_src, idx, n, n_dev,
@@ -134,11 +135,12 @@ static int launch_move_rows(const float* src, int64_t ld_src, const int32_t* idx
 struct PadJob { const float* src; int64_t ld_src; const int32_t* idx; int n; const int32_t* n_dev; int n_total;
                 int C; float* dst; int64_t ld_dst; int pad; };
 constexpr int kPadJobs = 3;
-struct PadJobs { PadJob j[kPadJobs]; };
+struct PadJobs { PadJob j[kPadJobs]; ShardMap smap; /* of job 0's gather source (world <= 1: off) */ };
 
 __global__ void __launch_bounds__(kRowThreads)
 pad_jobs_kernel(const PadJobs p, unsigned long long* trace) {
     const PadJob& a = p.j[blockIdx.y];
+    const bool sharded_src = blockIdx.y == 0 && p.smap.world > 1;
     TraceScope ts(trace, a.idx ? TR_GATHER : TR_PAD);
     asm volatile("griddepcontrol.launch_dependents;");          // (PDL) see move_rows_vec4_kernel
     if (!a.dst || a.n_total <= 0 || a.C <= 0) return;
@@ -164,7 +166,7 @@ pad_jobs_kernel(const PadJobs p, unsigned long long* trace) {
                     off_dst[u] = (int64_t)r * a.ld_dst + c;
                     if (r < n) {
                         const int64_t rs = a.idx ? (int64_t)a.idx[r] : (int64_t)r;
-                        v[u] = ldg_stream4(a.src + rs * a.ld_src + c);
+                        v[u] = ldg_stream4((sharded_src ? shard_row(p.smap, a.src, rs, a.ld_src) : a.src + rs * a.ld_src) + c);
                     } else {
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
@@ -297,6 +299,10 @@ int sgcn_gather_pad_pair(const float* src, int64_t ld_src, const int32_t* idx, i
     p.j[0] = PadJob{src, ld_src, idx, n, n_dev, n, C, n > 0 && C > 0 ? dst : nullptr, ld_dst, 0};
     p.j[1] = PadJob{src0, ld_src0, nullptr, n0, n0_dev, n_total0, D0, dst0, ld_dst0, 1};
     p.j[2] = PadJob{src1, ld_src1, nullptr, n1, n1_dev, n_total1, D1, dst1, ld_dst1, 1};
+    if (t_feat_map.world > 1) {
+        SGCN_REQUIRE(vec4_ok(src, ld_src, dst, ld_dst, C), "sharded features need 16-byte aligned rows");
+        p.smap = t_feat_map;
+    }
     return launch_pad_jobs(p, 3, (cudaStream_t)stream);
 }
 

@@ -522,6 +522,26 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
     const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0, multi = d.world > 1 && cv;
     const bool overlap = cv && !multi && d.overlap_write_back != 0 && d.x0_rows <= 4096;
     const bool ring = multi && d.ring > 0;
+    const bool sharded = d.shard_rows > 0 && d.world > 1;
+    if (sharded) SGCN_REQUIRE(!cv || ring, "step_run_trains: sharded tables need the ring form of the exchange");
+    // sharded tables: history rows / feature rows of other ranks are read over NVLink through the shard maps
+    struct ShardScope {
+        bool on;
+        ShardScope(bool enable, const sgcn_step_desc& d) : on(enable) {
+            if (on) {
+                sgcn_shard_set(0, d.world, d.shard_rows, d.hist_shards);
+                sgcn_shard_set(1, d.world, d.shard_rows, d.feat_shards);
+            }
+        }
+        ~ShardScope() {
+            if (on) {
+                sgcn_shard_set(0, 0, 0, nullptr);
+                sgcn_shard_set(1, 0, 0, nullptr);
+            }
+        }
+    } shard_scope(sharded, d);
+    // ... and the handshakes of the sharded write-back rely on plain stream order: no programmatic launches
+    PdlOff sharded_plain(sharded);
     const int width = H * (concat ? 2 : 1);
     cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp, pre = st->pre,
                  copy = st->copy;
@@ -669,6 +689,12 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
             SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_fwd[k % R], 0));
             if (!cv) {
                 STEP_TRY(sgcn_sampler_mark_consumed(smp, chain));
+            } else if (ring && sharded) {
+                STEP_TRY(sgcn_wb_wait_apply_sharded(d.history, d.ld_hist, H, d.ring_recv, d.slot_bytes, d.world, d.rank,
+                                                    d.shard_rows, d.wb_bound, d.owner, d.ring_flags, d.ring,
+                                                    d.ring_stride, d.apply_epoch, d.apply_stash, d.reads_flags,
+                                                    d.reads_peer_flags, d.applied_flags, d.applied_peer_flags,
+                                                    d.shard_counter, d.timeout_flag, st->pipe + 1, chain));
             } else if (ring) {
                 STEP_TRY(sgcn_wb_wait_apply_ring(d.history, d.ld_hist, H, d.ring_recv, d.slot_bytes, d.world, d.wb_bound,
                                                  d.owner, d.ring_flags, d.ring, d.ring_stride, d.apply_epoch,

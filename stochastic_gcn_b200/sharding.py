@@ -96,6 +96,7 @@ class PeerExchange:
         self.lib, self.rank, self.world, self.slot = lib, rank, world, int(slot_bytes)
         self.off_ctl, self.off_even = 256, 512
         self.off_ring_flags = 128                   # ring-form flags: ints 32 .. 47 of the flag block
+        self.off_reads, self.off_applied = 320, 384  # sharded tables: "reads done" / "applied" flags (control block)
         self.ring, self.ring_stride = RING, world * self.slot
         self.off_odd = self.off_even + self.ring_stride
         total = self.off_even + self.ring * self.ring_stride
@@ -145,18 +146,99 @@ class PeerExchange:
             self.base = 0
 
 
+class IpcShards:
+    """One row-sharded [N, width] fp32 table: this rank's rows [rank * rows, ...) in a cudaIpc-exported
+    allocation, every other rank's shard mapped into this process over NVLink."""
+
+    def __init__(self, rank, world, rows, width, device, init=None):
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.lib, self.rank, self.world, self.rows, self.width = lib, rank, world, int(rows), int(width)
+        nbytes = self.rows * self.width * 4
+        base = C.c_void_p()
+        check(lib.sgcn_ipc_alloc(C.byref(base), nbytes, 1))
+        self.base = base.value
+        self.local = torch.as_tensor(_DevBytes(self.base, nbytes), device=device).view(torch.float32).view(
+            self.rows, self.width)
+        if init is not None:
+            self.local[:init.shape[0]].copy_(init)
+        torch.cuda.synchronize(device)
+        handle = (C.c_ubyte * 64)()
+        check(lib.sgcn_ipc_export(C.c_void_p(self.base), handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle))
+        self.peer_base = []
+        for r in range(world):
+            if r == rank:
+                self.peer_base.append(self.base)
+            else:
+                p = C.c_void_p()
+                check(lib.sgcn_ipc_open((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p)))
+                self.peer_base.append(p.value)
+        dist.barrier()
+
+    def gather_full(self, n):
+        """the whole table [n, width] assembled on this rank (tests / checkpoints): peer shards read over NVLink"""
+        parts = []
+        for r in range(self.world):
+            nbytes = self.rows * self.width * 4
+            t = torch.as_tensor(_DevBytes(self.peer_base[r], nbytes), device=self.local.device).view(torch.float32)
+            parts.append(t.view(self.rows, self.width))
+        return torch.cat(parts)[:n].clone()
+
+    def close(self):
+        for r, b in enumerate(self.peer_base):
+            if r != self.rank and b:
+                self.lib.sgcn_ipc_close(C.c_void_p(b))
+        if self.base:
+            self.local = None
+            self.lib.sgcn_ipc_free(C.c_void_p(self.base))
+            self.base = 0
+
+
+def shard_rows(n, world):
+    """rows per shard of the sharded-table layout: ceil(n / world) rounded up to 8 (row i lives on rank
+    i // rows; the last shard may be short)"""
+    return ((n + world - 1) // world + 7) // 8 * 8
+
+
 class ShardedHotPathStep(HotPathStep):
-    """HotPathStep over one row-range shard, with the cross-GPU history write-back exchange."""
+    """HotPathStep over one row-range shard, with the cross-GPU history write-back exchange.
+
+    tables="replicated" (default): every rank holds the whole history table and PP feature matrix; only each
+    pass's write-back rows cross NVLink.  tables="sharded" ("boundary fetch"): rank r holds rows
+    [r * S, (r + 1) * S) of both tables (S = shard_rows(N, world)) and reads every other row its batches touch
+    straight out of the owner's HBM over NVLink -- memory per GPU falls with the number of GPUs, each pass moves
+    its (R-1)/R of distinct neighbour rows across the links.  Only the trains schedule (run_trains /
+    capture_trains / replay_trains) runs on sharded tables."""
 
     def __init__(self, graph, features, hidden, batch_size, degree, mode="cv", normalization="graphsage",
-                 seed=1, rank=0, world=1, transport="peer"):
+                 seed=1, rank=0, world=1, transport="peer", tables="replicated"):
         if transport not in ("nccl", "peer"):
             raise ValueError("transport must be 'nccl' or 'peer'")
-        self.rank, self.world, self.transport = int(rank), int(world), transport
-        self.lo, self.hi = row_range(graph.n, rank, world)
+        if tables not in ("replicated", "sharded"):
+            raise ValueError("tables must be 'replicated' or 'sharded'")
+        if tables == "sharded" and (transport != "peer" or world < 2):
+            raise ValueError("sharded tables need the peer transport and at least two ranks")
+        self.rank, self.world, self.transport, self.tables = int(rank), int(world), transport, tables
+        self._hist_shards = self._feat_shards = None
+        history = None
+        if tables == "sharded":
+            S = self.shard_rows = shard_rows(graph.n, world)
+            self.lo, self.hi = min(graph.n, rank * S), min(graph.n, (rank + 1) * S)
+            dev = features.device
+            # `features` may be the whole [N, F] matrix (this rank keeps its rows) or already the local rows
+            mine = features[self.lo:self.hi] if features.shape[0] == graph.n else features
+            self._feat_shards = IpcShards(rank, world, S, features.shape[1], dev, init=mine)
+            features = self._feat_shards.local
+            if mode != "ns":
+                self._hist_shards = IpcShards(rank, world, S, hidden, dev)
+                history = self._hist_shards.local
+        else:
+            self.lo, self.hi = row_range(graph.n, rank, world)
         local = restrict_rows(graph, self.lo, self.hi)
         super().__init__(local, features, hidden, batch_size, degree, mode=mode, normalization=normalization,
-                         seed=seed)
+                         seed=seed, history=history)
         self._exchange = None
         if self.mode == "ns":
             return     # plain neighbour sampling keeps no history: shards are independent
@@ -223,16 +305,59 @@ class ShardedHotPathStep(HotPathStep):
             d.recv_even, d.recv_odd, d.flags = x.recv_even.value, x.recv_odd.value, x.flags.value
             d.epoch, d.timeout_flag, d.block_counter = x.epoch.value, x.timeout.value, x.block_counter.value
             d.owner = self.owner.data_ptr()
-            if os.environ.get("SGCN_WB_RING", "1") != "0":      # trains schedule: ring form, pushes one pass ahead
+            if os.environ.get("SGCN_WB_RING", "1") != "0" or self.tables == "sharded":   # trains schedule: ring form
                 d.ring, d.ring_stride = x.ring, x.ring_stride
                 d.push_epoch, d.apply_epoch, d.apply_stash = x.push_epoch.value, x.apply_epoch.value, x.apply_stash.value
                 d.ring_flags, d.ring_recv = x.base + x.off_ring_flags, x.base + x.off_even
                 for i in range(self.world):
                     d.ring_dst[i] = x.peer_base[i] + x.off_even + self.rank * x.slot
                     d.ring_peer_flags[i] = x.peer_base[i] + x.off_ring_flags
+                if self.tables == "sharded":
+                    d.reads_flags, d.applied_flags = x.base + x.off_reads, x.base + x.off_applied
+                    d.shard_counter = x.base + x.off_ctl + 24
+                    for i in range(self.world):
+                        d.reads_peer_flags[i] = x.peer_base[i] + x.off_reads
+                        d.applied_peer_flags[i] = x.peer_base[i] + x.off_applied
         elif self.mode != "ns" and self.world > 1:
             raise RuntimeError("the native step driver needs the peer transport for multi-GPU runs")
+        if self.tables == "sharded":
+            d.world, d.rank, d.shard_rows = self.world, self.rank, self.shard_rows
+            for i in range(self.world):
+                d.feat_shards[i] = self._feat_shards.peer_base[i]
+                d.hist_shards[i] = (self._hist_shards or self._feat_shards).peer_base[i]
         return d
+
+    def _sharded_only_trains(self, what):
+        if self.tables == "sharded":
+            raise RuntimeError("%s addresses the tables directly; on sharded tables use run_trains / capture_trains / "
+                               "replay_trains" % what)
+
+    def _pass(self):
+        self._sharded_only_trains("the one-pass drivers")
+        return super()._pass()
+
+    def _eager_step(self, slot, sample):
+        self._sharded_only_trains("the pipelined driver")
+        return super()._eager_step(slot, sample)
+
+    def run_native(self, *a, **k):
+        self._sharded_only_trains("run_native")
+        return super().run_native(*a, **k)
+
+    def run_ahead(self, *a, **k):
+        self._sharded_only_trains("run_ahead")
+        return super().run_ahead(*a, **k)
+
+    def time_dominant_kernel(self, batches):
+        if self.tables == "sharded":
+            return None
+        return super().time_dominant_kernel(batches)
+
+    def full_history(self):
+        """the whole [N, hidden] history table on this rank (sharded tables: assembled over NVLink)"""
+        if self._hist_shards is not None:
+            return self._hist_shards.gather_full(self.n_nodes)
+        return self.history
 
     def _no_nccl_inside_graphs(self, what):
         """The NCCL transport runs its collective and the merge EAGERLY after each one-pass graph
@@ -293,3 +418,10 @@ class ShardedHotPathStep(HotPathStep):
         if self._exchange is not None:
             self._exchange.close()
             self._exchange = None
+        if self._hist_shards is not None or self._feat_shards is not None:
+            torch.cuda.synchronize(self.dev)
+            self.history = self.features = None      # views of the shards that are about to be freed
+        for sh in (self._hist_shards, self._feat_shards):
+            if sh is not None:
+                sh.close()
+        self._hist_shards = self._feat_shards = None

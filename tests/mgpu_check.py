@@ -24,6 +24,7 @@ def main():
     pipelined = len(sys.argv) > 3 and sys.argv[3] == "pipelined"
     ahead = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] in ("ahead", "ahead-graph") else None
     trains = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] in ("trains", "trains-graph") else None
+    tables = sys.argv[4] if len(sys.argv) > 4 else "replicated"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -34,14 +35,24 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(0)
     feats = torch.randn((g.n, 80), generator=gen, device=dev)
     step = ShardedHotPathStep(g, feats, D, B, deg, mode=mode, seed=seed + rank, rank=rank, world=world,
-                              transport=transport)
+                              transport=transport, tables=tables)
     hist0 = torch.randn((g.n, D), generator=gen, device=dev)
-    step.history.copy_(hist0)
+    if tables == "sharded":
+        step.history[:step.hi - step.lo].copy_(hist0[step.lo:step.hi])      # this rank's shard
+    else:
+        step.history.copy_(hist0)
+    torch.cuda.synchronize()
+    dist.barrier()
 
     # every rank's batches (all ranks need them to replay the oracle)
     batches = []
     for r in range(world):
-        lo, hi = row_range(g.n, r, world)
+        if tables == "sharded":
+            from stochastic_gcn_b200.sharding import shard_rows
+            S = shard_rows(g.n, world)
+            lo, hi = min(g.n, r * S), min(g.n, (r + 1) * S)
+        else:
+            lo, hi = row_range(g.n, r, world)
         rng = np.random.RandomState(50 + r)
         batches.append([(rng.permutation(hi - lo)[:B] + lo).astype(np.int32) for _ in range(steps)])
 
@@ -137,13 +148,14 @@ def main():
         err = np.abs(out - want_out[s]).max() / max(np.abs(want_out[s]).max(), 1e-30)
         assert err < 1e-4, "rank %d step %d: out differs by %g" % (rank, s, err)
     dist.barrier()
-    got_hist = step.history.cpu().numpy()
+    torch.cuda.synchronize()
+    got_hist = step.full_history().cpu().numpy()
     assert np.array_equal(got_hist, hist), "rank %d: history replica differs from the oracle in %d rows" % (
         rank, int((got_hist != hist).any(1).sum()))
     dist.barrier()
     if rank == 0:
-        print("mgpu_check ok: transport=%s mode=%s form=%s world=%d" % (
-            transport, mode, sys.argv[3] if len(sys.argv) > 3 else "eager", world))
+        print("mgpu_check ok: transport=%s mode=%s form=%s tables=%s world=%d" % (
+            transport, mode, sys.argv[3] if len(sys.argv) > 3 else "eager", tables, world))
     step.close()
     dist.destroy_process_group()
 

@@ -26,9 +26,11 @@ def test_two_rank_pass_matches_oracle(transport, mode, graph):
     assert "mgpu_check ok" in out.stdout
 
 
-@pytest.mark.parametrize("form,mode", [("trains", "cv"), ("trains-graph", "cv"), ("trains", "cvd"), ("ahead", "cv"),
-                                       ("ahead-graph", "cv")])
-def test_all_ranks_multi_pass_schedules_match_oracle(form, mode):
+@pytest.mark.parametrize("form,mode,tables", [("trains", "cv", "replicated"), ("trains-graph", "cv", "replicated"),
+                                              ("trains", "cvd", "replicated"), ("ahead", "cv", "replicated"),
+                                              ("ahead-graph", "cv", "replicated"), ("trains", "cv", "sharded"),
+                                              ("trains-graph", "cvd", "sharded")])
+def test_all_ranks_multi_pass_schedules_match_oracle(form, mode, tables):
     """the trains schedule (bench default) and the gather-ahead schedule on EVERY GPU of the box (2, 4 or 8 ranks)"""
     world = torch.cuda.device_count()
     if world < 2:
@@ -36,7 +38,7 @@ def test_all_ranks_multi_pass_schedules_match_oracle(form, mode):
     import signal
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
            "--master-addr", "127.0.0.1", "--master-port", "29537", os.path.join(ROOT, "tests", "mgpu_check.py"),
-           "peer", mode, form]
+           "peer", mode, form, tables]
     # a process group of its own: on a timeout every rank goes, not only the launcher
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
                             start_new_session=True)
@@ -48,5 +50,6 @@ def test_all_ranks_multi_pass_schedules_match_oracle(form, mode):
         raise
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "mgpu_check_%d.log" % world), "a") as f:
-        f.write("%s %s world=%d rc=%d: %s\n" % (form, mode, world, proc.returncode, stdout.strip().splitlines()[-1:]))
+        f.write("%s %s %s world=%d rc=%d: %s\n" % (form, mode, tables, world, proc.returncode,
+                                                    stdout.strip().splitlines()[-1:]))
     assert proc.returncode == 0 and "mgpu_check ok" in stdout, stdout[-3000:] + stderr[-3000:]
