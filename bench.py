@@ -14,6 +14,8 @@ One JSON line on stdout (rank 0).
 import argparse
 import json
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per stream (see stochastic_gcn_b200/__init__.py)
 import subprocess
 import sys
 import threading
@@ -298,6 +300,7 @@ class Rig:
             lo, hi = 0, self.g.n
         self.step.train = args.train
         self.step.overlap_write_back = args.overlap_write_back
+        self.step.persistent = args.persistent and world == 1
         gen = torch.Generator(device=dev).manual_seed(7)
         self.step.d_out.normal_(generator=gen)
         self.step.history.normal_(generator=gen)      # a warm history table (zero rows would skip reductions)
@@ -644,6 +647,9 @@ def main():
     ap.add_argument("--overlap-write-back", action="store_true",
                     help="take the history write-back off the critical chain (row override in the next pass's "
                          "full-neighbour mean); measured slower inside CUDA graphs, see DESIGN section 1")
+    ap.add_argument("--persistent", action="store_true",
+                    help="single GPU, CV / CVD: ONE persistent full-neighbour-mean launch per graph, device-side "
+                         "counters instead of kernel boundaries on the chain (sgcn_step_run_persistent)")
     ap.add_argument("--eager-trains", action="store_true",
                     help="trains driver as plain stream launches from C++ (no CUDA graphs): A/B of the graph overhead")
     ap.add_argument("--no-also", action="store_true", help="skip the extra keys for the other BASELINE configurations")

@@ -541,17 +541,6 @@ void sgcn_step_destroy(sgcn_step* st);
 int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
                   void* stream);
 
-/* "Gather ahead" schedule (parity-tested on hardware, not timed yet; bench.py --driver ahead):
- * the same n passes with the gather / dX init / output zeroing of pass k+1 issued one pass AHEAD into
- * second copies of x0 / dx (x0_alt, dx_alt: same shapes and strides as desc.x0 / desc.dx), so that a
- * pass's side branch is the sampled aggregate alone and the write-back can follow the full-neighbour
- * mean immediately.  ids / ids_on_host / out_host and the multi-GPU exchange fields as for sgcn_step_run
- * (the single-GPU device-buffer form is the one parity-tested on hardware so far).  Every internal stream
- * forks from and joins `stream`: the call may be captured into a CUDA graph.  Pass k's aggregated rows
- * are in desc.out[k & 1], its gathered rows in (k & 1 ? x0_alt : desc.x0). */
-int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32_t* ids, int32_t ids_on_host,
-                        int32_t n, float* out_host, void* stream);
-
 /* sgcn_full_history_mean with a row override: history rows of the nodes ov_ids[0 .. *ov_n_dev) (distinct,
  * at most ov_bound <= 4096) are read from ov_rows[i, :] (row stride ld_ov) instead of hist -- i.e. the
  * result is what sgcn_history_update(hist, ov_ids, ov_rows) followed by sgcn_full_history_mean would give,
@@ -563,6 +552,32 @@ int sgcn_full_history_mean_ov(const int32_t* nodes, const int32_t* rowptr_f, int
                               float* y0, int64_t ld_y0, float* y1, int64_t ld_y1,
                               const int32_t* ov_ids, const int32_t* ov_n_dev, int32_t ov_bound,
                               const float* ov_rows, int64_t ld_ov, void* stream);
+
+/* The full-neighbour means of up to 64 consecutive passes in ONE launch (persistent thread blocks; between two
+ * launches of the one-pass kernel the GPU idles for 4-7 us inside a CUDA graph).  Pass k starts on the device
+ * once flags[0] > passes[k].train (its batch is sampled), flags[1] > k (its output rows are zeroed and pass
+ * k-1's rows gathered) and flags[2] >= k - 1 (write-back k-2 has landed; the rows of pass k-1's input field are
+ * overridden from ov_rows as in sgcn_full_history_mean_ov); every thread block adds 1 to flags[8 + k] when its
+ * part of pass k is in memory.  flags: device int32[8 + 64], zeroed by sgcn_flags_reset before the launch;
+ * flags[3] != 0 afterwards = a counter never arrived (bounded spins).  *n_blocks (HOST out) = thread blocks
+ * launched = the value flags[8 + k] reaches.  All passes share the adjacency, the history table, widths and
+ * strides; n_out_bound = rows per pass (the true count comes from n_out_dev). */
+typedef struct {
+    const int32_t* nodes; const int32_t* rowptr_f; const int32_t* n_out_dev;
+    float* y0; float* y1;
+    const int32_t* ov_ids; const int32_t* ov_n_dev; const float* ov_rows;    /* NULL: no override (first pass) */
+    int32_t train; int32_t pad;
+} sgcn_full_pass;
+int sgcn_full_history_mean_passes(const sgcn_full_pass* passes /*HOST*/, int32_t n, int32_t n_out_bound,
+                                  const int32_t* adj_p, const int32_t* adj_i, const float* adj_w,
+                                  const float* hist, int64_t ld_h, int32_t D, int64_t ld_y0, int64_t ld_y1,
+                                  int32_t ov_bound, int64_t ld_ov, int32_t* flags, int32_t* n_blocks /*HOST out*/,
+                                  void* stream);
+/* stream-ordered helpers for such device-side counters: zero n of them; raise one to `value` (atomic max) once
+ * everything before it in the stream has finished; hold the stream until *flag >= want (bounded: sets *err) */
+int sgcn_flags_reset(int32_t* flags, int32_t n, void* stream);
+int sgcn_flag_set(int32_t* flag, int32_t value, void* stream);
+int sgcn_flag_gate(const int32_t* flag, int32_t want, int32_t* err, void* stream);
 
 /* The schedule bench.py times: n passes with
  *   samp  : trains of `train` batches sampled by ONE launch each (sgcn_sampler_expand_train), one train ahead
@@ -579,6 +594,17 @@ int sgcn_full_history_mean_ov(const int32_t* nodes, const int32_t* rowptr_f, int
  * (k & 1 ? dx_alt : desc.dx), sampler buffer set  ((train index & 1) * train + position in the train). */
 int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
                          int32_t first_train, void* stream);
+
+/* Persistent form of sgcn_step_run_trains (single GPU, CV / CVD, write-back off the chain): the chain is ONE
+ * launch of sgcn_full_history_mean_passes for all n passes (longer runs: 64 passes per launch) and the
+ * dependencies that crossed kernel boundaries on the chain are device-side counters (sgcn_flag_set /
+ * sgcn_flag_gate).  Same arguments, same results, same buffers as sgcn_step_run_trains. */
+int sgcn_step_run_persistent(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
+                             int32_t first_train, void* stream);
+
+/* *timed_out (HOST) != 0: a device-side wait of sgcn_step_run_persistent gave up (bounded spins) since the last
+ * run started -- its results are not to be trusted.  Synchronises the device. */
+int sgcn_step_status(sgcn_step* st, int32_t* timed_out);
 
 #ifdef __cplusplus
 }

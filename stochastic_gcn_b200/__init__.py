@@ -16,3 +16,11 @@ from . import _lib  # noqa: F401
 
 __all__ = ["_lib", "ops", "sampler", "scheduler", "history", "layers", "graphs", "step", "sharding"]
 __version__ = "0.1.0"
+
+import os as _os
+
+# The step drivers run five to six CUDA streams side by side, some of whose kernels wait on the device for
+# others (bounded spins).  With the default of 8 hardware work queues streams share queues, and a queue
+# processes its entries in order -- a waiting kernel's stream can then hold back an unrelated one.  One queue
+# per stream avoids that; it only takes effect if set before the CUDA context is created.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")

@@ -100,8 +100,14 @@ SIGNATURES = {
     "sgcn_step_create": (_i32, [C.POINTER(_vp), _vp, _vp]),
     "sgcn_step_destroy": (None, [_vp]),
     "sgcn_step_run": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
-    "sgcn_step_run_ahead": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "sgcn_step_run_trains": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp]),
+    "sgcn_step_status": (_i32, [_vp, C.POINTER(_i32)]),
+    "sgcn_step_run_persistent": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp]),
+    "sgcn_full_history_mean_passes": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i32, _i64,
+                                             _vp, _vp, _vp]),
+    "sgcn_flags_reset": (_i32, [_vp, _i32, _vp]),
+    "sgcn_flag_set": (_i32, [_vp, _i32, _vp]),
+    "sgcn_flag_gate": (_i32, [_vp, _i32, _vp, _vp]),
     "sgcn_full_history_mean_ov": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,
                                          _vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
     "sgcn_wb_payload_bytes": (_i64, [_i32, _i32]),

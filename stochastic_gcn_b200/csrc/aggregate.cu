@@ -386,26 +386,42 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 constexpr unsigned short kOvEmpty = 0xffffu;
 __device__ __forceinline__ unsigned ov_hash(int node, int bits) { return ((unsigned)node * 2654435761u) >> (32 - bits); }
 
+struct PassDesc {      // one pass of the persistent kernel below
+    const int32_t* nodes; const int32_t* rowptr_f; const int32_t* n_out_dev;
+    float* y0; float* y1;
+    const int32_t* ov_ids; const int32_t* ov_n_dev; const float* ov_rows;
+    int train;
+};
+
 template <typename V, int LPR, int VPL>
-__device__ __forceinline__ void full_flush(const FullArgs& a, int row, int gl, V (&acc)[VPL]) {
+__device__ __forceinline__ void full_flush(const FullArgs& a, float* y0, float* y1, int row, int gl, V (&acc)[VPL]) {
     using T = VT<V>;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
         const int off = (gl + k * LPR) * T::W;
         if (off < a.D && T::nonzero(acc[k])) {
-            T::red(a.y0 + (int64_t)row * a.ld_y0 + off, acc[k]);
-            if (a.y1) T::red(a.y1 + (int64_t)row * a.ld_y1 + off, acc[k]);
+            T::red(y0 + (int64_t)row * a.ld_y0 + off, acc[k]);
+            if (y1) T::red(y1 + (int64_t)row * a.ld_y1 + off, acc[k]);
         }
         acc[k] = T::zero();
     }
 }
 
-template <typename V, int LPR, int VPL>
-__global__ void __maxnreg__(96)      // 2 CTAs x 256 threads x 96 regs leave 16K registers per SM free
-full_mean_kernel(const FullArgs a) {
+// One pass of the full-neighbour mean by this thread block (its warps' spans of the pass's positions).
+// PDL: the block belongs to a launch of its own (full_mean_kernel) and orders itself against its stream
+// predecessor with griddepcontrol; !PDL: called pass after pass by the persistent kernel below.
+template <typename V, int LPR, int VPL, bool PDL>
+__device__ __forceinline__ void full_mean_body(const FullArgs& a, const PassDesc* pd) {
     using T = VT<V>;
-    TraceScope ts(a.trace, TR_FULL);
-    grid_dep_launch();                                           // (PDL) the write-back may get resident now
+    // what differs from pass to pass: from the launch arguments, or from the persistent kernel's pass list
+    const int32_t* const nodes = PDL ? a.nodes : pd->nodes;
+    const int32_t* const rowptr_f = PDL ? a.rowptr_f : pd->rowptr_f;
+    const int32_t* const n_out_dev = PDL ? a.n_out_dev : pd->n_out_dev;
+    float* const y0 = PDL ? a.y0 : pd->y0;
+    float* const y1 = PDL ? a.y1 : pd->y1;
+    const int32_t* const ov_ids = PDL ? a.ov_ids : pd->ov_ids;
+    const int32_t* const ov_n_dev = PDL ? a.ov_n_dev : pd->ov_n_dev;
+    const float* const ov_rows = PDL ? a.ov_rows : pd->ov_rows;
     constexpr int G = 32 / LPR;                                  // groups per warp
     constexpr int UN = (VPL >= 8) ? 1 : ((VPL == 4) ? 2 : ((VPL == 2) ? 4 : 8));   // row loads per buffer
     constexpr int STEP = G * UN;                                 // positions per group-iteration
@@ -418,22 +434,22 @@ full_mean_kernel(const FullArgs a) {
     __shared__ int32_t s_lcol[kFullWarps][kFullMacro];           // landing buffers of the NEXT chunk's metadata
     __shared__ float s_lw[kFullWarps][kFullMacro];
     __shared__ int32_t s_lr[kFullWarps][kFullMacro];
-    const int n_out = dev_count(a.n_out_dev, a.n_out);
+    const int n_out = dev_count(n_out_dev, a.n_out);
     if (n_out <= 0) return;
     const bool staged = n_out <= a.stage_rows;
     // override table (open addressing, 16-bit slots = index into the id list kept beside it)
     int32_t* s_ovid = s_dyn + 2 * a.stage_rows + 2;
     unsigned short* s_ovtab = (unsigned short*)(s_ovid + a.ov_bound);
-    const int ov_n = a.ov_ids ? min(*a.ov_n_dev, a.ov_bound) : 0;
+    const int ov_n = ov_ids ? min(*ov_n_dev, a.ov_bound) : 0;
     const unsigned ov_mask = (1u << a.ov_bits) - 1u;
     if (ov_n > 0) {
         for (int i = threadIdx.x; i < (1 << a.ov_bits); i += kAggThreads) s_ovtab[i] = kOvEmpty;
-        for (int i = threadIdx.x; i < ov_n; i += kAggThreads) s_ovid[i] = __ldg(a.ov_ids + i);
+        for (int i = threadIdx.x; i < ov_n; i += kAggThreads) s_ovid[i] = __ldg(ov_ids + i);
     }
     if (staged) {
-        for (int i = threadIdx.x; i <= n_out; i += kAggThreads) s_ptr[i] = __ldg(a.rowptr_f + i);
+        for (int i = threadIdx.x; i <= n_out; i += kAggThreads) s_ptr[i] = __ldg(rowptr_f + i);
         for (int i = threadIdx.x; i < n_out; i += kAggThreads)
-            s_base[i] = __ldg(a.adj_p + __ldg(a.nodes + i)) - __ldg(a.rowptr_f + i);
+            s_base[i] = __ldg(a.adj_p + __ldg(nodes + i)) - __ldg(rowptr_f + i);
     }
     if (staged || ov_n > 0) __syncthreads();
     if (ov_n > 0) {
@@ -444,8 +460,8 @@ full_mean_kernel(const FullArgs a) {
         __syncthreads();
     }
     // element offset (relative to hist) of override row i
-    const int64_t ov_base = a.ov_rows ? (int64_t)(((intptr_t)a.ov_rows - (intptr_t)a.hist) / (intptr_t)sizeof(float)) : 0;
-    const int32_t* ptr = staged ? s_ptr : a.rowptr_f;
+    const int64_t ov_base = ov_rows ? (int64_t)(((intptr_t)ov_rows - (intptr_t)a.hist) / (intptr_t)sizeof(float)) : 0;
+    const int32_t* ptr = staged ? s_ptr : rowptr_f;
     const int nnz = ptr[n_out];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gl = lane % LPR, g = lane / LPR;
@@ -505,7 +521,7 @@ full_mean_kernel(const FullArgs a) {
                 }
                 l_r[j] = lo;
                 const int q = staged ? (s_base[lo] + p)
-                                     : (__ldg(a.adj_p + __ldg(a.nodes + lo)) + (p - ptr[lo]));
+                                     : (__ldg(a.adj_p + __ldg(nodes + lo)) + (p - ptr[lo]));
                 cp_async4(l_col + j, a.adj_i + q);
                 cp_async4(l_w + j, a.adj_w + q);
             } else {
@@ -547,7 +563,7 @@ full_mean_kernel(const FullArgs a) {
     // (PDL) history rows: after the write-back.  With the row override the stream predecessor is the
     // previous pass's full-neighbour mean, which writes nothing this kernel reads: the wait moves to
     // the end (completion order only) and the two kernels overlap tail to head.
-    if (!a.ov_ids) grid_dep_wait();
+    if (PDL && !ov_ids) grid_dep_wait();
 
   for (;;) {
     int next_chunk = 0;
@@ -575,7 +591,7 @@ full_mean_kernel(const FullArgs a) {
             const int rf = my_r[jf], rl = my_r[jf + (UN - 1) * G];
             if (rf == rl && rf >= 0) {                            // whole group inside one output row
                 if (rf != cur) {
-                    if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
+                    if (cur >= 0) full_flush<V, LPR, VPL>(a, y0, y1, cur, gl, acc);
                     cur = rf;
                 }
 #pragma unroll
@@ -590,7 +606,7 @@ full_mean_kernel(const FullArgs a) {
                     const int r = my_r[jf + u * G];
                     if (r < 0) continue;
                     if (r != cur) {
-                        if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
+                        if (cur >= 0) full_flush<V, LPR, VPL>(a, y0, y1, cur, gl, acc);
                         cur = r;
                     }
                     const float w = my_w[jf + u * G];
@@ -619,8 +635,94 @@ full_mean_kernel(const FullArgs a) {
     p1 = min(p0 + kFullMacro, nnz);
     fetch(p0, p1);
   }
-    if (cur >= 0) full_flush<V, LPR, VPL>(a, cur, gl, acc);
+    if (cur >= 0) full_flush<V, LPR, VPL>(a, y0, y1, cur, gl, acc);
+}
+
+template <typename V, int LPR, int VPL>
+__global__ void __maxnreg__(96)      // 2 CTAs x 256 threads x 96 regs leave 16K registers per SM free
+full_mean_kernel(const FullArgs a) {
+    TraceScope ts(a.trace, TR_FULL);
+    grid_dep_launch();                                           // (PDL) the write-back may get resident now
+    full_mean_body<V, LPR, VPL, true>(a, nullptr);
     if (a.ov_ids) grid_dep_wait();
+}
+
+// ---- the full-neighbour means of a whole graph of passes in ONE launch ---------------------------------
+// Between two launches of full_mean_kernel the GPU idles for 4-7 us (dependent-launch latency under load,
+// measured inside CUDA graphs with and without programmatic launches: profiles/r02_timeline_trains_*.txt) --
+// a quarter of a 19 us kernel.  Here the thread blocks stay resident for all n passes of a run and the
+// dependencies become device-side counters:
+//   waits    pass k starts once  trains_done > train(k)   (its batch is sampled),
+//                                pre_done > k             (its output rows are zeroed, pass k-1's rows gathered),
+//                                wb_done >= k - 1         (write-back k-2 has landed; rows of field(k-1) come
+//                                                          from pass k-1's gathered rows: the row override)
+//   signals  every block adds 1 to full_done[k] when its part of pass k is in memory; the write-back of
+//            pass k, the D2H copy of its rows and the re-use of its buffers are gated on full_done[k] == blocks
+// All spins are bounded: a counter that never moves raises flags[F_ERROR] instead of hanging the GPU.
+constexpr int kMaxPasses = 64;
+enum { F_TRAINS = 0, F_PRE = 1, F_WB = 2, F_ERROR = 3, F_FULL = 8 };     // flags[F_FULL + k]: blocks done with pass k
+struct PassList { PassDesc p[kMaxPasses]; int n; };
+
+__device__ __forceinline__ bool spin_until_ge(const int32_t* ctr, int want, int32_t* err) {
+    long long spins = 0;
+    while ((int)ld_acquire_u32((const unsigned*)ctr) < want) {
+        if (++spins > 8000000LL) {         // ~2 s
+            atomicExch(err, 1);
+            return false;
+        }
+        __nanosleep(50);
+    }
+    return true;
+}
+
+template <typename V, int LPR, int VPL>
+__global__ void __maxnreg__(96)
+full_mean_persistent_kernel(const __grid_constant__ FullArgs a, const __grid_constant__ PassList passes, int32_t* flags) {
+    __shared__ int s_go;
+    for (int k = 0; k < passes.n; ++k) {
+        const PassDesc& pd = passes.p[k];
+        if (threadIdx.x == 0) {
+            bool go = spin_until_ge(flags + F_TRAINS, pd.train + 1, flags + F_ERROR) &&
+                      spin_until_ge(flags + F_PRE, k + 1, flags + F_ERROR) &&
+                      (k < 2 || spin_until_ge(flags + F_WB, k - 1, flags + F_ERROR));
+            s_go = go && *(volatile int32_t*)(flags + F_ERROR) == 0;
+        }
+        __syncthreads();
+        if (!s_go) return;
+        if (a.trace && threadIdx.x == 0 && blockIdx.x == 0) {        // timeline: one start / end pair per pass
+            const unsigned long long now = global_ns();
+            const unsigned long long i = atomicAdd(a.trace + 16, 1ull);
+            if (i < (unsigned long long)kTraceLogCap) { a.trace[17 + 2 * i] = (TR_FULL << 1); a.trace[18 + 2 * i] = now; }
+        }
+        full_mean_body<V, LPR, VPL, false>(a, &pd);
+        __syncthreads();                                              // every warp's REDs are issued
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(flags + F_FULL + k, 1);
+            if (a.trace && blockIdx.x == 0) {
+                const unsigned long long now = global_ns();
+                const unsigned long long i = atomicAdd(a.trace + 16, 1ull);
+                if (i < (unsigned long long)kTraceLogCap) { a.trace[17 + 2 * i] = (TR_FULL << 1) | 1; a.trace[18 + 2 * i] = now; }
+            }
+        }
+    }
+}
+
+// tiny stream-ordered helpers around the persistent kernel
+__global__ void flags_reset_kernel(int32_t* flags, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) flags[i] = 0;
+}
+__global__ void flag_set_kernel(int32_t* flag, int value) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicMax(flag, value);
+    }
+}
+__global__ void flag_gate_kernel(const int32_t* flag, int want, int32_t* err) {
+    if (threadIdx.x == 0) {
+        spin_until_ge(flag, want, err);
+        __threadfence();
+    }
 }
 
 // ---- full-neighbour history mean, bulk-copy (TMA engine) variant ---------------------------------
@@ -769,7 +871,7 @@ full_mean_tma_kernel(const FullArgs a, const FullTmaCfg cfg) {
                     const int row = m_row[b + r];
                     const float w = m_w[b + r];
                     if (row != cur) {
-                        if (cur >= 0) full_flush<float4, 32, 1>(a, cur, gl, acc);
+                        if (cur >= 0) full_flush<float4, 32, 1>(a, a.y0, a.y1, cur, gl, acc);
                         cur = row;
                     }
                     if (ok) T::fma(acc[0], w, *(const float4*)(base + (size_t)r * row_bytes));
@@ -783,7 +885,7 @@ full_mean_tma_kernel(const FullArgs a, const FullTmaCfg cfg) {
         }
         __syncthreads();                                          // metadata is rewritten by the next pass
     }
-    if (cur >= 0) full_flush<float4, 32, 1>(a, cur, gl, acc);
+    if (cur >= 0) full_flush<float4, 32, 1>(a, a.y0, a.y1, cur, gl, acc);
 }
 
 // runtime tunables (sgcn_tune_set): which full-mean variant runs and the shape of its ring
@@ -1206,6 +1308,75 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
 #undef CALL
         SGCN_LAUNCHED();
     }
+    return SGCN_OK;
+}
+
+int sgcn_flags_reset(int32_t* flags, int32_t n, void* stream) {
+    SGCN_REQUIRE(flags && n > 0, "flags_reset: bad argument");
+    flags_reset_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(flags, n);
+    SGCN_LAUNCHED();
+    return SGCN_OK;
+}
+
+int sgcn_flag_set(int32_t* flag, int32_t value, void* stream) {
+    SGCN_REQUIRE(flag, "flag_set: null flag");
+    flag_set_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag, value);
+    SGCN_LAUNCHED();
+    return SGCN_OK;
+}
+
+int sgcn_flag_gate(const int32_t* flag, int32_t want, int32_t* err, void* stream) {
+    SGCN_REQUIRE(flag && err, "flag_gate: null pointer");
+    flag_gate_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag, want, err);
+    SGCN_LAUNCHED();
+    return SGCN_OK;
+}
+
+int sgcn_full_history_mean_passes(const sgcn_full_pass* passes, int32_t n, int32_t n_out_bound,
+                                  const int32_t* adj_p, const int32_t* adj_i, const float* adj_w,
+                                  const float* hist, int64_t ld_h, int32_t D, int64_t ld_y0, int64_t ld_y1,
+                                  int32_t ov_bound, int64_t ld_ov, int32_t* flags, int32_t* n_blocks, void* stream) {
+    SGCN_REQUIRE(passes && n >= 1 && n <= kMaxPasses && n_out_bound > 0 && n_out_bound <= kFullStageRows,
+                 "full_history_mean_passes: 1..64 passes of at most 4096 rows");
+    SGCN_REQUIRE(adj_p && adj_i && adj_w && hist && flags && n_blocks && D > 0 && ld_h >= D && ld_y0 >= D,
+                 "full_history_mean_passes: bad argument");
+    SGCN_REQUIRE(ov_bound > 0 && ov_bound <= kFullOvMax && ld_ov >= D, "full_history_mean_passes: bad override bound");
+    bool vec_ok = D % 4 == 0 && ld_h % 4 == 0 && ld_y0 % 4 == 0 && ld_ov % 4 == 0 && aligned16(hist);
+    PassList pl{};
+    pl.n = n;
+    for (int k = 0; k < n; ++k) {
+        const sgcn_full_pass& s = passes[k];
+        SGCN_REQUIRE(s.nodes && s.rowptr_f && s.y0 && (!s.ov_ids || (s.ov_n_dev && s.ov_rows)),
+                     "full_history_mean_passes: null pointer in a pass");
+        vec_ok = vec_ok && aligned16(s.y0) && (!s.y1 || (aligned16(s.y1) && ld_y1 % 4 == 0)) &&
+                 (!s.ov_rows || aligned16(s.ov_rows));
+        pl.p[k] = PassDesc{s.nodes, s.rowptr_f, s.n_out_dev, s.y0, s.y1, s.ov_ids, s.ov_n_dev, s.ov_rows, s.train};
+    }
+    const Shape sh = pick_shape(D, vec_ok);
+    SGCN_REQUIRE(D <= sh.tile, "full_history_mean_passes: the aggregated width must fit one column tile");
+    int ov_bits = 4;
+    while ((1 << ov_bits) < 2 * ov_bound) ++ov_bits;
+    FullArgs a{nullptr, nullptr, n_out_bound, nullptr, adj_p, adj_i, adj_w, hist, ld_h, D, nullptr, ld_y0, nullptr, ld_y1,
+               nullptr, n_out_bound, g_trace, 0, nullptr, nullptr, ov_bound, ov_bits, nullptr, ld_ov, ShardMap{}};
+    const size_t dyn = sizeof(int32_t) * (2 * (size_t)a.stage_rows + 2) + sizeof(int32_t) * (size_t)ov_bound +
+                       sizeof(unsigned short) * ((size_t)1 << ov_bits);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(V, L, P)                                                                                    \
+    do {                                                                                                 \
+        int per_sm = 0;                                                                                  \
+        SGCN_CUDA(cudaFuncSetAttribute(full_mean_persistent_kernel<V, L, P>,                             \
+                                       cudaFuncAttributePreferredSharedMemoryCarveout, kStepCarveout));   \
+        SGCN_CUDA(cudaFuncSetAttribute(full_mean_persistent_kernel<V, L, P>,                             \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));         \
+        SGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                         \
+            &per_sm, full_mean_persistent_kernel<V, L, P>, kAggThreads, dyn));                           \
+        if (per_sm < 1) per_sm = 1;                                                                      \
+        *n_blocks = kNumSMs * per_sm;                                                                    \
+        full_mean_persistent_kernel<V, L, P><<<kNumSMs * per_sm, kAggThreads, dyn, st>>>(a, pl, flags);  \
+    } while (0)
+    SGCN_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+    SGCN_LAUNCHED();
     return SGCN_OK;
 }
 

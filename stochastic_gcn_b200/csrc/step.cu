@@ -39,6 +39,7 @@ struct sgcn_step {
     int32_t* ids_stage[2] = {nullptr, nullptr};     // staging of host ids, one per train parity
     static constexpr int kRing2 = 8;
     cudaEvent_t t_pre[kRing2]{}, t_full[kRing2]{}, t_fwd[kRing2]{}, t_rest[kRing2]{}, t_d2h[kRing2]{}, t_train[4]{};
+    int32_t* flags = nullptr;                       // sgcn_step_run_persistent: device counters (8 + 64 ints)
 };
 
 namespace sgcn {
@@ -123,6 +124,8 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
         for (cudaEvent_t* e : {&st->t_pre[i], &st->t_full[i], &st->t_fwd[i], &st->t_rest[i], &st->t_d2h[i]})
             CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&st->t_train[i], cudaEventDisableTiming));
+    CK(cudaMalloc(&st->flags, sizeof(int32_t) * (8 + 64)));
+    CK(cudaMemset(st->flags, 0, sizeof(int32_t) * (8 + 64)));
     {
         // trains of batches: 2 x train buffer sets (the passes of one train run while the next is sampled)
         const int T = d.train > 0 ? d.train : 16;
@@ -175,7 +178,15 @@ void sgcn_step_destroy(sgcn_step* st) {
             if (e) cudaEventDestroy(e);
     for (int i = 0; i < 4; ++i) if (st->t_train[i]) cudaEventDestroy(st->t_train[i]);
     for (int i = 0; i < 2; ++i) cudaFree(st->ids_stage[i]);
+    cudaFree(st->flags);
     delete st;
+}
+
+int sgcn_step_status(sgcn_step* st, int32_t* timed_out) {
+    SGCN_REQUIRE(st && timed_out, "step_status: null argument");
+    SGCN_CUDA(cudaDeviceSynchronize());
+    SGCN_CUDA(cudaMemcpy(timed_out, st->flags + 3, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return SGCN_OK;
 }
 
 int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
@@ -328,167 +339,6 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));
     if (out_host) SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_d2h[(n - 1) % R], 0));
-    return SGCN_OK;
-}
-
-// ---- "gather ahead" schedule (parity-green on a B200 at the end of round 1 -- tests/ahead_check.py --
-// but NOT TIMED yet: bench.py --driver ahead selects it, the default driver is unchanged) ----
-// sgcn_step_run's side branch per pass is [dX init + zero + gather] -> sampled aggregate, and under load
-// every dependent launch there costs 4-8 us, so the write-back (which must follow the sampled aggregate)
-// starts ~8 us after the full-neighbour mean has ended (profiles/r01_timeline_after.txt).  Here the
-// gather / dX init / output zeroing of pass k+1 run one pass AHEAD on a stream of their own, into second
-// copies of x0 / dx, so that pass k's side branch is the sampled aggregate alone:
-//   chain : [sampler k] full_mean(k) ═PDL═► history_update(k) ═PDL═► full_mean(k+1) ...
-//   side  : [ahead k, rest k-1] sampled fwd+bwd(k)
-//   pre   : [sampler k+1, rest k-1] gather(k+1) + dX init(k+1) + zero out(k+1)      (buffers of parity k+1)
-//   samp  : [rest k-1] expand(k+2)
-// Same arithmetic, same order of history reads and writes as n sequential passes.  ids / out_host as in
-// sgcn_step_run (the host-buffer and multi-GPU forms are newer than the parity run recorded above); every internal stream forks from and joins `stream`, so a call can be captured
-// into a CUDA graph (that is how it is meant to be used: graph-to-graph gaps instead of host launches).
-int sgcn_step_run_ahead(sgcn_step* st, float* x0_alt, float* dx_alt, const int32_t* ids, int32_t ids_on_host,
-                        int32_t n, float* out_host, void* stream) {
-    SGCN_REQUIRE(st && x0_alt && dx_alt && n >= 0 && (n == 0 || ids), "step_run_ahead: bad argument");
-    if (n == 0) return SGCN_OK;
-    const sgcn_step_desc& d = st->d;
-    sgcn_sampler* smp = st->sampler;
-    const int B = d.batch, H = d.hidden, R = sgcn_step::kRing;
-    const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0, multi = d.world > 1 && cv;
-    const int width = H * (concat ? 2 : 1);
-    cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp, pre = st->pre,
-                 copy = st->copy;
-    float* x0b[2] = {d.x0, x0_alt};
-    float* dxb[2] = {d.dx, dx_alt};
-    auto nb = [&](float* base) { return base + (concat ? H : 0); };
-    constexpr int NS = sgcn_step::kSlots;
-
-    SGCN_CUDA(cudaEventRecord(st->ev_begin, user));
-    for (cudaStream_t s : {chain, side, samp, pre}) SGCN_CUDA(cudaStreamWaitEvent(s, st->ev_begin, 0));
-    // (under stream capture a forked stream must be joined again: the copy stream forks only when it has work)
-    if (out_host) SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_begin, 0));
-
-    auto sample = [&](int k) -> int {
-        const int32_t* src = ids + (int64_t)k * B;
-        if (ids_on_host) {                       // pinned host ids: staged per pass on the sampler stream
-            SGCN_CUDA(cudaMemcpyAsync(st->ids_dev[k % NS], src, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice,
-                                      samp));
-            src = st->ids_dev[k % NS];
-        }
-        STEP_TRY(sgcn_sampler_set_slot(smp, k % NS));
-        STEP_TRY(sgcn_sampler_start_batch_device(smp, B, src));
-        STEP_TRY(sgcn_sampler_expand(smp, d.degree, 0));
-        SGCN_CUDA(cudaEventRecord(st->ev_samp[k % R], samp));
-        return SGCN_OK;
-    };
-    // gather + dX init + output zeroing of pass k, into the buffers of parity k & 1
-    auto ahead = [&](int k) -> int {
-        const sgcn_step::Lv& v = st->lv[k % NS];
-        const int r = k & 1;
-        SGCN_CUDA(cudaStreamWaitEvent(pre, st->ev_samp[k % R], 0));
-        if (k >= 2) SGCN_CUDA(cudaStreamWaitEvent(pre, st->ev_rest[(k - 2) % R], 0));   // pass k-2 used these buffers
-        if (k >= 2 && out_host) SGCN_CUDA(cudaStreamWaitEvent(pre, st->ev_d2h[(k - 2) % R], 0));   // ... its rows are out
-        STEP_TRY(sgcn_gather_pad_pair(d.features, d.ld_feat, v.field, d.x0_rows, v.meta + 1, d.feat_dim, x0b[r], d.ld_x0,
-                                      concat ? d.d_out : nullptr, d.ld_dout, concat ? B : 0,
-                                      concat ? v.meta + 0 : nullptr, d.x0_rows, H, dxb[r], d.ld_dx,
-                                      nullptr, 0, 0, nullptr, cv ? B : 0, H, cv ? nb(d.out[r]) : nullptr, d.ld_out, pre));
-        if (cvd) STEP_TRY(sgcn_copy_rows_pad(nullptr, 0, 0, nullptr, B, H, nb(d.out_mu[r]), d.ld_out, pre));
-        SGCN_CUDA(cudaEventRecord(st->ev_pre[k % R], pre));
-        return SGCN_OK;
-    };
-
-    STEP_TRY(sgcn_sampler_set_stream_async(smp, samp));
-    for (int slot = 0; slot < NS; ++slot) {          // forget the batches of earlier runs (see sgcn_step_run)
-        STEP_TRY(sgcn_sampler_set_slot(smp, slot));
-        STEP_TRY(sgcn_sampler_start_batch_device(smp, 0, nullptr));
-    }
-    STEP_TRY(sample(0));
-    if (n > 1) STEP_TRY(sample(1));
-    STEP_TRY(ahead(0));
-
-    for (int k = 0; k < n; ++k) {
-        const int r = k & 1;
-        const sgcn_step::Lv& v = st->lv[k % NS];
-        const int32_t* n_out_dev = v.meta + 0;
-        const int32_t* n_in_dev = v.meta + 1;
-        float* out_r = d.out[r];
-        float* outmu_r = d.out_mu[r];
-        const float* x = x0b[r];
-        const float* mu = x0b[r] + H;
-        const float* new_hist = cvd ? mu : x;
-        const float* d_nb = d.d_out + (concat ? H : 0);
-
-        // ---- chain: the full-neighbour history mean of pass k (its output was zeroed by ahead(k)) ----
-        SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_samp[k % R], 0));
-        SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_pre[k % R], 0));
-        if (cv) {
-            STEP_TRY(sgcn_full_history_mean(v.field, v.rowptr_f, B, n_out_dev, st->adj_p, st->adj_i, st->adj_w,
-                                            d.history, d.ld_hist, H, cvd ? nb(outmu_r) : nb(out_r), d.ld_out,
-                                            cvd ? nb(out_r) : nullptr, d.ld_out, nullptr, chain));
-        }
-        if (out_host) SGCN_CUDA(cudaEventRecord(st->ev_full[k % R], chain));
-        // ---- samp: sampler of batch k+2 into the buffer set pass k-1 used ----
-        if (k + 2 < n) {
-            if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(samp, st->ev_rest[(k - 1) % R], 0));
-            STEP_TRY(sample(k + 2));
-        }
-        // ---- pre: everything of pass k+1 that does not read the history ----
-        if (k + 1 < n) STEP_TRY(ahead(k + 1));
-        // ---- side: the sampled aggregate + backward of pass k (history as of write-back k-1) ----
-        SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_pre[k % R], 0));
-        if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_rest[(k - 1) % R], 0));
-        if (d.mode == 0) {
-            STEP_TRY(sgcn_spmm_csr(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, x, d.ld_x0, H, nb(out_r),
-                                   d.ld_out, 0, side));
-            if (concat) STEP_TRY(sgcn_copy_rows_pad(x, d.ld_x0, B, n_out_dev, B, H, out_r, d.ld_out, side));
-            STEP_TRY(sgcn_spmm_csr_bwd(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, d_nb, d.ld_dout, H, dxb[r],
-                                       d.ld_dx, side));
-        } else if (!cvd) {
-            if (multi)      // the write-back push rides on the sampled launch (see sgcn_wb_push_attach)
-                STEP_TRY(sgcn_wb_push_attach(v.field, n_in_dev, d.wb_bound, new_hist, d.ld_x0, H, d.dst_even, d.dst_odd,
-                                             d.world, d.peer_flags, d.rank, d.epoch, d.block_counter));
-            STEP_TRY(sgcn_cv_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, B, n_out_dev, x, d.ld_x0, d.history,
-                                             d.ld_hist, H, nb(out_r), d.ld_out, concat ? out_r : nullptr, d.ld_out, 1,
-                                             d_nb, d.ld_dout, dxb[r], d.ld_dx, side));
-        } else {
-            if (multi)
-                STEP_TRY(sgcn_wb_push_attach(v.field, n_in_dev, d.wb_bound, new_hist, d.ld_x0, H, d.dst_even, d.dst_odd,
-                                             d.world, d.peer_flags, d.rank, d.epoch, d.block_counter));
-            STEP_TRY(sgcn_cvd_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, v.scales, B, n_out_dev, x, d.ld_x0,
-                                              mu, d.ld_x0, d.history, d.ld_hist, H, nb(out_r), d.ld_out,
-                                              nb(outmu_r), d.ld_out, concat ? out_r : nullptr, d.ld_out,
-                                              concat ? outmu_r : nullptr, d.ld_out, 1, d_nb, d.ld_dout, dxb[r],
-                                              d.ld_dx, side));
-        }
-        SGCN_CUDA(cudaEventRecord(st->ev_fwd[k % R], side));
-        // ---- chain: write-back after every forward read of history (gcn/models.py:186-194) ----
-        SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_fwd[k % R], 0));
-        if (!cv) {
-            STEP_TRY(sgcn_sampler_mark_consumed(smp, chain));
-        } else if (multi) {
-            STEP_TRY(sgcn_wb_wait_apply(d.history, d.ld_hist, H, d.recv_even, d.recv_odd, d.slot_bytes, d.world,
-                                        d.wb_bound, d.owner, d.flags, d.epoch, d.timeout_flag, st->pipe + 1, chain));
-        } else {
-            STEP_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
-                                         st->pipe + 1, chain));
-        }
-        SGCN_CUDA(cudaEventRecord(st->ev_rest[k % R], chain));
-        // ---- copy: the pass's aggregated rows to pinned host memory (both aggregate kernels done) ----
-        if (out_host) {
-            SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_full[k % R], 0));
-            SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_fwd[k % R], 0));
-            SGCN_CUDA(cudaMemcpy2DAsync(out_host + (int64_t)k * B * width, sizeof(float) * (size_t)width, out_r,
-                                        sizeof(float) * (size_t)d.ld_out, sizeof(float) * (size_t)width, (size_t)B,
-                                        cudaMemcpyDeviceToHost, copy));
-            SGCN_CUDA(cudaEventRecord(st->ev_d2h[k % R], copy));
-        }
-    }
-    SGCN_CUDA(cudaEventRecord(st->ev_side_end, side));
-    SGCN_CUDA(cudaEventRecord(st->ev_samp_end, samp));
-    SGCN_CUDA(cudaEventRecord(st->ev_pre_end, pre));
-    if (out_host) SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_d2h[(n - 1) % R], 0));
-    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_rest[(n - 1) % R], 0));
-    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
-    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));
-    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_pre_end, 0));
     return SGCN_OK;
 }
 
@@ -726,6 +576,191 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
     SGCN_CUDA(cudaEventRecord(st->ev_zero0, chain));
     if (out_host) SGCN_CUDA(cudaStreamWaitEvent(user, st->t_d2h[(n - 1) % R], 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->t_rest[(n - 1) % R], 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_zero0, 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));
+    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_pre_end, 0));
+    return SGCN_OK;
+}
+
+// ---- persistent form of the trains schedule (single GPU, CV / CVD) ------------------------------------------
+// Same passes, same arithmetic as sgcn_step_run_trains with the write-back off the chain, but the chain is ONE
+// kernel: sgcn_full_history_mean_passes keeps its thread blocks resident for all n passes and every dependency
+// that crossed a kernel boundary on the chain is a device-side counter instead (flags, see the header):
+//   chain : flags_reset -> full_mean_persistent (passes 0 .. n-1, waits on the counters below)
+//   samp  : expand_train(c) -> flags[TRAINS] = c + 1
+//   pre   : [gate k-2, sampled k-2, rows k-2 on the host, write-back k-3] gather(k) + dX init + zero out(k)
+//           -> flags[PRE] = k + 1
+//   side  : [pre k] sampled fwd+bwd(k) -> gate: flags[FULL + k] == blocks -> write-back(k) -> flags[WB] = k + 1
+//   copy  : [gate k, sampled k] rows of pass k -> pinned host memory
+// Every wait is on work submitted EARLIER by the host, so the schedule cannot deadlock whatever the hardware
+// queues do with the order; every spin is bounded (flags[3] != 0 afterwards: a counter never arrived).
+int sgcn_step_run_persistent(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
+                             int32_t first_train, void* stream) {
+    SGCN_REQUIRE(st && n >= 0 && (n == 0 || ids) && first_train >= 0, "step_run_persistent: bad argument");
+    if (n == 0) return SGCN_OK;
+    const sgcn_step_desc& d = st->d;
+    const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0;
+    if (st->train <= 0 || !cv || d.world > 1 || d.x0_rows > 4096 || d.batch > 4096) {
+        set_error("step_run_persistent: single GPU, CV / CVD, at most 4096 rows per write-back, and a sampler that "
+                  "can sample trains of batches; use sgcn_step_run_trains");
+        return SGCN_ESTATE;
+    }
+    SGCN_REQUIRE(d.x0_alt[0] && d.x0_alt[1] && d.dx_alt, "step_run_persistent: desc.x0_alt / dx_alt are required");
+    const int B = d.batch, H = d.hidden;
+    const int width = H * (concat ? 2 : 1);
+    constexpr int kChunk = 64;                     // passes per persistent launch
+    if (n > kChunk) {                              // longer runs: one persistent launch after the other
+        for (int k0 = 0; k0 < n; k0 += kChunk) {
+            const int len = std::min(kChunk, n - k0);
+            STEP_TRY(sgcn_step_run_persistent(st, ids + (int64_t)k0 * B, ids_on_host, len,
+                                              out_host ? out_host + (int64_t)k0 * B * width : nullptr,
+                                              k0 == 0 ? first_train : std::min<int>(first_train > 0 ? first_train : st->train, 4),
+                                              stream));
+        }
+        return SGCN_OK;
+    }
+    sgcn_sampler* smp = st->sampler;
+    const int R = sgcn_step::kRing2, T = st->train;
+    cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp, pre = st->pre,
+                 copy = st->copy;
+    float* x0b[3] = {d.x0, d.x0_alt[0], d.x0_alt[1]};
+    float* dxb[2] = {d.dx, d.dx_alt};
+    auto nb = [&](float* base) { return base + (concat ? H : 0); };
+    int32_t* F = st->flags;
+    enum { F_TRAINS = 0, F_PRE = 1, F_WB = 2, F_ERROR = 3, F_FULL = 8 };
+
+    const int T0 = first_train > 0 ? std::min<int>(first_train, T) : T;
+    auto tb = [&](int c) { return c <= 0 ? 0 : std::min(n, T0 + (c - 1) * T); };
+    const int n_trains = n <= T0 ? 1 : 1 + (n - T0 + T - 1) / T;
+    auto train_of = [&](int k) { return k < T0 ? 0 : 1 + (k - T0) / T; };
+    auto set_of = [&](int k) { const int c = train_of(k); return (c & 1) * T + (k - tb(c)); };
+    auto ids_of = [&](int c) -> const int32_t* {
+        return ids_on_host ? st->ids_stage[c & 1] : ids + (int64_t)tb(c) * B;
+    };
+    PdlOff plain;                                  // no programmatic launches: the counters carry the order
+
+    SGCN_CUDA(cudaEventRecord(st->ev_begin, user));
+    SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_begin, 0));
+    STEP_TRY(sgcn_flags_reset(F, 8 + 64, chain));
+    SGCN_CUDA(cudaEventRecord(st->ev_zero0, chain));
+    for (cudaStream_t s : {side, samp, pre}) SGCN_CUDA(cudaStreamWaitEvent(s, st->ev_zero0, 0));
+    if (out_host) SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_zero0, 0));
+
+    // ---- chain: the persistent full-neighbour mean over all n passes ----
+    int n_blocks = 0;
+    {
+        sgcn_full_pass passes[kChunk];
+        for (int k = 0; k < n; ++k) {
+            const sgcn_step::Lv& v = st->tlv[(size_t)set_of(k)];
+            float* out_r = d.out[k & 1];
+            float* outmu_r = d.out_mu[k & 1];
+            sgcn_full_pass& p = passes[k];
+            p.nodes = v.field; p.rowptr_f = v.rowptr_f; p.n_out_dev = v.meta + 0;
+            p.y0 = cvd ? nb(outmu_r) : nb(out_r);
+            p.y1 = cvd ? nb(out_r) : nullptr;
+            p.ov_ids = nullptr; p.ov_n_dev = nullptr; p.ov_rows = nullptr;
+            if (k >= 1) {
+                const sgcn_step::Lv& pv = st->tlv[(size_t)set_of(k - 1)];
+                p.ov_ids = pv.field; p.ov_n_dev = pv.meta + 1;
+                p.ov_rows = x0b[(k - 1) % 3] + (cvd ? H : 0);
+            }
+            p.train = train_of(k); p.pad = 0;
+        }
+        STEP_TRY(sgcn_full_history_mean_passes(passes, n, B, st->adj_p, st->adj_i, st->adj_w, d.history, d.ld_hist, H,
+                                               d.ld_out, d.ld_out, d.x0_rows, d.ld_x0, F, &n_blocks, chain));
+    }
+
+    auto issue_train = [&](int c) -> int {
+        const int len = tb(c + 1) - tb(c);
+        if (c >= 2) SGCN_CUDA(cudaStreamWaitEvent(samp, st->t_rest[(tb(c - 1) - 1) % R], 0));
+        if (ids_on_host)
+            SGCN_CUDA(cudaMemcpyAsync(st->ids_stage[c & 1], ids + (int64_t)tb(c) * B, sizeof(int32_t) * (size_t)len * B,
+                                      cudaMemcpyHostToDevice, samp));
+        STEP_TRY(sgcn_sampler_expand_train(smp, ids_of(c), len, (c & 1) * T, c >= 1 ? ids_of(c - 1) : nullptr,
+                                           c >= 1 ? (tb(c) - tb(c - 1)) * B : 0, samp));
+        STEP_TRY(sgcn_flag_set(F + F_TRAINS, c + 1, samp));
+        SGCN_CUDA(cudaEventRecord(st->t_train[c % 4], samp));
+        return SGCN_OK;
+    };
+    auto ahead = [&](int k) -> int {
+        const sgcn_step::Lv& v = st->tlv[(size_t)set_of(k)];
+        const int r = k & 1;
+        SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_train[train_of(k) % 4], 0));
+        if (k >= 2) {     // out / dx copy r: pass k-2 is complete (gate) and its rows have left for the host
+            SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_full[(k - 2) % R], 0));      // = after the gate of pass k-2
+            SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_fwd[(k - 2) % R], 0));
+            if (out_host) SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_d2h[(k - 2) % R], 0));
+        }
+        if (k >= 3) SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_rest[(k - 3) % R], 0));
+        STEP_TRY(sgcn_gather_pad_pair(d.features, d.ld_feat, v.field, d.x0_rows, v.meta + 1, d.feat_dim, x0b[k % 3], d.ld_x0,
+                                      concat ? d.d_out : nullptr, d.ld_dout, concat ? B : 0,
+                                      concat ? v.meta + 0 : nullptr, d.x0_rows, H, dxb[r], d.ld_dx,
+                                      nullptr, 0, 0, nullptr, B, H, nb(d.out[r]), d.ld_out, pre));
+        if (cvd) STEP_TRY(sgcn_copy_rows_pad(nullptr, 0, 0, nullptr, B, H, nb(d.out_mu[r]), d.ld_out, pre));
+        STEP_TRY(sgcn_flag_set(F + F_PRE, k + 1, pre));
+        SGCN_CUDA(cudaEventRecord(st->t_pre[k % R], pre));
+        return SGCN_OK;
+    };
+
+    STEP_TRY(sgcn_sampler_set_stream_async(smp, samp));
+    for (int slot = 0; slot < 3; ++slot) {
+        STEP_TRY(sgcn_sampler_set_slot(smp, slot));
+        STEP_TRY(sgcn_sampler_start_batch_device(smp, 0, nullptr));
+    }
+    STEP_TRY(issue_train(0));
+    if (n_trains > 1) STEP_TRY(issue_train(1));
+    STEP_TRY(ahead(0));
+
+    for (int k = 0; k < n; ++k) {
+        const int r = k & 1, c = train_of(k);
+        const sgcn_step::Lv& v = st->tlv[(size_t)set_of(k)];
+        const int32_t* n_out_dev = v.meta + 0;
+        const int32_t* n_in_dev = v.meta + 1;
+        float* out_r = d.out[r];
+        float* outmu_r = d.out_mu[r];
+        const float* x = x0b[k % 3];
+        const float* mu = x + H;
+        const float* new_hist = cvd ? mu : x;
+        const float* d_nb = d.d_out + (concat ? H : 0);
+
+        if (k + 1 < n) STEP_TRY(ahead(k + 1));
+        // ---- side: sampled aggregate + backward (history as of write-back k-1: stream order) ----
+        SGCN_CUDA(cudaStreamWaitEvent(side, st->t_pre[k % R], 0));
+        if (!cvd) {
+            STEP_TRY(sgcn_cv_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, B, n_out_dev, x, d.ld_x0, d.history,
+                                             d.ld_hist, H, nb(out_r), d.ld_out, concat ? out_r : nullptr, d.ld_out, 1,
+                                             d_nb, d.ld_dout, dxb[r], d.ld_dx, side));
+        } else {
+            STEP_TRY(sgcn_cvd_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, v.scales, B, n_out_dev, x, d.ld_x0,
+                                              mu, d.ld_x0, d.history, d.ld_hist, H, nb(out_r), d.ld_out,
+                                              nb(outmu_r), d.ld_out, concat ? out_r : nullptr, d.ld_out,
+                                              concat ? outmu_r : nullptr, d.ld_out, 1, d_nb, d.ld_dout, dxb[r],
+                                              d.ld_dx, side));
+        }
+        SGCN_CUDA(cudaEventRecord(st->t_fwd[k % R], side));
+        // ---- gate: every block of the persistent kernel has finished pass k ----
+        STEP_TRY(sgcn_flag_gate(F + F_FULL + k, n_blocks, F + F_ERROR, side));
+        SGCN_CUDA(cudaEventRecord(st->t_full[k % R], side));
+        // ---- write-back (the next pass reads these rows through the override until it has landed) ----
+        STEP_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
+                                     st->pipe + 1, side));
+        STEP_TRY(sgcn_flag_set(F + F_WB, k + 1, side));
+        SGCN_CUDA(cudaEventRecord(st->t_rest[k % R], side));
+        if (out_host) {
+            SGCN_CUDA(cudaStreamWaitEvent(copy, st->t_full[k % R], 0));
+            SGCN_CUDA(cudaMemcpy2DAsync(out_host + (int64_t)k * B * width, sizeof(float) * (size_t)width, out_r,
+                                        sizeof(float) * (size_t)d.ld_out, sizeof(float) * (size_t)width, (size_t)B,
+                                        cudaMemcpyDeviceToHost, copy));
+            SGCN_CUDA(cudaEventRecord(st->t_d2h[k % R], copy));
+        }
+        if (k + 1 == tb(c + 1) && c + 2 < n_trains) STEP_TRY(issue_train(c + 2));
+    }
+    SGCN_CUDA(cudaEventRecord(st->ev_side_end, side));
+    SGCN_CUDA(cudaEventRecord(st->ev_samp_end, samp));
+    SGCN_CUDA(cudaEventRecord(st->ev_pre_end, pre));
+    SGCN_CUDA(cudaEventRecord(st->ev_zero0, chain));
+    if (out_host) SGCN_CUDA(cudaStreamWaitEvent(user, st->t_d2h[(n - 1) % R], 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_zero0, 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));

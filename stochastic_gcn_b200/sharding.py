@@ -344,10 +344,6 @@ class ShardedHotPathStep(HotPathStep):
         self._sharded_only_trains("run_native")
         return super().run_native(*a, **k)
 
-    def run_ahead(self, *a, **k):
-        self._sharded_only_trains("run_ahead")
-        return super().run_ahead(*a, **k)
-
     def time_dominant_kernel(self, batches):
         if self.tables == "sharded":
             return None

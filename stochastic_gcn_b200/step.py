@@ -82,6 +82,7 @@ class HotPathStep:
         self._last_slot = 0
         self.train = 16                # batches sampled per launch by the trains schedule (run_trains)
         self.overlap_write_back = False  # trains schedule: write-back off the chain (row override in the next mean)
+        self.persistent = False        # trains schedule with ONE persistent full-mean launch per run (single GPU, CV / CVD)
         self._trains = None            # captured graphs of the trains schedule
         self._last_x0 = self._last_dx = None
         self._s_b = torch.cuda.Stream(device=self.dev)      # side branch of the pass
@@ -555,8 +556,7 @@ class HotPathStep:
         self.sampler._stream = None                    # the driver left the sampler on its own stream
         return self.out
 
-    # -- "gather ahead" schedule, eager or as CUDA graphs (csrc/step.cu:sgcn_step_run_ahead; parity-tested on
-    #    hardware, not timed yet) ---------------------------------------------------------------------------
+    # -- native handle of the C++ step drivers ---------------------------------------------------------------
     def _native_handle(self):
         import ctypes as C
         if getattr(self, "_native_h", None) is None:
@@ -566,95 +566,6 @@ class HotPathStep:
             _lib.check(_lib.load().sgcn_step_create(C.byref(h), self.sampler._h, C.byref(desc)))
             self._native_h, self._native_desc = h, desc
         return self._native_h
-
-    def run_ahead(self, table, out_host=None):
-        """n passes through sgcn_step_run_ahead on the current stream (plain stream launches).
-        ``table``: contiguous int32 [n, B] ids on the GPU or in PINNED host memory; ``out_host``: optional
-        pinned float32 [n, B, width] tensor receiving every pass's aggregated rows."""
-        if getattr(self, "_ahead_bufs", None) is None:
-            self._ahead_bufs = (torch.zeros_like(self.x0), torch.zeros_like(self.dx))
-        x0_alt, dx_alt = self._ahead_bufs
-        n = int(table.shape[0])
-        on_host = not table.is_cuda
-        if on_host and not table.is_pinned():
-            raise ValueError("host id tables must be pinned")
-        if out_host is not None and not (out_host.is_pinned() and out_host.is_contiguous()
-                                         and tuple(out_host.shape) == (n, self.B, self.outs[0].shape[1])):
-            raise ValueError("out_host must be a pinned contiguous [n, B, width] float32 tensor")
-        self._ahead_keep = (table, out_host)           # borrowed by the driver until the run completes
-        _lib.check(_lib.load().sgcn_step_run_ahead(self._native_handle(), _lib.ptr(x0_alt), _lib.ptr(dx_alt),
-                                                   _lib.ptr(table), int(on_host), n,
-                                                   _lib.ptr(out_host) if out_host is not None else None,
-                                                   _lib.stream_ptr()))
-        self._last_slot, self._last_sampler_slot = (n - 1) & 1, (n - 1) % 3
-        self.sampler._stream = None
-        return self.out
-
-    def capture_ahead(self, warm_table, steps_per_graph=32, host_io=False):
-        """Capture S passes of the gather-ahead schedule into CUDA graphs over fixed [S, B] id tables (five
-        streams whatever S is, six with host IO).  ``warm_table``: [S, B] device ids for the eager warm-up run.
-        host_io=False: ONE graph over a device id table.  host_io=True: TWO graphs, each bound to its own
-        pinned staging set (ids in, every pass's rows out), so that the host can fill / drain one set while
-        the GPU runs the other (``replay_ahead`` alternates them)."""
-        S = int(steps_per_graph)
-        if tuple(warm_table.shape) != (S, self.B):
-            raise ValueError("warm_table must be [steps_per_graph, batch]")
-        tab = warm_table.to(torch.int32).contiguous().clone()
-        self.run_ahead(tab)                                       # sizes everything, warms the allocators
-        torch.cuda.synchronize(self.dev)
-        cap = torch.cuda.Stream(device=self.dev)
-        if not host_io:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=cap):
-                self.run_ahead(tab)
-            self._ahead = {"S": S, "tab": tab, "graph": g, "host_io": False}
-            return g
-        width = self.outs[0].shape[1]
-        pin_tab = [torch.zeros((S, self.B), dtype=torch.int32).pin_memory() for _ in range(2)]
-        pin_out = [torch.empty((S, self.B, width), dtype=torch.float32).pin_memory() for _ in range(2)]
-        graphs = []
-        for p in range(2):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=cap):
-                self.run_ahead(pin_tab[p], out_host=pin_out[p])
-            graphs.append(g)
-        self._ahead = {"S": S, "pin_tab": pin_tab, "pin_out": pin_out, "graphs": graphs, "host_io": True,
-                       "done": [None, None]}
-        return graphs
-
-    def replay_ahead(self, table, on_chunk=None):
-        """n passes: per chunk of S one id-table copy and one graph launch; the n mod S left-over passes run
-        through run_ahead (plain stream launches).  Captured with host_io: ``table`` is a HOST [n, B] id
-        table; ``on_chunk(first_pass, count, rows, done_event)`` is called after a chunk has been enqueued
-        -- once ``done_event`` has completed, ``rows`` ([S, B, width], pinned) holds the rows of those passes;
-        that staging set is refilled two chunks later, so consume it one chunk behind the launches."""
-        a = self._ahead
-        S = a["S"]
-        n = int(table.shape[0])
-        full = n // S
-        if not a["host_io"]:
-            for c in range(full):
-                a["tab"].copy_(table[c * S:(c + 1) * S], non_blocking=True)
-                a["graph"].replay()
-            self._last_slot, self._last_sampler_slot = (S - 1) & 1, (S - 1) % 3
-            if n % S:
-                self.run_ahead(table[full * S:].contiguous())
-            return self.out
-        if n % S:
-            raise ValueError("with host IO the number of passes must be a multiple of steps_per_graph")
-        for c in range(full):
-            p = c & 1
-            if a["done"][p] is not None:
-                a["done"][p].synchronize()                       # chunk c-2 has left this staging set
-            a["pin_tab"][p].copy_(table[c * S:(c + 1) * S])      # host -> pinned host
-            a["graphs"][p].replay()
-            ev = torch.cuda.Event()
-            ev.record()
-            a["done"][p] = ev
-            if on_chunk is not None:
-                on_chunk(c * S, S, a["pin_out"][p], ev)
-        self._last_slot, self._last_sampler_slot = (S - 1) & 1, (S - 1) % 3
-        return self.out
 
     # -- trains schedule (csrc/step.cu:sgcn_step_run_trains): the schedule bench.py times ------------------
     def _check_io(self, table, out_host):
@@ -693,9 +604,10 @@ class HotPathStep:
             return self.out
         h = self._native_handle()
         self._trains_keep = (table, out_host)          # borrowed by the driver until the run completes
-        _lib.check(_lib.load().sgcn_step_run_trains(h, _lib.ptr(table), int(not table.is_cuda), n,
-                                                    _lib.ptr(out_host) if out_host is not None else None,
-                                                    int(first_train), _lib.stream_ptr()))
+        lib = _lib.load()
+        fn = lib.sgcn_step_run_persistent if (self.persistent and self.mode != "ns") else lib.sgcn_step_run_trains
+        _lib.check(fn(h, _lib.ptr(table), int(not table.is_cuda), n,
+                      _lib.ptr(out_host) if out_host is not None else None, int(first_train), _lib.stream_ptr()))
         self._trains_done(n, first_train)
         return self.out
 
@@ -759,6 +671,16 @@ class HotPathStep:
                 on_chunk(c * n, n, t["pin_out"][p], ev)
         self._trains_done(n, t["first_train"])
         return self.out
+
+    def check_flags(self):
+        """Raise if a device-side wait of the persistent schedule timed out (synchronises)."""
+        import ctypes as C
+        if getattr(self, "_native_h", None) is None:
+            return
+        bad = C.c_int32()
+        _lib.check(_lib.load().sgcn_step_status(self._native_h, C.byref(bad)))
+        if bad.value:
+            raise _lib.SgcnError(_lib.SGCN_EDATA, "a device-side wait of the persistent schedule timed out")
 
     @property
     def last_x0(self):

@@ -22,7 +22,6 @@ def main():
     transport, mode = sys.argv[1], sys.argv[2]
     use_graph = len(sys.argv) > 3 and sys.argv[3] == "graph"
     pipelined = len(sys.argv) > 3 and sys.argv[3] == "pipelined"
-    ahead = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] in ("ahead", "ahead-graph") else None
     trains = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] in ("trains", "trains-graph") else None
     tables = sys.argv[4] if len(sys.argv) > 4 else "replicated"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -30,7 +29,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     deg = 2 if mode == "cv" else 1
-    D, B, steps, seed = 32, 24, (8 if pipelined else 12 if ahead else 15 if trains else 5), 3
+    D, B, steps, seed = 32, 24, (8 if pipelined else 15 if trains else 5), 3
     g = graphs.powerlaw_graph(1500, 60_000, seed=4, device=dev, max_degree=300)
     gen = torch.Generator(device=dev).manual_seed(0)
     feats = torch.randn((g.n, 80), generator=gen, device=dev)
@@ -98,20 +97,6 @@ def main():
         out = step.out.cpu().numpy()
         err = np.abs(out - want_out[-1]).max() / max(np.abs(want_out[-1]).max(), 1e-30)
         assert err < 1e-4, "rank %d: last pipelined out differs by %g" % (rank, err)
-        steps = 0
-    if ahead:
-        # gather-ahead schedule (sgcn_step_run_ahead) with the peer exchange: eager, or 4 passes per CUDA graph
-        table = torch.from_numpy(np.stack(batches[rank])).to(dev)
-        if ahead == "ahead":
-            step.run_ahead(table)
-        else:
-            step.capture_ahead(table[:4], steps_per_graph=4)      # eager warm-up run = passes 0 .. 3
-            step.replay_ahead(table[4:])
-        torch.cuda.synchronize()
-        step.check_exchange()
-        out = step.out.cpu().numpy()
-        err = np.abs(out - want_out[-1]).max() / max(np.abs(want_out[-1]).max(), 1e-30)
-        assert err < 1e-4, "rank %d: last gather-ahead out differs by %g" % (rank, err)
         steps = 0
     if trains:
         # trains schedule (sgcn_step_run_trains) with the peer exchange: eager with every pass's rows read back,

@@ -27,11 +27,10 @@ def test_two_rank_pass_matches_oracle(transport, mode, graph):
 
 
 @pytest.mark.parametrize("form,mode,tables", [("trains", "cv", "replicated"), ("trains-graph", "cv", "replicated"),
-                                              ("trains", "cvd", "replicated"), ("ahead", "cv", "replicated"),
-                                              ("ahead-graph", "cv", "replicated"), ("trains", "cv", "sharded"),
+                                              ("trains", "cvd", "replicated"), ("trains", "cv", "sharded"),
                                               ("trains-graph", "cvd", "sharded")])
 def test_all_ranks_multi_pass_schedules_match_oracle(form, mode, tables):
-    """the trains schedule (bench default) and the gather-ahead schedule on EVERY GPU of the box (2, 4 or 8 ranks)"""
+    """the trains schedule (bench default), replicated and sharded tables, on EVERY GPU of the box (2, 4 or 8 ranks)"""
     world = torch.cuda.device_count()
     if world < 2:
         pytest.skip("needs 2 GPUs")

@@ -13,7 +13,7 @@ from tests.test_step_gpu import close, oracle_step
 pytestmark = pytest.mark.gpu
 
 
-def setup(mode, deg, norm, n_batches, train, overlap=True, share=True, seed=4):
+def setup(mode, deg, norm, n_batches, train, overlap=True, share=True, seed=4, persistent=False):
     from stochastic_gcn_b200 import graphs
     from stochastic_gcn_b200.step import HotPathStep
     g = graphs.powerlaw_graph(3000, 120_000, seed=seed, device="cuda", max_degree=600)
@@ -21,7 +21,7 @@ def setup(mode, deg, norm, n_batches, train, overlap=True, share=True, seed=4):
     gen = torch.Generator(device="cuda").manual_seed(0)
     feats = torch.randn((g.n, 80), generator=gen, device="cuda")
     step = HotPathStep(g, feats, D, B, deg, mode=mode, normalization=norm, seed=5)
-    step.train, step.overlap_write_back = train, overlap
+    step.train, step.overlap_write_back, step.persistent = train, overlap, persistent
     step.history.normal_(generator=gen)
     step.d_out.normal_(generator=gen)
     o = native.OracleSampler(g.data.cpu().numpy(), g.indices.cpu().numpy(), g.indptr.cpu().numpy(), cv=mode != "ns")
@@ -91,6 +91,57 @@ def test_pinned_host_ids_and_a_second_run_continue_the_state():
     step.run_trains(host_tab[11:], out_host=rows[11:], first_train=1)
     torch.cuda.synchronize()
     check_run(step, o, mode, deg, norm, feats, table, D, [r.numpy() for r in rows])
+    assert np.array_equal(step.history.cpu().numpy(), check_run.hist)
+
+
+@pytest.mark.parametrize("mode,deg,norm", [("cv", 2, "graphsage"), ("cvd", 1, "graphsage"), ("cv", 1, "gcn")])
+def test_persistent_eager_matches_oracle(mode, deg, norm):
+    """sgcn_step_run_persistent: one full-neighbour-mean launch for the whole run, device-side counters"""
+    n = 23
+    g, step, o, feats, table, D = setup(mode, deg, norm, n, train=4, persistent=True)
+    check_run.hist = step.history.cpu().numpy().copy()
+    width = step.outs[0].shape[1]
+    rows = torch.empty((n, step.B, width), dtype=torch.float32).pin_memory()
+    step.run_trains(table, out_host=rows, first_train=2)
+    torch.cuda.synchronize()
+    step.check_flags()
+    oh, om, dx, s = check_run(step, o, mode, deg, norm, feats, table, D, [r.numpy() for r in rows])
+    z = step.sizes()
+    close(step.out.cpu().numpy(), oh, "last rows on the device")
+    close(step.last_dx.cpu().numpy()[:z["n_in"]], dx, "last dx")
+    assert np.array_equal(step.history.cpu().numpy(), check_run.hist), "history after the run"
+    assert np.array_equal(step.sampler.host("adj_i", step.sampler.num_edges), o.vec("adj_i")), "permuted adjacency"
+
+
+@pytest.mark.parametrize("host_io", [False, True])
+def test_persistent_captured_matches_oracle(host_io):
+    mode, deg, S = "cv", 2, 6
+    g, step, o, feats, table, D = setup(mode, deg, "graphsage", 4 * S, train=4, persistent=True)
+    check_run.hist = step.history.cpu().numpy().copy()
+    step.capture_trains(S, table[:S], host_io=host_io, first_train=2)
+    got, pending = {}, []
+
+    def drain():
+        f0, c0, r0, e0 = pending.pop()
+        e0.synchronize()
+        for j in range(c0):
+            got[f0 + j] = r0[j].clone().numpy()
+
+    def on_chunk(first, count, rows, done):
+        if pending:
+            drain()
+        pending.append((first, count, rows, done))
+
+    if host_io:
+        step.replay_trains(table[S:].cpu().pin_memory(), on_chunk=on_chunk)
+        drain()
+    else:
+        step.replay_trains(table[S:])
+    torch.cuda.synchronize()
+    step.check_flags()
+    rows = [None] * S + [got.get(i) for i in range(3 * S)]
+    oh, om, dx, s = check_run(step, o, mode, deg, "graphsage", feats, table, D, rows)
+    close(step.out.cpu().numpy(), oh, "last rows")
     assert np.array_equal(step.history.cpu().numpy(), check_run.hist)
 
 

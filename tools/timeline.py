@@ -52,6 +52,7 @@ def main():
         step.capture_pipelined(batches[0], batches[1], steps_per_graph=n_steps)
     if mode == "trains":                                             # the bench's schedule, one graph of n_steps
         step.overlap_write_back = os.environ.get("OVERLAP", "1") != "0"
+        step.persistent = os.environ.get("PERSISTENT", "0") == "1"
         step.train = int(os.environ.get("TRAIN", "16"))
         ft = int(os.environ.get("FIRST_TRAIN", "4"))
         step.capture_trains(n_steps, torch.stack(batches[:n_steps]), first_train=ft)
@@ -60,17 +61,8 @@ def main():
         step._trains["tab"].copy_(torch.stack(batches[30:30 + n_steps]))
         trace.copy_(init); torch.cuda.synchronize()
         step._trains["graph"].replay(); torch.cuda.synchronize()
-        dump_events(trace, n_steps, "one trains graph (train %d, first %d, overlap %s)" % (step.train, ft, step.overlap_write_back))
-        _lib.load().sgcn_trace_set(None)
-        return
-    if mode == "ahead":                                              # gather-ahead schedule, one graph of n_steps
-        step.capture_ahead(torch.stack(batches[:n_steps]), steps_per_graph=n_steps)
-        step.replay_ahead(torch.stack(batches[12:12 + n_steps]))
-        torch.cuda.synchronize()
-        step._ahead["tab"].copy_(torch.stack(batches[30:30 + n_steps]))
-        trace.copy_(init); torch.cuda.synchronize()
-        step._ahead["graph"].replay(); torch.cuda.synchronize()
-        dump_events(trace, n_steps, "one gather-ahead graph")
+        dump_events(trace, n_steps, "one trains graph (train %d, first %d, overlap %s, persistent %s)" % (
+            step.train, ft, step.overlap_write_back, step.persistent))
         _lib.load().sgcn_trace_set(None)
         return
     for b in batches[2:12]:
