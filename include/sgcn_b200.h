@@ -573,6 +573,14 @@ int sgcn_full_history_mean_passes(const sgcn_full_pass* passes /*HOST*/, int32_t
                                   const float* hist, int64_t ld_h, int32_t D, int64_t ld_y0, int64_t ld_y1,
                                   int32_t ov_bound, int64_t ld_ov, int32_t* flags, int32_t* n_blocks /*HOST out*/,
                                   void* stream);
+/* sgcn_history_update behind a device-side gate (the persistent step schedule): the stores wait until *gate >=
+ * want (bounded: *err), the rows are loaded before that; the last thread block raises *done_flag to done_value
+ * (atomic max) and block 0 adds 1 to *pipe_done (optional: the sampler's consumer counter) once the gate opens.
+ * counter: device int32 scratch, 0 on entry and on exit.  Rows must be 16-byte aligned multiples of 4 floats. */
+int sgcn_history_update_gated(float* hist, int64_t ld_h, const int32_t* idx, int32_t n, const int32_t* n_dev,
+                              const float* rows, int64_t ld_rows, int32_t D, const int32_t* gate, int32_t want,
+                              int32_t* err, int32_t* done_flag, int32_t done_value, int32_t* counter,
+                              int32_t* pipe_done, void* stream);
 /* stream-ordered helpers for such device-side counters: zero n of them; raise one to `value` (atomic max) once
  * everything before it in the stream has finished; hold the stream until *flag >= want (bounded: sets *err) */
 int sgcn_flags_reset(int32_t* flags, int32_t n, void* stream);

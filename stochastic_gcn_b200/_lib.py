@@ -105,6 +105,8 @@ SIGNATURES = {
     "sgcn_step_run_persistent": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp]),
     "sgcn_full_history_mean_passes": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i32, _i64,
                                              _vp, _vp, _vp]),
+    "sgcn_history_update_gated": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _vp,
+                                         _vp, _vp]),
     "sgcn_flags_reset": (_i32, [_vp, _i32, _vp]),
     "sgcn_flag_set": (_i32, [_vp, _i32, _vp]),
     "sgcn_flag_gate": (_i32, [_vp, _i32, _vp, _vp]),

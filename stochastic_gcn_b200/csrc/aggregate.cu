@@ -663,18 +663,6 @@ constexpr int kMaxPasses = 64;
 enum { F_TRAINS = 0, F_PRE = 1, F_WB = 2, F_ERROR = 3, F_FULL = 8 };     // flags[F_FULL + k]: blocks done with pass k
 struct PassList { PassDesc p[kMaxPasses]; int n; };
 
-__device__ __forceinline__ bool spin_until_ge(const int32_t* ctr, int want, int32_t* err) {
-    long long spins = 0;
-    while ((int)ld_acquire_u32((const unsigned*)ctr) < want) {
-        if (++spins > 8000000LL) {         // ~2 s
-            atomicExch(err, 1);
-            return false;
-        }
-        __nanosleep(50);
-    }
-    return true;
-}
-
 template <typename V, int LPR, int VPL>
 __global__ void __maxnreg__(96)
 full_mean_persistent_kernel(const __grid_constant__ FullArgs a, const __grid_constant__ PassList passes, int32_t* flags) {

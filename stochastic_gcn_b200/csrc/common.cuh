@@ -167,6 +167,21 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// bounded wait for a device-side counter (the persistent step schedule): false + *err = 1 after ~2 s, and at
+// once when another wait has already given up
+__device__ __forceinline__ bool spin_until_ge(const int32_t* ctr, int want, int32_t* err) {
+    long long spins = 0;
+    while ((int)ld_acquire_u32((const unsigned*)ctr) < want) {
+        if (*(volatile int32_t*)err != 0) return false;
+        if (++spins > 8000000LL) {
+            atomicExch(err, 1);
+            return false;
+        }
+        __nanosleep(50);
+    }
+    return true;
+}
+
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -739,13 +739,14 @@ int sgcn_step_run_persistent(sgcn_step* st, const int32_t* ids, int32_t ids_on_h
                                               d.ld_dx, side));
         }
         SGCN_CUDA(cudaEventRecord(st->t_fwd[k % R], side));
-        // ---- gate: every block of the persistent kernel has finished pass k ----
-        STEP_TRY(sgcn_flag_gate(F + F_FULL + k, n_blocks, F + F_ERROR, side));
+        // ---- write-back, gated on the device: every block of the persistent kernel has finished pass k (the
+        //      next pass reads these rows through the override until they have landed).  One launch: a separate
+        //      gate + write-back + signal made the side branch (4 dependent launches per pass, 4-5 us each under
+        //      load) the critical path: 29 us per pass (profiles/r02_timeline_persistent_first.txt) ----
+        STEP_TRY(sgcn_history_update_gated(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
+                                           F + F_FULL + k, n_blocks, F + F_ERROR, F + F_WB, k + 1, F + 4, st->pipe + 1,
+                                           side));
         SGCN_CUDA(cudaEventRecord(st->t_full[k % R], side));
-        // ---- write-back (the next pass reads these rows through the override until it has landed) ----
-        STEP_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
-                                     st->pipe + 1, side));
-        STEP_TRY(sgcn_flag_set(F + F_WB, k + 1, side));
         SGCN_CUDA(cudaEventRecord(st->t_rest[k % R], side));
         if (out_host) {
             SGCN_CUDA(cudaStreamWaitEvent(copy, st->t_full[k % R], 0));

@@ -30,7 +30,26 @@ if mode == "early":
         s.mark_consumed(b)
     torch.cuda.synchronize()
 s.expand_train(d1, first_set=4, prev=d0, stream=a)
-if mode != "early":
+if mode == "probe":
+    # does ANY kernel on another stream run while the train's thread block spins?
+    x = torch.zeros(4, device="cuda")
+    ev = torch.cuda.Event()
+    with torch.cuda.stream(b):
+        x.fill_(1.0)
+        ev.record(b)
+    t1_ = time.time()
+    while not ev.query() and time.time() - t1_ < 8:
+        time.sleep(0.001)
+    print("a kernel on stream b finished after %.4f s while the train waits" % (time.time() - t1_))
+    for _ in range(4):
+        s.mark_consumed(b)
+elif mode == "hiprio":
+    c = torch.cuda.Stream(priority=-1)
+    with torch.cuda.stream(c):
+        torch.cuda._sleep(2_000_000)
+    for _ in range(4):
+        s.mark_consumed(c)
+elif mode != "early":
     with torch.cuda.stream(b):
         torch.cuda._sleep(2_000_000)
     for _ in range(4):
