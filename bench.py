@@ -299,8 +299,7 @@ class Rig:
                                     seed=args.seed)
             lo, hi = 0, self.g.n
         self.step.train = args.train
-        self.step.overlap_write_back = args.overlap_write_back
-        self.step.persistent = args.persistent and world == 1
+        self.step.fuse_write_back = not args.no_fuse_write_back
         gen = torch.Generator(device=dev).manual_seed(7)
         self.step.d_out.normal_(generator=gen)
         self.step.history.normal_(generator=gen)      # a warm history table (zero rows would skip reductions)
@@ -560,8 +559,8 @@ def run_ours(args, w):
     value = total_edges / (ms * 1e-3)
     what = {"trains": "CUDA graph(s) of %d passes of the trains schedule: trains of %d batches sampled by one launch a "
                       "train ahead, gather one pass ahead, full-neighbour means back to back%s" % (
-                          S, args.train, " (write-back off the chain: row override)"
-                          if args.overlap_write_back and world == 1 else ""),
+                          S, args.train, " (history write-back in the tail of each mean's launch)"
+                          if not args.no_fuse_write_back and world == 1 and w["mode"] != "ns" else ""),
             "graph": "CUDA graphs of %d steps; batch k+1's sampler (1 CTA) runs beside batch k's aggregate" % S,
             "native": "plain stream launches from C++ on three streams, two batches of sampler lookahead",
             "one-graph-per-step": "one CUDA graph per step, back to back"}[driver]
@@ -644,12 +643,9 @@ def main():
     ap.add_argument("--train", type=int, default=16, help="batches sampled per launch by the trains schedule (2..32)")
     ap.add_argument("--first-train", type=int, default=4,
                     help="length of the first train of a graph (short: smaller start-up bubble)")
-    ap.add_argument("--overlap-write-back", action="store_true",
-                    help="take the history write-back off the critical chain (row override in the next pass's "
-                         "full-neighbour mean); measured slower inside CUDA graphs, see DESIGN section 1")
-    ap.add_argument("--persistent", action="store_true",
-                    help="single GPU, CV / CVD: ONE persistent full-neighbour-mean launch per graph, device-side "
-                         "counters instead of kernel boundaries on the chain (sgcn_step_run_persistent)")
+    ap.add_argument("--no-fuse-write-back", action="store_true",
+                    help="single GPU: the history write-back as a launch of its own on the chain instead of in the "
+                         "tail of the full-neighbour mean (A/B, see DESIGN section 1)")
     ap.add_argument("--eager-trains", action="store_true",
                     help="trains driver as plain stream launches from C++ (no CUDA graphs): A/B of the graph overhead")
     ap.add_argument("--no-also", action="store_true", help="skip the extra keys for the other BASELINE configurations")

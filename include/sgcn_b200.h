@@ -298,9 +298,13 @@ int sgcn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
  *   SGCN_TUNE_TMA_WARPS / _ROWS / _DEPTH  ring shape of variant 1: warps per CTA (1..16), history
  *                           rows per stage (1..32), stages per warp (1..4; clipped to fit 226 KB)
  *   SGCN_TUNE_TMA_GRID      CTAs of variant 1 (default 148 = one per SM; 147 leaves one SM to a kernel
- *                           that runs beside it, e.g. the next batch's sampler) */
+ *                           that runs beside it, e.g. the next batch's sampler)
+ *   SGCN_TUNE_HIST_L2       L2 eviction priority of history-row accesses: 0 = normal, p in 1..100 = evict_last
+ *                           for p % of the accesses (the 119 MB Reddit-shaped table is about the size of L2;
+ *                           everything else the step streams through L2 should not push it out)
+ *   SGCN_TUNE_STREAM_L2     same for the read-once feature rows of the gather: p % evict_first */
 enum { SGCN_TUNE_FULL_VARIANT = 0, SGCN_TUNE_TMA_WARPS = 1, SGCN_TUNE_TMA_ROWS = 2, SGCN_TUNE_TMA_DEPTH = 3,
-       SGCN_TUNE_TMA_GRID = 4, SGCN_TUNE_PDL = 5 };
+       SGCN_TUNE_TMA_GRID = 4, SGCN_TUNE_PDL = 5, SGCN_TUNE_HIST_L2 = 6, SGCN_TUNE_STREAM_L2 = 7 };
 int sgcn_tune_set(int32_t key, int32_t value);
 
 /* ---- det-dropout (mu, var) aggregation: PlainAggregator tuple branch layers.py:238-247 and
@@ -510,9 +514,9 @@ typedef struct {
     int32_t* epoch; int32_t* timeout_flag; int32_t* block_counter; int32_t* owner;
     /* sgcn_step_run_trains only (may be NULL / 0 otherwise): two more copies of x0 and one more of dx (same
      * shapes and strides), the number of batches sampled per launch (2 .. 32, 0 = 16) and whether the
-     * history write-back leaves the critical path (row override in the next pass's full-neighbour mean) */
+     * history write-back rides on the full-neighbour mean's launch (single GPU, CV / CVD) */
     float* x0_alt[2]; float* dx_alt;
-    int32_t train; int32_t overlap_write_back;
+    int32_t train; int32_t fuse_write_back;
     /* ring form of the peer exchange, used by sgcn_step_run_trains when ring > 0 (sgcn_wb_push_ring /
      * sgcn_wb_wait_apply_ring: the rows of pass k are pushed as soon as they are gathered, one pass ahead):
      * ring_dst[k] = rank k's receive base + rank * slot_bytes, ring_recv = this rank's receive base,
@@ -541,77 +545,44 @@ void sgcn_step_destroy(sgcn_step* st);
 int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
                   void* stream);
 
-/* sgcn_full_history_mean with a row override: history rows of the nodes ov_ids[0 .. *ov_n_dev) (distinct,
- * at most ov_bound <= 4096) are read from ov_rows[i, :] (row stride ld_ov) instead of hist -- i.e. the
- * result is what sgcn_history_update(hist, ov_ids, ov_rows) followed by sgcn_full_history_mean would give,
- * without waiting for that write-back (which may run concurrently: it only writes rows this kernel does
- * not read).  Each thread block hashes the id list into shared memory; one probe per neighbour. */
-int sgcn_full_history_mean_ov(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
+/* sgcn_full_history_mean with the pass's history write-back (gcn/models.py:160-166,186-194) fused into its tail:
+ * once EVERY thread block of the launch has consumed its history rows and the pass's sampled aggregate has
+ * consumed its own (counters[2] > counters[3], see sgcn_sampled_done_attach), the last thread blocks to finish
+ * store hist[wb_ids[i], :] = wb_rows[i, :D] for i < min(*wb_n_dev, wb_bound) (ids distinct), then add 1 to
+ * *consumed (optional: the sampler's consumer counter) and to counters[3].  The result is what
+ * sgcn_full_history_mean followed by sgcn_history_update gives, without a second launch on the step's chain.
+ * counters: device int32[8], zeroed by sgcn_wb_counters_reset before the first pass of a run; counters[4] != 0
+ * afterwards = a wait gave up (bounded spins).  Not for row-sharded tables. */
+int sgcn_full_history_mean_wb(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
                               const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
-                              const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
+                              const float* adj_w, float* hist, int64_t ld_h, int32_t D,
                               float* y0, int64_t ld_y0, float* y1, int64_t ld_y1,
-                              const int32_t* ov_ids, const int32_t* ov_n_dev, int32_t ov_bound,
-                              const float* ov_rows, int64_t ld_ov, void* stream);
-
-/* The full-neighbour means of up to 64 consecutive passes in ONE launch (persistent thread blocks; between two
- * launches of the one-pass kernel the GPU idles for 4-7 us inside a CUDA graph).  Pass k starts on the device
- * once flags[0] > passes[k].train (its batch is sampled), flags[1] > k (its output rows are zeroed and pass
- * k-1's rows gathered) and flags[2] >= k - 1 (write-back k-2 has landed; the rows of pass k-1's input field are
- * overridden from ov_rows as in sgcn_full_history_mean_ov); every thread block adds 1 to flags[8 + k] when its
- * part of pass k is in memory.  flags: device int32[8 + 64], zeroed by sgcn_flags_reset before the launch;
- * flags[3] != 0 afterwards = a counter never arrived (bounded spins).  *n_blocks (HOST out) = thread blocks
- * launched = the value flags[8 + k] reaches.  All passes share the adjacency, the history table, widths and
- * strides; n_out_bound = rows per pass (the true count comes from n_out_dev). */
-typedef struct {
-    const int32_t* nodes; const int32_t* rowptr_f; const int32_t* n_out_dev;
-    float* y0; float* y1;
-    const int32_t* ov_ids; const int32_t* ov_n_dev; const float* ov_rows;    /* NULL: no override (first pass) */
-    int32_t train; int32_t pad;
-} sgcn_full_pass;
-int sgcn_full_history_mean_passes(const sgcn_full_pass* passes /*HOST*/, int32_t n, int32_t n_out_bound,
-                                  const int32_t* adj_p, const int32_t* adj_i, const float* adj_w,
-                                  const float* hist, int64_t ld_h, int32_t D, int64_t ld_y0, int64_t ld_y1,
-                                  int32_t ov_bound, int64_t ld_ov, int32_t* flags, int32_t* n_blocks /*HOST out*/,
-                                  void* stream);
-/* sgcn_history_update behind a device-side gate (the persistent step schedule): the stores wait until *gate >=
- * want (bounded: *err), the rows are loaded before that; the last thread block raises *done_flag to done_value
- * (atomic max) and block 0 adds 1 to *pipe_done (optional: the sampler's consumer counter) once the gate opens.
- * counter: device int32 scratch, 0 on entry and on exit.  Rows must be 16-byte aligned multiples of 4 floats. */
-int sgcn_history_update_gated(float* hist, int64_t ld_h, const int32_t* idx, int32_t n, const int32_t* n_dev,
-                              const float* rows, int64_t ld_rows, int32_t D, const int32_t* gate, int32_t want,
-                              int32_t* err, int32_t* done_flag, int32_t done_value, int32_t* counter,
-                              int32_t* pipe_done, void* stream);
-/* stream-ordered helpers for such device-side counters: zero n of them; raise one to `value` (atomic max) once
- * everything before it in the stream has finished; hold the stream until *flag >= want (bounded: sets *err) */
-int sgcn_flags_reset(int32_t* flags, int32_t n, void* stream);
-int sgcn_flag_set(int32_t* flag, int32_t value, void* stream);
-int sgcn_flag_gate(const int32_t* flag, int32_t want, int32_t* err, void* stream);
+                              const int32_t* wb_ids, const int32_t* wb_n_dev, int32_t wb_bound,
+                              const float* wb_rows, int64_t ld_wb, int32_t* counters, int32_t* consumed,
+                              void* stream);
+int sgcn_wb_counters_reset(int32_t* counters, void* stream);
+/* The NEXT sgcn_cv_sampled_fwd[_bwd] / sgcn_cvd_sampled_fwd[_bwd] launch of this host thread adds 1 to
+ * counters[2] when its last thread block has finished (its reads of hist[tgt] are over). */
+int sgcn_sampled_done_attach(int32_t* counters);
 
 /* The schedule bench.py times: n passes with
  *   samp  : trains of `train` batches sampled by ONE launch each (sgcn_sampler_expand_train), one train ahead
  *           of the passes that consume them (first_train: length of the first train, 0 = `train`; a short
  *           first train shortens the start-up bubble)
  *   pre   : gather + dX init + output zeroing of pass k+1 while pass k runs (three x0 copies, two dx copies)
- *   chain : full-neighbour mean(k) back to back with full-neighbour mean(k+1)
- *   side  : write-back(k-1) -> sampled aggregate + backward(k) -> write-back(k) ...
- * With desc.overlap_write_back the full-neighbour mean of pass k+1 does not wait for write-back k: it reads
- * the rows of pass k's input field from that pass's gathered rows (sgcn_full_history_mean_ov), and write-back
- * k only has to land before pass k+2.  Same results as n sequential passes.  ids / ids_on_host / out_host as
+ *   chain : full-neighbour mean(k) -> write-back(k) -> full-neighbour mean(k+1) ...
+ *   side  : [write-back(k-1)] sampled aggregate + backward(k)
+ * With desc.fuse_write_back (single GPU, CV / CVD) the write-back of pass k is carried by the tail of the pass's
+ * own full-neighbour-mean launch (sgcn_full_history_mean_wb): the chain is mean(k) -> mean(k+1) and nothing else.
+ * Same results as n sequential passes.  ids / ids_on_host / out_host as
  * sgcn_step_run; every internal stream forks from and joins `stream` (capturable into a CUDA graph).  Pass k:
  * aggregated rows in desc.out[k & 1], gathered rows in x0 copy k % 3 (desc.x0, x0_alt[0], x0_alt[1]), dX in
  * (k & 1 ? dx_alt : desc.dx), sampler buffer set  ((train index & 1) * train + position in the train). */
 int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
                          int32_t first_train, void* stream);
 
-/* Persistent form of sgcn_step_run_trains (single GPU, CV / CVD, write-back off the chain): the chain is ONE
- * launch of sgcn_full_history_mean_passes for all n passes (longer runs: 64 passes per launch) and the
- * dependencies that crossed kernel boundaries on the chain are device-side counters (sgcn_flag_set /
- * sgcn_flag_gate).  Same arguments, same results, same buffers as sgcn_step_run_trains. */
-int sgcn_step_run_persistent(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
-                             int32_t first_train, void* stream);
-
-/* *timed_out (HOST) != 0: a device-side wait of sgcn_step_run_persistent gave up (bounded spins) since the last
- * run started -- its results are not to be trusted.  Synchronises the device. */
+/* *timed_out (HOST) != 0: a device-side wait of the fused write-back gave up (bounded spins) since the last run
+ * started -- its results are not to be trusted.  Synchronises the device. */
 int sgcn_step_status(sgcn_step* st, int32_t* timed_out);
 
 #ifdef __cplusplus

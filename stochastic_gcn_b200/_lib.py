@@ -102,16 +102,10 @@ SIGNATURES = {
     "sgcn_step_run": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "sgcn_step_run_trains": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp]),
     "sgcn_step_status": (_i32, [_vp, C.POINTER(_i32)]),
-    "sgcn_step_run_persistent": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp]),
-    "sgcn_full_history_mean_passes": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i32, _i64,
-                                             _vp, _vp, _vp]),
-    "sgcn_history_update_gated": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _vp,
-                                         _vp, _vp]),
-    "sgcn_flags_reset": (_i32, [_vp, _i32, _vp]),
-    "sgcn_flag_set": (_i32, [_vp, _i32, _vp]),
-    "sgcn_flag_gate": (_i32, [_vp, _i32, _vp, _vp]),
-    "sgcn_full_history_mean_ov": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,
-                                         _vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
+    "sgcn_full_history_mean_wb": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64,
+                                         _vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "sgcn_wb_counters_reset": (_i32, [_vp, _vp]),
+    "sgcn_sampled_done_attach": (_i32, [_vp]),
     "sgcn_wb_payload_bytes": (_i64, [_i32, _i32]),
     "sgcn_wb_pack": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), _i32, _i32, _vp]),
     "sgcn_wb_push": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, C.POINTER(_vp), C.POINTER(_vp), _i32,
@@ -144,7 +138,7 @@ class StepDesc(C.Structure):
                 ("dst_even", _vp * 16), ("dst_odd", _vp * 16), ("peer_flags", _vp * 16),
                 ("recv_even", _vp), ("recv_odd", _vp), ("flags", _vp), ("epoch", _vp), ("timeout_flag", _vp),
                 ("block_counter", _vp), ("owner", _vp),
-                ("x0_alt", _vp * 2), ("dx_alt", _vp), ("train", _i32), ("overlap_write_back", _i32),
+                ("x0_alt", _vp * 2), ("dx_alt", _vp), ("train", _i32), ("fuse_write_back", _i32),
                 ("ring", _i32), ("pad0", _i32), ("ring_stride", _i64), ("push_epoch", _vp), ("apply_epoch", _vp),
                 ("apply_stash", _vp), ("ring_flags", _vp), ("ring_dst", _vp * 16), ("ring_peer_flags", _vp * 16),
                 ("ring_recv", _vp),
@@ -172,7 +166,7 @@ def load():
     _lib = lib
     # optional overrides of the kernel tunables (include/sgcn_b200.h: SGCN_TUNE_*), for A/B runs
     for key, env in enumerate(("SGCN_FULL_VARIANT", "SGCN_TMA_WARPS", "SGCN_TMA_ROWS", "SGCN_TMA_DEPTH",
-                               "SGCN_TMA_GRID", "SGCN_PDL")):
+                               "SGCN_TMA_GRID", "SGCN_PDL", "SGCN_HIST_L2", "SGCN_STREAM_L2")):
         if os.environ.get(env, "") != "":
             if lib.sgcn_tune_set(key, int(os.environ[env])) != SGCN_OK:
                 raise SgcnError(SGCN_EINVAL, "%s=%s: %s" % (env, os.environ[env], lib.sgcn_last_error().decode()))

@@ -22,6 +22,7 @@ template <> struct VT<float4> {
     static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
     static __device__ __forceinline__ float4 ld(const float* p) { return __ldg((const float4*)p); }
     static __device__ __forceinline__ float4 ld_stream(const float* p) { return ldg_stream4(p); }
+    static __device__ __forceinline__ float4 ld_hist(const float* p, uint64_t pol) { return ld_hist4(p, pol); }
     static __device__ __forceinline__ void st(float* p, float4 v) { *(float4*)p = v; }
     static __device__ __forceinline__ void red(float* p, float4 v) { red_add4(p, v); }
     static __device__ __forceinline__ void fma(float4& a, float w, float4 v) { fma4(a, w, v); }
@@ -43,6 +44,7 @@ template <> struct VT<float> {
     static __device__ __forceinline__ float zero() { return 0.f; }
     static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
     static __device__ __forceinline__ float ld_stream(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ float ld_hist(const float* p, uint64_t pol) { return ld_hist1(p, pol); }
     static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
     static __device__ __forceinline__ void red(float* p, float v) { atomicAdd(p, v); }
     static __device__ __forceinline__ void fma(float& a, float w, float v) { a = fmaf(w, v, a); }
@@ -53,6 +55,10 @@ template <> struct VT<float> {
 };
 
 constexpr int kAggThreads = 256;
+constexpr int kWbWorkers = 64;         // thread blocks that carry the fused write-back (the last ones to finish)
+
+// counters of the fused write-back (device ints, zero before the first pass of a run: sgcn_wb_counters_reset)
+enum { WB_TICKET = 0, WB_FINISHED = 1, WB_SAMPLED = 2, WB_FULL = 3, WB_ERROR = 4, WB_STICKET = 5, WB_COUNTERS = 8 };
 
 enum { MODE_PLAIN = 0, MODE_CV = 1, MODE_CVD = 2, MODE_DET = 3 };
 
@@ -114,7 +120,26 @@ struct SampledArgs {
     // (both only need the gathered input rows; one launch instead of two on the step's side branch)
     int has_push; WbPushArgs push;
     ShardMap hmap;   // row-sharded history (CV / CVD): hist rows are addressed by GLOBAL node id through it
+    // optional (sgcn_sampled_done_attach): the last thread block to finish adds 1 to done_ctr[WB_SAMPLED] -- the
+    // fused write-back in the tail of the pass's full-neighbour mean waits for it (this kernel reads hist[tgt])
+    int32_t* done_ctr;
+    int hist_l2, hist_l2_pct;          // L2 eviction policy of the history rows (l2_policy)
 };
+
+// every thread of the block calls it on its way out; the last block of the grid publishes "one more sampled pass done"
+__device__ __forceinline__ void sampled_done_signal(int32_t* ctr) {
+    if (!ctr) return;
+    __syncthreads();                                   // every history row this block reads has been consumed
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int total = (int)(gridDim.x * gridDim.y);
+        if (atomicAdd(ctr + WB_STICKET, 1) == total - 1) {
+            ctr[WB_STICKET] = 0;
+            __threadfence();
+            atomicAdd(ctr + WB_SAMPLED, 1);
+        }
+    }
+}
 
 template <typename V, int LPR, int VPL, int MODE>
 __global__ void __launch_bounds__(kAggThreads)
@@ -124,8 +149,10 @@ sampled_rows_kernel(const SampledArgs a) {
     grid_dep_wait();      // (PDL) launched early behind the gather that writes x: nothing to do before it
     if (a.has_push && blockIdx.y == 1) {
         wb_pack_body(a.push, blockIdx.x, gridDim.x);
+        sampled_done_signal(a.done_ctr);
         return;
     }
+    const uint64_t hpol = l2_policy(a.hist_l2, a.hist_l2_pct);
     const int n_out = dev_count(a.n_out_dev, a.n_out);
     const int gl = threadIdx.x % LPR;                      // lane within the group
     const int groups = (gridDim.x * kAggThreads) / LPR;
@@ -156,7 +183,7 @@ sampled_rows_kernel(const SampledArgs a) {
 #pragma unroll
                 for (int k = 0; k < VPL; ++k) {
                     if (!ok[k]) continue;
-                    const V hv = T::ld_stream(shard_row(a.hmap, a.hist, t, a.ld_h) + off[k]);
+                    const V hv = T::ld_hist(shard_row(a.hmap, a.hist, t, a.ld_h) + off[k], hpol);
                     if (MODE == MODE_CV) {
                         const V xv = T::ld(a.x + (int64_t)c * a.ld_x + off[k]);
                         T::fma(acc[k], w, T::sub(xv, hv));
@@ -228,6 +255,7 @@ sampled_rows_kernel(const SampledArgs a) {
             }
         }
     }
+    sampled_done_signal(a.done_ctr);
 }
 
 // ---- SpMM backward: dx[cols[e]] += vals[e] * rscale[r] * dy[r] --------------------------------
@@ -357,7 +385,6 @@ spmm_coo_kernel(const int2* __restrict__ idx2, const float* __restrict__ vals, i
 //           path; partial sums stay in registers across the span and leave through one 128-bit RED
 //           per lane per row segment.
 constexpr int kFullStageRows = 4096;   // row pointers are staged in shared memory up to this many rows
-constexpr int kFullOvMax = 4096;       // override rows (sgcn_full_history_mean_ov) the shared-memory table holds
 constexpr int kFullMacro = 64;         // positions staged per warp per macro-chunk
 constexpr int kFullWarps = kAggThreads / 32;
 
@@ -370,10 +397,14 @@ struct FullArgs {
     int stage_rows;  // row pointers of up to this many output rows are staged in shared memory
     unsigned long long* trace;
     int square;      // use adj_w^2 (tf.square(fadj) @ var_history, gcn/layers.py:338)
-    // row override (sgcn_full_history_mean_ov): history rows of the nodes ov_ids[0 .. *ov_n_dev) are read
-    // from ov_rows instead -- the previous pass's write-back, applied on the fly
-    const int32_t* ov_ids; const int32_t* ov_n_dev; int ov_bound, ov_bits;
-    const float* ov_rows; int64_t ld_ov;
+    // fused write-back (sgcn_full_history_mean_wb): hist[wb_ids[i], :] = wb_rows[i, :] for i < *wb_n_dev, stored by
+    // the last thread blocks to finish once EVERY block of this launch has read its history rows and the pass's
+    // sampled aggregate has read its own (wb_ctr[WB_SAMPLED] > wb_ctr[WB_FULL]); then *consumed += 1
+    const int32_t* wb_ids; const int32_t* wb_n_dev; int wb_bound;
+    const float* wb_rows; int64_t ld_wb; int wb_D;
+    float* wb_hist;          // == hist of the first column tile, writable
+    int32_t* wb_ctr; int32_t* consumed;
+    int hist_l2, hist_l2_pct;          // L2 eviction policy of the history rows (l2_policy)
     ShardMap hmap;   // row-sharded history (world <= 1: hist is one local table)
 };
 
@@ -382,16 +413,6 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-constexpr unsigned short kOvEmpty = 0xffffu;
-__device__ __forceinline__ unsigned ov_hash(int node, int bits) { return ((unsigned)node * 2654435761u) >> (32 - bits); }
-
-struct PassDesc {      // one pass of the persistent kernel below
-    const int32_t* nodes; const int32_t* rowptr_f; const int32_t* n_out_dev;
-    float* y0; float* y1;
-    const int32_t* ov_ids; const int32_t* ov_n_dev; const float* ov_rows;
-    int train;
-};
 
 template <typename V, int LPR, int VPL>
 __device__ __forceinline__ void full_flush(const FullArgs& a, float* y0, float* y1, int row, int gl, V (&acc)[VPL]) {
@@ -407,21 +428,15 @@ __device__ __forceinline__ void full_flush(const FullArgs& a, float* y0, float* 
     }
 }
 
-// One pass of the full-neighbour mean by this thread block (its warps' spans of the pass's positions).
-// PDL: the block belongs to a launch of its own (full_mean_kernel) and orders itself against its stream
-// predecessor with griddepcontrol; !PDL: called pass after pass by the persistent kernel below.
-template <typename V, int LPR, int VPL, bool PDL>
-__device__ __forceinline__ void full_mean_body(const FullArgs& a, const PassDesc* pd) {
+// The full-neighbour mean by this thread block (its warps' spans of the pass's positions); the block orders
+// itself against its stream predecessor with griddepcontrol (programmatic dependent launch).
+template <typename V, int LPR, int VPL>
+__device__ __forceinline__ void full_mean_body(const FullArgs& a, const uint64_t hpol) {
     using T = VT<V>;
-    // what differs from pass to pass: from the launch arguments, or from the persistent kernel's pass list
-    const int32_t* const nodes = PDL ? a.nodes : pd->nodes;
-    const int32_t* const rowptr_f = PDL ? a.rowptr_f : pd->rowptr_f;
-    const int32_t* const n_out_dev = PDL ? a.n_out_dev : pd->n_out_dev;
-    float* const y0 = PDL ? a.y0 : pd->y0;
-    float* const y1 = PDL ? a.y1 : pd->y1;
-    const int32_t* const ov_ids = PDL ? a.ov_ids : pd->ov_ids;
-    const int32_t* const ov_n_dev = PDL ? a.ov_n_dev : pd->ov_n_dev;
-    const float* const ov_rows = PDL ? a.ov_rows : pd->ov_rows;
+    const int32_t* const nodes = a.nodes;
+    const int32_t* const rowptr_f = a.rowptr_f;
+    float* const y0 = a.y0;
+    float* const y1 = a.y1;
     constexpr int G = 32 / LPR;                                  // groups per warp
     constexpr int UN = (VPL >= 8) ? 1 : ((VPL == 4) ? 2 : ((VPL == 2) ? 4 : 8));   // row loads per buffer
     constexpr int STEP = G * UN;                                 // positions per group-iteration
@@ -434,33 +449,15 @@ __device__ __forceinline__ void full_mean_body(const FullArgs& a, const PassDesc
     __shared__ int32_t s_lcol[kFullWarps][kFullMacro];           // landing buffers of the NEXT chunk's metadata
     __shared__ float s_lw[kFullWarps][kFullMacro];
     __shared__ int32_t s_lr[kFullWarps][kFullMacro];
-    const int n_out = dev_count(n_out_dev, a.n_out);
+    const int n_out = dev_count(a.n_out_dev, a.n_out);
     if (n_out <= 0) return;
     const bool staged = n_out <= a.stage_rows;
-    // override table (open addressing, 16-bit slots = index into the id list kept beside it)
-    int32_t* s_ovid = s_dyn + 2 * a.stage_rows + 2;
-    unsigned short* s_ovtab = (unsigned short*)(s_ovid + a.ov_bound);
-    const int ov_n = ov_ids ? min(*ov_n_dev, a.ov_bound) : 0;
-    const unsigned ov_mask = (1u << a.ov_bits) - 1u;
-    if (ov_n > 0) {
-        for (int i = threadIdx.x; i < (1 << a.ov_bits); i += kAggThreads) s_ovtab[i] = kOvEmpty;
-        for (int i = threadIdx.x; i < ov_n; i += kAggThreads) s_ovid[i] = __ldg(ov_ids + i);
-    }
     if (staged) {
         for (int i = threadIdx.x; i <= n_out; i += kAggThreads) s_ptr[i] = __ldg(rowptr_f + i);
         for (int i = threadIdx.x; i < n_out; i += kAggThreads)
             s_base[i] = __ldg(a.adj_p + __ldg(nodes + i)) - __ldg(rowptr_f + i);
-    }
-    if (staged || ov_n > 0) __syncthreads();
-    if (ov_n > 0) {
-        for (int i = threadIdx.x; i < ov_n; i += kAggThreads) {      // ids are distinct
-            unsigned h = ov_hash(s_ovid[i], a.ov_bits);
-            while (atomicCAS(s_ovtab + h, kOvEmpty, (unsigned short)i) != kOvEmpty) h = (h + 1) & ov_mask;
-        }
         __syncthreads();
     }
-    // element offset (relative to hist) of override row i
-    const int64_t ov_base = ov_rows ? (int64_t)(((intptr_t)ov_rows - (intptr_t)a.hist) / (intptr_t)sizeof(float)) : 0;
     const int32_t* ptr = staged ? s_ptr : rowptr_f;
     const int nnz = ptr[n_out];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -502,7 +499,7 @@ __device__ __forceinline__ void full_mean_body(const FullArgs& a, const PassDesc
     // macro-chunk ahead: the lanes resolve their positions' rows, then the column ids and weights go
     // global -> shared memory as 4-byte asynchronous copies (cp.async / LDGSTS: no registers held while
     // they fly) into a landing buffer, under the previous chunk's streaming history rows.  It is COMMITTED
-    // -- element offsets computed, override rows substituted -- right before its own rows are issued.
+    // -- element offsets computed -- right before its own rows are issued.
     // ncu on the round-1 kernel: 22 % of the stall samples sat in this staging when it ran synchronously
     // in front of every chunk (profiles/r01_full_mean_ncu.json).
     int32_t* l_col = s_lcol[wib];
@@ -545,25 +542,13 @@ __device__ __forceinline__ void full_mean_body(const FullArgs& a, const PassDesc
             if (a.hmap.world > 1)          // a remote shard: the offset still is relative to a.hist
                 off = (int64_t)(((intptr_t)shard_row(a.hmap, a.hist, col, a.ld_h) - (intptr_t)a.hist) /
                                 (intptr_t)sizeof(float));
-            if (ov_n > 0 && r >= 0) {
-                unsigned h = ov_hash(col, a.ov_bits);
-                for (;;) {
-                    const unsigned short sl = s_ovtab[h];
-                    if (sl == kOvEmpty) break;
-                    if (s_ovid[sl] == col) { off = ov_base + (int64_t)sl * a.ld_ov; break; }
-                    h = (h + 1) & ov_mask;
-                }
-            }
             my_off[j] = off;
             my_w[j] = a.square ? w * w : w;
             my_r[j] = r;
         }
     };
     fetch(p0, p1);                                                // (PDL) still under the stream predecessor
-    // (PDL) history rows: after the write-back.  With the row override the stream predecessor is the
-    // previous pass's full-neighbour mean, which writes nothing this kernel reads: the wait moves to
-    // the end (completion order only) and the two kernels overlap tail to head.
-    if (PDL && !ov_ids) grid_dep_wait();
+    grid_dep_wait();                                              // (PDL) history rows: after the write-back
 
   for (;;) {
     int next_chunk = 0;
@@ -583,7 +568,7 @@ __device__ __forceinline__ void full_mean_body(const FullArgs& a, const PassDesc
                 const int64_t off = my_off[gi * STEP + u * G + g];
 #pragma unroll
                 for (int k = 0; k < VPL; ++k)
-                    buf[u][k] = ok[k] ? T::ld_stream(hist_lane[k] + off) : T::zero();
+                    buf[u][k] = ok[k] ? T::ld_hist(hist_lane[k] + off, hpol) : T::zero();
             }
         };
         auto consume = [&](V (&buf)[UN][VPL], int gi) {
@@ -638,79 +623,93 @@ __device__ __forceinline__ void full_mean_body(const FullArgs& a, const PassDesc
     if (cur >= 0) full_flush<V, LPR, VPL>(a, y0, y1, cur, gl, acc);
 }
 
+// ---- the history write-back fused into the tail of the full-neighbour mean -----------------------------------
+// As kernels of their own the write-back and its launch cost ~7 us between two 19 us means (device timelines,
+// profiles/r02_timeline_trains_ov0.txt: 4.5 us from the end of the mean to the end of the write-back -- a
+// programmatic launch that sits resident in griddepcontrol.wait and keeps the next pass's gather off the SMs --
+// and the gather behind it).  Here the LAST kWbWorkers thread blocks to finish (ticket order) wait until every
+// block of the launch has consumed its history rows and the pass's sampled aggregate has consumed its own
+// (device counters), then store the pass's new rows: hist[wb_ids[i]] = wb_rows[i].  Every read of the table
+// precedes every write as in the reference (gcn/models.py:186-194); the next mean follows with a programmatic
+// launch and nothing else on the chain.  The blocks that wait are those that finish last anyway; blocks not
+// yet resident need no slot of theirs (at most 64 of a few hundred are held), so the wait cannot deadlock;
+// it is bounded all the same (wb_ctr[WB_ERROR], sgcn_step_status).
+template <typename V>
+__device__ __forceinline__ void full_write_back_tail(const FullArgs& a, uint64_t hpol) {
+    __shared__ int s_ticket, s_go;
+    __syncthreads();                                   // every warp of the block has consumed its history rows
+    int32_t* const c = a.wb_ctr;
+    const int grid = (int)gridDim.x;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_ticket = atomicAdd(c + WB_TICKET, 1);
+    }
+    __syncthreads();
+    const int workers = min(grid, kWbWorkers);
+    const int wi = s_ticket - (grid - workers);
+    if (wi < 0) return;
+    if (threadIdx.x == 0) {
+        bool go = spin_until_ge(c + WB_TICKET, grid, c + WB_ERROR);
+        // sampled passes finished > full passes finished: this pass's sampled aggregate is through
+        if (go) go = spin_until_ge(c + WB_SAMPLED, (int)ld_acquire_u32((const unsigned*)(c + WB_FULL)) + 1, c + WB_ERROR);
+        s_go = go;
+    }
+    __syncthreads();
+    if (s_go) {
+        const int n = min(*a.wb_n_dev, a.wb_bound);
+        const int lane = threadIdx.x & 31;
+        const int wpb = kAggThreads / 32;
+        constexpr int RU = 4;                          // rows in flight per warp
+        for (int r0 = (wi * wpb + (threadIdx.x >> 5)) * RU; r0 < n; r0 += workers * wpb * RU) {
+            int id[RU];
+#pragma unroll
+            for (int u = 0; u < RU; ++u) id[u] = r0 + u < n ? a.wb_ids[r0 + u] : -1;
+            if (sizeof(V) == 16) {
+                for (int c0 = lane * 4; c0 < a.wb_D; c0 += 128) {
+                    float4 v[RU];
+#pragma unroll
+                    for (int u = 0; u < RU; ++u)
+                        if (id[u] >= 0) v[u] = *(const float4*)(a.wb_rows + (int64_t)(r0 + u) * a.ld_wb + c0);
+#pragma unroll
+                    for (int u = 0; u < RU; ++u)
+                        if (id[u] >= 0) st_hist4(a.wb_hist + (int64_t)id[u] * a.ld_h + c0, v[u], hpol);
+                }
+            } else {
+                for (int c0 = lane; c0 < a.wb_D; c0 += 32)
+#pragma unroll
+                    for (int u = 0; u < RU; ++u)
+                        if (id[u] >= 0) a.wb_hist[(int64_t)id[u] * a.ld_h + c0] = a.wb_rows[(int64_t)(r0 + u) * a.ld_wb + c0];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(c + WB_FINISHED, 1) == workers - 1) {       // the last worker: counters ready for the next pass
+            c[WB_TICKET] = 0;
+            c[WB_FINISHED] = 0;
+            if (a.consumed) atomicAdd(a.consumed, 1);             // the sampler's guard: this pass's reads are over
+            __threadfence();
+            atomicAdd(c + WB_FULL, 1);
+        }
+    }
+}
+
 template <typename V, int LPR, int VPL>
 __global__ void __maxnreg__(96)      // 2 CTAs x 256 threads x 96 regs leave 16K registers per SM free
 full_mean_kernel(const FullArgs a) {
     TraceScope ts(a.trace, TR_FULL);
-    grid_dep_launch();                                           // (PDL) the write-back may get resident now
-    full_mean_body<V, LPR, VPL, true>(a, nullptr);
-    if (a.ov_ids) grid_dep_wait();
-}
-
-// ---- the full-neighbour means of a whole graph of passes in ONE launch ---------------------------------
-// Between two launches of full_mean_kernel the GPU idles for 4-7 us (dependent-launch latency under load,
-// measured inside CUDA graphs with and without programmatic launches: profiles/r02_timeline_trains_*.txt) --
-// a quarter of a 19 us kernel.  Here the thread blocks stay resident for all n passes of a run and the
-// dependencies become device-side counters:
-//   waits    pass k starts once  trains_done > train(k)   (its batch is sampled),
-//                                pre_done > k             (its output rows are zeroed, pass k-1's rows gathered),
-//                                wb_done >= k - 1         (write-back k-2 has landed; rows of field(k-1) come
-//                                                          from pass k-1's gathered rows: the row override)
-//   signals  every block adds 1 to full_done[k] when its part of pass k is in memory; the write-back of
-//            pass k, the D2H copy of its rows and the re-use of its buffers are gated on full_done[k] == blocks
-// All spins are bounded: a counter that never moves raises flags[F_ERROR] instead of hanging the GPU.
-constexpr int kMaxPasses = 64;
-enum { F_TRAINS = 0, F_PRE = 1, F_WB = 2, F_ERROR = 3, F_FULL = 8 };     // flags[F_FULL + k]: blocks done with pass k
-struct PassList { PassDesc p[kMaxPasses]; int n; };
-
-template <typename V, int LPR, int VPL>
-__global__ void __maxnreg__(96)
-full_mean_persistent_kernel(const __grid_constant__ FullArgs a, const __grid_constant__ PassList passes, int32_t* flags) {
-    __shared__ int s_go;
-    for (int k = 0; k < passes.n; ++k) {
-        const PassDesc& pd = passes.p[k];
-        if (threadIdx.x == 0) {
-            bool go = spin_until_ge(flags + F_TRAINS, pd.train + 1, flags + F_ERROR) &&
-                      spin_until_ge(flags + F_PRE, k + 1, flags + F_ERROR) &&
-                      (k < 2 || spin_until_ge(flags + F_WB, k - 1, flags + F_ERROR));
-            s_go = go && *(volatile int32_t*)(flags + F_ERROR) == 0;
-        }
-        __syncthreads();
-        if (!s_go) return;
-        if (a.trace && threadIdx.x == 0 && blockIdx.x == 0) {        // timeline: one start / end pair per pass
-            const unsigned long long now = global_ns();
-            const unsigned long long i = atomicAdd(a.trace + 16, 1ull);
-            if (i < (unsigned long long)kTraceLogCap) { a.trace[17 + 2 * i] = (TR_FULL << 1); a.trace[18 + 2 * i] = now; }
-        }
-        full_mean_body<V, LPR, VPL, false>(a, &pd);
-        __syncthreads();                                              // every warp's REDs are issued
-        if (threadIdx.x == 0) {
-            __threadfence();
-            atomicAdd(flags + F_FULL + k, 1);
-            if (a.trace && blockIdx.x == 0) {
-                const unsigned long long now = global_ns();
-                const unsigned long long i = atomicAdd(a.trace + 16, 1ull);
-                if (i < (unsigned long long)kTraceLogCap) { a.trace[17 + 2 * i] = (TR_FULL << 1) | 1; a.trace[18 + 2 * i] = now; }
-            }
-        }
+    grid_dep_launch();                                           // (PDL) the stream successor may get resident now
+    const uint64_t hpol = l2_policy(a.hist_l2, a.hist_l2_pct);
+    full_mean_body<V, LPR, VPL>(a, hpol);
+    if (a.wb_ids) {
+        grid_dep_wait();                                         // (blocks without positions skipped it above)
+        full_write_back_tail<V>(a, hpol);
     }
 }
 
-// tiny stream-ordered helpers around the persistent kernel
-__global__ void flags_reset_kernel(int32_t* flags, int n) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) flags[i] = 0;
-}
-__global__ void flag_set_kernel(int32_t* flag, int value) {
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicMax(flag, value);
-    }
-}
-__global__ void flag_gate_kernel(const int32_t* flag, int want, int32_t* err) {
-    if (threadIdx.x == 0) {
-        spin_until_ge(flag, want, err);
-        __threadfence();
-    }
+__global__ void wb_counters_reset_kernel(int32_t* ctr) {
+    if (threadIdx.x < WB_COUNTERS) ctr[threadIdx.x] = 0;
 }
 
 // ---- full-neighbour history mean, bulk-copy (TMA engine) variant ---------------------------------
@@ -918,6 +917,7 @@ static int grid_for_groups(int64_t n_groups, int lpr) {
 
 struct PendingPush { bool valid = false; WbPushArgs args; };
 static thread_local PendingPush t_pending_push;
+static thread_local int32_t* t_pending_done = nullptr;      // sgcn_sampled_done_attach
 
 template <int MODE>
 static int launch_sampled(SampledArgs a, int D, bool vec_ok, cudaStream_t st) {
@@ -941,6 +941,13 @@ static int launch_sampled(SampledArgs a, int D, bool vec_ok, cudaStream_t st) {
         if (a.self1) t.self1 = a.self1 + c0;
         if (a.dx) { t.dy = a.dy + c0; t.dx = a.dx + c0; }
         int gx = grid_for_groups(a.n_out, sh.lpr);
+        t.hist_l2 = g_hist_l2[0];
+        t.hist_l2_pct = g_hist_l2[1];
+        t.done_ctr = nullptr;
+        if (c0 + sh.tile >= D && t_pending_done) {        // the last column tile's launch carries the signal
+            t.done_ctr = t_pending_done;
+            t_pending_done = nullptr;
+        }
         t.has_push = 0;
         if (c0 == 0 && t_pending_push.valid) {            // see sgcn_wb_push_attach
             t.has_push = 1;
@@ -1215,38 +1222,40 @@ int sgcn_spmm_coo(const int32_t* idx2, const float* vals, int32_t nnz, const flo
     return SGCN_OK;
 }
 
+struct FullWb {          // fused write-back of sgcn_full_history_mean_wb
+    const int32_t* ids = nullptr; const int32_t* n_dev = nullptr; int bound = 0;
+    const float* rows = nullptr; int64_t ld = 0; int32_t* ctr = nullptr; int32_t* consumed = nullptr;
+};
+
 static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
                                   const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
                                   const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
                                   float* y0, int64_t ld_y0, float* y1, int64_t ld_y1,
-                                  int32_t* work_counter, int square, void* stream,
-                                  const int32_t* ov_ids = nullptr, const int32_t* ov_n_dev = nullptr,
-                                  int ov_bound = 0, const float* ov_rows = nullptr, int64_t ld_ov = 0) {
+                                  int32_t* work_counter, int square, void* stream, const FullWb wb = FullWb{}) {
     SGCN_REQUIRE(n_out >= 0 && D >= 0, "full_history_mean: negative size");
-    if (n_out == 0 || D == 0) return SGCN_OK;
+    if (n_out == 0 || D == 0) {
+        SGCN_REQUIRE(!wb.ids, "full_history_mean_wb: empty launch");
+        return SGCN_OK;
+    }
     SGCN_REQUIRE(nodes && rowptr_f && adj_p && adj_i && adj_w && hist && y0,
                  "full_history_mean: null pointer");
     SGCN_REQUIRE(ld_h >= D && ld_y0 >= D && (!y1 || ld_y1 >= D),
                  "full_history_mean: row stride smaller than width");
     const bool vec_ok = D % 4 == 0 && ld_h % 4 == 0 && ld_y0 % 4 == 0 && aligned16(hist) &&
-                        aligned16(y0) && (!y1 || (ld_y1 % 4 == 0 && aligned16(y1)));
+                        aligned16(y0) && (!y1 || (ld_y1 % 4 == 0 && aligned16(y1))) &&
+                        (!wb.ids || (wb.ld % 4 == 0 && aligned16(wb.rows)));
     const Shape sh = pick_shape(D, vec_ok);
     cudaStream_t st = (cudaStream_t)stream;
-    int ov_bits = 0;
-    if (ov_ids) {
-        SGCN_REQUIRE(ov_n_dev && ov_rows && ov_bound > 0 && ov_bound <= kFullOvMax && ld_ov >= D,
-                     "full_history_mean_ov: bad override arguments (at most 4096 override rows)");
-        SGCN_REQUIRE(vec_ok ? (ld_ov % 4 == 0 && aligned16(ov_rows)) : true,
-                     "full_history_mean_ov: override rows must be aligned like the history rows");
-        ov_bits = 4;
-        while ((1 << ov_bits) < 2 * ov_bound) ++ov_bits;
-    }
+    if (wb.ids)
+        SGCN_REQUIRE(wb.n_dev && wb.rows && wb.ctr && wb.bound > 0 && wb.ld >= D,
+                     "full_history_mean_wb: bad write-back arguments");
     const bool sharded = t_hist_map.world > 1;
     if (sharded) SGCN_REQUIRE(D <= sh.tile, "sharded history: the aggregated width must fit one column tile");
-    if (g_full_variant == 1 && vec_ok && D <= 128 && n_out <= kFullStageRows && !ov_ids && !sharded) {
+    if (g_full_variant == 1 && vec_ok && D <= 128 && n_out <= kFullStageRows && !wb.ids && !sharded) {
         FullTmaCfg cfg = g_tma_cfg;
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0, ld_y0, y1, ld_y1,
-                   nullptr, n_out, g_trace, square, nullptr, nullptr, 0, 0, nullptr, 0, ShardMap{}};
+                   nullptr, n_out, g_trace, square, nullptr, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                   g_hist_l2[0], g_hist_l2[1], ShardMap{}};
         const size_t fixed = 12 * (size_t)kTmaMeta + sizeof(int32_t) * (2 * (size_t)n_out + 2) + 128;
         const size_t stage = (size_t)cfg.rows * D * 4;
         while (cfg.depth > 1 && fixed + (size_t)cfg.warps * cfg.depth * (stage + 8) > 226 * 1024) --cfg.depth;
@@ -1263,14 +1272,16 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
         return SGCN_OK;
     }
     for (int c0 = 0; c0 < D; c0 += sh.tile) {
+        // several column tiles: the write-back (whole rows) rides on the LAST tile's launch
+        const bool with_wb = wb.ids && c0 + sh.tile >= D;
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist + c0, ld_h,
                    std::min(sh.tile, D - c0), y0 + c0, ld_y0, y1 ? y1 + c0 : nullptr, ld_y1,
                    D <= sh.tile ? work_counter : nullptr,    // one launch per counter reset
                    std::min(n_out, kFullStageRows), g_trace, square,
-                   ov_ids, ov_n_dev, ov_ids ? ov_bound : 0, ov_bits, ov_rows ? ov_rows + c0 : nullptr, ld_ov,
+                   with_wb ? wb.ids : nullptr, wb.n_dev, wb.bound, wb.rows, wb.ld, D, const_cast<float*>(hist),
+                   wb.ctr, wb.consumed, g_hist_l2[0], g_hist_l2[1],
                    sharded ? t_hist_map : ShardMap{}};
-        const size_t dyn = sizeof(int32_t) * (2 * (size_t)a.stage_rows + 2) +
-                           (ov_ids ? sizeof(int32_t) * (size_t)ov_bound + sizeof(unsigned short) * ((size_t)1 << ov_bits) : 0);
+        const size_t dyn = sizeof(int32_t) * (2 * (size_t)a.stage_rows + 2);
         // one resident wave: every CTA the SMs can hold at once, spans cut accordingly
 #define CALL(V, L, P)                                                                        \
     do {                                                                                     \
@@ -1299,72 +1310,16 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
     return SGCN_OK;
 }
 
-int sgcn_flags_reset(int32_t* flags, int32_t n, void* stream) {
-    SGCN_REQUIRE(flags && n > 0, "flags_reset: bad argument");
-    flags_reset_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(flags, n);
+int sgcn_wb_counters_reset(int32_t* counters, void* stream) {
+    SGCN_REQUIRE(counters, "wb_counters_reset: null pointer");
+    wb_counters_reset_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counters);
     SGCN_LAUNCHED();
     return SGCN_OK;
 }
 
-int sgcn_flag_set(int32_t* flag, int32_t value, void* stream) {
-    SGCN_REQUIRE(flag, "flag_set: null flag");
-    flag_set_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag, value);
-    SGCN_LAUNCHED();
-    return SGCN_OK;
-}
-
-int sgcn_flag_gate(const int32_t* flag, int32_t want, int32_t* err, void* stream) {
-    SGCN_REQUIRE(flag && err, "flag_gate: null pointer");
-    flag_gate_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag, want, err);
-    SGCN_LAUNCHED();
-    return SGCN_OK;
-}
-
-int sgcn_full_history_mean_passes(const sgcn_full_pass* passes, int32_t n, int32_t n_out_bound,
-                                  const int32_t* adj_p, const int32_t* adj_i, const float* adj_w,
-                                  const float* hist, int64_t ld_h, int32_t D, int64_t ld_y0, int64_t ld_y1,
-                                  int32_t ov_bound, int64_t ld_ov, int32_t* flags, int32_t* n_blocks, void* stream) {
-    SGCN_REQUIRE(passes && n >= 1 && n <= kMaxPasses && n_out_bound > 0 && n_out_bound <= kFullStageRows,
-                 "full_history_mean_passes: 1..64 passes of at most 4096 rows");
-    SGCN_REQUIRE(adj_p && adj_i && adj_w && hist && flags && n_blocks && D > 0 && ld_h >= D && ld_y0 >= D,
-                 "full_history_mean_passes: bad argument");
-    SGCN_REQUIRE(ov_bound > 0 && ov_bound <= kFullOvMax && ld_ov >= D, "full_history_mean_passes: bad override bound");
-    bool vec_ok = D % 4 == 0 && ld_h % 4 == 0 && ld_y0 % 4 == 0 && ld_ov % 4 == 0 && aligned16(hist);
-    PassList pl{};
-    pl.n = n;
-    for (int k = 0; k < n; ++k) {
-        const sgcn_full_pass& s = passes[k];
-        SGCN_REQUIRE(s.nodes && s.rowptr_f && s.y0 && (!s.ov_ids || (s.ov_n_dev && s.ov_rows)),
-                     "full_history_mean_passes: null pointer in a pass");
-        vec_ok = vec_ok && aligned16(s.y0) && (!s.y1 || (aligned16(s.y1) && ld_y1 % 4 == 0)) &&
-                 (!s.ov_rows || aligned16(s.ov_rows));
-        pl.p[k] = PassDesc{s.nodes, s.rowptr_f, s.n_out_dev, s.y0, s.y1, s.ov_ids, s.ov_n_dev, s.ov_rows, s.train};
-    }
-    const Shape sh = pick_shape(D, vec_ok);
-    SGCN_REQUIRE(D <= sh.tile, "full_history_mean_passes: the aggregated width must fit one column tile");
-    int ov_bits = 4;
-    while ((1 << ov_bits) < 2 * ov_bound) ++ov_bits;
-    FullArgs a{nullptr, nullptr, n_out_bound, nullptr, adj_p, adj_i, adj_w, hist, ld_h, D, nullptr, ld_y0, nullptr, ld_y1,
-               nullptr, n_out_bound, g_trace, 0, nullptr, nullptr, ov_bound, ov_bits, nullptr, ld_ov, ShardMap{}};
-    const size_t dyn = sizeof(int32_t) * (2 * (size_t)a.stage_rows + 2) + sizeof(int32_t) * (size_t)ov_bound +
-                       sizeof(unsigned short) * ((size_t)1 << ov_bits);
-    cudaStream_t st = (cudaStream_t)stream;
-#define CALL(V, L, P)                                                                                    \
-    do {                                                                                                 \
-        int per_sm = 0;                                                                                  \
-        SGCN_CUDA(cudaFuncSetAttribute(full_mean_persistent_kernel<V, L, P>,                             \
-                                       cudaFuncAttributePreferredSharedMemoryCarveout, kStepCarveout));   \
-        SGCN_CUDA(cudaFuncSetAttribute(full_mean_persistent_kernel<V, L, P>,                             \
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));         \
-        SGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                         \
-            &per_sm, full_mean_persistent_kernel<V, L, P>, kAggThreads, dyn));                           \
-        if (per_sm < 1) per_sm = 1;                                                                      \
-        *n_blocks = kNumSMs * per_sm;                                                                    \
-        full_mean_persistent_kernel<V, L, P><<<kNumSMs * per_sm, kAggThreads, dyn, st>>>(a, pl, flags);  \
-    } while (0)
-    SGCN_DISPATCH_SHAPE(sh, CALL);
-#undef CALL
-    SGCN_LAUNCHED();
+int sgcn_sampled_done_attach(int32_t* counters) {
+    SGCN_REQUIRE(counters, "sampled_done_attach: null pointer");
+    t_pending_done = counters;
     return SGCN_OK;
 }
 
@@ -1384,6 +1339,12 @@ int sgcn_tune_set(int32_t key, int32_t value) {
             g_tma_cfg.depth = value; return SGCN_OK;
         case SGCN_TUNE_PDL:
             g_pdl = value != 0; return SGCN_OK;
+        case SGCN_TUNE_HIST_L2:
+            SGCN_REQUIRE(value >= 0 && value <= 100, "tune: history L2 policy is 0 (normal) or 1..100 (% evict_last)");
+            g_hist_l2[0] = value > 0 ? 1 : 0; g_hist_l2[1] = value; return SGCN_OK;
+        case SGCN_TUNE_STREAM_L2:
+            SGCN_REQUIRE(value >= 0 && value <= 100, "tune: stream L2 policy is 0 (normal) or 1..100 (% evict_first)");
+            g_stream_l2[0] = value > 0 ? 2 : 0; g_stream_l2[1] = value; return SGCN_OK;
         case SGCN_TUNE_TMA_GRID:
             SGCN_REQUIRE(value >= 1 && value <= 4 * kNumSMs, "tune: 1..592 CTAs");
             g_tma_grid = value; return SGCN_OK;
@@ -1401,15 +1362,20 @@ int sgcn_full_history_mean(const int32_t* nodes, const int32_t* rowptr_f, int32_
                                   ld_y0, y1, ld_y1, work_counter, 0, stream);
 }
 
-int sgcn_full_history_mean_ov(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
+int sgcn_full_history_mean_wb(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,
                               const int32_t* n_out_dev, const int32_t* adj_p, const int32_t* adj_i,
-                              const float* adj_w, const float* hist, int64_t ld_h, int32_t D,
+                              const float* adj_w, float* hist, int64_t ld_h, int32_t D,
                               float* y0, int64_t ld_y0, float* y1, int64_t ld_y1,
-                              const int32_t* ov_ids, const int32_t* ov_n_dev, int32_t ov_bound,
-                              const float* ov_rows, int64_t ld_ov, void* stream) {
-    SGCN_REQUIRE(ov_ids, "full_history_mean_ov: null override id list");
+                              const int32_t* wb_ids, const int32_t* wb_n_dev, int32_t wb_bound,
+                              const float* wb_rows, int64_t ld_wb, int32_t* counters, int32_t* consumed,
+                              void* stream) {
+    SGCN_REQUIRE(wb_ids, "full_history_mean_wb: null id list");
+    SGCN_REQUIRE(t_hist_map.world <= 1, "full_history_mean_wb: not for row-sharded history tables");
+    FullWb wb;
+    wb.ids = wb_ids; wb.n_dev = wb_n_dev; wb.bound = wb_bound; wb.rows = wb_rows; wb.ld = ld_wb;
+    wb.ctr = counters; wb.consumed = consumed;
     return full_history_mean_impl(nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0,
-                                  ld_y0, y1, ld_y1, nullptr, 0, stream, ov_ids, ov_n_dev, ov_bound, ov_rows, ld_ov);
+                                  ld_y0, y1, ld_y1, nullptr, 0, stream, wb);
 }
 
 int sgcn_full_history_mean_sq(const int32_t* nodes, const int32_t* rowptr_f, int32_t n_out,

@@ -135,6 +135,47 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     return r;
 }
 
+// History rows: tables that kernels of the same step WRITE (write-back fused into the tail of the full-neighbour
+// mean, programmatic dependent launches) -- coherent loads, never the read-only (.nc) path; no L1 allocation
+// (every row is read once per kernel); L2 eviction priority from a policy word (l2_policy).
+__device__ __forceinline__ float4 ld_hist4(const float* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ float ld_hist1(const float* p, uint64_t pol) {
+    float r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_hist4(float* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+// read-once streams (feature rows of the gather): same, through the read-only path
+__device__ __forceinline__ float4 ldg_stream4_hint(const float* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+// L2 eviction policy word: kind 0 = normal, 1 = evict_last for `pct` % of the accesses (the rest unchanged),
+// 2 = evict_first (sgcn_tune_set SGCN_TUNE_HIST_L2 / SGCN_TUNE_STREAM_L2)
+__device__ __forceinline__ uint64_t l2_policy(int kind, int pct) {
+    uint64_t pol;
+    const float frac = (float)pct * 0.01f;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, %1;" : "=l"(pol) : "f"(frac));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.L2::evict_unchanged.b64 %0, %1;" : "=l"(pol) : "f"(frac));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// host-side tunables behind them: {kind, percent}
+extern int g_hist_l2[2], g_stream_l2[2];
+
 // 128-bit vector reduction (sm_90+): one RED for 4 floats.
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -167,8 +208,8 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// bounded wait for a device-side counter (the persistent step schedule): false + *err = 1 after ~2 s, and at
-// once when another wait has already given up
+// bounded wait for a device-side counter: false + *err = 1 after ~2 s, and at once when another wait has
+// already given up
 __device__ __forceinline__ bool spin_until_ge(const int32_t* ctr, int want, int32_t* err) {
     long long spins = 0;
     while ((int)ld_acquire_u32((const unsigned*)ctr) < want) {

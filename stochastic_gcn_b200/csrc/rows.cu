@@ -65,65 +65,6 @@ move_rows_vec4_kernel(const float* __restrict__ src, int64_t ld_src, const int32
     }
 }
 
-// History write-back of the persistent step schedule: hist[idx[i]] = rows[i], but only once *gate >= want (every
-// block of the persistent full-neighbour mean has finished the pass whose reads this write-back must follow).
-// The rows were gathered a pass earlier, so each thread loads its first vectors BEFORE it waits and only the
-// stores are left behind the gate; the last block to finish raises *done_flag to done_value.
-struct GateArgs {
-    const int32_t* gate; int want; int32_t* err;
-    int32_t* done_flag; int done_value; int32_t* counter; int32_t* pipe_done;
-};
-__global__ void __launch_bounds__(kRowThreads)
-history_update_gated_kernel(const float* __restrict__ rows, int64_t ld_rows, const int32_t* __restrict__ idx,
-                            int n_host, const int32_t* __restrict__ n_dev, int c4, float* __restrict__ hist,
-                            int64_t ld_h, unsigned long long* trace, const GateArgs g) {
-    TraceScope ts(trace, TR_UPDATE);
-    __shared__ int s_ok, s_last;
-    const int n = dev_count(n_dev, n_host);
-    const int64_t total = (int64_t)n * c4;
-    const int64_t stride = (int64_t)gridDim.x * kRowThreads;
-    const int64_t first = (int64_t)blockIdx.x * kRowThreads + threadIdx.x;
-    float4 v[kRowUnroll];
-    int64_t off_dst[kRowUnroll];
-    auto load = [&](int64_t base) {
-#pragma unroll
-        for (int u = 0; u < kRowUnroll; ++u) {
-            const int64_t t = base + (int64_t)u * stride;
-            off_dst[u] = -1;
-            if (t < total) {
-                const int r = (int)(t / c4);
-                const int c = (int)(t - (int64_t)r * c4) * 4;
-                off_dst[u] = (int64_t)idx[r] * ld_h + c;
-                v[u] = ldg_stream4(rows + (int64_t)r * ld_rows + c);
-            }
-        }
-    };
-    load(first);
-    if (threadIdx.x == 0) {
-        s_ok = spin_until_ge(g.gate, g.want, g.err) ? 1 : 0;
-        if (s_ok && g.pipe_done && blockIdx.x == 0) atomicAdd(g.pipe_done, 1);    // the pass's adjacency reads are over
-        __threadfence();
-    }
-    __syncthreads();
-    if (s_ok) {
-        for (int64_t base = first; base < total; base += stride * kRowUnroll) {
-            if (base != first) load(base);
-#pragma unroll
-            for (int u = 0; u < kRowUnroll; ++u)
-                if (off_dst[u] >= 0) stg_stream4(hist + off_dst[u], v[u]);
-        }
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(g.counter, 1) == (int)gridDim.x - 1;
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        *g.counter = 0;
-        __threadfence();
-        atomicMax(g.done_flag, g.done_value);
-    }
-}
-
 // scalar fallback for widths / strides / pointers that are not 16-byte friendly (e.g. C = 1433)
 template <int MODE>
 __global__ void __launch_bounds__(kRowThreads)
@@ -194,7 +135,8 @@ static int launch_move_rows(const float* src, int64_t ld_src, const int32_t* idx
 struct PadJob { const float* src; int64_t ld_src; const int32_t* idx; int n; const int32_t* n_dev; int n_total;
                 int C; float* dst; int64_t ld_dst; int pad; };
 constexpr int kPadJobs = 3;
-struct PadJobs { PadJob j[kPadJobs]; ShardMap smap; /* of job 0's gather source (world <= 1: off) */ };
+struct PadJobs { PadJob j[kPadJobs]; ShardMap smap; /* of job 0's gather source (world <= 1: off) */
+                 int stream_l2, stream_l2_pct; /* L2 policy of the gathered (read-once) source rows */ };
 
 __global__ void __launch_bounds__(kRowThreads)
 pad_jobs_kernel(const PadJobs p, unsigned long long* trace) {
@@ -205,6 +147,7 @@ pad_jobs_kernel(const PadJobs p, unsigned long long* trace) {
     if (!a.dst || a.n_total <= 0 || a.C <= 0) return;
     const int n = dev_count(a.n_dev, a.n);
     const int rows = a.pad ? a.n_total : min(n, a.n_total);
+    const uint64_t spol = l2_policy(a.idx ? p.stream_l2 : 0, p.stream_l2_pct);
     const bool vec = (a.C & 3) == 0 && (a.ld_dst & 3) == 0 && (((uintptr_t)a.dst) & 15) == 0 &&
                      (a.n == 0 || ((a.ld_src & 3) == 0 && (((uintptr_t)a.src) & 15) == 0));
     const int64_t stride = (int64_t)gridDim.x * kRowThreads;
@@ -225,7 +168,7 @@ pad_jobs_kernel(const PadJobs p, unsigned long long* trace) {
                     off_dst[u] = (int64_t)r * a.ld_dst + c;
                     if (r < n) {
                         const int64_t rs = a.idx ? (int64_t)a.idx[r] : (int64_t)r;
-                        v[u] = ldg_stream4((sharded_src ? shard_row(p.smap, a.src, rs, a.ld_src) : a.src + rs * a.ld_src) + c);
+                        v[u] = ldg_stream4_hint((sharded_src ? shard_row(p.smap, a.src, rs, a.ld_src) : a.src + rs * a.ld_src) + c, spol);
                     } else {
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
@@ -315,26 +258,6 @@ int sgcn_history_update(float* hist, int64_t ld_h, const int32_t* idx, int32_t n
                                done_counter);
 }
 
-int sgcn_history_update_gated(float* hist, int64_t ld_h, const int32_t* idx, int32_t n, const int32_t* n_dev,
-                              const float* rows, int64_t ld_rows, int32_t D, const int32_t* gate, int32_t want,
-                              int32_t* err, int32_t* done_flag, int32_t done_value, int32_t* counter,
-                              int32_t* pipe_done, void* stream) {
-    SGCN_REQUIRE(n > 0 && D > 0 && hist && idx && rows && gate && err && done_flag && counter,
-                 "history_update_gated: bad argument");
-    SGCN_REQUIRE(ld_h >= D && ld_rows >= D && vec4_ok(rows, ld_rows, hist, ld_h, D),
-                 "history_update_gated: rows must be 16-byte aligned multiples of 4 floats");
-    const int c4 = D / 4;
-    const int64_t total = (int64_t)n * c4;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((total + (int64_t)kRowThreads * kRowUnroll - 1) /
-                                                                   ((int64_t)kRowThreads * kRowUnroll), kNumSMs));
-    SGCN_MATCH_CARVEOUT(history_update_gated_kernel);
-    const GateArgs g{gate, want, err, done_flag, done_value, counter, pipe_done};
-    history_update_gated_kernel<<<blocks, kRowThreads, 0, (cudaStream_t)stream>>>(rows, ld_rows, idx, n, n_dev, c4, hist,
-                                                                                  ld_h, g_trace, g);
-    SGCN_LAUNCHED();
-    return SGCN_OK;
-}
-
 int sgcn_copy_rows_pad(const float* src, int64_t ld_src, int32_t n, const int32_t* n_dev,
                        int32_t n_total, int32_t D, float* dst, int64_t ld_dst, void* stream) {
     SGCN_REQUIRE(n >= 0 && n_total >= 0 && D >= 0, "copy_rows_pad: negative size");
@@ -382,6 +305,8 @@ int sgcn_gather_pad_pair(const float* src, int64_t ld_src, const int32_t* idx, i
         SGCN_REQUIRE(vec4_ok(src, ld_src, dst, ld_dst, C), "sharded features need 16-byte aligned rows");
         p.smap = t_feat_map;
     }
+    p.stream_l2 = g_stream_l2[0];
+    p.stream_l2_pct = g_stream_l2[1];
     return launch_pad_jobs(p, 3, (cudaStream_t)stream);
 }
 

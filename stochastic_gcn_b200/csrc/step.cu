@@ -39,7 +39,7 @@ struct sgcn_step {
     int32_t* ids_stage[2] = {nullptr, nullptr};     // staging of host ids, one per train parity
     static constexpr int kRing2 = 8;
     cudaEvent_t t_pre[kRing2]{}, t_full[kRing2]{}, t_fwd[kRing2]{}, t_rest[kRing2]{}, t_d2h[kRing2]{}, t_train[4]{};
-    int32_t* flags = nullptr;                       // sgcn_step_run_persistent: device counters (8 + 64 ints)
+    int32_t* flags = nullptr;                       // counters of the fused write-back (8 ints, sgcn_full_history_mean_wb)
 };
 
 namespace sgcn {
@@ -124,8 +124,8 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
         for (cudaEvent_t* e : {&st->t_pre[i], &st->t_full[i], &st->t_fwd[i], &st->t_rest[i], &st->t_d2h[i]})
             CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&st->t_train[i], cudaEventDisableTiming));
-    CK(cudaMalloc(&st->flags, sizeof(int32_t) * (8 + 64)));
-    CK(cudaMemset(st->flags, 0, sizeof(int32_t) * (8 + 64)));
+    CK(cudaMalloc(&st->flags, sizeof(int32_t) * 8));
+    CK(cudaMemset(st->flags, 0, sizeof(int32_t) * 8));
     {
         // trains of batches: 2 x train buffer sets (the passes of one train run while the next is sampled)
         const int T = d.train > 0 ? d.train : 16;
@@ -185,7 +185,7 @@ void sgcn_step_destroy(sgcn_step* st) {
 int sgcn_step_status(sgcn_step* st, int32_t* timed_out) {
     SGCN_REQUIRE(st && timed_out, "step_status: null argument");
     SGCN_CUDA(cudaDeviceSynchronize());
-    SGCN_CUDA(cudaMemcpy(timed_out, st->flags + 3, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    SGCN_CUDA(cudaMemcpy(timed_out, st->flags + 4, sizeof(int32_t), cudaMemcpyDeviceToHost));
     return SGCN_OK;
 }
 
@@ -342,19 +342,19 @@ int sgcn_step_run(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_
     return SGCN_OK;
 }
 
-// ---- trains of batches + gather ahead + (optionally) the write-back off the critical path ----------------
-// What the device timelines of the two schedules above showed (profiles/r02_timeline_ahead.txt): with the
-// gather hoisted one pass ahead, the per-batch sampler became the critical path -- one CTA, 17-19 us per batch
-// under load, strictly serial from batch to batch (engine state), i.e. ~21 us per pass however far ahead it
-// runs.  Here a whole train of batches is sampled by ONE launch (sgcn_sampler_expand_train: one CTA per batch,
-// serial only in the prefix sum of the draw counts), one train ahead of the passes that consume it:
+// ---- trains of batches + gather ahead + the write-back fused into the full-neighbour mean ------------------
+// What the device timelines of the schedule above showed (profiles/r02_timeline_ahead_sampler_bound.txt): with
+// the gather hoisted one pass ahead, the per-batch sampler became the critical path -- one CTA, 17-19 us per
+// batch under load, strictly serial from batch to batch (engine state), i.e. ~21 us per pass however far ahead
+// it runs.  Here a whole train of batches is sampled by ONE launch (sgcn_sampler_expand_train: one CTA per
+// batch, serial only in the prefix sum of the draw counts), one train ahead of the passes that consume it:
 //   samp  : [rest of train c-2] (H2D ids of train c) -> mt_stream -> expand_train(c)
 //   pre   : [train of pass k+1; x0 / dx / out copies free] gather(k+1) + dX init(k+1) + zero out(k+1)
-//   chain : [train, pre k, write-back k-2] full_mean(k) -PDL-> full_mean(k+1) ...        (overlap_write_back)
-//   side  : [pre k] sampled fwd+bwd(k) -> [full_mean k] write-back(k) -> sampled(k+1) ...
-// overlap_write_back: full_mean(k+1) reads the rows of field(k) from pass k's gathered rows instead of waiting
-// for write-back k (sgcn_full_history_mean_ov) -- the values are the same bits, so results do not change.
-// Without it (multi-GPU exchange, or > 4096 rows per write-back) the write-back stays on the chain:
+//   chain : [train, pre k] full_mean(k) + write-back(k) in its tail -PDL-> full_mean(k+1) ...   (fuse_write_back)
+//   side  : [pre k, chain k-1] sampled fwd+bwd(k)  (signals the tail of full_mean(k) on the device)
+// fuse_write_back (single GPU, CV / CVD): the write-back is carried by the last thread blocks of the pass's own
+// full-neighbour mean (sgcn_full_history_mean_wb), after every read of the table by that pass.  Without it
+// (multi-GPU exchange) the write-back is a launch of its own on the chain:
 //   chain : full_mean(k) -> [sampled k] write-back(k) -> full_mean(k+1)
 int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
                          int32_t first_train, void* stream) {
@@ -370,7 +370,7 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
     sgcn_sampler* smp = st->sampler;
     const int B = d.batch, H = d.hidden, R = sgcn_step::kRing2, T = st->train;
     const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0, multi = d.world > 1 && cv;
-    const bool overlap = cv && !multi && d.overlap_write_back != 0 && d.x0_rows <= 4096;
+    const bool fuse = cv && !multi && d.fuse_write_back != 0;
     const bool ring = multi && d.ring > 0;
     const bool sharded = d.shard_rows > 0 && d.world > 1;
     if (sharded) SGCN_REQUIRE(!cv || ring, "step_run_trains: sharded tables need the ring form of the exchange");
@@ -412,6 +412,11 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
     SGCN_CUDA(cudaEventRecord(st->ev_begin, user));
     for (cudaStream_t s : {chain, side, samp, pre}) SGCN_CUDA(cudaStreamWaitEvent(s, st->ev_begin, 0));
     if (out_host) SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_begin, 0));
+    if (fuse) {       // counters of the fused write-back: zero before the first sampled aggregate / mean of the run
+        STEP_TRY(sgcn_wb_counters_reset(st->flags, chain));
+        SGCN_CUDA(cudaEventRecord(st->ev_zero0, chain));
+        SGCN_CUDA(cudaStreamWaitEvent(side, st->ev_zero0, 0));
+    }
 
     auto issue_train = [&](int c) -> int {
         const int len = tb(c + 1) - tb(c);
@@ -436,7 +441,7 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
             SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_fwd[(k - 2) % R], 0));
             if (out_host) SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_d2h[(k - 2) % R], 0));
         }
-        // x0 copy k % 3: read by sampled(k-3), write-back(k-3) and the override of full_mean(k-2)
+        // x0 copy k % 3: read by sampled(k-3) and write-back(k-3)
         if (k >= 3) SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_rest[(k - 3) % R], 0));
         STEP_TRY(sgcn_gather_pad_pair(d.features, d.ld_feat, v.field, d.x0_rows, v.meta + 1, d.feat_dim, x0b[k % 3], d.ld_x0,
                                       concat ? d.d_out : nullptr, d.ld_dout, concat ? B : 0,
@@ -478,15 +483,12 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
         SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_train[c % 4], 0));
         SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_pre[k % R], 0));
         if (cv) {
-            if (overlap && k >= 1) {
-                // rows of field(k-1) come from pass k-1's gathered rows; everything older is in the table
-                if (k >= 2) SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_rest[(k - 2) % R], 0));
-                const sgcn_step::Lv& pv = st->tlv[(size_t)set_of(k - 1)];
-                const float* prow = x0b[(k - 1) % 3] + (cvd ? H : 0);
-                STEP_TRY(sgcn_full_history_mean_ov(v.field, v.rowptr_f, B, n_out_dev, st->adj_p, st->adj_i, st->adj_w,
+            if (fuse) {
+                STEP_TRY(sgcn_full_history_mean_wb(v.field, v.rowptr_f, B, n_out_dev, st->adj_p, st->adj_i, st->adj_w,
                                                    d.history, d.ld_hist, H, cvd ? nb(outmu_r) : nb(out_r), d.ld_out,
-                                                   cvd ? nb(out_r) : nullptr, d.ld_out, pv.field, pv.meta + 1,
-                                                   d.x0_rows, prow, d.ld_x0, chain));
+                                                   cvd ? nb(out_r) : nullptr, d.ld_out, v.field, n_in_dev, d.x0_rows,
+                                                   new_hist, d.ld_x0, st->flags, st->pipe + 1, chain));
+                SGCN_CUDA(cudaEventRecord(st->t_rest[k % R], chain));
             } else {
                 STEP_TRY(sgcn_full_history_mean(v.field, v.rowptr_f, B, n_out_dev, st->adj_p, st->adj_i, st->adj_w,
                                                 d.history, d.ld_hist, H, cvd ? nb(outmu_r) : nb(out_r), d.ld_out,
@@ -502,7 +504,8 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
         {
         PdlOff side_plain;
         SGCN_CUDA(cudaStreamWaitEvent(side, st->t_pre[k % R], 0));
-        if (k >= 1 && !overlap) SGCN_CUDA(cudaStreamWaitEvent(side, st->t_rest[(k - 1) % R], 0));
+        if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(side, st->t_rest[(k - 1) % R], 0));     // history as of write-back k-1
+        if (fuse) STEP_TRY(sgcn_sampled_done_attach(st->flags));
         if (d.mode == 0) {
             STEP_TRY(sgcn_spmm_csr(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, x, d.ld_x0, H, nb(out_r),
                                    d.ld_out, 0, side));
@@ -527,15 +530,9 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
                                               d.ld_dx, side));
         }
         SGCN_CUDA(cudaEventRecord(st->t_fwd[k % R], side));
+        }
         // ---- write-back after every forward read of history (gcn/models.py:186-194) ----
-        if (overlap) {
-            SGCN_CUDA(cudaStreamWaitEvent(side, st->t_full[k % R], 0));
-            STEP_TRY(sgcn_history_update(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
-                                         st->pipe + 1, side));
-            SGCN_CUDA(cudaEventRecord(st->t_rest[k % R], side));
-        }
-        }
-        if (!overlap) {                  // on the chain (programmatic launch: it is the chain's next link)
+        if (!fuse) {                     // on the chain (programmatic launch: it is the chain's next link)
             SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_fwd[k % R], 0));
             if (!cv) {
                 STEP_TRY(sgcn_sampler_mark_consumed(smp, chain));
@@ -576,192 +573,6 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
     SGCN_CUDA(cudaEventRecord(st->ev_zero0, chain));
     if (out_host) SGCN_CUDA(cudaStreamWaitEvent(user, st->t_d2h[(n - 1) % R], 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->t_rest[(n - 1) % R], 0));
-    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_zero0, 0));
-    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
-    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));
-    SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_pre_end, 0));
-    return SGCN_OK;
-}
-
-// ---- persistent form of the trains schedule (single GPU, CV / CVD) ------------------------------------------
-// Same passes, same arithmetic as sgcn_step_run_trains with the write-back off the chain, but the chain is ONE
-// kernel: sgcn_full_history_mean_passes keeps its thread blocks resident for all n passes and every dependency
-// that crossed a kernel boundary on the chain is a device-side counter instead (flags, see the header):
-//   chain : flags_reset -> full_mean_persistent (passes 0 .. n-1, waits on the counters below)
-//   samp  : expand_train(c) -> flags[TRAINS] = c + 1
-//   pre   : [gate k-2, sampled k-2, rows k-2 on the host, write-back k-3] gather(k) + dX init + zero out(k)
-//           -> flags[PRE] = k + 1
-//   side  : [pre k] sampled fwd+bwd(k) -> gate: flags[FULL + k] == blocks -> write-back(k) -> flags[WB] = k + 1
-//   copy  : [gate k, sampled k] rows of pass k -> pinned host memory
-// Every wait is on work submitted EARLIER by the host, so the schedule cannot deadlock whatever the hardware
-// queues do with the order; every spin is bounded (flags[3] != 0 afterwards: a counter never arrived).
-int sgcn_step_run_persistent(sgcn_step* st, const int32_t* ids, int32_t ids_on_host, int32_t n, float* out_host,
-                             int32_t first_train, void* stream) {
-    SGCN_REQUIRE(st && n >= 0 && (n == 0 || ids) && first_train >= 0, "step_run_persistent: bad argument");
-    if (n == 0) return SGCN_OK;
-    const sgcn_step_desc& d = st->d;
-    const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0;
-    if (st->train <= 0 || !cv || d.world > 1 || d.x0_rows > 4096 || d.batch > 4096) {
-        set_error("step_run_persistent: single GPU, CV / CVD, at most 4096 rows per write-back, and a sampler that "
-                  "can sample trains of batches; use sgcn_step_run_trains");
-        return SGCN_ESTATE;
-    }
-    SGCN_REQUIRE(d.x0_alt[0] && d.x0_alt[1] && d.dx_alt, "step_run_persistent: desc.x0_alt / dx_alt are required");
-    const int B = d.batch, H = d.hidden;
-    const int width = H * (concat ? 2 : 1);
-    constexpr int kChunk = 64;                     // passes per persistent launch
-    if (n > kChunk) {                              // longer runs: one persistent launch after the other
-        for (int k0 = 0; k0 < n; k0 += kChunk) {
-            const int len = std::min(kChunk, n - k0);
-            STEP_TRY(sgcn_step_run_persistent(st, ids + (int64_t)k0 * B, ids_on_host, len,
-                                              out_host ? out_host + (int64_t)k0 * B * width : nullptr,
-                                              k0 == 0 ? first_train : std::min<int>(first_train > 0 ? first_train : st->train, 4),
-                                              stream));
-        }
-        return SGCN_OK;
-    }
-    sgcn_sampler* smp = st->sampler;
-    const int R = sgcn_step::kRing2, T = st->train;
-    cudaStream_t user = (cudaStream_t)stream, chain = st->chain, side = st->side, samp = st->samp, pre = st->pre,
-                 copy = st->copy;
-    float* x0b[3] = {d.x0, d.x0_alt[0], d.x0_alt[1]};
-    float* dxb[2] = {d.dx, d.dx_alt};
-    auto nb = [&](float* base) { return base + (concat ? H : 0); };
-    int32_t* F = st->flags;
-    enum { F_TRAINS = 0, F_PRE = 1, F_WB = 2, F_ERROR = 3, F_FULL = 8 };
-
-    const int T0 = first_train > 0 ? std::min<int>(first_train, T) : T;
-    auto tb = [&](int c) { return c <= 0 ? 0 : std::min(n, T0 + (c - 1) * T); };
-    const int n_trains = n <= T0 ? 1 : 1 + (n - T0 + T - 1) / T;
-    auto train_of = [&](int k) { return k < T0 ? 0 : 1 + (k - T0) / T; };
-    auto set_of = [&](int k) { const int c = train_of(k); return (c & 1) * T + (k - tb(c)); };
-    auto ids_of = [&](int c) -> const int32_t* {
-        return ids_on_host ? st->ids_stage[c & 1] : ids + (int64_t)tb(c) * B;
-    };
-    PdlOff plain;                                  // no programmatic launches: the counters carry the order
-
-    SGCN_CUDA(cudaEventRecord(st->ev_begin, user));
-    SGCN_CUDA(cudaStreamWaitEvent(chain, st->ev_begin, 0));
-    STEP_TRY(sgcn_flags_reset(F, 8 + 64, chain));
-    SGCN_CUDA(cudaEventRecord(st->ev_zero0, chain));
-    for (cudaStream_t s : {side, samp, pre}) SGCN_CUDA(cudaStreamWaitEvent(s, st->ev_zero0, 0));
-    if (out_host) SGCN_CUDA(cudaStreamWaitEvent(copy, st->ev_zero0, 0));
-
-    // ---- chain: the persistent full-neighbour mean over all n passes ----
-    int n_blocks = 0;
-    {
-        sgcn_full_pass passes[kChunk];
-        for (int k = 0; k < n; ++k) {
-            const sgcn_step::Lv& v = st->tlv[(size_t)set_of(k)];
-            float* out_r = d.out[k & 1];
-            float* outmu_r = d.out_mu[k & 1];
-            sgcn_full_pass& p = passes[k];
-            p.nodes = v.field; p.rowptr_f = v.rowptr_f; p.n_out_dev = v.meta + 0;
-            p.y0 = cvd ? nb(outmu_r) : nb(out_r);
-            p.y1 = cvd ? nb(out_r) : nullptr;
-            p.ov_ids = nullptr; p.ov_n_dev = nullptr; p.ov_rows = nullptr;
-            if (k >= 1) {
-                const sgcn_step::Lv& pv = st->tlv[(size_t)set_of(k - 1)];
-                p.ov_ids = pv.field; p.ov_n_dev = pv.meta + 1;
-                p.ov_rows = x0b[(k - 1) % 3] + (cvd ? H : 0);
-            }
-            p.train = train_of(k); p.pad = 0;
-        }
-        STEP_TRY(sgcn_full_history_mean_passes(passes, n, B, st->adj_p, st->adj_i, st->adj_w, d.history, d.ld_hist, H,
-                                               d.ld_out, d.ld_out, d.x0_rows, d.ld_x0, F, &n_blocks, chain));
-    }
-
-    auto issue_train = [&](int c) -> int {
-        const int len = tb(c + 1) - tb(c);
-        if (c >= 2) SGCN_CUDA(cudaStreamWaitEvent(samp, st->t_rest[(tb(c - 1) - 1) % R], 0));
-        if (ids_on_host)
-            SGCN_CUDA(cudaMemcpyAsync(st->ids_stage[c & 1], ids + (int64_t)tb(c) * B, sizeof(int32_t) * (size_t)len * B,
-                                      cudaMemcpyHostToDevice, samp));
-        STEP_TRY(sgcn_sampler_expand_train(smp, ids_of(c), len, (c & 1) * T, c >= 1 ? ids_of(c - 1) : nullptr,
-                                           c >= 1 ? (tb(c) - tb(c - 1)) * B : 0, samp));
-        STEP_TRY(sgcn_flag_set(F + F_TRAINS, c + 1, samp));
-        SGCN_CUDA(cudaEventRecord(st->t_train[c % 4], samp));
-        return SGCN_OK;
-    };
-    auto ahead = [&](int k) -> int {
-        const sgcn_step::Lv& v = st->tlv[(size_t)set_of(k)];
-        const int r = k & 1;
-        SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_train[train_of(k) % 4], 0));
-        if (k >= 2) {     // out / dx copy r: pass k-2 is complete (gate) and its rows have left for the host
-            SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_full[(k - 2) % R], 0));      // = after the gate of pass k-2
-            SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_fwd[(k - 2) % R], 0));
-            if (out_host) SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_d2h[(k - 2) % R], 0));
-        }
-        if (k >= 3) SGCN_CUDA(cudaStreamWaitEvent(pre, st->t_rest[(k - 3) % R], 0));
-        STEP_TRY(sgcn_gather_pad_pair(d.features, d.ld_feat, v.field, d.x0_rows, v.meta + 1, d.feat_dim, x0b[k % 3], d.ld_x0,
-                                      concat ? d.d_out : nullptr, d.ld_dout, concat ? B : 0,
-                                      concat ? v.meta + 0 : nullptr, d.x0_rows, H, dxb[r], d.ld_dx,
-                                      nullptr, 0, 0, nullptr, B, H, nb(d.out[r]), d.ld_out, pre));
-        if (cvd) STEP_TRY(sgcn_copy_rows_pad(nullptr, 0, 0, nullptr, B, H, nb(d.out_mu[r]), d.ld_out, pre));
-        STEP_TRY(sgcn_flag_set(F + F_PRE, k + 1, pre));
-        SGCN_CUDA(cudaEventRecord(st->t_pre[k % R], pre));
-        return SGCN_OK;
-    };
-
-    STEP_TRY(sgcn_sampler_set_stream_async(smp, samp));
-    for (int slot = 0; slot < 3; ++slot) {
-        STEP_TRY(sgcn_sampler_set_slot(smp, slot));
-        STEP_TRY(sgcn_sampler_start_batch_device(smp, 0, nullptr));
-    }
-    STEP_TRY(issue_train(0));
-    if (n_trains > 1) STEP_TRY(issue_train(1));
-    STEP_TRY(ahead(0));
-
-    for (int k = 0; k < n; ++k) {
-        const int r = k & 1, c = train_of(k);
-        const sgcn_step::Lv& v = st->tlv[(size_t)set_of(k)];
-        const int32_t* n_out_dev = v.meta + 0;
-        const int32_t* n_in_dev = v.meta + 1;
-        float* out_r = d.out[r];
-        float* outmu_r = d.out_mu[r];
-        const float* x = x0b[k % 3];
-        const float* mu = x + H;
-        const float* new_hist = cvd ? mu : x;
-        const float* d_nb = d.d_out + (concat ? H : 0);
-
-        if (k + 1 < n) STEP_TRY(ahead(k + 1));
-        // ---- side: sampled aggregate + backward (history as of write-back k-1: stream order) ----
-        SGCN_CUDA(cudaStreamWaitEvent(side, st->t_pre[k % R], 0));
-        if (!cvd) {
-            STEP_TRY(sgcn_cv_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, B, n_out_dev, x, d.ld_x0, d.history,
-                                             d.ld_hist, H, nb(out_r), d.ld_out, concat ? out_r : nullptr, d.ld_out, 1,
-                                             d_nb, d.ld_dout, dxb[r], d.ld_dx, side));
-        } else {
-            STEP_TRY(sgcn_cvd_sampled_fwd_bwd(v.rowptr_s, v.edg_t, v.edg_w, v.tgt, v.scales, B, n_out_dev, x, d.ld_x0,
-                                              mu, d.ld_x0, d.history, d.ld_hist, H, nb(out_r), d.ld_out,
-                                              nb(outmu_r), d.ld_out, concat ? out_r : nullptr, d.ld_out,
-                                              concat ? outmu_r : nullptr, d.ld_out, 1, d_nb, d.ld_dout, dxb[r],
-                                              d.ld_dx, side));
-        }
-        SGCN_CUDA(cudaEventRecord(st->t_fwd[k % R], side));
-        // ---- write-back, gated on the device: every block of the persistent kernel has finished pass k (the
-        //      next pass reads these rows through the override until they have landed).  One launch: a separate
-        //      gate + write-back + signal made the side branch (4 dependent launches per pass, 4-5 us each under
-        //      load) the critical path: 29 us per pass (profiles/r02_timeline_persistent_first.txt) ----
-        STEP_TRY(sgcn_history_update_gated(d.history, d.ld_hist, v.field, d.x0_rows, n_in_dev, new_hist, d.ld_x0, H,
-                                           F + F_FULL + k, n_blocks, F + F_ERROR, F + F_WB, k + 1, F + 4, st->pipe + 1,
-                                           side));
-        SGCN_CUDA(cudaEventRecord(st->t_full[k % R], side));
-        SGCN_CUDA(cudaEventRecord(st->t_rest[k % R], side));
-        if (out_host) {
-            SGCN_CUDA(cudaStreamWaitEvent(copy, st->t_full[k % R], 0));
-            SGCN_CUDA(cudaMemcpy2DAsync(out_host + (int64_t)k * B * width, sizeof(float) * (size_t)width, out_r,
-                                        sizeof(float) * (size_t)d.ld_out, sizeof(float) * (size_t)width, (size_t)B,
-                                        cudaMemcpyDeviceToHost, copy));
-            SGCN_CUDA(cudaEventRecord(st->t_d2h[k % R], copy));
-        }
-        if (k + 1 == tb(c + 1) && c + 2 < n_trains) STEP_TRY(issue_train(c + 2));
-    }
-    SGCN_CUDA(cudaEventRecord(st->ev_side_end, side));
-    SGCN_CUDA(cudaEventRecord(st->ev_samp_end, samp));
-    SGCN_CUDA(cudaEventRecord(st->ev_pre_end, pre));
-    SGCN_CUDA(cudaEventRecord(st->ev_zero0, chain));
-    if (out_host) SGCN_CUDA(cudaStreamWaitEvent(user, st->t_d2h[(n - 1) % R], 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_zero0, 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_side_end, 0));
     SGCN_CUDA(cudaStreamWaitEvent(user, st->ev_samp_end, 0));

@@ -81,8 +81,7 @@ class HotPathStep:
         self._pipe_done = None
         self._last_slot = 0
         self.train = 16                # batches sampled per launch by the trains schedule (run_trains)
-        self.overlap_write_back = False  # trains schedule: write-back off the chain (row override in the next mean)
-        self.persistent = False        # trains schedule with ONE persistent full-mean launch per run (single GPU, CV / CVD)
+        self.fuse_write_back = True    # trains schedule, single GPU: write-back in the tail of the full-neighbour mean
         self._trains = None            # captured graphs of the trains schedule
         self._last_x0 = self._last_dx = None
         self._s_b = torch.cuda.Stream(device=self.dev)      # side branch of the pass
@@ -522,7 +521,7 @@ class HotPathStep:
             self._alt_bufs = (torch.zeros_like(self.x0), torch.zeros_like(self.x0), torch.zeros_like(self.dx))
         d.x0_alt[0], d.x0_alt[1] = self._alt_bufs[0].data_ptr(), self._alt_bufs[1].data_ptr()
         d.dx_alt = self._alt_bufs[2].data_ptr()
-        d.train, d.overlap_write_back = int(self.train), int(bool(self.overlap_write_back))
+        d.train, d.fuse_write_back = int(self.train), int(bool(self.fuse_write_back))
         return d
 
     def run_native(self, batches, out_host=None):
@@ -595,7 +594,7 @@ class HotPathStep:
     def run_trains(self, table, out_host=None, first_train=0):
         """n consecutive passes through sgcn_step_run_trains on the current stream: the sampler runs a TRAIN of
         `self.train` batches per launch, one train ahead of the passes; gather / dX init / zeroing one pass
-        ahead; full-neighbour means back to back (write-back off the chain when self.overlap_write_back).
+        ahead; full-neighbour means back to back (the write-back rides in their tails when self.fuse_write_back).
         ``table``: contiguous int32 [n, B] ids on the GPU or in PINNED host memory; ``out_host``: optional pinned
         float32 [n, B, width] receiving every pass's aggregated rows; ``first_train``: length of the first
         train (0 = self.train; a short one shortens the start-up bubble).  Returns the last pass's rows."""
@@ -604,10 +603,9 @@ class HotPathStep:
             return self.out
         h = self._native_handle()
         self._trains_keep = (table, out_host)          # borrowed by the driver until the run completes
-        lib = _lib.load()
-        fn = lib.sgcn_step_run_persistent if (self.persistent and self.mode != "ns") else lib.sgcn_step_run_trains
-        _lib.check(fn(h, _lib.ptr(table), int(not table.is_cuda), n,
-                      _lib.ptr(out_host) if out_host is not None else None, int(first_train), _lib.stream_ptr()))
+        _lib.check(_lib.load().sgcn_step_run_trains(h, _lib.ptr(table), int(not table.is_cuda), n,
+                                                    _lib.ptr(out_host) if out_host is not None else None,
+                                                    int(first_train), _lib.stream_ptr()))
         self._trains_done(n, first_train)
         return self.out
 
@@ -673,14 +671,14 @@ class HotPathStep:
         return self.out
 
     def check_flags(self):
-        """Raise if a device-side wait of the persistent schedule timed out (synchronises)."""
+        """Raise if a device-side wait of the fused write-back timed out (synchronises)."""
         import ctypes as C
         if getattr(self, "_native_h", None) is None:
             return
         bad = C.c_int32()
         _lib.check(_lib.load().sgcn_step_status(self._native_h, C.byref(bad)))
         if bad.value:
-            raise _lib.SgcnError(_lib.SGCN_EDATA, "a device-side wait of the persistent schedule timed out")
+            raise _lib.SgcnError(_lib.SGCN_EDATA, "a device-side wait of the fused write-back timed out")
 
     @property
     def last_x0(self):

@@ -46,7 +46,7 @@ def record(name, entry):
         json.dump(SUMMARY, f, indent=1)
 
 
-def run_case(name, workload, S, n_graphs, host_io, overlap=False, persistent=False):
+def run_case(name, workload, S, n_graphs, host_io, fuse=True):
     import bench
     from stochastic_gcn_b200.step import HotPathStep
     w = bench.WORKLOADS[workload]
@@ -54,8 +54,7 @@ def run_case(name, workload, S, n_graphs, host_io, overlap=False, persistent=Fal
     g, feats = bench.build_inputs(w, 1, dev, 1.0)
     B, D, deg, mode = w["batch"], w["hidden"], w["degree"], w["mode"]
     step = HotPathStep(g, feats, D, B, deg, mode=mode, seed=1)
-    step.overlap_write_back = overlap
-    step.persistent = persistent
+    step.fuse_write_back = fuse
     gen = torch.Generator(device=dev).manual_seed(11)
     step.history.normal_(generator=gen)
     step.d_out.normal_(generator=gen)
@@ -88,6 +87,7 @@ def run_case(name, workload, S, n_graphs, host_io, overlap=False, persistent=Fal
     else:
         step.replay_trains(table[S:])
     torch.cuda.synchronize()
+    step.check_flags()
 
     worst_max, worst_elem, checked = 0.0, 0.0, 0
     for i in range(n):
@@ -101,7 +101,7 @@ def run_case(name, workload, S, n_graphs, host_io, overlap=False, persistent=Fal
     m_out, e_out = errors(step.out.cpu().numpy(), oh)
     m_dx, e_dx = errors(step.last_dx.cpu().numpy()[:z["n_in"]], dx)
     entry = {"workload": workload, "passes": n, "passes_with_rows_checked": checked, "graph_passes": S,
-             "host_buffers": host_io, "write_back_off_the_chain": overlap or persistent, "persistent_chain": persistent, "sampler_oracle": cls.__name__, "nodes": g.n, "stored_edges": g.nnz,
+             "host_buffers": host_io, "write_back_fused_into_the_mean": bool(fuse and mode != "ns"), "sampler_oracle": cls.__name__, "nodes": g.n, "stored_edges": g.nnz,
              "rows_max_norm_err": max(worst_max, m_out), "rows_elementwise_bound_ratio": max(worst_elem, e_out),
              "dx_max_norm_err": m_dx, "dx_elementwise_bound_ratio": e_dx, "last_sizes": z}
     if om is not None:
@@ -128,14 +128,9 @@ def test_reddit_cv_d2_device_graph_of_20():
     run_case("reddit_cv_device_graph20", "reddit_cv", 20, 2, False)
 
 
-def test_reddit_cv_d2_write_back_off_the_chain():
-    """same, with the history write-back off the chain (row override in the next pass's full-neighbour mean)"""
-    run_case("reddit_cv_device_graph20_overlap", "reddit_cv", 20, 1, False, overlap=True)
-
-
-def test_reddit_cv_d2_persistent_chain():
-    """same, with ONE persistent full-neighbour-mean launch per graph (sgcn_step_run_persistent), host buffers"""
-    run_case("reddit_cv_e2e_graphs_persistent", "reddit_cv", 20, 2, True, persistent=True)
+def test_reddit_cv_d2_write_back_as_its_own_launch():
+    """same, with the history write-back as a launch of its own on the chain (the multi-GPU form of the chain)"""
+    run_case("reddit_cv_device_graph20_unfused", "reddit_cv", 20, 1, False, fuse=False)
 
 
 def test_reddit_cvd_d1_host_buffer_graphs():

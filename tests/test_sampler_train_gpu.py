@@ -110,8 +110,10 @@ def test_train_shapes_of_the_bench():
 
 def test_train_waits_for_consumers_of_the_previous_train():
     """Pipeline mode: a batch that shares a node with the previous train must not permute that row before the
-    previous train's consumer passes are marked finished -- here they are marked from another stream AFTER
-    the train has been launched, so the train's thread block really waits."""
+    previous train's consumer passes are marked finished.  As in the step drivers, the marks are work that is
+    already queued when the train is launched (here: on another stream, behind a ~1 ms sleep kernel), so the
+    train's thread block really waits on the device -- and the permuted rows come out as the sequential
+    reference leaves them."""
     n, B, degree = 3000, 64, 2
     g = random_graph(n, 12, 78)
     o = native.OracleSampler(g.data, g.indices, g.indptr, cv=True)
@@ -119,9 +121,7 @@ def test_train_waits_for_consumers_of_the_previous_train():
     o.seed(9)
     s.reserve_sets(8, B, degree)
     a, b = torch.cuda.Stream(), torch.cuda.Stream()
-    # first launch of the mark kernel here, NOT while a train is spinning: with CUDA's lazy module loading a
-    # kernel's first launch may have to wait for the device to go idle (the step drivers run warm-up passes)
-    s.mark_consumed(b)
+    s.mark_consumed(b)                          # first launch of the mark kernel (module load) outside the test
     torch.cuda.synchronize()
     s.pipeline(True)                            # arms the guard, counters back to zero
     rng = np.random.RandomState(3)
@@ -132,11 +132,11 @@ def test_train_waits_for_consumers_of_the_previous_train():
     d0, d1 = torch.from_numpy(t0).cuda(), torch.from_numpy(t1).cuda()
     torch.cuda.synchronize()
     s.expand_train(d0, first_set=0, stream=a)
-    s.expand_train(d1, first_set=4, prev=d0, stream=a)
     with torch.cuda.stream(b):                  # (not the legacy default stream: it would wait for stream a)
-        torch.cuda._sleep(2_000_000)            # keep the marks ~1 ms late
+        torch.cuda._sleep(2_000_000)            # the marks land ~1 ms later
     for _ in range(4):
         s.mark_consumed(b)
+    s.expand_train(d1, first_set=4, prev=d0, stream=a)
     torch.cuda.synchronize()
     for j, ids in enumerate(list(t0) + list(t1)):
         o.start_batch(ids)

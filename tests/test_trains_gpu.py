@@ -1,6 +1,6 @@
 """GPU: the trains schedule (csrc/step.cu:sgcn_step_run_trains, HotPathStep.run_trains / capture_trains /
 replay_trains) -- trains of batches sampled by one launch, gather one pass ahead, full-neighbour means back to
-back with the write-back off the chain (row override) -- against the CPU oracle pass after pass: eager and as
+back with the history write-back carried by their tails -- against the CPU oracle pass after pass: eager and as
 CUDA graphs, device and host buffers, CV / CVD / NS, both normalisations, batches that share nodes within a
 train and across trains."""
 import numpy as np
@@ -13,7 +13,7 @@ from tests.test_step_gpu import close, oracle_step
 pytestmark = pytest.mark.gpu
 
 
-def setup(mode, deg, norm, n_batches, train, overlap=True, share=True, seed=4, persistent=False):
+def setup(mode, deg, norm, n_batches, train, fuse=True, share=True, seed=4):
     from stochastic_gcn_b200 import graphs
     from stochastic_gcn_b200.step import HotPathStep
     g = graphs.powerlaw_graph(3000, 120_000, seed=seed, device="cuda", max_degree=600)
@@ -21,7 +21,7 @@ def setup(mode, deg, norm, n_batches, train, overlap=True, share=True, seed=4, p
     gen = torch.Generator(device="cuda").manual_seed(0)
     feats = torch.randn((g.n, 80), generator=gen, device="cuda")
     step = HotPathStep(g, feats, D, B, deg, mode=mode, normalization=norm, seed=5)
-    step.train, step.overlap_write_back, step.persistent = train, overlap, persistent
+    step.train, step.fuse_write_back = train, fuse
     step.history.normal_(generator=gen)
     step.d_out.normal_(generator=gen)
     o = native.OracleSampler(g.data.cpu().numpy(), g.indices.cpu().numpy(), g.indptr.cpu().numpy(), cv=mode != "ns")
@@ -56,17 +56,18 @@ def check_run(step, o, mode, deg, norm, feats, table, D, got_rows, first=0):
 
 @pytest.mark.parametrize("mode,deg,norm", [("cv", 2, "graphsage"), ("cvd", 1, "graphsage"), ("ns", 1, "gcn"),
                                            ("cv", 1, "gcn"), ("ns", 2, "graphsage")])
-@pytest.mark.parametrize("overlap", [True, False])
-def test_eager_trains_match_oracle(mode, deg, norm, overlap):
-    if mode == "ns" and not overlap:
+@pytest.mark.parametrize("fuse", [True, False])
+def test_eager_trains_match_oracle(mode, deg, norm, fuse):
+    if mode == "ns" and not fuse:
         pytest.skip("plain sampling keeps no history: the flag has no effect")
     n = 23
-    g, step, o, feats, table, D = setup(mode, deg, norm, n, train=4, overlap=overlap)
+    g, step, o, feats, table, D = setup(mode, deg, norm, n, train=4, fuse=fuse)
     check_run.hist = step.history.cpu().numpy().copy()
     width = step.outs[0].shape[1]
     rows = torch.empty((n, step.B, width), dtype=torch.float32).pin_memory()
     step.run_trains(table, out_host=rows, first_train=2)
     torch.cuda.synchronize()
+    step.check_flags()
     oh, om, dx, s = check_run(step, o, mode, deg, norm, feats, table, D, [r.numpy() for r in rows])
     z = step.sizes()
     assert z["n_in"] == len(s["field"]) and z["nnz_s"] == len(s["edg_s"])
@@ -94,57 +95,6 @@ def test_pinned_host_ids_and_a_second_run_continue_the_state():
     assert np.array_equal(step.history.cpu().numpy(), check_run.hist)
 
 
-@pytest.mark.parametrize("mode,deg,norm", [("cv", 2, "graphsage"), ("cvd", 1, "graphsage"), ("cv", 1, "gcn")])
-def test_persistent_eager_matches_oracle(mode, deg, norm):
-    """sgcn_step_run_persistent: one full-neighbour-mean launch for the whole run, device-side counters"""
-    n = 23
-    g, step, o, feats, table, D = setup(mode, deg, norm, n, train=4, persistent=True)
-    check_run.hist = step.history.cpu().numpy().copy()
-    width = step.outs[0].shape[1]
-    rows = torch.empty((n, step.B, width), dtype=torch.float32).pin_memory()
-    step.run_trains(table, out_host=rows, first_train=2)
-    torch.cuda.synchronize()
-    step.check_flags()
-    oh, om, dx, s = check_run(step, o, mode, deg, norm, feats, table, D, [r.numpy() for r in rows])
-    z = step.sizes()
-    close(step.out.cpu().numpy(), oh, "last rows on the device")
-    close(step.last_dx.cpu().numpy()[:z["n_in"]], dx, "last dx")
-    assert np.array_equal(step.history.cpu().numpy(), check_run.hist), "history after the run"
-    assert np.array_equal(step.sampler.host("adj_i", step.sampler.num_edges), o.vec("adj_i")), "permuted adjacency"
-
-
-@pytest.mark.parametrize("host_io", [False, True])
-def test_persistent_captured_matches_oracle(host_io):
-    mode, deg, S = "cv", 2, 6
-    g, step, o, feats, table, D = setup(mode, deg, "graphsage", 4 * S, train=4, persistent=True)
-    check_run.hist = step.history.cpu().numpy().copy()
-    step.capture_trains(S, table[:S], host_io=host_io, first_train=2)
-    got, pending = {}, []
-
-    def drain():
-        f0, c0, r0, e0 = pending.pop()
-        e0.synchronize()
-        for j in range(c0):
-            got[f0 + j] = r0[j].clone().numpy()
-
-    def on_chunk(first, count, rows, done):
-        if pending:
-            drain()
-        pending.append((first, count, rows, done))
-
-    if host_io:
-        step.replay_trains(table[S:].cpu().pin_memory(), on_chunk=on_chunk)
-        drain()
-    else:
-        step.replay_trains(table[S:])
-    torch.cuda.synchronize()
-    step.check_flags()
-    rows = [None] * S + [got.get(i) for i in range(3 * S)]
-    oh, om, dx, s = check_run(step, o, mode, deg, "graphsage", feats, table, D, rows)
-    close(step.out.cpu().numpy(), oh, "last rows")
-    assert np.array_equal(step.history.cpu().numpy(), check_run.hist)
-
-
 @pytest.mark.parametrize("mode,deg", [("cv", 2), ("cvd", 1), ("ns", 1)])
 def test_captured_trains_device_tables(mode, deg):
     S = 10
@@ -153,6 +103,7 @@ def test_captured_trains_device_tables(mode, deg):
     step.capture_trains(S, table[:S], first_train=2)           # eager warm-up run = passes 0 .. S-1
     step.replay_trains(table[S:])                              # three replays
     torch.cuda.synchronize()
+    step.check_flags()
     oh, om, dx, s = check_run(step, o, mode, deg, "graphsage", feats, table, D, None)
     z = step.sizes()
     assert z["n_in"] == len(s["field"])
@@ -188,33 +139,49 @@ def test_captured_trains_host_buffers():
     assert np.array_equal(step.history.cpu().numpy(), check_run.hist)
 
 
-def test_full_mean_override_equals_write_back_then_mean():
-    """sgcn_full_history_mean_ov == sgcn_history_update followed by sgcn_full_history_mean, bit for bit up to
-    the order of the 128-bit reductions (same loads, same products)."""
-    import ctypes as C
+@pytest.mark.parametrize("D,ld_rows", [(128, 256), (32, 80), (30, 30), (300, 304)])
+def test_fused_write_back_equals_mean_then_write_back(D, ld_rows):
+    """sgcn_full_history_mean_wb == sgcn_full_history_mean followed by sgcn_history_update: the aggregated rows
+    come from the table BEFORE the write-back (every read precedes every store), the table afterwards holds the
+    new rows bit for bit, the consumer counter moved by one; three passes back to back on one stream (the
+    counters are handed from launch to launch), the sampled aggregate's signal given by a real launch."""
     from stochastic_gcn_b200 import _lib, graphs, ops
     from stochastic_gcn_b200.sampler import DeviceSampler
+    lib = _lib.load()
     g = graphs.powerlaw_graph(5000, 300_000, seed=2, device="cuda", max_degree=900)
-    D, B = 128, 256
+    B = 256
     gen = torch.Generator(device="cuda").manual_seed(1)
     hist = torch.randn((g.n, D), generator=gen, device="cuda")
     s = DeviceSampler(g.data, g.indices, g.indptr, L=1, cv=True)
-    ids = torch.randperm(g.n, generator=gen, device="cuda")[:B].to(torch.int32)
-    s.start_batch(ids); s.expand(2)
-    z = s.sizes()
-    ov_ids = torch.randperm(g.n, generator=gen, device="cuda")[:1500].to(torch.int32).contiguous()
-    ov_n = torch.tensor([1400], dtype=torch.int32, device="cuda")
-    ov_rows = torch.randn((1500, 2 * D), generator=gen, device="cuda")
-    field, rowptr_f = s.view("field"), s.view("rowptr_f")
-    y = torch.zeros((B, D), device="cuda")
-    _lib.check(_lib.load().sgcn_full_history_mean_ov(
-        _lib.ptr(field), _lib.ptr(rowptr_f), B, None, _lib.ptr(s.view("adj_p")), _lib.ptr(s.view("adj_i")),
-        _lib.ptr(s.view("adj_w")), _lib.ptr(hist), D, D, _lib.ptr(y), D, None, 0, _lib.ptr(ov_ids), _lib.ptr(ov_n),
-        1500, _lib.ptr(ov_rows[:, D:]), 2 * D, _lib.stream_ptr()))
-    hist2 = hist.clone()
-    hist2[ov_ids[:1400].long()] = ov_rows[:1400, D:]
-    want = torch.zeros((B, D), device="cuda")
-    ops.full_history_mean(field, rowptr_f, B, s.view("adj_p"), s.view("adj_i"), s.view("adj_w"), hist2, want)
-    torch.cuda.synchronize()
-    err = (y - want).abs().max() / want.abs().max()
-    assert float(err) < 1e-6, float(err)
+    counters = torch.ones(8, dtype=torch.int32, device="cuda")          # garbage: the reset must clear it
+    consumed = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(lib.sgcn_wb_counters_reset(_lib.ptr(counters), _lib.stream_ptr()))
+    ref = hist.clone()
+    for it in range(3):
+        ids = torch.randperm(g.n, generator=gen, device="cuda")[:B].to(torch.int32)
+        s.start_batch(ids); s.expand(2)
+        z = s.sizes()
+        field, rowptr_f = s.view("field").clone(), s.view("rowptr_f").clone()
+        n_in = torch.tensor([z["n_in"]], dtype=torch.int32, device="cuda")
+        rows = torch.randn((B * 3, ld_rows), generator=gen, device="cuda")
+        x = torch.randn((B * 3, D), generator=gen, device="cuda")
+        # the pass's sampled aggregate (reads hist[tgt]) signals the tail
+        y_s = torch.zeros((B, D), device="cuda")
+        _lib.check(lib.sgcn_sampled_done_attach(_lib.ptr(counters)))
+        ops.cv_sampled_fwd(s.view("rowptr_s"), s.view("edg_t"), s.view("edg_w"), s.view("tgt"), B, x, hist, y_s)
+        y = torch.zeros((B, D), device="cuda")
+        _lib.check(lib.sgcn_full_history_mean_wb(
+            _lib.ptr(field), _lib.ptr(rowptr_f), B, None, _lib.ptr(s.view("adj_p")), _lib.ptr(s.view("adj_i")),
+            _lib.ptr(s.view("adj_w")), _lib.ptr(hist), hist.stride(0), D, _lib.ptr(y), D, None, 0,
+            _lib.ptr(field), _lib.ptr(n_in), B * 3, _lib.ptr(rows), ld_rows, _lib.ptr(counters), _lib.ptr(consumed),
+            _lib.stream_ptr()))
+        want = torch.zeros((B, D), device="cuda")
+        ops.full_history_mean(field, rowptr_f, B, s.view("adj_p"), s.view("adj_i"), s.view("adj_w"), ref, want)
+        ref[field[:z["n_in"]].long()] = rows[:z["n_in"], :D]
+        torch.cuda.synchronize()
+        err = (y - want).abs().max() / want.abs().max()
+        assert float(err) < 1e-6, (it, float(err))
+        assert torch.equal(hist, ref), "table after the fused write-back, pass %d" % it
+        assert int(consumed.item()) == it + 1
+    c = counters.cpu().tolist()
+    assert c[0] == 0 and c[1] == 0 and c[2] == 3 and c[3] == 3 and c[4] == 0, c

@@ -51,8 +51,7 @@ def main():
     if mode == "pipelined":
         step.capture_pipelined(batches[0], batches[1], steps_per_graph=n_steps)
     if mode == "trains":                                             # the bench's schedule, one graph of n_steps
-        step.overlap_write_back = os.environ.get("OVERLAP", "1") != "0"
-        step.persistent = os.environ.get("PERSISTENT", "0") == "1"
+        step.fuse_write_back = os.environ.get("FUSE", "1") != "0"
         step.train = int(os.environ.get("TRAIN", "16"))
         ft = int(os.environ.get("FIRST_TRAIN", "4"))
         step.capture_trains(n_steps, torch.stack(batches[:n_steps]), first_train=ft)
@@ -61,8 +60,8 @@ def main():
         step._trains["tab"].copy_(torch.stack(batches[30:30 + n_steps]))
         trace.copy_(init); torch.cuda.synchronize()
         step._trains["graph"].replay(); torch.cuda.synchronize()
-        dump_events(trace, n_steps, "one trains graph (train %d, first %d, overlap %s, persistent %s)" % (
-            step.train, ft, step.overlap_write_back, step.persistent))
+        dump_events(trace, n_steps, "one trains graph (train %d, first %d, fused write-back %s)" % (
+            step.train, ft, step.fuse_write_back))
         _lib.load().sgcn_trace_set(None)
         return
     for b in batches[2:12]:
