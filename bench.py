@@ -16,6 +16,7 @@ import json
 import os
 
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per stream (see stochastic_gcn_b200/__init__.py)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")         # no first-launch stalls behind device-side waits (same place)
 import subprocess
 import sys
 import threading
@@ -299,7 +300,7 @@ class Rig:
                                     seed=args.seed)
             lo, hi = 0, self.g.n
         self.step.train = args.train
-        self.step.fuse_write_back = not args.no_fuse_write_back
+        self.step.fuse_write_back = args.fuse_write_back
         gen = torch.Generator(device=dev).manual_seed(7)
         self.step.d_out.normal_(generator=gen)
         self.step.history.normal_(generator=gen)      # a warm history table (zero rows would skip reductions)
@@ -560,7 +561,7 @@ def run_ours(args, w):
     what = {"trains": "CUDA graph(s) of %d passes of the trains schedule: trains of %d batches sampled by one launch a "
                       "train ahead, gather one pass ahead, full-neighbour means back to back%s" % (
                           S, args.train, " (history write-back in the tail of each mean's launch)"
-                          if not args.no_fuse_write_back and world == 1 and w["mode"] != "ns" else ""),
+                          if args.fuse_write_back and world == 1 and w["mode"] != "ns" else ""),
             "graph": "CUDA graphs of %d steps; batch k+1's sampler (1 CTA) runs beside batch k's aggregate" % S,
             "native": "plain stream launches from C++ on three streams, two batches of sampler lookahead",
             "one-graph-per-step": "one CUDA graph per step, back to back"}[driver]
@@ -643,9 +644,9 @@ def main():
     ap.add_argument("--train", type=int, default=16, help="batches sampled per launch by the trains schedule (2..32)")
     ap.add_argument("--first-train", type=int, default=4,
                     help="length of the first train of a graph (short: smaller start-up bubble)")
-    ap.add_argument("--no-fuse-write-back", action="store_true",
-                    help="single GPU: the history write-back as a launch of its own on the chain instead of in the "
-                         "tail of the full-neighbour mean (A/B, see DESIGN section 1)")
+    ap.add_argument("--fuse-write-back", action="store_true",
+                    help="single GPU: the history write-back in the tail of the full-neighbour mean's launch instead "
+                         "of a launch of its own on the chain (A/B, see DESIGN section 1)")
     ap.add_argument("--eager-trains", action="store_true",
                     help="trains driver as plain stream launches from C++ (no CUDA graphs): A/B of the graph overhead")
     ap.add_argument("--no-also", action="store_true", help="skip the extra keys for the other BASELINE configurations")

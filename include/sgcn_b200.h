@@ -302,9 +302,14 @@ int sgcn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
  *   SGCN_TUNE_HIST_L2       L2 eviction priority of history-row accesses: 0 = normal, p in 1..100 = evict_last
  *                           for p % of the accesses (the 119 MB Reddit-shaped table is about the size of L2;
  *                           everything else the step streams through L2 should not push it out)
- *   SGCN_TUNE_STREAM_L2     same for the read-once feature rows of the gather: p % evict_first */
+ *   SGCN_TUNE_STREAM_L2     same for the read-once feature rows of the gather: p % evict_first
+ *   SGCN_TUNE_FULL_TRIGGER  when full_mean_kernel lets its programmatic stream successor become resident:
+ *                           0 = at entry, 1 (default) = after its positions when the write-back is fused into
+ *                           its tail (the successor is the next full-neighbour mean), 2 = always after
+ *   SGCN_TUNE_FULL_REGS     register cap of full_mean_kernel: 96 (default; 2 thread blocks per SM) or 80 (3 per SM) */
 enum { SGCN_TUNE_FULL_VARIANT = 0, SGCN_TUNE_TMA_WARPS = 1, SGCN_TUNE_TMA_ROWS = 2, SGCN_TUNE_TMA_DEPTH = 3,
-       SGCN_TUNE_TMA_GRID = 4, SGCN_TUNE_PDL = 5, SGCN_TUNE_HIST_L2 = 6, SGCN_TUNE_STREAM_L2 = 7 };
+       SGCN_TUNE_TMA_GRID = 4, SGCN_TUNE_PDL = 5, SGCN_TUNE_HIST_L2 = 6, SGCN_TUNE_STREAM_L2 = 7,
+       SGCN_TUNE_FULL_TRIGGER = 8, SGCN_TUNE_FULL_REGS = 9 };
 int sgcn_tune_set(int32_t key, int32_t value);
 
 /* ---- det-dropout (mu, var) aggregation: PlainAggregator tuple branch layers.py:238-247 and

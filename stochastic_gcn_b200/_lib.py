@@ -166,7 +166,8 @@ def load():
     _lib = lib
     # optional overrides of the kernel tunables (include/sgcn_b200.h: SGCN_TUNE_*), for A/B runs
     for key, env in enumerate(("SGCN_FULL_VARIANT", "SGCN_TMA_WARPS", "SGCN_TMA_ROWS", "SGCN_TMA_DEPTH",
-                               "SGCN_TMA_GRID", "SGCN_PDL", "SGCN_HIST_L2", "SGCN_STREAM_L2")):
+                               "SGCN_TMA_GRID", "SGCN_PDL", "SGCN_HIST_L2", "SGCN_STREAM_L2",
+                               "SGCN_FULL_TRIGGER", "SGCN_FULL_REGS")):
         if os.environ.get(env, "") != "":
             if lib.sgcn_tune_set(key, int(os.environ[env])) != SGCN_OK:
                 raise SgcnError(SGCN_EINVAL, "%s=%s: %s" % (env, os.environ[env], lib.sgcn_last_error().decode()))

@@ -127,7 +127,7 @@ struct SampledArgs {
 };
 
 // every thread of the block calls it on its way out; the last block of the grid publishes "one more sampled pass done"
-__device__ __forceinline__ void sampled_done_signal(int32_t* ctr) {
+__device__ __forceinline__ void sampled_done_signal(int32_t* ctr, unsigned long long* trace) {
     if (!ctr) return;
     __syncthreads();                                   // every history row this block reads has been consumed
     if (threadIdx.x == 0) {
@@ -137,6 +137,7 @@ __device__ __forceinline__ void sampled_done_signal(int32_t* ctr) {
             ctr[WB_STICKET] = 0;
             __threadfence();
             atomicAdd(ctr + WB_SAMPLED, 1);
+            trace_stamp(trace, TR_SAMPLED_END);
         }
     }
 }
@@ -149,7 +150,7 @@ sampled_rows_kernel(const SampledArgs a) {
     grid_dep_wait();      // (PDL) launched early behind the gather that writes x: nothing to do before it
     if (a.has_push && blockIdx.y == 1) {
         wb_pack_body(a.push, blockIdx.x, gridDim.x);
-        sampled_done_signal(a.done_ctr);
+        sampled_done_signal(a.done_ctr, a.trace);
         return;
     }
     const uint64_t hpol = l2_policy(a.hist_l2, a.hist_l2_pct);
@@ -255,7 +256,7 @@ sampled_rows_kernel(const SampledArgs a) {
             }
         }
     }
-    sampled_done_signal(a.done_ctr);
+    sampled_done_signal(a.done_ctr, a.trace);
 }
 
 // ---- SpMM backward: dx[cols[e]] += vals[e] * rscale[r] * dy[r] --------------------------------
@@ -405,6 +406,7 @@ struct FullArgs {
     float* wb_hist;          // == hist of the first column tile, writable
     int32_t* wb_ctr; int32_t* consumed;
     int hist_l2, hist_l2_pct;          // L2 eviction policy of the history rows (l2_policy)
+    int late_trigger;                  // (PDL) launch_dependents after this block's positions instead of at entry
     ShardMap hmap;   // row-sharded history (world <= 1: hist is one local table)
 };
 
@@ -467,7 +469,7 @@ __device__ __forceinline__ void full_mean_body(const FullArgs& a, const uint64_t
     // static schedule: one contiguous span per warp.  dynamic schedule (a.work): warps pull
     // 64-position chunks from a device counter, which keeps every SM busy when some SMs are held
     // by a concurrently running kernel (the next batch's sampler in the pipelined step)
-    const int span = max(32, (((nnz + warps - 1) / warps) + 31) & ~31);
+    const int span = max(32, (((nnz + warps - 1) / warps) + 7) & ~7);        // every warp of the wave gets positions
     int p0 = warp * span;
     int p1 = min(p0 + span, nnz);
     if (a.work) {
@@ -643,11 +645,30 @@ __device__ __forceinline__ void full_write_back_tail(const FullArgs& a, uint64_t
     if (threadIdx.x == 0) {
         __threadfence();
         s_ticket = atomicAdd(c + WB_TICKET, 1);
+        if (s_ticket == grid - 1) trace_stamp(a.trace, TR_FULL_BODY_END);
     }
     __syncthreads();
     const int workers = min(grid, kWbWorkers);
     const int wi = s_ticket - (grid - workers);
     if (wi < 0) return;
+    // the new rows were gathered a pass ago: every warp loads its (first) rows BEFORE it waits, only the
+    // stores are left behind the wait
+    const int n = min(*a.wb_n_dev, a.wb_bound);
+    const int lane = threadIdx.x & 31;
+    constexpr int wpb = kAggThreads / 32;
+    constexpr int RU = 4;                              // rows in flight per warp
+    const int first = (wi * wpb + (threadIdx.x >> 5)) * RU;
+    const bool one_shot = sizeof(V) == 16 && a.wb_D <= 128;      // a row = one float4 per lane
+    int id[RU];
+    float4 v[RU];
+    if (one_shot) {
+        const bool in_row = lane * 4 < a.wb_D;
+#pragma unroll
+        for (int u = 0; u < RU; ++u) id[u] = (first + u < n && in_row) ? a.wb_ids[first + u] : -1;
+#pragma unroll
+        for (int u = 0; u < RU; ++u)
+            if (id[u] >= 0) v[u] = *(const float4*)(a.wb_rows + (int64_t)(first + u) * a.ld_wb + lane * 4);
+    }
     if (threadIdx.x == 0) {
         bool go = spin_until_ge(c + WB_TICKET, grid, c + WB_ERROR);
         // sampled passes finished > full passes finished: this pass's sampled aggregate is through
@@ -656,17 +677,25 @@ __device__ __forceinline__ void full_write_back_tail(const FullArgs& a, uint64_t
     }
     __syncthreads();
     if (s_go) {
-        const int n = min(*a.wb_n_dev, a.wb_bound);
-        const int lane = threadIdx.x & 31;
-        const int wpb = kAggThreads / 32;
-        constexpr int RU = 4;                          // rows in flight per warp
-        for (int r0 = (wi * wpb + (threadIdx.x >> 5)) * RU; r0 < n; r0 += workers * wpb * RU) {
-            int id[RU];
+        for (int r0 = first; r0 < n; r0 += workers * wpb * RU) {
+            if (one_shot) {
+                if (r0 != first) {
+                    const bool in_row = lane * 4 < a.wb_D;
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) id[u] = (r0 + u < n && in_row) ? a.wb_ids[r0 + u] : -1;
+#pragma unroll
+                    for (int u = 0; u < RU; ++u)
+                        if (id[u] >= 0) v[u] = *(const float4*)(a.wb_rows + (int64_t)(r0 + u) * a.ld_wb + lane * 4);
+                }
+#pragma unroll
+                for (int u = 0; u < RU; ++u)
+                    if (id[u] >= 0) st_hist4(a.wb_hist + (int64_t)id[u] * a.ld_h + lane * 4, v[u], hpol);
+                continue;
+            }
 #pragma unroll
             for (int u = 0; u < RU; ++u) id[u] = r0 + u < n ? a.wb_ids[r0 + u] : -1;
             if (sizeof(V) == 16) {
                 for (int c0 = lane * 4; c0 < a.wb_D; c0 += 128) {
-                    float4 v[RU];
 #pragma unroll
                     for (int u = 0; u < RU; ++u)
                         if (id[u] >= 0) v[u] = *(const float4*)(a.wb_rows + (int64_t)(r0 + u) * a.ld_wb + c0);
@@ -691,17 +720,26 @@ __device__ __forceinline__ void full_write_back_tail(const FullArgs& a, uint64_t
             if (a.consumed) atomicAdd(a.consumed, 1);             // the sampler's guard: this pass's reads are over
             __threadfence();
             atomicAdd(c + WB_FULL, 1);
+            trace_stamp(a.trace, TR_FULL_TAIL_END);
         }
     }
 }
 
-template <typename V, int LPR, int VPL>
-__global__ void __maxnreg__(96)      // 2 CTAs x 256 threads x 96 regs leave 16K registers per SM free
+// REGS = 96: 2 CTAs x 256 threads x 96 regs leave 16K registers per SM free for the kernels that run beside it;
+// REGS = 80 (sgcn_tune_set SGCN_TUNE_FULL_REGS): 3 CTAs per SM, shorter spans per warp, some spills
+template <typename V, int LPR, int VPL, int REGS>
+__global__ void __maxnreg__(REGS)
 full_mean_kernel(const FullArgs a) {
     TraceScope ts(a.trace, TR_FULL);
-    grid_dep_launch();                                           // (PDL) the stream successor may get resident now
+    // (PDL) when may the stream successor become resident?  At once (late_trigger = 0: right for a small
+    // write-back kernel that slips in beside this one), or when this block has finished its positions: the
+    // successor of the fused form is the NEXT full-neighbour mean, whose blocks cannot fit before these leave --
+    // and a launch that waits for room holds up every launch behind it, whatever its stream (the pass's sampled
+    // aggregate and the next gather started only after this kernel had drained: profiles/r02_timeline_fused_*)
+    if (!a.late_trigger) grid_dep_launch();
     const uint64_t hpol = l2_policy(a.hist_l2, a.hist_l2_pct);
     full_mean_body<V, LPR, VPL>(a, hpol);
+    if (a.late_trigger) grid_dep_launch();
     if (a.wb_ids) {
         grid_dep_wait();                                         // (blocks without positions skipped it above)
         full_write_back_tail<V>(a, hpol);
@@ -877,6 +915,8 @@ full_mean_tma_kernel(const FullArgs a, const FullTmaCfg cfg) {
 
 // runtime tunables (sgcn_tune_set): which full-mean variant runs and the shape of its ring
 static int g_full_variant = 0;        // 0 = register variant, 1 = bulk-copy variant
+static int g_full_regs = 96;          // register cap of full_mean_kernel: 96 (2 CTAs / SM) or 80 (3 CTAs / SM)
+static int g_full_trigger = 1;        // (PDL) launch_dependents of full_mean_kernel: 0 at entry, 1 late when fused, 2 late
 static FullTmaCfg g_tma_cfg = {12, 16, 2};
 static int g_tma_grid = kNumSMs;      // CTAs (one per SM); 147 leaves an SM to a concurrently running sampler
 
@@ -1255,7 +1295,7 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
         FullTmaCfg cfg = g_tma_cfg;
         FullArgs a{nodes, rowptr_f, n_out, n_out_dev, adj_p, adj_i, adj_w, hist, ld_h, D, y0, ld_y0, y1, ld_y1,
                    nullptr, n_out, g_trace, square, nullptr, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                   g_hist_l2[0], g_hist_l2[1], ShardMap{}};
+                   g_hist_l2[0], g_hist_l2[1], 0, ShardMap{}};
         const size_t fixed = 12 * (size_t)kTmaMeta + sizeof(int32_t) * (2 * (size_t)n_out + 2) + 128;
         const size_t stage = (size_t)cfg.rows * D * 4;
         while (cfg.depth > 1 && fixed + (size_t)cfg.warps * cfg.depth * (stage + 8) > 226 * 1024) --cfg.depth;
@@ -1280,31 +1320,37 @@ static int full_history_mean_impl(const int32_t* nodes, const int32_t* rowptr_f,
                    std::min(n_out, kFullStageRows), g_trace, square,
                    with_wb ? wb.ids : nullptr, wb.n_dev, wb.bound, wb.rows, wb.ld, D, const_cast<float*>(hist),
                    wb.ctr, wb.consumed, g_hist_l2[0], g_hist_l2[1],
+                   g_full_trigger == 2 || (g_full_trigger == 1 && with_wb) ? 1 : 0,
                    sharded ? t_hist_map : ShardMap{}};
         const size_t dyn = sizeof(int32_t) * (2 * (size_t)a.stage_rows + 2);
         // one resident wave: every CTA the SMs can hold at once, spans cut accordingly
-#define CALL(V, L, P)                                                                        \
+#define CALL_R(V, L, P, R)                                                                   \
     do {                                                                                     \
         static int per_sm = 0;                                                               \
         static size_t per_sm_dyn = 0;                                                        \
         if (per_sm == 0 || dyn != per_sm_dyn) {                                              \
-            /* ask for a 132 KB shared-memory carve-out although two CTAs need far less: a train-sampler \
+            /* ask for a 132 KB shared-memory carve-out although the CTAs need far less: a train-sampler \
                CTA (~47 KB) can then join an SM that runs this kernel without waiting for the SM  \
                to drain and re-partition its L1 / shared memory.  Occupancy is asked for THIS    \
                launch's dynamic shared memory (a worst-case figure halved it: 35 us per launch). */ \
-            SGCN_CUDA(cudaFuncSetAttribute(full_mean_kernel<V, L, P>,                        \
+            SGCN_CUDA(cudaFuncSetAttribute(full_mean_kernel<V, L, P, R>,                     \
                                            cudaFuncAttributePreferredSharedMemoryCarveout, kStepCarveout)); \
-            SGCN_CUDA(cudaFuncSetAttribute(full_mean_kernel<V, L, P>,                        \
+            SGCN_CUDA(cudaFuncSetAttribute(full_mean_kernel<V, L, P, R>,                     \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
             SGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                         \
-                &per_sm, full_mean_kernel<V, L, P>, kAggThreads, dyn));                      \
+                &per_sm, full_mean_kernel<V, L, P, R>, kAggThreads, dyn));                   \
             if (per_sm < 1) per_sm = 1;                                                      \
             per_sm_dyn = dyn;                                                                \
         }                                                                                    \
-        SGCN_CUDA(launch_pdl(full_mean_kernel<V, L, P>, kNumSMs * per_sm, kAggThreads, dyn, st, a)); \
+        SGCN_CUDA(launch_pdl(full_mean_kernel<V, L, P, R>, kNumSMs * per_sm, kAggThreads, dyn, st, a)); \
+    } while (0)
+#define CALL(V, L, P)                                                                        \
+    do {                                                                                     \
+        if (g_full_regs == 80) CALL_R(V, L, P, 80); else CALL_R(V, L, P, 96);                \
     } while (0)
         SGCN_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
+#undef CALL_R
         SGCN_LAUNCHED();
     }
     return SGCN_OK;
@@ -1339,6 +1385,12 @@ int sgcn_tune_set(int32_t key, int32_t value) {
             g_tma_cfg.depth = value; return SGCN_OK;
         case SGCN_TUNE_PDL:
             g_pdl = value != 0; return SGCN_OK;
+        case SGCN_TUNE_FULL_REGS:
+            SGCN_REQUIRE(value == 96 || value == 80, "tune: full-mean register cap is 96 or 80");
+            g_full_regs = value; return SGCN_OK;
+        case SGCN_TUNE_FULL_TRIGGER:
+            SGCN_REQUIRE(value >= 0 && value <= 2, "tune: full-mean trigger is 0, 1 or 2");
+            g_full_trigger = value; return SGCN_OK;
         case SGCN_TUNE_HIST_L2:
             SGCN_REQUIRE(value >= 0 && value <= 100, "tune: history L2 policy is 0 (normal) or 1..100 (% evict_last)");
             g_hist_l2[0] = value > 0 ? 1 : 0; g_hist_l2[1] = value; return SGCN_OK;

@@ -24,7 +24,10 @@ extern unsigned long long* g_trace;
 enum { TR_SAMPLER = 0, TR_FULL = 1, TR_GATHER = 2, TR_SAMPLED = 3, TR_BWD = 4, TR_UPDATE = 5, TR_PAD = 6,
        TR_EXCHANGE = 7, TR_CLASSES = 8,
        // event-log only (no min / max slots): the three kernels of the multi-GPU write-back exchange
-       TR_WB_PUSH = 8, TR_WB_CLAIM = 9, TR_WB_COPY = 10 };
+       TR_WB_PUSH = 8, TR_WB_CLAIM = 9, TR_WB_COPY = 10,
+       // single stamps of the fused write-back: the LAST block of a full-neighbour mean has finished its
+       // positions / the tail has stored the rows; the last block of a sampled aggregate has finished
+       TR_FULL_BODY_END = 11, TR_FULL_TAIL_END = 12, TR_SAMPLED_END = 13 };
 
 inline int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     char buf[512];
@@ -259,6 +262,17 @@ struct TraceScope {
         }
     }
 };
+
+// one stamp in the event log (class id, begin == end), whatever block calls it
+__device__ __forceinline__ void trace_stamp(unsigned long long* t, int id) {
+    if (!t) return;
+    const unsigned long long now = global_ns();
+    const unsigned long long i = atomicAdd(t + 16, 2ull);
+    if (i + 1 < (unsigned long long)kTraceLogCap) {
+        t[17 + 2 * i] = (unsigned long long)(id << 1);       t[18 + 2 * i] = now;
+        t[19 + 2 * i] = (unsigned long long)((id << 1) | 1); t[20 + 2 * i] = now;
+    }
+}
 
 __device__ __forceinline__ int dev_count(const int32_t* n_dev, int n_host) {
     return n_dev ? min(*n_dev, n_host) : n_host;

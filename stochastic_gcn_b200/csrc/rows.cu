@@ -195,7 +195,12 @@ static int launch_pad_jobs(const PadJobs& p, int n_jobs, cudaStream_t st) {
     for (int k = 0; k < n_jobs; ++k)
         if (p.j[k].dst) work = std::max<int64_t>(work, (int64_t)p.j[k].n_total * p.j[k].C / 4);
     const int64_t per_block = (int64_t)kRowThreads * kRowUnroll;
-    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((work + per_block - 1) / per_block, kNumSMs * 4)),
+    static int mult = 0;                     // thread blocks per SM and job (SGCN_PAD_GRID_MULT: A/B, default 4)
+    if (mult == 0) {
+        const char* e = getenv("SGCN_PAD_GRID_MULT");
+        mult = e ? std::max(1, std::min(16, atoi(e))) : 4;
+    }
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((work + per_block - 1) / per_block, kNumSMs * mult)),
               (unsigned)n_jobs);
     SGCN_MATCH_CARVEOUT(pad_jobs_kernel);
     pad_jobs_kernel<<<grid, kRowThreads, 0, st>>>(p, g_trace);

@@ -81,7 +81,8 @@ class HotPathStep:
         self._pipe_done = None
         self._last_slot = 0
         self.train = 16                # batches sampled per launch by the trains schedule (run_trains)
-        self.fuse_write_back = True    # trains schedule, single GPU: write-back in the tail of the full-neighbour mean
+        self.fuse_write_back = False   # trains schedule, single GPU: write-back in the tail of the full-neighbour mean
+                                       # (measured equal-to-slower than a launch of its own: DESIGN section 1)
         self._trains = None            # captured graphs of the trains schedule
         self._last_x0 = self._last_dx = None
         self._s_b = torch.cuda.Stream(device=self.dev)      # side branch of the pass

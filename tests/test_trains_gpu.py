@@ -162,7 +162,7 @@ def test_fused_write_back_equals_mean_then_write_back(D, ld_rows):
         s.start_batch(ids); s.expand(2)
         z = s.sizes()
         field, rowptr_f = s.view("field").clone(), s.view("rowptr_f").clone()
-        n_in = torch.tensor([z["n_in"]], dtype=torch.int32, device="cuda")
+        n_in = torch.tensor([z.n_in], dtype=torch.int32, device="cuda")
         rows = torch.randn((B * 3, ld_rows), generator=gen, device="cuda")
         x = torch.randn((B * 3, D), generator=gen, device="cuda")
         # the pass's sampled aggregate (reads hist[tgt]) signals the tail
@@ -177,7 +177,7 @@ def test_fused_write_back_equals_mean_then_write_back(D, ld_rows):
             _lib.stream_ptr()))
         want = torch.zeros((B, D), device="cuda")
         ops.full_history_mean(field, rowptr_f, B, s.view("adj_p"), s.view("adj_i"), s.view("adj_w"), ref, want)
-        ref[field[:z["n_in"]].long()] = rows[:z["n_in"], :D]
+        ref[field[:z.n_in].long()] = rows[:z.n_in, :D]
         torch.cuda.synchronize()
         err = (y - want).abs().max() / want.abs().max()
         assert float(err) < 1e-6, (it, float(err))

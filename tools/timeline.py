@@ -12,13 +12,14 @@ import bench
 from stochastic_gcn_b200 import _lib
 from stochastic_gcn_b200.step import HotPathStep
 
-NAMES = ["sampler", "full_mean", "gather", "sampled_fwd", "spmm_bwd", "history_update", "copy/zero", "exchange"]
+NAMES = ["sampler", "full_mean", "gather", "sampled_fwd", "spmm_bwd", "history_update", "copy/zero", "exchange",
+         "wb_push", "wb_claim", "wb_copy", "full_last_body", "full_tail_end", "sampled_end"]
 
 
 def dump_events(trace, S, what):
     t = trace.cpu().tolist()
     n = min(t[16], 1024)
-    ev = sorted((t[18 + 2 * i], t[17 + 2 * i]) for i in range(n))
+    ev = sorted((t[18 + 2 * i], t[17 + 2 * i]) for i in range(n) if t[18 + 2 * i] > 0)
     t0 = ev[0][0]
     print("%s of %d steps: %d events, span %.1f us (%.1f us / step)" % (
         what, S, n, (ev[-1][0] - t0) / 1e3, (ev[-1][0] - t0) / 1e3 / S))
