@@ -426,6 +426,8 @@ def run_ours(args, w):
     # ---- (2) timed region of record: exactly K passes ----
     nccl_multi = world > 1 and args.transport == "nccl"      # collective runs eagerly between one-pass graphs
     driver = "one-graph-per-step" if (args.no_pipeline or nccl_multi) else args.driver
+    if driver == "trains" and w["batch"] > 4096:
+        driver = "native"        # beyond the one-launch train sampler's bound: per-batch general sampler path
     ms, S = ms_serial, 1
     if driver == "trains":
         ms, S, launches_per_step = time_trains(rig, args, timed, warm, barrier, host_io=False)

@@ -30,9 +30,17 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     deg = 2 if mode == "cv" else 1
     D, B, steps, seed = 32, 24, (8 if pipelined else 15 if trains else 5), 3
-    g = graphs.powerlaw_graph(1500, 60_000, seed=4, device=dev, max_degree=300)
+    fullsize = os.environ.get("MGPU_FULLSIZE", "") == "1"      # the BENCHED shapes: BASELINE configs[2] / configs[3]
     gen = torch.Generator(device=dev).manual_seed(0)
-    feats = torch.randn((g.n, 80), generator=gen, device=dev)
+    if fullsize:
+        import bench
+        w = bench.WORKLOADS["reddit_cv" if mode == "cv" else "reddit_cvd"]
+        g, feats = bench.build_inputs(w, 1, dev, 1.0)
+        D, B, deg, steps = w["hidden"], w["batch"], w["degree"], 8
+        assert trains == "trains-graph", "the full-size check runs the benched form: graphs of the trains schedule"
+    else:
+        g = graphs.powerlaw_graph(1500, 60_000, seed=4, device=dev, max_degree=300)
+        feats = torch.randn((g.n, 80), generator=gen, device=dev)
     step = ShardedHotPathStep(g, feats, D, B, deg, mode=mode, seed=seed + rank, rank=rank, world=world,
                               transport=transport, tables=tables)
     hist0 = torch.randn((g.n, D), generator=gen, device=dev)
@@ -111,8 +119,9 @@ def main():
                 err = np.abs(rows[s].numpy() - want_out[s]).max() / max(np.abs(want_out[s]).max(), 1e-30)
                 assert err < 1e-4, "rank %d: trains pass %d differs by %g" % (rank, s, err)
         else:
-            step.capture_trains(5, table[:5], first_train=2)      # eager warm-up run = passes 0 .. 4
-            step.replay_trains(table[5:])
+            S = 4 if fullsize else 5
+            step.capture_trains(S, table[:S], first_train=2)      # eager warm-up run = passes 0 .. S-1
+            step.replay_trains(table[S:])
             torch.cuda.synchronize()
         step.check_exchange()
         out = step.out.cpu().numpy()
@@ -139,8 +148,9 @@ def main():
         rank, int((got_hist != hist).any(1).sum()))
     dist.barrier()
     if rank == 0:
-        print("mgpu_check ok: transport=%s mode=%s form=%s tables=%s world=%d" % (
-            transport, mode, sys.argv[3] if len(sys.argv) > 3 else "eager", tables, world))
+        print("mgpu_check ok: transport=%s mode=%s form=%s tables=%s world=%d nodes=%d batch=%d width=%d passes=%d" % (
+            transport, mode, sys.argv[3] if len(sys.argv) > 3 else "eager", tables, world, g.n, B, D,
+            15 if trains and not fullsize else 8))
     step.close()
     dist.destroy_process_group()
 

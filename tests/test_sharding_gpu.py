@@ -52,3 +52,28 @@ def test_all_ranks_multi_pass_schedules_match_oracle(form, mode, tables):
         f.write("%s %s %s world=%d rc=%d: %s\n" % (form, mode, tables, world, proc.returncode,
                                                     stdout.strip().splitlines()[-1:]))
     assert proc.returncode == 0 and "mgpu_check ok" in stdout, stdout[-3000:] + stderr[-3000:]
+
+
+@pytest.mark.parametrize("mode,tables", [("cv", "replicated"), ("cvd", "replicated"), ("cvd", "sharded")])
+def test_two_ranks_at_the_benched_shapes(mode, tables):
+    """BASELINE configs[2] (Reddit-shaped CV+PP degree 2) and configs[3] (CVD+PP degree 1) at FULL size, batch 512,
+    width 128, on two ranks: graphs of the trains schedule against R reference samplers sharing one history --
+    last pass's rows within 1e-4, every rank's history replica / shard bit-equal to the oracle's table."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import signal
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_check.py"),
+           "peer", mode, "trains-graph", tables]
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
+                            start_new_session=True, env=dict(os.environ, MGPU_FULLSIZE="1"))
+    try:
+        stdout, stderr = proc.communicate(timeout=420)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        proc.communicate()
+        raise
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "mgpu_check_fullsize.log"), "a") as f:
+        f.write("%s %s rc=%d: %s\n" % (mode, tables, proc.returncode, stdout.strip().splitlines()[-1:]))
+    assert proc.returncode == 0 and "mgpu_check ok" in stdout, stdout[-3000:] + stderr[-3000:]
