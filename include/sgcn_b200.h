@@ -426,6 +426,18 @@ int sgcn_wb_wait_apply_ring(float* hist, int64_t ld_h, int32_t D, const void* re
                             int32_t world, int32_t n_bound, int32_t* owner, const int32_t* flags, int32_t ring,
                             int64_t ring_stride, int32_t* apply_epoch, int32_t* apply_counter /*scratch = 0*/,
                             int32_t* timeout_flag, int32_t* done_counter, void* stream);
+/* The same epoch applied in two launches that need not share a stream: sgcn_wb_claim_ring (waits for every rank's
+ * ring flag, takes the claims; a plain launch -- order it after the previous epoch's copy, e.g. by an event) and
+ * sgcn_wb_copy_ring (the winners' rows into the table; launched programmatically behind the full-neighbour mean it
+ * loads ids, claims and rows BEFORE griddepcontrol.wait and only stores behind it; adds 1 to *done_counter).  The
+ * claim must have finished before the copy is launched.  Rows: 16-byte aligned, D in {4, 8, 16, 32, 64, 128}
+ * (other shapes: sgcn_wb_wait_apply_ring). */
+int sgcn_wb_claim_ring(const void* recv_base, int64_t slot_bytes, int32_t world, int32_t n_bound, int32_t* owner,
+                       const int32_t* flags, int32_t ring, int64_t ring_stride, const int32_t* apply_epoch,
+                       int32_t* apply_stash, int32_t* timeout_flag, void* stream);
+int sgcn_wb_copy_ring(float* hist, int64_t ld_h, int32_t D, const void* recv_base, int64_t slot_bytes, int32_t world,
+                      int32_t n_bound, int32_t* owner, int32_t ring, int64_t ring_stride, int32_t* apply_epoch,
+                      const int32_t* apply_stash, int32_t* done_counter, void* stream);
 /* Row-sharded tables ("boundary fetch").  Instead of replicating the history table and the PP
  * feature matrix on every GPU, rank r keeps rows [r * rows_per_shard, (r + 1) * rows_per_shard) and maps every
  * other rank's shard over NVLink (cudaIpc); the kernels that read history rows (full-neighbour mean, CV / CVD

@@ -121,6 +121,8 @@ SIGNATURES = {
                                  _i32, _vp, _vp, _vp]),
     "sgcn_wb_wait_apply_ring": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
                                        _vp, _vp]),
+    "sgcn_wb_claim_ring": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "sgcn_wb_copy_ring": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "sgcn_ipc_alloc": (_i32, [C.POINTER(_vp), _i64, _i32]),
     "sgcn_ipc_free": (_i32, [_vp]),
     "sgcn_ipc_export": (_i32, [_vp, _vp]),

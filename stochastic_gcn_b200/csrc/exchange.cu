@@ -227,6 +227,76 @@ wb_copy_kernel(const char* g_even, const char* g_odd,
     }
 }
 
+// copy, flat form (ring protocol, replicated tables; sgcn_wb_copy_ring): the claims of this epoch were taken by a
+// launch that has FINISHED (sgcn_wb_claim_ring on another stream, ordered by an event), so everything up to the
+// stores is independent of the stream predecessor -- the full-neighbour mean still reading the table -- and runs
+// before griddepcontrol.wait: ids, claim look-ups and the winners' row vectors land in registers (one thread =
+// up to 8 independent 16-byte vectors of a flattened (rank, row, vector) space), behind the wait only the stores
+// are left.  Rows never straddle warps (D / 4 divides 32, checked by the launcher): every
+// lane that compares a claim has done so before the winner's first lane releases it.
+constexpr int kCopyFlatU = 8;
+__global__ void __launch_bounds__(256)
+wb_copy_flat_kernel(const char* recv_base, int64_t slot_bytes, int world, int n_bound, int32_t* __restrict__ owner,
+                    float* __restrict__ hist, int64_t ld_h, int D, unsigned long long* trace, int ring,
+                    int64_t ring_stride, int32_t* epoch_out, const int32_t* cur_stash, int32_t* done_counter) {
+    TraceScope ts(trace, TR_WB_COPY);
+    __shared__ int s_n[kMaxPeers];
+    const int cur = *(volatile const int32_t*)cur_stash;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *(volatile int32_t*)epoch_out = cur;       // applied-epoch counter for the NEXT claim (launched after this grid)
+        __threadfence();
+    }
+    asm volatile("griddepcontrol.launch_dependents;");     // (PDL) the next full-neighbour mean's preamble
+    const char* gathered = recv_base + (int64_t)(cur % ring) * ring_stride;
+    if (threadIdx.x < world)
+        s_n[threadIdx.x] = min(__ldcg((const int32_t*)(gathered + (int64_t)threadIdx.x * slot_bytes)), n_bound);
+    __syncthreads();
+    const int c4 = D >> 2;
+    const int64_t per_rank = (int64_t)n_bound * c4;
+    const int64_t total = per_rank * world;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool waited = false;
+    // (trip count uniform within a warp: the __syncwarp below is executed by all 32 lanes or by none)
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base - (threadIdx.x & 31) < total || !waited;
+         base += stride * kCopyFlatU) {
+        float4 v[kCopyFlatU];
+        int64_t off[kCopyFlatU];
+        int32_t rel[kCopyFlatU];                   // node whose claim this thread releases (first vector of a row)
+#pragma unroll
+        for (int u = 0; u < kCopyFlatU; ++u) {
+            const int64_t e = base + (int64_t)u * stride;
+            off[u] = -1;
+            rel[u] = -1;
+            if (e < total) {
+                const int r = (int)(e / per_rank);
+                const int64_t rem = e - (int64_t)r * per_rank;
+                const int j = (int)(rem / c4);
+                const int c = (int)(rem - (int64_t)j * c4);
+                if (j < s_n[r]) {
+                    const char* slot = gathered + (int64_t)r * slot_bytes;
+                    const int node = __ldcg((const int32_t*)(slot + wb_ids_offset()) + j);
+                    if (__ldcg(owner + node) == r * n_bound + j) {
+                        v[u] = __ldcg((const float4*)((const float*)(slot + wb_rows_offset(n_bound)) + (int64_t)j * D) + c);
+                        off[u] = (int64_t)node * ld_h + c * 4;
+                        if (c == 0) rel[u] = node;
+                    }
+                }
+            }
+        }
+        if (!waited) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");  // (PDL) the table is no longer read
+            if (done_counter && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(done_counter, 1);
+            waited = true;
+        }
+        __syncwarp();                              // every lane of the row has compared the claim
+#pragma unroll
+        for (int u = 0; u < kCopyFlatU; ++u) {
+            if (off[u] >= 0) *(float4*)(hist + off[u]) = v[u];
+            if (rel[u] >= 0) owner[rel[u]] = -1;
+        }
+    }
+}
+
 }  // namespace sgcn
 
 using namespace sgcn;
@@ -392,6 +462,48 @@ int sgcn_wb_wait_apply_ring(float* hist, int64_t ld_h, int32_t D, const void* re
     return launch_apply(hist, ld_h, D, recv_base, recv_base, apply_epoch, slot_bytes, world, n_bound, owner,
                         (cudaStream_t)stream, flags, timeout_flag, done_counter, ring, ring_stride, apply_epoch,
                         apply_counter);
+}
+
+int sgcn_wb_claim_ring(const void* recv_base, int64_t slot_bytes, int32_t world, int32_t n_bound, int32_t* owner,
+                       const int32_t* flags, int32_t ring, int64_t ring_stride, const int32_t* apply_epoch,
+                       int32_t* apply_stash, int32_t* timeout_flag, void* stream) {
+    SGCN_REQUIRE(recv_base && owner && flags && apply_epoch && apply_stash && timeout_flag, "wb_claim_ring: null pointer");
+    SGCN_REQUIRE(world >= 1 && world <= kMaxPeers && n_bound > 0, "wb_claim_ring: bad size");
+    SGCN_REQUIRE(ring >= 2 && ring <= 64 && ring_stride >= (int64_t)world * slot_bytes && ring_stride % 16 == 0,
+                 "wb_claim_ring: bad ring");
+    SGCN_REQUIRE((int64_t)world * n_bound < 0x7fffffff, "wb_claim_ring: world * n_bound overflows");
+    const PeerPtrs none{};
+    dim3 g1(std::min(div_up(n_bound, 256), 64), world);
+    PdlOff plain;           // ordered by events: after the previous epoch's copy, before this epoch's
+    SGCN_CUDA(launch_pdl(wb_claim_kernel, g1, dim3(256), 0, (cudaStream_t)stream, (const char*)recv_base,
+                         (const char*)recv_base, apply_epoch, slot_bytes, world, n_bound, owner, flags, timeout_flag,
+                         20000000LL, (int32_t*)nullptr, g_trace, ring, ring_stride, apply_stash, 0, 0, none,
+                         (const int32_t*)nullptr));
+    SGCN_LAUNCHED();
+    return SGCN_OK;
+}
+
+int sgcn_wb_copy_ring(float* hist, int64_t ld_h, int32_t D, const void* recv_base, int64_t slot_bytes, int32_t world,
+                      int32_t n_bound, int32_t* owner, int32_t ring, int64_t ring_stride, int32_t* apply_epoch,
+                      const int32_t* apply_stash, int32_t* done_counter, void* stream) {
+    SGCN_REQUIRE(hist && recv_base && owner && apply_epoch && apply_stash, "wb_copy_ring: null pointer");
+    SGCN_REQUIRE(world >= 1 && world <= kMaxPeers && n_bound > 0 && D > 0 && ld_h >= D, "wb_copy_ring: bad size");
+    SGCN_REQUIRE(slot_bytes >= wb_payload_bytes(n_bound, D), "wb_copy_ring: slot smaller than a payload");
+    SGCN_REQUIRE(ring >= 2 && ring <= 64 && ring_stride >= (int64_t)world * slot_bytes && ring_stride % 16 == 0,
+                 "wb_copy_ring: bad ring");
+    const int c4 = D / 4;
+    SGCN_REQUIRE(D % 4 == 0 && ld_h % 4 == 0 && (((uintptr_t)hist) & 15) == 0 && slot_bytes % 16 == 0 &&
+                     (((uintptr_t)recv_base) & 15) == 0 && c4 <= 32 && 32 % c4 == 0,
+                 "wb_copy_ring: rows must be 16-byte aligned and 1, 2, 4, 8, 16 or 32 vectors of 16 bytes wide; use "
+                 "sgcn_wb_wait_apply_ring");
+    const int64_t total = (int64_t)world * n_bound * c4;
+    // one round of 8 vectors per thread when it fits in 96 thread blocks (they sit resident beside the mean)
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(96, (total + 256 * kCopyFlatU - 1) / (256 * kCopyFlatU)));
+    SGCN_CUDA(launch_pdl(wb_copy_flat_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const char*)recv_base,
+                         slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace, ring, ring_stride, apply_epoch,
+                         apply_stash, done_counter));
+    SGCN_LAUNCHED();
+    return SGCN_OK;
 }
 
 int sgcn_wb_wait_apply_sharded(float* hist_shard, int64_t ld_h, int32_t D, const void* recv_base, int64_t slot_bytes,

@@ -42,6 +42,8 @@ struct sgcn_step {
     int32_t* flags = nullptr;                       // counters of the fused write-back (8 ints, sgcn_full_history_mean_wb)
     bool warmed = false;                            // a first run has loaded every kernel (see sgcn_step_run_trains)
     bool gather_after_sampled = false;              // A/B: gather(k+1) ordered behind sampled(k)
+    bool split_apply = false;                       // ring exchange: claims off the chain (SGCN_WB_SPLIT=1; measured slower)
+    cudaEvent_t t_claim[8]{};
 };
 
 namespace sgcn {
@@ -129,6 +131,9 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
     {
         const char* ge = getenv("SGCN_GATHER_AFTER_SAMPLED");
         st->gather_after_sampled = ge && ge[0] == '1';
+        const char* se = getenv("SGCN_WB_SPLIT");
+        const int c4 = d.hidden / 4;
+        st->split_apply = se && se[0] == '1' && d.hidden % 4 == 0 && c4 <= 32 && 32 % c4 == 0 && d.ld_hist % 4 == 0;
     }
     for (int i = 0; i < sgcn_step::kSlots; ++i) CK(cudaMalloc(&st->ids_dev[i], sizeof(int32_t) * (size_t)d.batch));
     for (int i = 0; i < sgcn_step::kRing; ++i) {
@@ -140,7 +145,7 @@ int sgcn_step_create(sgcn_step** out, sgcn_sampler* sampler, const sgcn_step_des
         CK(cudaEventCreateWithFlags(&st->ev_pre[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < sgcn_step::kRing2; ++i)
-        for (cudaEvent_t* e : {&st->t_pre[i], &st->t_full[i], &st->t_fwd[i], &st->t_rest[i], &st->t_d2h[i]})
+        for (cudaEvent_t* e : {&st->t_pre[i], &st->t_full[i], &st->t_fwd[i], &st->t_rest[i], &st->t_d2h[i], &st->t_claim[i]})
             CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&st->t_train[i], cudaEventDisableTiming));
     CK(cudaMalloc(&st->flags, sizeof(int32_t) * 8));
@@ -193,7 +198,7 @@ void sgcn_step_destroy(sgcn_step* st) {
     for (cudaEvent_t e : {st->ev_begin, st->ev_side_end, st->ev_samp_end, st->ev_zero0, st->ev_pre_end})
         if (e) cudaEventDestroy(e);
     for (int i = 0; i < sgcn_step::kRing2; ++i)
-        for (cudaEvent_t e : {st->t_pre[i], st->t_full[i], st->t_fwd[i], st->t_rest[i], st->t_d2h[i]})
+        for (cudaEvent_t e : {st->t_pre[i], st->t_full[i], st->t_fwd[i], st->t_rest[i], st->t_d2h[i], st->t_claim[i]})
             if (e) cudaEventDestroy(e);
     for (int i = 0; i < 4; ++i) if (st->t_train[i]) cudaEventDestroy(st->t_train[i]);
     for (int i = 0; i < 2; ++i) cudaFree(st->ids_stage[i]);
@@ -531,6 +536,18 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
         SGCN_CUDA(cudaStreamWaitEvent(side, st->t_pre[k % R], 0));
         if (k >= 1) SGCN_CUDA(cudaStreamWaitEvent(side, st->t_rest[(k - 1) % R], 0));     // history as of write-back k-1
         if (fuse) STEP_TRY(sgcn_sampled_done_attach(st->flags));
+        const bool split = ring && !sharded && st->split_apply;
+        if (split) {
+            // multi-GPU, ring form, opt-in (SGCN_WB_SPLIT=1): the claims of this pass's exchange epoch (who refreshes
+            // which row: the highest rank wins) need the peers' rows and the previous epoch's copy (awaited just
+            // above), not this pass's reads of the table, so they can leave the chain.  Measured on 2 GPUs: 39.8 us
+            // per pass against 29.3 with claim -> copy on the chain -- the claim has to wait for the peers' pushes of
+            // THIS pass, which land ~10 us into the mean, and every event hop between streams costs 4-8 us of launch
+            // latency under load (profiles/r02_timeline_2gpu_split.txt).
+            STEP_TRY(sgcn_wb_claim_ring(d.ring_recv, d.slot_bytes, d.world, d.wb_bound, d.owner, d.ring_flags, d.ring,
+                                        d.ring_stride, d.apply_epoch, d.apply_stash, d.timeout_flag, side));
+            SGCN_CUDA(cudaEventRecord(st->t_claim[k % R], side));
+        }
         if (d.mode == 0) {
             STEP_TRY(sgcn_spmm_csr(v.rowptr_s, v.edg_t, v.edg_w, nullptr, B, n_out_dev, x, d.ld_x0, H, nb(out_r),
                                    d.ld_out, 0, side));
@@ -568,6 +585,12 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
                                                     d.ring_stride, d.apply_epoch, d.apply_stash, d.reads_flags,
                                                     d.reads_peer_flags, d.applied_flags, d.applied_peer_flags,
                                                     d.shard_counter, d.timeout_flag, st->pipe + 1, chain));
+            } else if (ring && st->split_apply) {
+                // ... and the chain keeps the copy alone: ids, claims and rows in registers before the mean has
+                // finished (programmatic launch), the stores behind it
+                SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_claim[k % R], 0));
+                STEP_TRY(sgcn_wb_copy_ring(d.history, d.ld_hist, H, d.ring_recv, d.slot_bytes, d.world, d.wb_bound, d.owner,
+                                           d.ring, d.ring_stride, d.apply_epoch, d.apply_stash, st->pipe + 1, chain));
             } else if (ring) {
                 STEP_TRY(sgcn_wb_wait_apply_ring(d.history, d.ld_hist, H, d.ring_recv, d.slot_bytes, d.world, d.wb_bound,
                                                  d.owner, d.ring_flags, d.ring, d.ring_stride, d.apply_epoch,
