@@ -285,6 +285,21 @@ int sgcn_xent(const float* logits, int64_t ld_l, const float* labels, int64_t ld
 int sgcn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1,
                    float beta2, float eps, float weight_decay, void* stream);
 
+/* ---- first dense layer with the feature-row gather fused into its A-operand load (gcn/layers.py:100-138
+ * `Dense` on the rows history.dense_slice picks, gcn/train.py:190) -- tcgen05 tensor cores, TF32 x 3 -------------
+ *   out[i, :] = act(LN(src[idx[i], :K] @ W)),  W: [K, 128] row-major, i < min(n, *n_dev)
+ * idx NULL: rows 0 .. n-1.  epilogue 0: the raw product; 1: MyLayerNorm (unit scale, zero offset, eps) + relu;
+ * 2: MyLayerNorm.  pre (optional): the raw product as well (input of sgcn_ln_act_bwd); stats (optional): {mean,
+ * rstd} per row as sgcn_ln_act_fwd writes them.  Both operands are split into tf32 hi + lo parts and three
+ * tensor-core products accumulate in fp32 (hi.hi + lo.hi + hi.lo): the result matches the fp32 product to ~1e-6.
+ * W is split and laid out once by sgcn_gemm_pack_w into `packed` (sgcn_gemm_packed_floats(K, 128) floats, 16-byte
+ * aligned); repack after every update of W.  Source rows: 16-byte aligned, K and ld_src multiples of 4. */
+int64_t sgcn_gemm_packed_floats(int32_t K, int32_t N);
+int sgcn_gemm_pack_w(const float* w, int64_t ld_w, int32_t K, int32_t N, float* packed, void* stream);
+int sgcn_gather_gemm_tf32x3(const float* src, int64_t ld_src, const int32_t* idx, int32_t n, const int32_t* n_dev,
+                            int32_t K, const float* w_packed, int32_t N, float* out, int64_t ld_out, float* pre,
+                            int64_t ld_pre, float* stats, int32_t epilogue, float eps, void* stream);
+
 /* Runtime tunables (process-wide, not thread-safe against concurrent launches).
  *   SGCN_TUNE_FULL_VARIANT  0 = register-pipelined full_mean_kernel (default, fastest measured),
  *                           1 = bulk-copy (cp.async.bulk + mbarrier ring) full_mean_tma_kernel
@@ -306,10 +321,14 @@ int sgcn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
  *   SGCN_TUNE_FULL_TRIGGER  when full_mean_kernel lets its programmatic stream successor become resident:
  *                           0 = at entry, 1 (default) = after its positions when the write-back is fused into
  *                           its tail (the successor is the next full-neighbour mean), 2 = always after
+ *   SGCN_TUNE_WB_TRIGGER    when the write-back kernels (sgcn_history_update, the exchange's copy pass) let their
+ *                           programmatic stream successor -- the next full-neighbour mean -- launch: 1 (default) =
+ *                           once their rows are stored, 0 = at entry (the mean then waits for room during the whole
+ *                           previous mean and holds up every launch issued after it)
  *   SGCN_TUNE_FULL_REGS     register cap of full_mean_kernel: 96 (default; 2 thread blocks per SM) or 80 (3 per SM) */
 enum { SGCN_TUNE_FULL_VARIANT = 0, SGCN_TUNE_TMA_WARPS = 1, SGCN_TUNE_TMA_ROWS = 2, SGCN_TUNE_TMA_DEPTH = 3,
        SGCN_TUNE_TMA_GRID = 4, SGCN_TUNE_PDL = 5, SGCN_TUNE_HIST_L2 = 6, SGCN_TUNE_STREAM_L2 = 7,
-       SGCN_TUNE_FULL_TRIGGER = 8, SGCN_TUNE_FULL_REGS = 9 };
+       SGCN_TUNE_FULL_TRIGGER = 8, SGCN_TUNE_FULL_REGS = 9, SGCN_TUNE_WB_TRIGGER = 10 };
 int sgcn_tune_set(int32_t key, int32_t value);
 
 /* ---- det-dropout (mu, var) aggregation: PlainAggregator tuple branch layers.py:238-247 and

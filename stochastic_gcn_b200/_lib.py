@@ -123,6 +123,10 @@ SIGNATURES = {
                                        _vp, _vp]),
     "sgcn_wb_claim_ring": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "sgcn_wb_copy_ring": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "sgcn_gemm_packed_floats": (_i64, [_i32, _i32]),
+    "sgcn_gemm_pack_w": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "sgcn_gather_gemm_tf32x3": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i64, _vp, _i64, _vp, _i32,
+                                       C.c_float, _vp]),
     "sgcn_ipc_alloc": (_i32, [C.POINTER(_vp), _i64, _i32]),
     "sgcn_ipc_free": (_i32, [_vp]),
     "sgcn_ipc_export": (_i32, [_vp, _vp]),
@@ -169,7 +173,7 @@ def load():
     # optional overrides of the kernel tunables (include/sgcn_b200.h: SGCN_TUNE_*), for A/B runs
     for key, env in enumerate(("SGCN_FULL_VARIANT", "SGCN_TMA_WARPS", "SGCN_TMA_ROWS", "SGCN_TMA_DEPTH",
                                "SGCN_TMA_GRID", "SGCN_PDL", "SGCN_HIST_L2", "SGCN_STREAM_L2",
-                               "SGCN_FULL_TRIGGER", "SGCN_FULL_REGS")):
+                               "SGCN_FULL_TRIGGER", "SGCN_FULL_REGS", "SGCN_WB_TRIGGER")):
         if os.environ.get(env, "") != "":
             if lib.sgcn_tune_set(key, int(os.environ[env])) != SGCN_OK:
                 raise SgcnError(SGCN_EINVAL, "%s=%s: %s" % (env, os.environ[env], lib.sgcn_last_error().decode()))

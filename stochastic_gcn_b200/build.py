@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsgcn_b200.so")
-SOURCES = ["api.cu", "rows.cu", "aggregate.cu", "sampler.cu", "exchange.cu", "step.cu", "precompute.cu", "dense.cu"]
+SOURCES = ["api.cu", "rows.cu", "aggregate.cu", "sampler.cu", "exchange.cu", "step.cu", "precompute.cu", "dense.cu", "gemm.cu"]
 HEADERS = ["common.cuh", "scan.cuh", "mt19937.cuh", "exchange.cuh"]
 
 NVCC_FLAGS = [

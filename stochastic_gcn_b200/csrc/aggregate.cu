@@ -1385,6 +1385,8 @@ int sgcn_tune_set(int32_t key, int32_t value) {
             g_tma_cfg.depth = value; return SGCN_OK;
         case SGCN_TUNE_PDL:
             g_pdl = value != 0; return SGCN_OK;
+        case SGCN_TUNE_WB_TRIGGER:
+            g_wb_late_trigger = value != 0; return SGCN_OK;
         case SGCN_TUNE_FULL_REGS:
             SGCN_REQUIRE(value == 96 || value == 80, "tune: full-mean register cap is 96 or 80");
             g_full_regs = value; return SGCN_OK;

@@ -8,6 +8,7 @@ std::atomic<int64_t> g_launches{0};
 unsigned long long* g_trace = nullptr;
 int g_pdl = 1;      // on by default; SGCN_TUNE_PDL / env SGCN_PDL=0 turn it off
 thread_local int t_pdl_off = 0;
+int g_wb_late_trigger = 1;
 int g_hist_l2[2] = {0, 0}, g_stream_l2[2] = {0, 0};   // L2 eviction policies {kind, percent} (sgcn_tune_set)
 thread_local ShardMap t_hist_map{}, t_feat_map{};
 

@@ -178,6 +178,11 @@ __device__ __forceinline__ uint64_t l2_policy(int kind, int pct) {
 }
 // host-side tunables behind them: {kind, percent}
 extern int g_hist_l2[2], g_stream_l2[2];
+// (PDL) the write-back kernels (history_update, wb_copy) let their stream successor -- the next full-neighbour mean --
+// launch at their END, not at entry: launched early it cannot fit beside the running mean anyway, and a launch that
+// waits for room holds up every later launch (the next pass's gather / push) for the whole mean
+// (sgcn_tune_set SGCN_TUNE_WB_TRIGGER: 1 = late (default), 0 = at entry)
+extern int g_wb_late_trigger;
 
 // 128-bit vector reduction (sm_90+): one RED for 4 floats.
 __device__ __forceinline__ void red_add4(float* p, float4 v) {

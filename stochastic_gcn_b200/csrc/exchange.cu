@@ -157,7 +157,7 @@ wb_copy_kernel(const char* g_even, const char* g_odd,
                int32_t* __restrict__ owner, float* __restrict__ hist, int64_t ld_h, int D,
                unsigned long long* trace, int ring, int64_t ring_stride, int32_t* epoch_out,
                const int32_t* cur_stash, int shard_rank, int shard_rows, PeerPtrs applied_peers,
-               int32_t* apply_counter) {
+               int32_t* apply_counter, const int late_trigger) {
     TraceScope ts(trace, TR_WB_COPY);
     // ring protocol: the epoch being applied was stashed by the claim kernel; advance the applied-epoch
     // counter for the NEXT claim before any dependent can launch (see wb_claim_kernel)
@@ -169,7 +169,9 @@ wb_copy_kernel(const char* g_even, const char* g_odd,
         }
         __syncthreads();
     }
-    asm volatile("griddepcontrol.launch_dependents;");     // (PDL) the next full-neighbour mean's preamble
+    // (PDL) the stream successor is the next full-neighbour mean: at entry, or (late_trigger, see
+    // g_wb_late_trigger) once this block's rows are stored
+    if (!late_trigger) asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");      // (PDL) claims final, history no longer read
     const int r = blockIdx.y;
     const char* gathered = ring > 0 ? g_even + (int64_t)(cur % ring) * ring_stride : ((cur & 1) ? g_odd : g_even);
@@ -212,6 +214,7 @@ wb_copy_kernel(const char* g_even, const char* g_odd,
         for (int q = 0; q < R; ++q)
             if (mine[q] && lane == 0) owner[node[q]] = -1;        // losers only ever compare for equality
     }
+    if (late_trigger) asm volatile("griddepcontrol.launch_dependents;");
     if (shard_rows > 0) {      // sharded history: the last block to finish tells every rank "my shard holds epoch cur"
         __shared__ int s_last;
         __threadfence_system();
@@ -238,7 +241,8 @@ constexpr int kCopyFlatU = 8;
 __global__ void __launch_bounds__(256)
 wb_copy_flat_kernel(const char* recv_base, int64_t slot_bytes, int world, int n_bound, int32_t* __restrict__ owner,
                     float* __restrict__ hist, int64_t ld_h, int D, unsigned long long* trace, int ring,
-                    int64_t ring_stride, int32_t* epoch_out, const int32_t* cur_stash, int32_t* done_counter) {
+                    int64_t ring_stride, int32_t* epoch_out, const int32_t* cur_stash, int32_t* done_counter,
+                    const int late_trigger) {
     TraceScope ts(trace, TR_WB_COPY);
     __shared__ int s_n[kMaxPeers];
     const int cur = *(volatile const int32_t*)cur_stash;
@@ -246,7 +250,7 @@ wb_copy_flat_kernel(const char* recv_base, int64_t slot_bytes, int world, int n_
         *(volatile int32_t*)epoch_out = cur;       // applied-epoch counter for the NEXT claim (launched after this grid)
         __threadfence();
     }
-    asm volatile("griddepcontrol.launch_dependents;");     // (PDL) the next full-neighbour mean's preamble
+    if (!late_trigger) asm volatile("griddepcontrol.launch_dependents;");     // (PDL) see wb_copy_kernel
     const char* gathered = recv_base + (int64_t)(cur % ring) * ring_stride;
     if (threadIdx.x < world)
         s_n[threadIdx.x] = min(__ldcg((const int32_t*)(gathered + (int64_t)threadIdx.x * slot_bytes)), n_bound);
@@ -295,6 +299,7 @@ wb_copy_flat_kernel(const char* recv_base, int64_t slot_bytes, int world, int n_
             if (rel[u] >= 0) owner[rel[u]] = -1;
         }
     }
+    if (late_trigger) asm volatile("griddepcontrol.launch_dependents;");
 }
 
 }  // namespace sgcn
@@ -319,9 +324,16 @@ static int fill_ptrs(PeerPtrs& p, void* const* src, int n, const char* what) {
     return SGCN_OK;
 }
 
+// Thread blocks of a pack / push launch.  Few enough to be resident all at once beside a full-neighbour mean (a
+// launch with blocks still waiting for room holds up every later launch): SGCN_PUSH_BLOCKS, default 64.
 static int pack_blocks(int n_bound, int D) {
+    static int cap = 0;
+    if (cap == 0) {
+        const char* e = getenv("SGCN_PUSH_BLOCKS");
+        cap = e ? std::max(1, std::min(atoi(e), kNumSMs * 2)) : 64;
+    }
     const int64_t work = std::max<int64_t>((int64_t)n_bound * std::max(D / 4, 1), 1);
-    return (int)std::min<int64_t>((work + 255) / 256, kNumSMs * 2);
+    return (int)std::min<int64_t>((work + 255) / 256, cap);
 }
 
 int sgcn_wb_pack(const int32_t* field, const int32_t* n_dev, int32_t n_bound, const float* rows,
@@ -407,12 +419,12 @@ static int launch_apply(float* hist, int64_t ld_h, int32_t D, const void* g_even
         SGCN_CUDA(launch_pdl(wb_copy_kernel<true>, g2, dim3(256), 0, st, (const char*)g_even, (const char*)g_odd,
                              epoch, slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace, ring, ring_stride,
                              epoch_out, apply_counter, shard_rank, shard_rows, applied_peers ? *applied_peers : none,
-                             shard_counter));
+                             shard_counter, g_wb_late_trigger));
     else
         SGCN_CUDA(launch_pdl(wb_copy_kernel<false>, g2, dim3(256), 0, st, (const char*)g_even, (const char*)g_odd,
                              epoch, slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace, ring, ring_stride,
                              epoch_out, apply_counter, shard_rank, shard_rows, applied_peers ? *applied_peers : none,
-                             shard_counter));
+                             shard_counter, g_wb_late_trigger));
     SGCN_LAUNCHED();
     return SGCN_OK;
 }
@@ -501,7 +513,7 @@ int sgcn_wb_copy_ring(float* hist, int64_t ld_h, int32_t D, const void* recv_bas
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(96, (total + 256 * kCopyFlatU - 1) / (256 * kCopyFlatU)));
     SGCN_CUDA(launch_pdl(wb_copy_flat_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const char*)recv_base,
                          slot_bytes, world, n_bound, owner, hist, ld_h, D, g_trace, ring, ring_stride, apply_epoch,
-                         apply_stash, done_counter));
+                         apply_stash, done_counter, g_wb_late_trigger));
     SGCN_LAUNCHED();
     return SGCN_OK;
 }

@@ -26,11 +26,12 @@ __global__ void __launch_bounds__(kRowThreads)
 move_rows_vec4_kernel(const float* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ idx,
                       int n_host, const int32_t* __restrict__ n_dev, int n_total, int c4,
                       float* __restrict__ dst, int64_t ld_dst, unsigned long long* trace,
-                      int32_t* done_counter, const ShardMap smap) {
+                      int32_t* done_counter, const ShardMap smap, const int late_trigger) {
     TraceScope ts(trace, MODE == 0 ? TR_GATHER : (MODE == 1 ? TR_UPDATE : TR_PAD));
     // (PDL) a dependent launched with programmatic stream serialization may start its preamble now;
-    // it still waits for this whole grid (griddepcontrol.wait) before touching what is written here
-    asm volatile("griddepcontrol.launch_dependents;");
+    // it still waits for this whole grid (griddepcontrol.wait) before touching what is written here.
+    // late_trigger (the history write-back): only when this block's stores are issued, see g_wb_late_trigger
+    if (!late_trigger) asm volatile("griddepcontrol.launch_dependents;");
     // ... and if THIS kernel was launched that way (the write-back behind the full-neighbour mean),
     // nothing below may run before the predecessor grid has finished reading the history table
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -63,6 +64,7 @@ move_rows_vec4_kernel(const float* __restrict__ src, int64_t ld_src, const int32
         for (int u = 0; u < kRowUnroll; ++u)
             if (off_dst[u] >= 0) stg_stream4(dst + off_dst[u], v[u]);
     }
+    if (late_trigger) asm volatile("griddepcontrol.launch_dependents;");
 }
 
 // scalar fallback for widths / strides / pointers that are not 16-byte friendly (e.g. C = 1433)
@@ -109,11 +111,11 @@ static int launch_move_rows(const float* src, int64_t ld_src, const int32_t* idx
         SGCN_MATCH_CARVEOUT(move_rows_vec4_kernel<MODE>);
         if (MODE == 1) {      // history write-back: second link of the step's main chain (PDL when enabled)
             SGCN_CUDA(launch_pdl(move_rows_vec4_kernel<MODE>, dim3(blocks), dim3(kRowThreads), 0, st, src, ld_src,
-                                 idx, n, n_dev, n_total, c4, dst, ld_dst, g_trace, done_counter, ShardMap{}));
+                                 idx, n, n_dev, n_total, c4, dst, ld_dst, g_trace, done_counter, ShardMap{}, g_wb_late_trigger));
         } else {
             move_rows_vec4_kernel<MODE><<<blocks, kRowThreads, 0, st>>>(src, ld_src, idx, n, n_dev,
                                                                        n_total, c4, dst, ld_dst, g_trace,
-                                                                       done_counter, MODE == 0 ? t_feat_map : ShardMap{});
+                                                                       done_counter, MODE == 0 ? t_feat_map : ShardMap{}, 0);
         }
     } else {
         SGCN_REQUIRE(!(MODE == 0 && t_feat_map.world > 1), "sharded features need 16-byte aligned rows");

@@ -168,6 +168,44 @@ def dot(x, w, sparse=False):
     return torch.mm(x, w)
 
 
+class _GatheredDenseFn(torch.autograd.Function):
+    """act(MyLayerNorm(features[idx] @ W)) in ONE kernel on the tcgen05 tensor cores (csrc/gemm.cu: the row gather
+    is the GEMM's A-operand load, TF32 x 3 split, layer norm + activation out of tensor memory).  Backward: the
+    row-wise layer-norm backward kernel, then dW = X^T dPre as a library GEMM over the gathered rows."""
+
+    @staticmethod
+    def forward(ctx, w, features, idx, norm, relu):
+        from . import ops
+        n, k = idx.numel(), w.shape[0]
+        packed = ops.pack_dense_weights(w.detach())
+        y = torch.empty((n, w.shape[1]), dtype=torch.float32, device=w.device)
+        pre = torch.empty_like(y) if norm else None
+        stats = torch.empty((n, 2), dtype=torch.float32, device=w.device) if norm else None
+        ops.gathered_dense(features, idx, packed, k, epilogue=("ln_relu" if relu else "ln") if norm else "none",
+                           out=y, pre=pre, stats=stats)
+        if not norm and relu:
+            y = torch.relu_(y)
+        ctx.save_for_backward(features, idx, y, pre if norm else y, stats if norm else torch.empty(0, device=w.device))
+        ctx.norm, ctx.relu, ctx.k = norm, relu, k
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        features, idx, y, pre, stats = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, d = y.shape
+        if ctx.norm:
+            d_pre = torch.empty_like(dy)
+            check(_lib.load().sgcn_ln_act_bwd(ptr(pre), pre.stride(0), ptr(y), y.stride(0), ptr(dy), dy.stride(0), n, None,
+                                              d, None, ptr(stats), 1 if ctx.relu else 0, ptr(d_pre), d_pre.stride(0),
+                                              None, None, stream_ptr()))
+        else:
+            d_pre = dy * (y > 0) if ctx.relu else dy
+        x = ops.gather_rows(features, idx)[:, :ctx.k]
+        return torch.mm(x.t(), d_pre), None, None, None, None
+
+
 # ---- layers -------------------------------------------------------------------------------------------
 class Parameter:
     """A trainable tensor with Adam slots (kept outside torch.optim: the update is the library's kernel)."""
@@ -197,6 +235,13 @@ class Dense(Layer):
         if self.norm:
             return layer_norm_act(out, None, None, 1e-9, relu)
         return torch.relu(out) if relu else out
+
+    def forward_gathered(self, features, idx):
+        """``self(features[idx])`` without materialising the gathered rows: one tensor-core kernel with the gather
+        as its A-operand load (128 output columns, 16-byte aligned feature rows)."""
+        if self.sparse_inputs or self.vars["weights"].data.shape[1] != 128:
+            raise ValueError("the fused layer needs dense inputs and 128 output columns")
+        return _GatheredDenseFn.apply(self.vars["weights"].data, features, idx, self.norm, self.act == "relu")
 
 
 class AugmentedDropoutDense(Layer):

@@ -44,6 +44,40 @@ def gather_rows(src, idx, out=None, n_dev=None):
     return out
 
 
+def pack_dense_weights(w):
+    """Split W [K, 128] into tf32 hi / lo parts in the shared-memory image of every K-chunk (sgcn_gemm_pack_w):
+    the B operand of gathered_dense; repack after every update of W."""
+    _f32(w, "w")
+    k, n = w.shape
+    lib = _lib.load()
+    count = lib.sgcn_gemm_packed_floats(k, n)
+    if count < 0:
+        raise ValueError("the fused dense layer is built for 128 output columns")
+    packed = torch.empty(count, dtype=torch.float32, device=w.device)
+    check(lib.sgcn_gemm_pack_w(ptr(w), _ld(w), k, n, ptr(packed), stream_ptr()))
+    return packed
+
+
+def gathered_dense(src, idx, w_packed, k, epilogue="ln_relu", eps=1e-9, out=None, pre=None, stats=None, n_dev=None):
+    """out[i, :] = act(LN(src[idx[i], :k] @ W)) in one kernel on the tcgen05 tensor cores (TF32 x 3 split, fp32
+    result to ~1e-6): the first dense layer of the pre-processed models (gcn/layers.py:100-138) with the
+    feature-row gather (history.dense_slice, gcn/train.py:190) as its A-operand load.  ``idx`` None: rows
+    0 .. len(out)-1.  ``epilogue``: "none" | "ln_relu" | "ln".  ``pre`` / ``stats``: optional outputs for the
+    backward (raw product; {mean, rstd} per row)."""
+    _f32(src, "src")
+    if idx is not None:
+        _i32(idx, "idx")
+    n = idx.numel() if idx is not None else (out.shape[0] if out is not None else src.shape[0])
+    if out is None:
+        out = torch.empty((n, 128), dtype=torch.float32, device=src.device)
+    _f32(out, "out")
+    code = {"none": 0, "ln_relu": 1, "ln": 2}[epilogue]
+    check(_lib.load().sgcn_gather_gemm_tf32x3(ptr(src), _ld(src), ptr(idx), n, ptr(n_dev), int(k), ptr(w_packed), 128,
+                                              ptr(out), _ld(out), ptr(pre), _ld(pre) if pre is not None else 0,
+                                              ptr(stats), code, float(eps), stream_ptr()))
+    return out
+
+
 def history_update(hist, idx, rows, n_dev=None, done_counter=None):
     """hist[idx[i], :] = rows[i, :]  -- tf.scatter_update (gcn/models.py:160-166)."""
     _f32(hist, "hist"); _i32(idx, "idx"); _f32(rows, "rows")

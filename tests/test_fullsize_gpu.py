@@ -46,7 +46,7 @@ def record(name, entry):
         json.dump(SUMMARY, f, indent=1)
 
 
-def run_case(name, workload, S, n_graphs, host_io, fuse=True):
+def run_case(name, workload, S, n_graphs, host_io, fuse=False):
     import bench
     from stochastic_gcn_b200.step import HotPathStep
     w = bench.WORKLOADS[workload]
@@ -128,9 +128,9 @@ def test_reddit_cv_d2_device_graph_of_20():
     run_case("reddit_cv_device_graph20", "reddit_cv", 20, 2, False)
 
 
-def test_reddit_cv_d2_write_back_as_its_own_launch():
-    """same, with the history write-back as a launch of its own on the chain (the multi-GPU form of the chain)"""
-    run_case("reddit_cv_device_graph20_unfused", "reddit_cv", 20, 1, False, fuse=False)
+def test_reddit_cv_d2_write_back_fused_into_the_mean():
+    """same, with the history write-back carried by the tail of the full-neighbour mean's launch (the opt-in form)"""
+    run_case("reddit_cv_device_graph20_fused", "reddit_cv", 20, 1, False, fuse=True)
 
 
 def test_reddit_cvd_d1_host_buffer_graphs():

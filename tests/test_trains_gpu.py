@@ -13,7 +13,7 @@ from tests.test_step_gpu import close, oracle_step
 pytestmark = pytest.mark.gpu
 
 
-def setup(mode, deg, norm, n_batches, train, fuse=True, share=True, seed=4):
+def setup(mode, deg, norm, n_batches, train, fuse=False, share=True, seed=4):
     from stochastic_gcn_b200 import graphs
     from stochastic_gcn_b200.step import HotPathStep
     g = graphs.powerlaw_graph(3000, 120_000, seed=seed, device="cuda", max_degree=600)
@@ -95,10 +95,11 @@ def test_pinned_host_ids_and_a_second_run_continue_the_state():
     assert np.array_equal(step.history.cpu().numpy(), check_run.hist)
 
 
-@pytest.mark.parametrize("mode,deg", [("cv", 2), ("cvd", 1), ("ns", 1)])
-def test_captured_trains_device_tables(mode, deg):
+@pytest.mark.parametrize("mode,deg,fuse", [("cv", 2, False), ("cvd", 1, False), ("ns", 1, False), ("cv", 2, True),
+                                           ("cvd", 1, True)])
+def test_captured_trains_device_tables(mode, deg, fuse):
     S = 10
-    g, step, o, feats, table, D = setup(mode, deg, "graphsage", 4 * S, train=4)
+    g, step, o, feats, table, D = setup(mode, deg, "graphsage", 4 * S, train=4, fuse=fuse)
     check_run.hist = step.history.cpu().numpy().copy()
     step.capture_trains(S, table[:S], first_train=2)           # eager warm-up run = passes 0 .. S-1
     step.replay_trains(table[S:])                              # three replays
