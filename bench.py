@@ -16,7 +16,6 @@ import json
 import os
 
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per stream (see stochastic_gcn_b200/__init__.py)
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")         # no first-launch stalls behind device-side waits (same place)
 import subprocess
 import sys
 import threading

@@ -24,8 +24,8 @@ import os as _os
 # processes its entries in order -- a waiting kernel's stream can then hold back an unrelated one.  One queue
 # per stream avoids that; it only takes effect if set before the CUDA context is created.
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# Lazy module loading can make the FIRST launch of a kernel wait for the device to go idle -- behind a thread
-# block that waits for that very kernel (the fused write-back waits for the sampled aggregate; the train sampler
-# for consumer marks).  The drivers run their first pass without device-side waits on later submissions; eager
-# loading removes the hazard for direct users of those entry points as well.
-_os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+# Lazy module loading (the CUDA default) can make the FIRST launch of a kernel wait for the device to go idle --
+# behind a thread block that waits for that very kernel.  The step drivers therefore run their first pass without
+# device-side waits on later submissions (csrc/step.cu); CUDA_MODULE_LOADING=EAGER removes the hazard for direct
+# users of the fused / train entry points too, at the price of loading every kernel of every CUDA library in the
+# process at start-up (tens of seconds on a cold machine) -- not set here.

@@ -17,8 +17,14 @@
 // registers (coalesced 128-byte row segments, two K-chunks prefetched ahead) -> hi / lo -> shared memory in the
 // swizzled layout the matrix descriptor names.  W is split and laid out ONCE (sgcn_gemm_pack_w) as the exact
 // shared-memory image of every K-chunk, so a stage's B operand (hi and lo tile, 32 KB) is one bulk copy by the
-// TMA engine (cp.async.bulk, completion counted on an mbarrier).  Three stages; a stage is handed back by
-// tcgen05.commit when the MMAs that read it have retired, so chunk k+1 is staged while chunk k multiplies.
+// TMA engine (cp.async.bulk, completion counted on an mbarrier).
+//
+// Roles (no block-wide barrier inside the K loop): eight producer warps stage A (3 stages; each warp arrives on
+// the stage's "A full" mbarrier after its stores and the proxy fence); one thread of a ninth warp keeps the bulk
+// copies of W three chunks ahead (4 stages), waits for "A full" / "B full", issues the 12 MMAs of the chunk and
+// hands both stages back with tcgen05.commit ("A empty" / "B empty" arrive when those MMAs have retired).
+// The first form of this kernel (all threads staging, one __syncthreads and the W copy's full latency per
+// chunk) took 59 us under ncu for the headline shape; profiles/r02_gather_gemm_ncu.json.
 #include "common.cuh"
 
 namespace sgcn {
@@ -26,12 +32,15 @@ namespace sgcn {
 constexpr int kGemmM = 128;            // rows per thread block = TMEM lanes
 constexpr int kGemmN = 128;            // output width = accumulator columns (fp32)
 constexpr int kGemmKC = 32;            // K per stage: 32 tf32 = one 128-byte swizzle row
-constexpr int kGemmStages = 3;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmStagesA = 3;        // A stages (hi | lo tile), filled by the producer warps
+constexpr int kGemmStagesB = 4;        // B stages (hi | lo tile), filled by the TMA engine three chunks ahead
+constexpr int kGemmProducers = 256;    // 8 producer warps stage the A rows ...
+constexpr int kGemmThreads = kGemmProducers + 32;        // ... one more warp issues the bulk copies and the MMAs
 constexpr int kGemmPrefetch = 2;       // K-chunks of A rows held in registers ahead of the one being staged
 constexpr int kTileBytes = kGemmM * 128;                 // 16 KB: 128 rows x 128 bytes
-constexpr int kStageBytes = 4 * kTileBytes;              // A_hi, A_lo, B_hi, B_lo
-constexpr int kGemmSmem = kGemmStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers, ids*/ + kGemmM * 4;
+constexpr int kPairBytes = 2 * kTileBytes;               // a hi | lo pair
+constexpr int kGemmSmem = (kGemmStagesA + kGemmStagesB) * kPairBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+                          kGemmM * 4;
 
 // byte offset of element (row r, k in [0, 32)) inside a 128-row K-major tile with the 128-byte swizzle:
 // 8-row groups of 1024 bytes, 16-byte chunk index XOR row-in-group (Swizzle<3,4,3>)
@@ -51,6 +60,9 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 // ---- mbarrier / TMA / tcgen05 wrappers (PTX ISA 8.6+, sm_100a) --------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -138,20 +150,29 @@ gather_gemm_tf32x3_kernel(const GemmArgs a) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: the swizzle pattern is a function of the address bits
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = (uint64_t*)(smem + kGemmStages * kStageBytes);     // [0,3) B landed, [3,6) stage free, [6] done
-    uint32_t* s_tmem = (uint32_t*)(bars + 8);
+    uint8_t* smem_a = smem;                                             // [3] x {hi tile, lo tile}
+    uint8_t* smem_b = smem + kGemmStagesA * kPairBytes;                 // [4] x {hi tile, lo tile}
+    uint64_t* bars = (uint64_t*)(smem + (kGemmStagesA + kGemmStagesB) * kPairBytes);
+    uint64_t* a_full = bars;                    // [3]  8 arrivals: the producer warps
+    uint64_t* a_empty = bars + 3;               // [3]  tcgen05.commit
+    uint64_t* b_full = bars + 6;                // [4]  bulk copy (transaction bytes)
+    uint64_t* b_empty = bars + 10;              // [4]  tcgen05.commit
+    uint64_t* done = bars + 14;                 //      the accumulator is complete
+    uint32_t* s_tmem = (uint32_t*)(bars + 16);
     int32_t* s_row = (int32_t*)(s_tmem + 4);                             // source row of each tile row, -1 = none
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = dev_count(a.n_dev, a.n);
     const int m0 = blockIdx.x * kGemmM;
     if (m0 >= n) return;
     const int nk = (a.K + kGemmKC - 1) / kGemmKC;
 
     if (tid == 0) {
-        for (int i = 0; i < 2 * kGemmStages + 1; ++i) mbar_init(smem_addr(bars + i), 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(smem_addr(a_full + i), kGemmProducers / 32); mbar_init(smem_addr(a_empty + i), 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(smem_addr(b_full + i), 1); mbar_init(smem_addr(b_empty + i), 1); }
+        mbar_init(smem_addr(done), 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(smem_addr(s_tmem), kGemmN);               // 128 columns x 128 lanes x fp32
+    if (warp == kGemmProducers / 32) tmem_alloc(smem_addr(s_tmem), kGemmN);   // 128 columns x 128 lanes x fp32
     for (int r = tid; r < kGemmM; r += kGemmThreads)
         s_row[r] = m0 + r < n ? (a.idx ? a.idx[m0 + r] : m0 + r) : -1;
     tc_fence_before();
@@ -159,55 +180,71 @@ gather_gemm_tf32x3_kernel(const GemmArgs a) {
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
 
-    // A staging: the tile is 128 rows x 8 chunks of 16 bytes; thread t covers rows t/8 + 32 i (i < 4), chunk t%8 --
-    // 8 consecutive threads read one row's contiguous 128 bytes
-    const int chunk = tid & 7;
-    int64_t row_off[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = (tid >> 3) + 32 * i;
-        const int src_row = s_row[r];
-        row_off[i] = src_row >= 0 ? (int64_t)src_row * a.ld_src : -1;
-    }
-    auto load_chunk = [&](int kc, float4 (&dst)[4]) {
-        const int k = kc * kGemmKC + chunk * 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            dst[i] = (kc < nk && row_off[i] >= 0 && k < a.K) ? ldg_stream4(a.src + row_off[i] + k)
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    // one K-chunk: `cur` holds its A rows (loaded two chunks ago), `far` receives the rows of chunk kc + 2
-    auto step = [&](int kc, float4 (&cur)[4], float4 (&far)[4]) {
-        const int s = kc % kGemmStages, use = kc / kGemmStages;
-        uint8_t* stage = smem + s * kStageBytes;
-        // the MMAs that read this stage three chunks ago have retired
-        if (kc >= kGemmStages) mbar_wait(smem_addr(bars + kGemmStages + s), (use - 1) & 1);
-        if (tid == 0) {                                   // B operand of this chunk: one bulk copy (hi | lo tile)
-            mbar_expect_tx(smem_addr(bars + s), 2 * kTileBytes);
-            bulk_g2s(smem_addr(stage + 2 * kTileBytes), a.w_packed + (size_t)kc * (2 * kTileBytes / 4), 2 * kTileBytes,
-                     smem_addr(bars + s));
-        }
-        load_chunk(kc + kGemmPrefetch, far);
-        // split and stage the A rows of this chunk
+    if (warp < kGemmProducers / 32) {
+        // ===== producers: A rows global -> registers -> tf32 hi / lo -> swizzled shared memory =====
+        // the tile is 128 rows x 8 chunks of 16 bytes; thread t covers rows t/8 + 32 i (i < 4), chunk t%8 --
+        // 8 consecutive threads read one row's contiguous 128 bytes
+        const int chunk = tid & 7;
+        int64_t row_off[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int r = (tid >> 3) + 32 * i;
-            float4 hi, lo;
-            hi.x = tf32_round(cur[i].x); lo.x = tf32_round(cur[i].x - hi.x);
-            hi.y = tf32_round(cur[i].y); lo.y = tf32_round(cur[i].y - hi.y);
-            hi.z = tf32_round(cur[i].z); lo.z = tf32_round(cur[i].z - hi.z);
-            hi.w = tf32_round(cur[i].w); lo.w = tf32_round(cur[i].w - hi.w);
-            const int off = tile_offset(r, chunk * 4);
-            *(float4*)(stage + off) = hi;
-            *(float4*)(stage + kTileBytes + off) = lo;
+            const int src_row = s_row[(tid >> 3) + 32 * i];
+            row_off[i] = src_row >= 0 ? (int64_t)src_row * a.ld_src : -1;
         }
-        fence_proxy_async_smem();                         // generic-proxy stores -> visible to the tensor core's reads
-        __syncthreads();
-        if (tid == 0) {
-            mbar_wait(smem_addr(bars + s), use & 1);      // the W tiles have landed
+        auto load_chunk = [&](int kc, float4 (&dst)[4]) {
+            const int k = kc * kGemmKC + chunk * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                dst[i] = (kc < nk && row_off[i] >= 0 && k < a.K) ? ldg_stream4(a.src + row_off[i] + k)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        // one K-chunk: `cur` holds its rows (loaded two chunks ago), `far` receives the rows of chunk kc + 2
+        auto step = [&](int kc, float4 (&cur)[4], float4 (&far)[4]) {
+            const int s = kc % kGemmStagesA, use = kc / kGemmStagesA;
+            uint8_t* stage = smem_a + s * kPairBytes;
+            if (kc >= kGemmStagesA) mbar_wait(smem_addr(a_empty + s), (use - 1) & 1);   // its last readers have retired
+            load_chunk(kc + kGemmPrefetch, far);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = (tid >> 3) + 32 * i;
+                float4 hi, lo;
+                hi.x = tf32_round(cur[i].x); lo.x = tf32_round(cur[i].x - hi.x);
+                hi.y = tf32_round(cur[i].y); lo.y = tf32_round(cur[i].y - hi.y);
+                hi.z = tf32_round(cur[i].z); lo.z = tf32_round(cur[i].z - hi.z);
+                hi.w = tf32_round(cur[i].w); lo.w = tf32_round(cur[i].w - hi.w);
+                const int off = tile_offset(r, chunk * 4);
+                *(float4*)(stage + off) = hi;
+                *(float4*)(stage + kTileBytes + off) = lo;
+            }
+            fence_proxy_async_smem();                     // generic-proxy stores -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_addr(a_full + s));
+        };
+        static_assert(kGemmPrefetch == 2, "the register rotation below is written for two chunks of prefetch");
+        float4 r0[4], r1[4], r2[4];                       // rotating register sets (static indices: no local memory)
+        load_chunk(0, r0);
+        load_chunk(1, r1);
+        for (int kc = 0; kc < nk; kc += 3) {
+            step(kc, r0, r2);
+            if (kc + 1 < nk) step(kc + 1, r1, r0);
+            if (kc + 2 < nk) step(kc + 2, r2, r1);
+        }
+    } else if (lane == 0) {
+        // ===== one thread: W tiles by bulk copy (three chunks ahead), MMA issue, stage hand-back =====
+        auto copy_b = [&](int kc) {
+            const int sb = kc % kGemmStagesB;
+            mbar_expect_tx(smem_addr(b_full + sb), kPairBytes);
+            bulk_g2s(smem_addr(smem_b + sb * kPairBytes), a.w_packed + (size_t)kc * (kPairBytes / 4), kPairBytes,
+                     smem_addr(b_full + sb));
+        };
+        for (int kc = 0; kc < kGemmStagesB - 1 && kc < nk; ++kc) copy_b(kc);
+        for (int kc = 0; kc < nk; ++kc) {
+            const int sa = kc % kGemmStagesA, sb = kc % kGemmStagesB;
+            mbar_wait(smem_addr(a_full + sa), (kc / kGemmStagesA) & 1);
+            mbar_wait(smem_addr(b_full + sb), (kc / kGemmStagesB) & 1);
             tc_fence_after();
-            const uint32_t a_hi = smem_addr(stage), a_lo = a_hi + kTileBytes, b_hi = a_hi + 2 * kTileBytes,
-                           b_lo = a_hi + 3 * kTileBytes;
+            const uint32_t a_hi = smem_addr(smem_a + sa * kPairBytes), a_lo = a_hi + kTileBytes;
+            const uint32_t b_hi = smem_addr(smem_b + sb * kPairBytes), b_lo = b_hi + kTileBytes;
 #pragma unroll
             for (int ks = 0; ks < kGemmKC / 8; ++ks) {    // one MMA = 8 tf32 of K = 32 bytes along the swizzle row
                 const uint32_t o = ks * 32;
@@ -215,22 +252,20 @@ gather_gemm_tf32x3_kernel(const GemmArgs a) {
                 umma_tf32(tmem, umma_desc(a_lo + o), umma_desc(b_hi + o), kIdescTf32, 1);
                 umma_tf32(tmem, umma_desc(a_hi + o), umma_desc(b_lo + o), kIdescTf32, 1);
             }
-            umma_commit(smem_addr(bars + kGemmStages + s));                  // stage free once these have retired
-            if (kc == nk - 1) umma_commit(smem_addr(bars + 2 * kGemmStages)); // ... and the accumulator complete
+            umma_commit(smem_addr(a_empty + sa));         // both stages free once these MMAs have retired
+            umma_commit(smem_addr(b_empty + sb));
+            if (kc == nk - 1) umma_commit(smem_addr(done));   // ... and the accumulator complete
+            // behind the issue: the W tiles of chunk kc + 3 go where chunk kc - 1 was read from
+            if (kc + kGemmStagesB - 1 < nk) {
+                if (kc >= 1) mbar_wait(smem_addr(b_empty + (kc - 1) % kGemmStagesB), ((kc - 1) / kGemmStagesB) & 1);
+                copy_b(kc + kGemmStagesB - 1);
+            }
         }
-    };
-    static_assert(kGemmPrefetch == 2, "the register rotation below is written for two chunks of prefetch");
-    float4 r0[4], r1[4], r2[4];                           // rotating register sets (static indices: no local memory)
-    load_chunk(0, r0);
-    load_chunk(1, r1);
-    for (int kc = 0; kc < nk; kc += 3) {
-        step(kc, r0, r2);
-        if (kc + 1 < nk) step(kc + 1, r1, r0);
-        if (kc + 2 < nk) step(kc + 2, r2, r1);
     }
+    if (warp == kGemmProducers / 32) __syncwarp();      // its other lanes park here instead of polling beside the issuer
 
     // ---- epilogue: TMEM -> registers, one thread = one row (warps 0..3 own TMEM lanes 32 w .. 32 w + 31) ----
-    mbar_wait(smem_addr(bars + 2 * kGemmStages), 0);
+    mbar_wait(smem_addr(done), 0);
     tc_fence_after();
     if (warp < 4) {
         const int r = tid;                                 // tile row = TMEM lane
@@ -280,14 +315,14 @@ gather_gemm_tf32x3_kernel(const GemmArgs a) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, kGemmN);
+    if (warp == kGemmProducers / 32) tmem_dealloc(tmem, kGemmN);
 }
 
 // W [K, 128] row-major (x @ W) -> per K-chunk of 32 the two B tiles (n-major rows of 32 k: B[n][k] = W[k][n]),
 // split into tf32 hi / lo and laid out exactly as the kernel's shared-memory stage expects them
 __global__ void gemm_pack_w_kernel(const float* __restrict__ w, int64_t ld_w, int K, float* __restrict__ packed) {
     const int kc = blockIdx.x;
-    uint8_t* base = (uint8_t*)packed + (size_t)kc * 2 * kTileBytes;
+    uint8_t* base = (uint8_t*)packed + (size_t)kc * kPairBytes;
     for (int e = threadIdx.x; e < kGemmN * kGemmKC; e += blockDim.x) {
         const int kk = e / kGemmN, nn = e % kGemmN;        // consecutive threads: consecutive n (coalesced reads of W)
         const int k = kc * kGemmKC + kk;
@@ -307,7 +342,7 @@ extern "C" {
 
 int64_t sgcn_gemm_packed_floats(int32_t K, int32_t N) {
     if (K <= 0 || N != kGemmN) return -1;
-    return (int64_t)((K + kGemmKC - 1) / kGemmKC) * (2 * kTileBytes / 4);
+    return (int64_t)((K + kGemmKC - 1) / kGemmKC) * (kPairBytes / 4);
 }
 
 int sgcn_gemm_pack_w(const float* w, int64_t ld_w, int32_t K, int32_t N, float* packed, void* stream) {
