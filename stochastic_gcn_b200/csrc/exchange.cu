@@ -325,13 +325,16 @@ static int fill_ptrs(PeerPtrs& p, void* const* src, int n, const char* what) {
 }
 
 // Thread blocks of a pack / push launch.  Few enough to be resident all at once beside a full-neighbour mean (a
-// launch with blocks still waiting for room holds up every later launch): SGCN_PUSH_BLOCKS, default 64.
-static int pack_blocks(int n_bound, int D) {
-    static int cap = 0;
-    if (cap == 0) {
+// launch with blocks still waiting for room holds up every later launch), enough to keep the peer stores flowing:
+// 64 for up to 4 destinations (2 GPUs: 28.8 us per pass against 29.5 with 192 and 35.7 with 24; 4 GPUs: 39.7
+// against 41.8), 192 beyond (the measured 8-GPU form).  SGCN_PUSH_BLOCKS overrides.
+static int pack_blocks(int n_bound, int D, int n_dst = 1) {
+    static int forced = -1;
+    if (forced < 0) {
         const char* e = getenv("SGCN_PUSH_BLOCKS");
-        cap = e ? std::max(1, std::min(atoi(e), kNumSMs * 2)) : 64;
+        forced = e ? std::max(1, std::min(atoi(e), kNumSMs * 2)) : 0;
     }
+    const int cap = forced > 0 ? forced : (n_dst > 4 ? 192 : 64);
     const int64_t work = std::max<int64_t>((int64_t)n_bound * std::max(D / 4, 1), 1);
     return (int)std::min<int64_t>((work + 255) / 256, cap);
 }
@@ -389,7 +392,7 @@ int sgcn_wb_push_ring(const int32_t* field, const int32_t* n_dev, int32_t n_boun
     if (rc != SGCN_OK) return rc;
     WbPushArgs a{field, n_dev, n_bound, rows, ld_rows, D, pb, pb, n_dst, 0, push_epoch, pf, my_rank, block_counter,
                  ring, ring_stride};
-    wb_pack_kernel<<<pack_blocks(n_bound, D), 256, 0, (cudaStream_t)stream>>>(a, g_trace);
+    wb_pack_kernel<<<pack_blocks(n_bound, D, n_dst), 256, 0, (cudaStream_t)stream>>>(a, g_trace);
     SGCN_LAUNCHED();
     return SGCN_OK;
 }
@@ -410,6 +413,17 @@ static int launch_apply(float* hist, int64_t ld_h, int32_t D, const void* g_even
                          ring, ring_stride, apply_counter, shard_rank, shard_rows, reads_peers ? *reads_peers : none,
                          reads_flags));
     SGCN_LAUNCHED();
+    // A/B (SGCN_WB_COPY_PDL=0): the copy pass launched plainly instead of programmatically.  Launched
+    // programmatically it is resident for the whole full-neighbour mean (256 threads x 64 registers per block take
+    // every register the mean leaves free on up to 96 SMs) -- yet the plain form measured SLOWER on 2 GPUs (37.6 vs
+    // 28.6 us per pass): its launch latency lands on the chain, and the gather / push of the next pass did not
+    // start any earlier (profiles/r02_timeline_2gpu_copy_plain.txt).
+    static int copy_pdl = -1;
+    if (copy_pdl < 0) {
+        const char* e = getenv("SGCN_WB_COPY_PDL");
+        copy_pdl = !(e && e[0] == '0');
+    }
+    PdlOff copy_plain(ring > 0 && shard_rows == 0 && !copy_pdl);
     // few CTAs: with PDL they sit resident beside the full-neighbour mean, and the next batch's sampler
     // CTA still has to find an SM with registers to spare
     dim3 g2(std::max(1, std::min(div_up(std::max(n_bound, 1), 32), 96 / std::max(world, 1))), world);
