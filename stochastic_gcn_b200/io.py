@@ -64,11 +64,15 @@ def load_cache(path):
 
 
 # ---- checkpoints ------------------------------------------------------------------------------------
-def save_checkpoint(path, variables, history, optimizer=None, sampler_state=None):
+def save_checkpoint(path, variables, history, optimizer=None, sampler_state=None, host_state=None):
     """variables: list of arrays (trainable variables in layer order); history: list of [N, D] tables;
     optimizer: optional dict {"t": int, "m": [...], "v": [...]}; sampler_state: optional dict
     {"mt_state": uint32[624], "mt_pos": int, "adj_i": int32[E], "adj_w": float32[E]} -- the engine and
-    the permuted adjacency rows (row pointers never change)."""
+    the permuted adjacency rows (row pointers never change; DeviceSampler.get_state()); host_state: optional dict
+    {"dropout_seed": int, "dropout_offset": int, "numpy_rng": np.random.get_state(), "epoch_data": int32[n],
+    "epoch_start": int} -- the Philox counter of nn.DropoutState, the global NumPy RNG PyScheduler.shuffle draws
+    from, and the shuffled id list with its cursor.  With all of them a resumed run repeats an uninterrupted one
+    bit for bit (tests/test_resume_gpu.py)."""
     out = {"n_vars": len(variables), "n_history": len(history)}
     for k, v in enumerate(variables):
         out["var_%d" % k] = np.asarray(v, dtype=np.float32)
@@ -84,17 +88,26 @@ def save_checkpoint(path, variables, history, optimizer=None, sampler_state=None
         out["mt_pos"] = int(sampler_state["mt_pos"])
         out["adj_i"] = np.asarray(sampler_state["adj_i"], dtype=np.int32)
         out["adj_w"] = np.asarray(sampler_state["adj_w"], dtype=np.float32)
+    if host_state is not None:
+        out["dropout_seed"], out["dropout_offset"] = int(host_state["dropout_seed"]), int(host_state["dropout_offset"])
+        if host_state.get("numpy_rng") is not None:
+            kind, keys, pos, has_gauss, cached = host_state["numpy_rng"]
+            out["np_rng_keys"], out["np_rng_pos"] = np.asarray(keys, dtype=np.uint32), int(pos)
+            out["np_rng_gauss"] = np.asarray([has_gauss, cached], dtype=np.float64)
+        if host_state.get("epoch_data") is not None:
+            out["epoch_data"] = np.asarray(host_state["epoch_data"], dtype=np.int32)
+            out["epoch_start"] = int(host_state.get("epoch_start", 0))
     with open(path, "wb") as f:
         np.savez(f, **out)
 
 
 def load_checkpoint(path, load_history=True):
-    """-> dict(variables, history, optimizer | None, sampler_state | None).  load_history=False mirrors
+    """-> dict(variables, history, optimizer | None, sampler_state | None, host_state | None).  load_history=False mirrors
     ``Model.load(sess, load_history=False)`` (gcn/models.py:211-220): the tables are left out."""
     data = np.load(path)
     res = {"variables": [data["var_%d" % k] for k in range(int(data["n_vars"]))],
            "history": [data["history_%d" % k] for k in range(int(data["n_history"]))] if load_history else [],
-           "optimizer": None, "sampler_state": None}
+           "optimizer": None, "sampler_state": None, "host_state": None}
     if "adam_t" in data.files:
         n = len(res["variables"])
         res["optimizer"] = {"t": int(data["adam_t"]), "m": [data["adam_m_%d" % k] for k in range(n)],
@@ -102,4 +115,13 @@ def load_checkpoint(path, load_history=True):
     if "mt_state" in data.files:
         res["sampler_state"] = {"mt_state": data["mt_state"], "mt_pos": int(data["mt_pos"]), "adj_i": data["adj_i"],
                                 "adj_w": data["adj_w"]}
+    if "dropout_seed" in data.files:
+        hs = {"dropout_seed": int(data["dropout_seed"]), "dropout_offset": int(data["dropout_offset"]),
+              "numpy_rng": None, "epoch_data": None, "epoch_start": 0}
+        if "np_rng_keys" in data.files:
+            g = data["np_rng_gauss"]
+            hs["numpy_rng"] = ("MT19937", data["np_rng_keys"], int(data["np_rng_pos"]), int(g[0]), float(g[1]))
+        if "epoch_data" in data.files:
+            hs["epoch_data"], hs["epoch_start"] = data["epoch_data"], int(data["epoch_start"])
+        res["host_state"] = hs
     return res

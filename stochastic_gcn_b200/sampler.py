@@ -199,6 +199,28 @@ class DeviceSampler:
         st = np.ascontiguousarray(state, dtype=np.uint32)
         check(self._lib.sgcn_sampler_set_rng(self._h, ptr(st), int(pos)))
 
+    def get_state(self):
+        """Everything a resumed run needs to continue the reference's sampling sequence bit for bit: the engine
+        (``mt_state`` / ``mt_pos``) and the stored adjacency rows, which the uniform sampler permutes in place and
+        never restores (gcn/scheduler.cpp:144-145; row pointers never change).  Synchronises."""
+        st, pos = self.get_rng()
+        return {"mt_state": st, "mt_pos": pos, "adj_i": self.host("adj_i", self.num_edges),
+                "adj_w": self.host("adj_w", self.num_edges)}
+
+    def set_state(self, state):
+        """Restore ``get_state()`` (e.g. from io.load_checkpoint(...)["sampler_state"]) into this sampler, which must
+        have been built over the same graph."""
+        adj_i = np.ascontiguousarray(state["adj_i"], dtype=np.int32)
+        adj_w = np.ascontiguousarray(state["adj_w"], dtype=np.float32)
+        if adj_i.shape[0] != self.num_edges or adj_w.shape[0] != self.num_edges:
+            raise ValueError("sampler state of a different graph: %d stored entries, this sampler has %d"
+                             % (adj_i.shape[0], self.num_edges))
+        torch.cuda.synchronize()
+        self.view("adj_i", count=self.num_edges).copy_(torch.from_numpy(adj_i))
+        self.view("adj_w", count=self.num_edges).copy_(torch.from_numpy(adj_w))
+        torch.cuda.synchronize()
+        self.set_rng(state["mt_state"], state["mt_pos"])
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.sgcn_sampler_destroy(self._h)

@@ -49,60 +49,60 @@ class PyScheduler:
 
     def shuffle(self):
         np.random.shuffle(self.data)      # the reference uses the global NumPy RNG (_scheduler.pyx:51)
-        self.start = 0
-        self.t = 0
+        self.start, self.t = 0, 0
 
     # -- reference-format (host) path ------------------------------------------------------------
+    # placeholder key -> (argument of get_feed_dict, only with control variates); one entry per hop
+    _PER_HOP = (("adj", "adjs", False), ("scales", "scales", False), ("madj", "madjs", True),
+                ("fadj", "fadjs", True), ("ffields", "ffields", True))
+
+    @staticmethod
+    def _coo(rows, cols, vals, n_rows, n_cols):
+        """(int32 [ne, 2] index pairs, float32 values, dense shape): the triple TF's sparse placeholders take"""
+        return np.stack((rows, cols), axis=1).astype(np.int32, copy=False), vals, (n_rows, n_cols)
+
+    def _hop_host(self, degree, n_rows):
+        """one expand() copied to fresh host arrays (as _scheduler.pyx:69-111 memcpy's the C++ vectors)"""
+        self.c_sch.expand(int(degree), materialize_full=self.cv)
+        s = self.c_sch.snapshot()
+        hop = {"fields": s["field"], "scales": s["scales"],
+               "adjs": self._coo(s["edg_s"], s["edg_t"], s["edg_w"], n_rows, s["field"].shape[0])}
+        if self.cv:
+            idx, _, shape = hop["adjs"]
+            hop["ffields"] = s["ffield"]
+            hop["madjs"] = (idx.copy(), s["medg_w"], np.array(shape))
+            hop["fadjs"] = self._coo(s["fedg_s"], s["fedg_t"], s["fedg_w"], n_rows, s["ffield"].shape[0])
+        return hop
+
     def batch(self, data):
         data = np.ascontiguousarray(data, dtype=np.int32)
-        fields, ffields, adjs, madjs, fadjs, scales = [data], [], [], [], [], []
-        sch = self.c_sch
-        sch.start_batch(data)
-        for l in range(self.L):
-            sch.expand(int(self.degrees[self.L - l - 1]), materialize_full=self.cv)
-            s = sch.snapshot()
-            fields.append(s["field"])
-            scales.append(s["scales"])
-            ne = s["edg_s"].shape[0]
-            edg_i = np.zeros((ne, 2), dtype=np.int32)
-            edg_i[:, 0] = s["edg_s"]
-            edg_i[:, 1] = s["edg_t"]
-            shape = (fields[-2].shape[0], fields[-1].shape[0])
-            adjs.append((edg_i, s["edg_w"], shape))
-            if self.cv:
-                ffields.append(s["ffield"])
-                ne2 = s["fedg_s"].shape[0]
-                fedg_i = np.zeros((ne2, 2), dtype=np.int32)
-                fedg_i[:, 0] = s["fedg_s"]
-                fedg_i[:, 1] = s["fedg_t"]
-                fshape = (fields[-2].shape[0], ffields[-1].shape[0])
-                madjs.append((np.copy(edg_i), s["medg_w"], np.copy(shape)))
-                fadjs.append((fedg_i, s["fedg_w"], fshape))
-        for lst in (fields, ffields, adjs, madjs, fadjs, scales):
-            lst.reverse()
-        return self.get_feed_dict(fields, ffields, adjs, madjs, fadjs, scales)
+        self.c_sch.start_batch(data)
+        hops, n_rows = [], data.shape[0]
+        for degree in reversed(list(self.degrees[:self.L])):          # output side first, as the sampler walks
+            hops.append(self._hop_host(degree, n_rows))
+            n_rows = hops[-1]["fields"].shape[0]
+        hops.reverse()                                                # index 0 = input-side layer
+        lists = {k: [h[k] for h in hops if k in h] for k in ("fields", "ffields", "adjs", "madjs", "fadjs", "scales")}
+        lists["fields"].append(data)
+        return self.get_feed_dict(**lists)
 
     def minibatch(self, batch_size):
-        if self.start == self.data.shape[0]:
+        n = self.data.shape[0]
+        if self.start >= n:
             return None
-        end = min(self.data.shape[0], self.start + batch_size)
-        batch = self.data[self.start:end]
-        self.start = end
-        return self.batch(batch)
+        ids = self.data[self.start:self.start + batch_size]
+        self.start = min(n, self.start + batch_size)
+        return self.batch(ids)
 
     def get_feed_dict(self, fields, ffields, adjs, madjs, fadjs, scales):
-        ph = self.placeholders
-        labels = self.labels[fields[-1]]
-        feed_dict = {ph['adj'][i]: adjs[i] for i in range(self.L)}
-        feed_dict.update({ph['scales'][i]: scales[i] for i in range(len(scales))})
-        if self.cv:
-            feed_dict.update({ph['madj'][i]: madjs[i] for i in range(len(madjs))})
-            feed_dict.update({ph['fadj'][i]: fadjs[i] for i in range(len(fadjs))})
-            feed_dict.update({ph['ffields'][i]: ffields[i] for i in range(len(ffields))})
-        feed_dict[ph['labels']] = labels
-        for i in range(self.L + 1):
-            feed_dict[ph['fields'][i]] = fields[i]
-        return feed_dict
+        """placeholder -> value, the layout gcn/models.py feeds to sess.run (keys as _scheduler.pyx:136-148)"""
+        ph, given = self.placeholders, locals()
+        feed = {ph["labels"]: self.labels[fields[-1]]}
+        feed.update(zip(ph["fields"], fields[:self.L + 1]))
+        for key, arg, cv_only in self._PER_HOP:
+            if not cv_only or self.cv:
+                feed.update(zip(ph[key], given[arg]))
+        return feed
 
     def get_t(self):
         return self.t

@@ -93,3 +93,26 @@ def test_checkpoint_round_trip(tmp_path):
     io.save_checkpoint(path, variables, history)
     ck = io.load_checkpoint(path)
     assert ck["optimizer"] is None and ck["sampler_state"] is None
+
+
+def test_checkpoint_keeps_the_host_side_random_state(tmp_path):
+    """dropout Philox counter, the global NumPy RNG PyScheduler.shuffle draws from, the shuffled epoch and its cursor"""
+    rng = np.random.RandomState(5)
+    variables, history = [rng.randn(3, 2).astype(np.float32)], []
+    np.random.seed(123)
+    np.random.rand(7)
+    data = np.arange(50, dtype=np.int32)
+    np.random.shuffle(data)
+    host = {"dropout_seed": 9, "dropout_offset": 123456789012, "numpy_rng": np.random.get_state(),
+            "epoch_data": data, "epoch_start": 32}
+    want_next = np.random.rand(5)
+    path = str(tmp_path / "model.npz")
+    io.save_checkpoint(path, variables, history, host_state=host)
+    ck = io.load_checkpoint(path)["host_state"]
+    assert ck["dropout_seed"] == 9 and ck["dropout_offset"] == 123456789012 and ck["epoch_start"] == 32
+    assert np.array_equal(ck["epoch_data"], data)
+    np.random.seed(0)
+    np.random.set_state(ck["numpy_rng"])
+    assert np.array_equal(np.random.rand(5), want_next)
+    io.save_checkpoint(path, variables, history)
+    assert io.load_checkpoint(path)["host_state"] is None
