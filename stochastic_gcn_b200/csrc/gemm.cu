@@ -14,7 +14,7 @@
 // which reproduces the fp32 product to ~1e-6 (tests/test_gemm_gpu.py, against float64).
 //
 // Data movement.  The gather needs a transformation on the way (the split), so the A tile goes global ->
-// registers (coalesced 128-byte row segments, two K-chunks prefetched ahead) -> hi / lo -> shared memory in the
+// registers (coalesced 128-byte row segments, three K-chunks prefetched ahead) -> hi / lo -> shared memory in the
 // swizzled layout the matrix descriptor names.  W is split and laid out ONCE (sgcn_gemm_pack_w) as the exact
 // shared-memory image of every K-chunk, so a stage's B operand (hi and lo tile, 32 KB) is one bulk copy by the
 // TMA engine (cp.async.bulk, completion counted on an mbarrier).
@@ -36,7 +36,7 @@ constexpr int kGemmStagesA = 3;        // A stages (hi | lo tile), filled by the
 constexpr int kGemmStagesB = 4;        // B stages (hi | lo tile), filled by the TMA engine three chunks ahead
 constexpr int kGemmProducers = 256;    // 8 producer warps stage the A rows ...
 constexpr int kGemmThreads = kGemmProducers + 32;        // ... one more warp issues the bulk copies and the MMAs
-constexpr int kGemmPrefetch = 2;       // K-chunks of A rows held in registers ahead of the one being staged
+constexpr int kGemmPrefetch = 3;       // K-chunks of A rows held in registers ahead of the one being staged
 constexpr int kTileBytes = kGemmM * 128;                 // 16 KB: 128 rows x 128 bytes
 constexpr int kPairBytes = 2 * kTileBytes;               // a hi | lo pair
 constexpr int kGemmSmem = (kGemmStagesA + kGemmStagesB) * kPairBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ +
@@ -198,7 +198,7 @@ gather_gemm_tf32x3_kernel(const GemmArgs a) {
                 dst[i] = (kc < nk && row_off[i] >= 0 && k < a.K) ? ldg_stream4(a.src + row_off[i] + k)
                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        // one K-chunk: `cur` holds its rows (loaded two chunks ago), `far` receives the rows of chunk kc + 2
+        // one K-chunk: `cur` holds its rows (loaded three chunks ago), `far` receives the rows of chunk kc + 3
         auto step = [&](int kc, float4 (&cur)[4], float4 (&far)[4]) {
             const int s = kc % kGemmStagesA, use = kc / kGemmStagesA;
             uint8_t* stage = smem_a + s * kPairBytes;
@@ -220,14 +220,16 @@ gather_gemm_tf32x3_kernel(const GemmArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_addr(a_full + s));
         };
-        static_assert(kGemmPrefetch == 2, "the register rotation below is written for two chunks of prefetch");
-        float4 r0[4], r1[4], r2[4];                       // rotating register sets (static indices: no local memory)
+        static_assert(kGemmPrefetch == 3, "the register rotation below is written for three chunks of prefetch");
+        float4 r0[4], r1[4], r2[4], r3[4];                // rotating register sets (static indices: no local memory)
         load_chunk(0, r0);
         load_chunk(1, r1);
-        for (int kc = 0; kc < nk; kc += 3) {
-            step(kc, r0, r2);
+        load_chunk(2, r2);
+        for (int kc = 0; kc < nk; kc += 4) {              // chunk kc lives in set kc % 4, chunk kc + 3 goes to (kc + 3) % 4
+            step(kc, r0, r3);
             if (kc + 1 < nk) step(kc + 1, r1, r0);
             if (kc + 2 < nk) step(kc + 2, r2, r1);
+            if (kc + 3 < nk) step(kc + 3, r3, r2);
         }
     } else if (lane == 0) {
         // ===== one thread: W tiles by bulk copy (three chunks ahead), MMA issue, stage hand-back =====
