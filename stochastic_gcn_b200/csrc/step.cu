@@ -394,11 +394,15 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
     sgcn_sampler* smp = st->sampler;
     const int B = d.batch, H = d.hidden, R = sgcn_step::kRing2, T = st->train;
     const bool cv = d.mode != 0, cvd = d.mode == 2, concat = d.concat != 0, multi = d.world > 1 && cv;
-    // The fused write-back waits ON THE DEVICE for the pass's sampled aggregate, which the host submits after the
-    // mean.  With CUDA's lazy module loading the FIRST launch of a kernel may have to wait for the device to go
-    // idle -- behind a thread block that is waiting for it.  So the first run of a step object uses the unfused
-    // chain (same kernels, no device-side wait on later submissions) and thereby loads every kernel.
-    const bool fuse = cv && !multi && d.fuse_write_back != 0 && st->warmed;
+    // Two device-side waits are for work the host submits LATER: the fused write-back waits for the pass's sampled
+    // aggregate, and a train's sampler waits for the consumer marks of the previous train's passes when they share
+    // a node.  With CUDA's lazy module loading the FIRST launch of a kernel may have to wait for the device to go
+    // idle -- behind a thread block that is waiting for that very kernel (seen as a 4 s bounded spin and a
+    // mis-ordered row permutation in a cold process).  So the first run of a step object uses the unfused chain
+    // and samples every train only after the previous train's passes have finished (stream-ordered, nothing to
+    // wait for on the device), and thereby loads every kernel.
+    const bool cold = !st->warmed;           // first run of this step object: kernels may not be loaded yet
+    const bool fuse = cv && !multi && d.fuse_write_back != 0 && !cold;
     st->warmed = true;
     const bool ring = multi && d.ring > 0;
     const bool sharded = d.shard_rows > 0 && d.world > 1;
@@ -451,6 +455,8 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
         const int len = tb(c + 1) - tb(c);
         // its buffer sets (and its id staging) were those of train c-2: every pass of that train has finished
         if (c >= 2) SGCN_CUDA(cudaStreamWaitEvent(samp, st->t_rest[(tb(c - 1) - 1) % R], 0));
+        // cold run: ... and so has every pass of train c-1 (issued by now, see the pass loop)
+        if (cold && c >= 1) SGCN_CUDA(cudaStreamWaitEvent(samp, st->t_rest[(tb(c) - 1) % R], 0));
         if (ids_on_host)
             SGCN_CUDA(cudaMemcpyAsync(st->ids_stage[c & 1], ids + (int64_t)tb(c) * B, sizeof(int32_t) * (size_t)len * B,
                                       cudaMemcpyHostToDevice, samp));
@@ -494,11 +500,15 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
         STEP_TRY(sgcn_sampler_start_batch_device(smp, 0, nullptr));
     }
     STEP_TRY(issue_train(0));
-    if (n_trains > 1) STEP_TRY(issue_train(1));
+    if (n_trains > 1 && !cold) STEP_TRY(issue_train(1));
     STEP_TRY(ahead(0));
 
     for (int k = 0; k < n; ++k) {
         const int r = k & 1, c = train_of(k);
+        if (cold && k >= 1 && k == tb(c)) {       // cold run: train c is sampled here, behind the passes of train c-1
+            STEP_TRY(issue_train(c));
+            STEP_TRY(ahead(k));
+        }
         const sgcn_step::Lv& v = st->tlv[(size_t)set_of(k)];
         const int32_t* n_out_dev = v.meta + 0;
         const int32_t* n_in_dev = v.meta + 1;
@@ -527,7 +537,7 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
         }
         SGCN_CUDA(cudaEventRecord(st->t_full[k % R], chain));
         // ---- pre: everything of pass k+1 that does not read the history ----
-        if (k + 1 < n && !st->gather_after_sampled) STEP_TRY(ahead(k + 1));
+        if (k + 1 < n && !st->gather_after_sampled && !(cold && k + 1 == tb(c + 1))) STEP_TRY(ahead(k + 1));
         // ---- side: the sampled aggregate + backward of pass k (history as of write-back k-1) ----
         // plain launches: a programmatic launch here would sit resident in griddepcontrol.wait for most of a
         // full-neighbour mean and keep the NEXT mean's thread blocks off those SMs (profiles/r02_timeline_*)
@@ -573,7 +583,7 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
         }
         SGCN_CUDA(cudaEventRecord(st->t_fwd[k % R], side));
         }
-        if (k + 1 < n && st->gather_after_sampled) STEP_TRY(ahead(k + 1));
+        if (k + 1 < n && st->gather_after_sampled && !(cold && k + 1 == tb(c + 1))) STEP_TRY(ahead(k + 1));
         // ---- write-back after every forward read of history (gcn/models.py:186-194) ----
         if (!fuse) {                     // on the chain (programmatic launch: it is the chain's next link)
             SGCN_CUDA(cudaStreamWaitEvent(chain, st->t_fwd[k % R], 0));
@@ -614,7 +624,7 @@ int sgcn_step_run_trains(sgcn_step* st, const int32_t* ids, int32_t ids_on_host,
             SGCN_CUDA(cudaEventRecord(st->t_d2h[k % R], copy));
         }
         // ---- samp: the train after next, once the last pass of this train has been issued ----
-        if (k + 1 == tb(c + 1) && c + 2 < n_trains) STEP_TRY(issue_train(c + 2));
+        if (k + 1 == tb(c + 1) && c + 2 < n_trains && !cold) STEP_TRY(issue_train(c + 2));
     }
     SGCN_CUDA(cudaEventRecord(st->ev_side_end, side));
     SGCN_CUDA(cudaEventRecord(st->ev_samp_end, samp));
