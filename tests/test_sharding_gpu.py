@@ -77,3 +77,15 @@ def test_two_ranks_at_the_benched_shapes(mode, tables):
     with open(os.path.join(ROOT, "gpurun_out", "mgpu_check_fullsize.log"), "a") as f:
         f.write("%s %s rc=%d: %s\n" % (mode, tables, proc.returncode, stdout.strip().splitlines()[-1:]))
     assert proc.returncode == 0 and "mgpu_check ok" in stdout, stdout[-3000:] + stderr[-3000:]
+
+
+def test_two_ranks_claims_off_the_chain():
+    """the opt-in split form of the ring exchange (SGCN_WB_SPLIT=1: sgcn_wb_claim_ring on the side stream,
+    sgcn_wb_copy_ring on the chain) against the same multi-process oracle"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29543", os.path.join(ROOT, "tests", "mgpu_check.py"),
+           "peer", "cv", "trains-graph", "replicated"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=dict(os.environ, SGCN_WB_SPLIT="1"))
+    assert out.returncode == 0 and "mgpu_check ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
